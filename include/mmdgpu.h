@@ -1,0 +1,377 @@
+/*
+ * mmdgpu.h — C-ABI of the B200-native MMD deformation library (libmmdgpu.so).
+ *
+ * This is the drop-in boundary for the per-frame deformation path that
+ * simple_mmd_renderer drives through libmmd (main.cpp:1786-1825):
+ *
+ *     ResetPosing -> SeekFrame -> PrePhysicsPosing -> [React] ->
+ *     PostPhysicsPosing -> Deform -> UpdateDeformedVertices
+ *
+ * libmmd is header-only C++ inlined into main.cpp, so there is no FFI in the
+ * reference; every entry point below cites the libmmd member (file:line under
+ * 3rd_party/libmmd/include/mmd/, abbreviated L/) or the main.cpp lines it
+ * replaces.  Signatures are plain C: pointers, sizes, integer status codes.
+ * Nothing here throws and nothing here falls back to the CPU: a call that
+ * needs the device and cannot reach it returns MMDGPU_ERR_CUDA.
+ *
+ * Conventions (identical to libmmd, L/util/math.inl:10-19):
+ *   - vectors are rows, y = x * M; 4x4 matrices are 16 floats row-major with
+ *     the translation in row 3 (elements 12..14);
+ *   - quaternions are stored (x, y, z, w) = libmmd's (i, j, k, e);
+ *   - indices are int32 with -1 = "none" (libmmd: size_t nil);
+ *   - all host arrays are little-endian, borrowed for the duration of the call.
+ *
+ * Threading: one context per host thread / CUDA stream.  Calls on one context
+ * are issued in stream order.  Different contexts are independent.
+ */
+#ifndef MMDGPU_H_INCLUDED
+#define MMDGPU_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define MMDGPU_API __declspec(dllexport)
+#else
+#define MMDGPU_API __attribute__((visibility("default")))
+#endif
+
+#define MMDGPU_VERSION_MAJOR 0
+#define MMDGPU_VERSION_MINOR 1
+
+/* ------------------------------------------------------------------ status */
+
+typedef int mmdgpu_status;
+enum {
+    MMDGPU_OK              = 0,
+    MMDGPU_ERR_INVALID_ARG = -1, /* NULL where data is required, sizes inconsistent            */
+    MMDGPU_ERR_BAD_INDEX   = -2, /* bone / vertex / morph index out of range, group-morph cycle */
+    MMDGPU_ERR_UNSUPPORTED = -3, /* valid input that this build cannot represent               */
+    MMDGPU_ERR_CUDA        = -4, /* CUDA runtime error (no device, launch failure, ...)        */
+    MMDGPU_ERR_OOM         = -5, /* host or device allocation failed                           */
+    MMDGPU_ERR_PARSE       = -6  /* PMX / VMD byte stream malformed                             */
+};
+
+/* ----------------------------------------------------------------- handles */
+
+typedef struct mmdgpu_context*   mmdgpu_context_t;   /* one per GPU / stream                        */
+typedef struct mmdgpu_model*     mmdgpu_model_t;     /* immutable after create; shared by instances  */
+typedef struct mmdgpu_animation* mmdgpu_animation_t; /* flattened VMD tracks bound to one model      */
+typedef struct mmdgpu_frames*    mmdgpu_frames_t;    /* device state + output for instances x frames */
+typedef struct mmdgpu_plan*      mmdgpu_plan_t;      /* host-only flattened model (no GPU needed)    */
+
+/* ------------------------------------------------------- PMX-shaped model */
+
+/* PMX skinning numbering, L/reader/pmx_reader_impl.inl:67-99 (+4 = PMX 2.1 QDEF). */
+enum {
+    MMDGPU_SKIN_BDEF1 = 0,
+    MMDGPU_SKIN_BDEF2 = 1,
+    MMDGPU_SKIN_BDEF4 = 2,
+    MMDGPU_SKIN_SDEF  = 3,
+    MMDGPU_SKIN_QDEF  = 4
+};
+
+/* PMX bone flag bits, L/reader/interprete/pmx_types.inl:46-59.  Only these four are consumed. */
+enum {
+    MMDGPU_BONE_HAS_IK           = 0x0020,
+    MMDGPU_BONE_APPEND_ROTATE    = 0x0100,
+    MMDGPU_BONE_APPEND_TRANSLATE = 0x0200,
+    MMDGPU_BONE_POST_PHYSICS     = 0x1000
+};
+
+/* PMX morph numbering, L/model/model.inl:485-495. */
+enum {
+    MMDGPU_MORPH_GROUP    = 0,
+    MMDGPU_MORPH_VERTEX   = 1,
+    MMDGPU_MORPH_BONE     = 2,
+    MMDGPU_MORPH_UV       = 3,
+    MMDGPU_MORPH_EXT_UV1  = 4,
+    MMDGPU_MORPH_EXT_UV2  = 5,
+    MMDGPU_MORPH_EXT_UV3  = 6,
+    MMDGPU_MORPH_EXT_UV4  = 7,
+    MMDGPU_MORPH_MATERIAL = 8
+};
+
+typedef struct mmdgpu_vertex_morph_entry { uint32_t vertex; float offset[3]; } mmdgpu_vertex_morph_entry;
+typedef struct mmdgpu_uv_morph_entry     { uint32_t vertex; float offset[4]; } mmdgpu_uv_morph_entry;
+typedef struct mmdgpu_bone_morph_entry   { uint32_t bone; float translation[3]; float rotation[4]; } mmdgpu_bone_morph_entry;
+typedef struct mmdgpu_group_morph_entry  { uint32_t morph; float rate; } mmdgpu_group_morph_entry;
+
+/*
+ * Flat image of mmd::Model (L/model/model.inl:719-734) restricted to what
+ * Poser consumes.  Arrays may be NULL only when their count is zero (or where
+ * marked optional).
+ */
+typedef struct mmdgpu_model_desc {
+    /* vertices — Model::VertexInfo, L/model/model.inl:719-726 */
+    uint32_t       n_vertices;
+    const float*   position;      /* 3n  */
+    const float*   normal;        /* 3n  */
+    const float*   uv;            /* 2n, optional (NULL = zeros) */
+    const uint8_t* skin_type;     /* n, MMDGPU_SKIN_*            */
+    const int32_t* bone_id;       /* 4n, unused lanes ignored    */
+    const float*   weight;        /* 4n; BDEF2/SDEF use weight[0] (weight of bone_id[0]) */
+    const float*   sdef_c;        /* 3n, optional */
+    const float*   sdef_r0;       /* 3n, optional */
+    const float*   sdef_r1;       /* 3n, optional */
+
+    /* bones — Model::Bone, L/model/model.inl:183-332 */
+    uint32_t        n_bones;
+    const float*    bone_position;        /* 3nb */
+    const int32_t*  bone_parent;          /* nb, -1 or >= nb: no parent (poser_impl.inl:39-46) */
+    const int32_t*  bone_transform_level; /* nb */
+    const uint16_t* bone_flags;           /* nb, MMDGPU_BONE_* */
+    const int32_t*  bone_append_parent;   /* nb, optional */
+    const float*    bone_append_ratio;    /* nb, optional */
+    /* IK, valid where HAS_IK — Bone::IKInfo */
+    const int32_t*  ik_target;            /* nb, optional */
+    const int32_t*  ik_iterations;        /* nb */
+    const float*    ik_angle_limit;       /* nb */
+    const uint32_t* ik_link_begin;        /* nb */
+    const uint32_t* ik_link_count;        /* nb */
+    uint32_t        n_ik_links;
+    const int32_t*  ik_link_bone;         /* n_ik_links, tip-most first as stored in PMX */
+    const uint8_t*  ik_link_has_limit;    /* n_ik_links */
+    const float*    ik_link_lo;           /* 3*n_ik_links */
+    const float*    ik_link_hi;           /* 3*n_ik_links */
+
+    /* morphs — Model::Morph, L/model/model.inl:334-517 */
+    uint32_t        n_morphs;
+    const uint8_t*  morph_type;           /* nm, MMDGPU_MORPH_* */
+    const uint32_t* morph_entry_begin;    /* nm, index into the pool of the morph's type */
+    const uint32_t* morph_entry_count;    /* nm */
+    uint32_t n_vertex_morph_entries; const mmdgpu_vertex_morph_entry* vertex_morph_entries;
+    uint32_t n_uv_morph_entries;     const mmdgpu_uv_morph_entry*     uv_morph_entries;
+    uint32_t n_bone_morph_entries;   const mmdgpu_bone_morph_entry*   bone_morph_entries;
+    uint32_t n_group_morph_entries;  const mmdgpu_group_morph_entry*  group_morph_entries;
+} mmdgpu_model_desc;
+
+/* ------------------------------------------------------ VMD-shaped motion */
+
+/*
+ * One bone keyframe: the VMD 111-byte record minus the name
+ * (L/reader/interprete/vmd_types.inl:22-31).  interp[c] = (x0, y0, x1, y1) of
+ * channel c in {X, Y, Z, R} = bytes [0],[4],[8],[12] of the channel's
+ * 16-byte block (L/reader/vmd_reader_impl.inl:32-61); signed as in the reader.
+ */
+typedef struct mmdgpu_bone_key {
+    uint32_t frame;
+    float    translation[3];
+    float    rotation[4];
+    int8_t   interp[4][4];
+} mmdgpu_bone_key;
+
+typedef struct mmdgpu_morph_key { uint32_t frame; float weight; } mmdgpu_morph_key;
+
+/*
+ * Flat image of mmd::Motion (L/motion/motion.inl:128-129) after the name join
+ * of MotionPlayer::MotionPlayer (L/motion/poser_impl.inl:522-537): one track
+ * per animated model bone / morph.  Keys of a track need not be sorted; equal
+ * frames keep the last one (std::map::operator[] semantics,
+ * L/motion/motion_impl.inl:221-227).  A bone or morph may appear in at most
+ * one track.
+ */
+typedef struct mmdgpu_anim_desc {
+    uint32_t               n_bone_tracks;
+    const int32_t*         bone_track_bone;       /* model bone index per track */
+    const uint32_t*        bone_track_key_begin;
+    const uint32_t*        bone_track_key_count;
+    uint32_t               n_bone_keys;
+    const mmdgpu_bone_key* bone_keys;
+    uint32_t                n_morph_tracks;
+    const int32_t*          morph_track_morph;
+    const uint32_t*         morph_track_key_begin;
+    const uint32_t*         morph_track_key_count;
+    uint32_t                n_morph_keys;
+    const mmdgpu_morph_key* morph_keys;
+} mmdgpu_anim_desc;
+
+/* ------------------------------------------------------------------ output */
+
+typedef enum mmdgpu_layout {
+    /* pose_image.coordinates / .normals (L/motion/poser.inl:17-20): two planes of n x float3 */
+    MMDGPU_LAYOUT_SOA_POS_NRM = 0,
+    /* main.cpp:50-54 Vertex{pos[3]*0.1f, normal[3], uv[2]} = 32 B, as main.cpp:838-859 packs it */
+    MMDGPU_LAYOUT_INTERLEAVED_SOKOL32 = 1
+} mmdgpu_layout;
+
+typedef enum mmdgpu_stream_id {
+    MMDGPU_STREAM_POSITION    = 0, /* SOA: n x float3                    */
+    MMDGPU_STREAM_NORMAL      = 1, /* SOA: n x float3                    */
+    MMDGPU_STREAM_INTERLEAVED = 2, /* INTERLEAVED: n x 32 B              */
+    MMDGPU_STREAM_SKIN_MATRIX = 3  /* device palette, nb x 12 floats (3 columns x float4) */
+} mmdgpu_stream_id;
+
+/* Behaviour switches.  Zero-initialised = libmmd-exact. */
+typedef struct mmdgpu_options {
+    /* 0: libmmd-exact (SDEF -> BDEF2 lerp, QDEF -> BDEF4 lerp, UV morphs ignored;
+     *    L/motion/poser_impl.inl:417-426, :355-358).
+     * 1: extensions (spherical SDEF, dual-quaternion QDEF, applied UV morphs); parity unpinned. */
+    uint32_t extensions;
+    uint32_t reserved[7];
+} mmdgpu_options;
+
+/* ---------------------------------------------------------------- contexts */
+
+MMDGPU_API int         mmdgpu_version(void);
+MMDGPU_API const char* mmdgpu_status_string(mmdgpu_status s);
+
+/* cuda_stream_or_null: a cudaStream_t the caller owns (e.g. torch's current stream), or NULL to
+ * let the context create its own non-blocking stream. */
+MMDGPU_API mmdgpu_status mmdgpu_context_create(int device, void* cuda_stream_or_null, mmdgpu_context_t* out);
+MMDGPU_API void          mmdgpu_context_destroy(mmdgpu_context_t ctx);
+MMDGPU_API const char*   mmdgpu_last_error(mmdgpu_context_t ctx);
+MMDGPU_API mmdgpu_status mmdgpu_context_synchronize(mmdgpu_context_t ctx);
+MMDGPU_API void*         mmdgpu_context_stream(mmdgpu_context_t ctx);
+/* Number of kernels this context has launched since creation (bench "gpu_launches"). */
+MMDGPU_API uint64_t      mmdgpu_context_launch_count(mmdgpu_context_t ctx);
+
+/* ------------------------------------------------------------------ models */
+
+/* Replaces: PmxReader::ReadModel's result + Model::Normalize (L/model/model_impl.inl:406-452)
+ * + Poser::Poser's static precomputation (L/motion/poser_impl.inl:16-128).  Unlike libmmd,
+ * which never bounds-checks, out-of-range bone / vertex / morph ids are rejected with BAD_INDEX. */
+MMDGPU_API mmdgpu_status mmdgpu_model_create_from_arrays(mmdgpu_context_t ctx, const mmdgpu_model_desc* desc,
+                                                         const mmdgpu_options* opt_or_null, mmdgpu_model_t* out);
+/* PMX 2.0 / 2.1 byte stream, layout of L/reader/pmx_reader_impl.inl:16-449. */
+MMDGPU_API mmdgpu_status mmdgpu_model_create_from_pmx(mmdgpu_context_t ctx, const void* bytes, size_t n,
+                                                      const mmdgpu_options* opt_or_null, mmdgpu_model_t* out);
+MMDGPU_API void          mmdgpu_model_destroy(mmdgpu_model_t model);
+MMDGPU_API uint32_t      mmdgpu_model_vertex_count(mmdgpu_model_t model);
+MMDGPU_API uint32_t      mmdgpu_model_bone_count(mmdgpu_model_t model);
+MMDGPU_API uint32_t      mmdgpu_model_morph_count(mmdgpu_model_t model);
+/* The host plan the model was built from (owned by the model). */
+MMDGPU_API mmdgpu_plan_t mmdgpu_model_plan(mmdgpu_model_t model);
+/* Bone / morph lookup by raw name bytes as stored in the PMX (only for models created from PMX). */
+MMDGPU_API int32_t       mmdgpu_model_find_bone(mmdgpu_model_t model, const void* name_bytes, size_t n);
+MMDGPU_API int32_t       mmdgpu_model_find_morph(mmdgpu_model_t model, const void* name_bytes, size_t n);
+
+/* -------------------------------------------------------------- animations */
+
+/* Replaces: mmd::Motion storage + MotionPlayer's name join (L/motion/poser_impl.inl:522-537). */
+MMDGPU_API mmdgpu_status mmdgpu_animation_create_from_arrays(mmdgpu_context_t ctx, mmdgpu_model_t model,
+                                                             const mmdgpu_anim_desc* desc, mmdgpu_animation_t* out);
+/* VMD byte stream (50-B header, 111-B bone records, 23-B morph records; L/reader/vmd_reader_impl.inl:9-79).
+ * Track names are joined to the model's bone / morph names byte-wise (Shift-JIS, NUL-trimmed). */
+MMDGPU_API mmdgpu_status mmdgpu_animation_create_from_vmd(mmdgpu_context_t ctx, mmdgpu_model_t model,
+                                                          const void* bytes, size_t n, mmdgpu_animation_t* out);
+MMDGPU_API void          mmdgpu_animation_destroy(mmdgpu_animation_t anim);
+/* Motion::GetLength (L/motion/motion_impl.inl:242-245): largest key frame. */
+MMDGPU_API uint32_t      mmdgpu_animation_length(mmdgpu_animation_t anim);
+
+/* ------------------------------------------------------------------ frames */
+
+/* A frames object holds n_instances x n_frames independent "slots"; slot = instance * n_frames + k.
+ * Each slot is one mmd::Poser worth of state: bone poses, morph rates, bone matrices and one
+ * deformed vertex buffer (Poser::pose_image, L/motion/poser.inl:17-20). */
+MMDGPU_API mmdgpu_status mmdgpu_frames_create(mmdgpu_context_t ctx, mmdgpu_model_t model, uint32_t n_instances,
+                                              uint32_t n_frames, mmdgpu_layout layout, mmdgpu_frames_t* out);
+MMDGPU_API void          mmdgpu_frames_destroy(mmdgpu_frames_t frames);
+MMDGPU_API uint32_t      mmdgpu_frames_slot_count(mmdgpu_frames_t frames);
+
+/* Poser::ResetPosing (L/motion/poser_impl.inl:130-140): zero morph rates, identity bone poses.
+ * The redundant Pre+PostPhysicsPosing evaluation libmmd runs inside ResetPosing is not executed:
+ * its results are overwritten by the next PrePhysicsPosing. */
+MMDGPU_API mmdgpu_status mmdgpu_reset_posing(mmdgpu_frames_t frames);
+/* MotionPlayer::SeekFrame(size_t) (L/motion/poser_impl.inl:539-546) for every slot: per_instance has
+ * n_instances handles (instance i's clip), frame_per_slot has n_slots frame ids (host memory). */
+MMDGPU_API mmdgpu_status mmdgpu_seek_frame(mmdgpu_frames_t frames, const mmdgpu_animation_t* per_instance,
+                                           const uint32_t* frame_per_slot);
+/* Same, frame ids generated on the device: slot (i, k) seeks first_frame[i] + k * frame_stride.
+ * first_frame_per_instance is host memory (n_instances). */
+MMDGPU_API mmdgpu_status mmdgpu_seek_frame_range(mmdgpu_frames_t frames, const mmdgpu_animation_t* per_instance,
+                                                 const uint32_t* first_frame_per_instance, uint32_t frame_stride);
+/* Poser::SetBonePose / SetMorphPose by index (L/motion/poser_impl.inl:466-480). */
+MMDGPU_API mmdgpu_status mmdgpu_set_bone_pose(mmdgpu_frames_t frames, uint32_t slot, uint32_t bone,
+                                              const float translation[3], const float rotation[4]);
+MMDGPU_API mmdgpu_status mmdgpu_set_morph_pose(mmdgpu_frames_t frames, uint32_t slot, uint32_t morph, float weight);
+/* Poser::PrePhysicsPosing / PostPhysicsPosing / Deform (L/motion/poser_impl.inl:362-394, 396-461). */
+MMDGPU_API mmdgpu_status mmdgpu_pre_physics_posing(mmdgpu_frames_t frames);
+MMDGPU_API mmdgpu_status mmdgpu_post_physics_posing(mmdgpu_frames_t frames);
+MMDGPU_API mmdgpu_status mmdgpu_deform(mmdgpu_frames_t frames);
+/* Physics hand-back (PoserMotionState::Synchronize / Fix, mmd-bullet_impl.inl:34-56): overwrite one
+ * bone's skinning matrix (and, if local_or_null != NULL, its local matrix) between pre and post. */
+MMDGPU_API mmdgpu_status mmdgpu_set_skinning_matrix_override(mmdgpu_frames_t frames, uint32_t slot, uint32_t bone,
+                                                             const float skinning[16], const float* local_or_null);
+/* Fused ResetPosing + SeekFrame + PrePhysicsPosing + PostPhysicsPosing + Deform for every slot
+ * (main.cpp:1788-1821 with physics off). */
+MMDGPU_API mmdgpu_status mmdgpu_update(mmdgpu_frames_t frames, const mmdgpu_animation_t* per_instance,
+                                       const uint32_t* frame_per_slot);
+MMDGPU_API mmdgpu_status mmdgpu_update_range(mmdgpu_frames_t frames, const mmdgpu_animation_t* per_instance,
+                                             const uint32_t* first_frame_per_instance, uint32_t frame_stride);
+
+/* Device pointer of slot 0 of one output stream and the byte stride between slots. */
+MMDGPU_API mmdgpu_status mmdgpu_frames_device_ptr(mmdgpu_frames_t frames, mmdgpu_stream_id id, void** dptr,
+                                                  size_t* slot_stride_bytes);
+/* Copy one slot's output stream to host memory (synchronous); feeds sg_update_buffer (main.cpp:862)
+ * or Poser::pose_image unchanged.  bytes must equal the stream's size for one slot. */
+MMDGPU_API mmdgpu_status mmdgpu_frames_download(mmdgpu_frames_t frames, uint32_t slot, mmdgpu_stream_id id,
+                                                void* host_dst, size_t bytes);
+/* Asynchronous variant on the context's download stream for a slot range into pinned host memory;
+ * pair with mmdgpu_context_synchronize.  Overlaps with the next update on the compute stream. */
+MMDGPU_API mmdgpu_status mmdgpu_frames_download_async(mmdgpu_frames_t frames, uint32_t first_slot, uint32_t n_slots,
+                                                      mmdgpu_stream_id id, void* pinned_host_dst, size_t bytes);
+/* BoneImage::skinning_matrix_ / local_matrix_ of one slot as nb x 16 floats (parity on bone globals). */
+MMDGPU_API mmdgpu_status mmdgpu_bone_matrices_download(mmdgpu_frames_t frames, uint32_t slot, float* host_dst);
+MMDGPU_API mmdgpu_status mmdgpu_bone_local_matrices_download(mmdgpu_frames_t frames, uint32_t slot, float* host_dst);
+/* Sampled BoneImage::rotation_/translation_ (nb x 7 floats: T xyz, R xyzw) and morph_rates_ (nm). */
+MMDGPU_API mmdgpu_status mmdgpu_bone_poses_download(mmdgpu_frames_t frames, uint32_t slot, float* host_dst);
+MMDGPU_API mmdgpu_status mmdgpu_morph_rates_download(mmdgpu_frames_t frames, uint32_t slot, float* host_dst);
+
+/* Pinned host memory helpers for the download path. */
+MMDGPU_API mmdgpu_status mmdgpu_host_alloc(size_t bytes, void** out);
+MMDGPU_API void          mmdgpu_host_free(void* p);
+
+/* ------------------------------------------------- host plan (no GPU used) */
+
+/*
+ * The flattened, device-ready image of a model, built on the host only.  It is what
+ * mmdgpu_model_create_from_arrays uploads; it is exposed so that the index tier (Normalize rewrite,
+ * evaluation order, wave schedule, IK classification, morph application slots, per-vertex CSR) can be
+ * checked bit-exactly on a machine without a GPU.
+ */
+MMDGPU_API mmdgpu_status mmdgpu_plan_create(const mmdgpu_model_desc* desc, const mmdgpu_options* opt_or_null,
+                                            mmdgpu_plan_t* out, char* err_buf, size_t err_buf_len);
+MMDGPU_API void          mmdgpu_plan_destroy(mmdgpu_plan_t plan);
+
+typedef enum mmdgpu_plan_array {
+    MMDGPU_PLAN_SKIN_TYPE = 0,      /* u8  [nv]   type after Model::Normalize + Lerp shortcuts        */
+    MMDGPU_PLAN_BONE_ID = 1,        /* u16 [4nv]  ids after the rewrite                               */
+    MMDGPU_PLAN_WEIGHT = 2,         /* f32 [4nv]                                                      */
+    MMDGPU_PLAN_ORDER_PRE = 3,      /* i32 [..]   pre_physics_bones_ after std::sort                  */
+    MMDGPU_PLAN_ORDER_POST = 4,     /* i32 [..]   post_physics_bones_ after std::sort                 */
+    MMDGPU_PLAN_OP_KIND = 5,        /* u8  [n_ops] 0 EVAL, 1 IK, 2 SKIN, in program order             */
+    MMDGPU_PLAN_OP_BONE = 6,        /* i32 [n_ops]                                                    */
+    MMDGPU_PLAN_OP_WAVE = 7,        /* i32 [n_ops] wave each op was scheduled into                    */
+    MMDGPU_PLAN_WAVE_BEGIN = 8,     /* i32 [n_waves+1] offsets into the wave-ordered op list           */
+    MMDGPU_PLAN_WAVE_OPS = 9,       /* i32 [n_ops] op indices (program order ids) grouped by wave      */
+    MMDGPU_PLAN_IK_FIX_TYPE = 10,   /* u8  [n_ik_links] 0 NONE 1 X 2 Y 3 Z 4 ALL                       */
+    MMDGPU_PLAN_IK_EULER_ORDER = 11,/* u8  [n_ik_links] 0 YZX 1 ZXY 2 XYZ                              */
+    MMDGPU_PLAN_APP_SLOT_MORPH = 12,/* i32 [n_app_slots] morph index of every DFS application slot     */
+    MMDGPU_PLAN_APP_SLOT_PARENT = 13,/* i32 [n_app_slots] parent slot (group) or -1                    */
+    MMDGPU_PLAN_APP_SLOT_MULT = 14, /* f32 [n_app_slots] group rate multiplier                         */
+    MMDGPU_PLAN_CSR_ROW_PTR = 15,   /* u32 [nv+1]                                                     */
+    MMDGPU_PLAN_CSR_SLOT = 16,      /* u32 [n_csr] application slot of every CSR entry                 */
+    MMDGPU_PLAN_CSR_OFFSET = 17,    /* f32 [3 n_csr]                                                  */
+    MMDGPU_PLAN_BEZIER_UNUSED = 18,
+    MMDGPU_PLAN_WAVE_PHASE_SPLIT = 19 /* i32 [1] index of the first wave of the post-physics segment   */
+} mmdgpu_plan_array;
+
+/* Returns a pointer into plan-owned memory and the element count; the pointer is valid until the plan
+ * (or the model that owns it) is destroyed. */
+MMDGPU_API mmdgpu_status mmdgpu_plan_get(mmdgpu_plan_t plan, mmdgpu_plan_array which, const void** data,
+                                         size_t* count);
+
+/* Presampled Bezier table of Bezier::presample (L/util/math_impl.inl:1398-1428) for one VMD control
+ * quadruple (x0, y0, x1, y1).  Returns 1 and leaves table untouched if the curve is linear. */
+MMDGPU_API int mmdgpu_bezier_table(const int8_t ctrl[4], float table[32]);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+
+#endif /* MMDGPU_H_INCLUDED */

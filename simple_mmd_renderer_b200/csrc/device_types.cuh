@@ -1,0 +1,94 @@
+// device_types.cuh — plain structs passed by value to the sm_100a kernels.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "host_plan.hpp"
+
+namespace mmdgpu {
+
+constexpr uint32_t kVertsPerThread = 4;
+constexpr uint32_t kSkinThreads = 256;
+constexpr uint32_t kTileVerts = kVertsPerThread * kSkinThreads;  // vertices one CTA handles per iteration
+
+// Static model image in HBM.  Vertex streams are structure-of-arrays so that a thread owning 4 consecutive
+// vertices issues only 16-byte loads (48 B read + 4 B CSR row pointer per vertex).
+struct DevModel {
+    uint32_t nv, nv_pad, nb, nm;
+    uint32_t n_nodes, n_nodes_pad;  // morph application slots; padded to a multiple of 4 (16-byte bulk copy)
+    // vertex streams (nv_pad entries each)
+    const float *px, *py, *pz, *nx, *ny, *nz;
+    const uint2* ids;        // 4 x u16 bone ids; bits 15:13 of id0 carry the device skinning type
+    const float4* weights;
+    const float2* uv;
+    const uint32_t* csr_row; // nv_pad + 1
+    const float4* csr_ent;   // (offset.xyz, bit-cast application slot)
+    // extension streams (NULL in libmmd-exact mode)
+    const float4* sdef_c;    // per vertex: C.xyz, unused
+    const float4* sdef_r0;
+    const float4* sdef_r1;
+    const uint32_t* uv_row;
+    const float4* uv_ent;    // (offset.xy, unused, bit-cast application slot)
+    // bones
+    const BoneStatic* bones;
+    const IkDesc* iks;
+    const IkLink* links;
+    const int32_t* reset_bones;
+    uint32_t n_reset, n_link_slots, n_morph_slots;
+    // program: ops grouped by wave; op word = kind << 28 | arg
+    const uint32_t* wave_begin;
+    const uint32_t* wave_ops;
+    uint32_t n_waves, phase_split;
+    // morph application slots
+    const int32_t* node_morph;
+    const int32_t* node_parent;
+    const float* node_mult;
+    const int32_t* nodes_by_depth;
+    const int32_t* depth_begin;
+    uint32_t n_depths;
+    // bone morphs grouped by bone
+    const int32_t* morph_bones;
+    const int32_t* bone_morph_row;
+    const BoneMorphEntry* bone_morph_entries;
+};
+
+// Flattened VMD clip bound to one model.
+struct DevAnim {
+    const uint32_t* bone_key_begin;
+    const uint32_t* bone_key_count;
+    const uint8_t* bone_tracked;
+    const uint32_t* key_frame;
+    const float4* key_T;
+    const float4* key_R;
+    const uint4* key_curve;   // Bezier table index per channel X, Y, Z, R; 0xFFFFFFFF = linear
+    const float* tables;      // 32 floats per table
+    const uint32_t* morph_key_begin;
+    const uint32_t* morph_key_count;
+    const uint8_t* morph_tracked;
+    const uint32_t* mkey_frame;
+    const float* mkey_weight;
+};
+
+// Per-slot dynamic state and outputs.  Slot = instance * n_frames + k.
+struct DevFrames {
+    uint32_t n_slots, n_instances, n_frames;
+    float4* poseR;      // [slot][nb]   BoneImage::rotation_
+    float4* poseT;      // [slot][nb]   BoneImage::translation_ (w unused)
+    float* rate;        // [slot][nm]   Poser::morph_rates_
+    float* node_rate;   // [slot][n_nodes_pad]  rate of every application slot, 0 = skipped
+    float4* totR;       // [slot][nb]
+    float4* totT;       // [slot][nb]
+    float* local;       // [slot][nb][12]  rows 0..3 x cols 0..2 of BoneImage::local_matrix_
+    float4* ikR;        // [slot][n_link_slots]
+    float4* preIK;      // [slot][n_link_slots]
+    float4* morphR;     // [slot][n_morph_slots]
+    float4* morphT;     // [slot][n_morph_slots]
+    float4* palette;    // [slot][nb][3]   column c of skinning_matrix_: (M0c, M1c, M2c, M3c)
+    float* out_pos;     // SOA: [slot][nv_pad][3]
+    float* out_nrm;     // SOA: [slot][nv_pad][3]
+    float4* out_inter;  // INTERLEAVED: [slot][nv_pad][2]
+    uint32_t* frame_id; // [slot]
+};
+
+}  // namespace mmdgpu

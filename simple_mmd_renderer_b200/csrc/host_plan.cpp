@@ -1,0 +1,543 @@
+// host_plan.cpp — see host_plan.hpp.  Host-only; no CUDA.
+#include "host_plan.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <unordered_map>
+
+namespace mmdgpu {
+
+namespace {
+
+constexpr double kEpsD = 1e-7;  // mmd_math_const_eps (L/util/math.inl:24), a double
+constexpr double kPiD = 3.141592653589793238462643383279502884;
+constexpr uint32_t kMaxNodes = 1u << 20;
+constexpr uint32_t kMaxBones = 8191;  // 13-bit ids in the packed vertex stream
+
+mmdgpu_status fail(std::string& err, mmdgpu_status s, const std::string& msg) {
+    err = msg;
+    return s;
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------------------------------------
+// Bezier::SetC / presample / interpolate, L/util/math_impl.inl:1393-1428, control points scaled as
+// VmdReader does (L/reader/vmd_reader_impl.inl:29-37).  fp32 throughout; built with -ffp-contract=off.
+bool bezier_table(const int8_t c[4], float table[32]) {
+    const float r = 1.0f / 127.0f;
+    const float c0x = (float(c[0]) * r) * 3.0f, c0y = (float(c[1]) * r) * 3.0f;
+    const float c1x = (float(c[2]) * r) * 3.0f, c1y = (float(c[3]) * r) * 3.0f;
+    if (c0x == c0y && c1x == c1y) return true;
+    for (int i = 0; i < 32; ++i) {
+        const float x = float(i) / 31.0f;
+        float lo = 0.0f, hi = 1.0f, mid = 0.0f, rm, m;
+        for (int it = 0; it < 32; ++it) {
+            mid = (lo + hi) * 0.5f;
+            rm = 1.0f - mid;
+            m = mid * (rm * (rm * c0x + mid * c1x) + mid * mid);
+            if (std::fabs(m - x) < float(kEpsD)) break;
+            if (m > x) hi = mid; else lo = mid;
+        }
+        rm = 1.0f - mid;
+        table[i] = mid * (rm * (rm * c0y + mid * c1y) + mid * mid);
+    }
+    return false;
+}
+
+// --------------------------------------------------------------------------------------------------
+mmdgpu_status build_plan(const mmdgpu_model_desc& d, const mmdgpu_options* opt, Plan& p, std::string& err) {
+    const uint32_t nv = d.n_vertices, nb = d.n_bones, nm = d.n_morphs;
+    p = Plan();
+    p.nv = nv; p.nb = nb; p.nm = nm;
+    p.extensions = opt && opt->extensions != 0;
+
+    if (nb == 0) return fail(err, MMDGPU_ERR_INVALID_ARG, "model has no bones");
+    if (nb > kMaxBones) return fail(err, MMDGPU_ERR_UNSUPPORTED, "more than 8191 bones (13-bit packed bone ids)");
+    if (nv && (!d.position || !d.normal || !d.skin_type || !d.bone_id || !d.weight))
+        return fail(err, MMDGPU_ERR_INVALID_ARG, "vertex arrays missing");
+    if (!d.bone_position || !d.bone_parent || !d.bone_transform_level || !d.bone_flags)
+        return fail(err, MMDGPU_ERR_INVALID_ARG, "bone arrays missing");
+    if (nm && (!d.morph_type || !d.morph_entry_begin || !d.morph_entry_count))
+        return fail(err, MMDGPU_ERR_INVALID_ARG, "morph arrays missing");
+
+    // ---------------------------------------------------------------- bones (Poser::Poser, poser_impl.inl:30-105)
+    p.bones.resize(nb);
+    std::vector<int32_t> ik_of_bone(nb, -1);
+    for (uint32_t b = 0; b < nb; ++b) {
+        BoneStatic& s = p.bones[b];
+        std::memset(&s, 0, sizeof s);
+        const uint16_t fl = d.bone_flags[b];
+        const int32_t par = d.bone_parent[b];
+        for (int k = 0; k < 3; ++k) s.position[k] = d.bone_position[3 * b + k];
+        s.link_slot = s.morph_slot = -1;
+        s.append_parent = -1;
+        if (par >= 0 && uint32_t(par) < nb) {
+            s.parent = par;
+            s.flags |= kHasParent;
+            for (int k = 0; k < 3; ++k) s.local_offset[k] = d.bone_position[3 * b + k] - d.bone_position[3 * par + k];
+        } else {
+            s.parent = -1;
+            for (int k = 0; k < 3; ++k) s.local_offset[k] = d.bone_position[3 * b + k];
+        }
+        if (fl & (MMDGPU_BONE_APPEND_ROTATE | MMDGPU_BONE_APPEND_TRANSLATE)) {
+            const int32_t ap = d.bone_append_parent ? d.bone_append_parent[b] : -1;
+            if (ap >= 0 && uint32_t(ap) < nb) {  // dropped otherwise, poser_impl.inl:51-57
+                s.append_parent = ap;
+                s.append_ratio = d.bone_append_ratio ? d.bone_append_ratio[b] : 0.0f;
+                if (fl & MMDGPU_BONE_APPEND_ROTATE) s.flags |= kAppendRot;
+                if (fl & MMDGPU_BONE_APPEND_TRANSLATE) s.flags |= kAppendTrans;
+            }
+        }
+        if (fl & MMDGPU_BONE_POST_PHYSICS) s.flags |= kPostPhysics;
+        if (fl & MMDGPU_BONE_HAS_IK) s.flags |= kHasIk;
+    }
+    // IK descriptors.  Link records keep the descriptor's order so PLAN_IK_* line up with ik_link_*.
+    p.links.resize(d.n_ik_links);
+    std::vector<uint8_t> link_seen(d.n_ik_links, 0);
+    for (uint32_t b = 0; b < nb; ++b) {
+        if (!(p.bones[b].flags & kHasIk)) continue;
+        if (!d.ik_target || !d.ik_iterations || !d.ik_angle_limit || !d.ik_link_begin || !d.ik_link_count)
+            return fail(err, MMDGPU_ERR_INVALID_ARG, "IK arrays missing");
+        IkDesc k{};
+        k.bone = int32_t(b);
+        k.target = d.ik_target[b];
+        if (k.target < 0 || uint32_t(k.target) >= nb)
+            return fail(err, MMDGPU_ERR_BAD_INDEX, "IK target out of range at bone " + std::to_string(b));
+        const uint32_t it = uint32_t(d.ik_iterations[b]);
+        k.iterations = int32_t(std::min<uint32_t>(it, 256u));
+        k.angle_limit = d.ik_angle_limit[b];
+        k.link_begin = int32_t(d.ik_link_begin[b]);
+        k.link_count = int32_t(d.ik_link_count[b]);
+        if (uint64_t(d.ik_link_begin[b]) + d.ik_link_count[b] > d.n_ik_links)
+            return fail(err, MMDGPU_ERR_BAD_INDEX, "IK link range out of range at bone " + std::to_string(b));
+        if (k.link_count && (!d.ik_link_bone || !d.ik_link_has_limit || !d.ik_link_lo || !d.ik_link_hi))
+            return fail(err, MMDGPU_ERR_INVALID_ARG, "IK link arrays missing");
+        for (int32_t j = 0; j < k.link_count; ++j) {
+            const uint32_t l = uint32_t(k.link_begin + j);
+            if (link_seen[l]) return fail(err, MMDGPU_ERR_INVALID_ARG, "IK link record shared by two IK bones");
+            link_seen[l] = 1;
+            IkLink& L = p.links[l];
+            std::memset(&L, 0, sizeof L);
+            L.bone = d.ik_link_bone[l];
+            if (L.bone < 0 || uint32_t(L.bone) >= nb)
+                return fail(err, MMDGPU_ERR_BAD_INDEX, "IK link bone out of range at bone " + std::to_string(b));
+            L.limited = d.ik_link_has_limit[l] != 0;
+            L.order = 0;  // ORDER_YZX default (poser_impl.inl:64)
+            L.fix = 0;    // FIX_NONE
+            if (L.limited) {
+                for (int c = 0; c < 3; ++c) {
+                    const float lo = d.ik_link_lo[3 * l + c], hi = d.ik_link_hi[3 * l + c];
+                    L.lo[c] = std::min(lo, hi);
+                    L.hi[c] = std::max(lo, hi);
+                }
+                // poser_impl.inl:78-82 — float limits compared as double against -(pi)*0.5f
+                if (double(L.lo[0]) > -kPiD * 0.5f && double(L.hi[0]) < kPiD * 0.5f) L.order = 1;       // ZXY
+                else if (double(L.lo[1]) > -kPiD * 0.5f && double(L.hi[1]) < kPiD * 0.5f) L.order = 2;  // XYZ
+                // poser_impl.inl:83-91 — float abs (main.cpp's TU), double compare
+                const bool zx = double(std::fabs(L.lo[0])) < kEpsD && double(std::fabs(L.hi[0])) < kEpsD;
+                const bool zy = double(std::fabs(L.lo[1])) < kEpsD && double(std::fabs(L.hi[1])) < kEpsD;
+                const bool zz = double(std::fabs(L.lo[2])) < kEpsD && double(std::fabs(L.hi[2])) < kEpsD;
+                if (zx && zy && zz) L.fix = 4;
+                else if (zy && zz) L.fix = 1;
+                else if (zx && zz) L.fix = 2;
+                else if (zx && zy) L.fix = 3;
+            }
+            p.bones[L.bone].flags |= kIsLink;
+        }
+        ik_of_bone[b] = int32_t(p.iks.size());
+        p.iks.push_back(k);
+    }
+    for (const IkDesc& k : p.iks) {
+        // libmmd would recurse into a nested solve here (UpdateBoneTransform on a bone that itself has IK).
+        if (p.bones[k.target].flags & kHasIk)
+            return fail(err, MMDGPU_ERR_UNSUPPORTED, "IK target is itself an IK bone (nested solve)");
+        for (int32_t j = 0; j < k.link_count; ++j)
+            if (p.bones[p.links[k.link_begin + j].bone].flags & kHasIk)
+                return fail(err, MMDGPU_ERR_UNSUPPORTED, "IK link is itself an IK bone (nested solve)");
+    }
+    for (uint32_t b = 0; b < nb; ++b)
+        if (p.bones[b].flags & kIsLink) {
+            p.bones[b].link_slot = int32_t(p.link_bones.size());
+            p.link_bones.push_back(int32_t(b));
+        }
+
+    // evaluation order: two lists, each std::sort'ed by (transform level, index) (poser_impl.inl:100-109, 500-510)
+    for (uint32_t b = 0; b < nb; ++b) (p.bones[b].flags & kPostPhysics ? p.order_post : p.order_pre).push_back(int32_t(b));
+    auto by_level = [&](int32_t a, int32_t b) {
+        const size_t la = size_t(d.bone_transform_level[a]), lb = size_t(d.bone_transform_level[b]);
+        if (la < lb) return true;
+        if (la > lb) return false;
+        return a < b;
+    };
+    std::sort(p.order_pre.begin(), p.order_pre.end(), by_level);
+    std::sort(p.order_post.begin(), p.order_post.end(), by_level);
+
+    // ---------------------------------------------------------------- program + wave schedule
+    // Symbolic execution of PrePhysicsPosing / PostPhysicsPosing (poser_impl.inl:362-394): every op gets
+    // the read / write sets of the state it touches; an op's wave is one past the last conflicting access.
+    enum { V_TOT = 0, V_LOCAL = 1, V_IK = 2, V_PRE = 3, V_SKIN = 4, V_KINDS = 5 };
+    auto var = [&](int kind, int32_t b) { return size_t(kind) * nb + size_t(b); };
+    std::vector<int32_t> lastW(size_t(V_KINDS) * nb, -1), lastR(size_t(V_KINDS) * nb, -1);
+    std::vector<uint8_t> need_reset(nb, 0);
+    auto eval_sets = [&](int32_t b, std::vector<size_t>& R, std::vector<size_t>& W) {
+        const BoneStatic& s = p.bones[b];
+        if (s.flags & (kAppendRot | kAppendTrans)) R.push_back(var(V_TOT, s.append_parent));
+        if (s.flags & kIsLink) { R.push_back(var(V_IK, b)); W.push_back(var(V_PRE, b)); }
+        if (s.flags & kHasParent) R.push_back(var(V_LOCAL, s.parent));
+        W.push_back(var(V_TOT, b));
+        W.push_back(var(V_LOCAL, b));
+    };
+    int32_t phase_floor = 0, max_wave = -1;
+    auto emit = [&](uint8_t kind, int32_t arg, std::vector<size_t>& R, std::vector<size_t>& W) {
+        int32_t w = phase_floor;
+        // reads that a write of the same op precedes do not count as "read before written"
+        for (size_t v : R) {
+            w = std::max(w, lastW[v] + 1);
+            if (lastW[v] < 0 && (v / nb == V_TOT || v / nb == V_LOCAL)) need_reset[v % nb] = 1;
+        }
+        for (size_t v : W) w = std::max(w, std::max(lastW[v], lastR[v]) + 1);
+        for (size_t v : R) lastR[v] = std::max(lastR[v], w);
+        for (size_t v : W) lastW[v] = w;
+        p.ops.push_back(Op{kind, arg});
+        p.op_wave.push_back(w);
+        max_wave = std::max(max_wave, w);
+    };
+    auto run_list = [&](const std::vector<int32_t>& list) {
+        std::vector<size_t> R, W;
+        for (int32_t b : list) {
+            R.clear(); W.clear();
+            eval_sets(b, R, W);
+            emit(kOpEval, b, R, W);
+            if (p.bones[b].flags & kHasIk) {
+                const IkDesc& k = p.iks[ik_of_bone[b]];
+                R.clear(); W.clear();
+                R.push_back(var(V_LOCAL, b));
+                // Internal order of the solve (poser_impl.inl:199-206): reset ikR, re-evaluate links root-most
+                // first, then the target.  State an inner step reads after an earlier inner step wrote it is
+                // not an external read; the sets below are the external view.
+                std::vector<size_t> wrote;
+                auto add_eval = [&](int32_t x) {
+                    std::vector<size_t> r2, w2;
+                    eval_sets(x, r2, w2);
+                    for (size_t v : r2)
+                        if (std::find(wrote.begin(), wrote.end(), v) == wrote.end()) R.push_back(v);
+                    for (size_t v : w2) { W.push_back(v); wrote.push_back(v); }
+                };
+                for (int32_t j = 0; j < k.link_count; ++j) {
+                    const size_t v = var(V_IK, p.links[k.link_begin + j].bone);
+                    W.push_back(v); wrote.push_back(v);
+                }
+                for (int32_t j = k.link_count - 1; j >= 0; --j) add_eval(p.links[k.link_begin + j].bone);
+                add_eval(k.target);
+                for (int32_t j = 0; j < k.link_count; ++j) {
+                    const BoneStatic& ls = p.bones[p.links[k.link_begin + j].bone];
+                    if (ls.flags & kHasParent) {
+                        const size_t v = var(V_LOCAL, ls.parent);
+                        if (std::find(wrote.begin(), wrote.end(), v) == wrote.end()) R.push_back(v);
+                    }
+                }
+                emit(kOpIk, ik_of_bone[b], R, W);
+            }
+        }
+        for (int32_t b : list) {  // UpdateBoneSkinningMatrix (poser_impl.inl:320-326)
+            R.clear(); W.clear();
+            R.push_back(var(V_LOCAL, b));
+            W.push_back(var(V_SKIN, b));
+            emit(kOpSkin, b, R, W);
+        }
+    };
+    run_list(p.order_pre);
+    p.phase_split = max_wave + 1;
+    phase_floor = p.phase_split;
+    run_list(p.order_post);
+    const int32_t n_waves = std::max(max_wave + 1, p.phase_split);
+    p.wave_begin.assign(size_t(n_waves) + 1, 0);
+    for (int32_t w : p.op_wave) p.wave_begin[size_t(w) + 1]++;
+    for (int32_t w = 0; w < n_waves; ++w) p.wave_begin[w + 1] += p.wave_begin[w];
+    p.wave_ops.resize(p.ops.size());
+    {
+        std::vector<int32_t> cur(p.wave_begin.begin(), p.wave_begin.end() - 1);
+        for (size_t i = 0; i < p.ops.size(); ++i) p.wave_ops[size_t(cur[p.op_wave[i]]++)] = int32_t(i);
+    }
+    for (uint32_t b = 0; b < nb; ++b)
+        if (need_reset[b]) p.reset_bones.push_back(int32_t(b));
+
+    // ---------------------------------------------------------------- morph application slots
+    // DFS expansion of UpdateMorphTransform's recursion (poser_impl.inl:328-360): node order == the order in
+    // which libmmd applies morph data.
+    for (uint32_t m = 0; m < nm; ++m) {
+        const uint8_t t = d.morph_type[m];
+        const uint64_t end = uint64_t(d.morph_entry_begin[m]) + d.morph_entry_count[m];
+        uint32_t pool = 0xFFFFFFFFu;
+        if (t == MMDGPU_MORPH_GROUP) pool = d.n_group_morph_entries;
+        else if (t == MMDGPU_MORPH_VERTEX) pool = d.n_vertex_morph_entries;
+        else if (t == MMDGPU_MORPH_BONE) pool = d.n_bone_morph_entries;
+        else if (t >= MMDGPU_MORPH_UV && t <= MMDGPU_MORPH_EXT_UV4) pool = d.n_uv_morph_entries;
+        if (pool != 0xFFFFFFFFu && d.morph_entry_count[m] && end > pool)
+            return fail(err, MMDGPU_ERR_BAD_INDEX, "morph entry range out of range at morph " + std::to_string(m));
+    }
+    {
+        std::vector<uint8_t> on_stack(nm, 0);
+        mmdgpu_status st = MMDGPU_OK;
+        std::function<void(uint32_t, int32_t, float, int32_t)> visit = [&](uint32_t m, int32_t parent, float mult,
+                                                                          int32_t depth) {
+            if (st != MMDGPU_OK) return;
+            if (p.node_morph.size() >= kMaxNodes) { st = fail(err, MMDGPU_ERR_UNSUPPORTED, "group morph expansion too large"); return; }
+            const int32_t me = int32_t(p.node_morph.size());
+            p.node_morph.push_back(int32_t(m));
+            p.node_parent.push_back(parent);
+            p.node_mult.push_back(mult);
+            p.node_depth.push_back(depth);
+            if (d.morph_type[m] != MMDGPU_MORPH_GROUP) return;
+            on_stack[m] = 1;
+            for (uint32_t j = 0; j < d.morph_entry_count[m]; ++j) {
+                const mmdgpu_group_morph_entry& g = d.group_morph_entries[d.morph_entry_begin[m] + j];
+                if (g.morph >= nm) { st = fail(err, MMDGPU_ERR_BAD_INDEX, "group morph child out of range"); return; }
+                if (on_stack[g.morph]) { st = fail(err, MMDGPU_ERR_BAD_INDEX, "group morph cycle (libmmd would recurse forever)"); return; }
+                visit(g.morph, me, g.rate, depth + 1);
+                if (st != MMDGPU_OK) return;
+            }
+            on_stack[m] = 0;
+        };
+        for (uint32_t m = 0; m < nm; ++m) {
+            visit(m, -1, 1.0f, 0);
+            if (st != MMDGPU_OK) return st;
+        }
+    }
+    const size_t n_nodes = p.node_morph.size();
+    {
+        int32_t max_depth = -1;
+        for (int32_t x : p.node_depth) max_depth = std::max(max_depth, x);
+        p.depth_begin.assign(size_t(max_depth + 2), 0);
+        for (int32_t x : p.node_depth) p.depth_begin[size_t(x) + 1]++;
+        for (int32_t x = 0; x <= max_depth; ++x) p.depth_begin[x + 1] += p.depth_begin[x];
+        p.nodes_by_depth.resize(n_nodes);
+        std::vector<int32_t> cur(p.depth_begin.begin(), p.depth_begin.end() - 1);
+        for (size_t i = 0; i < n_nodes; ++i) p.nodes_by_depth[size_t(cur[p.node_depth[i]]++)] = int32_t(i);
+    }
+
+    // per-vertex CSR: rows sorted by (application slot, entry order) because nodes are visited in order
+    auto build_vertex_csr = [&](bool uv, std::vector<uint32_t>& row, std::vector<uint32_t>& node_of,
+                                std::vector<float>& off) -> mmdgpu_status {
+        row.assign(size_t(nv) + 1, 0);
+        const int width = uv ? 4 : 3;
+        auto is_mine = [&](uint8_t t) { return uv ? (t == MMDGPU_MORPH_UV) : (t == MMDGPU_MORPH_VERTEX); };
+        for (size_t n = 0; n < n_nodes; ++n) {
+            const uint32_t m = uint32_t(p.node_morph[n]);
+            if (!is_mine(d.morph_type[m])) continue;
+            for (uint32_t j = 0; j < d.morph_entry_count[m]; ++j) {
+                const uint32_t v = uv ? d.uv_morph_entries[d.morph_entry_begin[m] + j].vertex
+                                      : d.vertex_morph_entries[d.morph_entry_begin[m] + j].vertex;
+                if (v >= nv) return fail(err, MMDGPU_ERR_BAD_INDEX, "morph vertex index out of range at morph " + std::to_string(m));
+                row[size_t(v) + 1]++;
+            }
+        }
+        for (uint32_t v = 0; v < nv; ++v) row[v + 1] += row[v];
+        node_of.resize(row[nv]);
+        off.resize(size_t(row[nv]) * width);
+        std::vector<uint32_t> cur(row.begin(), row.end() - 1);
+        for (size_t n = 0; n < n_nodes; ++n) {
+            const uint32_t m = uint32_t(p.node_morph[n]);
+            if (!is_mine(d.morph_type[m])) continue;
+            for (uint32_t j = 0; j < d.morph_entry_count[m]; ++j) {
+                const uint32_t e = d.morph_entry_begin[m] + j;
+                const uint32_t v = uv ? d.uv_morph_entries[e].vertex : d.vertex_morph_entries[e].vertex;
+                const float* o = uv ? d.uv_morph_entries[e].offset : d.vertex_morph_entries[e].offset;
+                const uint32_t at = cur[v]++;
+                node_of[at] = uint32_t(n);
+                for (int k = 0; k < width; ++k) off[size_t(at) * width + k] = o[k];
+            }
+        }
+        return MMDGPU_OK;
+    };
+    if (mmdgpu_status st = build_vertex_csr(false, p.csr_row, p.csr_node, p.csr_offset)) return st;
+    if (p.extensions)
+        if (mmdgpu_status st = build_vertex_csr(true, p.uv_row, p.uv_node, p.uv_offset)) return st;
+
+    // bone morphs grouped by affected bone, application order inside a bone
+    {
+        std::vector<std::vector<BoneMorphEntry>> per_bone(nb);
+        for (size_t n = 0; n < n_nodes; ++n) {
+            const uint32_t m = uint32_t(p.node_morph[n]);
+            if (d.morph_type[m] != MMDGPU_MORPH_BONE) continue;
+            for (uint32_t j = 0; j < d.morph_entry_count[m]; ++j) {
+                const mmdgpu_bone_morph_entry& e = d.bone_morph_entries[d.morph_entry_begin[m] + j];
+                if (e.bone >= nb) return fail(err, MMDGPU_ERR_BAD_INDEX, "bone morph bone index out of range at morph " + std::to_string(m));
+                BoneMorphEntry x;
+                x.node = int32_t(n);
+                std::memcpy(x.translation, e.translation, 12);
+                std::memcpy(x.rotation, e.rotation, 16);
+                per_bone[e.bone].push_back(x);
+            }
+        }
+        p.bone_morph_row.push_back(0);
+        for (uint32_t b = 0; b < nb; ++b) {
+            if (per_bone[b].empty()) continue;
+            p.bones[b].morph_slot = int32_t(p.morph_bones.size());
+            p.morph_bones.push_back(int32_t(b));
+            p.bone_morph_entries.insert(p.bone_morph_entries.end(), per_bone[b].begin(), per_bone[b].end());
+            p.bone_morph_row.push_back(int32_t(p.bone_morph_entries.size()));
+        }
+    }
+
+    // ---------------------------------------------------------------- vertices
+    p.norm_type.resize(nv);
+    p.dev_type.resize(nv);
+    p.bone_id.assign(size_t(nv) * 4, 0);
+    p.weight.assign(size_t(nv) * 4, 0.0f);
+    p.position.assign(d.position, d.position + size_t(nv) * 3);
+    p.normal.assign(d.normal, d.normal + size_t(nv) * 3);
+    if (d.uv) p.uv.assign(d.uv, d.uv + size_t(nv) * 2); else p.uv.assign(size_t(nv) * 2, 0.0f);
+    bool any_sdef = false;
+    for (uint32_t i = 0; i < nv; ++i) {
+        uint8_t t = d.skin_type[i];
+        if (t > MMDGPU_SKIN_QDEF) return fail(err, MMDGPU_ERR_INVALID_ARG, "unknown skinning type at vertex " + std::to_string(i));
+        const int n_ids = (t == MMDGPU_SKIN_BDEF1) ? 1 : (t == MMDGPU_SKIN_BDEF2 || t == MMDGPU_SKIN_SDEF) ? 2 : 4;
+        int32_t id[4] = {0, 0, 0, 0};
+        float w[4] = {0, 0, 0, 0};
+        for (int k = 0; k < n_ids; ++k) {
+            id[k] = d.bone_id[size_t(i) * 4 + k];
+            // libmmd reads bone_images_[id] unchecked (poser_impl.inl:412-432); reject instead
+            if (id[k] < 0 || uint32_t(id[k]) >= nb)
+                return fail(err, MMDGPU_ERR_BAD_INDEX, "bone id out of range at vertex " + std::to_string(i));
+        }
+        for (int k = 0; k < 4; ++k) w[k] = d.weight[size_t(i) * 4 + k];
+        const bool was_qdef = (t == MMDGPU_SKIN_QDEF);
+        if (was_qdef) t = MMDGPU_SKIN_BDEF4;  // libmmd cannot represent QDEF (L/model/model.inl:23-28)
+        // Model::Normalize, L/model/model_impl.inl:406-452
+        if (t == MMDGPU_SKIN_BDEF2) {
+            if (w[0] == 0.0f) { id[0] = id[1]; t = MMDGPU_SKIN_BDEF1; }
+            else if (w[0] == 1.0f) { t = MMDGPU_SKIN_BDEF1; }
+        } else if (t == MMDGPU_SKIN_SDEF) {
+            if (d.bone_parent[id[0]] != id[1] && d.bone_parent[id[1]] != id[0]) {
+                if (w[0] == 0.0f) { id[0] = id[1]; t = MMDGPU_SKIN_BDEF1; }
+                else if (w[0] == 1.0f) { t = MMDGPU_SKIN_BDEF1; }
+                else t = MMDGPU_SKIN_BDEF2;
+            }
+        }
+        p.norm_type[i] = t;
+        // device type: fold the Lerp shortcuts (math_impl.inl:1246-1250) of Deform's BDEF2 / SDEF branch
+        uint8_t dt;
+        if (t == MMDGPU_SKIN_BDEF1) dt = kDevBdef1;
+        else if (t == MMDGPU_SKIN_BDEF4) dt = (was_qdef && p.extensions) ? kDevQdef : kDevBdef4;
+        else if (t == MMDGPU_SKIN_SDEF && p.extensions) { dt = kDevSdef; any_sdef = true; }
+        else {
+            if (w[0] < float(kEpsD)) { id[0] = id[1]; dt = kDevBdef1; }
+            else if (w[0] > float(1.0 - kEpsD)) dt = kDevBdef1;
+            else dt = kDevBdef2;
+        }
+        p.dev_type[i] = dt;
+        const int keep = (dt == kDevBdef1) ? 1 : (dt == kDevBdef2 || dt == kDevSdef) ? 2 : 4;
+        for (int k = 0; k < keep; ++k) p.bone_id[size_t(i) * 4 + k] = uint16_t(id[k]);
+        if (dt == kDevBdef2 || dt == kDevSdef) p.weight[size_t(i) * 4] = w[0];
+        else if (dt == kDevBdef4 || dt == kDevQdef) for (int k = 0; k < 4; ++k) p.weight[size_t(i) * 4 + k] = w[k];
+        else p.weight[size_t(i) * 4] = 1.0f;
+    }
+    if (any_sdef) {
+        auto grab = [&](const float* src, std::vector<float>& dst) {
+            if (src) dst.assign(src, src + size_t(nv) * 3); else dst.assign(size_t(nv) * 3, 0.0f);
+        };
+        grab(d.sdef_c, p.sdef_c); grab(d.sdef_r0, p.sdef_r0); grab(d.sdef_r1, p.sdef_r1);
+    }
+
+    // introspection mirrors
+    p.op_kind_u8.resize(p.ops.size());
+    p.op_arg_i32.resize(p.ops.size());
+    for (size_t i = 0; i < p.ops.size(); ++i) {
+        p.op_kind_u8[i] = p.ops[i].kind;
+        p.op_arg_i32[i] = (p.ops[i].kind == kOpIk) ? p.iks[p.ops[i].arg].bone : p.ops[i].arg;
+    }
+    p.ik_fix_u8.resize(p.links.size());
+    p.ik_order_u8.resize(p.links.size());
+    for (size_t i = 0; i < p.links.size(); ++i) { p.ik_fix_u8[i] = p.links[i].fix; p.ik_order_u8[i] = p.links[i].order; }
+    p.phase_split_i32.assign(1, p.phase_split);
+    return MMDGPU_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// mmd::Motion storage (std::map<frame, key>, L/motion/motion.inl:128-129): sorted by frame, a later record
+// with the same frame replaces the earlier one.
+mmdgpu_status build_anim(const mmdgpu_anim_desc& d, uint32_t nb, uint32_t nm, HostAnim& a, std::string& err) {
+    a = HostAnim();
+    a.nb = nb; a.nm = nm;
+    a.bone_key_begin.assign(nb, 0); a.bone_key_count.assign(nb, 0); a.bone_tracked.assign(nb, 0);
+    a.morph_key_begin.assign(nm, 0); a.morph_key_count.assign(nm, 0); a.morph_tracked.assign(nm, 0);
+    std::unordered_map<uint32_t, uint32_t> table_of;
+    auto sorted_unique = [](std::vector<uint32_t>& idx, auto frame_of) {
+        std::stable_sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) { return frame_of(x) < frame_of(y); });
+        size_t o = 0;
+        for (size_t i = 0; i < idx.size(); ++i) {
+            if (i + 1 < idx.size() && frame_of(idx[i + 1]) == frame_of(idx[i])) continue;
+            idx[o++] = idx[i];
+        }
+        idx.resize(o);
+    };
+    if (d.n_bone_tracks && (!d.bone_track_bone || !d.bone_track_key_begin || !d.bone_track_key_count))
+        return fail(err, MMDGPU_ERR_INVALID_ARG, "bone track arrays missing");
+    if (d.n_morph_tracks && (!d.morph_track_morph || !d.morph_track_key_begin || !d.morph_track_key_count))
+        return fail(err, MMDGPU_ERR_INVALID_ARG, "morph track arrays missing");
+    std::vector<uint32_t> idx;
+    for (uint32_t t = 0; t < d.n_bone_tracks; ++t) {
+        const int32_t b = d.bone_track_bone[t];
+        if (b < 0 || uint32_t(b) >= nb) return fail(err, MMDGPU_ERR_BAD_INDEX, "bone track " + std::to_string(t) + " names a bone out of range");
+        if (a.bone_tracked[b]) return fail(err, MMDGPU_ERR_INVALID_ARG, "bone " + std::to_string(b) + " appears in two tracks");
+        const uint32_t k0 = d.bone_track_key_begin[t], kn = d.bone_track_key_count[t];
+        if (uint64_t(k0) + kn > d.n_bone_keys) return fail(err, MMDGPU_ERR_BAD_INDEX, "bone key range out of range");
+        if (kn && !d.bone_keys) return fail(err, MMDGPU_ERR_INVALID_ARG, "bone keys missing");
+        idx.resize(kn);
+        for (uint32_t i = 0; i < kn; ++i) idx[i] = k0 + i;
+        sorted_unique(idx, [&](uint32_t i) { return d.bone_keys[i].frame; });
+        a.bone_tracked[b] = 1;
+        a.bone_key_begin[b] = uint32_t(a.key_frame.size());
+        a.bone_key_count[b] = uint32_t(idx.size());
+        for (uint32_t i : idx) {
+            const mmdgpu_bone_key& k = d.bone_keys[i];
+            a.length = std::max(a.length, k.frame);
+            a.key_frame.push_back(k.frame);
+            a.key_T.insert(a.key_T.end(), {k.translation[0], k.translation[1], k.translation[2], 0.0f});
+            a.key_R.insert(a.key_R.end(), k.rotation, k.rotation + 4);
+            for (int c = 0; c < 4; ++c) {
+                uint32_t packed;
+                std::memcpy(&packed, k.interp[c], 4);
+                auto it = table_of.find(packed);
+                uint32_t ti;
+                if (it != table_of.end()) ti = it->second;
+                else {
+                    float tab[32];
+                    if (bezier_table(k.interp[c], tab)) ti = 0xFFFFFFFFu;
+                    else {
+                        ti = uint32_t(a.tables.size() / 32);
+                        a.tables.insert(a.tables.end(), tab, tab + 32);
+                    }
+                    table_of.emplace(packed, ti);
+                }
+                a.key_curve.push_back(ti);
+            }
+        }
+    }
+    for (uint32_t t = 0; t < d.n_morph_tracks; ++t) {
+        const int32_t m = d.morph_track_morph[t];
+        if (m < 0 || uint32_t(m) >= nm) return fail(err, MMDGPU_ERR_BAD_INDEX, "morph track " + std::to_string(t) + " names a morph out of range");
+        if (a.morph_tracked[m]) return fail(err, MMDGPU_ERR_INVALID_ARG, "morph " + std::to_string(m) + " appears in two tracks");
+        const uint32_t k0 = d.morph_track_key_begin[t], kn = d.morph_track_key_count[t];
+        if (uint64_t(k0) + kn > d.n_morph_keys) return fail(err, MMDGPU_ERR_BAD_INDEX, "morph key range out of range");
+        if (kn && !d.morph_keys) return fail(err, MMDGPU_ERR_INVALID_ARG, "morph keys missing");
+        idx.resize(kn);
+        for (uint32_t i = 0; i < kn; ++i) idx[i] = k0 + i;
+        sorted_unique(idx, [&](uint32_t i) { return d.morph_keys[i].frame; });
+        a.morph_tracked[m] = 1;
+        a.morph_key_begin[m] = uint32_t(a.mkey_frame.size());
+        a.morph_key_count[m] = uint32_t(idx.size());
+        for (uint32_t i : idx) {
+            a.length = std::max(a.length, d.morph_keys[i].frame);
+            a.mkey_frame.push_back(d.morph_keys[i].frame);
+            a.mkey_weight.push_back(d.morph_keys[i].weight);
+        }
+    }
+    return MMDGPU_OK;
+}
+
+}  // namespace mmdgpu

@@ -1,0 +1,618 @@
+// kernels.cu — the sm_100a kernels of the deformation path.
+//
+//   K1 pose_sample_kernel   VMD keyframe lookup + Bezier table lerp + NLerp      (Motion::GetBonePose/GetMorphPose)
+//   K2 hierarchy_kernel     morph rates, bone morphs, bone program in waves, CCD IK, skinning palette
+//   K3 skin_kernel          vertex morph gather + BDEF1/2/4 skinning of positions and normals (Poser::Deform)
+//
+// Compiled with -fmad=false: the fp32 expression trees are libmmd's, un-contracted.
+#include <cstdint>
+
+#include "device_types.cuh"
+#include "kernels.cuh"
+#include "mmd_math.cuh"
+
+namespace mmdgpu {
+
+using namespace dm;
+
+// =================================================================================================
+// K1 — keyframe sampling.  One thread per (slot, bone) and (slot, morph).
+// Motion::GetBonePose(name, size_t)  L/motion/motion_impl.inl:255-319
+// Motion::GetMorphPose(name, size_t) L/motion/motion_impl.inl:382-424
+// MotionPlayer::SeekFrame            L/motion/poser_impl.inl:539-546
+// Poser::ResetPosing (pose part)     L/motion/poser_impl.inl:131-137   (write_untracked = 1)
+// =================================================================================================
+__device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t* __restrict__ a, uint32_t n, uint32_t key) {
+    uint32_t lo = 0, hi = n;  // first index with a[i] > key
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(a + mid) <= key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(128) pose_sample_kernel(DevModel M, const DevAnim* __restrict__ anims, DevFrames F,
+                                                          uint32_t write_untracked, uint32_t range_mode,
+                                                          uint32_t frame_stride, uint32_t has_anims) {
+    const uint32_t slot = blockIdx.y;
+    const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= M.nb + M.nm) return;
+    const uint32_t inst = slot / F.n_frames;
+    const uint32_t frame = range_mode ? (F.frame_id[inst] + (slot - inst * F.n_frames) * frame_stride) : F.frame_id[slot];
+    if (item < M.nb) {
+        const uint32_t b = item;
+        float4 T = make_float4(0.f, 0.f, 0.f, 0.f), R = make_float4(0.f, 0.f, 0.f, 1.f);
+        bool tracked = false;
+        if (has_anims) {
+            const DevAnim A = anims[inst];
+            tracked = A.bone_tracked[b] != 0;
+            const uint32_t n = A.bone_key_count[b];
+            if (tracked && n > 0) {
+                const uint32_t k0 = A.bone_key_begin[b];
+                const uint32_t* kf = A.key_frame + k0;
+                uint32_t use = 0xFFFFFFFFu;
+                if (kf[0] >= frame) use = 0;
+                else if (kf[n - 1] <= frame) use = n - 1;
+                else {
+                    const uint32_t r = upper_bound_u32(kf, n, frame);
+                    const uint32_t l = r - 1;
+                    const uint32_t lf = kf[l], rf = kf[r];
+                    if (lf == frame) use = l;
+                    else {
+                        const float bary = (float)(frame - lf) / (float)(rf - lf);
+                        const float4 lT = A.key_T[k0 + l], rT = A.key_T[k0 + r];
+                        const float4 lR = A.key_R[k0 + l], rR = A.key_R[k0 + r];
+                        const uint4 cv = A.key_curve[k0 + l];  // curves of the LEFT key (motion_impl.inl:302-312)
+                        float lam = bezier_at(A.tables, cv.x, bary);
+                        T.x = lT.x * (1 - lam) + rT.x * lam;
+                        lam = bezier_at(A.tables, cv.y, bary);
+                        T.y = lT.y * (1 - lam) + rT.y * lam;
+                        lam = bezier_at(A.tables, cv.z, bary);
+                        T.z = lT.z * (1 - lam) + rT.z * lam;
+                        const float l_ = bezier_at(A.tables, cv.w, bary);
+                        // NLerpProxy<Vector4f>::operator[], L/util/math_impl.inl:1265-1277
+                        if (l_ < kEpsF) R = lR;
+                        else if (l_ > (1.0f - kEpsF)) R = rR;
+                        else {
+                            const float dot = lR.x * rR.x + lR.y * rR.y + lR.z * rR.z + lR.w * rR.w;
+                            float4 v;
+                            if (dot < 0.0f) {
+                                v.x = (1.0f - l_) * lR.x - l_ * rR.x; v.y = (1.0f - l_) * lR.y - l_ * rR.y;
+                                v.z = (1.0f - l_) * lR.z - l_ * rR.z; v.w = (1.0f - l_) * lR.w - l_ * rR.w;
+                            } else {
+                                v.x = (1.0f - l_) * lR.x + l_ * rR.x; v.y = (1.0f - l_) * lR.y + l_ * rR.y;
+                                v.z = (1.0f - l_) * lR.z + l_ * rR.z; v.w = (1.0f - l_) * lR.w + l_ * rR.w;
+                            }
+                            const float nn = 1.0f / m_sqrt(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
+                            R = make_float4(v.x * nn, v.y * nn, v.z * nn, v.w * nn);
+                        }
+                    }
+                }
+                if (use != 0xFFFFFFFFu) {
+                    T = A.key_T[k0 + use];
+                    R = A.key_R[k0 + use];
+                }
+                T.w = 0.f;
+            }
+        }
+        if (tracked || write_untracked) {
+            F.poseT[(size_t)slot * M.nb + b] = T;
+            F.poseR[(size_t)slot * M.nb + b] = R;
+        }
+    } else {
+        const uint32_t m = item - M.nb;
+        float w = 0.0f;
+        bool tracked = false;
+        if (has_anims) {
+            const DevAnim A = anims[inst];
+            tracked = A.morph_tracked[m] != 0;
+            const uint32_t n = A.morph_key_count[m];
+            if (tracked && n > 0) {
+                const uint32_t k0 = A.morph_key_begin[m];
+                const uint32_t* kf = A.mkey_frame + k0;
+                const float* kw = A.mkey_weight + k0;
+                if (kf[0] >= frame) w = kw[0];
+                else if (kf[n - 1] <= frame) w = kw[n - 1];
+                else {
+                    const uint32_t r = upper_bound_u32(kf, n, frame);
+                    const uint32_t l = r - 1;
+                    if (kf[l] == frame) w = kw[l];
+                    else {
+                        const float bary = (float)(frame - kf[l]) / (float)(kf[r] - kf[l]);
+                        const float lam = bary;  // default-constructed Bezier is linear (math_impl.inl:1350-1354)
+                        w = kw[l] * (1 - lam) + kw[r] * lam;
+                    }
+                }
+            }
+        }
+        if (tracked || write_untracked) F.rate[(size_t)slot * M.nm + m] = w;
+    }
+}
+
+// =================================================================================================
+// K2 — hierarchy.  One warp per slot; lanes execute the ops of one wave in parallel.
+// =================================================================================================
+struct SlotState {
+    const float4* poseR;
+    const float4* poseT;
+    float4* totR;
+    float4* totT;
+    float4* local;   // 3 float4 per bone
+    float4* ikR;
+    float4* preIK;
+    const float4* morphR;
+    const float4* morphT;
+    float4* palette; // 3 float4 per bone
+};
+
+__device__ __forceinline__ Mat43 load_local(const float4* p) {
+    const float4 a = p[0], b = p[1], c = p[2];
+    Mat43 M;
+    M.m[0][0] = a.x; M.m[0][1] = a.y; M.m[0][2] = a.z; M.m[1][0] = a.w;
+    M.m[1][1] = b.x; M.m[1][2] = b.y; M.m[2][0] = b.z; M.m[2][1] = b.w;
+    M.m[2][2] = c.x; M.m[3][0] = c.y; M.m[3][1] = c.z; M.m[3][2] = c.w;
+    return M;
+}
+__device__ __forceinline__ void store_local(float4* p, const Mat43& M) {
+    p[0] = make_float4(M.m[0][0], M.m[0][1], M.m[0][2], M.m[1][0]);
+    p[1] = make_float4(M.m[1][1], M.m[1][2], M.m[2][0], M.m[2][1]);
+    p[2] = make_float4(M.m[2][2], M.m[3][0], M.m[3][1], M.m[3][2]);
+}
+__device__ __forceinline__ BoneStatic load_bone(const BoneStatic* __restrict__ bones, int32_t b) {
+    const float4* p = reinterpret_cast<const float4*>(bones + b);
+    const float4 a = __ldg(p), c = __ldg(p + 1), d = __ldg(p + 2);
+    BoneStatic s;
+    s.local_offset[0] = a.x; s.local_offset[1] = a.y; s.local_offset[2] = a.z; s.parent = __float_as_int(a.w);
+    s.position[0] = c.x; s.position[1] = c.y; s.position[2] = c.z; s.append_parent = __float_as_int(c.w);
+    s.append_ratio = d.x; s.flags = (uint32_t)__float_as_int(d.y);
+    s.link_slot = __float_as_int(d.z); s.morph_slot = __float_as_int(d.w);
+    return s;
+}
+
+// local_matrix_ from total rotation / translation, then * parent (poser_impl.inl:161-166, :294-299)
+__device__ __forceinline__ void set_local(const SlotState& S, const BoneStatic& s, int32_t b, const Quat& totR,
+                                          const float4& totT) {
+    Mat43 L;
+    q_to_rows(totR, L);
+    L.m[3][0] = totT.x + s.local_offset[0];
+    L.m[3][1] = totT.y + s.local_offset[1];
+    L.m[3][2] = totT.z + s.local_offset[2];
+    if (s.flags & kHasParent) {
+        const Mat43 P = load_local(S.local + 3 * (size_t)s.parent);
+        L = m_mul(L, P);
+    }
+    store_local(S.local + 3 * (size_t)b, L);
+}
+
+// Poser::UpdateBoneTransform(size_t) without the IK part, L/motion/poser_impl.inl:142-166
+__device__ __noinline__ void eval_bone(const DevModel& M, const SlotState& S, int32_t b) {
+    const BoneStatic s = load_bone(M.bones, b);
+    const Quat R = q_from(S.poseR[b]);
+    const float4 T = S.poseT[b];
+    Quat mR = q_identity();
+    float4 mT = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s.morph_slot >= 0) {
+        mR = q_from(S.morphR[s.morph_slot]);
+        mT = S.morphT[s.morph_slot];
+    }
+    Quat totR = q_mul(mR, R);
+    float4 totT = make_float4(mT.x + T.x, mT.y + T.y, mT.z + T.z, 0.f);
+    if (s.flags & (kAppendRot | kAppendTrans)) {
+        if (s.flags & kAppendRot) {
+            const Quat pr = q_from(S.totR[s.append_parent]);
+            totR = q_mul(totR, q_slerp(q_identity(), pr, s.append_ratio));
+        }
+        if (s.flags & kAppendTrans) {
+            const float4 pt = S.totT[s.append_parent];
+            totT.x = totT.x + s.append_ratio * pt.x;
+            totT.y = totT.y + s.append_ratio * pt.y;
+            totT.z = totT.z + s.append_ratio * pt.z;
+        }
+    }
+    if (s.flags & kIsLink) {
+        S.preIK[s.link_slot] = q_to4(totR);
+        totR = q_mul(q_from(S.ikR[s.link_slot]), totR);
+    }
+    S.totR[b] = q_to4(totR);
+    S.totT[b] = totT;
+    set_local(S, s, b, totR, totT);
+}
+
+__device__ __forceinline__ Vec3 local_pos(const SlotState& S, int32_t b) {
+    const float4 c = S.local[3 * (size_t)b + 2];
+    return Vec3{c.y, c.z, c.w};
+}
+
+// CCD IK, L/motion/poser_impl.inl:168-310 (the part of UpdateBoneTransform after the bone's own transform)
+__device__ __noinline__ void solve_ik(const DevModel& M, const SlotState& S, const IkDesc k) {
+    const IkLink* __restrict__ links = M.links + k.link_begin;
+    const int nl = k.link_count;
+    for (int i = 0; i < nl; ++i) S.ikR[M.bones[links[i].bone].link_slot] = make_float4(0.f, 0.f, 0.f, 1.f);
+    const Vec3 ik_pos = local_pos(S, k.bone);
+    for (int i = 0; i < nl; ++i) eval_bone(M, S, links[nl - i - 1].bone);
+    eval_bone(M, S, k.target);
+    Vec3 tp = local_pos(S, k.target);
+    Vec3 err{ik_pos.x - tp.x, ik_pos.y - tp.y, ik_pos.z - tp.z};
+    if ((double)v_dot(err, err) < kEpsD) return;
+    const int iters = k.iterations;
+    const int ikt = iters / 2;
+    for (int i = 0; i < iters; ++i) {
+        for (int j = 0; j < nl; ++j) {
+            const IkLink L = links[j];
+            if (L.fix == 4) continue;
+            const BoneStatic ls = load_bone(M.bones, L.bone);
+            const Vec3 lp = local_pos(S, L.bone);
+            Vec3 td = v_normalize(Vec3{lp.x - tp.x, lp.y - tp.y, lp.z - tp.z});
+            Vec3 id = v_normalize(Vec3{lp.x - ik_pos.x, lp.y - ik_pos.y, lp.z - ik_pos.z});
+            // Triple::operator*, L/util/math_impl.inl:260-266
+            Vec3 ax{td.y * id.z - td.z * id.y, td.z * id.x - td.x * id.z, td.x * id.y - td.y * id.x};
+            if ((double)fabsf(ax.x) < kEpsD) ax.x = (float)kEpsD;
+            if ((double)fabsf(ax.y) < kEpsD) ax.y = (float)kEpsD;
+            if ((double)fabsf(ax.z) < kEpsD) ax.z = (float)kEpsD;
+            Mat43 P = m_identity();
+            if (ls.flags & kHasParent) P = load_local(S.local + 3 * (size_t)ls.parent);
+            if (L.limited && L.fix != 0 && i < ikt) {
+                const int r = L.fix - 1;
+                const float d = ax.x * P.m[r][0] + ax.y * P.m[r][1] + ax.z * P.m[r][2];
+                const float sgn = (d >= 0.0f) ? 1.0f : -1.0f;
+                ax = Vec3{r == 0 ? sgn : 0.0f, r == 1 ? sgn : 0.0f, r == 2 ? sgn : 0.0f};
+            } else {
+                // rotate(axis, P^T), L/util/math_impl.inl:1032-1038
+                const Vec3 t{ax.x * P.m[0][0] + ax.y * P.m[0][1] + ax.z * P.m[0][2],
+                             ax.x * P.m[1][0] + ax.y * P.m[1][1] + ax.z * P.m[1][2],
+                             ax.x * P.m[2][0] + ax.y * P.m[2][1] + ax.z * P.m[2][2]};
+                ax = v_normalize(t);
+            }
+            const float ang = s_min(m_acos(m_clamp(v_dot(td, id), -1.0f, 1.0f)), k.angle_limit * (float)(j + 1));
+            Quat ikR = q_mul(axis_to_quat(ax, ang), q_from(S.ikR[ls.link_slot]));
+            if (L.limited) {
+                const Quat pre = q_from(S.preIK[ls.link_slot]);
+                Quat lr = q_mul(ikR, pre);
+                Vec3 eu = quat_to_euler(L.order, lr);
+                const bool refl = i < ikt;
+                eu.x = limit_one(eu.x, L.lo[0], L.hi[0], refl);
+                eu.y = limit_one(eu.y, L.lo[1], L.hi[1], refl);
+                eu.z = limit_one(eu.z, L.lo[2], L.hi[2], refl);
+                lr = euler_to_quat(L.order, eu);
+                ikR = q_mul(lr, q_inverse(pre));
+            }
+            S.ikR[ls.link_slot] = q_to4(ikR);
+            for (int c = j; c >= 0; --c) {  // links j .. 0 (poser_impl.inl:292-300)
+                const int32_t cb = links[c].bone;
+                const BoneStatic cs = load_bone(M.bones, cb);
+                const Quat tot = q_mul(q_from(S.ikR[cs.link_slot]), q_from(S.preIK[cs.link_slot]));
+                S.totR[cb] = q_to4(tot);
+                set_local(S, cs, cb, tot, S.totT[cb]);
+            }
+            eval_bone(M, S, k.target);
+            tp = local_pos(S, k.target);
+        }
+        err = Vec3{ik_pos.x - tp.x, ik_pos.y - tp.y, ik_pos.z - tp.z};
+        if (v_dot(err, err) < kEpsF) return;
+    }
+}
+
+// Poser::UpdateBoneSkinningMatrix, L/motion/poser_impl.inl:320-326: skin = global_offset * local, stored as
+// the three columns the skinning kernel consumes.
+__device__ __forceinline__ void skin_bone(const DevModel& M, const SlotState& S, int32_t b) {
+    const BoneStatic s = load_bone(M.bones, b);
+    const Mat43 L = load_local(S.local + 3 * (size_t)b);
+    const float g30 = -s.position[0], g31 = -s.position[1], g32 = -s.position[2];
+    float4 col[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        // rows of global_offset are unit vectors; the zero products are kept for signed-zero fidelity
+        const float r0 = 1.0f * L.m[0][c] + 0.0f * L.m[1][c] + 0.0f * L.m[2][c] + 0.0f * L.m[3][c];
+        const float r1 = 0.0f * L.m[0][c] + 1.0f * L.m[1][c] + 0.0f * L.m[2][c] + 0.0f * L.m[3][c];
+        const float r2 = 0.0f * L.m[0][c] + 0.0f * L.m[1][c] + 1.0f * L.m[2][c] + 0.0f * L.m[3][c];
+        const float r3 = g30 * L.m[0][c] + g31 * L.m[1][c] + g32 * L.m[2][c] + 1.0f * L.m[3][c];
+        col[c] = make_float4(r0, r1, r2, r3);
+    }
+    S.palette[3 * (size_t)b + 0] = col[0];
+    S.palette[3 * (size_t)b + 1] = col[1];
+    S.palette[3 * (size_t)b + 2] = col[2];
+}
+
+constexpr uint32_t kHierWarps = 4;
+
+__global__ void __launch_bounds__(32 * kHierWarps) hierarchy_kernel(DevModel M, DevFrames F, uint32_t wave_lo,
+                                                                    uint32_t wave_hi, uint32_t prologue) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t slot = blockIdx.x * kHierWarps + (threadIdx.x >> 5);
+    if (slot >= F.n_slots) return;
+    SlotState S;
+    S.poseR = F.poseR + (size_t)slot * M.nb;
+    S.poseT = F.poseT + (size_t)slot * M.nb;
+    S.totR = F.totR + (size_t)slot * M.nb;
+    S.totT = F.totT + (size_t)slot * M.nb;
+    S.local = reinterpret_cast<float4*>(F.local) + (size_t)slot * M.nb * 3;
+    S.ikR = F.ikR + (size_t)slot * M.n_link_slots;
+    S.preIK = F.preIK + (size_t)slot * M.n_link_slots;
+    float4* morphR = F.morphR + (size_t)slot * M.n_morph_slots;
+    float4* morphT = F.morphT + (size_t)slot * M.n_morph_slots;
+    S.morphR = morphR;
+    S.morphT = morphT;
+    S.palette = F.palette + (size_t)slot * M.nb * 3;
+
+    if (prologue) {
+        // ---- morph application-slot rates: Poser::UpdateMorphTransform's skip test and group recursion
+        //      (poser_impl.inl:329-339), evaluated breadth-first over the static DFS tree.
+        const float* rate = F.rate + (size_t)slot * M.nm;
+        float* nrate = F.node_rate + (size_t)slot * M.n_nodes_pad;
+        for (uint32_t dpt = 0; dpt < M.n_depths; ++dpt) {
+            const int32_t b0 = M.depth_begin[dpt], b1 = M.depth_begin[dpt + 1];
+            for (int32_t i = b0 + (int32_t)lane; i < b1; i += 32) {
+                const int32_t n = M.nodes_by_depth[i];
+                const int32_t par = M.node_parent[n];
+                float r;
+                bool active = true;
+                if (par < 0) r = rate[M.node_morph[n]];
+                else {
+                    const float pr = nrate[par];
+                    active = pr != 0.0f;            // a skipped group skips its whole subtree
+                    r = M.node_mult[n] * pr;        // data.GetMorphRate()*rate
+                }
+                if (!active || (double)r < kEpsD) r = 0.0f;
+                nrate[n] = r;
+            }
+            __syncwarp();
+        }
+        // ---- PrePhysicsPosing's per-bone reset (poser_impl.inl:366-377), restricted to state that is read
+        //      before it is written this frame, and the compact IK / bone-morph state.
+        for (uint32_t i = lane; i < M.n_reset; i += 32) {
+            const int32_t b = M.reset_bones[i];
+            S.totR[b] = make_float4(0.f, 0.f, 0.f, 1.f);
+            S.totT[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+            store_local(S.local + 3 * (size_t)b, m_identity());
+        }
+        for (uint32_t i = lane; i < M.n_link_slots; i += 32) {
+            S.ikR[i] = make_float4(0.f, 0.f, 0.f, 1.f);
+            S.preIK[i] = make_float4(0.f, 0.f, 0.f, 1.f);
+        }
+        // ---- bone morphs (poser_impl.inl:347-354), application order inside each affected bone
+        for (uint32_t i = lane; i < M.n_morph_slots; i += 32) {
+            Quat mr = q_identity();
+            float tx = 0.f, ty = 0.f, tz = 0.f;
+            for (int32_t e = M.bone_morph_row[i]; e < M.bone_morph_row[i + 1]; ++e) {
+                const BoneMorphEntry E = M.bone_morph_entries[e];
+                const float r = nrate[E.node];
+                if (r != 0.0f) {
+                    tx = tx + E.translation[0] * r;
+                    ty = ty + E.translation[1] * r;
+                    tz = tz + E.translation[2] * r;
+                    const Quat q{E.rotation[0], E.rotation[1], E.rotation[2], E.rotation[3]};
+                    mr = q_mul(mr, q_slerp(q_identity(), q, r));
+                }
+            }
+            morphR[i] = q_to4(mr);
+            morphT[i] = make_float4(tx, ty, tz, 0.f);
+        }
+        __syncwarp();
+    }
+
+    for (uint32_t w = wave_lo; w < wave_hi; ++w) {
+        const uint32_t o0 = M.wave_begin[w], o1 = M.wave_begin[w + 1];
+        for (uint32_t o = o0 + lane; o < o1; o += 32) {
+            const uint32_t word = __ldg(M.wave_ops + o);
+            const uint32_t kind = word >> 28;
+            const int32_t arg = (int32_t)(word & 0x0FFFFFFFu);
+            if (kind == kOpEval) eval_bone(M, S, arg);
+            else if (kind == kOpIk) solve_ik(M, S, M.iks[arg]);
+            else skin_bone(M, S, arg);
+        }
+        __syncwarp();
+    }
+}
+
+// =================================================================================================
+// K3 — skinning.  Poser::Deform, L/motion/poser_impl.inl:396-461; transform / rotate math_impl.inl:1032-1045.
+//
+// One CTA stages the slot's bone palette (nb x 48 B) and application-slot rates in shared memory with one
+// bulk async copy each (cp.async.bulk + mbarrier), then every thread streams 4 consecutive vertices per
+// iteration with 16-byte loads from the SoA planes.  The sparse vertex morphs arrive as a per-vertex CSR
+// gather in application order: no vertex_images_ buffer, no clear pass, no atomics.
+// =================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+struct Col3 { float4 c0, c1, c2; };  // skinning matrix as three columns (M0c, M1c, M2c, M3c)
+
+__device__ __forceinline__ Col3 pal_load(const float4* __restrict__ pal, uint32_t id) {
+    Col3 r;
+    r.c0 = pal[3 * id + 0];
+    r.c1 = pal[3 * id + 1];
+    r.c2 = pal[3 * id + 2];
+    return r;
+}
+__device__ __forceinline__ float4 f4_scale(const float4& a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float4 f4_add(const float4& a, const float4& b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+// One vertex.  ids: 4 x u16 (type in bits 15:13 of id0); w: BDEF2 uses w.x, BDEF4 all four.
+__device__ __forceinline__ void skin_vertex(const float4* __restrict__ pal, uint32_t ids_lo, uint32_t ids_hi,
+                                            const float4& w, float px, float py, float pz, float nx, float ny,
+                                            float nz, float* __restrict__ op, float* __restrict__ on) {
+    const uint32_t type = (ids_lo >> 13) & 7u;
+    const uint32_t id0 = ids_lo & 0x1FFFu, id1 = ids_lo >> 16;
+    Col3 Mx = pal_load(pal, id0);
+    if (type == kDevBdef2) {
+        // Lerp(mat_1, mat_0)[w] = (1-w)*mat_1 + w*mat_0 (poser_impl.inl:422, math_impl.inl:1246-1254)
+        const Col3 B = pal_load(pal, id1);
+        const float l = w.x, om = 1.0f - w.x;
+        Mx.c0 = f4_add(f4_scale(B.c0, om), f4_scale(Mx.c0, l));
+        Mx.c1 = f4_add(f4_scale(B.c1, om), f4_scale(Mx.c1, l));
+        Mx.c2 = f4_add(f4_scale(B.c2, om), f4_scale(Mx.c2, l));
+    } else if (type == kDevBdef4) {
+        // mat_0*w0 + mat_1*w1 + mat_2*w2 + mat_3*w3, left to right (poser_impl.inl:433)
+        const uint32_t id2 = ids_hi & 0xFFFFu, id3 = ids_hi >> 16;
+        const Col3 B = pal_load(pal, id1), C = pal_load(pal, id2), D = pal_load(pal, id3);
+        Mx.c0 = f4_add(f4_add(f4_add(f4_scale(Mx.c0, w.x), f4_scale(B.c0, w.y)), f4_scale(C.c0, w.z)), f4_scale(D.c0, w.w));
+        Mx.c1 = f4_add(f4_add(f4_add(f4_scale(Mx.c1, w.x), f4_scale(B.c1, w.y)), f4_scale(C.c1, w.z)), f4_scale(D.c1, w.w));
+        Mx.c2 = f4_add(f4_add(f4_add(f4_scale(Mx.c2, w.x), f4_scale(B.c2, w.y)), f4_scale(C.c2, w.z)), f4_scale(D.c2, w.w));
+    }
+    // transform: v0*m00 + v1*m10 + v2*m20 + m30 ; rotate: without the translation row
+    op[0] = px * Mx.c0.x + py * Mx.c0.y + pz * Mx.c0.z + Mx.c0.w;
+    op[1] = px * Mx.c1.x + py * Mx.c1.y + pz * Mx.c1.z + Mx.c1.w;
+    op[2] = px * Mx.c2.x + py * Mx.c2.y + pz * Mx.c2.z + Mx.c2.w;
+    on[0] = nx * Mx.c0.x + ny * Mx.c0.y + nz * Mx.c0.z;
+    on[1] = nx * Mx.c1.x + ny * Mx.c1.y + nz * Mx.c1.z;
+    on[2] = nx * Mx.c2.x + ny * Mx.c2.y + nz * Mx.c2.z;
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(kSkinThreads) skin_kernel(DevModel M, DevFrames F, uint32_t tiles_per_cta) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* pal = reinterpret_cast<float4*>(smem_raw);
+    float* nrate = reinterpret_cast<float*>(smem_raw + (size_t)M.nb * 48);
+    __shared__ __align__(8) uint64_t bar;
+
+    const uint32_t slot = blockIdx.y;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t pal_bytes = M.nb * 48u, rate_bytes = M.n_nodes_pad * 4u;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar, pal_bytes + rate_bytes);
+        bulk_g2s(pal, F.palette + (size_t)slot * M.nb * 3, pal_bytes, &bar);
+        if (rate_bytes) bulk_g2s(nrate, F.node_rate + (size_t)slot * M.n_nodes_pad, rate_bytes, &bar);
+    }
+
+    const uint32_t tile0 = blockIdx.x * tiles_per_cta;
+    bool waited = false;
+    for (uint32_t t = 0; t < tiles_per_cta; ++t) {
+        const uint32_t v0 = (tile0 + t) * kTileVerts + tid * kVertsPerThread;
+        if (v0 >= M.nv_pad) break;
+        // ---- 16-byte loads of the static streams (issued before waiting for the palette)
+        const float4 PX = __ldg(reinterpret_cast<const float4*>(M.px + v0));
+        const float4 PY = __ldg(reinterpret_cast<const float4*>(M.py + v0));
+        const float4 PZ = __ldg(reinterpret_cast<const float4*>(M.pz + v0));
+        const float4 NX = __ldg(reinterpret_cast<const float4*>(M.nx + v0));
+        const float4 NY = __ldg(reinterpret_cast<const float4*>(M.ny + v0));
+        const float4 NZ = __ldg(reinterpret_cast<const float4*>(M.nz + v0));
+        const uint4 I01 = __ldg(reinterpret_cast<const uint4*>(M.ids + v0));
+        const uint4 I23 = __ldg(reinterpret_cast<const uint4*>(M.ids + v0 + 2));
+        const float4 W0 = __ldg(M.weights + v0), W1 = __ldg(M.weights + v0 + 1), W2 = __ldg(M.weights + v0 + 2),
+                     W3 = __ldg(M.weights + v0 + 3);
+        const uint4 RP = __ldg(reinterpret_cast<const uint4*>(M.csr_row + v0));
+        const uint32_t RE = __ldg(M.csr_row + v0 + 4);
+        if (!waited) {
+            mbar_wait(&bar, 0);
+            waited = true;
+        }
+        const float px[4] = {PX.x, PX.y, PX.z, PX.w}, py[4] = {PY.x, PY.y, PY.z, PY.w}, pz[4] = {PZ.x, PZ.y, PZ.z, PZ.w};
+        const float nx[4] = {NX.x, NX.y, NX.z, NX.w}, ny[4] = {NY.x, NY.y, NY.z, NY.w}, nz[4] = {NZ.x, NZ.y, NZ.z, NZ.w};
+        const uint32_t ilo[4] = {I01.x, I01.z, I23.x, I23.z}, ihi[4] = {I01.y, I01.w, I23.y, I23.w};
+        const float4 wv[4] = {W0, W1, W2, W3};
+        const uint32_t rp[5] = {RP.x, RP.y, RP.z, RP.w, RE};
+        float op[12], on[12];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            // vertex_images_[i] accumulated in application order: img = img + off*rate (poser_impl.inl:340-346)
+            float ix = 0.f, iy = 0.f, iz = 0.f;
+            for (uint32_t e = rp[j]; e < rp[j + 1]; ++e) {
+                const float4 ent = __ldg(M.csr_ent + e);
+                const float r = nrate[__float_as_int(ent.w)];
+                if (r != 0.0f) {
+                    ix = ix + ent.x * r;
+                    iy = iy + ent.y * r;
+                    iz = iz + ent.z * r;
+                }
+            }
+            // coordinate + vertex_image (poser_impl.inl:407)
+            skin_vertex(pal, ilo[j], ihi[j], wv[j], px[j] + ix, py[j] + iy, pz[j] + iz, nx[j], ny[j], nz[j], op + 3 * j,
+                        on + 3 * j);
+        }
+        if (LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) {
+            float4* dp = reinterpret_cast<float4*>(F.out_pos + ((size_t)slot * M.nv_pad + v0) * 3);
+            float4* dn = reinterpret_cast<float4*>(F.out_nrm + ((size_t)slot * M.nv_pad + v0) * 3);
+            dp[0] = make_float4(op[0], op[1], op[2], op[3]);
+            dp[1] = make_float4(op[4], op[5], op[6], op[7]);
+            dp[2] = make_float4(op[8], op[9], op[10], op[11]);
+            dn[0] = make_float4(on[0], on[1], on[2], on[3]);
+            dn[1] = make_float4(on[4], on[5], on[6], on[7]);
+            dn[2] = make_float4(on[8], on[9], on[10], on[11]);
+        } else {
+            // main.cpp:838-859: Vertex{pos*0.1f, normal, uv}
+            const float4 UV01 = __ldg(reinterpret_cast<const float4*>(M.uv + v0));
+            const float4 UV23 = __ldg(reinterpret_cast<const float4*>(M.uv + v0 + 2));
+            const float uu[4] = {UV01.x, UV01.z, UV23.x, UV23.z}, vv[4] = {UV01.y, UV01.w, UV23.y, UV23.w};
+            float4* d = F.out_inter + ((size_t)slot * M.nv_pad + v0) * 2;
+            const float mmd_to_meter = 0.1f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                d[2 * j] = make_float4(op[3 * j] * mmd_to_meter, op[3 * j + 1] * mmd_to_meter, op[3 * j + 2] * mmd_to_meter, on[3 * j]);
+                d[2 * j + 1] = make_float4(on[3 * j + 1], on[3 * j + 2], uu[j], vv[j]);
+            }
+        }
+    }
+    if (!waited) mbar_wait(&bar, 0);  // never leave a bulk copy in flight when the CTA exits
+}
+
+// =================================================================================================
+// launchers
+// =================================================================================================
+cudaError_t launch_pose_sample(cudaStream_t st, const DevModel& M, const DevAnim* anims, const DevFrames& F,
+                               bool write_untracked, bool range_mode, uint32_t frame_stride) {
+    const uint32_t items = M.nb + M.nm;
+    if (items == 0 || F.n_slots == 0) return cudaSuccess;
+    dim3 grid((items + 127) / 128, F.n_slots);
+    pose_sample_kernel<<<grid, 128, 0, st>>>(M, anims, F, write_untracked ? 1u : 0u, range_mode ? 1u : 0u, frame_stride,
+                                             anims ? 1u : 0u);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hierarchy(cudaStream_t st, const DevModel& M, const DevFrames& F, uint32_t wave_lo, uint32_t wave_hi,
+                             bool prologue) {
+    if (F.n_slots == 0) return cudaSuccess;
+    const uint32_t blocks = (F.n_slots + kHierWarps - 1) / kHierWarps;
+    hierarchy_kernel<<<blocks, 32 * kHierWarps, 0, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u);
+    return cudaGetLastError();
+}
+
+size_t skin_smem_bytes(const DevModel& M) { return (size_t)M.nb * 48 + (size_t)M.n_nodes_pad * 4; }
+
+cudaError_t prepare_skin_kernels(size_t smem) {
+    cudaError_t e = cudaFuncSetAttribute(skin_kernel<MMDGPU_LAYOUT_SOA_POS_NRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(skin_kernel<MMDGPU_LAYOUT_INTERLEAVED_SOKOL32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, int layout, uint32_t tiles_per_cta) {
+    if (F.n_slots == 0 || M.nv_pad == 0) return cudaSuccess;
+    const uint32_t tiles = M.nv_pad / kTileVerts;
+    dim3 grid((tiles + tiles_per_cta - 1) / tiles_per_cta, F.n_slots);
+    const size_t smem = skin_smem_bytes(M);
+    if (layout == MMDGPU_LAYOUT_SOA_POS_NRM)
+        skin_kernel<MMDGPU_LAYOUT_SOA_POS_NRM><<<grid, kSkinThreads, smem, st>>>(M, F, tiles_per_cta);
+    else
+        skin_kernel<MMDGPU_LAYOUT_INTERLEAVED_SOKOL32><<<grid, kSkinThreads, smem, st>>>(M, F, tiles_per_cta);
+    return cudaGetLastError();
+}
+
+}  // namespace mmdgpu

@@ -1,0 +1,22 @@
+// kernels.cuh — host-callable launchers of the sm_100a kernels (kernels.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "device_types.cuh"
+
+namespace mmdgpu {
+
+// K1: keyframe sampling for every (slot, bone) and (slot, morph).  anims == nullptr: write identity / zero
+// (Poser::ResetPosing's pose part).  write_untracked: also write identity / zero for items without a track.
+cudaError_t launch_pose_sample(cudaStream_t st, const DevModel& M, const DevAnim* anims, const DevFrames& F,
+                               bool write_untracked, bool range_mode, uint32_t frame_stride);
+// K2: waves [wave_lo, wave_hi) of the bone program; prologue = morph rates + reset + bone morphs.
+cudaError_t launch_hierarchy(cudaStream_t st, const DevModel& M, const DevFrames& F, uint32_t wave_lo, uint32_t wave_hi,
+                             bool prologue);
+// K3: skinning + fused vertex-morph gather.
+size_t skin_smem_bytes(const DevModel& M);
+cudaError_t prepare_skin_kernels(size_t smem);
+cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, int layout, uint32_t tiles_per_cta);
+
+}  // namespace mmdgpu

@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py — skinned vertex-frames/s of the libmmd deformation path on B200 (BASELINE.json metric).
+
+One step = one pass of the whole hot path (VMD sampling K1 -> bone hierarchy / CCD IK / palette K2 -> morph
+gather + skinning K3) over one batch of (instance, frame) slots of a synthetic PMX/VMD:
+
+  workload C3 (default): 1 M vertices, 1 k bones, 200 vertex morphs; `--frames-per-step` consecutive VMD frames
+                         per step per GPU (the bake pattern of BASELINE configs[2]/[4]); N > 1 shards by frame
+                         range, every rank fully independent ("scaling": "weak").
+  workload C4:           512 instances of the 50 k-vertex model with independent clips, one frame each per
+                         step, instances sharded across ranks ("scaling": "strong").
+  workload C1 / C2:      one 50 k-vertex model (C2 adds SDEF/QDEF tags, UV/group/bone morphs, two CCD IK chains).
+
+`--impl reference` times the reference's own CPU implementation (libmmd, compiled into oracle/_ref; else the
+C restatement) on the host cores for the same workload.
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "skinned_vertex_frames_per_sec"
+UNIT = "vertex-frames/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="mmdgpu", choices=["mmdgpu", "reference"])
+    ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4"])
+    ap.add_argument("--frames-per-step", type=int, default=64, help="C1/C2/C3: VMD frames per step per GPU")
+    ap.add_argument("--instances", type=int, default=512, help="C4: crowd size (whole job)")
+    ap.add_argument("--layout", default="soa", choices=["soa", "sokol32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def algorithmic_bytes_per_vertex(model: dict, layout: str) -> float:
+    """48 B static read + 24 B write + 4 B CSR row pointer + 16 B per morph entry
+    (+8 B uv read +8 B wider record for the interleaved layout)."""
+    e = float(model["n_vertex_morph_entries"]) / max(1, int(model["n_vertices"]))
+    b = 48.0 + 24.0 + 4.0 + 16.0 * e
+    if layout == "sokol32":
+        b += 16.0
+    return b
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy, of measured)"
+    return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+def ncu_traffic_bytes(workload: str):
+    """dram read+write bytes per skin launch from the committed ncu capture, if there is one for this workload."""
+    p = os.path.join(ROOT, "profiles", "skin_dram_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get(workload)
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.proc = None
+        self.path = None
+        sel = str(device_index)
+        try:
+            import torch
+            u = str(torch.cuda.get_device_properties(device_index).uuid)
+            sel = u if u.startswith("GPU-") else "GPU-" + u
+        except Exception:
+            pass
+        self.sel = sel
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.out = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.sel, f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.out, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvidia-smi unavailable"}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.out.close()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for nme, v in zip(names, parts[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "no samples"}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_inputs(args):
+    from simple_mmd_renderer_b200 import synth
+    wl = args.workload
+    cfg = synth.CONFIGS[wl]
+    model = synth.make_model(cfg)
+    return cfg, model
+
+
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_session(model, motion):
+    import oracle
+    if not oracle.have_restatement() or (os.path.isdir("/root/reference") and not oracle.have_reference()):
+        oracle.build()
+    if oracle.have_reference():
+        return oracle.Reference(model, motion), "reference"
+    return oracle.Restatement(model, motion), "port"
+
+
+def frames_for_step(step: int, n: int, clip_len: int) -> np.ndarray:
+    first = (step * n) % max(1, clip_len)
+    return ((first + np.arange(n)) % (clip_len + 1)).astype(np.uint32)
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from simple_mmd_renderer_b200 import synth
+    cfg, model = build_inputs(args)
+    motion = synth.make_motion(cfg, model)
+    ses, kind = cpu_session(model, motion)
+    T = host_threads()
+    nv = int(model["n_vertices"])
+    per_step = 2 * T if nv >= 500_000 else 16 * T
+    times = []
+    for s in range(args.warmup + args.steps):
+        fr = frames_for_step(s, per_step, cfg.n_frames)
+        sec, _ = ses.time_frames(fr, T)
+        if s >= args.warmup:
+            times.append(sec)
+    total = float(sum(times))
+    value = per_step * nv * args.steps / total
+    sample = f"{per_step} frames of {cfg.name} per step on {T} host threads (private Poser per thread, shared Model)"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.workload == "C4" else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": workload_config(args, cfg, model, per_step, "host"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": T, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, cfg, model, slots_per_step, where):
+    e = float(model["n_vertex_morph_entries"]) / max(1, int(model["n_vertices"]))
+    return {
+        "workload": f"{cfg.name}: {cfg.n_vertices} vertices, {cfg.n_bones} bones, {int(model['n_morphs'])} morphs "
+                    f"(e={e:.2f} morph entries/vertex), {cfg.n_frames}-frame VMD, physics off",
+        "slots_per_step_per_gpu": int(slots_per_step), "layout": args.layout, "where": where,
+        "l2": "every step writes its slots' output (>= 1.2 GB at the default C3 size, > 126 MB L2) between "
+              "re-reads of the static streams; no separate flush",
+    }
+
+
+# ------------------------------------------------------------------------------------------ own arm
+def run_mmdgpu(args):
+    import torch
+    import torch.distributed as dist
+    from simple_mmd_renderer_b200 import capi, lib, synth
+    from simple_mmd_renderer_b200.poser import Context, Frames, Model, Motion
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the deformation path has no CPU fallback")
+    if not os.path.exists(lib.SO_PATH):
+        if local == 0:
+            lib.build_library()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+
+    cfg, model = build_inputs(args)
+    nv = int(model["n_vertices"])
+    layout = capi.LAYOUT_SOA_POS_NRM if args.layout == "soa" else capi.LAYOUT_INTERLEAVED_SOKOL32
+    stream = torch.cuda.Stream(device=local)
+    ctx = Context(local, stream.cuda_stream)
+    m = Model(ctx, model)
+    if args.workload == "C4":
+        total_inst = args.instances
+        lo, hi = total_inst * rank // world, total_inst * (rank + 1) // world
+        n_inst, n_frames = hi - lo, 1
+        motions = [Motion(m, synth.make_motion(cfg, model, instance=i)) for i in range(lo, hi)]
+    else:
+        n_inst, n_frames = 1, args.frames_per_step
+        motions = [Motion(m, synth.make_motion(cfg, model))]
+    fr = Frames(m, n_inst, n_frames, layout)
+    slots = n_inst * n_frames
+    rng = np.random.default_rng(1234 + rank)
+
+    def first_frames(step):
+        if args.workload == "C4":
+            return ((step * 3 + rng.integers(0, cfg.n_frames, n_inst)) % (cfg.n_frames + 1)).astype(np.uint32)
+        # bake pattern: rank r owns the r-th range of consecutive frames of this step
+        base = (step * world + rank) * n_frames
+        return np.asarray([base % max(1, cfg.n_frames - n_frames + 1)], np.uint32)
+
+    def step(s):
+        fr.update_range(motions, first_frames(s), 1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput
+    for s in range(args.warmup):
+        step(s)
+    ctx.synchronize()
+    ctx.set_profiling(True)
+    ctx.profile_read()
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for s in range(args.steps):
+        step(args.warmup + s)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = ctx.launch_count - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")
+    kernel_ms, kernel_n = ctx.profile_read()
+    ctx.set_profiling(False)
+    slots_t = torch.tensor([float(slots)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(slots_t, op=dist.ReduceOp.SUM)
+    total_ms = float(ms.item())
+    total_slots = float(slots_t.item())
+    value = total_slots * nv * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the C-ABI with host buffers: frame ids in, deformed vertex buffers out (pinned)
+    e2e = None
+    if not args.no_e2e:
+        stream_ids = [capi.STREAM_POSITION, capi.STREAM_NORMAL] if args.layout == "soa" else [capi.STREAM_INTERLEAVED]
+        per_stream = nv * (12 if args.layout == "soa" else 32) * slots
+        host = [torch.empty(per_stream, dtype=torch.uint8, pin_memory=True) for _ in stream_ids]
+        h2d = 4 * n_inst
+        d2h = per_stream * len(stream_ids)
+
+        def e2e_step(s):
+            fr.update_range(motions, first_frames(s), 1)          # H2D: frame ids (clips / model are resident)
+            for sid, buf in zip(stream_ids, host):
+                fr.download_async(0, slots, sid, buf.data_ptr(), per_stream)
+            ctx.join_downloads()
+
+        e2e_steps = max(3, min(args.steps, 10))
+        for s in range(2):
+            e2e_step(s)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for s in range(e2e_steps):
+            e2e_step(2 + s)
+        a1.record(stream)
+        barrier()
+        ems = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_slots * nv * e2e_steps / (float(ems.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+               "ms_per_step": float(ems.item()) / e2e_steps,
+               "note": "update_range + download of every slot's deformed buffer to pinned host memory, per GPU"}
+
+    # ---- CPU baseline (rank 0, N = 1 only): libmmd itself on a bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        motion0 = synth.make_motion(cfg, model)
+        ses, kind = cpu_session(model, motion0)
+        T = host_threads()
+        nfr = 8 * T if nv >= 500_000 else 64 * T
+        sec, _ = ses.time_frames(frames_for_step(0, nfr, cfg.n_frames), T)
+        cpu = {"value": nfr * nv / sec, "unit": UNIT, "cores": T, "kind": kind,
+               "sample": f"{nfr} frames of {cfg.name} on {T} host threads, {sec:.2f} s wall"}
+
+    if rank == 0:
+        b_alg = algorithmic_bytes_per_vertex(model, args.layout)
+        peak, peak_src = measured_peaks()
+        skin_ms = kernel_ms[2] / max(1, kernel_n[2])
+        achieved = b_alg * nv * slots / (skin_ms * 1e-3) / 1e9 if skin_ms > 0 else 0.0
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.workload == "C4" else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": workload_config(args, cfg, model, slots, "device-resident inputs and outputs"),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": ncu_traffic_bytes(args.workload),
+                         "kernel": "skin_kernel", "algorithmic_bytes_per_vertex": b_alg,
+                         "vertices_per_launch": nv * slots, "avg_launch_ms": skin_ms, "peak_source": peak_src,
+                         "frac_of_nominal_8TBs": achieved / 8000.0},
+            "kernel_ms_per_step": {"pose_sample": kernel_ms[0] / args.steps, "hierarchy": kernel_ms[1] / args.steps,
+                                   "skin": kernel_ms[2] / args.steps},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_mmdgpu(args)
+
+
+if __name__ == "__main__":
+    main()

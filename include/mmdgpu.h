@@ -230,6 +230,22 @@ MMDGPU_API void*         mmdgpu_context_stream(mmdgpu_context_t ctx);
 /* Number of kernels this context has launched since creation (bench "gpu_launches"). */
 MMDGPU_API uint64_t      mmdgpu_context_launch_count(mmdgpu_context_t ctx);
 
+/* Device timing of this context's own kernels: when enabled, every launch is bracketed by CUDA events on the
+ * context's stream.  profile_read synchronises the stream, returns the summed device milliseconds and the
+ * launch count per kernel since the last read, and resets both. */
+typedef enum mmdgpu_kernel_id {
+    MMDGPU_KERNEL_POSE_SAMPLE = 0, /* K1: VMD key-frame sampling                      */
+    MMDGPU_KERNEL_HIERARCHY   = 1, /* K2: morph rates, bone program, CCD IK, palette  */
+    MMDGPU_KERNEL_SKIN        = 2, /* K3: morph gather + skinning                     */
+    MMDGPU_KERNEL_COUNT       = 3
+} mmdgpu_kernel_id;
+MMDGPU_API mmdgpu_status mmdgpu_context_set_profiling(mmdgpu_context_t ctx, int enabled);
+MMDGPU_API mmdgpu_status mmdgpu_context_profile_read(mmdgpu_context_t ctx, double ms_total[MMDGPU_KERNEL_COUNT],
+                                                     uint64_t launches[MMDGPU_KERNEL_COUNT]);
+/* Make the context's compute stream wait for every asynchronous download issued so far, so that an event
+ * recorded on the compute stream afterwards covers them (end-to-end timing). */
+MMDGPU_API mmdgpu_status mmdgpu_context_join_downloads(mmdgpu_context_t ctx);
+
 /* ------------------------------------------------------------------ models */
 
 /* Replaces: PmxReader::ReadModel's result + Model::Normalize (L/model/model_impl.inl:406-452)

@@ -102,6 +102,7 @@ struct Plan {
 
     // names (only for models parsed from PMX bytes)
     std::vector<std::string> bone_names, morph_names;
+    bool names_utf8 = false;  // PMX text encoding flag: UTF-8, else UTF-16LE
 
     // scratch for mmdgpu_plan_get
     std::vector<uint8_t> op_kind_u8, ik_fix_u8, ik_order_u8;

@@ -1,0 +1,960 @@
+// mmdgpu_api.cu — the C-ABI of include/mmdgpu.h: handles, uploads, launches, downloads.
+//
+// There is no CPU path in this file: every entry point that produces poses, matrices or vertices launches
+// the sm_100a kernels of kernels.cu; when CUDA is unavailable the call returns MMDGPU_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/mmdgpu.h"
+#include "device_types.cuh"
+#include "host_plan.hpp"
+#include "kernels.cuh"
+
+using namespace mmdgpu;
+
+// ------------------------------------------------------------------------------------------- handles
+struct mmdgpu_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t dl_stream = nullptr;
+    cudaEvent_t dl_event = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    int max_smem_optin = 0;
+    int sm_count = 0;
+    // optional per-kernel device timing
+    bool profiling = false;
+    struct Span { int id; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
+};
+
+struct mmdgpu_plan {
+    Plan plan;
+};
+
+namespace {
+
+// Owns device allocations of one handle.
+struct DevArena {
+    std::vector<void*> ptrs;
+    ~DevArena() { release(); }
+    void release() {
+        for (void* p : ptrs) cudaFree(p);
+        ptrs.clear();
+    }
+    cudaError_t alloc(void** out, size_t bytes) {
+        *out = nullptr;
+        cudaError_t e = cudaMalloc(out, bytes ? bytes : 16);
+        if (e == cudaSuccess) ptrs.push_back(*out);
+        return e;
+    }
+};
+
+thread_local std::string g_err;  // errors of calls that have no context to attach them to
+
+}  // namespace
+
+struct mmdgpu_model {
+    mmdgpu_context_t ctx = nullptr;
+    mmdgpu_plan plan;
+    DevModel dev{};
+    DevArena mem;
+    uint32_t skin_tiles_per_cta = 1;
+};
+
+struct mmdgpu_animation {
+    mmdgpu_context_t ctx = nullptr;
+    mmdgpu_model_t model = nullptr;
+    HostAnim host;
+    DevAnim dev{};
+    DevArena mem;
+};
+
+struct mmdgpu_frames {
+    mmdgpu_context_t ctx = nullptr;
+    mmdgpu_model_t model = nullptr;
+    mmdgpu_layout layout = MMDGPU_LAYOUT_SOA_POS_NRM;
+    DevFrames dev{};
+    DevArena mem;
+    DevAnim* d_anims = nullptr;                 // [n_instances]
+    std::vector<mmdgpu_animation_t> bound;      // what d_anims currently holds
+    std::vector<DevAnim> h_anims;
+    bool range_mode = false;
+    uint32_t frame_stride = 1;
+    uint32_t tiles_per_cta = 1;
+};
+
+namespace {
+
+mmdgpu_status set_err(mmdgpu_context_t ctx, mmdgpu_status s, const std::string& msg) {
+    if (ctx) ctx->err = msg; else g_err = msg;
+    return s;
+}
+mmdgpu_status cuda_fail(mmdgpu_context_t ctx, cudaError_t e, const char* what) {
+    const mmdgpu_status s = (e == cudaErrorMemoryAllocation) ? MMDGPU_ERR_OOM : MMDGPU_ERR_CUDA;
+    return set_err(ctx, s, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CU(ctx, call)                                             \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+template <class T>
+cudaError_t upload(mmdgpu_context_t ctx, DevArena& mem, const T* src, size_t n, const T** out) {
+    void* d = nullptr;
+    cudaError_t e = mem.alloc(&d, n * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (n) e = cudaMemcpyAsync(d, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+    *out = static_cast<const T*>(d);
+    return e;
+}
+template <class T>
+cudaError_t upload(mmdgpu_context_t ctx, DevArena& mem, const std::vector<T>& v, const T** out) {
+    return upload(ctx, mem, v.data(), v.size(), out);
+}
+template <class T>
+cudaError_t dalloc(DevArena& mem, T** out, size_t n, bool zero, cudaStream_t st) {
+    void* d = nullptr;
+    cudaError_t e = mem.alloc(&d, n * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (zero && n) e = cudaMemsetAsync(d, 0, n * sizeof(T), st);
+    *out = static_cast<T*>(d);
+    return e;
+}
+
+uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
+
+// Choose how many 1024-vertex tiles one CTA walks: enough CTAs to fill the machine a few times over, few
+// enough that restaging the palette (nb x 48 B per CTA) stays a small fraction of the streamed bytes.
+uint32_t choose_tiles_per_cta(uint32_t tiles, uint32_t n_slots, uint32_t nb, int sm_count) {
+    if (tiles == 0) return 1;
+    const uint64_t total = uint64_t(tiles) * n_slots;
+    const uint64_t target_ctas = uint64_t(sm_count > 0 ? sm_count : 148) * 16;
+    uint32_t t = uint32_t(std::max<uint64_t>(1, total / target_ctas));
+    // palette bytes per CTA <= ~6 % of the stream bytes (76 KB per tile)
+    const uint32_t min_t = std::max<uint32_t>(1, (nb * 48u * 16u + 76u * 1024u - 1) / (76u * 1024u));
+    t = std::max(t, std::min(min_t, tiles));
+    t = std::min(t, tiles);
+    // balance: equal-sized chunks
+    const uint32_t chunks = (tiles + t - 1) / t;
+    return (tiles + chunks - 1) / chunks;
+}
+
+mmdgpu_status upload_model(mmdgpu_model* m) {
+    mmdgpu_context_t ctx = m->ctx;
+    const Plan& p = m->plan.plan;
+    DevModel& D = m->dev;
+    D = DevModel{};
+    const uint32_t nv = p.nv, nb = p.nb;
+    const uint32_t nvp = round_up(nv, kTileVerts);
+    D.nv = nv; D.nv_pad = nvp; D.nb = nb; D.nm = p.nm;
+    D.n_nodes = uint32_t(p.node_morph.size());
+    D.n_nodes_pad = round_up(D.n_nodes, 4);
+
+    // ---- vertex streams, structure of arrays, padded to a whole tile
+    std::vector<float> plane[6];
+    for (auto& v : plane) v.assign(nvp, 0.0f);
+    std::vector<uint2> ids(nvp, make_uint2(0, 0));
+    std::vector<float4> wts(nvp, make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<float2> uv(nvp, make_float2(0.f, 0.f));
+    for (uint32_t i = 0; i < nv; ++i) {
+        for (int k = 0; k < 3; ++k) {
+            plane[k][i] = p.position[size_t(i) * 3 + k];
+            plane[3 + k][i] = p.normal[size_t(i) * 3 + k];
+        }
+        const uint16_t* id = &p.bone_id[size_t(i) * 4];
+        ids[i].x = uint32_t(id[0]) | (uint32_t(p.dev_type[i]) << 13) | (uint32_t(id[1]) << 16);
+        ids[i].y = uint32_t(id[2]) | (uint32_t(id[3]) << 16);
+        const float* w = &p.weight[size_t(i) * 4];
+        wts[i] = make_float4(w[0], w[1], w[2], w[3]);
+        uv[i] = make_float2(p.uv[size_t(i) * 2], p.uv[size_t(i) * 2 + 1]);
+    }
+    CU(ctx, upload(ctx, m->mem, plane[0], &D.px)); CU(ctx, upload(ctx, m->mem, plane[1], &D.py));
+    CU(ctx, upload(ctx, m->mem, plane[2], &D.pz)); CU(ctx, upload(ctx, m->mem, plane[3], &D.nx));
+    CU(ctx, upload(ctx, m->mem, plane[4], &D.ny)); CU(ctx, upload(ctx, m->mem, plane[5], &D.nz));
+    CU(ctx, upload(ctx, m->mem, ids, &D.ids));
+    CU(ctx, upload(ctx, m->mem, wts, &D.weights));
+    CU(ctx, upload(ctx, m->mem, uv, &D.uv));
+    // ---- morph CSR (rows padded: the padded vertices own no entries)
+    std::vector<uint32_t> row(size_t(nvp) + 4, 0);
+    for (uint32_t i = 0; i <= nv; ++i) row[i] = p.csr_row[i];
+    for (size_t i = size_t(nv) + 1; i < row.size(); ++i) row[i] = p.csr_row[nv];
+    std::vector<float4> ent(p.csr_node.size());
+    for (size_t e = 0; e < ent.size(); ++e) {
+        float slot_bits;
+        const uint32_t node = p.csr_node[e];
+        std::memcpy(&slot_bits, &node, 4);
+        ent[e] = make_float4(p.csr_offset[3 * e], p.csr_offset[3 * e + 1], p.csr_offset[3 * e + 2], slot_bits);
+    }
+    CU(ctx, upload(ctx, m->mem, row, &D.csr_row));
+    CU(ctx, upload(ctx, m->mem, ent, &D.csr_ent));
+    // ---- bones and the program
+    static_assert(sizeof(BoneStatic) == 48, "BoneStatic is read as three float4");
+    CU(ctx, upload(ctx, m->mem, p.bones, &D.bones));
+    CU(ctx, upload(ctx, m->mem, p.iks, &D.iks));
+    CU(ctx, upload(ctx, m->mem, p.links, &D.links));
+    CU(ctx, upload(ctx, m->mem, p.reset_bones, &D.reset_bones));
+    D.n_reset = uint32_t(p.reset_bones.size());
+    D.n_link_slots = uint32_t(p.link_bones.size());
+    D.n_morph_slots = uint32_t(p.morph_bones.size());
+    std::vector<uint32_t> wb(p.wave_begin.begin(), p.wave_begin.end());
+    std::vector<uint32_t> words(p.wave_ops.size());
+    for (size_t i = 0; i < words.size(); ++i) {
+        const Op& o = p.ops[size_t(p.wave_ops[i])];
+        words[i] = (uint32_t(o.kind) << 28) | (uint32_t(o.arg) & 0x0FFFFFFFu);
+    }
+    CU(ctx, upload(ctx, m->mem, wb, &D.wave_begin));
+    CU(ctx, upload(ctx, m->mem, words, &D.wave_ops));
+    D.n_waves = uint32_t(p.wave_begin.size() - 1);
+    D.phase_split = uint32_t(p.phase_split);
+    CU(ctx, upload(ctx, m->mem, p.node_morph, &D.node_morph));
+    CU(ctx, upload(ctx, m->mem, p.node_parent, &D.node_parent));
+    CU(ctx, upload(ctx, m->mem, p.node_mult, &D.node_mult));
+    CU(ctx, upload(ctx, m->mem, p.nodes_by_depth, &D.nodes_by_depth));
+    CU(ctx, upload(ctx, m->mem, p.depth_begin, &D.depth_begin));
+    D.n_depths = p.depth_begin.empty() ? 0u : uint32_t(p.depth_begin.size() - 1);
+    CU(ctx, upload(ctx, m->mem, p.morph_bones, &D.morph_bones));
+    CU(ctx, upload(ctx, m->mem, p.bone_morph_row, &D.bone_morph_row));
+    CU(ctx, upload(ctx, m->mem, p.bone_morph_entries, &D.bone_morph_entries));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));  // the staging vectors above die with this frame
+
+    const size_t smem = skin_smem_bytes(D);
+    if (smem + 1024 > size_t(ctx->max_smem_optin))
+        return set_err(ctx, MMDGPU_ERR_UNSUPPORTED,
+                       "bone palette + morph slot rates (" + std::to_string(smem) + " B) exceed shared memory per CTA");
+    CU(ctx, prepare_skin_kernels(smem));
+    return MMDGPU_OK;
+}
+
+mmdgpu_status upload_anim(mmdgpu_animation* a) {
+    mmdgpu_context_t ctx = a->ctx;
+    const HostAnim& h = a->host;
+    DevAnim& D = a->dev;
+    D = DevAnim{};
+    CU(ctx, upload(ctx, a->mem, h.bone_key_begin, &D.bone_key_begin));
+    CU(ctx, upload(ctx, a->mem, h.bone_key_count, &D.bone_key_count));
+    CU(ctx, upload(ctx, a->mem, h.bone_tracked, &D.bone_tracked));
+    CU(ctx, upload(ctx, a->mem, h.key_frame, &D.key_frame));
+    CU(ctx, upload(ctx, a->mem, reinterpret_cast<const float4*>(h.key_T.data()), h.key_T.size() / 4, &D.key_T));
+    CU(ctx, upload(ctx, a->mem, reinterpret_cast<const float4*>(h.key_R.data()), h.key_R.size() / 4, &D.key_R));
+    CU(ctx, upload(ctx, a->mem, reinterpret_cast<const uint4*>(h.key_curve.data()), h.key_curve.size() / 4, &D.key_curve));
+    CU(ctx, upload(ctx, a->mem, h.tables, &D.tables));
+    CU(ctx, upload(ctx, a->mem, h.morph_key_begin, &D.morph_key_begin));
+    CU(ctx, upload(ctx, a->mem, h.morph_key_count, &D.morph_key_count));
+    CU(ctx, upload(ctx, a->mem, h.morph_tracked, &D.morph_tracked));
+    CU(ctx, upload(ctx, a->mem, h.mkey_frame, &D.mkey_frame));
+    CU(ctx, upload(ctx, a->mem, h.mkey_weight, &D.mkey_weight));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return MMDGPU_OK;
+}
+
+mmdgpu_status bind_anims(mmdgpu_frames* f, const mmdgpu_animation_t* per_instance) {
+    mmdgpu_context_t ctx = f->ctx;
+    const uint32_t ni = f->dev.n_instances;
+    if (!per_instance) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "per_instance animation array is NULL");
+    bool same = f->bound.size() == ni;
+    for (uint32_t i = 0; i < ni; ++i) {
+        if (!per_instance[i]) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "animation handle is NULL");
+        if (per_instance[i]->model != f->model)
+            return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "animation was created for a different model");
+        if (same && f->bound[i] != per_instance[i]) same = false;
+    }
+    if (same) return MMDGPU_OK;
+    // the previous upload may still be in flight from pageable memory semantics' point of view: cudaMemcpyAsync
+    // from pageable memory returns after staging, so h_anims may be rewritten immediately.
+    f->h_anims.resize(ni);
+    for (uint32_t i = 0; i < ni; ++i) f->h_anims[i] = per_instance[i]->dev;
+    CU(ctx, cudaMemcpyAsync(f->d_anims, f->h_anims.data(), sizeof(DevAnim) * ni, cudaMemcpyHostToDevice, ctx->stream));
+    f->bound.assign(per_instance, per_instance + ni);
+    return MMDGPU_OK;
+}
+
+// Brackets one launch with events when profiling is on.
+struct Timed {
+    mmdgpu_context_t ctx;
+    cudaEvent_t b = nullptr;
+    Timed(mmdgpu_context_t c, int id) : ctx(c) {
+        if (!c->profiling) return;
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        for (auto& e : ev) {
+            if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); }
+            else if (cudaEventCreate(&e) != cudaSuccess) return;
+        }
+        cudaEventRecord(ev[0], c->stream);
+        b = ev[1];
+        c->spans.push_back({id, ev[0], ev[1]});
+    }
+    ~Timed() {
+        if (b) cudaEventRecord(b, ctx->stream);
+        ctx->launches++;
+    }
+};
+
+mmdgpu_status enter(mmdgpu_context_t ctx) {
+    if (!ctx) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "context is NULL");
+    CU(ctx, cudaSetDevice(ctx->device));
+    return MMDGPU_OK;
+}
+
+mmdgpu_status do_seek(mmdgpu_frames* f, const mmdgpu_animation_t* per_instance, const uint32_t* frames, bool range,
+                      uint32_t stride, bool write_untracked) {
+    mmdgpu_context_t ctx = f->ctx;
+    if (!frames) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "frame id array is NULL");
+    if (mmdgpu_status s = bind_anims(f, per_instance)) return s;
+    const uint32_t n = range ? f->dev.n_instances : f->dev.n_slots;
+    CU(ctx, cudaMemcpyAsync(f->dev.frame_id, frames, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    f->range_mode = range;
+    f->frame_stride = stride;
+    {
+        Timed t(ctx, MMDGPU_KERNEL_POSE_SAMPLE);
+        CU(ctx, launch_pose_sample(ctx->stream, f->model->dev, f->d_anims, f->dev, write_untracked, range, stride));
+    }
+    return MMDGPU_OK;
+}
+
+mmdgpu_status do_hierarchy(mmdgpu_frames* f, uint32_t lo, uint32_t hi, bool prologue) {
+    mmdgpu_context_t ctx = f->ctx;
+    {
+        Timed t(ctx, MMDGPU_KERNEL_HIERARCHY);
+        CU(ctx, launch_hierarchy(ctx->stream, f->model->dev, f->dev, lo, hi, prologue));
+    }
+    return MMDGPU_OK;
+}
+
+mmdgpu_status do_skin(mmdgpu_frames* f) {
+    mmdgpu_context_t ctx = f->ctx;
+    if (f->model->dev.nv_pad == 0) return MMDGPU_OK;
+    {
+        Timed t(ctx, MMDGPU_KERNEL_SKIN);
+        CU(ctx, launch_skin(ctx->stream, f->model->dev, f->dev, int(f->layout), f->tiles_per_cta));
+    }
+    return MMDGPU_OK;
+}
+
+struct StreamView {
+    const char* base;
+    size_t slot_stride, slot_bytes;
+};
+mmdgpu_status stream_view(mmdgpu_frames* f, mmdgpu_stream_id id, StreamView& v) {
+    const DevModel& M = f->model->dev;
+    switch (id) {
+    case MMDGPU_STREAM_POSITION:
+    case MMDGPU_STREAM_NORMAL:
+        if (f->layout != MMDGPU_LAYOUT_SOA_POS_NRM)
+            return set_err(f->ctx, MMDGPU_ERR_INVALID_ARG, "frames were created with the interleaved layout");
+        v.base = reinterpret_cast<const char*>(id == MMDGPU_STREAM_POSITION ? f->dev.out_pos : f->dev.out_nrm);
+        v.slot_stride = size_t(M.nv_pad) * 12;
+        v.slot_bytes = size_t(M.nv) * 12;
+        return MMDGPU_OK;
+    case MMDGPU_STREAM_INTERLEAVED:
+        if (f->layout != MMDGPU_LAYOUT_INTERLEAVED_SOKOL32)
+            return set_err(f->ctx, MMDGPU_ERR_INVALID_ARG, "frames were created with the SoA layout");
+        v.base = reinterpret_cast<const char*>(f->dev.out_inter);
+        v.slot_stride = size_t(M.nv_pad) * 32;
+        v.slot_bytes = size_t(M.nv) * 32;
+        return MMDGPU_OK;
+    case MMDGPU_STREAM_SKIN_MATRIX:
+        v.base = reinterpret_cast<const char*>(f->dev.palette);
+        v.slot_stride = v.slot_bytes = size_t(M.nb) * 48;
+        return MMDGPU_OK;
+    }
+    return set_err(f->ctx, MMDGPU_ERR_INVALID_ARG, "unknown stream id");
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------- basics
+extern "C" {
+
+MMDGPU_API int mmdgpu_version(void) { return MMDGPU_VERSION_MAJOR * 100 + MMDGPU_VERSION_MINOR; }
+
+MMDGPU_API const char* mmdgpu_status_string(mmdgpu_status s) {
+    switch (s) {
+    case MMDGPU_OK: return "ok";
+    case MMDGPU_ERR_INVALID_ARG: return "invalid argument";
+    case MMDGPU_ERR_BAD_INDEX: return "index out of range";
+    case MMDGPU_ERR_UNSUPPORTED: return "unsupported";
+    case MMDGPU_ERR_CUDA: return "CUDA error";
+    case MMDGPU_ERR_OOM: return "out of memory";
+    case MMDGPU_ERR_PARSE: return "malformed PMX/VMD data";
+    }
+    return "unknown status";
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_context_create(int device, void* cuda_stream_or_null, mmdgpu_context_t* out) {
+    if (!out) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceCount");
+    if (count == 0) return set_err(nullptr, MMDGPU_ERR_CUDA, "no CUDA device");
+    if (device < 0 || device >= count) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "device ordinal out of range");
+    std::unique_ptr<mmdgpu_context> c(new (std::nothrow) mmdgpu_context());
+    if (!c) return set_err(nullptr, MMDGPU_ERR_OOM, "host allocation failed");
+    c->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+    cudaDeviceProp prop{};
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major < 10)
+        return set_err(nullptr, MMDGPU_ERR_UNSUPPORTED, "this library is built for sm_100a only; device is sm_" +
+                                                            std::to_string(prop.major) + std::to_string(prop.minor));
+    c->max_smem_optin = int(prop.sharedMemPerBlockOptin);
+    c->sm_count = prop.multiProcessorCount;
+    if (cuda_stream_or_null) c->stream = static_cast<cudaStream_t>(cuda_stream_or_null);
+    else {
+        if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess)
+            return cuda_fail(nullptr, e, "cudaStreamCreate");
+        c->own_stream = true;
+    }
+    if ((e = cudaStreamCreateWithFlags(&c->dl_stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return cuda_fail(nullptr, e, "cudaStreamCreate");
+    if ((e = cudaEventCreateWithFlags(&c->dl_event, cudaEventDisableTiming)) != cudaSuccess)
+        return cuda_fail(nullptr, e, "cudaEventCreate");
+    *out = c.release();
+    return MMDGPU_OK;
+}
+
+MMDGPU_API void mmdgpu_context_destroy(mmdgpu_context_t ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->dl_stream) { cudaStreamSynchronize(ctx->dl_stream); cudaStreamDestroy(ctx->dl_stream); }
+    if (ctx->dl_event) cudaEventDestroy(ctx->dl_event);
+    for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+MMDGPU_API const char* mmdgpu_last_error(mmdgpu_context_t ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+MMDGPU_API mmdgpu_status mmdgpu_context_synchronize(mmdgpu_context_t ctx) {
+    if (mmdgpu_status s = enter(ctx)) return s;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->dl_stream));
+    return MMDGPU_OK;
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_context_set_profiling(mmdgpu_context_t ctx, int enabled) {
+    if (mmdgpu_status s = enter(ctx)) return s;
+    ctx->profiling = enabled != 0;
+    return MMDGPU_OK;
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_context_profile_read(mmdgpu_context_t ctx, double ms_total[MMDGPU_KERNEL_COUNT],
+                                                     uint64_t launches[MMDGPU_KERNEL_COUNT]) {
+    if (mmdgpu_status s = enter(ctx)) return s;
+    if (!ms_total || !launches) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "NULL argument");
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < MMDGPU_KERNEL_COUNT; ++i) { ms_total[i] = 0.0; launches[i] = 0; }
+    for (const auto& sp : ctx->spans) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess && sp.id >= 0 && sp.id < MMDGPU_KERNEL_COUNT) {
+            ms_total[sp.id] += double(ms);
+            launches[sp.id]++;
+        }
+        ctx->event_pool.push_back(sp.a);
+        ctx->event_pool.push_back(sp.b);
+    }
+    ctx->spans.clear();
+    return MMDGPU_OK;
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_context_join_downloads(mmdgpu_context_t ctx) {
+    if (mmdgpu_status s = enter(ctx)) return s;
+    CU(ctx, cudaEventRecord(ctx->dl_event, ctx->dl_stream));
+    CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->dl_event, 0));
+    return MMDGPU_OK;
+}
+
+MMDGPU_API void* mmdgpu_context_stream(mmdgpu_context_t ctx) { return ctx ? ctx->stream : nullptr; }
+MMDGPU_API uint64_t mmdgpu_context_launch_count(mmdgpu_context_t ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------- plan
+MMDGPU_API mmdgpu_status mmdgpu_plan_create(const mmdgpu_model_desc* desc, const mmdgpu_options* opt, mmdgpu_plan_t* out,
+                                            char* err_buf, size_t err_buf_len) {
+    auto report = [&](const std::string& m) {
+        g_err = m;
+        if (err_buf && err_buf_len) std::snprintf(err_buf, err_buf_len, "%s", m.c_str());
+    };
+    if (!desc || !out) { report("desc or out is NULL"); return MMDGPU_ERR_INVALID_ARG; }
+    *out = nullptr;
+    std::unique_ptr<mmdgpu_plan> p(new (std::nothrow) mmdgpu_plan());
+    if (!p) { report("host allocation failed"); return MMDGPU_ERR_OOM; }
+    std::string err;
+    mmdgpu_status s;
+    try {
+        s = build_plan(*desc, opt, p->plan, err);
+    } catch (const std::bad_alloc&) {
+        s = MMDGPU_ERR_OOM; err = "host allocation failed";
+    }
+    if (s != MMDGPU_OK) { report(err); return s; }
+    *out = p.release();
+    return MMDGPU_OK;
+}
+
+MMDGPU_API void mmdgpu_plan_destroy(mmdgpu_plan_t plan) { delete plan; }
+
+MMDGPU_API mmdgpu_status mmdgpu_plan_get(mmdgpu_plan_t plan, mmdgpu_plan_array which, const void** data, size_t* count) {
+    if (!plan || !data || !count) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "NULL argument");
+    const Plan& p = plan->plan;
+#define RET(vec)                \
+    do {                        \
+        *data = (vec).data();   \
+        *count = (vec).size();  \
+        return MMDGPU_OK;       \
+    } while (0)
+    switch (which) {
+    case MMDGPU_PLAN_SKIN_TYPE: RET(p.norm_type);
+    case MMDGPU_PLAN_BONE_ID: RET(p.bone_id);
+    case MMDGPU_PLAN_WEIGHT: RET(p.weight);
+    case MMDGPU_PLAN_ORDER_PRE: RET(p.order_pre);
+    case MMDGPU_PLAN_ORDER_POST: RET(p.order_post);
+    case MMDGPU_PLAN_OP_KIND: RET(p.op_kind_u8);
+    case MMDGPU_PLAN_OP_BONE: RET(p.op_arg_i32);
+    case MMDGPU_PLAN_OP_WAVE: RET(p.op_wave);
+    case MMDGPU_PLAN_WAVE_BEGIN: RET(p.wave_begin);
+    case MMDGPU_PLAN_WAVE_OPS: RET(p.wave_ops);
+    case MMDGPU_PLAN_IK_FIX_TYPE: RET(p.ik_fix_u8);
+    case MMDGPU_PLAN_IK_EULER_ORDER: RET(p.ik_order_u8);
+    case MMDGPU_PLAN_APP_SLOT_MORPH: RET(p.node_morph);
+    case MMDGPU_PLAN_APP_SLOT_PARENT: RET(p.node_parent);
+    case MMDGPU_PLAN_APP_SLOT_MULT: RET(p.node_mult);
+    case MMDGPU_PLAN_CSR_ROW_PTR: RET(p.csr_row);
+    case MMDGPU_PLAN_CSR_SLOT: RET(p.csr_node);
+    case MMDGPU_PLAN_CSR_OFFSET: RET(p.csr_offset);
+    case MMDGPU_PLAN_WAVE_PHASE_SPLIT: RET(p.phase_split_i32);
+    default: break;
+    }
+#undef RET
+    return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "unknown plan array");
+}
+
+MMDGPU_API int mmdgpu_bezier_table(const int8_t ctrl[4], float table[32]) { return bezier_table(ctrl, table) ? 1 : 0; }
+
+// ------------------------------------------------------------------------------------------- model
+MMDGPU_API mmdgpu_status mmdgpu_model_create_from_arrays(mmdgpu_context_t ctx, const mmdgpu_model_desc* desc,
+                                                         const mmdgpu_options* opt, mmdgpu_model_t* out) {
+    if (mmdgpu_status s = enter(ctx)) return s;
+    if (!desc || !out) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "desc or out is NULL");
+    *out = nullptr;
+    std::unique_ptr<mmdgpu_model> m(new (std::nothrow) mmdgpu_model());
+    if (!m) return set_err(ctx, MMDGPU_ERR_OOM, "host allocation failed");
+    m->ctx = ctx;
+    std::string err;
+    mmdgpu_status s;
+    try {
+        s = build_plan(*desc, opt, m->plan.plan, err);
+        if (s != MMDGPU_OK) return set_err(ctx, s, err);
+        s = upload_model(m.get());
+    } catch (const std::bad_alloc&) {
+        return set_err(ctx, MMDGPU_ERR_OOM, "host allocation failed");
+    }
+    if (s != MMDGPU_OK) return s;
+    *out = m.release();
+    return MMDGPU_OK;
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_model_create_from_pmx(mmdgpu_context_t ctx, const void* bytes, size_t n,
+                                                      const mmdgpu_options* opt, mmdgpu_model_t* out) {
+    if (mmdgpu_status s = enter(ctx)) return s;
+    if (!bytes || !out) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "bytes or out is NULL");
+    *out = nullptr;
+    ParsedModel pm;
+    std::string err;
+    mmdgpu_status s;
+    try {
+        s = parse_pmx(bytes, n, pm, err);
+    } catch (const std::bad_alloc&) {
+        return set_err(ctx, MMDGPU_ERR_OOM, "host allocation failed");
+    }
+    if (s != MMDGPU_OK) return set_err(ctx, s, err);
+    s = mmdgpu_model_create_from_arrays(ctx, &pm.desc, opt, out);
+    if (s != MMDGPU_OK) return s;
+    (*out)->plan.plan.bone_names = std::move(pm.bone_names);
+    (*out)->plan.plan.morph_names = std::move(pm.morph_names);
+    (*out)->plan.plan.names_utf8 = pm.utf8;
+    return MMDGPU_OK;
+}
+
+MMDGPU_API void mmdgpu_model_destroy(mmdgpu_model_t model) {
+    if (!model) return;
+    cudaSetDevice(model->ctx->device);
+    cudaStreamSynchronize(model->ctx->stream);
+    delete model;
+}
+MMDGPU_API uint32_t mmdgpu_model_vertex_count(mmdgpu_model_t m) { return m ? m->plan.plan.nv : 0; }
+MMDGPU_API uint32_t mmdgpu_model_bone_count(mmdgpu_model_t m) { return m ? m->plan.plan.nb : 0; }
+MMDGPU_API uint32_t mmdgpu_model_morph_count(mmdgpu_model_t m) { return m ? m->plan.plan.nm : 0; }
+MMDGPU_API mmdgpu_plan_t mmdgpu_model_plan(mmdgpu_model_t m) { return m ? &m->plan : nullptr; }
+
+static int32_t find_name(const std::vector<std::string>& names, const void* bytes, size_t n) {
+    if (!bytes) return -1;
+    const std::string key(static_cast<const char*>(bytes), n);
+    for (size_t i = 0; i < names.size(); ++i)
+        if (names[i] == key) return int32_t(i);
+    return -1;
+}
+MMDGPU_API int32_t mmdgpu_model_find_bone(mmdgpu_model_t m, const void* name_bytes, size_t n) {
+    return m ? find_name(m->plan.plan.bone_names, name_bytes, n) : -1;
+}
+MMDGPU_API int32_t mmdgpu_model_find_morph(mmdgpu_model_t m, const void* name_bytes, size_t n) {
+    return m ? find_name(m->plan.plan.morph_names, name_bytes, n) : -1;
+}
+
+// ------------------------------------------------------------------------------------------- animation
+MMDGPU_API mmdgpu_status mmdgpu_animation_create_from_arrays(mmdgpu_context_t ctx, mmdgpu_model_t model,
+                                                             const mmdgpu_anim_desc* desc, mmdgpu_animation_t* out) {
+    if (mmdgpu_status s = enter(ctx)) return s;
+    if (!model || !desc || !out) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "model, desc or out is NULL");
+    if (model->ctx != ctx) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "model belongs to a different context");
+    *out = nullptr;
+    std::unique_ptr<mmdgpu_animation> a(new (std::nothrow) mmdgpu_animation());
+    if (!a) return set_err(ctx, MMDGPU_ERR_OOM, "host allocation failed");
+    a->ctx = ctx;
+    a->model = model;
+    std::string err;
+    mmdgpu_status s;
+    try {
+        s = build_anim(*desc, model->plan.plan.nb, model->plan.plan.nm, a->host, err);
+        if (s != MMDGPU_OK) return set_err(ctx, s, err);
+        s = upload_anim(a.get());
+    } catch (const std::bad_alloc&) {
+        return set_err(ctx, MMDGPU_ERR_OOM, "host allocation failed");
+    }
+    if (s != MMDGPU_OK) return s;
+    *out = a.release();
+    return MMDGPU_OK;
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_animation_create_from_vmd(mmdgpu_context_t ctx, mmdgpu_model_t model, const void* bytes,
+                                                          size_t n, mmdgpu_animation_t* out) {
+    if (mmdgpu_status s = enter(ctx)) return s;
+    if (!model || !bytes || !out) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "model, bytes or out is NULL");
+    *out = nullptr;
+    ParsedMotion pm;
+    std::string err;
+    mmdgpu_status s;
+    try {
+        s = parse_vmd(bytes, n, model->plan.plan, pm, err);
+    } catch (const std::bad_alloc&) {
+        return set_err(ctx, MMDGPU_ERR_OOM, "host allocation failed");
+    }
+    if (s != MMDGPU_OK) return set_err(ctx, s, err);
+    return mmdgpu_animation_create_from_arrays(ctx, model, &pm.desc, out);
+}
+
+MMDGPU_API void mmdgpu_animation_destroy(mmdgpu_animation_t a) {
+    if (!a) return;
+    cudaSetDevice(a->ctx->device);
+    cudaStreamSynchronize(a->ctx->stream);
+    delete a;
+}
+MMDGPU_API uint32_t mmdgpu_animation_length(mmdgpu_animation_t a) { return a ? a->host.length : 0; }
+
+// ------------------------------------------------------------------------------------------- frames
+MMDGPU_API mmdgpu_status mmdgpu_frames_create(mmdgpu_context_t ctx, mmdgpu_model_t model, uint32_t n_instances,
+                                              uint32_t n_frames, mmdgpu_layout layout, mmdgpu_frames_t* out) {
+    if (mmdgpu_status s = enter(ctx)) return s;
+    if (!model || !out) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "model or out is NULL");
+    if (model->ctx != ctx) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "model belongs to a different context");
+    if (n_instances == 0 || n_frames == 0) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "n_instances and n_frames must be > 0");
+    if (uint64_t(n_instances) * n_frames > 65535u)
+        return set_err(ctx, MMDGPU_ERR_UNSUPPORTED, "more than 65535 slots in one frames object (grid.y limit)");
+    if (layout != MMDGPU_LAYOUT_SOA_POS_NRM && layout != MMDGPU_LAYOUT_INTERLEAVED_SOKOL32)
+        return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "unknown layout");
+    *out = nullptr;
+    std::unique_ptr<mmdgpu_frames> f(new (std::nothrow) mmdgpu_frames());
+    if (!f) return set_err(ctx, MMDGPU_ERR_OOM, "host allocation failed");
+    f->ctx = ctx;
+    f->model = model;
+    f->layout = layout;
+    const DevModel& M = model->dev;
+    DevFrames& F = f->dev;
+    const size_t ns = size_t(n_instances) * n_frames;
+    F.n_slots = uint32_t(ns); F.n_instances = n_instances; F.n_frames = n_frames;
+    cudaStream_t st = ctx->stream;
+    CU(ctx, dalloc(f->mem, &F.poseR, ns * M.nb, false, st));
+    CU(ctx, dalloc(f->mem, &F.poseT, ns * M.nb, false, st));
+    CU(ctx, dalloc(f->mem, &F.rate, ns * M.nm, true, st));
+    CU(ctx, dalloc(f->mem, &F.node_rate, ns * M.n_nodes_pad, true, st));
+    CU(ctx, dalloc(f->mem, &F.totR, ns * M.nb, true, st));
+    CU(ctx, dalloc(f->mem, &F.totT, ns * M.nb, true, st));
+    CU(ctx, dalloc(f->mem, &F.local, ns * M.nb * 12, true, st));
+    CU(ctx, dalloc(f->mem, &F.ikR, ns * M.n_link_slots, true, st));
+    CU(ctx, dalloc(f->mem, &F.preIK, ns * M.n_link_slots, true, st));
+    CU(ctx, dalloc(f->mem, &F.morphR, ns * M.n_morph_slots, true, st));
+    CU(ctx, dalloc(f->mem, &F.morphT, ns * M.n_morph_slots, true, st));
+    CU(ctx, dalloc(f->mem, &F.palette, ns * M.nb * 3, true, st));
+    if (layout == MMDGPU_LAYOUT_SOA_POS_NRM) {
+        CU(ctx, dalloc(f->mem, &F.out_pos, ns * M.nv_pad * 3, false, st));
+        CU(ctx, dalloc(f->mem, &F.out_nrm, ns * M.nv_pad * 3, false, st));
+    } else {
+        CU(ctx, dalloc(f->mem, &F.out_inter, ns * M.nv_pad * 2, false, st));
+    }
+    CU(ctx, dalloc(f->mem, &F.frame_id, ns, true, st));
+    CU(ctx, dalloc(f->mem, &f->d_anims, size_t(n_instances), true, st));
+    f->tiles_per_cta = choose_tiles_per_cta(M.nv_pad / kTileVerts, F.n_slots, M.nb, ctx->sm_count);
+    // Poser::Poser ends with ResetPosing() (poser_impl.inl:125-127): a fresh object holds identity poses.
+    {
+        Timed t(ctx, MMDGPU_KERNEL_POSE_SAMPLE);
+        CU(ctx, launch_pose_sample(st, M, nullptr, F, true, false, 1));
+    }
+    *out = f.release();
+    return MMDGPU_OK;
+}
+
+MMDGPU_API void mmdgpu_frames_destroy(mmdgpu_frames_t f) {
+    if (!f) return;
+    cudaSetDevice(f->ctx->device);
+    cudaStreamSynchronize(f->ctx->stream);
+    cudaStreamSynchronize(f->ctx->dl_stream);
+    delete f;
+}
+MMDGPU_API uint32_t mmdgpu_frames_slot_count(mmdgpu_frames_t f) { return f ? f->dev.n_slots : 0; }
+
+MMDGPU_API mmdgpu_status mmdgpu_reset_posing(mmdgpu_frames_t f) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    if (mmdgpu_status s = enter(f->ctx)) return s;
+    {
+        Timed t(f->ctx, MMDGPU_KERNEL_POSE_SAMPLE);
+        CU(f->ctx, launch_pose_sample(f->ctx->stream, f->model->dev, nullptr, f->dev, true, false, 1));
+    }
+    return MMDGPU_OK;
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_seek_frame(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance,
+                                           const uint32_t* frame_per_slot) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    if (mmdgpu_status s = enter(f->ctx)) return s;
+    return do_seek(f, per_instance, frame_per_slot, false, 1, false);
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_seek_frame_range(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance,
+                                                 const uint32_t* first_frame_per_instance, uint32_t frame_stride) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    if (mmdgpu_status s = enter(f->ctx)) return s;
+    return do_seek(f, per_instance, first_frame_per_instance, true, frame_stride, false);
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_set_bone_pose(mmdgpu_frames_t f, uint32_t slot, uint32_t bone, const float T[3],
+                                              const float R[4]) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    if (mmdgpu_status s = enter(f->ctx)) return s;
+    if (!T || !R) return set_err(f->ctx, MMDGPU_ERR_INVALID_ARG, "pose is NULL");
+    if (slot >= f->dev.n_slots || bone >= f->model->dev.nb) return set_err(f->ctx, MMDGPU_ERR_BAD_INDEX, "slot or bone out of range");
+    const float t4[4] = {T[0], T[1], T[2], 0.0f};
+    const size_t at = size_t(slot) * f->model->dev.nb + bone;
+    CU(f->ctx, cudaMemcpyAsync(f->dev.poseT + at, t4, 16, cudaMemcpyHostToDevice, f->ctx->stream));
+    CU(f->ctx, cudaMemcpyAsync(f->dev.poseR + at, R, 16, cudaMemcpyHostToDevice, f->ctx->stream));
+    return MMDGPU_OK;
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_set_morph_pose(mmdgpu_frames_t f, uint32_t slot, uint32_t morph, float weight) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    if (mmdgpu_status s = enter(f->ctx)) return s;
+    if (slot >= f->dev.n_slots || morph >= f->model->dev.nm) return set_err(f->ctx, MMDGPU_ERR_BAD_INDEX, "slot or morph out of range");
+    CU(f->ctx, cudaMemcpyAsync(f->dev.rate + size_t(slot) * f->model->dev.nm + morph, &weight, 4, cudaMemcpyHostToDevice,
+                               f->ctx->stream));
+    return MMDGPU_OK;
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_pre_physics_posing(mmdgpu_frames_t f) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    if (mmdgpu_status s = enter(f->ctx)) return s;
+    return do_hierarchy(f, 0, f->model->dev.phase_split, true);
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_post_physics_posing(mmdgpu_frames_t f) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    if (mmdgpu_status s = enter(f->ctx)) return s;
+    const DevModel& M = f->model->dev;
+    if (M.phase_split >= M.n_waves) return MMDGPU_OK;  // no post-physics bones: nothing to evaluate
+    return do_hierarchy(f, M.phase_split, M.n_waves, false);
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_deform(mmdgpu_frames_t f) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    if (mmdgpu_status s = enter(f->ctx)) return s;
+    return do_skin(f);
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_set_skinning_matrix_override(mmdgpu_frames_t f, uint32_t slot, uint32_t bone,
+                                                             const float skinning[16], const float* local_or_null) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    if (mmdgpu_status s = enter(f->ctx)) return s;
+    if (!skinning) return set_err(f->ctx, MMDGPU_ERR_INVALID_ARG, "matrix is NULL");
+    const uint32_t nb = f->model->dev.nb;
+    if (slot >= f->dev.n_slots || bone >= nb) return set_err(f->ctx, MMDGPU_ERR_BAD_INDEX, "slot or bone out of range");
+    float cols[12];
+    for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 4; ++r) cols[4 * c + r] = skinning[4 * r + c];
+    CU(f->ctx, cudaMemcpyAsync(f->dev.palette + (size_t(slot) * nb + bone) * 3, cols, 48, cudaMemcpyHostToDevice, f->ctx->stream));
+    if (local_or_null) {
+        float rows[12];
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 3; ++c) rows[3 * r + c] = local_or_null[4 * r + c];
+        CU(f->ctx, cudaMemcpyAsync(f->dev.local + (size_t(slot) * nb + bone) * 12, rows, 48, cudaMemcpyHostToDevice, f->ctx->stream));
+    }
+    return MMDGPU_OK;
+}
+
+static mmdgpu_status update_common(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance, const uint32_t* frames,
+                                   bool range, uint32_t stride) {
+    // ResetPosing + SeekFrame collapse into one sampling launch that writes identity / zero for items the
+    // clip does not animate (main.cpp:1788-1796).
+    if (mmdgpu_status s = do_seek(f, per_instance, frames, range, stride, true)) return s;
+    const DevModel& M = f->model->dev;
+    if (mmdgpu_status s = do_hierarchy(f, 0, M.n_waves, true)) return s;
+    return do_skin(f);
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_update(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance, const uint32_t* frame_per_slot) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    if (mmdgpu_status s = enter(f->ctx)) return s;
+    return update_common(f, per_instance, frame_per_slot, false, 1);
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_update_range(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance,
+                                             const uint32_t* first_frame_per_instance, uint32_t frame_stride) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    if (mmdgpu_status s = enter(f->ctx)) return s;
+    return update_common(f, per_instance, first_frame_per_instance, true, frame_stride);
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_frames_device_ptr(mmdgpu_frames_t f, mmdgpu_stream_id id, void** dptr, size_t* slot_stride_bytes) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    if (!dptr) return set_err(f->ctx, MMDGPU_ERR_INVALID_ARG, "dptr is NULL");
+    StreamView v{};
+    if (mmdgpu_status s = stream_view(f, id, v)) return s;
+    *dptr = const_cast<char*>(v.base);
+    if (slot_stride_bytes) *slot_stride_bytes = v.slot_stride;
+    return MMDGPU_OK;
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_frames_download(mmdgpu_frames_t f, uint32_t slot, mmdgpu_stream_id id, void* host_dst, size_t bytes) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    if (mmdgpu_status s = enter(f->ctx)) return s;
+    if (!host_dst) return set_err(f->ctx, MMDGPU_ERR_INVALID_ARG, "host_dst is NULL");
+    if (slot >= f->dev.n_slots) return set_err(f->ctx, MMDGPU_ERR_BAD_INDEX, "slot out of range");
+    StreamView v{};
+    if (mmdgpu_status s = stream_view(f, id, v)) return s;
+    if (bytes != v.slot_bytes) return set_err(f->ctx, MMDGPU_ERR_INVALID_ARG, "bytes must equal the size of one slot of the stream");
+    if (bytes) CU(f->ctx, cudaMemcpyAsync(host_dst, v.base + size_t(slot) * v.slot_stride, bytes, cudaMemcpyDeviceToHost, f->ctx->stream));
+    CU(f->ctx, cudaStreamSynchronize(f->ctx->stream));
+    return MMDGPU_OK;
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_frames_download_async(mmdgpu_frames_t f, uint32_t first_slot, uint32_t n_slots,
+                                                      mmdgpu_stream_id id, void* pinned_host_dst, size_t bytes) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    mmdgpu_context_t ctx = f->ctx;
+    if (mmdgpu_status s = enter(ctx)) return s;
+    if (!pinned_host_dst) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "host_dst is NULL");
+    if (uint64_t(first_slot) + n_slots > f->dev.n_slots) return set_err(ctx, MMDGPU_ERR_BAD_INDEX, "slot range out of range");
+    StreamView v{};
+    if (mmdgpu_status s = stream_view(f, id, v)) return s;
+    if (bytes != v.slot_bytes * n_slots) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "bytes must equal n_slots x the size of one slot");
+    if (bytes == 0) return MMDGPU_OK;
+    CU(ctx, cudaEventRecord(ctx->dl_event, ctx->stream));
+    CU(ctx, cudaStreamWaitEvent(ctx->dl_stream, ctx->dl_event, 0));
+    CU(ctx, cudaMemcpy2DAsync(pinned_host_dst, v.slot_bytes, v.base + size_t(first_slot) * v.slot_stride, v.slot_stride,
+                              v.slot_bytes, n_slots, cudaMemcpyDeviceToHost, ctx->dl_stream));
+    return MMDGPU_OK;
+}
+
+static mmdgpu_status download_small(mmdgpu_frames_t f, const void* src, size_t bytes, std::vector<float>& tmp) {
+    tmp.resize(bytes / 4);
+    CU(f->ctx, cudaMemcpyAsync(tmp.data(), src, bytes, cudaMemcpyDeviceToHost, f->ctx->stream));
+    CU(f->ctx, cudaStreamSynchronize(f->ctx->stream));
+    return MMDGPU_OK;
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_bone_matrices_download(mmdgpu_frames_t f, uint32_t slot, float* host_dst) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    if (mmdgpu_status s = enter(f->ctx)) return s;
+    if (!host_dst) return set_err(f->ctx, MMDGPU_ERR_INVALID_ARG, "host_dst is NULL");
+    if (slot >= f->dev.n_slots) return set_err(f->ctx, MMDGPU_ERR_BAD_INDEX, "slot out of range");
+    const uint32_t nb = f->model->dev.nb;
+    std::vector<float> tmp;
+    if (mmdgpu_status s = download_small(f, f->dev.palette + size_t(slot) * nb * 3, size_t(nb) * 48, tmp)) return s;
+    for (uint32_t b = 0; b < nb; ++b) {
+        float* o = host_dst + size_t(b) * 16;
+        for (int r = 0; r < 4; ++r) {
+            for (int c = 0; c < 3; ++c) o[4 * r + c] = tmp[size_t(b) * 12 + 4 * c + r];
+            o[4 * r + 3] = (r == 3) ? 1.0f : 0.0f;
+        }
+    }
+    return MMDGPU_OK;
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_bone_local_matrices_download(mmdgpu_frames_t f, uint32_t slot, float* host_dst) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    if (mmdgpu_status s = enter(f->ctx)) return s;
+    if (!host_dst) return set_err(f->ctx, MMDGPU_ERR_INVALID_ARG, "host_dst is NULL");
+    if (slot >= f->dev.n_slots) return set_err(f->ctx, MMDGPU_ERR_BAD_INDEX, "slot out of range");
+    const uint32_t nb = f->model->dev.nb;
+    std::vector<float> tmp;
+    if (mmdgpu_status s = download_small(f, f->dev.local + size_t(slot) * nb * 12, size_t(nb) * 48, tmp)) return s;
+    for (uint32_t b = 0; b < nb; ++b) {
+        float* o = host_dst + size_t(b) * 16;
+        for (int r = 0; r < 4; ++r) {
+            for (int c = 0; c < 3; ++c) o[4 * r + c] = tmp[size_t(b) * 12 + 3 * r + c];
+            o[4 * r + 3] = (r == 3) ? 1.0f : 0.0f;
+        }
+    }
+    return MMDGPU_OK;
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_bone_poses_download(mmdgpu_frames_t f, uint32_t slot, float* host_dst) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    if (mmdgpu_status s = enter(f->ctx)) return s;
+    if (!host_dst) return set_err(f->ctx, MMDGPU_ERR_INVALID_ARG, "host_dst is NULL");
+    if (slot >= f->dev.n_slots) return set_err(f->ctx, MMDGPU_ERR_BAD_INDEX, "slot out of range");
+    const uint32_t nb = f->model->dev.nb;
+    std::vector<float> t, r;
+    if (mmdgpu_status s = download_small(f, f->dev.poseT + size_t(slot) * nb, size_t(nb) * 16, t)) return s;
+    if (mmdgpu_status s = download_small(f, f->dev.poseR + size_t(slot) * nb, size_t(nb) * 16, r)) return s;
+    for (uint32_t b = 0; b < nb; ++b) {
+        float* o = host_dst + size_t(b) * 7;
+        o[0] = t[4 * b]; o[1] = t[4 * b + 1]; o[2] = t[4 * b + 2];
+        o[3] = r[4 * b]; o[4] = r[4 * b + 1]; o[5] = r[4 * b + 2]; o[6] = r[4 * b + 3];
+    }
+    return MMDGPU_OK;
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_morph_rates_download(mmdgpu_frames_t f, uint32_t slot, float* host_dst) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    if (mmdgpu_status s = enter(f->ctx)) return s;
+    if (slot >= f->dev.n_slots) return set_err(f->ctx, MMDGPU_ERR_BAD_INDEX, "slot out of range");
+    const uint32_t nm = f->model->dev.nm;
+    if (nm == 0) return MMDGPU_OK;
+    if (!host_dst) return set_err(f->ctx, MMDGPU_ERR_INVALID_ARG, "host_dst is NULL");
+    CU(f->ctx, cudaMemcpyAsync(host_dst, f->dev.rate + size_t(slot) * nm, size_t(nm) * 4, cudaMemcpyDeviceToHost, f->ctx->stream));
+    CU(f->ctx, cudaStreamSynchronize(f->ctx->stream));
+    return MMDGPU_OK;
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_host_alloc(size_t bytes, void** out) {
+    if (!out) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocDefault);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaHostAlloc");
+    return MMDGPU_OK;
+}
+MMDGPU_API void mmdgpu_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+"""Pins the CPU restatement (oracle/mmd_oracle.c) against the reference: bit-for-bit against libmmd itself where
+the reference harness could be built (this container), and against the committed libmmd-generated fixtures
+(tests/golden/*.npz, made by tests/golden/make_golden.py) everywhere."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import assert_bitwise, synth_case
+from golden_util import check_against_golden, input_digest, load_golden, sha
+
+CASES = ["tiny", "tiny_full", "small"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_generator_is_deterministic(name):
+    cfg, model, motion = synth_case(name)
+    g = load_golden(name)
+    assert input_digest(model, motion) == str(g["input_digest"]), \
+        "synthetic generator drifted from the inputs the golden fixtures were made with"
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_restatement_matches_golden(name):
+    cfg, model, motion = synth_case(name)
+    g = load_golden(name)
+    port = oracle.Restatement(model, motion)
+    t, ids, w = port.skinning()
+    np.testing.assert_array_equal(t, g["norm_type"])
+    np.testing.assert_array_equal(ids, g["norm_ids"])
+    np.testing.assert_array_equal(w.view(np.uint32), g["norm_w"].view(np.uint32))
+    fix, order = port.ik_class()
+    np.testing.assert_array_equal(fix, g["ik_fix"])
+    np.testing.assert_array_equal(order, g["ik_order"])
+    for f in g["frames"]:
+        f = int(f)
+        got = port.run_frame(f)
+        check_against_golden(g, f, got, f"{name} frame {f}")
+        assert sha(port.repack_sokol32()) == str(g[f"f{f}_sokol32_sha"])
+
+
+@pytest.mark.skipif(not oracle.have_reference(), reason="libmmd reference harness not built (needs /root/reference)")
+@pytest.mark.parametrize("name,frames", [("tiny", range(0, 70, 3)), ("tiny_full", range(0, 100)), ("small", [0, 7, 60, 119])])
+def test_restatement_matches_libmmd_bitwise(name, frames):
+    cfg, model, motion = synth_case(name)
+    ref = oracle.Reference(model, motion)
+    port = oracle.Restatement(model, motion)
+    for a, b in zip(ref.skinning(), port.skinning()):
+        np.testing.assert_array_equal(a, b)
+    for f in frames:
+        r, p = ref.run_frame(f), port.run_frame(f)
+        for k in ("poses", "rates", "local", "skin", "pos", "nrm"):
+            assert_bitwise(p[k], r[k], f"{name} frame {f} {k}")
+        assert_bitwise(port.repack_sokol32(), ref.repack_sokol32(), f"{name} frame {f} sokol32")
+
+
+@pytest.mark.skipif(not oracle.have_reference(), reason="libmmd reference harness not built (needs /root/reference)")
+def test_restatement_manual_posing_matches_libmmd():
+    cfg, model, motion = synth_case("tiny_full")
+    rng = np.random.default_rng(3)
+    nb, nm = model["n_bones"], model["n_morphs"]
+    bones = rng.choice(nb, 10, replace=False).astype(np.int32)
+    q = rng.normal(size=(10, 4)).astype(np.float32)
+    q /= np.sqrt((q * q).sum(1, keepdims=True)).astype(np.float32)
+    pose7 = np.concatenate([rng.uniform(-1, 1, (10, 3)).astype(np.float32), q], 1)
+    morphs = np.arange(nm, dtype=np.int32)
+    w = rng.uniform(-0.3, 1.0, nm).astype(np.float32)
+    r = oracle.Reference(model, None).run_manual(bones, pose7, morphs, w)
+    p = oracle.Restatement(model, None).run_manual(bones, pose7, morphs, w)
+    for k in ("skin", "pos", "nrm"):
+        assert_bitwise(p[k], r[k], f"manual {k}")
+
+
+def test_multithreaded_timing_entry_is_consistent():
+    """port_time_frames (the CPU-baseline leg of bench.py): same checksum for 1 and 4 threads."""
+    cfg, model, motion = synth_case("tiny")
+    port = oracle.Restatement(model, motion)
+    frames = np.arange(40, dtype=np.uint32)
+    _, c1 = port.time_frames(frames, 1)
+    _, c4 = port.time_frames(frames, 4)
+    assert abs(c1 - c4) <= 1e-6 * max(1.0, abs(c1))

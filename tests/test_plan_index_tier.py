@@ -1,0 +1,217 @@
+"""Index tier (bit-exact): Model::Normalize rewrite, evaluation order, IK classification, morph application
+slots, per-vertex morph CSR and the wave schedule of the bone program — all host-side, no GPU."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import synth_case
+from golden_util import load_golden
+from simple_mmd_renderer_b200 import capi, synth
+from simple_mmd_renderer_b200.poser import plan_arrays
+
+CASES = ["tiny", "tiny_full", "small", "C2"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_normalize_rewrite_matches_oracle(name):
+    cfg, model, motion = synth_case(name)
+    plan = plan_arrays(model)
+    t, ids, w = oracle.Restatement(model, None).skinning()
+    np.testing.assert_array_equal(plan[capi.PLAN_SKIN_TYPE], t)
+    pid = plan[capi.PLAN_BONE_ID].reshape(-1, 4).astype(np.int32)
+    pw = plan[capi.PLAN_WEIGHT].reshape(-1, 4)
+    # the plan additionally folds Deform's Lerp shortcuts (w < 1e-7 -> bone 1, w > 0.99999988 -> bone 0) into the
+    # stream; everything else must be identical to Model::Normalize's output
+    two = (t == capi.SKIN_BDEF2) | (t == capi.SKIN_SDEF)
+    lo = two & (w[:, 0] < np.float32(1e-7))
+    hi = two & (w[:, 0] > np.float32(1.0 - 1e-7))
+    plain = ~(lo | hi)
+    n_ids = np.where(t == capi.SKIN_BDEF1, 1, np.where(t == capi.SKIN_BDEF4, 4, 2))
+    for k in range(4):
+        use = plain & (n_ids > k)
+        np.testing.assert_array_equal(pid[use, k], ids[use, k])
+    np.testing.assert_array_equal(pid[lo, 0], ids[lo, 1])
+    np.testing.assert_array_equal(pid[hi, 0], ids[hi, 0])
+    four = t == capi.SKIN_BDEF4
+    np.testing.assert_array_equal(pw[four].view(np.uint32), w[four].view(np.uint32))
+    np.testing.assert_array_equal(pw[two & plain, 0].view(np.uint32), w[two & plain, 0].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_full", "small"])
+def test_normalize_and_ik_class_match_libmmd_golden(name):
+    cfg, model, motion = synth_case(name)
+    g = load_golden(name)
+    plan = plan_arrays(model)
+    np.testing.assert_array_equal(plan[capi.PLAN_SKIN_TYPE], g["norm_type"])
+    np.testing.assert_array_equal(plan[capi.PLAN_IK_FIX_TYPE], g["ik_fix"])
+    np.testing.assert_array_equal(plan[capi.PLAN_IK_EULER_ORDER], g["ik_order"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_evaluation_order_is_libmmd_sort(name):
+    """poser_impl.inl:100-109, 500-510: two lists split by the post-physics flag, sorted by (level, index)."""
+    cfg, model, _ = synth_case(name)
+    plan = plan_arrays(model)
+    flags, level = model["bone_flags"], model["bone_transform_level"]
+    nb = model["n_bones"]
+    pre = sorted((b for b in range(nb) if not flags[b] & capi.BONE_POST_PHYSICS), key=lambda b: (int(level[b]), b))
+    post = sorted((b for b in range(nb) if flags[b] & capi.BONE_POST_PHYSICS), key=lambda b: (int(level[b]), b))
+    np.testing.assert_array_equal(plan[capi.PLAN_ORDER_PRE], pre)
+    np.testing.assert_array_equal(plan[capi.PLAN_ORDER_POST], post)
+    # program order = EVAL(b) [IK(b)] over pre, SKIN over pre, then the same over post
+    kinds, bones = plan[capi.PLAN_OP_KIND], plan[capi.PLAN_OP_BONE]
+    want = []
+    for lst in (pre, post):
+        for b in lst:
+            want.append((0, b))
+            if flags[b] & capi.BONE_HAS_IK:
+                want.append((1, b))
+        want += [(2, b) for b in lst]
+    assert list(zip(kinds.tolist(), bones.tolist())) == want
+
+
+def _app_slots(model):
+    """DFS expansion of UpdateMorphTransform's recursion (poser_impl.inl:328-360)."""
+    mt, mb, mc = model["morph_type"], model["morph_entry_begin"], model["morph_entry_count"]
+    ge = model["group_morph_entries"]
+    slots = []
+
+    def visit(m, parent, mult):
+        me = len(slots)
+        slots.append((m, parent, mult))
+        if mt[m] == capi.MORPH_GROUP:
+            for j in range(int(mc[m])):
+                e = ge[int(mb[m]) + j]
+                visit(int(e["morph"]), me, np.float32(e["rate"]))
+    for m in range(int(model["n_morphs"])):
+        visit(m, -1, np.float32(1.0))
+    return slots
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_morph_csr_is_the_transpose_in_application_order(name):
+    cfg, model, _ = synth_case(name)
+    plan = plan_arrays(model)
+    slots = _app_slots(model)
+    np.testing.assert_array_equal(plan[capi.PLAN_APP_SLOT_MORPH], [s[0] for s in slots])
+    np.testing.assert_array_equal(plan[capi.PLAN_APP_SLOT_PARENT], [s[1] for s in slots])
+    np.testing.assert_array_equal(plan[capi.PLAN_APP_SLOT_MULT].view(np.uint32),
+                                  np.asarray([s[2] for s in slots], np.float32).view(np.uint32))
+    # brute-force transpose: (vertex, slot, entry order) sorted
+    mt, mb, mc = model["morph_type"], model["morph_entry_begin"], model["morph_entry_count"]
+    ve = model["vertex_morph_entries"]
+    vs, ss, offs = [], [], []
+    for s, (m, _, _) in enumerate(slots):
+        if mt[m] != capi.MORPH_VERTEX:
+            continue
+        seg = ve[int(mb[m]):int(mb[m]) + int(mc[m])]
+        vs.append(seg["vertex"].astype(np.int64))
+        ss.append(np.full(seg.size, s, np.int64))
+        offs.append(seg["offset"])
+    nv = int(model["n_vertices"])
+    if vs:
+        v = np.concatenate(vs); s = np.concatenate(ss); o = np.concatenate(offs)
+        order = np.argsort(v, kind="stable")       # stable: keeps (slot, entry order) inside a vertex
+        row = np.zeros(nv + 1, np.uint32)
+        np.add.at(row, v + 1, 1)
+        row = np.cumsum(row).astype(np.uint32)
+        np.testing.assert_array_equal(plan[capi.PLAN_CSR_ROW_PTR], row)
+        np.testing.assert_array_equal(plan[capi.PLAN_CSR_SLOT], s[order].astype(np.uint32))
+        np.testing.assert_array_equal(plan[capi.PLAN_CSR_OFFSET].reshape(-1, 3).view(np.uint32), o[order].view(np.uint32))
+    else:
+        assert plan[capi.PLAN_CSR_SLOT].size == 0
+
+
+def _op_sets(model, kind, b):
+    """External read set and write set of one program op, restated from poser_impl.inl:142-311."""
+    nb = int(model["n_bones"])
+    flags, parent = model["bone_flags"], model["bone_parent"]
+    app = model["bone_append_parent"]
+    is_link = np.zeros(nb, bool)
+    for ikb in range(nb):
+        if flags[ikb] & capi.BONE_HAS_IK:
+            lb, lc = int(model["ik_link_begin"][ikb]), int(model["ik_link_count"][ikb])
+            is_link[model["ik_link_bone"][lb:lb + lc]] = True
+
+    def eval_sets(x):
+        R, W = [], []
+        if flags[x] & (capi.BONE_APPEND_ROTATE | capi.BONE_APPEND_TRANSLATE) and 0 <= app[x] < nb:
+            R.append(("tot", int(app[x])))
+        if is_link[x]:
+            R.append(("ik", x)); W.append(("pre", x))
+        if 0 <= parent[x] < nb:
+            R.append(("local", int(parent[x])))
+        W += [("tot", x), ("local", x)]
+        return R, W
+    if kind == 0:
+        return eval_sets(b)
+    if kind == 2:
+        return [("local", b)], [("skin", b)]
+    lb, lc = int(model["ik_link_begin"][b]), int(model["ik_link_count"][b])
+    links = [int(x) for x in model["ik_link_bone"][lb:lb + lc]]
+    R, W = [("local", b)], []
+    wrote = set()
+    for l in links:
+        W.append(("ik", l)); wrote.add(("ik", l))
+    for x in list(reversed(links)) + [int(model["ik_target"][b])]:
+        r2, w2 = eval_sets(x)
+        R += [v for v in r2 if v not in wrote]
+        W += w2
+        wrote.update(w2)
+    for l in links:
+        if 0 <= parent[l] < nb and ("local", int(parent[l])) not in wrote:
+            R.append(("local", int(parent[l])))
+    return R, W
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_full", "small", "C2"])
+def test_wave_schedule_preserves_sequential_semantics(name):
+    """Every op must observe, in the wave program, exactly the writers it observes in libmmd's sequential program,
+    and ops that share a wave must not touch each other's state."""
+    cfg, model, _ = synth_case(name)
+    plan = plan_arrays(model)
+    kinds, bones, wave = plan[capi.PLAN_OP_KIND], plan[capi.PLAN_OP_BONE], plan[capi.PLAN_OP_WAVE]
+    wb, wops = plan[capi.PLAN_WAVE_BEGIN], plan[capi.PLAN_WAVE_OPS]
+    n = kinds.size
+    sets = [_op_sets(model, int(kinds[i]), int(bones[i])) for i in range(n)]
+
+    def observed(order_groups):
+        last = {}
+        seen = [None] * n
+        for grp in order_groups:
+            # all ops of a group read the state left by earlier groups
+            for i in grp:
+                seen[i] = tuple(sorted((v, last.get(v, -1)) for v in set(sets[i][0])))
+            for i in grp:
+                for v in sets[i][1]:
+                    last[v] = i
+        return seen, last
+    seq_seen, seq_last = observed([[i] for i in range(n)])
+    groups = [[int(x) for x in wops[wb[w]:wb[w + 1]]] for w in range(wb.size - 1)]
+    assert sorted(sum(groups, [])) == list(range(n))
+    for w, grp in enumerate(groups):
+        assert all(wave[i] == w for i in grp)
+        touched = {}
+        for i in grp:
+            for v in set(sets[i][0]) | set(sets[i][1]):
+                touched.setdefault(v, []).append(i)
+        for v, ops in touched.items():
+            writers = [i for i in ops if v in sets[i][1]]
+            assert not (writers and len(set(ops)) > 1), f"wave {w}: ops {ops} conflict on {v}"
+    wav_seen, wav_last = observed(groups)
+    assert wav_seen == seq_seen
+    assert wav_last == seq_last
+    split = int(plan[capi.PLAN_WAVE_PHASE_SPLIT][0])
+    post = set(int(b) for b in plan[capi.PLAN_ORDER_POST])
+    for i in range(n):
+        b = int(bones[i])
+        assert (wave[i] >= split) == (b in post), "pre / post physics ops must not share a launch segment"
+
+
+def test_waves_are_shallow_on_the_headline_model():
+    """C3 (1 k bones): the schedule must expose parallelism — far fewer waves than bones."""
+    cfg = synth.CONFIGS["C3"]
+    small = synth.SynthConfig("c3_bones", cfg.config_id, 2000, cfg.n_bones, 4, 30)
+    plan = plan_arrays(synth.make_model(small))
+    n_waves = plan[capi.PLAN_WAVE_BEGIN].size - 1
+    assert n_waves < 64

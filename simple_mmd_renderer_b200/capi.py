@@ -23,7 +23,8 @@ STREAM_POSITION, STREAM_NORMAL, STREAM_INTERLEAVED, STREAM_SKIN_MATRIX = 0, 1, 2
 (PLAN_SKIN_TYPE, PLAN_BONE_ID, PLAN_WEIGHT, PLAN_ORDER_PRE, PLAN_ORDER_POST, PLAN_OP_KIND, PLAN_OP_BONE,
  PLAN_OP_WAVE, PLAN_WAVE_BEGIN, PLAN_WAVE_OPS, PLAN_IK_FIX_TYPE, PLAN_IK_EULER_ORDER, PLAN_APP_SLOT_MORPH,
  PLAN_APP_SLOT_PARENT, PLAN_APP_SLOT_MULT, PLAN_CSR_ROW_PTR, PLAN_CSR_SLOT, PLAN_CSR_OFFSET, PLAN_BEZIER_UNUSED,
- PLAN_WAVE_PHASE_SPLIT) = range(20)
+ PLAN_WAVE_PHASE_SPLIT, PLAN_TILE_ORIG, PLAN_TILE_TYPE, PLAN_TILE_LOCAL_ID, PLAN_TILE_BONE_BEGIN, PLAN_TILE_BONES,
+ PLAN_ELL_BASE, PLAN_ELL_ROUNDS, PLAN_ELL_SLOT, PLAN_ELL_OFFSET) = range(29)
 
 PLAN_DTYPES = {
     PLAN_SKIN_TYPE: np.uint8, PLAN_BONE_ID: np.uint16, PLAN_WEIGHT: np.float32, PLAN_ORDER_PRE: np.int32,
@@ -32,6 +33,9 @@ PLAN_DTYPES = {
     PLAN_APP_SLOT_MORPH: np.int32, PLAN_APP_SLOT_PARENT: np.int32, PLAN_APP_SLOT_MULT: np.float32,
     PLAN_CSR_ROW_PTR: np.uint32, PLAN_CSR_SLOT: np.uint32, PLAN_CSR_OFFSET: np.float32,
     PLAN_WAVE_PHASE_SPLIT: np.int32,
+    PLAN_TILE_ORIG: np.uint16, PLAN_TILE_TYPE: np.uint8, PLAN_TILE_LOCAL_ID: np.uint16,
+    PLAN_TILE_BONE_BEGIN: np.uint32, PLAN_TILE_BONES: np.uint16, PLAN_ELL_BASE: np.uint32,
+    PLAN_ELL_ROUNDS: np.uint32, PLAN_ELL_SLOT: np.uint32, PLAN_ELL_OFFSET: np.float32,
 }
 
 # ---------------------------------------------------------------- numpy record dtypes (AoS pools)

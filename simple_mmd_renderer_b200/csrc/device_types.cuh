@@ -10,26 +10,29 @@ namespace mmdgpu {
 
 constexpr uint32_t kVertsPerThread = 4;
 constexpr uint32_t kSkinThreads = 256;
-constexpr uint32_t kTileVerts = kVertsPerThread * kSkinThreads;  // vertices one CTA handles per iteration
+static_assert(kVertsPerThread * kSkinThreads == kTileVerts, "one CTA iteration = one tile");
 
-// Static model image in HBM.  Vertex streams are structure-of-arrays so that a thread owning 4 consecutive
-// vertices issues only 16-byte loads (48 B read + 4 B CSR row pointer per vertex).
+// Static model image in HBM.  Vertex streams are structure-of-arrays in TILE STORAGE ORDER (host_plan.hpp):
+// a thread owns 4 consecutive storage positions, so every global access is a 16-byte vector, and the 32 lanes
+// of a warp step share a skinning type and a morph entry count.
 struct DevModel {
     uint32_t nv, nv_pad, nb, nm;
-    uint32_t n_nodes, n_nodes_pad;  // morph application slots; padded to a multiple of 4 (16-byte bulk copy)
-    // vertex streams (nv_pad entries each)
+    uint32_t n_nodes, n_nodes_pad;  // morph application slots; padded to a multiple of 4, >= n_nodes + 1
+    uint32_t n_tiles, max_tile_bones;
+    // vertex streams (nv_pad entries each, storage order)
     const float *px, *py, *pz, *nx, *ny, *nz;
-    const uint2* ids;        // 4 x u16 bone ids; bits 15:13 of id0 carry the device skinning type
+    const uint2* ids;        // 4 x u16 tile-local bone indices; bits 15:13 of id0 carry the device skinning type
     const float4* weights;
     const float2* uv;
-    const uint32_t* csr_row; // nv_pad + 1
-    const float4* csr_ent;   // (offset.xyz, bit-cast application slot)
+    const uint2* orig4;      // per thread: 4 x u16 PMX index (within the tile) of its 4 storage positions
+    const uint2* ell_hdr;    // per 32-lane group (tile, step, warp): (first entry, rounds)
+    const float4* ell_ent;   // (offset.xyz, bit-cast application slot); entry (round k, lane l) at base + 32 k + l
+    const uint32_t* tile_bone_begin;  // n_tiles + 1
+    const uint16_t* tile_bones;       // distinct bones of each tile
     // extension streams (NULL in libmmd-exact mode)
     const float4* sdef_c;    // per vertex: C.xyz, unused
     const float4* sdef_r0;
     const float4* sdef_r1;
-    const uint32_t* uv_row;
-    const float4* uv_ent;    // (offset.xy, unused, bit-cast application slot)
     // bones
     const BoneStatic* bones;
     const IkDesc* iks;

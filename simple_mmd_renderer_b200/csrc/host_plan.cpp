@@ -443,6 +443,91 @@ mmdgpu_status build_plan(const mmdgpu_model_desc& d, const mmdgpu_options* opt, 
         grab(d.sdef_c, p.sdef_c); grab(d.sdef_r0, p.sdef_r0); grab(d.sdef_r1, p.sdef_r1);
     }
 
+    // ---------------------------------------------------------------- tiles (device vertex layout)
+    // Vertices stay in PMX order in the OUTPUT (the renderer's index buffer is reused unchanged), but the static
+    // streams of each 1024-vertex tile are stored sorted by (skinning type, morph entry count, PMX index), so
+    // that the 32 lanes of a warp step run one skinning branch and one morph loop trip count.  Sorted rank r
+    // lands at storage position tile_position_of_rank(r).  Bone ids become indices into the tile's own list of
+    // distinct bones (the CTA stages only those matrices).
+    p.nv_pad = (nv + kTileVerts - 1) / kTileVerts * kTileVerts;
+    p.n_tiles = p.nv_pad / kTileVerts;
+    p.tile_orig.assign(p.nv_pad, 0);
+    p.st_type.assign(p.nv_pad, kDevBdef1);
+    p.st_local_id.assign(size_t(p.nv_pad) * 4, 0);
+    p.st_weight.assign(size_t(p.nv_pad) * 4, 0.0f);
+    p.tile_bone_begin.assign(size_t(p.n_tiles) + 1, 0);
+    p.ell_base.assign(size_t(p.n_tiles) * kTileGroups, 0);
+    p.ell_rounds.assign(size_t(p.n_tiles) * kTileGroups, 0);
+    p.pad_node = uint32_t(n_nodes);
+    {
+        std::vector<uint32_t> order(kTileVerts);
+        std::vector<int32_t> local_of(nb, -1);
+        for (uint32_t t = 0; t < p.n_tiles; ++t) {
+            const uint32_t v0 = t * kTileVerts;
+            auto type_of = [&](uint32_t i) -> uint32_t { return (v0 + i < nv) ? p.dev_type[v0 + i] : uint32_t(kDevBdef1); };
+            auto count_of = [&](uint32_t i) -> uint32_t { return (v0 + i < nv) ? p.csr_row[v0 + i + 1] - p.csr_row[v0 + i] : 0u; };
+            for (uint32_t i = 0; i < kTileVerts; ++i) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+                const uint32_t ta = type_of(a), tb = type_of(b);
+                if (ta != tb) return ta < tb;
+                return count_of(a) < count_of(b);
+            });
+            // distinct bones of the tile, ascending
+            std::vector<uint16_t> used;
+            for (uint32_t i = 0; i < kTileVerts && v0 + i < nv; ++i) {
+                const uint8_t dt = p.dev_type[v0 + i];
+                const int keep = (dt == kDevBdef1) ? 1 : (dt == kDevBdef2 || dt == kDevSdef) ? 2 : 4;
+                for (int k = 0; k < keep; ++k) {
+                    const uint16_t b = p.bone_id[size_t(v0 + i) * 4 + k];
+                    if (local_of[b] < 0) { local_of[b] = 0; used.push_back(b); }
+                }
+            }
+            if (used.empty()) { used.push_back(0); local_of[0] = 0; }  // padded vertices read bone 0
+            std::sort(used.begin(), used.end());
+            for (size_t k = 0; k < used.size(); ++k) local_of[used[k]] = int32_t(k);
+            p.tile_bone_begin[t] = uint32_t(p.tile_bones.size());
+            p.tile_bones.insert(p.tile_bones.end(), used.begin(), used.end());
+            p.max_tile_bones = std::max<uint32_t>(p.max_tile_bones, uint32_t(used.size()));
+            for (uint32_t r = 0; r < kTileVerts; ++r) {
+                const uint32_t i = order[r];
+                const size_t pos = size_t(v0) + tile_position_of_rank(r);
+                p.tile_orig[pos] = uint16_t(i);
+                if (v0 + i < nv) {
+                    p.st_type[pos] = p.dev_type[v0 + i];
+                    for (int k = 0; k < 4; ++k) {
+                        p.st_local_id[pos * 4 + k] = uint16_t(local_of[p.bone_id[size_t(v0 + i) * 4 + k]] < 0
+                                                                   ? 0 : local_of[p.bone_id[size_t(v0 + i) * 4 + k]]);
+                        p.st_weight[pos * 4 + k] = p.weight[size_t(v0 + i) * 4 + k];
+                    }
+                } else {
+                    p.st_local_id[pos * 4] = uint16_t(local_of[0] < 0 ? 0 : local_of[0]);
+                }
+            }
+            // sliced ELL: group g = r / 32 holds ranks [32 g, 32 g + 32)
+            for (uint32_t g = 0; g < kTileGroups; ++g) {
+                uint32_t rounds = 0;
+                for (uint32_t l = 0; l < 32; ++l) rounds = std::max(rounds, count_of(order[g * 32 + l]));
+                const size_t base = p.ell_node.size();
+                if (base + size_t(rounds) * 32 > 0xFFFFFFFFull) return fail(err, MMDGPU_ERR_UNSUPPORTED, "morph entry table exceeds 2^32 entries");
+                p.ell_base[size_t(t) * kTileGroups + g] = uint32_t(base);
+                p.ell_rounds[size_t(t) * kTileGroups + g] = rounds;
+                p.ell_node.resize(base + size_t(rounds) * 32, p.pad_node);
+                p.ell_offset.resize((base + size_t(rounds) * 32) * 3, 0.0f);
+                for (uint32_t l = 0; l < 32; ++l) {
+                    const uint32_t i = order[g * 32 + l];
+                    const uint32_t cnt = count_of(i);
+                    for (uint32_t k = 0; k < cnt; ++k) {
+                        const size_t e = size_t(p.csr_row[v0 + i]) + k, at = base + size_t(k) * 32 + l;
+                        p.ell_node[at] = p.csr_node[e];
+                        for (int c = 0; c < 3; ++c) p.ell_offset[at * 3 + c] = p.csr_offset[e * 3 + c];
+                    }
+                }
+            }
+            for (uint16_t b : used) local_of[b] = -1;
+        }
+        p.tile_bone_begin[p.n_tiles] = uint32_t(p.tile_bones.size());
+    }
+
     // introspection mirrors
     p.op_kind_u8.resize(p.ops.size());
     p.op_arg_i32.resize(p.ops.size());

@@ -95,6 +95,24 @@ struct Plan {
     // per-vertex CSR of UV-morph entries (extensions only)
     std::vector<uint32_t> uv_row, uv_node;
     std::vector<float> uv_offset;    // 4 per entry (only .xy applied to the base UV)
+    // ---- device vertex layout: 1024-vertex tiles, each stored in a tile-local order that makes the 32 lanes
+    //      of a warp step share a skinning type and a morph entry count (see build_tiles in host_plan.cpp)
+    uint32_t nv_pad = 0, n_tiles = 0;
+    std::vector<uint16_t> tile_orig;        // nv_pad: storage position -> PMX index within the tile
+    std::vector<uint8_t> st_type;           // nv_pad: device skinning type per storage position
+    std::vector<uint16_t> st_local_id;      // 4 nv_pad: tile-local bone indices per storage position
+    std::vector<float> st_weight;           // 4 nv_pad
+    std::vector<uint32_t> tile_bone_begin;  // n_tiles + 1
+    std::vector<uint16_t> tile_bones;       // distinct global bone ids of every tile, ascending
+    uint32_t max_tile_bones = 0;
+    // sliced ELL of the vertex-morph entries: group = (tile, step j, warp w) = 32 lanes; rounds = max entry
+    // count of the group; entry (round k, lane l) at ell_base + k * 32 + l; padding uses node = pad_node
+    std::vector<uint32_t> ell_base;         // n_tiles * 32
+    std::vector<uint32_t> ell_rounds;       // n_tiles * 32
+    std::vector<uint32_t> ell_node;
+    std::vector<float> ell_offset;          // 3 per entry
+    uint32_t pad_node = 0;                  // application slot whose rate is always 0
+
     // bone morphs grouped by affected bone
     std::vector<int32_t> morph_bones;        // morph_slot -> bone
     std::vector<int32_t> bone_morph_row;     // morph_bones.size() + 1
@@ -108,6 +126,11 @@ struct Plan {
     std::vector<uint8_t> op_kind_u8, ik_fix_u8, ik_order_u8;
     std::vector<int32_t> op_arg_i32, phase_split_i32;
 };
+
+constexpr uint32_t kTileVerts = 1024;   // vertices per tile (one CTA iteration: 256 threads x 4 vertices)
+constexpr uint32_t kTileGroups = 32;    // (step j in 0..3) x (warp w in 0..7)
+// storage position of sorted rank r inside a tile: step j = r / 256, warp w = (r / 32) % 8, lane l = r % 32
+inline uint32_t tile_position_of_rank(uint32_t r) { return (((r >> 5) & 7u) * 32u + (r & 31u)) * 4u + (r >> 8); }
 
 // Returns MMDGPU_OK or an error code with a message in `err`.
 mmdgpu_status build_plan(const mmdgpu_model_desc& d, const mmdgpu_options* opt, Plan& out, std::string& err);

@@ -407,37 +407,28 @@ __global__ void __launch_bounds__(32 * kHierWarps) hierarchy_kernel(DevModel M, 
 // =================================================================================================
 // K3 — skinning.  Poser::Deform, L/motion/poser_impl.inl:396-461; transform / rotate math_impl.inl:1032-1045.
 //
-// One CTA stages the slot's bone palette (nb x 48 B) and application-slot rates in shared memory with one
-// bulk async copy each (cp.async.bulk + mbarrier), then every thread streams 4 consecutive vertices per
-// iteration with 16-byte loads from the SoA planes.  The sparse vertex morphs arrive as a per-vertex CSR
-// gather in application order: no vertex_images_ buffer, no clear pass, no atomics.
+// Work item = one 1024-vertex tile x a run of consecutive slots (frames of a bake, instances of a crowd).
+//   * The tile's static streams are read ONCE (16-byte coalesced loads, 4 storage positions per thread) and stay
+//     in registers while the CTA walks its slots: per vertex-frame only the output leaves the SM.
+//   * Per slot the CTA stages just the matrices of the bones this tile uses (tile-local palette) and the slot's
+//     morph application-slot rates in shared memory, double-buffered: the next slot's loads are in flight
+//     while the current slot is computed.
+//   * Sparse vertex morphs arrive as a sliced-ELL gather (32-lane groups, coalesced 512-byte rounds, warp-uniform
+//     trip count) in libmmd's application order: no vertex_images_ buffer, no clear pass, no atomics.
+//   * Tiles are stored sorted by (skinning type, morph entry count), so a warp step runs one branch; results are
+//     written to a shared-memory staging tile at the vertex's PMX index and leave the SM as one bulk async
+//     copy (cp.async.bulk shared -> global) per output plane.
 // =================================================================================================
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 struct Col3 { float4 c0, c1, c2; };  // skinning matrix as three columns (M0c, M1c, M2c, M3c)
 
@@ -451,7 +442,7 @@ __device__ __forceinline__ Col3 pal_load(const float4* __restrict__ pal, uint32_
 __device__ __forceinline__ float4 f4_scale(const float4& a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
 __device__ __forceinline__ float4 f4_add(const float4& a, const float4& b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
-// One vertex.  ids: 4 x u16 (type in bits 15:13 of id0); w: BDEF2 uses w.x, BDEF4 all four.
+// One vertex.  ids: 4 x u16 tile-local bone indices (type in bits 15:13 of id0); w: BDEF2 uses w.x, BDEF4 all four.
 __device__ __forceinline__ void skin_vertex(const float4* __restrict__ pal, uint32_t ids_lo, uint32_t ids_hi,
                                             const float4& w, float px, float py, float pz, float nx, float ny,
                                             float nz, float* __restrict__ op, float* __restrict__ on) {
@@ -482,61 +473,106 @@ __device__ __forceinline__ void skin_vertex(const float4* __restrict__ pal, uint
     on[2] = nx * Mx.c2.x + ny * Mx.c2.y + nz * Mx.c2.z;
 }
 
-template <int LAYOUT>
-__global__ void __launch_bounds__(kSkinThreads) skin_kernel(DevModel M, DevFrames F, uint32_t tiles_per_cta) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4* pal = reinterpret_cast<float4*>(smem_raw);
-    float* nrate = reinterpret_cast<float*>(smem_raw + (size_t)M.nb * 48);
-    __shared__ __align__(8) uint64_t bar;
+// shared memory carve-up (bytes): [stage 0][stage 1][palette 0][palette 1][rates 0][rates 1]
+__host__ __device__ inline uint32_t skin_stage_bytes(int layout) {
+    return layout == MMDGPU_LAYOUT_SOA_POS_NRM ? kTileVerts * 24u : kTileVerts * 32u;
+}
+__host__ __device__ inline uint32_t skin_pal_bytes(uint32_t max_tile_bones) { return max_tile_bones * 48u; }
 
-    const uint32_t slot = blockIdx.y;
-    const uint32_t tid = threadIdx.x;
-    const uint32_t pal_bytes = M.nb * 48u, rate_bytes = M.n_nodes_pad * 4u;
-    if (tid == 0) {
-        mbar_init(&bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+constexpr uint32_t kPalPrefetch = 2;  // palette float4 per thread held in registers across the compute phase
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(kSkinThreads, 2) skin_kernel(DevModel M, DevFrames F, uint32_t chunk, uint32_t n_chunks) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t stage_bytes = skin_stage_bytes(LAYOUT), pal_bytes = skin_pal_bytes(M.max_tile_bones);
+    unsigned char* stage_base = smem_raw;
+    float4* pal_base = reinterpret_cast<float4*>(smem_raw + 2 * stage_bytes);
+    float* rate_base = reinterpret_cast<float*>(smem_raw + 2 * stage_bytes + 2 * pal_bytes);
+
+    const uint32_t tile = blockIdx.x / n_chunks, ck = blockIdx.x - tile * n_chunks;
+    const uint32_t s0 = ck * chunk;
+    const uint32_t s1 = min(F.n_slots, s0 + chunk);
+    if (s0 >= s1) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+
+    // ---- the tile's static streams: read once, kept in registers for every slot of this work item
+    const uint32_t v0 = tile * kTileVerts + tid * kVertsPerThread;
+    const float4 PX = __ldg(reinterpret_cast<const float4*>(M.px + v0));
+    const float4 PY = __ldg(reinterpret_cast<const float4*>(M.py + v0));
+    const float4 PZ = __ldg(reinterpret_cast<const float4*>(M.pz + v0));
+    const float4 NX = __ldg(reinterpret_cast<const float4*>(M.nx + v0));
+    const float4 NY = __ldg(reinterpret_cast<const float4*>(M.ny + v0));
+    const float4 NZ = __ldg(reinterpret_cast<const float4*>(M.nz + v0));
+    const uint4 I01 = __ldg(reinterpret_cast<const uint4*>(M.ids + v0));
+    const uint4 I23 = __ldg(reinterpret_cast<const uint4*>(M.ids + v0 + 2));
+    const float4 W0 = __ldg(M.weights + v0), W1 = __ldg(M.weights + v0 + 1), W2 = __ldg(M.weights + v0 + 2),
+                 W3 = __ldg(M.weights + v0 + 3);
+    const uint2 OR = __ldg(M.orig4 + (v0 >> 2));
+    float4 UV01 = make_float4(0.f, 0.f, 0.f, 0.f), UV23 = UV01;
+    if (LAYOUT == MMDGPU_LAYOUT_INTERLEAVED_SOKOL32) {
+        UV01 = __ldg(reinterpret_cast<const float4*>(M.uv + v0));
+        UV23 = __ldg(reinterpret_cast<const float4*>(M.uv + v0 + 2));
+    }
+    const float px[4] = {PX.x, PX.y, PX.z, PX.w}, py[4] = {PY.x, PY.y, PY.z, PY.w}, pz[4] = {PZ.x, PZ.y, PZ.z, PZ.w};
+    const float nx[4] = {NX.x, NX.y, NX.z, NX.w}, ny[4] = {NY.x, NY.y, NY.z, NY.w}, nz[4] = {NZ.x, NZ.y, NZ.z, NZ.w};
+    const uint32_t ilo[4] = {I01.x, I01.z, I23.x, I23.z}, ihi[4] = {I01.y, I01.w, I23.y, I23.w};
+    const float4 wv[4] = {W0, W1, W2, W3};
+    const uint32_t orig[4] = {OR.x & 0xFFFFu, OR.x >> 16, OR.y & 0xFFFFu, OR.y >> 16};
+    const float uu[4] = {UV01.x, UV01.z, UV23.x, UV23.z}, vv[4] = {UV01.y, UV01.w, UV23.y, UV23.w};
+    // sliced-ELL group headers of this warp's four steps (warp-uniform addresses: one broadcast load each)
+    uint32_t ebase[4], erounds[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint2 h = __ldg(M.ell_hdr + tile * kTileGroups + j * 8 + warp);
+        ebase[j] = h.x + lane;
+        erounds[j] = h.y;
+    }
+    // tile-local palette: float4 i of the staged palette comes from float4 psrc(i) of the slot's global palette
+    const uint32_t tb0 = __ldg(M.tile_bone_begin + tile);
+    const uint32_t npal4 = (__ldg(M.tile_bone_begin + tile + 1) - tb0) * 3u;
+    const uint32_t nrate4 = M.n_nodes_pad >> 2;
+    uint32_t psrc[kPalPrefetch];
+#pragma unroll
+    for (uint32_t q = 0; q < kPalPrefetch; ++q) {
+        const uint32_t i = tid + q * kSkinThreads;
+        psrc[q] = (i < npal4) ? (uint32_t)__ldg(M.tile_bones + tb0 + i / 3u) * 3u + i % 3u : 0xFFFFFFFFu;
+    }
+    const size_t pal_slot_stride = (size_t)M.nb * 3;  // float4 per slot
+
+    // ---- prologue: slot s0 straight into buffer 0
+    {
+        const float4* gp = F.palette + (size_t)s0 * pal_slot_stride;
+        for (uint32_t i = tid; i < npal4; i += kSkinThreads)
+            pal_base[i] = __ldg(gp + (uint32_t)__ldg(M.tile_bones + tb0 + i / 3u) * 3u + i % 3u);
+        const float4* gr = reinterpret_cast<const float4*>(F.node_rate + (size_t)s0 * M.n_nodes_pad);
+        for (uint32_t i = tid; i < nrate4; i += kSkinThreads) reinterpret_cast<float4*>(rate_base)[i] = __ldg(gr + i);
     }
     __syncthreads();
-    if (tid == 0) {
-        mbar_expect_tx(&bar, pal_bytes + rate_bytes);
-        bulk_g2s(pal, F.palette + (size_t)slot * M.nb * 3, pal_bytes, &bar);
-        if (rate_bytes) bulk_g2s(nrate, F.node_rate + (size_t)slot * M.n_nodes_pad, rate_bytes, &bar);
-    }
 
-    const uint32_t tile0 = blockIdx.x * tiles_per_cta;
-    bool waited = false;
-    for (uint32_t t = 0; t < tiles_per_cta; ++t) {
-        const uint32_t v0 = (tile0 + t) * kTileVerts + tid * kVertsPerThread;
-        if (v0 >= M.nv_pad) break;
-        // ---- 16-byte loads of the static streams (issued before waiting for the palette)
-        const float4 PX = __ldg(reinterpret_cast<const float4*>(M.px + v0));
-        const float4 PY = __ldg(reinterpret_cast<const float4*>(M.py + v0));
-        const float4 PZ = __ldg(reinterpret_cast<const float4*>(M.pz + v0));
-        const float4 NX = __ldg(reinterpret_cast<const float4*>(M.nx + v0));
-        const float4 NY = __ldg(reinterpret_cast<const float4*>(M.ny + v0));
-        const float4 NZ = __ldg(reinterpret_cast<const float4*>(M.nz + v0));
-        const uint4 I01 = __ldg(reinterpret_cast<const uint4*>(M.ids + v0));
-        const uint4 I23 = __ldg(reinterpret_cast<const uint4*>(M.ids + v0 + 2));
-        const float4 W0 = __ldg(M.weights + v0), W1 = __ldg(M.weights + v0 + 1), W2 = __ldg(M.weights + v0 + 2),
-                     W3 = __ldg(M.weights + v0 + 3);
-        const uint4 RP = __ldg(reinterpret_cast<const uint4*>(M.csr_row + v0));
-        const uint32_t RE = __ldg(M.csr_row + v0 + 4);
-        if (!waited) {
-            mbar_wait(&bar, 0);
-            waited = true;
+    for (uint32_t s = s0; s < s1; ++s) {
+        const uint32_t b = (s - s0) & 1u;
+        const float4* __restrict__ pal = pal_base + (size_t)b * (pal_bytes >> 4);
+        const float* __restrict__ nrate = rate_base + (size_t)b * M.n_nodes_pad;
+        unsigned char* stage = stage_base + (size_t)b * stage_bytes;
+        const bool has_next = s + 1 < s1;
+        // ---- next slot's palette subset and rates: loads issued now, consumed after the compute phase
+        float4 pf[kPalPrefetch], rf = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* gp = F.palette + (size_t)(s + 1) * pal_slot_stride;
+        const float4* gr = reinterpret_cast<const float4*>(F.node_rate + (size_t)(s + 1) * M.n_nodes_pad);
+        if (has_next) {
+#pragma unroll
+            for (uint32_t q = 0; q < kPalPrefetch; ++q)
+                if (psrc[q] != 0xFFFFFFFFu) pf[q] = __ldg(gp + psrc[q]);
+            if (tid < nrate4) rf = __ldg(gr + tid);
         }
-        const float px[4] = {PX.x, PX.y, PX.z, PX.w}, py[4] = {PY.x, PY.y, PY.z, PY.w}, pz[4] = {PZ.x, PZ.y, PZ.z, PZ.w};
-        const float nx[4] = {NX.x, NX.y, NX.z, NX.w}, ny[4] = {NY.x, NY.y, NY.z, NY.w}, nz[4] = {NZ.x, NZ.y, NZ.z, NZ.w};
-        const uint32_t ilo[4] = {I01.x, I01.z, I23.x, I23.z}, ihi[4] = {I01.y, I01.w, I23.y, I23.w};
-        const float4 wv[4] = {W0, W1, W2, W3};
-        const uint32_t rp[5] = {RP.x, RP.y, RP.z, RP.w, RE};
-        float op[12], on[12];
+        // ---- compute: 4 storage positions; step j is (nearly always) one skinning type across the warp
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             // vertex_images_[i] accumulated in application order: img = img + off*rate (poser_impl.inl:340-346)
             float ix = 0.f, iy = 0.f, iz = 0.f;
-            for (uint32_t e = rp[j]; e < rp[j + 1]; ++e) {
-                const float4 ent = __ldg(M.csr_ent + e);
+            const float4* __restrict__ e = M.ell_ent + ebase[j];
+            for (uint32_t k = 0; k < erounds[j]; ++k) {
+                const float4 ent = __ldg(e + (size_t)k * 32);
                 const float r = nrate[__float_as_int(ent.w)];
                 if (r != 0.0f) {
                     ix = ix + ent.x * r;
@@ -544,34 +580,50 @@ __global__ void __launch_bounds__(kSkinThreads) skin_kernel(DevModel M, DevFrame
                     iz = iz + ent.z * r;
                 }
             }
+            float op[3], on[3];
             // coordinate + vertex_image (poser_impl.inl:407)
-            skin_vertex(pal, ilo[j], ihi[j], wv[j], px[j] + ix, py[j] + iy, pz[j] + iz, nx[j], ny[j], nz[j], op + 3 * j,
-                        on + 3 * j);
-        }
-        if (LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) {
-            float4* dp = reinterpret_cast<float4*>(F.out_pos + ((size_t)slot * M.nv_pad + v0) * 3);
-            float4* dn = reinterpret_cast<float4*>(F.out_nrm + ((size_t)slot * M.nv_pad + v0) * 3);
-            dp[0] = make_float4(op[0], op[1], op[2], op[3]);
-            dp[1] = make_float4(op[4], op[5], op[6], op[7]);
-            dp[2] = make_float4(op[8], op[9], op[10], op[11]);
-            dn[0] = make_float4(on[0], on[1], on[2], on[3]);
-            dn[1] = make_float4(on[4], on[5], on[6], on[7]);
-            dn[2] = make_float4(on[8], on[9], on[10], on[11]);
-        } else {
-            // main.cpp:838-859: Vertex{pos*0.1f, normal, uv}
-            const float4 UV01 = __ldg(reinterpret_cast<const float4*>(M.uv + v0));
-            const float4 UV23 = __ldg(reinterpret_cast<const float4*>(M.uv + v0 + 2));
-            const float uu[4] = {UV01.x, UV01.z, UV23.x, UV23.z}, vv[4] = {UV01.y, UV01.w, UV23.y, UV23.w};
-            float4* d = F.out_inter + ((size_t)slot * M.nv_pad + v0) * 2;
-            const float mmd_to_meter = 0.1f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                d[2 * j] = make_float4(op[3 * j] * mmd_to_meter, op[3 * j + 1] * mmd_to_meter, op[3 * j + 2] * mmd_to_meter, on[3 * j]);
-                d[2 * j + 1] = make_float4(on[3 * j + 1], on[3 * j + 2], uu[j], vv[j]);
+            skin_vertex(pal, ilo[j], ihi[j], wv[j], px[j] + ix, py[j] + iy, pz[j] + iz, nx[j], ny[j], nz[j], op, on);
+            if (LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) {
+                float* sp = reinterpret_cast<float*>(stage) + orig[j] * 3u;
+                float* sn = reinterpret_cast<float*>(stage + kTileVerts * 12u) + orig[j] * 3u;
+                sp[0] = op[0]; sp[1] = op[1]; sp[2] = op[2];
+                sn[0] = on[0]; sn[1] = on[1]; sn[2] = on[2];
+            } else {
+                // main.cpp:838-859: Vertex{pos*0.1f, normal, uv}
+                const float mmd_to_meter = 0.1f;
+                float4* sv = reinterpret_cast<float4*>(stage) + orig[j] * 2u;
+                sv[0] = make_float4(op[0] * mmd_to_meter, op[1] * mmd_to_meter, op[2] * mmd_to_meter, on[0]);
+                sv[1] = make_float4(on[1], on[2], uu[j], vv[j]);
             }
         }
+        // ---- publish the next slot's staging data into the other buffer
+        if (has_next) {
+            float4* npal = pal_base + (size_t)(b ^ 1u) * (pal_bytes >> 4);
+            float4* nrt = reinterpret_cast<float4*>(rate_base + (size_t)(b ^ 1u) * M.n_nodes_pad);
+#pragma unroll
+            for (uint32_t q = 0; q < kPalPrefetch; ++q)
+                if (psrc[q] != 0xFFFFFFFFu) npal[tid + q * kSkinThreads] = pf[q];
+            for (uint32_t i = tid + kPalPrefetch * kSkinThreads; i < npal4; i += kSkinThreads)
+                npal[i] = __ldg(gp + (uint32_t)__ldg(M.tile_bones + tb0 + i / 3u) * 3u + i % 3u);
+            if (tid < nrate4) nrt[tid] = rf;
+            for (uint32_t i = tid + kSkinThreads; i < nrate4; i += kSkinThreads) nrt[i] = __ldg(gr + i);
+        }
+        // ---- hand the staged tile to the bulk-copy engine
+        fence_proxy_async_smem();                 // my staging writes become visible to the async proxy
+        if (tid == 0) bulk_wait_read_all();       // the previous slot's copy has finished reading the other buffer
+        __syncthreads();
+        if (tid == 0) {
+            const size_t vbase = (size_t)s * M.nv_pad + (size_t)tile * kTileVerts;
+            if (LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) {
+                bulk_s2g(F.out_pos + vbase * 3, stage, kTileVerts * 12u);
+                bulk_s2g(F.out_nrm + vbase * 3, stage + kTileVerts * 12u, kTileVerts * 12u);
+            } else {
+                bulk_s2g(F.out_inter + vbase * 2, stage, kTileVerts * 32u);
+            }
+            bulk_commit();
+        }
     }
-    if (!waited) mbar_wait(&bar, 0);  // never leave a bulk copy in flight when the CTA exits
+    if (tid == 0) bulk_wait_all();  // shared memory must outlive the copies that read it
 }
 
 // =================================================================================================
@@ -595,23 +647,28 @@ cudaError_t launch_hierarchy(cudaStream_t st, const DevModel& M, const DevFrames
     return cudaGetLastError();
 }
 
-size_t skin_smem_bytes(const DevModel& M) { return (size_t)M.nb * 48 + (size_t)M.n_nodes_pad * 4; }
-
-cudaError_t prepare_skin_kernels(size_t smem) {
-    cudaError_t e = cudaFuncSetAttribute(skin_kernel<MMDGPU_LAYOUT_SOA_POS_NRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(skin_kernel<MMDGPU_LAYOUT_INTERLEAVED_SOKOL32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+size_t skin_smem_bytes(const DevModel& M, int layout) {
+    return 2 * (size_t)skin_stage_bytes(layout) + 2 * (size_t)skin_pal_bytes(M.max_tile_bones) + 2 * (size_t)M.n_nodes_pad * 4;
 }
 
-cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, int layout, uint32_t tiles_per_cta) {
-    if (F.n_slots == 0 || M.nv_pad == 0) return cudaSuccess;
-    const uint32_t tiles = M.nv_pad / kTileVerts;
-    dim3 grid((tiles + tiles_per_cta - 1) / tiles_per_cta, F.n_slots);
-    const size_t smem = skin_smem_bytes(M);
+cudaError_t prepare_skin_kernels(const DevModel& M) {
+    cudaError_t e = cudaFuncSetAttribute(skin_kernel<MMDGPU_LAYOUT_SOA_POS_NRM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)skin_smem_bytes(M, MMDGPU_LAYOUT_SOA_POS_NRM));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(skin_kernel<MMDGPU_LAYOUT_INTERLEAVED_SOKOL32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)skin_smem_bytes(M, MMDGPU_LAYOUT_INTERLEAVED_SOKOL32));
+}
+
+cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, int layout, uint32_t slots_per_cta) {
+    if (F.n_slots == 0 || M.n_tiles == 0) return cudaSuccess;
+    if (slots_per_cta == 0) slots_per_cta = 1;
+    const uint32_t n_chunks = (F.n_slots + slots_per_cta - 1) / slots_per_cta;
+    const uint32_t grid = M.n_tiles * n_chunks;
+    const size_t smem = skin_smem_bytes(M, layout);
     if (layout == MMDGPU_LAYOUT_SOA_POS_NRM)
-        skin_kernel<MMDGPU_LAYOUT_SOA_POS_NRM><<<grid, kSkinThreads, smem, st>>>(M, F, tiles_per_cta);
+        skin_kernel<MMDGPU_LAYOUT_SOA_POS_NRM><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);
     else
-        skin_kernel<MMDGPU_LAYOUT_INTERLEAVED_SOKOL32><<<grid, kSkinThreads, smem, st>>>(M, F, tiles_per_cta);
+        skin_kernel<MMDGPU_LAYOUT_INTERLEAVED_SOKOL32><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);
     return cudaGetLastError();
 }
 

@@ -14,9 +14,9 @@ cudaError_t launch_pose_sample(cudaStream_t st, const DevModel& M, const DevAnim
 // K2: waves [wave_lo, wave_hi) of the bone program; prologue = morph rates + reset + bone morphs.
 cudaError_t launch_hierarchy(cudaStream_t st, const DevModel& M, const DevFrames& F, uint32_t wave_lo, uint32_t wave_hi,
                              bool prologue);
-// K3: skinning + fused vertex-morph gather.
-size_t skin_smem_bytes(const DevModel& M);
-cudaError_t prepare_skin_kernels(size_t smem);
-cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, int layout, uint32_t tiles_per_cta);
+// K3: skinning + fused vertex-morph gather.  One CTA = one 1024-vertex tile x `slots_per_cta` consecutive slots.
+size_t skin_smem_bytes(const DevModel& M, int layout);
+cudaError_t prepare_skin_kernels(const DevModel& M);
+cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, int layout, uint32_t slots_per_cta);
 
 }  // namespace mmdgpu

@@ -90,7 +90,7 @@ struct mmdgpu_frames {
     std::vector<DevAnim> h_anims;
     bool range_mode = false;
     uint32_t frame_stride = 1;
-    uint32_t tiles_per_cta = 1;
+    uint32_t slots_per_cta = 1;
 };
 
 namespace {
@@ -135,20 +135,14 @@ cudaError_t dalloc(DevArena& mem, T** out, size_t n, bool zero, cudaStream_t st)
 
 uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
 
-// Choose how many 1024-vertex tiles one CTA walks: enough CTAs to fill the machine a few times over, few
-// enough that restaging the palette (nb x 48 B per CTA) stays a small fraction of the streamed bytes.
-uint32_t choose_tiles_per_cta(uint32_t tiles, uint32_t n_slots, uint32_t nb, int sm_count) {
-    if (tiles == 0) return 1;
-    const uint64_t total = uint64_t(tiles) * n_slots;
-    const uint64_t target_ctas = uint64_t(sm_count > 0 ? sm_count : 148) * 16;
-    uint32_t t = uint32_t(std::max<uint64_t>(1, total / target_ctas));
-    // palette bytes per CTA <= ~6 % of the stream bytes (76 KB per tile)
-    const uint32_t min_t = std::max<uint32_t>(1, (nb * 48u * 16u + 76u * 1024u - 1) / (76u * 1024u));
-    t = std::max(t, std::min(min_t, tiles));
-    t = std::min(t, tiles);
-    // balance: equal-sized chunks
-    const uint32_t chunks = (tiles + t - 1) / t;
-    return (tiles + chunks - 1) / chunks;
+// How many consecutive slots one CTA walks for its tile.  Longer runs amortise the tile's static streams (read
+// once per run); shorter runs give more work items to balance over the SMs.
+uint32_t choose_slots_per_cta(uint32_t tiles, uint32_t n_slots, int sm_count) {
+    if (tiles == 0 || n_slots == 0) return 1;
+    const uint64_t target_items = uint64_t(sm_count > 0 ? sm_count : 148) * 2 * 8;  // 8 waves of 2 CTAs per SM
+    uint64_t n_chunks = (target_items + tiles - 1) / tiles;
+    n_chunks = std::min<uint64_t>(std::max<uint64_t>(n_chunks, 1), n_slots);
+    return uint32_t((n_slots + n_chunks - 1) / n_chunks);
 }
 
 mmdgpu_status upload_model(mmdgpu_model* m) {
@@ -157,28 +151,39 @@ mmdgpu_status upload_model(mmdgpu_model* m) {
     DevModel& D = m->dev;
     D = DevModel{};
     const uint32_t nv = p.nv, nb = p.nb;
-    const uint32_t nvp = round_up(nv, kTileVerts);
+    const uint32_t nvp = p.nv_pad;
+    if (p.extensions)
+        return set_err(ctx, MMDGPU_ERR_UNSUPPORTED,
+                       "extensions (spherical SDEF, dual-quaternion QDEF, applied UV morphs) are not built into this version");
     D.nv = nv; D.nv_pad = nvp; D.nb = nb; D.nm = p.nm;
     D.n_nodes = uint32_t(p.node_morph.size());
-    D.n_nodes_pad = round_up(D.n_nodes, 4);
+    D.n_nodes_pad = round_up(D.n_nodes + 1, 4);  // + the always-zero slot the ELL padding points at
+    D.n_tiles = p.n_tiles;
+    D.max_tile_bones = std::max<uint32_t>(1, p.max_tile_bones);
 
-    // ---- vertex streams, structure of arrays, padded to a whole tile
+    // ---- vertex streams, structure of arrays, in tile storage order (host_plan.hpp)
     std::vector<float> plane[6];
     for (auto& v : plane) v.assign(nvp, 0.0f);
     std::vector<uint2> ids(nvp, make_uint2(0, 0));
     std::vector<float4> wts(nvp, make_float4(0.f, 0.f, 0.f, 0.f));
     std::vector<float2> uv(nvp, make_float2(0.f, 0.f));
-    for (uint32_t i = 0; i < nv; ++i) {
-        for (int k = 0; k < 3; ++k) {
-            plane[k][i] = p.position[size_t(i) * 3 + k];
-            plane[3 + k][i] = p.normal[size_t(i) * 3 + k];
+    std::vector<uint2> orig4(nvp / 4, make_uint2(0, 0));
+    for (uint32_t pos = 0; pos < nvp; ++pos) {
+        const uint32_t src = (pos / kTileVerts) * kTileVerts + p.tile_orig[pos];
+        if (src < nv) {
+            for (int k = 0; k < 3; ++k) {
+                plane[k][pos] = p.position[size_t(src) * 3 + k];
+                plane[3 + k][pos] = p.normal[size_t(src) * 3 + k];
+            }
+            uv[pos] = make_float2(p.uv[size_t(src) * 2], p.uv[size_t(src) * 2 + 1]);
         }
-        const uint16_t* id = &p.bone_id[size_t(i) * 4];
-        ids[i].x = uint32_t(id[0]) | (uint32_t(p.dev_type[i]) << 13) | (uint32_t(id[1]) << 16);
-        ids[i].y = uint32_t(id[2]) | (uint32_t(id[3]) << 16);
-        const float* w = &p.weight[size_t(i) * 4];
-        wts[i] = make_float4(w[0], w[1], w[2], w[3]);
-        uv[i] = make_float2(p.uv[size_t(i) * 2], p.uv[size_t(i) * 2 + 1]);
+        const uint16_t* id = &p.st_local_id[size_t(pos) * 4];
+        ids[pos].x = uint32_t(id[0]) | (uint32_t(p.st_type[pos]) << 13) | (uint32_t(id[1]) << 16);
+        ids[pos].y = uint32_t(id[2]) | (uint32_t(id[3]) << 16);
+        const float* w = &p.st_weight[size_t(pos) * 4];
+        wts[pos] = make_float4(w[0], w[1], w[2], w[3]);
+        uint32_t& word = (pos & 2u) ? orig4[pos >> 2].y : orig4[pos >> 2].x;
+        word |= uint32_t(p.tile_orig[pos]) << ((pos & 1u) * 16);
     }
     CU(ctx, upload(ctx, m->mem, plane[0], &D.px)); CU(ctx, upload(ctx, m->mem, plane[1], &D.py));
     CU(ctx, upload(ctx, m->mem, plane[2], &D.pz)); CU(ctx, upload(ctx, m->mem, plane[3], &D.nx));
@@ -186,19 +191,21 @@ mmdgpu_status upload_model(mmdgpu_model* m) {
     CU(ctx, upload(ctx, m->mem, ids, &D.ids));
     CU(ctx, upload(ctx, m->mem, wts, &D.weights));
     CU(ctx, upload(ctx, m->mem, uv, &D.uv));
-    // ---- morph CSR (rows padded: the padded vertices own no entries)
-    std::vector<uint32_t> row(size_t(nvp) + 4, 0);
-    for (uint32_t i = 0; i <= nv; ++i) row[i] = p.csr_row[i];
-    for (size_t i = size_t(nv) + 1; i < row.size(); ++i) row[i] = p.csr_row[nv];
-    std::vector<float4> ent(p.csr_node.size());
+    CU(ctx, upload(ctx, m->mem, orig4, &D.orig4));
+    // ---- sliced-ELL morph entries
+    std::vector<uint2> hdr(p.ell_base.size());
+    for (size_t g = 0; g < hdr.size(); ++g) hdr[g] = make_uint2(p.ell_base[g], p.ell_rounds[g]);
+    std::vector<float4> ent(p.ell_node.size());
     for (size_t e = 0; e < ent.size(); ++e) {
         float slot_bits;
-        const uint32_t node = p.csr_node[e];
+        const uint32_t node = p.ell_node[e];
         std::memcpy(&slot_bits, &node, 4);
-        ent[e] = make_float4(p.csr_offset[3 * e], p.csr_offset[3 * e + 1], p.csr_offset[3 * e + 2], slot_bits);
+        ent[e] = make_float4(p.ell_offset[3 * e], p.ell_offset[3 * e + 1], p.ell_offset[3 * e + 2], slot_bits);
     }
-    CU(ctx, upload(ctx, m->mem, row, &D.csr_row));
-    CU(ctx, upload(ctx, m->mem, ent, &D.csr_ent));
+    CU(ctx, upload(ctx, m->mem, hdr, &D.ell_hdr));
+    CU(ctx, upload(ctx, m->mem, ent, &D.ell_ent));
+    CU(ctx, upload(ctx, m->mem, p.tile_bone_begin, &D.tile_bone_begin));
+    CU(ctx, upload(ctx, m->mem, p.tile_bones, &D.tile_bones));
     // ---- bones and the program
     static_assert(sizeof(BoneStatic) == 48, "BoneStatic is read as three float4");
     CU(ctx, upload(ctx, m->mem, p.bones, &D.bones));
@@ -229,11 +236,11 @@ mmdgpu_status upload_model(mmdgpu_model* m) {
     CU(ctx, upload(ctx, m->mem, p.bone_morph_entries, &D.bone_morph_entries));
     CU(ctx, cudaStreamSynchronize(ctx->stream));  // the staging vectors above die with this frame
 
-    const size_t smem = skin_smem_bytes(D);
+    const size_t smem = skin_smem_bytes(D, MMDGPU_LAYOUT_INTERLEAVED_SOKOL32);
     if (smem + 1024 > size_t(ctx->max_smem_optin))
         return set_err(ctx, MMDGPU_ERR_UNSUPPORTED,
-                       "bone palette + morph slot rates (" + std::to_string(smem) + " B) exceed shared memory per CTA");
-    CU(ctx, prepare_skin_kernels(smem));
+                       "tile palettes + morph slot rates (" + std::to_string(smem) + " B) exceed shared memory per CTA");
+    CU(ctx, prepare_skin_kernels(D));
     return MMDGPU_OK;
 }
 
@@ -337,7 +344,7 @@ mmdgpu_status do_skin(mmdgpu_frames* f) {
     if (f->model->dev.nv_pad == 0) return MMDGPU_OK;
     {
         Timed t(ctx, MMDGPU_KERNEL_SKIN);
-        CU(ctx, launch_skin(ctx->stream, f->model->dev, f->dev, int(f->layout), f->tiles_per_cta));
+        CU(ctx, launch_skin(ctx->stream, f->model->dev, f->dev, int(f->layout), f->slots_per_cta));
     }
     return MMDGPU_OK;
 }
@@ -535,6 +542,15 @@ MMDGPU_API mmdgpu_status mmdgpu_plan_get(mmdgpu_plan_t plan, mmdgpu_plan_array w
     case MMDGPU_PLAN_CSR_SLOT: RET(p.csr_node);
     case MMDGPU_PLAN_CSR_OFFSET: RET(p.csr_offset);
     case MMDGPU_PLAN_WAVE_PHASE_SPLIT: RET(p.phase_split_i32);
+    case MMDGPU_PLAN_TILE_ORIG: RET(p.tile_orig);
+    case MMDGPU_PLAN_TILE_TYPE: RET(p.st_type);
+    case MMDGPU_PLAN_TILE_LOCAL_ID: RET(p.st_local_id);
+    case MMDGPU_PLAN_TILE_BONE_BEGIN: RET(p.tile_bone_begin);
+    case MMDGPU_PLAN_TILE_BONES: RET(p.tile_bones);
+    case MMDGPU_PLAN_ELL_BASE: RET(p.ell_base);
+    case MMDGPU_PLAN_ELL_ROUNDS: RET(p.ell_rounds);
+    case MMDGPU_PLAN_ELL_SLOT: RET(p.ell_node);
+    case MMDGPU_PLAN_ELL_OFFSET: RET(p.ell_offset);
     default: break;
     }
 #undef RET
@@ -705,7 +721,7 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_create(mmdgpu_context_t ctx, mmdgpu_model
     }
     CU(ctx, dalloc(f->mem, &F.frame_id, ns, true, st));
     CU(ctx, dalloc(f->mem, &f->d_anims, size_t(n_instances), true, st));
-    f->tiles_per_cta = choose_tiles_per_cta(M.nv_pad / kTileVerts, F.n_slots, M.nb, ctx->sm_count);
+    f->slots_per_cta = choose_slots_per_cta(M.n_tiles, F.n_slots, ctx->sm_count);
     // Poser::Poser ends with ResetPosing() (poser_impl.inl:125-127): a fresh object holds identity poses.
     {
         Timed t(ctx, MMDGPU_KERNEL_POSE_SAMPLE);

@@ -215,3 +215,82 @@ def test_waves_are_shallow_on_the_headline_model():
     plan = plan_arrays(synth.make_model(small))
     n_waves = plan[capi.PLAN_WAVE_BEGIN].size - 1
     assert n_waves < 64
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_full", "small", "C2"])
+def test_tile_layout_is_a_faithful_permutation(name):
+    """Device vertex layout: every 1024-vertex tile is stored in a tile-local order; the permutation, the
+    tile-local bone lists and the sliced-ELL morph table must reproduce the PMX-order arrays exactly."""
+    cfg, model, _ = synth_case(name)
+    plan = plan_arrays(model)
+    nv = int(model["n_vertices"])
+    orig = plan[capi.PLAN_TILE_ORIG].astype(np.int64)
+    nvp = orig.size
+    assert nvp % 1024 == 0 and nvp >= nv and nvp - nv < 1024
+    n_tiles = nvp // 1024
+    tiles = orig.reshape(n_tiles, 1024)
+    assert (np.sort(tiles, axis=1) == np.arange(1024)).all(), "tile_orig must be a permutation of each tile"
+    src = (np.arange(nvp) // 1024) * 1024 + orig           # PMX vertex of every storage position
+    real = src < nv
+    # device type per PMX vertex, derived independently from the Normalize output + Deform's Lerp shortcuts
+    t = plan[capi.PLAN_SKIN_TYPE].astype(np.int64)
+    pw = plan[capi.PLAN_WEIGHT].reshape(-1, 4)
+    pid = plan[capi.PLAN_BONE_ID].reshape(-1, 4).astype(np.int64)
+    two = (t == capi.SKIN_BDEF2) | (t == capi.SKIN_SDEF)
+    dev = np.where(t == capi.SKIN_BDEF1, 0, np.where(t == capi.SKIN_BDEF4, 2, 1))
+    dev = np.where(two & ((pw[:, 0] < np.float32(1e-7)) | (pw[:, 0] > np.float32(1.0 - 1e-7))), 0, dev)
+    st_type = plan[capi.PLAN_TILE_TYPE].astype(np.int64)
+    np.testing.assert_array_equal(st_type[real], dev[src[real]])
+    assert (st_type[~real] == 0).all()
+    # tile-local bone indices map back to the global ids
+    tb_begin = plan[capi.PLAN_TILE_BONE_BEGIN].astype(np.int64)
+    tb = plan[capi.PLAN_TILE_BONES].astype(np.int64)
+    local = plan[capi.PLAN_TILE_LOCAL_ID].reshape(-1, 4).astype(np.int64)
+    n_ids = np.where(st_type == 0, 1, np.where(st_type == 2, 4, 2))
+    for ti in range(n_tiles):
+        bones = tb[tb_begin[ti]:tb_begin[ti + 1]]
+        assert (np.diff(bones) > 0).all()
+        sl = slice(ti * 1024, (ti + 1) * 1024)
+        for k in range(4):
+            use = real[sl] & (n_ids[sl] > k)
+            np.testing.assert_array_equal(bones[local[sl][use, k]], pid[src[sl][use], k])
+        used = set()
+        for k in range(4):
+            used |= set(pid[src[sl][real[sl] & (n_ids[sl] > k)], k].tolist())
+        assert used == set(bones.tolist()) or (not used and bones.tolist() == [0])
+    # sliced ELL -> per-vertex entry lists == CSR rows, application order kept; padding points at the zero slot
+    row = plan[capi.PLAN_CSR_ROW_PTR].astype(np.int64)
+    cslot = plan[capi.PLAN_CSR_SLOT]
+    coff = plan[capi.PLAN_CSR_OFFSET].reshape(-1, 3)
+    base = plan[capi.PLAN_ELL_BASE].astype(np.int64)
+    rounds = plan[capi.PLAN_ELL_ROUNDS].astype(np.int64)
+    eslot = plan[capi.PLAN_ELL_SLOT]
+    eoff = plan[capi.PLAN_ELL_OFFSET].reshape(-1, 3)
+    pad = plan[capi.PLAN_APP_SLOT_MORPH].size
+    total_real = 0
+    for ti in range(n_tiles):
+        for j in range(4):
+            for w in range(8):
+                g = ti * 32 + j * 8 + w
+                cnts = []
+                for l in range(32):
+                    pos = ti * 1024 + (w * 32 + l) * 4 + j
+                    v = src[pos]
+                    cnt = int(row[v + 1] - row[v]) if v < nv else 0
+                    cnts.append(cnt)
+                    at = base[g] + np.arange(rounds[g]) * 32 + l
+                    np.testing.assert_array_equal(eslot[at[:cnt]], cslot[row[v]:row[v] + cnt] if v < nv else [])
+                    if cnt:
+                        np.testing.assert_array_equal(eoff[at[:cnt]].view(np.uint32), coff[row[v]:row[v] + cnt].view(np.uint32))
+                    assert (eslot[at[cnt:]] == pad).all() and (eoff[at[cnt:]] == 0).all()
+                    total_real += cnt
+                assert rounds[g] == max(cnts)
+    assert total_real == cslot.size
+    # the point of the sort: a warp step (32 consecutive ranks) is one skinning type except at the boundaries
+    mixed = 0
+    for ti in range(n_tiles):
+        for j in range(4):
+            for w in range(8):
+                pos = ti * 1024 + (w * 32 + np.arange(32)) * 4 + j
+                mixed += len(set(st_type[pos].tolist())) > 1
+    assert mixed <= 3 * n_tiles

@@ -332,6 +332,13 @@ mmdgpu_status build_plan(const mmdgpu_model_desc& d, const mmdgpu_options* opt, 
                 const uint32_t v = uv ? d.uv_morph_entries[d.morph_entry_begin[m] + j].vertex
                                       : d.vertex_morph_entries[d.morph_entry_begin[m] + j].vertex;
                 if (v >= nv) return fail(err, MMDGPU_ERR_BAD_INDEX, "morph vertex index out of range at morph " + std::to_string(m));
+                if (!uv) {
+                    // the device applies skipped morphs with rate 0 instead of branching; that is bit-identical to
+                    // libmmd's skip only for finite offsets
+                    const float* o = d.vertex_morph_entries[d.morph_entry_begin[m] + j].offset;
+                    if (!std::isfinite(o[0]) || !std::isfinite(o[1]) || !std::isfinite(o[2]))
+                        return fail(err, MMDGPU_ERR_INVALID_ARG, "non-finite vertex morph offset at morph " + std::to_string(m));
+                }
                 row[size_t(v) + 1]++;
             }
         }

@@ -573,12 +573,14 @@ __global__ void __launch_bounds__(kSkinThreads, 2) skin_kernel(DevModel M, DevFr
             const float4* __restrict__ e = M.ell_ent + ebase[j];
             for (uint32_t k = 0; k < erounds[j]; ++k) {
                 const float4 ent = __ldg(e + (size_t)k * 32);
-                const float r = nrate[__float_as_int(ent.w)];
-                if (r != 0.0f) {
-                    ix = ix + ent.x * r;
-                    iy = iy + ent.y * r;
-                    iz = iz + ent.z * r;
-                }
+                // ent.w = byte offset of the entry's application slot in the rate table.  A skipped slot has
+                // rate +0 and is applied unconditionally: the accumulator starts at +0 and can never become -0,
+                // so adding (finite offset) * 0 = +-0 leaves it bit-identical to libmmd's skip (the host rejects
+                // non-finite offsets).
+                const float r = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(nrate) + __float_as_uint(ent.w));
+                ix = ix + ent.x * r;
+                iy = iy + ent.y * r;
+                iz = iz + ent.z * r;
             }
             float op[3], on[3];
             // coordinate + vertex_image (poser_impl.inl:407)

@@ -198,7 +198,7 @@ mmdgpu_status upload_model(mmdgpu_model* m) {
     std::vector<float4> ent(p.ell_node.size());
     for (size_t e = 0; e < ent.size(); ++e) {
         float slot_bits;
-        const uint32_t node = p.ell_node[e];
+        const uint32_t node = p.ell_node[e] * 4u;  // byte offset into the slot's rate table
         std::memcpy(&slot_bits, &node, 4);
         ent[e] = make_float4(p.ell_offset[3 * e], p.ell_offset[3 * e + 1], p.ell_offset[3 * e + 2], slot_bits);
     }

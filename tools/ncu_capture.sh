@@ -9,4 +9,4 @@ $cmd > gpurun_out/${tag}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${tag}_launches.csv $cmd > gpurun_out/${tag}_ncu_list.log 2>&1
 $cmd > gpurun_out/${tag}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:skin_kernel -s 3 -c 2 -f -o gpurun_out/${tag}_skin $cmd > gpurun_out/${tag}_ncu_full.log 2>&1
-tail -3 gpurun_out/${tag}_plain.log gpurun_out/${tag}_ncu_list.log gpurun_out/${tag}_ncu_full.log
+tail -n 3 gpurun_out/${tag}_ncu_full.log

@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--layout", default="soa", choices=["soa", "sokol32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather", action="store_true",
+                    help="N > 1: also time the NCCL gather of one window of baked frames to rank 0 (reported separately)")
     return ap.parse_args()
 
 
@@ -284,7 +286,6 @@ def run_mmdgpu(args):
         step(args.warmup + s)
     e1.record(stream)
     barrier()
-    clocks = sampler.stop() if sampler else None
     launches = ctx.launch_count - launches0
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")
     kernel_ms, kernel_n = ctx.profile_read()
@@ -330,6 +331,31 @@ def run_mmdgpu(args):
                "ms_per_step": float(ems.item()) / e2e_steps,
                "note": "update_range + download of every slot's deformed buffer to pinned host memory, per GPU"}
 
+    clocks = sampler.stop() if sampler else None
+
+    # ---- optional: NCCL gather of one window of baked frames to rank 0 (bake pattern; not part of `value`)
+    gather = None
+    if args.gather and world > 1 and args.layout == "soa":
+        from simple_mmd_renderer_b200 import shard
+        local_t = shard.frames_as_tensor(fr, capi.STREAM_POSITION).contiguous()
+        torch.cuda.synchronize()
+        for _ in range(2):
+            shard.gather_window(local_t, slots, root=0)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        g0.record()
+        for _ in range(reps):
+            shard.gather_window(local_t, slots, root=0)
+        g1.record()
+        barrier()
+        gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        nbytes = local_t.numel() * 4 * (world - 1)
+        gather = {"bytes_into_root_per_window": int(nbytes), "ms_per_window": float(gms.item()) / reps,
+                  "gbs_into_root": nbytes * reps / (float(gms.item()) * 1e-3) / 1e9,
+                  "note": "torch.distributed.gather (NCCL) of every rank's position plane for one window of frames"}
+
     # ---- CPU baseline (rank 0, N = 1 only): libmmd itself on a bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -361,6 +387,8 @@ def run_mmdgpu(args):
                                    "skin": kernel_ms[2] / args.steps},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
+        if gather is not None:
+            out["gather"] = gather
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

@@ -384,13 +384,54 @@ typedef enum mmdgpu_plan_array {
     MMDGPU_PLAN_ELL_BASE = 25,      /* u32 [32 n_tiles] first entry of every 32-lane group                  */
     MMDGPU_PLAN_ELL_ROUNDS = 26,    /* u32 [32 n_tiles] entries per lane (padded) of every group            */
     MMDGPU_PLAN_ELL_SLOT = 27,      /* u32 [n_ell] application slot; padding = number of application slots  */
-    MMDGPU_PLAN_ELL_OFFSET = 28     /* f32 [3 n_ell]                                                        */
+    MMDGPU_PLAN_ELL_OFFSET = 28,    /* f32 [3 n_ell]                                                        */
+    /* model data as the plan holds it (lets a PMX byte stream be checked against flat arrays on the host) */
+    MMDGPU_PLAN_POSITION = 29,      /* f32 [3 nv] */
+    MMDGPU_PLAN_NORMAL = 30,        /* f32 [3 nv] */
+    MMDGPU_PLAN_UV = 31,            /* f32 [2 nv] */
+    MMDGPU_PLAN_BONE_STATIC = 32,   /* u8  [48 nb] per-bone record read by the hierarchy kernel (host_plan.hpp) */
+    MMDGPU_PLAN_IK_DESC = 33,       /* u8  [32 n_ik] */
+    MMDGPU_PLAN_IK_LINK = 34,       /* u8  [32 n_ik_links] */
+    MMDGPU_PLAN_BONE_MORPH = 35     /* u8  [32 n] bone-morph entries grouped by bone, application order        */
 } mmdgpu_plan_array;
+
+/* Host-only: parse a PMX 2.0 / 2.1 byte stream (layout of L/reader/pmx_reader_impl.inl:16-449) and build the
+ * plan; bone / morph names are kept for VMD joins. */
+MMDGPU_API mmdgpu_status mmdgpu_plan_create_from_pmx(const void* bytes, size_t n, const mmdgpu_options* opt_or_null,
+                                                     mmdgpu_plan_t* out, char* err_buf, size_t err_buf_len);
 
 /* Returns a pointer into plan-owned memory and the element count; the pointer is valid until the plan
  * (or the model that owns it) is destroyed. */
 MMDGPU_API mmdgpu_status mmdgpu_plan_get(mmdgpu_plan_t plan, mmdgpu_plan_array which, const void** data,
                                          size_t* count);
+
+/* Host-only flattened motion: what mmdgpu_animation_create_* uploads (mmd::Motion's std::map storage,
+ * L/motion/motion.inl:128-129, as sorted, de-duplicated key arrays per model bone / morph plus the
+ * de-duplicated Bezier tables). */
+typedef struct mmdgpu_anim_plan* mmdgpu_anim_plan_t;
+MMDGPU_API mmdgpu_status mmdgpu_anim_plan_create(const mmdgpu_anim_desc* desc, uint32_t n_bones, uint32_t n_morphs,
+                                                 mmdgpu_anim_plan_t* out, char* err_buf, size_t err_buf_len);
+/* VMD byte stream joined by name against a plan that was created from PMX bytes. */
+MMDGPU_API mmdgpu_status mmdgpu_anim_plan_create_from_vmd(mmdgpu_plan_t model_plan, const void* bytes, size_t n,
+                                                          mmdgpu_anim_plan_t* out, char* err_buf, size_t err_buf_len);
+MMDGPU_API void          mmdgpu_anim_plan_destroy(mmdgpu_anim_plan_t plan);
+typedef enum mmdgpu_anim_array {
+    MMDGPU_ANIM_BONE_KEY_BEGIN = 0,  /* u32 [nb]  first key of every model bone                   */
+    MMDGPU_ANIM_BONE_KEY_COUNT = 1,  /* u32 [nb]                                                  */
+    MMDGPU_ANIM_BONE_TRACKED = 2,    /* u8  [nb]  1 if the motion registers the bone              */
+    MMDGPU_ANIM_KEY_FRAME = 3,       /* u32 [nk]  ascending inside a track, duplicates removed    */
+    MMDGPU_ANIM_KEY_T = 4,           /* f32 [4 nk] translation (w unused)                         */
+    MMDGPU_ANIM_KEY_R = 5,           /* f32 [4 nk] rotation xyzw                                  */
+    MMDGPU_ANIM_KEY_CURVE = 6,       /* u32 [4 nk] Bezier table index of X, Y, Z, R; 0xFFFFFFFF = linear */
+    MMDGPU_ANIM_TABLES = 7,          /* f32 [32 nt]                                               */
+    MMDGPU_ANIM_MORPH_KEY_BEGIN = 8, /* u32 [nm] */
+    MMDGPU_ANIM_MORPH_KEY_COUNT = 9, /* u32 [nm] */
+    MMDGPU_ANIM_MORPH_TRACKED = 10,  /* u8  [nm] */
+    MMDGPU_ANIM_MKEY_FRAME = 11,     /* u32 [nmk] */
+    MMDGPU_ANIM_MKEY_WEIGHT = 12     /* f32 [nmk] */
+} mmdgpu_anim_array;
+MMDGPU_API mmdgpu_status mmdgpu_anim_plan_get(mmdgpu_anim_plan_t plan, mmdgpu_anim_array which, const void** data,
+                                              size_t* count);
 
 /* Presampled Bezier table of Bezier::presample (L/util/math_impl.inl:1398-1428) for one VMD control
  * quadruple (x0, y0, x1, y1).  Returns 1 and leaves table untouched if the curve is linear. */

@@ -24,7 +24,8 @@ STREAM_POSITION, STREAM_NORMAL, STREAM_INTERLEAVED, STREAM_SKIN_MATRIX = 0, 1, 2
  PLAN_OP_WAVE, PLAN_WAVE_BEGIN, PLAN_WAVE_OPS, PLAN_IK_FIX_TYPE, PLAN_IK_EULER_ORDER, PLAN_APP_SLOT_MORPH,
  PLAN_APP_SLOT_PARENT, PLAN_APP_SLOT_MULT, PLAN_CSR_ROW_PTR, PLAN_CSR_SLOT, PLAN_CSR_OFFSET, PLAN_BEZIER_UNUSED,
  PLAN_WAVE_PHASE_SPLIT, PLAN_TILE_ORIG, PLAN_TILE_TYPE, PLAN_TILE_LOCAL_ID, PLAN_TILE_BONE_BEGIN, PLAN_TILE_BONES,
- PLAN_ELL_BASE, PLAN_ELL_ROUNDS, PLAN_ELL_SLOT, PLAN_ELL_OFFSET) = range(29)
+ PLAN_ELL_BASE, PLAN_ELL_ROUNDS, PLAN_ELL_SLOT, PLAN_ELL_OFFSET, PLAN_POSITION, PLAN_NORMAL, PLAN_UV,
+ PLAN_BONE_STATIC, PLAN_IK_DESC, PLAN_IK_LINK, PLAN_BONE_MORPH) = range(36)
 
 PLAN_DTYPES = {
     PLAN_SKIN_TYPE: np.uint8, PLAN_BONE_ID: np.uint16, PLAN_WEIGHT: np.float32, PLAN_ORDER_PRE: np.int32,
@@ -36,6 +37,18 @@ PLAN_DTYPES = {
     PLAN_TILE_ORIG: np.uint16, PLAN_TILE_TYPE: np.uint8, PLAN_TILE_LOCAL_ID: np.uint16,
     PLAN_TILE_BONE_BEGIN: np.uint32, PLAN_TILE_BONES: np.uint16, PLAN_ELL_BASE: np.uint32,
     PLAN_ELL_ROUNDS: np.uint32, PLAN_ELL_SLOT: np.uint32, PLAN_ELL_OFFSET: np.float32,
+    PLAN_POSITION: np.float32, PLAN_NORMAL: np.float32, PLAN_UV: np.float32, PLAN_BONE_STATIC: np.uint8,
+    PLAN_IK_DESC: np.uint8, PLAN_IK_LINK: np.uint8, PLAN_BONE_MORPH: np.uint8,
+}
+
+(ANIM_BONE_KEY_BEGIN, ANIM_BONE_KEY_COUNT, ANIM_BONE_TRACKED, ANIM_KEY_FRAME, ANIM_KEY_T, ANIM_KEY_R, ANIM_KEY_CURVE,
+ ANIM_TABLES, ANIM_MORPH_KEY_BEGIN, ANIM_MORPH_KEY_COUNT, ANIM_MORPH_TRACKED, ANIM_MKEY_FRAME,
+ ANIM_MKEY_WEIGHT) = range(13)
+ANIM_DTYPES = {
+    ANIM_BONE_KEY_BEGIN: np.uint32, ANIM_BONE_KEY_COUNT: np.uint32, ANIM_BONE_TRACKED: np.uint8,
+    ANIM_KEY_FRAME: np.uint32, ANIM_KEY_T: np.float32, ANIM_KEY_R: np.float32, ANIM_KEY_CURVE: np.uint32,
+    ANIM_TABLES: np.float32, ANIM_MORPH_KEY_BEGIN: np.uint32, ANIM_MORPH_KEY_COUNT: np.uint32,
+    ANIM_MORPH_TRACKED: np.uint8, ANIM_MKEY_FRAME: np.uint32, ANIM_MKEY_WEIGHT: np.float32,
 }
 
 # ---------------------------------------------------------------- numpy record dtypes (AoS pools)

@@ -40,6 +40,9 @@ struct mmdgpu_context {
 struct mmdgpu_plan {
     Plan plan;
 };
+struct mmdgpu_anim_plan {
+    HostAnim anim;
+};
 
 namespace {
 
@@ -511,7 +514,105 @@ MMDGPU_API mmdgpu_status mmdgpu_plan_create(const mmdgpu_model_desc* desc, const
     return MMDGPU_OK;
 }
 
+MMDGPU_API mmdgpu_status mmdgpu_plan_create_from_pmx(const void* bytes, size_t n, const mmdgpu_options* opt, mmdgpu_plan_t* out,
+                                                     char* err_buf, size_t err_buf_len) {
+    auto report = [&](const std::string& m) {
+        g_err = m;
+        if (err_buf && err_buf_len) std::snprintf(err_buf, err_buf_len, "%s", m.c_str());
+    };
+    if (!bytes || !out) { report("bytes or out is NULL"); return MMDGPU_ERR_INVALID_ARG; }
+    *out = nullptr;
+    std::string err;
+    mmdgpu_status s;
+    try {
+        ParsedModel pm;
+        s = parse_pmx(bytes, n, pm, err);
+        if (s != MMDGPU_OK) { report(err); return s; }
+        s = mmdgpu_plan_create(&pm.desc, opt, out, err_buf, err_buf_len);
+        if (s != MMDGPU_OK) return s;
+        (*out)->plan.bone_names = std::move(pm.bone_names);
+        (*out)->plan.morph_names = std::move(pm.morph_names);
+        (*out)->plan.names_utf8 = pm.utf8;
+    } catch (const std::bad_alloc&) {
+        report("host allocation failed");
+        return MMDGPU_ERR_OOM;
+    }
+    return MMDGPU_OK;
+}
+
 MMDGPU_API void mmdgpu_plan_destroy(mmdgpu_plan_t plan) { delete plan; }
+
+MMDGPU_API mmdgpu_status mmdgpu_anim_plan_create(const mmdgpu_anim_desc* desc, uint32_t n_bones, uint32_t n_morphs,
+                                                 mmdgpu_anim_plan_t* out, char* err_buf, size_t err_buf_len) {
+    auto report = [&](const std::string& m) {
+        g_err = m;
+        if (err_buf && err_buf_len) std::snprintf(err_buf, err_buf_len, "%s", m.c_str());
+    };
+    if (!desc || !out) { report("desc or out is NULL"); return MMDGPU_ERR_INVALID_ARG; }
+    *out = nullptr;
+    std::unique_ptr<mmdgpu_anim_plan> a(new (std::nothrow) mmdgpu_anim_plan());
+    if (!a) { report("host allocation failed"); return MMDGPU_ERR_OOM; }
+    std::string err;
+    mmdgpu_status s;
+    try {
+        s = build_anim(*desc, n_bones, n_morphs, a->anim, err);
+    } catch (const std::bad_alloc&) {
+        s = MMDGPU_ERR_OOM; err = "host allocation failed";
+    }
+    if (s != MMDGPU_OK) { report(err); return s; }
+    *out = a.release();
+    return MMDGPU_OK;
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_anim_plan_create_from_vmd(mmdgpu_plan_t model_plan, const void* bytes, size_t n,
+                                                          mmdgpu_anim_plan_t* out, char* err_buf, size_t err_buf_len) {
+    auto report = [&](const std::string& m) {
+        g_err = m;
+        if (err_buf && err_buf_len) std::snprintf(err_buf, err_buf_len, "%s", m.c_str());
+    };
+    if (!model_plan || !bytes || !out) { report("NULL argument"); return MMDGPU_ERR_INVALID_ARG; }
+    *out = nullptr;
+    std::string err;
+    try {
+        ParsedMotion pm;
+        mmdgpu_status s = parse_vmd(bytes, n, model_plan->plan, pm, err);
+        if (s != MMDGPU_OK) { report(err); return s; }
+        return mmdgpu_anim_plan_create(&pm.desc, model_plan->plan.nb, model_plan->plan.nm, out, err_buf, err_buf_len);
+    } catch (const std::bad_alloc&) {
+        report("host allocation failed");
+        return MMDGPU_ERR_OOM;
+    }
+}
+
+MMDGPU_API void mmdgpu_anim_plan_destroy(mmdgpu_anim_plan_t plan) { delete plan; }
+
+MMDGPU_API mmdgpu_status mmdgpu_anim_plan_get(mmdgpu_anim_plan_t plan, mmdgpu_anim_array which, const void** data, size_t* count) {
+    if (!plan || !data || !count) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "NULL argument");
+    const HostAnim& a = plan->anim;
+#define RET(vec)                \
+    do {                        \
+        *data = (vec).data();   \
+        *count = (vec).size();  \
+        return MMDGPU_OK;       \
+    } while (0)
+    switch (which) {
+    case MMDGPU_ANIM_BONE_KEY_BEGIN: RET(a.bone_key_begin);
+    case MMDGPU_ANIM_BONE_KEY_COUNT: RET(a.bone_key_count);
+    case MMDGPU_ANIM_BONE_TRACKED: RET(a.bone_tracked);
+    case MMDGPU_ANIM_KEY_FRAME: RET(a.key_frame);
+    case MMDGPU_ANIM_KEY_T: RET(a.key_T);
+    case MMDGPU_ANIM_KEY_R: RET(a.key_R);
+    case MMDGPU_ANIM_KEY_CURVE: RET(a.key_curve);
+    case MMDGPU_ANIM_TABLES: RET(a.tables);
+    case MMDGPU_ANIM_MORPH_KEY_BEGIN: RET(a.morph_key_begin);
+    case MMDGPU_ANIM_MORPH_KEY_COUNT: RET(a.morph_key_count);
+    case MMDGPU_ANIM_MORPH_TRACKED: RET(a.morph_tracked);
+    case MMDGPU_ANIM_MKEY_FRAME: RET(a.mkey_frame);
+    case MMDGPU_ANIM_MKEY_WEIGHT: RET(a.mkey_weight);
+    }
+#undef RET
+    return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "unknown animation array");
+}
 
 MMDGPU_API mmdgpu_status mmdgpu_plan_get(mmdgpu_plan_t plan, mmdgpu_plan_array which, const void** data, size_t* count) {
     if (!plan || !data || !count) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "NULL argument");
@@ -551,6 +652,17 @@ MMDGPU_API mmdgpu_status mmdgpu_plan_get(mmdgpu_plan_t plan, mmdgpu_plan_array w
     case MMDGPU_PLAN_ELL_ROUNDS: RET(p.ell_rounds);
     case MMDGPU_PLAN_ELL_SLOT: RET(p.ell_node);
     case MMDGPU_PLAN_ELL_OFFSET: RET(p.ell_offset);
+    case MMDGPU_PLAN_POSITION: RET(p.position);
+    case MMDGPU_PLAN_NORMAL: RET(p.normal);
+    case MMDGPU_PLAN_UV: RET(p.uv);
+    case MMDGPU_PLAN_BONE_STATIC:
+        *data = p.bones.data(); *count = p.bones.size() * sizeof(BoneStatic); return MMDGPU_OK;
+    case MMDGPU_PLAN_IK_DESC:
+        *data = p.iks.data(); *count = p.iks.size() * sizeof(IkDesc); return MMDGPU_OK;
+    case MMDGPU_PLAN_IK_LINK:
+        *data = p.links.data(); *count = p.links.size() * sizeof(IkLink); return MMDGPU_OK;
+    case MMDGPU_PLAN_BONE_MORPH:
+        *data = p.bone_morph_entries.data(); *count = p.bone_morph_entries.size() * sizeof(BoneMorphEntry); return MMDGPU_OK;
     default: break;
     }
 #undef RET

@@ -89,7 +89,12 @@ SIGNATURES = {
     "mmdgpu_host_alloc": (C.c_int, [_sz, _PP]),
     "mmdgpu_host_free": (None, [_vp]),
     "mmdgpu_plan_create": (C.c_int, [_vp, _vp, _PP, C.c_char_p, _sz]),
+    "mmdgpu_plan_create_from_pmx": (C.c_int, [_vp, _sz, _vp, _PP, C.c_char_p, _sz]),
     "mmdgpu_plan_destroy": (None, [_vp]),
+    "mmdgpu_anim_plan_create": (C.c_int, [_vp, _u32, _u32, _PP, C.c_char_p, _sz]),
+    "mmdgpu_anim_plan_create_from_vmd": (C.c_int, [_vp, _vp, _sz, _PP, C.c_char_p, _sz]),
+    "mmdgpu_anim_plan_destroy": (None, [_vp]),
+    "mmdgpu_anim_plan_get": (C.c_int, [_vp, C.c_int, _PP, C.POINTER(_sz)]),
     "mmdgpu_plan_get": (C.c_int, [_vp, C.c_int, _PP, C.POINTER(_sz)]),
     "mmdgpu_bezier_table": (C.c_int, [_vp, _vp]),
 }

@@ -22,7 +22,7 @@ import numpy as np
 from . import capi
 from .lib import MmdGpuError, check, load
 
-__all__ = ["Context", "Model", "Motion", "Frames", "Poser", "MotionPlayer", "PoseImage", "plan_arrays",
+__all__ = ["Context", "Model", "Motion", "Frames", "Poser", "MotionPlayer", "PoseImage", "plan_arrays", "HostPlan",
            "bezier_table", "MmdGpuError"]
 
 
@@ -384,6 +384,78 @@ def plan_arrays(model_arrays: dict, extensions: bool = False) -> dict:
     finally:
         lib.mmdgpu_plan_destroy(h)
         del keep
+
+
+def _arrays_from(getter, handle, dtypes) -> dict:
+    out = {}
+    for which, dt in dtypes.items():
+        p, n = C.c_void_p(), C.c_size_t()
+        check(getter(handle, which, C.byref(p), C.byref(n)))
+        cnt = int(n.value)
+        if cnt == 0:
+            out[which] = np.zeros(0, dt)
+        else:
+            buf = (C.c_char * (cnt * np.dtype(dt).itemsize)).from_address(p.value)
+            out[which] = np.frombuffer(buf, dtype=dt).copy()
+    return out
+
+
+class HostPlan:
+    """Host-only plan handle (no GPU): from flat arrays or PMX bytes; `anim_*` flatten motions against it."""
+
+    def __init__(self, arrays: dict | None = None, pmx_bytes: bytes | None = None, extensions: bool = False):
+        self.lib = load()
+        opt = capi.Options()
+        opt.extensions = 1 if extensions else 0
+        h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        if arrays is not None:
+            desc, keep = capi.model_desc(arrays)
+            st = self.lib.mmdgpu_plan_create(C.byref(desc), C.byref(opt), C.byref(h), err, 512)
+        else:
+            buf = (C.c_char * len(pmx_bytes)).from_buffer_copy(pmx_bytes)
+            st = self.lib.mmdgpu_plan_create_from_pmx(buf, len(pmx_bytes), C.byref(opt), C.byref(h), err, 512)
+        if st != capi.OK:
+            raise MmdGpuError(st, err.value.decode("utf-8", "replace"))
+        self.h = h
+
+    def arrays(self) -> dict:
+        return _plan_to_dict(self.lib, self.h)
+
+    def anim_from_arrays(self, motion: dict, n_bones: int, n_morphs: int) -> dict:
+        desc, keep = capi.anim_desc(motion)
+        h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        st = self.lib.mmdgpu_anim_plan_create(C.byref(desc), int(n_bones), int(n_morphs), C.byref(h), err, 512)
+        if st != capi.OK:
+            raise MmdGpuError(st, err.value.decode("utf-8", "replace"))
+        try:
+            return _arrays_from(self.lib.mmdgpu_anim_plan_get, h, capi.ANIM_DTYPES)
+        finally:
+            self.lib.mmdgpu_anim_plan_destroy(h)
+
+    def anim_from_vmd(self, vmd_bytes: bytes) -> dict:
+        buf = (C.c_char * len(vmd_bytes)).from_buffer_copy(vmd_bytes)
+        h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        st = self.lib.mmdgpu_anim_plan_create_from_vmd(self.h, buf, len(vmd_bytes), C.byref(h), err, 512)
+        if st != capi.OK:
+            raise MmdGpuError(st, err.value.decode("utf-8", "replace"))
+        try:
+            return _arrays_from(self.lib.mmdgpu_anim_plan_get, h, capi.ANIM_DTYPES)
+        finally:
+            self.lib.mmdgpu_anim_plan_destroy(h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mmdgpu_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def bezier_table(ctrl4) -> np.ndarray | None:

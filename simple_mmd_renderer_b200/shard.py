@@ -1,0 +1,111 @@
+"""Multi-GPU decomposition of the deformation path: one process per GPU, no data-path collective.
+
+The path shards where the reference's work is independent:
+  * crowd  — instances are independent mmd::Poser objects: contiguous instance blocks per rank;
+  * bake   — with physics off a frame is a pure function of its index (poser_impl.inl:362-377 resets all
+             per-bone scratch every frame): contiguous frame ranges per rank.
+The model (static streams, morph table, bone program) and the clips are replicated per GPU.  The only
+communication is the optional final gather of baked vertex buffers, windowed because a whole bake does not fit
+one GPU (10 k frames x 24 MB = 240 GB): `gather_window` moves one window of frames per rank to the root over
+torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def split_range(n: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous, balanced block [lo, hi) of range(n) owned by `rank`; blocks differ by at most one item."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad world / rank")
+    return n * rank // world, n * (rank + 1) // world
+
+
+def owner_of(i: int, n: int, world: int) -> int:
+    """Rank whose block contains item i (inverse of split_range)."""
+    if not (0 <= i < n):
+        raise ValueError("item out of range")
+    r = (i * world) // n
+    while split_range(n, world, r)[1] <= i:
+        r += 1
+    while split_range(n, world, r)[0] > i:
+        r -= 1
+    return r
+
+
+def bake_windows(frame_lo: int, frame_hi: int, window: int):
+    """(first_frame, n_frames) chunks a rank evaluates for its frame range; one chunk = one update_range call."""
+    f = frame_lo
+    while f < frame_hi:
+        n = min(window, frame_hi - f)
+        yield f, n
+        f += n
+
+
+def n_windows(n_frames_total: int, world: int, window: int) -> int:
+    """Number of gather rounds: every rank must join every collective, so all use the longest rank's count."""
+    longest = max(split_range(n_frames_total, world, r)[1] - split_range(n_frames_total, world, r)[0] for r in range(world))
+    return (longest + window - 1) // window
+
+
+class DeviceView:
+    """Zero-copy torch view of a libmmdgpu device buffer (via __cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, shape, strides_bytes=None, typestr: str = "<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 3,
+                                         "strides": None if strides_bytes is None else tuple(int(x) for x in strides_bytes)}
+
+
+def frames_as_tensor(frames, stream_id: int, n_slots: int | None = None):
+    """torch tensor [n_slots, nv, 3] (SoA streams) or [n_slots, nv, 8] (interleaved) over the frames object's
+    device output; slots are nv_pad apart, so the view is strided."""
+    import torch
+    from . import capi
+    ptr, stride = frames.device_ptr(stream_id)
+    nv = frames.model.n_vertices
+    width = 8 if stream_id == capi.STREAM_INTERLEAVED else 3
+    n = frames.n_slots if n_slots is None else n_slots
+    view = DeviceView(ptr, (n, nv, width), (stride, width * 4, 4))
+    return torch.as_tensor(view, device=f"cuda:{frames.ctx.device}")
+
+
+def gather_window(local, n_valid: int, root: int = 0, group=None):
+    """Gather one window of baked frames to `root`.
+
+    `local` is this rank's [window, nv, c] tensor (device tensor under NCCL, CPU tensor under gloo); only the first
+    `n_valid` frames are meaningful (the last window of a rank may be short, and a rank that has run out of
+    frames still joins with n_valid = 0).  Returns on the root a list of (rank, tensor[:n_valid_of_rank]) in rank
+    order, elsewhere None.  Rank order == frame order because frame ranges are contiguous blocks by rank.
+    """
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    counts = torch.zeros(world, dtype=torch.int64, device=local.device)
+    counts[rank] = n_valid
+    dist.all_reduce(counts, group=group)
+    buf = local if local.is_contiguous() else local.contiguous()
+    if rank == root:
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        dist.gather(buf, parts, dst=root, group=group)
+        return [(r, parts[r][: int(counts[r].item())]) for r in range(world)]
+    dist.gather(buf, None, dst=root, group=group)
+    return None
+
+
+def assemble(windows, n_frames_total: int, world: int):
+    """Root-side: concatenate what `gather_window` returned over all windows into frame order (numpy / CPU torch)."""
+    per_rank = [[] for _ in range(world)]
+    for parts in windows:
+        for r, t in parts:
+            if t.shape[0]:
+                per_rank[r].append(t)
+    out = []
+    for r in range(world):
+        lo, hi = split_range(n_frames_total, world, r)
+        got = sum(t.shape[0] for t in per_rank[r])
+        if got != hi - lo:
+            raise RuntimeError(f"rank {r} delivered {got} frames, expected {hi - lo}")
+        out.extend(per_rank[r])
+    return out

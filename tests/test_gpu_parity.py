@@ -202,3 +202,101 @@ def test_c3_full_size(ctx):
     fr.update(a, [3, 144])
     for k, f in enumerate((3, 144)):
         _check_frame(fr, k, orc.run_frame(f), f"C3 frame {f}")
+
+
+def test_pmx_and_vmd_byte_streams_drive_the_same_result(ctx):
+    """Row 8f-2: a model created from PMX bytes and a clip joined from VMD bytes by (Japanese) names."""
+    import pmxio
+    cfg, model, motion = synth_case("tiny_full")
+    fixed = dict(model)
+    ap = model["bone_append_parent"].copy()
+    ap[(ap < 0) | (ap >= model["n_bones"])] = -1
+    fixed["bone_append_parent"] = ap
+    keep = np.flatnonzero(motion["bone_track_key_count"] > 0)      # a VMD cannot hold an empty registered track
+    mo = dict(motion)
+    mo["n_bone_tracks"] = int(keep.size)
+    for k in ("bone_track_bone", "bone_track_key_begin", "bone_track_key_count"):
+        mo[k] = motion[k][keep]
+    orc = _oracle(fixed, mo)
+    m = Model(ctx, pmx_bytes=pmxio.write_pmx(fixed, version=2.1))
+    assert m.find_bone(pmxio.bone_name(3).encode("utf-16-le")) == 3
+    assert m.find_morph("nope".encode("utf-16-le")) == -1
+    a = Motion(m, vmd_bytes=pmxio.write_vmd(mo))
+    assert a.GetLength() == int(max(mo["bone_keys"]["frame"].max(), mo["morph_keys"]["frame"].max()))
+    frames = [0, 9, 44, 90]
+    fr = Frames(m, 1, len(frames))
+    fr.update(a, frames)
+    for k, f in enumerate(frames):
+        _check_frame(fr, k, orc.run_frame(f), f"pmx/vmd frame {f}")
+
+
+def test_many_slots_span_several_work_items(ctx):
+    """More slots than one CTA walks: chunk boundaries and the double-buffered palette staging, odd and even runs."""
+    cfg, model, motion = synth_case("tiny_full")
+    orc = _oracle(model, motion)
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    n = 203
+    fr = Frames(m, 1, n)
+    fr.update_range(a, [0], 1)
+    for k in list(range(0, n, 17)) + [1, 2, n - 2, n - 1]:
+        ref = orc.run_frame(k)
+        assert_bitwise(fr.download(k, capi.STREAM_POSITION), ref["pos"], f"slot {k} pos")
+        assert_bitwise(fr.download(k, capi.STREAM_NORMAL), ref["nrm"], f"slot {k} nrm")
+
+
+def test_device_view_and_async_download(ctx):
+    """Zero-copy torch view of the output (what the NCCL gather sends) and the pinned-memory download path."""
+    import torch
+    from simple_mmd_renderer_b200 import shard
+    cfg, model, motion = synth_case("tiny")
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    fr = Frames(m, 1, 5)
+    fr.update_range(a, [10], 3)
+    ctx.synchronize()
+    t = shard.frames_as_tensor(fr, capi.STREAM_POSITION)
+    assert t.shape == (5, m.n_vertices, 3) and t.is_cuda
+    nv = m.n_vertices
+    host = torch.empty(5 * nv * 12, dtype=torch.uint8, pin_memory=True)
+    fr.download_async(0, 5, capi.STREAM_POSITION, host.data_ptr(), host.numel())
+    ctx.synchronize()
+    got = host.view(torch.float32).reshape(5, nv, 3).numpy()
+    for k in range(5):
+        want = fr.download(k, capi.STREAM_POSITION)
+        assert_bitwise(got[k], want, f"async slot {k}")
+        assert_bitwise(t[k].cpu().numpy(), want, f"view slot {k}")
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_full", "small"])
+def test_gpu_matches_libmmd_golden_fixtures(ctx, name):
+    """The committed libmmd-generated fixtures (tests/golden), independent of the C restatement."""
+    from golden_util import check_against_golden, load_golden
+    cfg, model, motion = synth_case(name)
+    g = load_golden(name)
+    frames = [int(f) for f in g["frames"]]
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    fr = Frames(m, 1, len(frames))
+    fr.update(a, frames)
+    for k, f in enumerate(frames):
+        got = dict(pos=fr.download(k, capi.STREAM_POSITION), nrm=fr.download(k, capi.STREAM_NORMAL),
+                   skin=fr.bone_matrices(k), local=fr.bone_local_matrices(k), poses=fr.bone_poses(k),
+                   rates=fr.morph_rates(k))
+        check_against_golden(g, f, got, f"{name} frame {f}")
+
+
+def test_random_binding_stress(ctx):
+    """Random bone binding: every tile touches (almost) every bone — the large tile-local palette path."""
+    from dataclasses import replace
+    from simple_mmd_renderer_b200 import synth
+    cfg = replace(synth.SMALL, name="small_random", config_id=31, binding="random", n_bones=300)
+    model = synth.make_model(cfg)
+    motion = synth.make_motion(cfg, model)
+    orc = _oracle(model, motion)
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    fr = Frames(m, 1, 3)
+    fr.update(a, [5, 60, 61])
+    for k, f in enumerate((5, 60, 61)):
+        _check_frame(fr, k, orc.run_frame(f), f"random binding frame {f}")

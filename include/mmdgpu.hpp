@@ -1,0 +1,228 @@
+// mmdgpu.hpp — header-only C++ mirror of the libmmd classes simple_mmd_renderer's frame loop drives
+// (main.cpp:1786-1825, :820-863), implemented on the mmdgpu_* C-ABI (mmdgpu.h).
+//
+//   libmmd (L/ = 3rd_party/libmmd/include/mmd/)                     here
+//   --------------------------------------------------------------  ---------------------------------------------
+//   mmd::Model + PmxReader::ReadModel   L/reader/pmx_reader_impl.inl  mmdgpu::Model        (PMX bytes or flat arrays)
+//   mmd::Motion + VmdReader::ReadMotion L/reader/vmd_reader_impl.inl  mmdgpu::Motion       (VMD bytes or flat arrays)
+//   mmd::Poser                          L/motion/poser.inl:15-45      mmdgpu::Poser        same method names, pose_image
+//   mmd::MotionPlayer                   L/motion/poser.inl:184-198    mmdgpu::MotionPlayer SeekFrame / SeekTime
+//
+// Error behaviour: libmmd's engine methods are void and never throw; its readers throw mmd::exception.  Here the
+// constructors that parse or allocate throw mmdgpu::Error; the per-frame methods throw only on a CUDA failure
+// (there is no CPU fallback to continue on).
+#ifndef MMDGPU_HPP_INCLUDED
+#define MMDGPU_HPP_INCLUDED
+
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "mmdgpu.h"
+
+namespace mmdgpu {
+
+class Error : public std::runtime_error {
+public:
+    Error(mmdgpu_status s, const std::string& what) : std::runtime_error(what), status(s) {}
+    mmdgpu_status status;
+};
+
+// Same member spelling as mmd::Vector3f where main.cpp reads it (pos.p.x, main.cpp:843-855).
+struct Vector3f {
+    struct { float x, y, z; } p;
+};
+static_assert(sizeof(Vector3f) == 12, "Vector3f must be three packed floats");
+
+class Context {
+public:
+    explicit Context(int device = 0, void* cuda_stream = nullptr) {
+        mmdgpu_status s = mmdgpu_context_create(device, cuda_stream, &h_);
+        if (s != MMDGPU_OK) throw Error(s, std::string("mmdgpu_context_create: ") + mmdgpu_last_error(nullptr));
+    }
+    ~Context() { mmdgpu_context_destroy(h_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    mmdgpu_context_t handle() const { return h_; }
+    void check(mmdgpu_status s, const char* what) const {
+        if (s != MMDGPU_OK) throw Error(s, std::string(what) + ": " + mmdgpu_last_error(h_));
+    }
+    void Synchronize() const { check(mmdgpu_context_synchronize(h_), "mmdgpu_context_synchronize"); }
+
+private:
+    mmdgpu_context_t h_ = nullptr;
+};
+
+inline std::vector<unsigned char> ReadFile(const std::string& path) {
+    std::FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) throw Error(MMDGPU_ERR_INVALID_ARG, "cannot open " + path);
+    std::vector<unsigned char> buf;
+    unsigned char tmp[1 << 16];
+    size_t n;
+    while ((n = std::fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + n);
+    std::fclose(f);
+    return buf;
+}
+
+class Model {
+public:
+    Model(Context& ctx, const void* pmx_bytes, size_t n, const mmdgpu_options* opt = nullptr) : ctx_(ctx) {
+        ctx_.check(mmdgpu_model_create_from_pmx(ctx.handle(), pmx_bytes, n, opt, &h_), "mmdgpu_model_create_from_pmx");
+    }
+    Model(Context& ctx, const mmdgpu_model_desc& desc, const mmdgpu_options* opt = nullptr) : ctx_(ctx) {
+        ctx_.check(mmdgpu_model_create_from_arrays(ctx.handle(), &desc, opt, &h_), "mmdgpu_model_create_from_arrays");
+    }
+    ~Model() { mmdgpu_model_destroy(h_); }
+    Model(const Model&) = delete;
+    Model& operator=(const Model&) = delete;
+    size_t GetVertexNum() const { return mmdgpu_model_vertex_count(h_); }
+    size_t GetBoneNum() const { return mmdgpu_model_bone_count(h_); }
+    size_t GetMorphNum() const { return mmdgpu_model_morph_count(h_); }
+    mmdgpu_model_t handle() const { return h_; }
+    Context& context() const { return ctx_; }
+
+private:
+    Context& ctx_;
+    mmdgpu_model_t h_ = nullptr;
+};
+
+class Motion {
+public:
+    Motion(Model& model, const void* vmd_bytes, size_t n) : model_(model) {
+        model.context().check(mmdgpu_animation_create_from_vmd(model.context().handle(), model.handle(), vmd_bytes, n, &h_),
+                              "mmdgpu_animation_create_from_vmd");
+    }
+    Motion(Model& model, const mmdgpu_anim_desc& desc) : model_(model) {
+        model.context().check(mmdgpu_animation_create_from_arrays(model.context().handle(), model.handle(), &desc, &h_),
+                              "mmdgpu_animation_create_from_arrays");
+    }
+    ~Motion() { mmdgpu_animation_destroy(h_); }
+    Motion(const Motion&) = delete;
+    Motion& operator=(const Motion&) = delete;
+    size_t GetLength() const { return mmdgpu_animation_length(h_); }  // Motion::GetLength, motion_impl.inl:242-245
+    mmdgpu_animation_t handle() const { return h_; }
+    Model& model() const { return model_; }
+
+private:
+    Model& model_;
+    mmdgpu_animation_t h_ = nullptr;
+};
+
+class Poser {
+public:
+    // Poser::pose_image (L/motion/poser.inl:17-20).  The device owns the deformed buffer; each vector here is a
+    // host mirror that is downloaded on first access after Deform().
+    class LazyVectors {
+    public:
+        size_t size() const { return owner_->model_.GetVertexNum(); }
+        const Vector3f& operator[](size_t i) const { return data()[i]; }
+        const Vector3f* data() const {
+            if (!valid_) {
+                host_.resize(size());
+                owner_->model_.context().check(
+                    mmdgpu_frames_download(owner_->frames_, 0, stream_, host_.data(), host_.size() * sizeof(Vector3f)),
+                    "mmdgpu_frames_download");
+                valid_ = true;
+            }
+            return host_.data();
+        }
+
+    private:
+        friend class Poser;
+        LazyVectors(Poser* owner, mmdgpu_stream_id id) : owner_(owner), stream_(id) {}
+        Poser* owner_;
+        mmdgpu_stream_id stream_;
+        mutable std::vector<Vector3f> host_;
+        mutable bool valid_ = false;
+    };
+    struct PoseImage {
+        LazyVectors coordinates, normals;
+    } pose_image;
+
+    // Poser::Poser (poser_impl.inl:16-128) ends with ResetPosing(); Deform();
+    explicit Poser(Model& model, mmdgpu_layout layout = MMDGPU_LAYOUT_SOA_POS_NRM)
+        : pose_image{LazyVectors(this, MMDGPU_STREAM_POSITION), LazyVectors(this, MMDGPU_STREAM_NORMAL)},
+          model_(model),
+          layout_(layout) {
+        check(mmdgpu_frames_create(model.context().handle(), model.handle(), 1, 1, layout, &frames_), "mmdgpu_frames_create");
+        ResetPosing();
+        Deform();
+    }
+    ~Poser() { mmdgpu_frames_destroy(frames_); }
+    Poser(const Poser&) = delete;
+    Poser& operator=(const Poser&) = delete;
+
+    // poser_impl.inl:130-140 — zero rates, identity poses, then a full Pre + PostPhysicsPosing
+    void ResetPosing() {
+        check(mmdgpu_reset_posing(frames_), "mmdgpu_reset_posing");
+        PrePhysicsPosing();
+        PostPhysicsPosing();
+    }
+    void SetBonePose(size_t index, const float translation[3], const float rotation_xyzw[4]) {
+        check(mmdgpu_set_bone_pose(frames_, 0, uint32_t(index), translation, rotation_xyzw), "mmdgpu_set_bone_pose");
+    }
+    void SetMorphPose(size_t index, float weight) {
+        check(mmdgpu_set_morph_pose(frames_, 0, uint32_t(index), weight), "mmdgpu_set_morph_pose");
+    }
+    void PrePhysicsPosing() { check(mmdgpu_pre_physics_posing(frames_), "mmdgpu_pre_physics_posing"); }
+    void PostPhysicsPosing() { check(mmdgpu_post_physics_posing(frames_), "mmdgpu_post_physics_posing"); }
+    void Deform() {
+        check(mmdgpu_deform(frames_), "mmdgpu_deform");
+        pose_image.coordinates.valid_ = pose_image.normals.valid_ = false;
+    }
+    // ResetPosing + SeekFrame + Pre + Post + Deform in one call (the fused path; physics off).
+    void Update(const Motion& motion, size_t frame) {
+        mmdgpu_animation_t a = motion.handle();
+        const uint32_t f = uint32_t(frame);
+        check(mmdgpu_update(frames_, &a, &f), "mmdgpu_update");
+        pose_image.coordinates.valid_ = pose_image.normals.valid_ = false;
+    }
+    // Physics hand-back between Pre and Post (PoserMotionState::Synchronize / Fix, mmd-bullet_impl.inl:34-56).
+    void OverrideSkinningMatrix(size_t bone, const float skinning[16], const float* local_or_null = nullptr) {
+        check(mmdgpu_set_skinning_matrix_override(frames_, 0, uint32_t(bone), skinning, local_or_null),
+              "mmdgpu_set_skinning_matrix_override");
+    }
+    // The 32-byte Vertex{pos*0.1f, normal, uv} records main.cpp:838-859 builds, ready for sg_update_buffer
+    // (requires layout = MMDGPU_LAYOUT_INTERLEAVED_SOKOL32).
+    void DownloadInterleaved(void* dst_vertices) {
+        check(mmdgpu_frames_download(frames_, 0, MMDGPU_STREAM_INTERLEAVED, dst_vertices, model_.GetVertexNum() * 32),
+              "mmdgpu_frames_download");
+    }
+    void DownloadSkinningMatrices(float* dst_nb_x_16) { check(mmdgpu_bone_matrices_download(frames_, 0, dst_nb_x_16), "mmdgpu_bone_matrices_download"); }
+    const Model& GetModel() const { return model_; }
+    Model& GetModel() { return model_; }
+    mmdgpu_frames_t frames() const { return frames_; }
+
+private:
+    void check(mmdgpu_status s, const char* what) const { model_.context().check(s, what); }
+    Model& model_;
+    mmdgpu_layout layout_;
+    mmdgpu_frames_t frames_ = nullptr;
+};
+
+class MotionPlayer {
+public:
+    MotionPlayer(const Motion& motion, Poser& poser) : motion_(motion), poser_(poser) {
+        if (&motion.model() != &poser.GetModel()) throw Error(MMDGPU_ERR_INVALID_ARG, "motion and poser use different models");
+    }
+    // MotionPlayer::SeekFrame(size_t), poser_impl.inl:539-546
+    void SeekFrame(size_t frame) {
+        mmdgpu_animation_t a = motion_.handle();
+        const uint32_t f = uint32_t(frame);
+        poser_.GetModel().context().check(mmdgpu_seek_frame(poser_.frames(), &a, &f), "mmdgpu_seek_frame");
+    }
+    // main.cpp only uses SeekFrame (main.cpp:1793-1796); sub-frame sampling (SeekTime(double),
+    // motion_impl.inl:321-380) is not on the path and is served at the integer frame.
+    void SeekTime(double time_seconds) { SeekFrame(size_t(time_seconds * 30.0)); }
+
+private:
+    const Motion& motion_;
+    Poser& poser_;
+};
+
+}  // namespace mmdgpu
+
+#endif  // MMDGPU_HPP_INCLUDED

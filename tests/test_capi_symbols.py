@@ -115,3 +115,13 @@ def test_bezier_table_linear_and_endpoints():
     assert t is not None and t.shape == (32,)
     assert 0 < t[0] < 1e-5 and abs(t[31] - 1.0) < 1e-5      # tab[0] is ~2.7e-7, not 0
     assert (np.diff(t) > -1e-6).all()
+
+
+def test_cxx_shim_and_example_compile_and_link(tmp_path):
+    """include/mmdgpu.hpp (the libmmd-named C++ mirror) and examples/headless_update.cc build against the library."""
+    exe = tmp_path / "headless_update"
+    r = subprocess.run(["g++", "-std=c++14", "-O1", "-Wall", "-Wextra", "-Werror", f"-I{ROOT}/include",
+                        f"{ROOT}/examples/headless_update.cc", lib.SO_PATH, "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr

@@ -300,3 +300,27 @@ def test_random_binding_stress(ctx):
     fr.update(a, [5, 60, 61])
     for k, f in enumerate((5, 60, 61)):
         _check_frame(fr, k, orc.run_frame(f), f"random binding frame {f}")
+
+
+def test_cxx_shim_runs_the_libmmd_frame_loop(ctx, tmp_path):
+    """examples/headless_update.cc: mmdgpu::Poser / MotionPlayer (include/mmdgpu.hpp) driven exactly like
+    main.cpp:1786-1825, on PMX / VMD files, compared with the oracle."""
+    import subprocess
+    import pmxio
+    from conftest import ROOT
+    from simple_mmd_renderer_b200 import lib
+    cfg, model, motion = synth_case("tiny")
+    (tmp_path / "m.pmx").write_bytes(pmxio.write_pmx(model))
+    (tmp_path / "m.vmd").write_bytes(pmxio.write_vmd(motion))
+    exe = tmp_path / "headless_update"
+    r = subprocess.run(["g++", "-std=c++14", "-O2", f"-I{ROOT}/include", f"{ROOT}/examples/headless_update.cc", lib.SO_PATH,
+                        "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = tmp_path / "out.bin"
+    r = subprocess.run([str(exe), str(tmp_path / "m.pmx"), str(tmp_path / "m.vmd"), "20", "14", str(out)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = np.fromfile(out, np.float32).reshape(2, -1, 3)
+    ref = _oracle(model, motion).run_frame(33)
+    assert_bitwise(got[0], ref["pos"], "C++ shim coordinates")
+    assert_bitwise(got[1], ref["nrm"], "C++ shim normals")

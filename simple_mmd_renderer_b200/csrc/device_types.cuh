@@ -42,7 +42,7 @@ struct DevModel {
     // program: ops grouped by wave; op word = kind << 28 | arg
     const uint32_t* wave_begin;
     const uint32_t* wave_ops;
-    uint32_t n_waves, phase_split;
+    uint32_t n_waves, phase_split, n_ops;
     // morph application slots
     const int32_t* node_morph;
     const int32_t* node_parent;

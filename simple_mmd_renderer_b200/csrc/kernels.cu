@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(128) pose_sample_kernel(DevModel M, const DevA
 // K2 — hierarchy.  One warp per slot; lanes execute the ops of one wave in parallel.
 // =================================================================================================
 struct SlotState {
+    const BoneStatic* bones;  // static per-bone records (global memory, or the CTA's shared-memory copy)
     const float4* poseR;
     const float4* poseT;
     float4* totR;
@@ -160,7 +161,7 @@ __device__ __forceinline__ void store_local(float4* p, const Mat43& M) {
 }
 __device__ __forceinline__ BoneStatic load_bone(const BoneStatic* __restrict__ bones, int32_t b) {
     const float4* p = reinterpret_cast<const float4*>(bones + b);
-    const float4 a = __ldg(p), c = __ldg(p + 1), d = __ldg(p + 2);
+    const float4 a = p[0], c = p[1], d = p[2];
     BoneStatic s;
     s.local_offset[0] = a.x; s.local_offset[1] = a.y; s.local_offset[2] = a.z; s.parent = __float_as_int(a.w);
     s.position[0] = c.x; s.position[1] = c.y; s.position[2] = c.z; s.append_parent = __float_as_int(c.w);
@@ -186,7 +187,7 @@ __device__ __forceinline__ void set_local(const SlotState& S, const BoneStatic& 
 
 // Poser::UpdateBoneTransform(size_t) without the IK part, L/motion/poser_impl.inl:142-166
 __device__ __noinline__ void eval_bone(const DevModel& M, const SlotState& S, int32_t b) {
-    const BoneStatic s = load_bone(M.bones, b);
+    const BoneStatic s = load_bone(S.bones, b);
     const Quat R = q_from(S.poseR[b]);
     const float4 T = S.poseT[b];
     Quat mR = q_identity();
@@ -227,7 +228,7 @@ __device__ __forceinline__ Vec3 local_pos(const SlotState& S, int32_t b) {
 __device__ __noinline__ void solve_ik(const DevModel& M, const SlotState& S, const IkDesc k) {
     const IkLink* __restrict__ links = M.links + k.link_begin;
     const int nl = k.link_count;
-    for (int i = 0; i < nl; ++i) S.ikR[M.bones[links[i].bone].link_slot] = make_float4(0.f, 0.f, 0.f, 1.f);
+    for (int i = 0; i < nl; ++i) S.ikR[S.bones[links[i].bone].link_slot] = make_float4(0.f, 0.f, 0.f, 1.f);
     const Vec3 ik_pos = local_pos(S, k.bone);
     for (int i = 0; i < nl; ++i) eval_bone(M, S, links[nl - i - 1].bone);
     eval_bone(M, S, k.target);
@@ -240,7 +241,7 @@ __device__ __noinline__ void solve_ik(const DevModel& M, const SlotState& S, con
         for (int j = 0; j < nl; ++j) {
             const IkLink L = links[j];
             if (L.fix == 4) continue;
-            const BoneStatic ls = load_bone(M.bones, L.bone);
+            const BoneStatic ls = load_bone(S.bones, L.bone);
             const Vec3 lp = local_pos(S, L.bone);
             Vec3 td = v_normalize(Vec3{lp.x - tp.x, lp.y - tp.y, lp.z - tp.z});
             Vec3 id = v_normalize(Vec3{lp.x - ik_pos.x, lp.y - ik_pos.y, lp.z - ik_pos.z});
@@ -279,7 +280,7 @@ __device__ __noinline__ void solve_ik(const DevModel& M, const SlotState& S, con
             S.ikR[ls.link_slot] = q_to4(ikR);
             for (int c = j; c >= 0; --c) {  // links j .. 0 (poser_impl.inl:292-300)
                 const int32_t cb = links[c].bone;
-                const BoneStatic cs = load_bone(M.bones, cb);
+                const BoneStatic cs = load_bone(S.bones, cb);
                 const Quat tot = q_mul(q_from(S.ikR[cs.link_slot]), q_from(S.preIK[cs.link_slot]));
                 S.totR[cb] = q_to4(tot);
                 set_local(S, cs, cb, tot, S.totT[cb]);
@@ -295,7 +296,7 @@ __device__ __noinline__ void solve_ik(const DevModel& M, const SlotState& S, con
 // Poser::UpdateBoneSkinningMatrix, L/motion/poser_impl.inl:320-326: skin = global_offset * local, stored as
 // the three columns the skinning kernel consumes.
 __device__ __forceinline__ void skin_bone(const DevModel& M, const SlotState& S, int32_t b) {
-    const BoneStatic s = load_bone(M.bones, b);
+    const BoneStatic s = load_bone(S.bones, b);
     const Mat43 L = load_local(S.local + 3 * (size_t)b);
     const float g30 = -s.position[0], g31 = -s.position[1], g32 = -s.position[2];
     float4 col[3];
@@ -321,6 +322,7 @@ __global__ void __launch_bounds__(32 * kHierWarps) hierarchy_kernel(DevModel M, 
     const uint32_t slot = blockIdx.x * kHierWarps + (threadIdx.x >> 5);
     if (slot >= F.n_slots) return;
     SlotState S;
+    S.bones = M.bones;
     S.poseR = F.poseR + (size_t)slot * M.nb;
     S.poseT = F.poseT + (size_t)slot * M.nb;
     S.totR = F.totR + (size_t)slot * M.nb;
@@ -402,6 +404,156 @@ __global__ void __launch_bounds__(32 * kHierWarps) hierarchy_kernel(DevModel M, 
         }
         __syncwarp();
     }
+}
+
+// -------------------------------------------------------------------------------------------------
+// K2, shared-memory form: one CTA per slot keeps the slot's whole bone state (poses, total rotation /
+// translation, local matrices, IK and bone-morph scratch: 112 B per bone) in shared memory, so the dependent chain
+// of the wave program runs at shared-memory latency instead of a global-memory round trip per wave.  Used whenever
+// the state fits (about 2000 bones); the warp-per-slot kernel above remains the fallback.
+// -------------------------------------------------------------------------------------------------
+constexpr uint32_t kHierCtaThreads = 256;
+constexpr size_t kHierCtaSmemLimit = 200 * 1024;
+
+// per bone: poses 2 + totals 2 + local 3 + static record 3 float4; plus the op words of the program
+__host__ __device__ inline size_t hier_cta_smem_bytes(uint32_t nb, uint32_t n_link_slots, uint32_t n_morph_slots, uint32_t n_ops,
+                                                      uint32_t n_waves) {
+    return ((size_t)nb * 10 + (size_t)n_link_slots * 2 + (size_t)n_morph_slots * 2) * sizeof(float4) +
+           (((size_t)n_ops + n_waves + 1 + 3) & ~(size_t)3) * sizeof(uint32_t);
+}
+
+__global__ void __launch_bounds__(kHierCtaThreads) hierarchy_cta_kernel(DevModel M, DevFrames F, uint32_t wave_lo,
+                                                                        uint32_t wave_hi, uint32_t prologue) {
+    extern __shared__ __align__(16) float4 hsm[];
+    const uint32_t slot = blockIdx.x, tid = threadIdx.x, nb = M.nb;
+    float4* s_poseR = hsm;
+    float4* s_poseT = s_poseR + nb;
+    float4* s_totR = s_poseT + nb;
+    float4* s_totT = s_totR + nb;
+    float4* s_local = s_totT + nb;  // 3 per bone
+    float4* s_ikR = s_local + 3 * (size_t)nb;
+    float4* s_preIK = s_ikR + M.n_link_slots;
+    float4* s_morphR = s_preIK + M.n_link_slots;
+    float4* s_morphT = s_morphR + M.n_morph_slots;
+    float4* s_bones = s_morphT + M.n_morph_slots;  // 3 per bone: the static records
+    uint32_t* s_wave_begin = reinterpret_cast<uint32_t*>(s_bones + 3 * (size_t)nb);
+    uint32_t* s_wave_ops = s_wave_begin + M.n_waves + 1;
+
+    float4* g_totR = F.totR + (size_t)slot * nb;
+    float4* g_totT = F.totT + (size_t)slot * nb;
+    float4* g_local = reinterpret_cast<float4*>(F.local) + (size_t)slot * nb * 3;
+    float4* g_ikR = F.ikR + (size_t)slot * M.n_link_slots;
+    float4* g_preIK = F.preIK + (size_t)slot * M.n_link_slots;
+    float4* g_morphR = F.morphR + (size_t)slot * M.n_morph_slots;
+    float4* g_morphT = F.morphT + (size_t)slot * M.n_morph_slots;
+
+    SlotState S;
+    S.bones = reinterpret_cast<const BoneStatic*>(s_bones);
+    S.poseR = s_poseR; S.poseT = s_poseT; S.totR = s_totR; S.totT = s_totT; S.local = s_local;
+    S.ikR = s_ikR; S.preIK = s_preIK; S.morphR = s_morphR; S.morphT = s_morphT;
+    S.palette = F.palette + (size_t)slot * nb * 3;
+
+    // ---- sampled poses of every bone (written by K1 / SetBonePose), the static bone records and the program
+    for (uint32_t b = tid; b < nb; b += kHierCtaThreads) {
+        s_poseR[b] = F.poseR[(size_t)slot * nb + b];
+        s_poseT[b] = F.poseT[(size_t)slot * nb + b];
+    }
+    {
+        const float4* gb = reinterpret_cast<const float4*>(M.bones);
+        for (uint32_t i = tid; i < 3 * nb; i += kHierCtaThreads) s_bones[i] = __ldg(gb + i);
+        for (uint32_t i = tid; i <= M.n_waves; i += kHierCtaThreads) s_wave_begin[i] = __ldg(M.wave_begin + i);
+        const uint32_t n_ops = __ldg(M.wave_begin + M.n_waves);
+        for (uint32_t i = tid; i < n_ops; i += kHierCtaThreads) s_wave_ops[i] = __ldg(M.wave_ops + i);
+    }
+    if (prologue) {
+        // ---- morph application-slot rates (poser_impl.inl:329-339), breadth-first over the static DFS tree
+        const float* rate = F.rate + (size_t)slot * M.nm;
+        float* nrate = F.node_rate + (size_t)slot * M.n_nodes_pad;
+        for (uint32_t dpt = 0; dpt < M.n_depths; ++dpt) {
+            const int32_t b0 = M.depth_begin[dpt], b1 = M.depth_begin[dpt + 1];
+            for (int32_t i = b0 + (int32_t)tid; i < b1; i += kHierCtaThreads) {
+                const int32_t n = M.nodes_by_depth[i];
+                const int32_t par = M.node_parent[n];
+                float r;
+                bool active = true;
+                if (par < 0) r = rate[M.node_morph[n]];
+                else {
+                    const float pr = nrate[par];
+                    active = pr != 0.0f;
+                    r = M.node_mult[n] * pr;
+                }
+                if (!active || (double)r < kEpsD) r = 0.0f;
+                nrate[n] = r;
+            }
+            if (dpt + 1 < M.n_depths) { __threadfence_block(); __syncthreads(); }
+        }
+        // ---- PrePhysicsPosing's per-bone reset (poser_impl.inl:366-377)
+        for (uint32_t b = tid; b < nb; b += kHierCtaThreads) {
+            s_totR[b] = make_float4(0.f, 0.f, 0.f, 1.f);
+            s_totT[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+            store_local(s_local + 3 * (size_t)b, m_identity());
+        }
+        for (uint32_t i = tid; i < M.n_link_slots; i += kHierCtaThreads) {
+            s_ikR[i] = make_float4(0.f, 0.f, 0.f, 1.f);
+            s_preIK[i] = make_float4(0.f, 0.f, 0.f, 1.f);
+        }
+        __syncthreads();  // node rates of this CTA are visible (written by its own threads)
+        // ---- bone morphs (poser_impl.inl:347-354), application order inside each affected bone
+        for (uint32_t i = tid; i < M.n_morph_slots; i += kHierCtaThreads) {
+            Quat mr = q_identity();
+            float tx = 0.f, ty = 0.f, tz = 0.f;
+            for (int32_t e = M.bone_morph_row[i]; e < M.bone_morph_row[i + 1]; ++e) {
+                const BoneMorphEntry E = M.bone_morph_entries[e];
+                const float r = nrate[E.node];
+                if (r != 0.0f) {
+                    tx = tx + E.translation[0] * r;
+                    ty = ty + E.translation[1] * r;
+                    tz = tz + E.translation[2] * r;
+                    const Quat q{E.rotation[0], E.rotation[1], E.rotation[2], E.rotation[3]};
+                    mr = q_mul(mr, q_slerp(q_identity(), q, r));
+                }
+            }
+            s_morphR[i] = q_to4(mr);
+            s_morphT[i] = make_float4(tx, ty, tz, 0.f);
+        }
+    } else {
+        // continue from the state the previous launch (pre-physics segment, possibly edited by the host physics
+        // hook) left in global memory
+        for (uint32_t b = tid; b < nb; b += kHierCtaThreads) {
+            s_totR[b] = g_totR[b];
+            s_totT[b] = g_totT[b];
+            s_local[3 * (size_t)b] = g_local[3 * (size_t)b];
+            s_local[3 * (size_t)b + 1] = g_local[3 * (size_t)b + 1];
+            s_local[3 * (size_t)b + 2] = g_local[3 * (size_t)b + 2];
+        }
+        for (uint32_t i = tid; i < M.n_link_slots; i += kHierCtaThreads) { s_ikR[i] = g_ikR[i]; s_preIK[i] = g_preIK[i]; }
+        for (uint32_t i = tid; i < M.n_morph_slots; i += kHierCtaThreads) { s_morphR[i] = g_morphR[i]; s_morphT[i] = g_morphT[i]; }
+    }
+    __syncthreads();
+
+    for (uint32_t w = wave_lo; w < wave_hi; ++w) {
+        const uint32_t o0 = s_wave_begin[w], o1 = s_wave_begin[w + 1];
+        for (uint32_t o = o0 + tid; o < o1; o += kHierCtaThreads) {
+            const uint32_t word = s_wave_ops[o];
+            const uint32_t kind = word >> 28;
+            const int32_t arg = (int32_t)(word & 0x0FFFFFFFu);
+            if (kind == kOpEval) eval_bone(M, S, arg);
+            else if (kind == kOpIk) solve_ik(M, S, M.iks[arg]);
+            else skin_bone(M, S, arg);
+        }
+        __syncthreads();
+    }
+
+    // ---- leave the state in global memory for the next segment / the download entry points
+    for (uint32_t b = tid; b < nb; b += kHierCtaThreads) {
+        g_totR[b] = s_totR[b];
+        g_totT[b] = s_totT[b];
+        g_local[3 * (size_t)b] = s_local[3 * (size_t)b];
+        g_local[3 * (size_t)b + 1] = s_local[3 * (size_t)b + 1];
+        g_local[3 * (size_t)b + 2] = s_local[3 * (size_t)b + 2];
+    }
+    for (uint32_t i = tid; i < M.n_link_slots; i += kHierCtaThreads) { g_ikR[i] = s_ikR[i]; g_preIK[i] = s_preIK[i]; }
+    for (uint32_t i = tid; i < M.n_morph_slots; i += kHierCtaThreads) { g_morphR[i] = s_morphR[i]; g_morphT[i] = s_morphT[i]; }
 }
 
 // =================================================================================================
@@ -644,6 +796,11 @@ cudaError_t launch_pose_sample(cudaStream_t st, const DevModel& M, const DevAnim
 cudaError_t launch_hierarchy(cudaStream_t st, const DevModel& M, const DevFrames& F, uint32_t wave_lo, uint32_t wave_hi,
                              bool prologue) {
     if (F.n_slots == 0) return cudaSuccess;
+    const size_t cta_smem = hier_cta_smem_bytes(M.nb, M.n_link_slots, M.n_morph_slots, M.n_ops, M.n_waves);
+    if (cta_smem <= kHierCtaSmemLimit) {
+        hierarchy_cta_kernel<<<F.n_slots, kHierCtaThreads, cta_smem, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u);
+        return cudaGetLastError();
+    }
     const uint32_t blocks = (F.n_slots + kHierWarps - 1) / kHierWarps;
     hierarchy_kernel<<<blocks, 32 * kHierWarps, 0, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u);
     return cudaGetLastError();
@@ -654,7 +811,14 @@ size_t skin_smem_bytes(const DevModel& M, int layout) {
 }
 
 cudaError_t prepare_skin_kernels(const DevModel& M) {
-    cudaError_t e = cudaFuncSetAttribute(skin_kernel<MMDGPU_LAYOUT_SOA_POS_NRM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    const size_t cta_smem = hier_cta_smem_bytes(M.nb, M.n_link_slots, M.n_morph_slots, M.n_ops, M.n_waves);
+    cudaError_t e = cudaSuccess;
+    if (cta_smem <= kHierCtaSmemLimit) {
+        // opt in to the largest size any model of this process may need; the attribute is per function and device
+        e = cudaFuncSetAttribute(hierarchy_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHierCtaSmemLimit);
+        if (e != cudaSuccess) return e;
+    }
+    e = cudaFuncSetAttribute(skin_kernel<MMDGPU_LAYOUT_SOA_POS_NRM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)skin_smem_bytes(M, MMDGPU_LAYOUT_SOA_POS_NRM));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(skin_kernel<MMDGPU_LAYOUT_INTERLEAVED_SOKOL32>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -228,6 +228,7 @@ mmdgpu_status upload_model(mmdgpu_model* m) {
     CU(ctx, upload(ctx, m->mem, words, &D.wave_ops));
     D.n_waves = uint32_t(p.wave_begin.size() - 1);
     D.phase_split = uint32_t(p.phase_split);
+    D.n_ops = uint32_t(p.wave_ops.size());
     CU(ctx, upload(ctx, m->mem, p.node_morph, &D.node_morph));
     CU(ctx, upload(ctx, m->mem, p.node_parent, &D.node_parent));
     CU(ctx, upload(ctx, m->mem, p.node_mult, &D.node_mult));

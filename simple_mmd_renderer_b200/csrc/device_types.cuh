@@ -8,9 +8,8 @@
 
 namespace mmdgpu {
 
-constexpr uint32_t kVertsPerThread = 4;
-constexpr uint32_t kSkinThreads = 256;
 static_assert(kVertsPerThread * kSkinThreads == kTileVerts, "one CTA iteration = one tile");
+static_assert(kVertsPerThread == 2 || kVertsPerThread == 4, "vector loads are written for 2 or 4 positions per thread");
 
 // Static model image in HBM.  Vertex streams are structure-of-arrays in TILE STORAGE ORDER (host_plan.hpp):
 // a thread owns 4 consecutive storage positions, so every global access is a 16-byte vector, and the 32 lanes
@@ -24,7 +23,7 @@ struct DevModel {
     const uint2* ids;        // 4 x u16 tile-local bone indices; bits 15:13 of id0 carry the device skinning type
     const float4* weights;
     const float2* uv;
-    const uint2* orig4;      // per thread: 4 x u16 PMX index (within the tile) of its 4 storage positions
+    const uint16_t* orig;    // per storage position: PMX index within the tile
     const uint2* ell_hdr;    // per 32-lane group (tile, step, warp): (first entry, rounds)
     const float4* ell_ent;   // (offset.xyz, bit-cast application slot); entry (round k, lane l) at base + 32 k + l
     const uint32_t* tile_bone_begin;  // n_tiles + 1

@@ -127,10 +127,17 @@ struct Plan {
     std::vector<int32_t> op_arg_i32, phase_split_i32;
 };
 
-constexpr uint32_t kTileVerts = 1024;   // vertices per tile (one CTA iteration: 256 threads x 4 vertices)
-constexpr uint32_t kTileGroups = 32;    // (step j in 0..3) x (warp w in 0..7)
-// storage position of sorted rank r inside a tile: step j = r / 256, warp w = (r / 32) % 8, lane l = r % 32
-inline uint32_t tile_position_of_rank(uint32_t r) { return (((r >> 5) & 7u) * 32u + (r & 31u)) * 4u + (r >> 8); }
+constexpr uint32_t kTileVerts = 1024;      // vertices per tile = one CTA iteration
+constexpr uint32_t kVertsPerThread = 4;    // consecutive storage positions one thread owns ("steps" of a warp)
+constexpr uint32_t kSkinThreads = kTileVerts / kVertsPerThread;
+constexpr uint32_t kSkinWarps = kSkinThreads / 32;
+constexpr uint32_t kTileGroups = kTileVerts / 32;  // (step j) x (warp w) groups of 32 lanes
+// storage position of sorted rank r inside a tile: group g = r / 32 is step j = g / kSkinWarps of warp
+// w = g % kSkinWarps; lane l = r % 32 owns positions (w*32 + l) * kVertsPerThread + j
+inline uint32_t tile_position_of_rank(uint32_t r) {
+    const uint32_t g = r >> 5, l = r & 31u;
+    return ((g % kSkinWarps) * 32u + l) * kVertsPerThread + g / kSkinWarps;
+}
 
 // Returns MMDGPU_OK or an error code with a message in `err`.
 mmdgpu_status build_plan(const mmdgpu_model_desc& d, const mmdgpu_options* opt, Plan& out, std::string& err);

@@ -632,6 +632,7 @@ __host__ __device__ inline uint32_t skin_stage_bytes(int layout) {
 __host__ __device__ inline uint32_t skin_pal_bytes(uint32_t max_tile_bones) { return max_tile_bones * 48u; }
 
 constexpr uint32_t kPalPrefetch = 2;  // palette float4 per thread held in registers across the compute phase
+constexpr int V = (int)kVertsPerThread;
 
 template <int LAYOUT>
 __global__ void __launch_bounds__(kSkinThreads, 2) skin_kernel(DevModel M, DevFrames F, uint32_t chunk, uint32_t n_chunks) {
@@ -649,33 +650,47 @@ __global__ void __launch_bounds__(kSkinThreads, 2) skin_kernel(DevModel M, DevFr
 
     // ---- the tile's static streams: read once, kept in registers for every slot of this work item
     const uint32_t v0 = tile * kTileVerts + tid * kVertsPerThread;
-    const float4 PX = __ldg(reinterpret_cast<const float4*>(M.px + v0));
-    const float4 PY = __ldg(reinterpret_cast<const float4*>(M.py + v0));
-    const float4 PZ = __ldg(reinterpret_cast<const float4*>(M.pz + v0));
-    const float4 NX = __ldg(reinterpret_cast<const float4*>(M.nx + v0));
-    const float4 NY = __ldg(reinterpret_cast<const float4*>(M.ny + v0));
-    const float4 NZ = __ldg(reinterpret_cast<const float4*>(M.nz + v0));
-    const uint4 I01 = __ldg(reinterpret_cast<const uint4*>(M.ids + v0));
-    const uint4 I23 = __ldg(reinterpret_cast<const uint4*>(M.ids + v0 + 2));
-    const float4 W0 = __ldg(M.weights + v0), W1 = __ldg(M.weights + v0 + 1), W2 = __ldg(M.weights + v0 + 2),
-                 W3 = __ldg(M.weights + v0 + 3);
-    const uint2 OR = __ldg(M.orig4 + (v0 >> 2));
-    float4 UV01 = make_float4(0.f, 0.f, 0.f, 0.f), UV23 = UV01;
-    if (LAYOUT == MMDGPU_LAYOUT_INTERLEAVED_SOKOL32) {
-        UV01 = __ldg(reinterpret_cast<const float4*>(M.uv + v0));
-        UV23 = __ldg(reinterpret_cast<const float4*>(M.uv + v0 + 2));
-    }
-    const float px[4] = {PX.x, PX.y, PX.z, PX.w}, py[4] = {PY.x, PY.y, PY.z, PY.w}, pz[4] = {PZ.x, PZ.y, PZ.z, PZ.w};
-    const float nx[4] = {NX.x, NX.y, NX.z, NX.w}, ny[4] = {NY.x, NY.y, NY.z, NY.w}, nz[4] = {NZ.x, NZ.y, NZ.z, NZ.w};
-    const uint32_t ilo[4] = {I01.x, I01.z, I23.x, I23.z}, ihi[4] = {I01.y, I01.w, I23.y, I23.w};
-    const float4 wv[4] = {W0, W1, W2, W3};
-    const uint32_t orig[4] = {OR.x & 0xFFFFu, OR.x >> 16, OR.y & 0xFFFFu, OR.y >> 16};
-    const float uu[4] = {UV01.x, UV01.z, UV23.x, UV23.z}, vv[4] = {UV01.y, UV01.w, UV23.y, UV23.w};
-    // sliced-ELL group headers of this warp's four steps (warp-uniform addresses: one broadcast load each)
-    uint32_t ebase[4], erounds[4];
+    float px[V], py[V], pz[V], nx[V], ny[V], nz[V], uu[V], vv[V];
+    uint32_t ilo[V], ihi[V], orig[V];
+    float4 wv[V];
+    if (V == 4) {
+        const float4 PX = __ldg(reinterpret_cast<const float4*>(M.px + v0)), PY = __ldg(reinterpret_cast<const float4*>(M.py + v0)),
+                     PZ = __ldg(reinterpret_cast<const float4*>(M.pz + v0)), NX = __ldg(reinterpret_cast<const float4*>(M.nx + v0)),
+                     NY = __ldg(reinterpret_cast<const float4*>(M.ny + v0)), NZ = __ldg(reinterpret_cast<const float4*>(M.nz + v0));
+        const float a[6][4] = {{PX.x, PX.y, PX.z, PX.w}, {PY.x, PY.y, PY.z, PY.w}, {PZ.x, PZ.y, PZ.z, PZ.w},
+                               {NX.x, NX.y, NX.z, NX.w}, {NY.x, NY.y, NY.z, NY.w}, {NZ.x, NZ.y, NZ.z, NZ.w}};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const uint2 h = __ldg(M.ell_hdr + tile * kTileGroups + j * 8 + warp);
+        for (int j = 0; j < V; ++j) { px[j] = a[0][j]; py[j] = a[1][j]; pz[j] = a[2][j]; nx[j] = a[3][j]; ny[j] = a[4][j]; nz[j] = a[5][j]; }
+        const uint2 OR = __ldg(reinterpret_cast<const uint2*>(M.orig + v0));
+        const uint32_t o[4] = {OR.x & 0xFFFFu, OR.x >> 16, OR.y & 0xFFFFu, OR.y >> 16};
+#pragma unroll
+        for (int j = 0; j < V; ++j) orig[j] = o[j];
+    } else {
+        const float2 PX = __ldg(reinterpret_cast<const float2*>(M.px + v0)), PY = __ldg(reinterpret_cast<const float2*>(M.py + v0)),
+                     PZ = __ldg(reinterpret_cast<const float2*>(M.pz + v0)), NX = __ldg(reinterpret_cast<const float2*>(M.nx + v0)),
+                     NY = __ldg(reinterpret_cast<const float2*>(M.ny + v0)), NZ = __ldg(reinterpret_cast<const float2*>(M.nz + v0));
+        px[0] = PX.x; px[1] = PX.y; py[0] = PY.x; py[1] = PY.y; pz[0] = PZ.x; pz[1] = PZ.y;
+        nx[0] = NX.x; nx[1] = NX.y; ny[0] = NY.x; ny[1] = NY.y; nz[0] = NZ.x; nz[1] = NZ.y;
+        const uint32_t OR = __ldg(reinterpret_cast<const uint32_t*>(M.orig + v0));
+        orig[0] = OR & 0xFFFFu; orig[1] = OR >> 16;
+    }
+#pragma unroll
+    for (int j = 0; j < V; j += 2) {
+        const uint4 I = __ldg(reinterpret_cast<const uint4*>(M.ids + v0 + j));
+        ilo[j] = I.x; ihi[j] = I.y; ilo[j + 1] = I.z; ihi[j + 1] = I.w;
+        uu[j] = vv[j] = uu[j + 1] = vv[j + 1] = 0.f;
+        if (LAYOUT == MMDGPU_LAYOUT_INTERLEAVED_SOKOL32) {
+            const float4 UV = __ldg(reinterpret_cast<const float4*>(M.uv + v0 + j));
+            uu[j] = UV.x; vv[j] = UV.y; uu[j + 1] = UV.z; vv[j + 1] = UV.w;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) wv[j] = __ldg(M.weights + v0 + j);
+    // sliced-ELL group headers of this warp's steps (warp-uniform addresses: one broadcast load each)
+    uint32_t ebase[V], erounds[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const uint2 h = __ldg(M.ell_hdr + tile * kTileGroups + j * kSkinWarps + warp);
         ebase[j] = h.x + lane;
         erounds[j] = h.y;
     }
@@ -704,7 +719,7 @@ __global__ void __launch_bounds__(kSkinThreads, 2) skin_kernel(DevModel M, DevFr
     for (uint32_t s = s0; s < s1; ++s) {
         const uint32_t b = (s - s0) & 1u;
         const float4* __restrict__ pal = pal_base + (size_t)b * (pal_bytes >> 4);
-        const float* __restrict__ nrate = rate_base + (size_t)b * M.n_nodes_pad;
+        const char* __restrict__ nrate = reinterpret_cast<const char*>(rate_base + (size_t)b * M.n_nodes_pad);
         unsigned char* stage = stage_base + (size_t)b * stage_bytes;
         const bool has_next = s + 1 < s1;
         // ---- next slot's palette subset and rates: loads issued now, consumed after the compute phase
@@ -717,9 +732,9 @@ __global__ void __launch_bounds__(kSkinThreads, 2) skin_kernel(DevModel M, DevFr
                 if (psrc[q] != 0xFFFFFFFFu) pf[q] = __ldg(gp + psrc[q]);
             if (tid < nrate4) rf = __ldg(gr + tid);
         }
-        // ---- compute: 4 storage positions; step j is (nearly always) one skinning type across the warp
+        // ---- compute: step j is (nearly always) one skinning type across the warp
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < V; ++j) {
             // vertex_images_[i] accumulated in application order: img = img + off*rate (poser_impl.inl:340-346)
             float ix = 0.f, iy = 0.f, iz = 0.f;
             const float4* __restrict__ e = M.ell_ent + ebase[j];
@@ -729,7 +744,7 @@ __global__ void __launch_bounds__(kSkinThreads, 2) skin_kernel(DevModel M, DevFr
                 // rate +0 and is applied unconditionally: the accumulator starts at +0 and can never become -0,
                 // so adding (finite offset) * 0 = +-0 leaves it bit-identical to libmmd's skip (the host rejects
                 // non-finite offsets).
-                const float r = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(nrate) + __float_as_uint(ent.w));
+                const float r = *reinterpret_cast<const float*>(nrate + __float_as_uint(ent.w));
                 ix = ix + ent.x * r;
                 iy = iy + ent.y * r;
                 iz = iz + ent.z * r;

@@ -170,7 +170,7 @@ mmdgpu_status upload_model(mmdgpu_model* m) {
     std::vector<uint2> ids(nvp, make_uint2(0, 0));
     std::vector<float4> wts(nvp, make_float4(0.f, 0.f, 0.f, 0.f));
     std::vector<float2> uv(nvp, make_float2(0.f, 0.f));
-    std::vector<uint2> orig4(nvp / 4, make_uint2(0, 0));
+
     for (uint32_t pos = 0; pos < nvp; ++pos) {
         const uint32_t src = (pos / kTileVerts) * kTileVerts + p.tile_orig[pos];
         if (src < nv) {
@@ -185,8 +185,6 @@ mmdgpu_status upload_model(mmdgpu_model* m) {
         ids[pos].y = uint32_t(id[2]) | (uint32_t(id[3]) << 16);
         const float* w = &p.st_weight[size_t(pos) * 4];
         wts[pos] = make_float4(w[0], w[1], w[2], w[3]);
-        uint32_t& word = (pos & 2u) ? orig4[pos >> 2].y : orig4[pos >> 2].x;
-        word |= uint32_t(p.tile_orig[pos]) << ((pos & 1u) * 16);
     }
     CU(ctx, upload(ctx, m->mem, plane[0], &D.px)); CU(ctx, upload(ctx, m->mem, plane[1], &D.py));
     CU(ctx, upload(ctx, m->mem, plane[2], &D.pz)); CU(ctx, upload(ctx, m->mem, plane[3], &D.nx));
@@ -194,7 +192,7 @@ mmdgpu_status upload_model(mmdgpu_model* m) {
     CU(ctx, upload(ctx, m->mem, ids, &D.ids));
     CU(ctx, upload(ctx, m->mem, wts, &D.weights));
     CU(ctx, upload(ctx, m->mem, uv, &D.uv));
-    CU(ctx, upload(ctx, m->mem, orig4, &D.orig4));
+    CU(ctx, upload(ctx, m->mem, p.tile_orig, &D.orig));
     // ---- sliced-ELL morph entries
     std::vector<uint2> hdr(p.ell_base.size());
     for (size_t g = 0; g < hdr.size(); ++g) hdr[g] = make_uint2(p.ell_base[g], p.ell_rounds[g]);

@@ -268,13 +268,15 @@ def test_tile_layout_is_a_faithful_permutation(name):
     eoff = plan[capi.PLAN_ELL_OFFSET].reshape(-1, 3)
     pad = plan[capi.PLAN_APP_SLOT_MORPH].size
     total_real = 0
+    V = 4                       # storage positions per thread (kVertsPerThread in host_plan.hpp)
+    WARPS = 1024 // V // 32     # warps per CTA; group g = step j * WARPS + warp w
     for ti in range(n_tiles):
-        for j in range(4):
-            for w in range(8):
-                g = ti * 32 + j * 8 + w
+        for j in range(V):
+            for w in range(WARPS):
+                g = ti * 32 + j * WARPS + w
                 cnts = []
                 for l in range(32):
-                    pos = ti * 1024 + (w * 32 + l) * 4 + j
+                    pos = ti * 1024 + (w * 32 + l) * V + j
                     v = src[pos]
                     cnt = int(row[v + 1] - row[v]) if v < nv else 0
                     cnts.append(cnt)
@@ -289,8 +291,8 @@ def test_tile_layout_is_a_faithful_permutation(name):
     # the point of the sort: a warp step (32 consecutive ranks) is one skinning type except at the boundaries
     mixed = 0
     for ti in range(n_tiles):
-        for j in range(4):
-            for w in range(8):
-                pos = ti * 1024 + (w * 32 + np.arange(32)) * 4 + j
+        for j in range(V):
+            for w in range(WARPS):
+                pos = ti * 1024 + (w * 32 + np.arange(32)) * V + j
                 mixed += len(set(st_type[pos].tolist())) > 1
     assert mixed <= 3 * n_tiles

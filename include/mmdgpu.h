@@ -203,14 +203,19 @@ typedef enum mmdgpu_stream_id {
     MMDGPU_STREAM_POSITION    = 0, /* SOA: n x float3                    */
     MMDGPU_STREAM_NORMAL      = 1, /* SOA: n x float3                    */
     MMDGPU_STREAM_INTERLEAVED = 2, /* INTERLEAVED: n x 32 B              */
-    MMDGPU_STREAM_SKIN_MATRIX = 3  /* device palette, nb x 12 floats (3 columns x float4) */
+    MMDGPU_STREAM_SKIN_MATRIX = 3, /* device palette, nb x 12 floats (3 columns x float4) */
+    MMDGPU_STREAM_UV          = 4  /* SOA + extensions only: n x float2 morphed UV           */
 } mmdgpu_stream_id;
 
 /* Behaviour switches.  Zero-initialised = libmmd-exact. */
 typedef struct mmdgpu_options {
     /* 0: libmmd-exact (SDEF -> BDEF2 lerp, QDEF -> BDEF4 lerp, UV morphs ignored;
      *    L/motion/poser_impl.inl:417-426, :355-358).
-     * 1: extensions (spherical SDEF, dual-quaternion QDEF, applied UV morphs); parity unpinned. */
+     * 1: extensions — what the PMX format means but libmmd does not implement: spherical SDEF (rotation
+     *    slerp(q0, q1, w1) about C, centres blended through R0 / R1), dual-quaternion QDEF, applied UV morphs
+     *    (type 3; output stream MMDGPU_STREAM_UV, or the uv fields of the interleaved record).  PARITY UNPINNED:
+     *    there is no libmmd behaviour to compare with; tests check them against an fp64 restatement of the same
+     *    formulas and through self-consistency properties. */
     uint32_t extensions;
     uint32_t reserved[7];
 } mmdgpu_options;

@@ -18,7 +18,7 @@ BONE_HAS_IK, BONE_APPEND_ROTATE, BONE_APPEND_TRANSLATE, BONE_POST_PHYSICS = 0x20
 (MORPH_GROUP, MORPH_VERTEX, MORPH_BONE, MORPH_UV, MORPH_EXT_UV1, MORPH_EXT_UV2, MORPH_EXT_UV3, MORPH_EXT_UV4,
  MORPH_MATERIAL) = range(9)
 LAYOUT_SOA_POS_NRM, LAYOUT_INTERLEAVED_SOKOL32 = 0, 1
-STREAM_POSITION, STREAM_NORMAL, STREAM_INTERLEAVED, STREAM_SKIN_MATRIX = 0, 1, 2, 3
+STREAM_POSITION, STREAM_NORMAL, STREAM_INTERLEAVED, STREAM_SKIN_MATRIX, STREAM_UV = 0, 1, 2, 3, 4
 
 (PLAN_SKIN_TYPE, PLAN_BONE_ID, PLAN_WEIGHT, PLAN_ORDER_PRE, PLAN_ORDER_POST, PLAN_OP_KIND, PLAN_OP_BONE,
  PLAN_OP_WAVE, PLAN_WAVE_BEGIN, PLAN_WAVE_OPS, PLAN_IK_FIX_TYPE, PLAN_IK_EULER_ORDER, PLAN_APP_SLOT_MORPH,

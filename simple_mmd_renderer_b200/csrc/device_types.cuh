@@ -29,9 +29,10 @@ struct DevModel {
     const uint32_t* tile_bone_begin;  // n_tiles + 1
     const uint16_t* tile_bones;       // distinct bones of each tile
     // extension streams (NULL in libmmd-exact mode)
-    const float4* sdef_c;    // per vertex: C.xyz, unused
-    const float4* sdef_r0;
-    const float4* sdef_r1;
+    uint32_t extensions;
+    const float4* sdef;        // 3 per storage position: C, cr0, cr1 (spherical deform)
+    const uint2* uv_ell_hdr;   // UV-morph sliced ELL, same group structure as ell_hdr
+    const float4* uv_ell_ent;  // (du, dv, byte offset of the application slot's rate, unused)
     // bones
     const BoneStatic* bones;
     const IkDesc* iks;
@@ -87,6 +88,8 @@ struct DevFrames {
     float4* morphR;     // [slot][n_morph_slots]
     float4* morphT;     // [slot][n_morph_slots]
     float4* palette;    // [slot][nb][3]   column c of skinning_matrix_: (M0c, M1c, M2c, M3c)
+    float4* pal_ext;    // [slot][nb][2]   extensions: rotation quaternion and dual part of the skinning transform
+    float2* out_uv;     // extensions, SOA layout: [slot][nv_pad] morphed UV
     float* out_pos;     // SOA: [slot][nv_pad][3]
     float* out_nrm;     // SOA: [slot][nv_pad][3]
     float4* out_inter;  // INTERLEAVED: [slot][nv_pad][2]

@@ -332,12 +332,13 @@ mmdgpu_status build_plan(const mmdgpu_model_desc& d, const mmdgpu_options* opt, 
                 const uint32_t v = uv ? d.uv_morph_entries[d.morph_entry_begin[m] + j].vertex
                                       : d.vertex_morph_entries[d.morph_entry_begin[m] + j].vertex;
                 if (v >= nv) return fail(err, MMDGPU_ERR_BAD_INDEX, "morph vertex index out of range at morph " + std::to_string(m));
-                if (!uv) {
+                {
                     // the device applies skipped morphs with rate 0 instead of branching; that is bit-identical to
                     // libmmd's skip only for finite offsets
-                    const float* o = d.vertex_morph_entries[d.morph_entry_begin[m] + j].offset;
-                    if (!std::isfinite(o[0]) || !std::isfinite(o[1]) || !std::isfinite(o[2]))
-                        return fail(err, MMDGPU_ERR_INVALID_ARG, "non-finite vertex morph offset at morph " + std::to_string(m));
+                    const float* o = uv ? d.uv_morph_entries[d.morph_entry_begin[m] + j].offset
+                                        : d.vertex_morph_entries[d.morph_entry_begin[m] + j].offset;
+                    if (!std::isfinite(o[0]) || !std::isfinite(o[1]) || !std::isfinite(o[2]) || (uv && !std::isfinite(o[3])))
+                        return fail(err, MMDGPU_ERR_INVALID_ARG, "non-finite morph offset at morph " + std::to_string(m));
                 }
                 row[size_t(v) + 1]++;
             }
@@ -469,6 +470,7 @@ mmdgpu_status build_plan(const mmdgpu_model_desc& d, const mmdgpu_options* opt, 
     {
         std::vector<uint32_t> order(kTileVerts);
         std::vector<int32_t> local_of(nb, -1);
+        std::vector<uint16_t> rank_vertex(p.nv_pad);  // tile rank -> PMX index within the tile
         for (uint32_t t = 0; t < p.n_tiles; ++t) {
             const uint32_t v0 = t * kTileVerts;
             auto type_of = [&](uint32_t i) -> uint32_t { return (v0 + i < nv) ? p.dev_type[v0 + i] : uint32_t(kDevBdef1); };
@@ -510,29 +512,66 @@ mmdgpu_status build_plan(const mmdgpu_model_desc& d, const mmdgpu_options* opt, 
                     p.st_local_id[pos * 4] = uint16_t(local_of[0] < 0 ? 0 : local_of[0]);
                 }
             }
-            // sliced ELL: group g = r / 32 holds ranks [32 g, 32 g + 32)
-            for (uint32_t g = 0; g < kTileGroups; ++g) {
-                uint32_t rounds = 0;
-                for (uint32_t l = 0; l < 32; ++l) rounds = std::max(rounds, count_of(order[g * 32 + l]));
-                const size_t base = p.ell_node.size();
-                if (base + size_t(rounds) * 32 > 0xFFFFFFFFull) return fail(err, MMDGPU_ERR_UNSUPPORTED, "morph entry table exceeds 2^32 entries");
-                p.ell_base[size_t(t) * kTileGroups + g] = uint32_t(base);
-                p.ell_rounds[size_t(t) * kTileGroups + g] = rounds;
-                p.ell_node.resize(base + size_t(rounds) * 32, p.pad_node);
-                p.ell_offset.resize((base + size_t(rounds) * 32) * 3, 0.0f);
-                for (uint32_t l = 0; l < 32; ++l) {
-                    const uint32_t i = order[g * 32 + l];
-                    const uint32_t cnt = count_of(i);
-                    for (uint32_t k = 0; k < cnt; ++k) {
-                        const size_t e = size_t(p.csr_row[v0 + i]) + k, at = base + size_t(k) * 32 + l;
-                        p.ell_node[at] = p.csr_node[e];
-                        for (int c = 0; c < 3; ++c) p.ell_offset[at * 3 + c] = p.csr_offset[e * 3 + c];
-                    }
-                }
-            }
+            for (uint32_t r = 0; r < kTileVerts; ++r) rank_vertex[size_t(v0) + r] = uint16_t(order[r]);
             for (uint16_t b : used) local_of[b] = -1;
         }
         p.tile_bone_begin[p.n_tiles] = uint32_t(p.tile_bones.size());
+
+        // sliced ELL of a per-vertex CSR: group g = rank / 32 holds ranks [32 g, 32 g + 32); rounds = the group's
+        // largest row; entry (round k, lane l) at base + 32 k + l; padding points at the always-zero slot
+        auto build_ell = [&](const std::vector<uint32_t>& row, const std::vector<uint32_t>& node, const std::vector<float>& off,
+                             int width, std::vector<uint32_t>& base_of, std::vector<uint32_t>& rounds_of,
+                             std::vector<uint32_t>& ell_node, std::vector<float>& ell_off) -> mmdgpu_status {
+            base_of.assign(size_t(p.n_tiles) * kTileGroups, 0);
+            rounds_of.assign(size_t(p.n_tiles) * kTileGroups, 0);
+            ell_node.clear(); ell_off.clear();
+            for (uint32_t t = 0; t < p.n_tiles; ++t) {
+                const uint32_t v0 = t * kTileVerts;
+                auto count_of = [&](uint32_t i) -> uint32_t { return (v0 + i < nv) ? row[v0 + i + 1] - row[v0 + i] : 0u; };
+                for (uint32_t g = 0; g < kTileGroups; ++g) {
+                    uint32_t rounds = 0;
+                    for (uint32_t l = 0; l < 32; ++l) rounds = std::max(rounds, count_of(rank_vertex[size_t(v0) + g * 32 + l]));
+                    const size_t base = ell_node.size();
+                    if (base + size_t(rounds) * 32 > 0xFFFFFFFFull) return fail(err, MMDGPU_ERR_UNSUPPORTED, "morph entry table exceeds 2^32 entries");
+                    base_of[size_t(t) * kTileGroups + g] = uint32_t(base);
+                    rounds_of[size_t(t) * kTileGroups + g] = rounds;
+                    ell_node.resize(base + size_t(rounds) * 32, p.pad_node);
+                    ell_off.resize((base + size_t(rounds) * 32) * size_t(width), 0.0f);
+                    for (uint32_t l = 0; l < 32; ++l) {
+                        const uint32_t i = rank_vertex[size_t(v0) + g * 32 + l];
+                        const uint32_t cnt = count_of(i);
+                        for (uint32_t k = 0; k < cnt; ++k) {
+                            const size_t e = size_t(row[v0 + i]) + k, at = base + size_t(k) * 32 + l;
+                            ell_node[at] = node[e];
+                            for (int c = 0; c < width; ++c) ell_off[at * size_t(width) + c] = off[e * size_t(width) + c];
+                        }
+                    }
+                }
+            }
+            return MMDGPU_OK;
+        };
+        if (mmdgpu_status st = build_ell(p.csr_row, p.csr_node, p.csr_offset, 3, p.ell_base, p.ell_rounds, p.ell_node, p.ell_offset)) return st;
+        if (p.extensions)
+            if (mmdgpu_status st = build_ell(p.uv_row, p.uv_node, p.uv_offset, 4, p.uv_ell_base, p.uv_ell_rounds, p.uv_ell_node, p.uv_ell_offset)) return st;
+
+        // spherical-deform parameters per storage position (extensions): C and the two blended centres
+        // cr0 = (C + (C + R0 - rw)) / 2, cr1 = (C + (C + R1 - rw)) / 2 with rw = R0*w0 + R1*w1
+        if (p.extensions && !p.sdef_c.empty()) {
+            p.st_sdef.assign(size_t(p.nv_pad) * 12, 0.0f);
+            for (uint32_t pos = 0; pos < p.nv_pad; ++pos) {
+                const uint32_t src = (pos / kTileVerts) * kTileVerts + p.tile_orig[pos];
+                if (src >= nv || p.dev_type[src] != kDevSdef) continue;
+                const float w0 = p.weight[size_t(src) * 4], w1 = 1.0f - w0;
+                float* o = &p.st_sdef[size_t(pos) * 12];
+                for (int c = 0; c < 3; ++c) {
+                    const float C = p.sdef_c[size_t(src) * 3 + c], R0 = p.sdef_r0[size_t(src) * 3 + c], R1 = p.sdef_r1[size_t(src) * 3 + c];
+                    const float rw = R0 * w0 + R1 * w1;
+                    o[c] = C;
+                    o[4 + c] = (C + (C + R0 - rw)) * 0.5f;
+                    o[8 + c] = (C + (C + R1 - rw)) * 0.5f;
+                }
+            }
+        }
     }
 
     // introspection mirrors

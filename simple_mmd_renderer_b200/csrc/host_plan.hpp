@@ -112,6 +112,10 @@ struct Plan {
     std::vector<uint32_t> ell_node;
     std::vector<float> ell_offset;          // 3 per entry
     uint32_t pad_node = 0;                  // application slot whose rate is always 0
+    // extensions only: sliced ELL of the UV-morph entries (offset.xyzw), spherical-deform parameters
+    std::vector<uint32_t> uv_ell_base, uv_ell_rounds, uv_ell_node;
+    std::vector<float> uv_ell_offset;       // 4 per entry
+    std::vector<float> st_sdef;             // 12 per storage position: C.xyz_, cr0.xyz_, cr1.xyz_
 
     // bone morphs grouped by affected bone
     std::vector<int32_t> morph_bones;        // morph_slot -> bone

@@ -144,6 +144,7 @@ struct SlotState {
     const float4* morphR;
     const float4* morphT;
     float4* palette; // 3 float4 per bone
+    float4* pal_ext; // extensions: 2 float4 per bone (rotation quaternion, dual part), else nullptr
 };
 
 __device__ __forceinline__ Mat43 load_local(const float4* p) {
@@ -312,6 +313,36 @@ __device__ __forceinline__ void skin_bone(const DevModel& M, const SlotState& S,
     S.palette[3 * (size_t)b + 0] = col[0];
     S.palette[3 * (size_t)b + 1] = col[1];
     S.palette[3 * (size_t)b + 2] = col[2];
+    if (S.pal_ext) {
+        // Extensions (no libmmd counterpart): the rotation of the skinning transform as a unit quaternion q and the
+        // dual part d = 0.5 * (t, 0) (x) q for dual-quaternion blending.  Column-vector rotation R[i][j] = col[i][j].
+        const float r00 = col[0].x, r01 = col[0].y, r02 = col[0].z, r10 = col[1].x, r11 = col[1].y, r12 = col[1].z,
+                    r20 = col[2].x, r21 = col[2].y, r22 = col[2].z;
+        float qx, qy, qz, qw;
+        const float tr = r00 + r11 + r22;
+        if (tr > 0.0f) {
+            const float s4 = sqrtf(tr + 1.0f) * 2.0f;
+            qw = 0.25f * s4; qx = (r21 - r12) / s4; qy = (r02 - r20) / s4; qz = (r10 - r01) / s4;
+        } else if (r00 > r11 && r00 > r22) {
+            const float s4 = sqrtf(1.0f + r00 - r11 - r22) * 2.0f;
+            qw = (r21 - r12) / s4; qx = 0.25f * s4; qy = (r01 + r10) / s4; qz = (r02 + r20) / s4;
+        } else if (r11 > r22) {
+            const float s4 = sqrtf(1.0f + r11 - r00 - r22) * 2.0f;
+            qw = (r02 - r20) / s4; qx = (r01 + r10) / s4; qy = 0.25f * s4; qz = (r12 + r21) / s4;
+        } else {
+            const float s4 = sqrtf(1.0f + r22 - r00 - r11) * 2.0f;
+            qw = (r10 - r01) / s4; qx = (r02 + r20) / s4; qy = (r12 + r21) / s4; qz = 0.25f * s4;
+        }
+        const float inv = 1.0f / sqrtf(qx * qx + qy * qy + qz * qz + qw * qw);
+        qx *= inv; qy *= inv; qz *= inv; qw *= inv;
+        const float tx = col[0].w, ty = col[1].w, tz = col[2].w;
+        const float dx = 0.5f * (tx * qw + ty * qz - tz * qy);
+        const float dy = 0.5f * (-tx * qz + ty * qw + tz * qx);
+        const float dz = 0.5f * (tx * qy - ty * qx + tz * qw);
+        const float dw = -0.5f * (tx * qx + ty * qy + tz * qz);
+        S.pal_ext[2 * (size_t)b + 0] = make_float4(qx, qy, qz, qw);
+        S.pal_ext[2 * (size_t)b + 1] = make_float4(dx, dy, dz, dw);
+    }
 }
 
 constexpr uint32_t kHierWarps = 4;
@@ -335,6 +366,7 @@ __global__ void __launch_bounds__(32 * kHierWarps) hierarchy_kernel(DevModel M, 
     S.morphR = morphR;
     S.morphT = morphT;
     S.palette = F.palette + (size_t)slot * M.nb * 3;
+    S.pal_ext = F.pal_ext ? F.pal_ext + (size_t)slot * M.nb * 2 : nullptr;
 
     if (prologue) {
         // ---- morph application-slot rates: Poser::UpdateMorphTransform's skip test and group recursion
@@ -452,6 +484,7 @@ __global__ void __launch_bounds__(kHierCtaThreads) hierarchy_cta_kernel(DevModel
     S.poseR = s_poseR; S.poseT = s_poseT; S.totR = s_totR; S.totT = s_totT; S.local = s_local;
     S.ikR = s_ikR; S.preIK = s_preIK; S.morphR = s_morphR; S.morphT = s_morphT;
     S.palette = F.palette + (size_t)slot * nb * 3;
+    S.pal_ext = F.pal_ext ? F.pal_ext + (size_t)slot * nb * 2 : nullptr;
 
     // ---- sampled poses of every bone (written by K1 / SetBonePose), the static bone records and the program
     for (uint32_t b = tid; b < nb; b += kHierCtaThreads) {
@@ -584,26 +617,28 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 
 struct Col3 { float4 c0, c1, c2; };  // skinning matrix as three columns (M0c, M1c, M2c, M3c)
 
+template <int PS>  // PS = float4 per staged bone: 3 (matrix columns) or 5 (+ rotation quaternion, dual part)
 __device__ __forceinline__ Col3 pal_load(const float4* __restrict__ pal, uint32_t id) {
     Col3 r;
-    r.c0 = pal[3 * id + 0];
-    r.c1 = pal[3 * id + 1];
-    r.c2 = pal[3 * id + 2];
+    r.c0 = pal[PS * id + 0];
+    r.c1 = pal[PS * id + 1];
+    r.c2 = pal[PS * id + 2];
     return r;
 }
 __device__ __forceinline__ float4 f4_scale(const float4& a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
 __device__ __forceinline__ float4 f4_add(const float4& a, const float4& b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
 // One vertex.  ids: 4 x u16 tile-local bone indices (type in bits 15:13 of id0); w: BDEF2 uses w.x, BDEF4 all four.
+template <int PS>
 __device__ __forceinline__ void skin_vertex(const float4* __restrict__ pal, uint32_t ids_lo, uint32_t ids_hi,
                                             const float4& w, float px, float py, float pz, float nx, float ny,
                                             float nz, float* __restrict__ op, float* __restrict__ on) {
     const uint32_t type = (ids_lo >> 13) & 7u;
     const uint32_t id0 = ids_lo & 0x1FFFu, id1 = ids_lo >> 16;
-    Col3 Mx = pal_load(pal, id0);
+    Col3 Mx = pal_load<PS>(pal, id0);
     if (type == kDevBdef2) {
         // Lerp(mat_1, mat_0)[w] = (1-w)*mat_1 + w*mat_0 (poser_impl.inl:422, math_impl.inl:1246-1254)
-        const Col3 B = pal_load(pal, id1);
+        const Col3 B = pal_load<PS>(pal, id1);
         const float l = w.x, om = 1.0f - w.x;
         Mx.c0 = f4_add(f4_scale(B.c0, om), f4_scale(Mx.c0, l));
         Mx.c1 = f4_add(f4_scale(B.c1, om), f4_scale(Mx.c1, l));
@@ -611,7 +646,7 @@ __device__ __forceinline__ void skin_vertex(const float4* __restrict__ pal, uint
     } else if (type == kDevBdef4) {
         // mat_0*w0 + mat_1*w1 + mat_2*w2 + mat_3*w3, left to right (poser_impl.inl:433)
         const uint32_t id2 = ids_hi & 0xFFFFu, id3 = ids_hi >> 16;
-        const Col3 B = pal_load(pal, id1), C = pal_load(pal, id2), D = pal_load(pal, id3);
+        const Col3 B = pal_load<PS>(pal, id1), C = pal_load<PS>(pal, id2), D = pal_load<PS>(pal, id3);
         Mx.c0 = f4_add(f4_add(f4_add(f4_scale(Mx.c0, w.x), f4_scale(B.c0, w.y)), f4_scale(C.c0, w.z)), f4_scale(D.c0, w.w));
         Mx.c1 = f4_add(f4_add(f4_add(f4_scale(Mx.c1, w.x), f4_scale(B.c1, w.y)), f4_scale(C.c1, w.z)), f4_scale(D.c1, w.w));
         Mx.c2 = f4_add(f4_add(f4_add(f4_scale(Mx.c2, w.x), f4_scale(B.c2, w.y)), f4_scale(C.c2, w.z)), f4_scale(D.c2, w.w));
@@ -625,19 +660,88 @@ __device__ __forceinline__ void skin_vertex(const float4* __restrict__ pal, uint
     on[2] = nx * Mx.c2.x + ny * Mx.c2.y + nz * Mx.c2.z;
 }
 
-// shared memory carve-up (bytes): [stage 0][stage 1][palette 0][palette 1][rates 0][rates 1]
-__host__ __device__ inline uint32_t skin_stage_bytes(int layout) {
-    return layout == MMDGPU_LAYOUT_SOA_POS_NRM ? kTileVerts * 24u : kTileVerts * 32u;
+// ---- extensions (parity unpinned: libmmd implements none of these) -----------------------------
+__device__ __forceinline__ void quat_rotate(const float4& q, float vx, float vy, float vz, float* o) {
+    // v' = v + 2 * cross(q.xyz, cross(q.xyz, v) + q.w * v)
+    const float cx = q.y * vz - q.z * vy + q.w * vx, cy = q.z * vx - q.x * vz + q.w * vy, cz = q.x * vy - q.y * vx + q.w * vz;
+    o[0] = vx + 2.0f * (q.y * cz - q.z * cy);
+    o[1] = vy + 2.0f * (q.z * cx - q.x * cz);
+    o[2] = vz + 2.0f * (q.x * cy - q.y * cx);
 }
-__host__ __device__ inline uint32_t skin_pal_bytes(uint32_t max_tile_bones) { return max_tile_bones * 48u; }
+// Spherical deform (PMX SDEF): rotate about the centre C with slerp(q0, q1, w1), translate by the weighted
+// transformed centres cr0 / cr1 (precomputed at load).  sd = {C, cr0, cr1}.
+__device__ __forceinline__ void skin_sdef(const float4* __restrict__ pal, uint32_t id0, uint32_t id1, float w0,
+                                          const float4* __restrict__ sd, float px, float py, float pz, float nx, float ny,
+                                          float nz, float* __restrict__ op, float* __restrict__ on) {
+    const float w1 = 1.0f - w0;
+    const Col3 A = pal_load<5>(pal, id0), B = pal_load<5>(pal, id1);
+    const float4 q0 = pal[5 * id0 + 3];
+    float4 q1 = pal[5 * id1 + 3];
+    float dot = q0.x * q1.x + q0.y * q1.y + q0.z * q1.z + q0.w * q1.w;
+    if (dot < 0.0f) { q1 = make_float4(-q1.x, -q1.y, -q1.z, -q1.w); dot = -dot; }
+    float k0 = w0, k1 = w1;
+    if (dot < 0.9995f) {
+        const float om = acosf(dot), so = sinf(om);
+        k0 = sinf(w0 * om) / so;
+        k1 = sinf(w1 * om) / so;
+    }
+    float4 q = make_float4(q0.x * k0 + q1.x * k1, q0.y * k0 + q1.y * k1, q0.z * k0 + q1.z * k1, q0.w * k0 + q1.w * k1);
+    const float inv = 1.0f / sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    q = make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
+    const float4 C = sd[0], c0 = sd[1], c1 = sd[2];
+    float r[3];
+    quat_rotate(q, px - C.x, py - C.y, pz - C.z, r);
+    const float t0x = c0.x * A.c0.x + c0.y * A.c0.y + c0.z * A.c0.z + A.c0.w, t0y = c0.x * A.c1.x + c0.y * A.c1.y + c0.z * A.c1.z + A.c1.w,
+                t0z = c0.x * A.c2.x + c0.y * A.c2.y + c0.z * A.c2.z + A.c2.w;
+    const float t1x = c1.x * B.c0.x + c1.y * B.c0.y + c1.z * B.c0.z + B.c0.w, t1y = c1.x * B.c1.x + c1.y * B.c1.y + c1.z * B.c1.z + B.c1.w,
+                t1z = c1.x * B.c2.x + c1.y * B.c2.y + c1.z * B.c2.z + B.c2.w;
+    op[0] = r[0] + t0x * w0 + t1x * w1;
+    op[1] = r[1] + t0y * w0 + t1y * w1;
+    op[2] = r[2] + t0z * w0 + t1z * w1;
+    quat_rotate(q, nx, ny, nz, on);
+}
+// Dual-quaternion blend (PMX 2.1 QDEF) of four bones, antipodality resolved against the first bone.
+__device__ __forceinline__ void skin_qdef(const float4* __restrict__ pal, uint32_t ids_lo, uint32_t ids_hi, const float4& w,
+                                          float px, float py, float pz, float nx, float ny, float nz, float* __restrict__ op,
+                                          float* __restrict__ on) {
+    const uint32_t id[4] = {ids_lo & 0x1FFFu, ids_lo >> 16, ids_hi & 0xFFFFu, ids_hi >> 16};
+    const float wt[4] = {w.x, w.y, w.z, w.w};
+    const float4 qa = pal[5 * id[0] + 3];
+    float4 br = make_float4(0.f, 0.f, 0.f, 0.f), bd = br;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 q = pal[5 * id[i] + 3], d = pal[5 * id[i] + 4];
+        float s = wt[i];
+        if (q.x * qa.x + q.y * qa.y + q.z * qa.z + q.w * qa.w < 0.0f) s = -s;
+        br = make_float4(br.x + q.x * s, br.y + q.y * s, br.z + q.z * s, br.w + q.w * s);
+        bd = make_float4(bd.x + d.x * s, bd.y + d.y * s, bd.z + d.z * s, bd.w + d.w * s);
+    }
+    const float inv = 1.0f / sqrtf(br.x * br.x + br.y * br.y + br.z * br.z + br.w * br.w);
+    br = make_float4(br.x * inv, br.y * inv, br.z * inv, br.w * inv);
+    bd = make_float4(bd.x * inv, bd.y * inv, bd.z * inv, bd.w * inv);
+    float r[3];
+    quat_rotate(br, px, py, pz, r);
+    // translation of a unit dual quaternion: 2 * (qr.w * qd.xyz - qd.w * qr.xyz + cross(qr.xyz, qd.xyz))
+    op[0] = r[0] + 2.0f * (br.w * bd.x - bd.w * br.x + (br.y * bd.z - br.z * bd.y));
+    op[1] = r[1] + 2.0f * (br.w * bd.y - bd.w * br.y + (br.z * bd.x - br.x * bd.z));
+    op[2] = r[2] + 2.0f * (br.w * bd.z - bd.w * br.z + (br.x * bd.y - br.y * bd.x));
+    quat_rotate(br, nx, ny, nz, on);
+}
+
+// shared memory carve-up (bytes): [stage 0][stage 1][palette 0][palette 1][rates 0][rates 1]
+__host__ __device__ inline uint32_t skin_stage_bytes(int layout, bool ext) {
+    return layout == MMDGPU_LAYOUT_SOA_POS_NRM ? kTileVerts * (ext ? 32u : 24u) : kTileVerts * 32u;  // ext SoA: + UV plane
+}
+__host__ __device__ inline uint32_t skin_pal_bytes(uint32_t max_tile_bones, bool ext) { return max_tile_bones * (ext ? 80u : 48u); }
 
 constexpr uint32_t kPalPrefetch = 2;  // palette float4 per thread held in registers across the compute phase
 constexpr int V = (int)kVertsPerThread;
 
-template <int LAYOUT>
+template <int LAYOUT, bool EXT>
 __global__ void __launch_bounds__(kSkinThreads, 2) skin_kernel(DevModel M, DevFrames F, uint32_t chunk, uint32_t n_chunks) {
+    constexpr uint32_t PS = EXT ? 5u : 3u;  // float4 per staged bone
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const uint32_t stage_bytes = skin_stage_bytes(LAYOUT), pal_bytes = skin_pal_bytes(M.max_tile_bones);
+    const uint32_t stage_bytes = skin_stage_bytes(LAYOUT, EXT), pal_bytes = skin_pal_bytes(M.max_tile_bones, EXT);
     unsigned char* stage_base = smem_raw;
     float4* pal_base = reinterpret_cast<float4*>(smem_raw + 2 * stage_bytes);
     float* rate_base = reinterpret_cast<float*>(smem_raw + 2 * stage_bytes + 2 * pal_bytes);
@@ -679,7 +783,7 @@ __global__ void __launch_bounds__(kSkinThreads, 2) skin_kernel(DevModel M, DevFr
         const uint4 I = __ldg(reinterpret_cast<const uint4*>(M.ids + v0 + j));
         ilo[j] = I.x; ihi[j] = I.y; ilo[j + 1] = I.z; ihi[j + 1] = I.w;
         uu[j] = vv[j] = uu[j + 1] = vv[j + 1] = 0.f;
-        if (LAYOUT == MMDGPU_LAYOUT_INTERLEAVED_SOKOL32) {
+        if (LAYOUT == MMDGPU_LAYOUT_INTERLEAVED_SOKOL32 || EXT) {
             const float4 UV = __ldg(reinterpret_cast<const float4*>(M.uv + v0 + j));
             uu[j] = UV.x; vv[j] = UV.y; uu[j + 1] = UV.z; vv[j + 1] = UV.w;
         }
@@ -696,21 +800,37 @@ __global__ void __launch_bounds__(kSkinThreads, 2) skin_kernel(DevModel M, DevFr
     }
     // tile-local palette: float4 i of the staged palette comes from float4 psrc(i) of the slot's global palette
     const uint32_t tb0 = __ldg(M.tile_bone_begin + tile);
-    const uint32_t npal4 = (__ldg(M.tile_bone_begin + tile + 1) - tb0) * 3u;
+    const uint32_t npal4 = (__ldg(M.tile_bone_begin + tile + 1) - tb0) * PS;
     const uint32_t nrate4 = M.n_nodes_pad >> 2;
+    // float4 i of the staged palette = component i % PS of tile bone i / PS: a matrix column (components 0..2) or,
+    // with extensions, the rotation quaternion / dual part (components 3, 4; flagged by bit 31)
+    auto pal_source = [&](uint32_t i) -> uint32_t {
+        const uint32_t bone = (uint32_t)__ldg(M.tile_bones + tb0 + i / PS), comp = i % PS;
+        return comp < 3u ? bone * 3u + comp : (0x80000000u | (bone * 2u + comp - 3u));
+    };
+    auto pal_fetch = [&](uint32_t slot, uint32_t src) -> float4 {
+        if (EXT && (src & 0x80000000u)) return __ldg(F.pal_ext + (size_t)slot * M.nb * 2 + (src & 0x7FFFFFFFu));
+        return __ldg(F.palette + (size_t)slot * M.nb * 3 + src);
+    };
     uint32_t psrc[kPalPrefetch];
 #pragma unroll
     for (uint32_t q = 0; q < kPalPrefetch; ++q) {
         const uint32_t i = tid + q * kSkinThreads;
-        psrc[q] = (i < npal4) ? (uint32_t)__ldg(M.tile_bones + tb0 + i / 3u) * 3u + i % 3u : 0xFFFFFFFFu;
+        psrc[q] = (i < npal4) ? pal_source(i) : 0xFFFFFFFFu;
     }
-    const size_t pal_slot_stride = (size_t)M.nb * 3;  // float4 per slot
+    uint32_t uvbase[V], uvrounds[V];
+    if (EXT) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const uint2 h = __ldg(M.uv_ell_hdr + tile * kTileGroups + j * kSkinWarps + warp);
+            uvbase[j] = h.x + lane;
+            uvrounds[j] = h.y;
+        }
+    }
 
     // ---- prologue: slot s0 straight into buffer 0
     {
-        const float4* gp = F.palette + (size_t)s0 * pal_slot_stride;
-        for (uint32_t i = tid; i < npal4; i += kSkinThreads)
-            pal_base[i] = __ldg(gp + (uint32_t)__ldg(M.tile_bones + tb0 + i / 3u) * 3u + i % 3u);
+        for (uint32_t i = tid; i < npal4; i += kSkinThreads) pal_base[i] = pal_fetch(s0, pal_source(i));
         const float4* gr = reinterpret_cast<const float4*>(F.node_rate + (size_t)s0 * M.n_nodes_pad);
         for (uint32_t i = tid; i < nrate4; i += kSkinThreads) reinterpret_cast<float4*>(rate_base)[i] = __ldg(gr + i);
     }
@@ -724,12 +844,11 @@ __global__ void __launch_bounds__(kSkinThreads, 2) skin_kernel(DevModel M, DevFr
         const bool has_next = s + 1 < s1;
         // ---- next slot's palette subset and rates: loads issued now, consumed after the compute phase
         float4 pf[kPalPrefetch], rf = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4* gp = F.palette + (size_t)(s + 1) * pal_slot_stride;
         const float4* gr = reinterpret_cast<const float4*>(F.node_rate + (size_t)(s + 1) * M.n_nodes_pad);
         if (has_next) {
 #pragma unroll
             for (uint32_t q = 0; q < kPalPrefetch; ++q)
-                if (psrc[q] != 0xFFFFFFFFu) pf[q] = __ldg(gp + psrc[q]);
+                if (psrc[q] != 0xFFFFFFFFu) pf[q] = pal_fetch(s + 1, psrc[q]);
             if (tid < nrate4) rf = __ldg(gr + tid);
         }
         // ---- compute: step j is (nearly always) one skinning type across the warp
@@ -750,19 +869,38 @@ __global__ void __launch_bounds__(kSkinThreads, 2) skin_kernel(DevModel M, DevFr
                 iz = iz + ent.z * r;
             }
             float op[3], on[3];
+            const uint32_t type = (ilo[j] >> 13) & 7u;
             // coordinate + vertex_image (poser_impl.inl:407)
-            skin_vertex(pal, ilo[j], ihi[j], wv[j], px[j] + ix, py[j] + iy, pz[j] + iz, nx[j], ny[j], nz[j], op, on);
+            if (EXT && type == kDevSdef)
+                skin_sdef(pal, ilo[j] & 0x1FFFu, ilo[j] >> 16, wv[j].x, M.sdef + (size_t)(v0 + j) * 3, px[j] + ix, py[j] + iy,
+                          pz[j] + iz, nx[j], ny[j], nz[j], op, on);
+            else if (EXT && type == kDevQdef)
+                skin_qdef(pal, ilo[j], ihi[j], wv[j], px[j] + ix, py[j] + iy, pz[j] + iz, nx[j], ny[j], nz[j], op, on);
+            else
+                skin_vertex<(int)PS>(pal, ilo[j], ihi[j], wv[j], px[j] + ix, py[j] + iy, pz[j] + iz, nx[j], ny[j], nz[j], op, on);
+            float mu = uu[j], mv = vv[j];
+            if (EXT) {
+                // applied UV morphs: uv = uv + offset.xy * rate, application order
+                const float4* __restrict__ ue = M.uv_ell_ent + uvbase[j];
+                for (uint32_t k = 0; k < uvrounds[j]; ++k) {
+                    const float4 ent = __ldg(ue + (size_t)k * 32);
+                    const float r = *reinterpret_cast<const float*>(nrate + __float_as_uint(ent.z));
+                    mu = mu + ent.x * r;
+                    mv = mv + ent.y * r;
+                }
+            }
             if (LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) {
                 float* sp = reinterpret_cast<float*>(stage) + orig[j] * 3u;
                 float* sn = reinterpret_cast<float*>(stage + kTileVerts * 12u) + orig[j] * 3u;
                 sp[0] = op[0]; sp[1] = op[1]; sp[2] = op[2];
                 sn[0] = on[0]; sn[1] = on[1]; sn[2] = on[2];
+                if (EXT) reinterpret_cast<float2*>(stage + kTileVerts * 24u)[orig[j]] = make_float2(mu, mv);
             } else {
                 // main.cpp:838-859: Vertex{pos*0.1f, normal, uv}
                 const float mmd_to_meter = 0.1f;
                 float4* sv = reinterpret_cast<float4*>(stage) + orig[j] * 2u;
                 sv[0] = make_float4(op[0] * mmd_to_meter, op[1] * mmd_to_meter, op[2] * mmd_to_meter, on[0]);
-                sv[1] = make_float4(on[1], on[2], uu[j], vv[j]);
+                sv[1] = make_float4(on[1], on[2], mu, mv);
             }
         }
         // ---- publish the next slot's staging data into the other buffer
@@ -773,7 +911,7 @@ __global__ void __launch_bounds__(kSkinThreads, 2) skin_kernel(DevModel M, DevFr
             for (uint32_t q = 0; q < kPalPrefetch; ++q)
                 if (psrc[q] != 0xFFFFFFFFu) npal[tid + q * kSkinThreads] = pf[q];
             for (uint32_t i = tid + kPalPrefetch * kSkinThreads; i < npal4; i += kSkinThreads)
-                npal[i] = __ldg(gp + (uint32_t)__ldg(M.tile_bones + tb0 + i / 3u) * 3u + i % 3u);
+                npal[i] = pal_fetch(s + 1, pal_source(i));
             if (tid < nrate4) nrt[tid] = rf;
             for (uint32_t i = tid + kSkinThreads; i < nrate4; i += kSkinThreads) nrt[i] = __ldg(gr + i);
         }
@@ -786,6 +924,7 @@ __global__ void __launch_bounds__(kSkinThreads, 2) skin_kernel(DevModel M, DevFr
             if (LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) {
                 bulk_s2g(F.out_pos + vbase * 3, stage, kTileVerts * 12u);
                 bulk_s2g(F.out_nrm + vbase * 3, stage + kTileVerts * 12u, kTileVerts * 12u);
+                if (EXT) bulk_s2g(F.out_uv + vbase, stage + kTileVerts * 24u, kTileVerts * 8u);
             } else {
                 bulk_s2g(F.out_inter + vbase * 2, stage, kTileVerts * 32u);
             }
@@ -822,7 +961,13 @@ cudaError_t launch_hierarchy(cudaStream_t st, const DevModel& M, const DevFrames
 }
 
 size_t skin_smem_bytes(const DevModel& M, int layout) {
-    return 2 * (size_t)skin_stage_bytes(layout) + 2 * (size_t)skin_pal_bytes(M.max_tile_bones) + 2 * (size_t)M.n_nodes_pad * 4;
+    const bool ext = M.extensions != 0;
+    return 2 * (size_t)skin_stage_bytes(layout, ext) + 2 * (size_t)skin_pal_bytes(M.max_tile_bones, ext) + 2 * (size_t)M.n_nodes_pad * 4;
+}
+
+template <int LAYOUT, bool EXT>
+static cudaError_t skin_opt_in(const DevModel& M) {
+    return cudaFuncSetAttribute(skin_kernel<LAYOUT, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skin_smem_bytes(M, LAYOUT));
 }
 
 cudaError_t prepare_skin_kernels(const DevModel& M) {
@@ -833,11 +978,14 @@ cudaError_t prepare_skin_kernels(const DevModel& M) {
         e = cudaFuncSetAttribute(hierarchy_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHierCtaSmemLimit);
         if (e != cudaSuccess) return e;
     }
-    e = cudaFuncSetAttribute(skin_kernel<MMDGPU_LAYOUT_SOA_POS_NRM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)skin_smem_bytes(M, MMDGPU_LAYOUT_SOA_POS_NRM));
+    if (M.extensions) {
+        e = skin_opt_in<MMDGPU_LAYOUT_SOA_POS_NRM, true>(M);
+        if (e != cudaSuccess) return e;
+        return skin_opt_in<MMDGPU_LAYOUT_INTERLEAVED_SOKOL32, true>(M);
+    }
+    e = skin_opt_in<MMDGPU_LAYOUT_SOA_POS_NRM, false>(M);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(skin_kernel<MMDGPU_LAYOUT_INTERLEAVED_SOKOL32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)skin_smem_bytes(M, MMDGPU_LAYOUT_INTERLEAVED_SOKOL32));
+    return skin_opt_in<MMDGPU_LAYOUT_INTERLEAVED_SOKOL32, false>(M);
 }
 
 cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, int layout, uint32_t slots_per_cta) {
@@ -846,10 +994,14 @@ cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, 
     const uint32_t n_chunks = (F.n_slots + slots_per_cta - 1) / slots_per_cta;
     const uint32_t grid = M.n_tiles * n_chunks;
     const size_t smem = skin_smem_bytes(M, layout);
-    if (layout == MMDGPU_LAYOUT_SOA_POS_NRM)
-        skin_kernel<MMDGPU_LAYOUT_SOA_POS_NRM><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);
-    else
-        skin_kernel<MMDGPU_LAYOUT_INTERLEAVED_SOKOL32><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);
+    const bool soa = layout == MMDGPU_LAYOUT_SOA_POS_NRM;
+    if (M.extensions) {
+        if (soa) skin_kernel<MMDGPU_LAYOUT_SOA_POS_NRM, true><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);
+        else skin_kernel<MMDGPU_LAYOUT_INTERLEAVED_SOKOL32, true><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);
+    } else {
+        if (soa) skin_kernel<MMDGPU_LAYOUT_SOA_POS_NRM, false><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);
+        else skin_kernel<MMDGPU_LAYOUT_INTERLEAVED_SOKOL32, false><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);
+    }
     return cudaGetLastError();
 }
 

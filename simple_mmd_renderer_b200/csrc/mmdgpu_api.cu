@@ -155,14 +155,12 @@ mmdgpu_status upload_model(mmdgpu_model* m) {
     D = DevModel{};
     const uint32_t nv = p.nv, nb = p.nb;
     const uint32_t nvp = p.nv_pad;
-    if (p.extensions)
-        return set_err(ctx, MMDGPU_ERR_UNSUPPORTED,
-                       "extensions (spherical SDEF, dual-quaternion QDEF, applied UV morphs) are not built into this version");
     D.nv = nv; D.nv_pad = nvp; D.nb = nb; D.nm = p.nm;
     D.n_nodes = uint32_t(p.node_morph.size());
     D.n_nodes_pad = round_up(D.n_nodes + 1, 4);  // + the always-zero slot the ELL padding points at
     D.n_tiles = p.n_tiles;
     D.max_tile_bones = std::max<uint32_t>(1, p.max_tile_bones);
+    D.extensions = p.extensions ? 1u : 0u;
 
     // ---- vertex streams, structure of arrays, in tile storage order (host_plan.hpp)
     std::vector<float> plane[6];
@@ -207,6 +205,25 @@ mmdgpu_status upload_model(mmdgpu_model* m) {
     CU(ctx, upload(ctx, m->mem, ent, &D.ell_ent));
     CU(ctx, upload(ctx, m->mem, p.tile_bone_begin, &D.tile_bone_begin));
     CU(ctx, upload(ctx, m->mem, p.tile_bones, &D.tile_bones));
+    if (p.extensions) {
+        // spherical-deform parameters (3 float4 per storage position) and the UV-morph table
+        std::vector<float4> sd(size_t(nvp) * 3, make_float4(0.f, 0.f, 0.f, 0.f));
+        if (!p.st_sdef.empty())
+            for (size_t i = 0; i < sd.size(); ++i)
+                sd[i] = make_float4(p.st_sdef[4 * i], p.st_sdef[4 * i + 1], p.st_sdef[4 * i + 2], 0.f);
+        CU(ctx, upload(ctx, m->mem, sd, &D.sdef));
+        std::vector<uint2> uhdr(p.uv_ell_base.size());
+        for (size_t g = 0; g < uhdr.size(); ++g) uhdr[g] = make_uint2(p.uv_ell_base[g], p.uv_ell_rounds[g]);
+        std::vector<float4> uent(p.uv_ell_node.size());
+        for (size_t e = 0; e < uent.size(); ++e) {
+            float slot_bits;
+            const uint32_t node = p.uv_ell_node[e] * 4u;
+            std::memcpy(&slot_bits, &node, 4);
+            uent[e] = make_float4(p.uv_ell_offset[4 * e], p.uv_ell_offset[4 * e + 1], slot_bits, 0.f);
+        }
+        CU(ctx, upload(ctx, m->mem, uhdr, &D.uv_ell_hdr));
+        CU(ctx, upload(ctx, m->mem, uent, &D.uv_ell_ent));
+    }
     // ---- bones and the program
     static_assert(sizeof(BoneStatic) == 48, "BoneStatic is read as three float4");
     CU(ctx, upload(ctx, m->mem, p.bones, &D.bones));
@@ -376,6 +393,13 @@ mmdgpu_status stream_view(mmdgpu_frames* f, mmdgpu_stream_id id, StreamView& v) 
     case MMDGPU_STREAM_SKIN_MATRIX:
         v.base = reinterpret_cast<const char*>(f->dev.palette);
         v.slot_stride = v.slot_bytes = size_t(M.nb) * 48;
+        return MMDGPU_OK;
+    case MMDGPU_STREAM_UV:
+        if (!f->dev.out_uv)
+            return set_err(f->ctx, MMDGPU_ERR_INVALID_ARG, "the UV stream exists only for SoA frames of a model created with extensions");
+        v.base = reinterpret_cast<const char*>(f->dev.out_uv);
+        v.slot_stride = size_t(M.nv_pad) * 8;
+        v.slot_bytes = size_t(M.nv) * 8;
         return MMDGPU_OK;
     }
     return set_err(f->ctx, MMDGPU_ERR_INVALID_ARG, "unknown stream id");
@@ -824,9 +848,11 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_create(mmdgpu_context_t ctx, mmdgpu_model
     CU(ctx, dalloc(f->mem, &F.morphR, ns * M.n_morph_slots, true, st));
     CU(ctx, dalloc(f->mem, &F.morphT, ns * M.n_morph_slots, true, st));
     CU(ctx, dalloc(f->mem, &F.palette, ns * M.nb * 3, true, st));
+    if (M.extensions) CU(ctx, dalloc(f->mem, &F.pal_ext, ns * M.nb * 2, true, st));
     if (layout == MMDGPU_LAYOUT_SOA_POS_NRM) {
         CU(ctx, dalloc(f->mem, &F.out_pos, ns * M.nv_pad * 3, false, st));
         CU(ctx, dalloc(f->mem, &F.out_nrm, ns * M.nv_pad * 3, false, st));
+        if (M.extensions) CU(ctx, dalloc(f->mem, &F.out_uv, ns * M.nv_pad, false, st));
     } else {
         CU(ctx, dalloc(f->mem, &F.out_inter, ns * M.nv_pad * 2, false, st));
     }

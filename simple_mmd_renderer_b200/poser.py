@@ -237,7 +237,7 @@ class Frames:
     def download(self, slot: int, stream_id: int) -> np.ndarray:
         nv, nb = self.model.n_vertices, self.model.n_bones
         shape = {capi.STREAM_POSITION: (nv, 3), capi.STREAM_NORMAL: (nv, 3), capi.STREAM_INTERLEAVED: (nv, 8),
-                 capi.STREAM_SKIN_MATRIX: (nb, 12)}[stream_id]
+                 capi.STREAM_SKIN_MATRIX: (nb, 12), capi.STREAM_UV: (nv, 2)}[stream_id]
         out = np.empty(shape, np.float32)
         check(self.lib.mmdgpu_frames_download(self.h, int(slot), int(stream_id), _ptr(out), out.nbytes), self.ctx.h)
         return out

@@ -26,6 +26,9 @@ struct mmdgpu_context {
     bool own_stream = false;
     cudaStream_t dl_stream = nullptr;
     cudaEvent_t dl_event = nullptr;
+    // fused updates run key-frame sampling and the bone hierarchy of update n+1 on this stream while the skinning
+    // kernel of update n still runs on `stream`
+    cudaStream_t pre_stream = nullptr;
     std::string err;
     uint64_t launches = 0;
     int max_smem_optin = 0;
@@ -94,6 +97,30 @@ struct mmdgpu_frames {
     bool range_mode = false;
     uint32_t frame_stride = 1;
     uint32_t slots_per_cta = 1;
+    // What the hierarchy kernel hands to the skinning kernel (palette, extension palette, application-slot rates)
+    // exists twice: fused update n+1 writes one copy on the pre stream while update n's skinning reads the other.
+    float4* pal_buf[2] = {nullptr, nullptr};
+    float4* ext_buf[2] = {nullptr, nullptr};
+    float* rate_buf[2] = {nullptr, nullptr};
+    int cur = 0;                                  // copy the step-wise entry points and the downloads use
+    cudaEvent_t ev_pre[2] = {nullptr, nullptr};   // hierarchy of the update that wrote copy i has finished
+    cudaEvent_t ev_skin[2] = {nullptr, nullptr};  // skinning that read copy i has finished
+    bool skin_recorded[2] = {false, false};
+    cudaEvent_t ev_main = nullptr;                // main-stream work the next fused update must follow
+    bool main_dirty = true;
+    void select(int i) {
+        dev.palette = pal_buf[i];
+        dev.pal_ext = ext_buf[i];
+        dev.node_rate = rate_buf[i];
+        cur = i;
+    }
+    ~mmdgpu_frames() {
+        for (int i = 0; i < 2; ++i) {
+            if (ev_pre[i]) cudaEventDestroy(ev_pre[i]);
+            if (ev_skin[i]) cudaEventDestroy(ev_skin[i]);
+        }
+        if (ev_main) cudaEventDestroy(ev_main);
+    }
 };
 
 namespace {
@@ -285,7 +312,7 @@ mmdgpu_status upload_anim(mmdgpu_animation* a) {
     return MMDGPU_OK;
 }
 
-mmdgpu_status bind_anims(mmdgpu_frames* f, const mmdgpu_animation_t* per_instance) {
+mmdgpu_status bind_anims(mmdgpu_frames* f, const mmdgpu_animation_t* per_instance, cudaStream_t st) {
     mmdgpu_context_t ctx = f->ctx;
     const uint32_t ni = f->dev.n_instances;
     if (!per_instance) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "per_instance animation array is NULL");
@@ -301,7 +328,7 @@ mmdgpu_status bind_anims(mmdgpu_frames* f, const mmdgpu_animation_t* per_instanc
     // from pageable memory returns after staging, so h_anims may be rewritten immediately.
     f->h_anims.resize(ni);
     for (uint32_t i = 0; i < ni; ++i) f->h_anims[i] = per_instance[i]->dev;
-    CU(ctx, cudaMemcpyAsync(f->d_anims, f->h_anims.data(), sizeof(DevAnim) * ni, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(f->d_anims, f->h_anims.data(), sizeof(DevAnim) * ni, cudaMemcpyHostToDevice, st));
     f->bound.assign(per_instance, per_instance + ni);
     return MMDGPU_OK;
 }
@@ -309,20 +336,21 @@ mmdgpu_status bind_anims(mmdgpu_frames* f, const mmdgpu_animation_t* per_instanc
 // Brackets one launch with events when profiling is on.
 struct Timed {
     mmdgpu_context_t ctx;
+    cudaStream_t st;
     cudaEvent_t b = nullptr;
-    Timed(mmdgpu_context_t c, int id) : ctx(c) {
+    Timed(mmdgpu_context_t c, int id, cudaStream_t stream = nullptr) : ctx(c), st(stream ? stream : c->stream) {
         if (!c->profiling) return;
         cudaEvent_t ev[2] = {nullptr, nullptr};
         for (auto& e : ev) {
             if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); }
             else if (cudaEventCreate(&e) != cudaSuccess) return;
         }
-        cudaEventRecord(ev[0], c->stream);
+        cudaEventRecord(ev[0], st);
         b = ev[1];
         c->spans.push_back({id, ev[0], ev[1]});
     }
     ~Timed() {
-        if (b) cudaEventRecord(b, ctx->stream);
+        if (b) cudaEventRecord(b, st);
         ctx->launches++;
     }
 };
@@ -334,26 +362,26 @@ mmdgpu_status enter(mmdgpu_context_t ctx) {
 }
 
 mmdgpu_status do_seek(mmdgpu_frames* f, const mmdgpu_animation_t* per_instance, const uint32_t* frames, bool range,
-                      uint32_t stride, bool write_untracked) {
+                      uint32_t stride, bool write_untracked, cudaStream_t st) {
     mmdgpu_context_t ctx = f->ctx;
     if (!frames) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "frame id array is NULL");
-    if (mmdgpu_status s = bind_anims(f, per_instance)) return s;
+    if (mmdgpu_status s = bind_anims(f, per_instance, st)) return s;
     const uint32_t n = range ? f->dev.n_instances : f->dev.n_slots;
-    CU(ctx, cudaMemcpyAsync(f->dev.frame_id, frames, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(f->dev.frame_id, frames, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
     f->range_mode = range;
     f->frame_stride = stride;
     {
-        Timed t(ctx, MMDGPU_KERNEL_POSE_SAMPLE);
-        CU(ctx, launch_pose_sample(ctx->stream, f->model->dev, f->d_anims, f->dev, write_untracked, range, stride));
+        Timed t(ctx, MMDGPU_KERNEL_POSE_SAMPLE, st);
+        CU(ctx, launch_pose_sample(st, f->model->dev, f->d_anims, f->dev, write_untracked, range, stride));
     }
     return MMDGPU_OK;
 }
 
-mmdgpu_status do_hierarchy(mmdgpu_frames* f, uint32_t lo, uint32_t hi, bool prologue) {
+mmdgpu_status do_hierarchy(mmdgpu_frames* f, uint32_t lo, uint32_t hi, bool prologue, cudaStream_t st) {
     mmdgpu_context_t ctx = f->ctx;
     {
-        Timed t(ctx, MMDGPU_KERNEL_HIERARCHY);
-        CU(ctx, launch_hierarchy(ctx->stream, f->model->dev, f->dev, lo, hi, prologue));
+        Timed t(ctx, MMDGPU_KERNEL_HIERARCHY, st);
+        CU(ctx, launch_hierarchy(st, f->model->dev, f->dev, lo, hi, prologue));
     }
     return MMDGPU_OK;
 }
@@ -454,6 +482,8 @@ MMDGPU_API mmdgpu_status mmdgpu_context_create(int device, void* cuda_stream_or_
         return cuda_fail(nullptr, e, "cudaStreamCreate");
     if ((e = cudaEventCreateWithFlags(&c->dl_event, cudaEventDisableTiming)) != cudaSuccess)
         return cuda_fail(nullptr, e, "cudaEventCreate");
+    if ((e = cudaStreamCreateWithFlags(&c->pre_stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return cuda_fail(nullptr, e, "cudaStreamCreate");
     *out = c.release();
     return MMDGPU_OK;
 }
@@ -461,8 +491,10 @@ MMDGPU_API mmdgpu_status mmdgpu_context_create(int device, void* cuda_stream_or_
 MMDGPU_API void mmdgpu_context_destroy(mmdgpu_context_t ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->pre_stream) cudaStreamSynchronize(ctx->pre_stream);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->dl_stream) { cudaStreamSynchronize(ctx->dl_stream); cudaStreamDestroy(ctx->dl_stream); }
+    if (ctx->pre_stream) { cudaStreamSynchronize(ctx->pre_stream); cudaStreamDestroy(ctx->pre_stream); }
     if (ctx->dl_event) cudaEventDestroy(ctx->dl_event);
     for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
@@ -474,6 +506,7 @@ MMDGPU_API const char* mmdgpu_last_error(mmdgpu_context_t ctx) { return ctx ? ct
 
 MMDGPU_API mmdgpu_status mmdgpu_context_synchronize(mmdgpu_context_t ctx) {
     if (mmdgpu_status s = enter(ctx)) return s;
+    CU(ctx, cudaStreamSynchronize(ctx->pre_stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->dl_stream));
     return MMDGPU_OK;
@@ -489,6 +522,7 @@ MMDGPU_API mmdgpu_status mmdgpu_context_profile_read(mmdgpu_context_t ctx, doubl
                                                      uint64_t launches[MMDGPU_KERNEL_COUNT]) {
     if (mmdgpu_status s = enter(ctx)) return s;
     if (!ms_total || !launches) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "NULL argument");
+    CU(ctx, cudaStreamSynchronize(ctx->pre_stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < MMDGPU_KERNEL_COUNT; ++i) { ms_total[i] = 0.0; launches[i] = 0; }
     for (const auto& sp : ctx->spans) {
@@ -742,6 +776,7 @@ MMDGPU_API mmdgpu_status mmdgpu_model_create_from_pmx(mmdgpu_context_t ctx, cons
 MMDGPU_API void mmdgpu_model_destroy(mmdgpu_model_t model) {
     if (!model) return;
     cudaSetDevice(model->ctx->device);
+    cudaStreamSynchronize(model->ctx->pre_stream);
     cudaStreamSynchronize(model->ctx->stream);
     delete model;
 }
@@ -809,6 +844,7 @@ MMDGPU_API mmdgpu_status mmdgpu_animation_create_from_vmd(mmdgpu_context_t ctx, 
 MMDGPU_API void mmdgpu_animation_destroy(mmdgpu_animation_t a) {
     if (!a) return;
     cudaSetDevice(a->ctx->device);
+    cudaStreamSynchronize(a->ctx->pre_stream);
     cudaStreamSynchronize(a->ctx->stream);
     delete a;
 }
@@ -839,7 +875,7 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_create(mmdgpu_context_t ctx, mmdgpu_model
     CU(ctx, dalloc(f->mem, &F.poseR, ns * M.nb, false, st));
     CU(ctx, dalloc(f->mem, &F.poseT, ns * M.nb, false, st));
     CU(ctx, dalloc(f->mem, &F.rate, ns * M.nm, true, st));
-    CU(ctx, dalloc(f->mem, &F.node_rate, ns * M.n_nodes_pad, true, st));
+    for (int i = 0; i < 2; ++i) CU(ctx, dalloc(f->mem, &f->rate_buf[i], ns * M.n_nodes_pad, true, st));
     CU(ctx, dalloc(f->mem, &F.totR, ns * M.nb, true, st));
     CU(ctx, dalloc(f->mem, &F.totT, ns * M.nb, true, st));
     CU(ctx, dalloc(f->mem, &F.local, ns * M.nb * 12, true, st));
@@ -847,8 +883,14 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_create(mmdgpu_context_t ctx, mmdgpu_model
     CU(ctx, dalloc(f->mem, &F.preIK, ns * M.n_link_slots, true, st));
     CU(ctx, dalloc(f->mem, &F.morphR, ns * M.n_morph_slots, true, st));
     CU(ctx, dalloc(f->mem, &F.morphT, ns * M.n_morph_slots, true, st));
-    CU(ctx, dalloc(f->mem, &F.palette, ns * M.nb * 3, true, st));
-    if (M.extensions) CU(ctx, dalloc(f->mem, &F.pal_ext, ns * M.nb * 2, true, st));
+    for (int i = 0; i < 2; ++i) {
+        CU(ctx, dalloc(f->mem, &f->pal_buf[i], ns * M.nb * 3, true, st));
+        if (M.extensions) CU(ctx, dalloc(f->mem, &f->ext_buf[i], ns * M.nb * 2, true, st));
+        CU(ctx, cudaEventCreateWithFlags(&f->ev_pre[i], cudaEventDisableTiming));
+        CU(ctx, cudaEventCreateWithFlags(&f->ev_skin[i], cudaEventDisableTiming));
+    }
+    CU(ctx, cudaEventCreateWithFlags(&f->ev_main, cudaEventDisableTiming));
+    f->select(0);
     if (layout == MMDGPU_LAYOUT_SOA_POS_NRM) {
         CU(ctx, dalloc(f->mem, &F.out_pos, ns * M.nv_pad * 3, false, st));
         CU(ctx, dalloc(f->mem, &F.out_nrm, ns * M.nv_pad * 3, false, st));
@@ -871,6 +913,7 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_create(mmdgpu_context_t ctx, mmdgpu_model
 MMDGPU_API void mmdgpu_frames_destroy(mmdgpu_frames_t f) {
     if (!f) return;
     cudaSetDevice(f->ctx->device);
+    cudaStreamSynchronize(f->ctx->pre_stream);
     cudaStreamSynchronize(f->ctx->stream);
     cudaStreamSynchronize(f->ctx->dl_stream);
     delete f;
@@ -880,6 +923,7 @@ MMDGPU_API uint32_t mmdgpu_frames_slot_count(mmdgpu_frames_t f) { return f ? f->
 MMDGPU_API mmdgpu_status mmdgpu_reset_posing(mmdgpu_frames_t f) {
     if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
     if (mmdgpu_status s = enter(f->ctx)) return s;
+    f->main_dirty = true;
     {
         Timed t(f->ctx, MMDGPU_KERNEL_POSE_SAMPLE);
         CU(f->ctx, launch_pose_sample(f->ctx->stream, f->model->dev, nullptr, f->dev, true, false, 1));
@@ -891,14 +935,16 @@ MMDGPU_API mmdgpu_status mmdgpu_seek_frame(mmdgpu_frames_t f, const mmdgpu_anima
                                            const uint32_t* frame_per_slot) {
     if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
     if (mmdgpu_status s = enter(f->ctx)) return s;
-    return do_seek(f, per_instance, frame_per_slot, false, 1, false);
+    f->main_dirty = true;
+    return do_seek(f, per_instance, frame_per_slot, false, 1, false, f->ctx->stream);
 }
 
 MMDGPU_API mmdgpu_status mmdgpu_seek_frame_range(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance,
                                                  const uint32_t* first_frame_per_instance, uint32_t frame_stride) {
     if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
     if (mmdgpu_status s = enter(f->ctx)) return s;
-    return do_seek(f, per_instance, first_frame_per_instance, true, frame_stride, false);
+    f->main_dirty = true;
+    return do_seek(f, per_instance, first_frame_per_instance, true, frame_stride, false, f->ctx->stream);
 }
 
 MMDGPU_API mmdgpu_status mmdgpu_set_bone_pose(mmdgpu_frames_t f, uint32_t slot, uint32_t bone, const float T[3],
@@ -907,6 +953,7 @@ MMDGPU_API mmdgpu_status mmdgpu_set_bone_pose(mmdgpu_frames_t f, uint32_t slot, 
     if (mmdgpu_status s = enter(f->ctx)) return s;
     if (!T || !R) return set_err(f->ctx, MMDGPU_ERR_INVALID_ARG, "pose is NULL");
     if (slot >= f->dev.n_slots || bone >= f->model->dev.nb) return set_err(f->ctx, MMDGPU_ERR_BAD_INDEX, "slot or bone out of range");
+    f->main_dirty = true;
     const float t4[4] = {T[0], T[1], T[2], 0.0f};
     const size_t at = size_t(slot) * f->model->dev.nb + bone;
     CU(f->ctx, cudaMemcpyAsync(f->dev.poseT + at, t4, 16, cudaMemcpyHostToDevice, f->ctx->stream));
@@ -918,6 +965,7 @@ MMDGPU_API mmdgpu_status mmdgpu_set_morph_pose(mmdgpu_frames_t f, uint32_t slot,
     if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
     if (mmdgpu_status s = enter(f->ctx)) return s;
     if (slot >= f->dev.n_slots || morph >= f->model->dev.nm) return set_err(f->ctx, MMDGPU_ERR_BAD_INDEX, "slot or morph out of range");
+    f->main_dirty = true;
     CU(f->ctx, cudaMemcpyAsync(f->dev.rate + size_t(slot) * f->model->dev.nm + morph, &weight, 4, cudaMemcpyHostToDevice,
                                f->ctx->stream));
     return MMDGPU_OK;
@@ -926,7 +974,8 @@ MMDGPU_API mmdgpu_status mmdgpu_set_morph_pose(mmdgpu_frames_t f, uint32_t slot,
 MMDGPU_API mmdgpu_status mmdgpu_pre_physics_posing(mmdgpu_frames_t f) {
     if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
     if (mmdgpu_status s = enter(f->ctx)) return s;
-    return do_hierarchy(f, 0, f->model->dev.phase_split, true);
+    f->main_dirty = true;
+    return do_hierarchy(f, 0, f->model->dev.phase_split, true, f->ctx->stream);
 }
 
 MMDGPU_API mmdgpu_status mmdgpu_post_physics_posing(mmdgpu_frames_t f) {
@@ -934,7 +983,8 @@ MMDGPU_API mmdgpu_status mmdgpu_post_physics_posing(mmdgpu_frames_t f) {
     if (mmdgpu_status s = enter(f->ctx)) return s;
     const DevModel& M = f->model->dev;
     if (M.phase_split >= M.n_waves) return MMDGPU_OK;  // no post-physics bones: nothing to evaluate
-    return do_hierarchy(f, M.phase_split, M.n_waves, false);
+    f->main_dirty = true;
+    return do_hierarchy(f, M.phase_split, M.n_waves, false, f->ctx->stream);
 }
 
 MMDGPU_API mmdgpu_status mmdgpu_deform(mmdgpu_frames_t f) {
@@ -950,6 +1000,7 @@ MMDGPU_API mmdgpu_status mmdgpu_set_skinning_matrix_override(mmdgpu_frames_t f, 
     if (!skinning) return set_err(f->ctx, MMDGPU_ERR_INVALID_ARG, "matrix is NULL");
     const uint32_t nb = f->model->dev.nb;
     if (slot >= f->dev.n_slots || bone >= nb) return set_err(f->ctx, MMDGPU_ERR_BAD_INDEX, "slot or bone out of range");
+    f->main_dirty = true;
     float cols[12];
     for (int c = 0; c < 3; ++c)
         for (int r = 0; r < 4; ++r) cols[4 * c + r] = skinning[4 * r + c];
@@ -966,11 +1017,26 @@ MMDGPU_API mmdgpu_status mmdgpu_set_skinning_matrix_override(mmdgpu_frames_t f, 
 static mmdgpu_status update_common(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance, const uint32_t* frames,
                                    bool range, uint32_t stride) {
     // ResetPosing + SeekFrame collapse into one sampling launch that writes identity / zero for items the
-    // clip does not animate (main.cpp:1788-1796).
-    if (mmdgpu_status s = do_seek(f, per_instance, frames, range, stride, true)) return s;
+    // clip does not animate (main.cpp:1788-1796).  Sampling and the hierarchy run on the pre stream into the copy
+    // of (palette, rates) the previous update is NOT using, so they overlap that update's skinning kernel.
+    mmdgpu_context_t ctx = f->ctx;
+    const int next = f->cur ^ 1;
+    if (f->skin_recorded[next]) CU(ctx, cudaStreamWaitEvent(ctx->pre_stream, f->ev_skin[next], 0));
+    if (f->main_dirty) {  // step-wise calls / uploads issued on the main stream since the last fused update
+        CU(ctx, cudaEventRecord(f->ev_main, ctx->stream));
+        CU(ctx, cudaStreamWaitEvent(ctx->pre_stream, f->ev_main, 0));
+        f->main_dirty = false;
+    }
+    f->select(next);
+    if (mmdgpu_status s = do_seek(f, per_instance, frames, range, stride, true, ctx->pre_stream)) return s;
     const DevModel& M = f->model->dev;
-    if (mmdgpu_status s = do_hierarchy(f, 0, M.n_waves, true)) return s;
-    return do_skin(f);
+    if (mmdgpu_status s = do_hierarchy(f, 0, M.n_waves, true, ctx->pre_stream)) return s;
+    CU(ctx, cudaEventRecord(f->ev_pre[next], ctx->pre_stream));
+    CU(ctx, cudaStreamWaitEvent(ctx->stream, f->ev_pre[next], 0));
+    if (mmdgpu_status s = do_skin(f)) return s;
+    CU(ctx, cudaEventRecord(f->ev_skin[next], ctx->stream));
+    f->skin_recorded[next] = true;
+    return MMDGPU_OK;
 }
 
 MMDGPU_API mmdgpu_status mmdgpu_update(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance, const uint32_t* frame_per_slot) {

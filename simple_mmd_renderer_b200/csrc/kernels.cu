@@ -457,7 +457,7 @@ __host__ __device__ inline size_t hier_cta_smem_bytes(uint32_t nb, uint32_t n_li
 __global__ void __launch_bounds__(kHierCtaThreads) hierarchy_cta_kernel(DevModel M, DevFrames F, uint32_t wave_lo,
                                                                         uint32_t wave_hi, uint32_t prologue) {
     extern __shared__ __align__(16) float4 hsm[];
-    const uint32_t slot = blockIdx.x, tid = threadIdx.x, nb = M.nb;
+    const uint32_t slot = blockIdx.x, tid = threadIdx.x, nb = M.nb, nthreads = blockDim.x;
     float4* s_poseR = hsm;
     float4* s_poseT = s_poseR + nb;
     float4* s_totR = s_poseT + nb;
@@ -487,16 +487,16 @@ __global__ void __launch_bounds__(kHierCtaThreads) hierarchy_cta_kernel(DevModel
     S.pal_ext = F.pal_ext ? F.pal_ext + (size_t)slot * nb * 2 : nullptr;
 
     // ---- sampled poses of every bone (written by K1 / SetBonePose), the static bone records and the program
-    for (uint32_t b = tid; b < nb; b += kHierCtaThreads) {
+    for (uint32_t b = tid; b < nb; b += nthreads) {
         s_poseR[b] = F.poseR[(size_t)slot * nb + b];
         s_poseT[b] = F.poseT[(size_t)slot * nb + b];
     }
     {
         const float4* gb = reinterpret_cast<const float4*>(M.bones);
-        for (uint32_t i = tid; i < 3 * nb; i += kHierCtaThreads) s_bones[i] = __ldg(gb + i);
-        for (uint32_t i = tid; i <= M.n_waves; i += kHierCtaThreads) s_wave_begin[i] = __ldg(M.wave_begin + i);
+        for (uint32_t i = tid; i < 3 * nb; i += nthreads) s_bones[i] = __ldg(gb + i);
+        for (uint32_t i = tid; i <= M.n_waves; i += nthreads) s_wave_begin[i] = __ldg(M.wave_begin + i);
         const uint32_t n_ops = __ldg(M.wave_begin + M.n_waves);
-        for (uint32_t i = tid; i < n_ops; i += kHierCtaThreads) s_wave_ops[i] = __ldg(M.wave_ops + i);
+        for (uint32_t i = tid; i < n_ops; i += nthreads) s_wave_ops[i] = __ldg(M.wave_ops + i);
     }
     if (prologue) {
         // ---- morph application-slot rates (poser_impl.inl:329-339), breadth-first over the static DFS tree
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(kHierCtaThreads) hierarchy_cta_kernel(DevModel
         float* nrate = F.node_rate + (size_t)slot * M.n_nodes_pad;
         for (uint32_t dpt = 0; dpt < M.n_depths; ++dpt) {
             const int32_t b0 = M.depth_begin[dpt], b1 = M.depth_begin[dpt + 1];
-            for (int32_t i = b0 + (int32_t)tid; i < b1; i += kHierCtaThreads) {
+            for (int32_t i = b0 + (int32_t)tid; i < b1; i += nthreads) {
                 const int32_t n = M.nodes_by_depth[i];
                 const int32_t par = M.node_parent[n];
                 float r;
@@ -521,18 +521,18 @@ __global__ void __launch_bounds__(kHierCtaThreads) hierarchy_cta_kernel(DevModel
             if (dpt + 1 < M.n_depths) { __threadfence_block(); __syncthreads(); }
         }
         // ---- PrePhysicsPosing's per-bone reset (poser_impl.inl:366-377)
-        for (uint32_t b = tid; b < nb; b += kHierCtaThreads) {
+        for (uint32_t b = tid; b < nb; b += nthreads) {
             s_totR[b] = make_float4(0.f, 0.f, 0.f, 1.f);
             s_totT[b] = make_float4(0.f, 0.f, 0.f, 0.f);
             store_local(s_local + 3 * (size_t)b, m_identity());
         }
-        for (uint32_t i = tid; i < M.n_link_slots; i += kHierCtaThreads) {
+        for (uint32_t i = tid; i < M.n_link_slots; i += nthreads) {
             s_ikR[i] = make_float4(0.f, 0.f, 0.f, 1.f);
             s_preIK[i] = make_float4(0.f, 0.f, 0.f, 1.f);
         }
         __syncthreads();  // node rates of this CTA are visible (written by its own threads)
         // ---- bone morphs (poser_impl.inl:347-354), application order inside each affected bone
-        for (uint32_t i = tid; i < M.n_morph_slots; i += kHierCtaThreads) {
+        for (uint32_t i = tid; i < M.n_morph_slots; i += nthreads) {
             Quat mr = q_identity();
             float tx = 0.f, ty = 0.f, tz = 0.f;
             for (int32_t e = M.bone_morph_row[i]; e < M.bone_morph_row[i + 1]; ++e) {
@@ -552,21 +552,21 @@ __global__ void __launch_bounds__(kHierCtaThreads) hierarchy_cta_kernel(DevModel
     } else {
         // continue from the state the previous launch (pre-physics segment, possibly edited by the host physics
         // hook) left in global memory
-        for (uint32_t b = tid; b < nb; b += kHierCtaThreads) {
+        for (uint32_t b = tid; b < nb; b += nthreads) {
             s_totR[b] = g_totR[b];
             s_totT[b] = g_totT[b];
             s_local[3 * (size_t)b] = g_local[3 * (size_t)b];
             s_local[3 * (size_t)b + 1] = g_local[3 * (size_t)b + 1];
             s_local[3 * (size_t)b + 2] = g_local[3 * (size_t)b + 2];
         }
-        for (uint32_t i = tid; i < M.n_link_slots; i += kHierCtaThreads) { s_ikR[i] = g_ikR[i]; s_preIK[i] = g_preIK[i]; }
-        for (uint32_t i = tid; i < M.n_morph_slots; i += kHierCtaThreads) { s_morphR[i] = g_morphR[i]; s_morphT[i] = g_morphT[i]; }
+        for (uint32_t i = tid; i < M.n_link_slots; i += nthreads) { s_ikR[i] = g_ikR[i]; s_preIK[i] = g_preIK[i]; }
+        for (uint32_t i = tid; i < M.n_morph_slots; i += nthreads) { s_morphR[i] = g_morphR[i]; s_morphT[i] = g_morphT[i]; }
     }
     __syncthreads();
 
     for (uint32_t w = wave_lo; w < wave_hi; ++w) {
         const uint32_t o0 = s_wave_begin[w], o1 = s_wave_begin[w + 1];
-        for (uint32_t o = o0 + tid; o < o1; o += kHierCtaThreads) {
+        for (uint32_t o = o0 + tid; o < o1; o += nthreads) {
             const uint32_t word = s_wave_ops[o];
             const uint32_t kind = word >> 28;
             const int32_t arg = (int32_t)(word & 0x0FFFFFFFu);
@@ -578,15 +578,15 @@ __global__ void __launch_bounds__(kHierCtaThreads) hierarchy_cta_kernel(DevModel
     }
 
     // ---- leave the state in global memory for the next segment / the download entry points
-    for (uint32_t b = tid; b < nb; b += kHierCtaThreads) {
+    for (uint32_t b = tid; b < nb; b += nthreads) {
         g_totR[b] = s_totR[b];
         g_totT[b] = s_totT[b];
         g_local[3 * (size_t)b] = s_local[3 * (size_t)b];
         g_local[3 * (size_t)b + 1] = s_local[3 * (size_t)b + 1];
         g_local[3 * (size_t)b + 2] = s_local[3 * (size_t)b + 2];
     }
-    for (uint32_t i = tid; i < M.n_link_slots; i += kHierCtaThreads) { g_ikR[i] = s_ikR[i]; g_preIK[i] = s_preIK[i]; }
-    for (uint32_t i = tid; i < M.n_morph_slots; i += kHierCtaThreads) { g_morphR[i] = s_morphR[i]; g_morphT[i] = s_morphT[i]; }
+    for (uint32_t i = tid; i < M.n_link_slots; i += nthreads) { g_ikR[i] = s_ikR[i]; g_preIK[i] = s_preIK[i]; }
+    for (uint32_t i = tid; i < M.n_morph_slots; i += nthreads) { g_morphR[i] = s_morphR[i]; g_morphT[i] = s_morphT[i]; }
 }
 
 // =================================================================================================
@@ -952,7 +952,9 @@ cudaError_t launch_hierarchy(cudaStream_t st, const DevModel& M, const DevFrames
     if (F.n_slots == 0) return cudaSuccess;
     const size_t cta_smem = hier_cta_smem_bytes(M.nb, M.n_link_slots, M.n_morph_slots, M.n_ops, M.n_waves);
     if (cta_smem <= kHierCtaSmemLimit) {
-        hierarchy_cta_kernel<<<F.n_slots, kHierCtaThreads, cta_smem, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u);
+        // small skeletons: narrower CTAs, so that more slots are resident per SM (a CCD IK solve is one thread)
+        const uint32_t threads = M.nb <= 512 ? 128u : kHierCtaThreads;
+        hierarchy_cta_kernel<<<F.n_slots, threads, cta_smem, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u);
         return cudaGetLastError();
     }
     const uint32_t blocks = (F.n_slots + kHierWarps - 1) / kHierWarps;

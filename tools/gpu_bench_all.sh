@@ -1,7 +1,7 @@
 #!/bin/bash
 # device-resident bench of every workload, one summary line each
 for w in C3 C4 C1 C2; do
-  timeout 300 python bench.py --workload $w --steps 10 --warmup 3 --no-cpu-baseline --no-e2e "$@" | python -c "
+  timeout 300 python bench.py --workload $w --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-also "$@" | python -c "
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):

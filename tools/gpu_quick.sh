@@ -1,7 +1,7 @@
 #!/bin/bash
 # quick GPU check: parity tests + short device-resident bench; prints a one-line summary
 timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e "$@" | python -c "
+timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-also "$@" | python -c "
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):

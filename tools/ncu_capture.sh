@@ -4,7 +4,7 @@
 set -u
 tag=$1; shift
 kre=$1; shift
-cmd="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e $*"
+cmd="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-also $*"
 mkdir -p gpurun_out
 $cmd > gpurun_out/${tag}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${tag}_launches.csv $cmd > gpurun_out/${tag}_ncu_list.log 2>&1

@@ -143,6 +143,32 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa(device_index: int):
+    """Pin this rank to the CPUs of its GPU's NUMA node before any pinned host memory is allocated, so that the
+    device->host copies of the e2e leg land in local memory (8 ranks on a 2-socket host otherwise share one UPI)."""
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(device_index)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        return None
+    return None
+
+
 def build_inputs(args):
     from simple_mmd_renderer_b200 import synth
     wl = args.workload
@@ -285,6 +311,7 @@ def run_mmdgpu(args):
         if local == 0:
             lib.build_library()
     torch.cuda.set_device(local)
+    numa_node = bind_to_gpu_numa(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
@@ -382,7 +409,8 @@ def run_mmdgpu(args):
         e2e = {"value": total_slots * nv * e2e_steps / (float(ems.item()) * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                "ms_per_step": float(ems.item()) / e2e_steps,
-               "note": "update_range + download of every slot's deformed buffer to pinned host memory, per GPU"}
+               "note": "update_range + download of every slot's deformed buffer to pinned host memory, per GPU",
+               "numa_node_of_rank0": numa_node}
 
     clocks = sampler.stop() if sampler else None
 

@@ -783,7 +783,7 @@ __global__ void __launch_bounds__(kSkinThreads, 2) skin_kernel(DevModel M, DevFr
         const uint4 I = __ldg(reinterpret_cast<const uint4*>(M.ids + v0 + j));
         ilo[j] = I.x; ihi[j] = I.y; ilo[j + 1] = I.z; ihi[j + 1] = I.w;
         uu[j] = vv[j] = uu[j + 1] = vv[j + 1] = 0.f;
-        if (LAYOUT == MMDGPU_LAYOUT_INTERLEAVED_SOKOL32 || EXT) {
+        if (EXT) {  // extensions morph the UV every slot; the compat sokol32 path re-reads the static UV at staging time
             const float4 UV = __ldg(reinterpret_cast<const float4*>(M.uv + v0 + j));
             uu[j] = UV.x; vv[j] = UV.y; uu[j + 1] = UV.z; vv[j + 1] = UV.w;
         }
@@ -899,6 +899,10 @@ __global__ void __launch_bounds__(kSkinThreads, 2) skin_kernel(DevModel M, DevFr
                 // main.cpp:838-859: Vertex{pos*0.1f, normal, uv}
                 const float mmd_to_meter = 0.1f;
                 float4* sv = reinterpret_cast<float4*>(stage) + orig[j] * 2u;
+                if (!EXT) {  // static UV passthrough (main.cpp:840,855-856): an L1-resident 8-byte load, no registers held
+                    const float2 t = __ldg(M.uv + v0 + j);
+                    mu = t.x; mv = t.y;
+                }
                 sv[0] = make_float4(op[0] * mmd_to_meter, op[1] * mmd_to_meter, op[2] * mmd_to_meter, on[0]);
                 sv[1] = make_float4(on[1], on[2], mu, mv);
             }

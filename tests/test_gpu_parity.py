@@ -324,3 +324,72 @@ def test_cxx_shim_runs_the_libmmd_frame_loop(ctx, tmp_path):
     ref = _oracle(model, motion).run_frame(33)
     assert_bitwise(got[0], ref["pos"], "C++ shim coordinates")
     assert_bitwise(got[1], ref["nrm"], "C++ shim normals")
+
+
+def test_full_size_bake_batch_equals_single_frame_runs(ctx):
+    """BASELINE configs[4] pattern at full size (1 M vertices, 128-frame window): every slot of the batched launch
+    is bit-identical to evaluating that frame alone (frames are pure functions of their index), and one slot is
+    checked against the CPU oracle."""
+    import hashlib
+    cfg, model, motion = synth_case("C3")
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    big = Frames(m, 1, 128)
+    big.update_range(a, [40], 1)
+    one = Frames(m, 1, 1)
+    for k in (0, 63, 64, 127):
+        one.update(a, [40 + k])
+        for sid in (capi.STREAM_POSITION, capi.STREAM_NORMAL):
+            x, y = big.download(k, sid), one.download(0, sid)
+            assert hashlib.sha256(x.tobytes()).digest() == hashlib.sha256(y.tobytes()).digest(), f"slot {k} stream {sid}"
+    ref = _oracle(model, motion).run_frame(40 + 127)
+    assert_bitwise(big.download(127, capi.STREAM_POSITION), ref["pos"], "slot 127 vs oracle")
+
+
+def test_full_size_crowd_equals_single_instance_runs(ctx):
+    """BASELINE configs[3]: 512 instances of the 50 k-vertex model with independent clips; sampled instances are
+    bit-identical to a one-instance run of the same clip and frame and to the CPU oracle."""
+    from simple_mmd_renderer_b200 import synth
+    cfg, model, _ = synth_case("C1")
+    m = Model(ctx, model)
+    n = 512
+    sample = (0, 1, 255, 300, 511)
+    clips = {i: synth.make_motion(cfg, model, instance=i) for i in sample}
+    filler = Motion(m, clips[0])
+    anims = [Motion(m, clips[i]) if i in clips else filler for i in range(n)]
+    first = (np.arange(n, dtype=np.uint32) * 7) % 300
+    crowd = Frames(m, n, 1)
+    crowd.update_range(anims, first, 1)
+    one = Frames(m, 1, 1)
+    for i in sample:
+        one.update(anims[i], [int(first[i])])
+        assert_bitwise(crowd.download(i, capi.STREAM_POSITION), one.download(0, capi.STREAM_POSITION), f"instance {i} pos")
+        assert_bitwise(crowd.download(i, capi.STREAM_NORMAL), one.download(0, capi.STREAM_NORMAL), f"instance {i} nrm")
+    ref = _oracle(model, clips[300]).run_frame(int(first[300]))
+    assert_bitwise(crowd.download(300, capi.STREAM_POSITION), ref["pos"], "instance 300 vs oracle")
+
+
+def test_back_to_back_updates_are_ordered(ctx):
+    """The fused update pipelines sampling + hierarchy of call n+1 behind the skinning of call n on a second
+    stream (double-buffered palette): results of consecutive calls must not mix."""
+    cfg, model, motion = synth_case("small")
+    orc = _oracle(model, motion)
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    fr = Frames(m, 1, 2)
+    seq = [(3, 90), (44, 45), (119, 0), (7, 8), (60, 61)]
+    for f0, f1 in seq:
+        fr.update(a, [f0, f1])            # no synchronisation between calls
+    for k, f in enumerate(seq[-1]):
+        ref = orc.run_frame(f)
+        assert_bitwise(fr.download(k, capi.STREAM_POSITION), ref["pos"], f"last call slot {k}")
+        assert_bitwise(fr.bone_matrices(k), ref["skin"], f"last call slot {k} skin")
+    # a step-wise call after fused calls sees the fused result and may override it
+    fr.reset_posing()
+    fr.seek_frame(a, [10, 11])
+    fr.pre_physics_posing()
+    fr.post_physics_posing()
+    fr.deform()
+    assert_bitwise(fr.download(1, capi.STREAM_POSITION), orc.run_frame(11)["pos"], "step-wise after fused")
+    fr.update(a, [100, 101])
+    assert_bitwise(fr.download(0, capi.STREAM_POSITION), orc.run_frame(100)["pos"], "fused after step-wise")

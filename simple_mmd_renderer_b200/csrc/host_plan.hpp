@@ -131,7 +131,8 @@ struct Plan {
     std::vector<int32_t> op_arg_i32, phase_split_i32;
 };
 
-constexpr uint32_t kTileVerts = 1024;      // vertices per tile = one CTA iteration
+constexpr uint32_t kTileVerts = 512;       // vertices per tile = one CTA iteration
+constexpr uint32_t kSlotGroup = 4;         // slots (frames / instances) a skinning CTA evaluates together
 constexpr uint32_t kVertsPerThread = 4;    // consecutive storage positions one thread owns ("steps" of a warp)
 constexpr uint32_t kSkinThreads = kTileVerts / kVertsPerThread;
 constexpr uint32_t kSkinWarps = kSkinThreads / 32;

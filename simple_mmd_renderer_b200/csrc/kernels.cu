@@ -372,7 +372,9 @@ __global__ void __launch_bounds__(32 * kHierWarps) hierarchy_kernel(DevModel M, 
         // ---- morph application-slot rates: Poser::UpdateMorphTransform's skip test and group recursion
         //      (poser_impl.inl:329-339), evaluated breadth-first over the static DFS tree.
         const float* rate = F.rate + (size_t)slot * M.nm;
-        float* nrate = F.node_rate + (size_t)slot * M.n_nodes_pad;
+        // application-slot rates are stored [slot / 4][node][slot % 4]: the skinning kernel evaluates four slots
+        // together and reads one float4 per morph entry
+        float* nrate = F.node_rate + (size_t)(slot >> 2) * M.n_nodes_pad * kSlotGroup + (slot & 3u);
         for (uint32_t dpt = 0; dpt < M.n_depths; ++dpt) {
             const int32_t b0 = M.depth_begin[dpt], b1 = M.depth_begin[dpt + 1];
             for (int32_t i = b0 + (int32_t)lane; i < b1; i += 32) {
@@ -382,12 +384,12 @@ __global__ void __launch_bounds__(32 * kHierWarps) hierarchy_kernel(DevModel M, 
                 bool active = true;
                 if (par < 0) r = rate[M.node_morph[n]];
                 else {
-                    const float pr = nrate[par];
+                    const float pr = nrate[kSlotGroup * par];
                     active = pr != 0.0f;            // a skipped group skips its whole subtree
                     r = M.node_mult[n] * pr;        // data.GetMorphRate()*rate
                 }
                 if (!active || (double)r < kEpsD) r = 0.0f;
-                nrate[n] = r;
+                nrate[kSlotGroup * n] = r;
             }
             __syncwarp();
         }
@@ -409,7 +411,7 @@ __global__ void __launch_bounds__(32 * kHierWarps) hierarchy_kernel(DevModel M, 
             float tx = 0.f, ty = 0.f, tz = 0.f;
             for (int32_t e = M.bone_morph_row[i]; e < M.bone_morph_row[i + 1]; ++e) {
                 const BoneMorphEntry E = M.bone_morph_entries[e];
-                const float r = nrate[E.node];
+                const float r = nrate[kSlotGroup * E.node];
                 if (r != 0.0f) {
                     tx = tx + E.translation[0] * r;
                     ty = ty + E.translation[1] * r;
@@ -501,7 +503,9 @@ __global__ void __launch_bounds__(kHierCtaThreads) hierarchy_cta_kernel(DevModel
     if (prologue) {
         // ---- morph application-slot rates (poser_impl.inl:329-339), breadth-first over the static DFS tree
         const float* rate = F.rate + (size_t)slot * M.nm;
-        float* nrate = F.node_rate + (size_t)slot * M.n_nodes_pad;
+        // application-slot rates are stored [slot / 4][node][slot % 4]: the skinning kernel evaluates four slots
+        // together and reads one float4 per morph entry
+        float* nrate = F.node_rate + (size_t)(slot >> 2) * M.n_nodes_pad * kSlotGroup + (slot & 3u);
         for (uint32_t dpt = 0; dpt < M.n_depths; ++dpt) {
             const int32_t b0 = M.depth_begin[dpt], b1 = M.depth_begin[dpt + 1];
             for (int32_t i = b0 + (int32_t)tid; i < b1; i += nthreads) {
@@ -511,12 +515,12 @@ __global__ void __launch_bounds__(kHierCtaThreads) hierarchy_cta_kernel(DevModel
                 bool active = true;
                 if (par < 0) r = rate[M.node_morph[n]];
                 else {
-                    const float pr = nrate[par];
+                    const float pr = nrate[kSlotGroup * par];
                     active = pr != 0.0f;
                     r = M.node_mult[n] * pr;
                 }
                 if (!active || (double)r < kEpsD) r = 0.0f;
-                nrate[n] = r;
+                nrate[kSlotGroup * n] = r;
             }
             if (dpt + 1 < M.n_depths) { __threadfence_block(); __syncthreads(); }
         }
@@ -537,7 +541,7 @@ __global__ void __launch_bounds__(kHierCtaThreads) hierarchy_cta_kernel(DevModel
             float tx = 0.f, ty = 0.f, tz = 0.f;
             for (int32_t e = M.bone_morph_row[i]; e < M.bone_morph_row[i + 1]; ++e) {
                 const BoneMorphEntry E = M.bone_morph_entries[e];
-                const float r = nrate[E.node];
+                const float r = nrate[kSlotGroup * E.node];
                 if (r != 0.0f) {
                     tx = tx + E.translation[0] * r;
                     ty = ty + E.translation[1] * r;
@@ -736,18 +740,21 @@ __host__ __device__ inline uint32_t skin_pal_bytes(uint32_t max_tile_bones, bool
 
 constexpr uint32_t kPalPrefetch = 2;  // palette float4 per thread held in registers across the compute phase
 constexpr int V = (int)kVertsPerThread;
+constexpr int G = (int)kSlotGroup;    // slots one CTA evaluates together
 
+// shared memory carve-up (bytes): [stage: G tiles][palette 0: G slots][palette 1][rates 0: n_nodes_pad float4][rates 1]
 template <int LAYOUT, bool EXT>
-__global__ void __launch_bounds__(kSkinThreads, 2) skin_kernel(DevModel M, DevFrames F, uint32_t chunk, uint32_t n_chunks) {
+__global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevModel M, DevFrames F, uint32_t chunk, uint32_t n_chunks) {
     constexpr uint32_t PS = EXT ? 5u : 3u;  // float4 per staged bone
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t stage_bytes = skin_stage_bytes(LAYOUT, EXT), pal_bytes = skin_pal_bytes(M.max_tile_bones, EXT);
+    const uint32_t pal4 = pal_bytes >> 4;  // float4 per staged slot palette
     unsigned char* stage_base = smem_raw;
-    float4* pal_base = reinterpret_cast<float4*>(smem_raw + 2 * stage_bytes);
-    float* rate_base = reinterpret_cast<float*>(smem_raw + 2 * stage_bytes + 2 * pal_bytes);
+    float4* pal_base = reinterpret_cast<float4*>(smem_raw + G * stage_bytes);
+    float4* rate_base = pal_base + 2u * G * pal4;
 
     const uint32_t tile = blockIdx.x / n_chunks, ck = blockIdx.x - tile * n_chunks;
-    const uint32_t s0 = ck * chunk;
+    const uint32_t s0 = ck * chunk;                      // chunk is a multiple of G: groups never straddle work items
     const uint32_t s1 = min(F.n_slots, s0 + chunk);
     if (s0 >= s1) return;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -798,26 +805,6 @@ __global__ void __launch_bounds__(kSkinThreads, 2) skin_kernel(DevModel M, DevFr
         ebase[j] = h.x + lane;
         erounds[j] = h.y;
     }
-    // tile-local palette: float4 i of the staged palette comes from float4 psrc(i) of the slot's global palette
-    const uint32_t tb0 = __ldg(M.tile_bone_begin + tile);
-    const uint32_t npal4 = (__ldg(M.tile_bone_begin + tile + 1) - tb0) * PS;
-    const uint32_t nrate4 = M.n_nodes_pad >> 2;
-    // float4 i of the staged palette = component i % PS of tile bone i / PS: a matrix column (components 0..2) or,
-    // with extensions, the rotation quaternion / dual part (components 3, 4; flagged by bit 31)
-    auto pal_source = [&](uint32_t i) -> uint32_t {
-        const uint32_t bone = (uint32_t)__ldg(M.tile_bones + tb0 + i / PS), comp = i % PS;
-        return comp < 3u ? bone * 3u + comp : (0x80000000u | (bone * 2u + comp - 3u));
-    };
-    auto pal_fetch = [&](uint32_t slot, uint32_t src) -> float4 {
-        if (EXT && (src & 0x80000000u)) return __ldg(F.pal_ext + (size_t)slot * M.nb * 2 + (src & 0x7FFFFFFFu));
-        return __ldg(F.palette + (size_t)slot * M.nb * 3 + src);
-    };
-    uint32_t psrc[kPalPrefetch];
-#pragma unroll
-    for (uint32_t q = 0; q < kPalPrefetch; ++q) {
-        const uint32_t i = tid + q * kSkinThreads;
-        psrc[q] = (i < npal4) ? pal_source(i) : 0xFFFFFFFFu;
-    }
     uint32_t uvbase[V], uvrounds[V];
     if (EXT) {
 #pragma unroll
@@ -827,110 +814,159 @@ __global__ void __launch_bounds__(kSkinThreads, 2) skin_kernel(DevModel M, DevFr
             uvrounds[j] = h.y;
         }
     }
+    // tile-local palette of one slot group: item i = (slot f = i / npal4, float4 q = i % npal4); float4 q is component
+    // q % PS of tile bone q / PS: a matrix column (0..2) or, with extensions, the rotation quaternion / dual part
+    const uint32_t tb0 = __ldg(M.tile_bone_begin + tile);
+    const uint32_t npal4 = (__ldg(M.tile_bone_begin + tile + 1) - tb0) * PS;
+    const uint32_t n_items = npal4 * G;
+    const uint32_t npad = M.n_nodes_pad;               // float4 per rate block (one float4 = the G slots of a node)
+    auto item_source = [&](uint32_t i) -> uint32_t {   // bits 31:30 = slot within the group, 29 = extension array
+        const uint32_t f = i / npal4, q = i - f * npal4;
+        const uint32_t bone = (uint32_t)__ldg(M.tile_bones + tb0 + q / PS), comp = q % PS;
+        return (f << 30) | (comp < 3u ? bone * 3u + comp : (0x20000000u | (bone * 2u + comp - 3u)));
+    };
+    auto item_dest = [&](uint32_t i) -> uint32_t { const uint32_t f = i / npal4; return f * pal4 + (i - f * npal4); };
+    auto item_fetch = [&](uint32_t group_slot0, uint32_t src) -> float4 {
+        const uint32_t slot = min(group_slot0 + (src >> 30), F.n_slots - 1u);  // a partial last group re-reads its last slot
+        const uint32_t idx = src & 0x1FFFFFFFu;
+        if (EXT && (src & 0x20000000u)) return __ldg(F.pal_ext + (size_t)slot * M.nb * 2 + idx);
+        return __ldg(F.palette + (size_t)slot * M.nb * 3 + idx);
+    };
+    uint32_t psrc[kPalPrefetch], pdst[kPalPrefetch];
+#pragma unroll
+    for (uint32_t q = 0; q < kPalPrefetch; ++q) {
+        const uint32_t i = tid + q * kSkinThreads;
+        psrc[q] = (i < n_items) ? item_source(i) : 0xFFFFFFFFu;
+        pdst[q] = (i < n_items) ? item_dest(i) : 0u;
+    }
 
-    // ---- prologue: slot s0 straight into buffer 0
+    // ---- prologue: first group straight into buffer 0
     {
-        for (uint32_t i = tid; i < npal4; i += kSkinThreads) pal_base[i] = pal_fetch(s0, pal_source(i));
-        const float4* gr = reinterpret_cast<const float4*>(F.node_rate + (size_t)s0 * M.n_nodes_pad);
-        for (uint32_t i = tid; i < nrate4; i += kSkinThreads) reinterpret_cast<float4*>(rate_base)[i] = __ldg(gr + i);
+        for (uint32_t i = tid; i < n_items; i += kSkinThreads) pal_base[item_dest(i)] = item_fetch(s0, item_source(i));
+        const float4* gr = reinterpret_cast<const float4*>(F.node_rate) + (size_t)(s0 / G) * npad;
+        for (uint32_t i = tid; i < npad; i += kSkinThreads) rate_base[i] = __ldg(gr + i);
     }
     __syncthreads();
 
-    for (uint32_t s = s0; s < s1; ++s) {
-        const uint32_t b = (s - s0) & 1u;
-        const float4* __restrict__ pal = pal_base + (size_t)b * (pal_bytes >> 4);
-        const char* __restrict__ nrate = reinterpret_cast<const char*>(rate_base + (size_t)b * M.n_nodes_pad);
-        unsigned char* stage = stage_base + (size_t)b * stage_bytes;
-        const bool has_next = s + 1 < s1;
-        // ---- next slot's palette subset and rates: loads issued now, consumed after the compute phase
+    uint32_t b = 0;
+    for (uint32_t g0 = s0; g0 < s1; g0 += G, b ^= 1u) {
+        const float4* __restrict__ pal = pal_base + (size_t)b * G * pal4;
+        const char* __restrict__ nrate = reinterpret_cast<const char*>(rate_base + (size_t)b * npad);
+        const uint32_t n_live = min((uint32_t)G, s1 - g0);   // slots of this group that exist (CTA-uniform)
+        const bool has_next = g0 + G < s1;
+        // ---- next group's palettes and rates: loads issued now, consumed after the compute phase
         float4 pf[kPalPrefetch], rf = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4* gr = reinterpret_cast<const float4*>(F.node_rate + (size_t)(s + 1) * M.n_nodes_pad);
+        const float4* gr = reinterpret_cast<const float4*>(F.node_rate) + (size_t)(g0 / G + 1) * npad;
         if (has_next) {
 #pragma unroll
             for (uint32_t q = 0; q < kPalPrefetch; ++q)
-                if (psrc[q] != 0xFFFFFFFFu) pf[q] = pal_fetch(s + 1, psrc[q]);
-            if (tid < nrate4) rf = __ldg(gr + tid);
+                if (psrc[q] != 0xFFFFFFFFu) pf[q] = item_fetch(g0 + G, psrc[q]);
+            if (tid < npad) rf = __ldg(gr + tid);
         }
-        // ---- compute: step j is (nearly always) one skinning type across the warp
+        // ---- per storage position: morph gather for the G slots at once, then G skinnings.  vertex_images_[i]
+        //      accumulates in application order: img = img + off*rate (poser_impl.inl:340-346).  ent.w = byte
+        //      offset of the entry's float4 of rates (one per slot of the group).  A skipped slot has rate +0 and
+        //      is applied unconditionally: the accumulator starts at +0 and can never become -0, so adding
+        //      (finite offset) * 0 = +-0 leaves it bit-identical to libmmd's skip (the host rejects non-finite offsets).
+        //      Step j is (nearly always) one skinning type across the warp.
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-            // vertex_images_[i] accumulated in application order: img = img + off*rate (poser_impl.inl:340-346)
-            float ix = 0.f, iy = 0.f, iz = 0.f;
+            float ix[G], iy[G], iz[G];
+#pragma unroll
+            for (int f = 0; f < G; ++f) ix[f] = iy[f] = iz[f] = 0.f;
             const float4* __restrict__ e = M.ell_ent + ebase[j];
             for (uint32_t k = 0; k < erounds[j]; ++k) {
                 const float4 ent = __ldg(e + (size_t)k * 32);
-                // ent.w = byte offset of the entry's application slot in the rate table.  A skipped slot has
-                // rate +0 and is applied unconditionally: the accumulator starts at +0 and can never become -0,
-                // so adding (finite offset) * 0 = +-0 leaves it bit-identical to libmmd's skip (the host rejects
-                // non-finite offsets).
-                const float r = *reinterpret_cast<const float*>(nrate + __float_as_uint(ent.w));
-                ix = ix + ent.x * r;
-                iy = iy + ent.y * r;
-                iz = iz + ent.z * r;
+                const float4 r4 = *reinterpret_cast<const float4*>(nrate + __float_as_uint(ent.w));
+                const float r[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                for (int f = 0; f < G; ++f) {
+                    ix[f] = ix[f] + ent.x * r[f];
+                    iy[f] = iy[f] + ent.y * r[f];
+                    iz[f] = iz[f] + ent.z * r[f];
+                }
             }
-            float op[3], on[3];
+            if (j == 0) {
+                // the staging tiles are single-buffered: the previous group's bulk copies must have read them
+                if (tid == 0) bulk_wait_read_all();
+                __syncthreads();
+            }
             const uint32_t type = (ilo[j] >> 13) & 7u;
-            // coordinate + vertex_image (poser_impl.inl:407)
-            if (EXT && type == kDevSdef)
-                skin_sdef(pal, ilo[j] & 0x1FFFu, ilo[j] >> 16, wv[j].x, M.sdef + (size_t)(v0 + j) * 3, px[j] + ix, py[j] + iy,
-                          pz[j] + iz, nx[j], ny[j], nz[j], op, on);
-            else if (EXT && type == kDevQdef)
-                skin_qdef(pal, ilo[j], ihi[j], wv[j], px[j] + ix, py[j] + iy, pz[j] + iz, nx[j], ny[j], nz[j], op, on);
-            else
-                skin_vertex<(int)PS>(pal, ilo[j], ihi[j], wv[j], px[j] + ix, py[j] + iy, pz[j] + iz, nx[j], ny[j], nz[j], op, on);
-            float mu = uu[j], mv = vv[j];
-            if (EXT) {
-                // applied UV morphs: uv = uv + offset.xy * rate, application order
-                const float4* __restrict__ ue = M.uv_ell_ent + uvbase[j];
-                for (uint32_t k = 0; k < uvrounds[j]; ++k) {
-                    const float4 ent = __ldg(ue + (size_t)k * 32);
-                    const float r = *reinterpret_cast<const float*>(nrate + __float_as_uint(ent.z));
-                    mu = mu + ent.x * r;
-                    mv = mv + ent.y * r;
-                }
+            float su = uu[j], sv_ = vv[j];
+            if (LAYOUT == MMDGPU_LAYOUT_INTERLEAVED_SOKOL32 && !EXT) {
+                // static UV passthrough (main.cpp:840,855-856): an L1-resident 8-byte load, no registers held across slots
+                const float2 t = __ldg(M.uv + v0 + j);
+                su = t.x; sv_ = t.y;
             }
-            if (LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) {
-                float* sp = reinterpret_cast<float*>(stage) + orig[j] * 3u;
-                float* sn = reinterpret_cast<float*>(stage + kTileVerts * 12u) + orig[j] * 3u;
-                sp[0] = op[0]; sp[1] = op[1]; sp[2] = op[2];
-                sn[0] = on[0]; sn[1] = on[1]; sn[2] = on[2];
-                if (EXT) reinterpret_cast<float2*>(stage + kTileVerts * 24u)[orig[j]] = make_float2(mu, mv);
-            } else {
-                // main.cpp:838-859: Vertex{pos*0.1f, normal, uv}
-                const float mmd_to_meter = 0.1f;
-                float4* sv = reinterpret_cast<float4*>(stage) + orig[j] * 2u;
-                if (!EXT) {  // static UV passthrough (main.cpp:840,855-856): an L1-resident 8-byte load, no registers held
-                    const float2 t = __ldg(M.uv + v0 + j);
-                    mu = t.x; mv = t.y;
+#pragma unroll
+            for (int f = 0; f < G; ++f) {
+                // slots past the end of a partial last group are computed on the clamped palette and not stored
+                const bool live = (uint32_t)f < n_live;
+                const float4* __restrict__ palf = pal + (size_t)f * pal4;
+                unsigned char* stage = stage_base + (size_t)f * stage_bytes;
+                float op[3], on[3];
+                // coordinate + vertex_image (poser_impl.inl:407)
+                const float qx = px[j] + ix[f], qy = py[j] + iy[f], qz = pz[j] + iz[f];
+                if (EXT && type == kDevSdef)
+                    skin_sdef(palf, ilo[j] & 0x1FFFu, ilo[j] >> 16, wv[j].x, M.sdef + (size_t)(v0 + j) * 3, qx, qy, qz, nx[j], ny[j],
+                              nz[j], op, on);
+                else if (EXT && type == kDevQdef)
+                    skin_qdef(palf, ilo[j], ihi[j], wv[j], qx, qy, qz, nx[j], ny[j], nz[j], op, on);
+                else
+                    skin_vertex<(int)PS>(palf, ilo[j], ihi[j], wv[j], qx, qy, qz, nx[j], ny[j], nz[j], op, on);
+                float mu = su, mv = sv_;
+                if (EXT) {
+                    // applied UV morphs: uv = uv + offset.xy * rate, application order
+                    const float4* __restrict__ ue = M.uv_ell_ent + uvbase[j];
+                    for (uint32_t k = 0; k < uvrounds[j]; ++k) {
+                        const float4 ent = __ldg(ue + (size_t)k * 32);
+                        const float r = *reinterpret_cast<const float*>(nrate + __float_as_uint(ent.z) + 4u * f);
+                        mu = mu + ent.x * r;
+                        mv = mv + ent.y * r;
+                    }
                 }
-                sv[0] = make_float4(op[0] * mmd_to_meter, op[1] * mmd_to_meter, op[2] * mmd_to_meter, on[0]);
-                sv[1] = make_float4(on[1], on[2], mu, mv);
+                if (!live) continue;
+                if (LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) {
+                    float* sp = reinterpret_cast<float*>(stage) + orig[j] * 3u;
+                    float* sn = reinterpret_cast<float*>(stage + kTileVerts * 12u) + orig[j] * 3u;
+                    sp[0] = op[0]; sp[1] = op[1]; sp[2] = op[2];
+                    sn[0] = on[0]; sn[1] = on[1]; sn[2] = on[2];
+                    if (EXT) reinterpret_cast<float2*>(stage + kTileVerts * 24u)[orig[j]] = make_float2(mu, mv);
+                } else {
+                    // main.cpp:838-859: Vertex{pos*0.1f, normal, uv}
+                    const float mmd_to_meter = 0.1f;
+                    float4* sv = reinterpret_cast<float4*>(stage) + orig[j] * 2u;
+                    sv[0] = make_float4(op[0] * mmd_to_meter, op[1] * mmd_to_meter, op[2] * mmd_to_meter, on[0]);
+                    sv[1] = make_float4(on[1], on[2], mu, mv);
+                }
             }
         }
-        // ---- publish the next slot's staging data into the other buffer
+        // ---- publish the next group's palettes / rates into the other buffer
         if (has_next) {
-            float4* npal = pal_base + (size_t)(b ^ 1u) * (pal_bytes >> 4);
-            float4* nrt = reinterpret_cast<float4*>(rate_base + (size_t)(b ^ 1u) * M.n_nodes_pad);
+            float4* npal = pal_base + (size_t)(b ^ 1u) * G * pal4;
+            float4* nrt = rate_base + (size_t)(b ^ 1u) * npad;
 #pragma unroll
             for (uint32_t q = 0; q < kPalPrefetch; ++q)
-                if (psrc[q] != 0xFFFFFFFFu) npal[tid + q * kSkinThreads] = pf[q];
-            for (uint32_t i = tid + kPalPrefetch * kSkinThreads; i < npal4; i += kSkinThreads)
-                npal[i] = pal_fetch(s + 1, pal_source(i));
-            if (tid < nrate4) nrt[tid] = rf;
-            for (uint32_t i = tid + kSkinThreads; i < nrate4; i += kSkinThreads) nrt[i] = __ldg(gr + i);
+                if (psrc[q] != 0xFFFFFFFFu) npal[pdst[q]] = pf[q];
+            for (uint32_t i = tid + kPalPrefetch * kSkinThreads; i < n_items; i += kSkinThreads)
+                npal[item_dest(i)] = item_fetch(g0 + G, item_source(i));
+            if (tid < npad) nrt[tid] = rf;
+            for (uint32_t i = tid + kSkinThreads; i < npad; i += kSkinThreads) nrt[i] = __ldg(gr + i);
         }
-        // ---- hand the staged tile to the bulk-copy engine
-        fence_proxy_async_smem();                 // my staging writes become visible to the async proxy
-        if (tid == 0) bulk_wait_read_all();       // the previous slot's copy has finished reading the other buffer
+        // ---- hand the staged tiles to the bulk-copy engine
+        fence_proxy_async_smem();  // my staging writes become visible to the async proxy
         __syncthreads();
         if (tid == 0) {
-            const size_t vbase = (size_t)s * M.nv_pad + (size_t)tile * kTileVerts;
-            if (LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) {
-                bulk_s2g(F.out_pos + vbase * 3, stage, kTileVerts * 12u);
-                bulk_s2g(F.out_nrm + vbase * 3, stage + kTileVerts * 12u, kTileVerts * 12u);
-                if (EXT) bulk_s2g(F.out_uv + vbase, stage + kTileVerts * 24u, kTileVerts * 8u);
-            } else {
-                bulk_s2g(F.out_inter + vbase * 2, stage, kTileVerts * 32u);
+            for (uint32_t f = 0; f < n_live; ++f) {
+                unsigned char* stage = stage_base + (size_t)f * stage_bytes;
+                const size_t vbase = (size_t)(g0 + f) * M.nv_pad + (size_t)tile * kTileVerts;
+                if (LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) {
+                    bulk_s2g(F.out_pos + vbase * 3, stage, kTileVerts * 12u);
+                    bulk_s2g(F.out_nrm + vbase * 3, stage + kTileVerts * 12u, kTileVerts * 12u);
+                    if (EXT) bulk_s2g(F.out_uv + vbase, stage + kTileVerts * 24u, kTileVerts * 8u);
+                } else {
+                    bulk_s2g(F.out_inter + vbase * 2, stage, kTileVerts * 32u);
+                }
             }
             bulk_commit();
         }
@@ -968,7 +1004,8 @@ cudaError_t launch_hierarchy(cudaStream_t st, const DevModel& M, const DevFrames
 
 size_t skin_smem_bytes(const DevModel& M, int layout) {
     const bool ext = M.extensions != 0;
-    return 2 * (size_t)skin_stage_bytes(layout, ext) + 2 * (size_t)skin_pal_bytes(M.max_tile_bones, ext) + 2 * (size_t)M.n_nodes_pad * 4;
+    return (size_t)kSlotGroup * skin_stage_bytes(layout, ext) + 2 * (size_t)kSlotGroup * skin_pal_bytes(M.max_tile_bones, ext) +
+           2 * (size_t)M.n_nodes_pad * 16;
 }
 
 template <int LAYOUT, bool EXT>
@@ -996,7 +1033,7 @@ cudaError_t prepare_skin_kernels(const DevModel& M) {
 
 cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, int layout, uint32_t slots_per_cta) {
     if (F.n_slots == 0 || M.n_tiles == 0) return cudaSuccess;
-    if (slots_per_cta == 0) slots_per_cta = 1;
+    slots_per_cta = (std::max<uint32_t>(slots_per_cta, 1u) + kSlotGroup - 1) / kSlotGroup * kSlotGroup;  // whole slot groups
     const uint32_t n_chunks = (F.n_slots + slots_per_cta - 1) / slots_per_cta;
     const uint32_t grid = M.n_tiles * n_chunks;
     const size_t smem = skin_smem_bytes(M, layout);

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -169,7 +170,11 @@ uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
 // once per run); shorter runs give more work items to balance over the SMs.
 uint32_t choose_slots_per_cta(uint32_t tiles, uint32_t n_slots, int sm_count) {
     if (tiles == 0 || n_slots == 0) return 1;
-    const uint64_t target_items = uint64_t(sm_count > 0 ? sm_count : 148) * 2 * 8;  // 8 waves of 2 CTAs per SM
+    if (const char* env = std::getenv("MMDGPU_SLOTS_PER_CTA")) {  // tuning knob for experiments
+        const long v = std::strtol(env, nullptr, 10);
+        if (v > 0) return uint32_t(std::min<long>(v, n_slots));
+    }
+    const uint64_t target_items = uint64_t(sm_count > 0 ? sm_count : 148) * 3 * 8;  // 8 waves of 3 CTAs per SM
     uint64_t n_chunks = (target_items + tiles - 1) / tiles;
     n_chunks = std::min<uint64_t>(std::max<uint64_t>(n_chunks, 1), n_slots);
     return uint32_t((n_slots + n_chunks - 1) / n_chunks);
@@ -224,7 +229,7 @@ mmdgpu_status upload_model(mmdgpu_model* m) {
     std::vector<float4> ent(p.ell_node.size());
     for (size_t e = 0; e < ent.size(); ++e) {
         float slot_bits;
-        const uint32_t node = p.ell_node[e] * 4u;  // byte offset into the slot's rate table
+        const uint32_t node = p.ell_node[e] * 16u;  // byte offset of the node's float4 (one rate per slot of a group)
         std::memcpy(&slot_bits, &node, 4);
         ent[e] = make_float4(p.ell_offset[3 * e], p.ell_offset[3 * e + 1], p.ell_offset[3 * e + 2], slot_bits);
     }
@@ -244,7 +249,7 @@ mmdgpu_status upload_model(mmdgpu_model* m) {
         std::vector<float4> uent(p.uv_ell_node.size());
         for (size_t e = 0; e < uent.size(); ++e) {
             float slot_bits;
-            const uint32_t node = p.uv_ell_node[e] * 4u;
+            const uint32_t node = p.uv_ell_node[e] * 16u;
             std::memcpy(&slot_bits, &node, 4);
             uent[e] = make_float4(p.uv_ell_offset[4 * e], p.uv_ell_offset[4 * e + 1], slot_bits, 0.f);
         }
@@ -875,7 +880,9 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_create(mmdgpu_context_t ctx, mmdgpu_model
     CU(ctx, dalloc(f->mem, &F.poseR, ns * M.nb, false, st));
     CU(ctx, dalloc(f->mem, &F.poseT, ns * M.nb, false, st));
     CU(ctx, dalloc(f->mem, &F.rate, ns * M.nm, true, st));
-    for (int i = 0; i < 2; ++i) CU(ctx, dalloc(f->mem, &f->rate_buf[i], ns * M.n_nodes_pad, true, st));
+    // application-slot rates, [slot / 4][node][slot % 4] (kernels.cu)
+    for (int i = 0; i < 2; ++i)
+        CU(ctx, dalloc(f->mem, &f->rate_buf[i], (ns + kSlotGroup - 1) / kSlotGroup * kSlotGroup * M.n_nodes_pad, true, st));
     CU(ctx, dalloc(f->mem, &F.totR, ns * M.nb, true, st));
     CU(ctx, dalloc(f->mem, &F.totT, ns * M.nb, true, st));
     CU(ctx, dalloc(f->mem, &F.local, ns * M.nb * 12, true, st));

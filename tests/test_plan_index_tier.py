@@ -219,18 +219,21 @@ def test_waves_are_shallow_on_the_headline_model():
 
 @pytest.mark.parametrize("name", ["tiny", "tiny_full", "small", "C2"])
 def test_tile_layout_is_a_faithful_permutation(name):
-    """Device vertex layout: every 1024-vertex tile is stored in a tile-local order; the permutation, the
+    """Device vertex layout: every TILE-vertex tile is stored in a tile-local order; the permutation, the
     tile-local bone lists and the sliced-ELL morph table must reproduce the PMX-order arrays exactly."""
     cfg, model, _ = synth_case(name)
     plan = plan_arrays(model)
+    TILE, V = 512, 4            # kTileVerts, kVertsPerThread (host_plan.hpp)
+    WARPS = TILE // V // 32     # warps per CTA; group g = step j * WARPS + warp w
+    GROUPS = TILE // 32
     nv = int(model["n_vertices"])
     orig = plan[capi.PLAN_TILE_ORIG].astype(np.int64)
     nvp = orig.size
-    assert nvp % 1024 == 0 and nvp >= nv and nvp - nv < 1024
-    n_tiles = nvp // 1024
-    tiles = orig.reshape(n_tiles, 1024)
-    assert (np.sort(tiles, axis=1) == np.arange(1024)).all(), "tile_orig must be a permutation of each tile"
-    src = (np.arange(nvp) // 1024) * 1024 + orig           # PMX vertex of every storage position
+    assert nvp % TILE == 0 and nvp >= nv and nvp - nv < TILE
+    n_tiles = nvp // TILE
+    tiles = orig.reshape(n_tiles, TILE)
+    assert (np.sort(tiles, axis=1) == np.arange(TILE)).all(), "tile_orig must be a permutation of each tile"
+    src = (np.arange(nvp) // TILE) * TILE + orig           # PMX vertex of every storage position
     real = src < nv
     # device type per PMX vertex, derived independently from the Normalize output + Deform's Lerp shortcuts
     t = plan[capi.PLAN_SKIN_TYPE].astype(np.int64)
@@ -250,7 +253,7 @@ def test_tile_layout_is_a_faithful_permutation(name):
     for ti in range(n_tiles):
         bones = tb[tb_begin[ti]:tb_begin[ti + 1]]
         assert (np.diff(bones) > 0).all()
-        sl = slice(ti * 1024, (ti + 1) * 1024)
+        sl = slice(ti * TILE, (ti + 1) * TILE)
         for k in range(4):
             use = real[sl] & (n_ids[sl] > k)
             np.testing.assert_array_equal(bones[local[sl][use, k]], pid[src[sl][use], k])
@@ -268,15 +271,13 @@ def test_tile_layout_is_a_faithful_permutation(name):
     eoff = plan[capi.PLAN_ELL_OFFSET].reshape(-1, 3)
     pad = plan[capi.PLAN_APP_SLOT_MORPH].size
     total_real = 0
-    V = 4                       # storage positions per thread (kVertsPerThread in host_plan.hpp)
-    WARPS = 1024 // V // 32     # warps per CTA; group g = step j * WARPS + warp w
     for ti in range(n_tiles):
         for j in range(V):
             for w in range(WARPS):
-                g = ti * 32 + j * WARPS + w
+                g = ti * GROUPS + j * WARPS + w
                 cnts = []
                 for l in range(32):
-                    pos = ti * 1024 + (w * 32 + l) * V + j
+                    pos = ti * TILE + (w * 32 + l) * V + j
                     v = src[pos]
                     cnt = int(row[v + 1] - row[v]) if v < nv else 0
                     cnts.append(cnt)
@@ -293,6 +294,6 @@ def test_tile_layout_is_a_faithful_permutation(name):
     for ti in range(n_tiles):
         for j in range(V):
             for w in range(WARPS):
-                pos = ti * 1024 + (w * 32 + np.arange(32)) * V + j
+                pos = ti * TILE + (w * 32 + np.arange(32)) * V + j
                 mixed += len(set(st_type[pos].tolist())) > 1
     assert mixed <= 3 * n_tiles

@@ -166,18 +166,19 @@ cudaError_t dalloc(DevArena& mem, T** out, size_t n, bool zero, cudaStream_t st)
 
 uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
 
-// How many consecutive slots one CTA walks for its tile.  Longer runs amortise the tile's static streams (read
-// once per run); shorter runs give more work items to balance over the SMs.
+// How many consecutive slots one CTA walks for its tile (a multiple of the slot group).  Long runs amortise the
+// per-item prologue (static streams, first palette); enough items must remain to fill the machine.  Measured on
+// B200 (profiles/r01_experiments.md): 64-slot runs are best whenever they still leave >= ~1.5 waves of work items.
 uint32_t choose_slots_per_cta(uint32_t tiles, uint32_t n_slots, int sm_count) {
-    if (tiles == 0 || n_slots == 0) return 1;
+    if (tiles == 0 || n_slots == 0) return kSlotGroup;
     if (const char* env = std::getenv("MMDGPU_SLOTS_PER_CTA")) {  // tuning knob for experiments
         const long v = std::strtol(env, nullptr, 10);
         if (v > 0) return uint32_t(std::min<long>(v, n_slots));
     }
-    const uint64_t target_items = uint64_t(sm_count > 0 ? sm_count : 148) * 3 * 8;  // 8 waves of 3 CTAs per SM
-    uint64_t n_chunks = (target_items + tiles - 1) / tiles;
-    n_chunks = std::min<uint64_t>(std::max<uint64_t>(n_chunks, 1), n_slots);
-    return uint32_t((n_slots + n_chunks - 1) / n_chunks);
+    const uint64_t min_items = uint64_t(sm_count > 0 ? sm_count : 148) * 3 * 3 / 2;  // 1.5 waves of 3 CTAs per SM
+    uint32_t chunk = std::min<uint32_t>(64, (n_slots + kSlotGroup - 1) / kSlotGroup * kSlotGroup);
+    while (chunk > kSlotGroup && uint64_t(tiles) * ((n_slots + chunk - 1) / chunk) < min_items) chunk = std::max(kSlotGroup, chunk / 2);
+    return (chunk + kSlotGroup - 1) / kSlotGroup * kSlotGroup;
 }
 
 mmdgpu_status upload_model(mmdgpu_model* m) {

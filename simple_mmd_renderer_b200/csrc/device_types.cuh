@@ -18,6 +18,7 @@ struct DevModel {
     uint32_t nv, nv_pad, nb, nm;
     uint32_t n_nodes, n_nodes_pad;  // morph application slots; padded to a multiple of 4, >= n_nodes + 1
     uint32_t n_tiles, max_tile_bones;
+    uint32_t global_palette;        // 1: tiles touch too many bones to stage; bone ids are global and the palette is read from HBM / L2
     // vertex streams (nv_pad entries each, storage order)
     const float *px, *py, *pz, *nx, *ny, *nz;
     const uint2* ids;        // 4 x u16 tile-local bone indices; bits 15:13 of id0 carry the device skinning type

@@ -817,7 +817,8 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
     // tile-local palette of one slot group: item i = (slot f = i / npal4, float4 q = i % npal4); float4 q is component
     // q % PS of tile bone q / PS: a matrix column (0..2) or, with extensions, the rotation quaternion / dual part
     const uint32_t tb0 = __ldg(M.tile_bone_begin + tile);
-    const uint32_t npal4 = (__ldg(M.tile_bone_begin + tile + 1) - tb0) * PS;
+    // global-palette models stage nothing: their bone ids index the slot's palette in global memory directly
+    const uint32_t npal4 = M.global_palette ? 0u : (__ldg(M.tile_bone_begin + tile + 1) - tb0) * PS;
     const uint32_t n_items = npal4 * G;
     const uint32_t npad = M.n_nodes_pad;               // float4 per rate block (one float4 = the G slots of a node)
     auto item_source = [&](uint32_t i) -> uint32_t {   // bits 31:30 = slot within the group, 29 = extension array
@@ -902,7 +903,8 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
             for (int f = 0; f < G; ++f) {
                 // slots past the end of a partial last group are computed on the clamped palette and not stored
                 const bool live = (uint32_t)f < n_live;
-                const float4* __restrict__ palf = pal + (size_t)f * pal4;
+                const float4* __restrict__ palf =
+                    M.global_palette ? F.palette + (size_t)min(g0 + (uint32_t)f, F.n_slots - 1u) * M.nb * 3 : pal + (size_t)f * pal4;
                 unsigned char* stage = stage_base + (size_t)f * stage_bytes;
                 float op[3], on[3];
                 // coordinate + vertex_image (poser_impl.inl:407)

@@ -165,6 +165,7 @@ cudaError_t dalloc(DevArena& mem, T** out, size_t n, bool zero, cudaStream_t st)
 }
 
 uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
+constexpr uint32_t kMaxStagedTileBones = 256;
 
 // How many consecutive slots one CTA walks for its tile (a multiple of the slot group).  Long runs amortise the
 // per-item prologue (static streams, first palette); enough items must remain to fill the machine.  Measured on
@@ -195,6 +196,14 @@ mmdgpu_status upload_model(mmdgpu_model* m) {
     D.max_tile_bones = std::max<uint32_t>(1, p.max_tile_bones);
     D.extensions = p.extensions ? 1u : 0u;
 
+    // A tile that touches more bones than fit the staged palettes (4 slots x 2 buffers x 48 B per bone next to the
+    // staging tiles) switches the whole model to global bone ids read straight from the slot's palette.
+    D.global_palette = (!p.extensions && p.max_tile_bones > kMaxStagedTileBones) ? 1u : 0u;
+    if (p.extensions && p.max_tile_bones > kMaxStagedTileBones)
+        return set_err(ctx, MMDGPU_ERR_UNSUPPORTED, "extensions with more than " + std::to_string(kMaxStagedTileBones) +
+                                                        " distinct bones in one 512-vertex tile");
+    if (D.global_palette) D.max_tile_bones = 0;
+
     // ---- vertex streams, structure of arrays, in tile storage order (host_plan.hpp)
     std::vector<float> plane[6];
     for (auto& v : plane) v.assign(nvp, 0.0f);
@@ -211,7 +220,12 @@ mmdgpu_status upload_model(mmdgpu_model* m) {
             }
             uv[pos] = make_float2(p.uv[size_t(src) * 2], p.uv[size_t(src) * 2 + 1]);
         }
-        const uint16_t* id = &p.st_local_id[size_t(pos) * 4];
+        uint16_t gid[4] = {0, 0, 0, 0};
+        if (D.global_palette) {
+            const uint32_t tb0 = p.tile_bone_begin[pos / kTileVerts];
+            for (int k = 0; k < 4; ++k) gid[k] = p.tile_bones[tb0 + p.st_local_id[size_t(pos) * 4 + k]];
+        }
+        const uint16_t* id = D.global_palette ? gid : &p.st_local_id[size_t(pos) * 4];
         ids[pos].x = uint32_t(id[0]) | (uint32_t(p.st_type[pos]) << 13) | (uint32_t(id[1]) << 16);
         ids[pos].y = uint32_t(id[2]) | (uint32_t(id[3]) << 16);
         const float* w = &p.st_weight[size_t(pos) * 4];

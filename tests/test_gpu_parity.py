@@ -393,3 +393,41 @@ def test_back_to_back_updates_are_ordered(ctx):
     assert_bitwise(fr.download(1, capi.STREAM_POSITION), orc.run_frame(11)["pos"], "step-wise after fused")
     fr.update(a, [100, 101])
     assert_bitwise(fr.download(0, capi.STREAM_POSITION), orc.run_frame(100)["pos"], "fused after step-wise")
+
+
+def test_global_palette_fallback_for_tiles_touching_hundreds_of_bones(ctx):
+    """Random binding over 1000 bones: a 512-vertex tile touches far more bones than can be staged, so the model
+    switches to global bone ids read straight from the palette.  Same results."""
+    from dataclasses import replace
+    from simple_mmd_renderer_b200 import synth
+    cfg = replace(synth.SMALL, name="small_random_1k", config_id=32, binding="random", n_bones=1000, n_vertices=6000)
+    model = synth.make_model(cfg)
+    motion = synth.make_motion(cfg, model)
+    orc = _oracle(model, motion)
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    fr = Frames(m, 1, 6)
+    fr.update(a, [0, 5, 60, 61, 62, 119])
+    for k, f in enumerate((0, 5, 60, 61, 62, 119)):
+        _check_frame(fr, k, orc.run_frame(f), f"global palette frame {f}")
+    fi = Frames(m, 1, 1, capi.LAYOUT_INTERLEAVED_SOKOL32)
+    fi.update(a, [61])
+    orc.run_frame(61)
+    assert_bitwise(fi.download(0, capi.STREAM_INTERLEAVED), orc.repack_sokol32(), "global palette interleaved")
+
+
+def test_large_skeleton_uses_the_global_state_hierarchy_kernel(ctx):
+    """1400 bones: the per-slot bone state no longer fits one CTA's shared memory, so K2 falls back to the
+    warp-per-slot kernel with state in global memory.  Same results, including IK and append bones."""
+    from dataclasses import replace
+    from simple_mmd_renderer_b200 import synth
+    cfg = replace(synth.TINY_FULL, name="tiny_1400_bones", config_id=33, n_bones=1400, n_vertices=4000)
+    model = synth.make_model(cfg)
+    motion = synth.make_motion(cfg, model)
+    orc = _oracle(model, motion)
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    fr = Frames(m, 1, 3)
+    fr.update(a, [4, 45, 88])
+    for k, f in enumerate((4, 45, 88)):
+        _check_frame(fr, k, orc.run_frame(f), f"1400 bones frame {f}")

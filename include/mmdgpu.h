@@ -380,14 +380,14 @@ typedef enum mmdgpu_plan_array {
     MMDGPU_PLAN_CSR_OFFSET = 17,    /* f32 [3 n_csr]                                                  */
     MMDGPU_PLAN_BEZIER_UNUSED = 18,
     MMDGPU_PLAN_WAVE_PHASE_SPLIT = 19,/* i32 [1] index of the first wave of the post-physics segment   */
-    /* device vertex layout: 1024-vertex tiles stored in a tile-local order (type, morph entry count, index) */
+    /* device vertex layout: 512-vertex tiles stored in a tile-local order (type, morph entry count, index) */
     MMDGPU_PLAN_TILE_ORIG = 20,     /* u16 [nv_pad] storage position -> PMX vertex index within its tile     */
     MMDGPU_PLAN_TILE_TYPE = 21,     /* u8  [nv_pad] device skinning type per storage position (0 B1 1 B2 2 B4 3 SDEF 4 QDEF) */
     MMDGPU_PLAN_TILE_LOCAL_ID = 22, /* u16 [4 nv_pad] tile-local bone index per storage position           */
     MMDGPU_PLAN_TILE_BONE_BEGIN = 23,/* u32 [n_tiles+1] offsets into TILE_BONES                             */
     MMDGPU_PLAN_TILE_BONES = 24,    /* u16 [..] distinct bone ids used by each tile, ascending              */
-    MMDGPU_PLAN_ELL_BASE = 25,      /* u32 [32 n_tiles] first entry of every 32-lane group                  */
-    MMDGPU_PLAN_ELL_ROUNDS = 26,    /* u32 [32 n_tiles] entries per lane (padded) of every group            */
+    MMDGPU_PLAN_ELL_BASE = 25,      /* u32 [16 n_tiles] first entry of every 32-lane group (16 per tile)  */
+    MMDGPU_PLAN_ELL_ROUNDS = 26,    /* u32 [16 n_tiles] entries per lane (padded) of every group            */
     MMDGPU_PLAN_ELL_SLOT = 27,      /* u32 [n_ell] application slot; padding = number of application slots  */
     MMDGPU_PLAN_ELL_OFFSET = 28,    /* f32 [3 n_ell]                                                        */
     /* model data as the plan holds it (lets a PMX byte stream be checked against flat arrays on the host) */

@@ -453,7 +453,7 @@ mmdgpu_status build_plan(const mmdgpu_model_desc& d, const mmdgpu_options* opt, 
 
     // ---------------------------------------------------------------- tiles (device vertex layout)
     // Vertices stay in PMX order in the OUTPUT (the renderer's index buffer is reused unchanged), but the static
-    // streams of each 1024-vertex tile are stored sorted by (skinning type, morph entry count, PMX index), so
+    // streams of each kTileVerts-vertex tile are stored sorted by (skinning type, morph entry count, PMX index), so
     // that the 32 lanes of a warp step run one skinning branch and one morph loop trip count.  Sorted rank r
     // lands at storage position tile_position_of_rank(r).  Bone ids become indices into the tile's own list of
     // distinct bones (the CTA stages only those matrices).

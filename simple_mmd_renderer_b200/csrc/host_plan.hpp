@@ -95,7 +95,7 @@ struct Plan {
     // per-vertex CSR of UV-morph entries (extensions only)
     std::vector<uint32_t> uv_row, uv_node;
     std::vector<float> uv_offset;    // 4 per entry (only .xy applied to the base UV)
-    // ---- device vertex layout: 1024-vertex tiles, each stored in a tile-local order that makes the 32 lanes
+    // ---- device vertex layout: kTileVerts-vertex tiles, each stored in a tile-local order that makes the 32 lanes
     //      of a warp step share a skinning type and a morph entry count (see build_tiles in host_plan.cpp)
     uint32_t nv_pad = 0, n_tiles = 0;
     std::vector<uint16_t> tile_orig;        // nv_pad: storage position -> PMX index within the tile

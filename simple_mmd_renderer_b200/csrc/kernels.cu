@@ -596,17 +596,19 @@ __global__ void __launch_bounds__(kHierCtaThreads) hierarchy_cta_kernel(DevModel
 // =================================================================================================
 // K3 — skinning.  Poser::Deform, L/motion/poser_impl.inl:396-461; transform / rotate math_impl.inl:1032-1045.
 //
-// Work item = one 1024-vertex tile x a run of consecutive slots (frames of a bake, instances of a crowd).
+// Work item = one 512-vertex tile x a run of consecutive slots (frames of a bake, instances of a crowd), walked
+// four slots (one "slot group") at a time.
 //   * The tile's static streams are read ONCE (16-byte coalesced loads, 4 storage positions per thread) and stay
 //     in registers while the CTA walks its slots: per vertex-frame only the output leaves the SM.
-//   * Per slot the CTA stages just the matrices of the bones this tile uses (tile-local palette) and the slot's
-//     morph application-slot rates in shared memory, double-buffered: the next slot's loads are in flight
-//     while the current slot is computed.
+//   * Per slot group the CTA stages just the matrices of the bones this tile uses (tile-local palettes of the four
+//     slots) and the group's morph application-slot rates (one float4 per slot = the four slots' rates) in shared
+//     memory, double-buffered: the next group's loads are in flight while the current group is computed.
 //   * Sparse vertex morphs arrive as a sliced-ELL gather (32-lane groups, coalesced 512-byte rounds, warp-uniform
-//     trip count) in libmmd's application order: no vertex_images_ buffer, no clear pass, no atomics.
+//     trip count) in libmmd's application order; one entry load serves the four slots.  No vertex_images_ buffer,
+//     no clear pass, no atomics.
 //   * Tiles are stored sorted by (skinning type, morph entry count), so a warp step runs one branch; results are
-//     written to a shared-memory staging tile at the vertex's PMX index and leave the SM as one bulk async
-//     copy (cp.async.bulk shared -> global) per output plane.
+//     written to shared-memory staging tiles at the vertex's PMX index and leave the SM as one bulk async copy
+//     (cp.async.bulk shared -> global) per output plane and slot.
 // =================================================================================================
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -14,7 +14,7 @@ cudaError_t launch_pose_sample(cudaStream_t st, const DevModel& M, const DevAnim
 // K2: waves [wave_lo, wave_hi) of the bone program; prologue = morph rates + reset + bone morphs.
 cudaError_t launch_hierarchy(cudaStream_t st, const DevModel& M, const DevFrames& F, uint32_t wave_lo, uint32_t wave_hi,
                              bool prologue);
-// K3: skinning + fused vertex-morph gather.  One CTA = one 1024-vertex tile x `slots_per_cta` consecutive slots.
+// K3: skinning + fused vertex-morph gather.  One CTA = one 512-vertex tile x `slots_per_cta` consecutive slots, four at a time.
 size_t skin_smem_bytes(const DevModel& M, int layout);
 cudaError_t prepare_skin_kernels(const DevModel& M);
 cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, int layout, uint32_t slots_per_cta);

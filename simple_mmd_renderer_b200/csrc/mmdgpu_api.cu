@@ -75,7 +75,6 @@ struct mmdgpu_model {
     mmdgpu_plan plan;
     DevModel dev{};
     DevArena mem;
-    uint32_t skin_tiles_per_cta = 1;
 };
 
 struct mmdgpu_animation {

@@ -306,6 +306,10 @@ MMDGPU_API mmdgpu_status mmdgpu_seek_frame(mmdgpu_frames_t frames, const mmdgpu_
  * first_frame_per_instance is host memory (n_instances). */
 MMDGPU_API mmdgpu_status mmdgpu_seek_frame_range(mmdgpu_frames_t frames, const mmdgpu_animation_t* per_instance,
                                                  const uint32_t* first_frame_per_instance, uint32_t frame_stride);
+/* MotionPlayer::SeekTime(double) (L/motion/poser_impl.inl:548-555; sampling of L/motion/motion_impl.inl:321-380,
+ * 426-470): frame = seconds * 30 as a double, no snapping to key frames.  time_per_slot: n_slots seconds (host). */
+MMDGPU_API mmdgpu_status mmdgpu_seek_time(mmdgpu_frames_t frames, const mmdgpu_animation_t* per_instance,
+                                          const double* time_per_slot);
 /* Poser::SetBonePose / SetMorphPose by index (L/motion/poser_impl.inl:466-480). */
 MMDGPU_API mmdgpu_status mmdgpu_set_bone_pose(mmdgpu_frames_t frames, uint32_t slot, uint32_t bone,
                                               const float translation[3], const float rotation[4]);

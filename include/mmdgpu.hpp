@@ -214,9 +214,11 @@ public:
         const uint32_t f = uint32_t(frame);
         poser_.GetModel().context().check(mmdgpu_seek_frame(poser_.frames(), &a, &f), "mmdgpu_seek_frame");
     }
-    // main.cpp only uses SeekFrame (main.cpp:1793-1796); sub-frame sampling (SeekTime(double),
-    // motion_impl.inl:321-380) is not on the path and is served at the integer frame.
-    void SeekTime(double time_seconds) { SeekFrame(size_t(time_seconds * 30.0)); }
+    // MotionPlayer::SeekTime(double), poser_impl.inl:548-555 (main.cpp itself only uses SeekFrame)
+    void SeekTime(double time_seconds) {
+        mmdgpu_animation_t a = motion_.handle();
+        poser_.GetModel().context().check(mmdgpu_seek_time(poser_.frames(), &a, &time_seconds), "mmdgpu_seek_time");
+    }
 
 private:
     const Motion& motion_;

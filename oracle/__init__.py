@@ -60,6 +60,8 @@ class _Session:
         self._manual = getattr(self.lib, p + "run_manual")
         self._manual.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        self._run_time = getattr(self.lib, p + "run_time")
+        self._run_time.argtypes = [C.c_void_p, C.c_double] + [C.c_void_p] * 5
         self._skin = getattr(self.lib, p + "get_skinning")
         self._skin.argtypes = [C.c_void_p] * 4
         self._ik = getattr(self.lib, p + "get_ik_class")
@@ -104,6 +106,15 @@ class _Session:
             else:
                 ptrs.append(None)
         self._run(self.h, int(frame), *ptrs)
+        return out
+
+    def run_time(self, seconds: float) -> dict:
+        """ResetPosing; MotionPlayer::SeekTime(seconds); Pre; Post; Deform."""
+        out = dict(pos=np.zeros((self.nv, 3), np.float32), nrm=np.zeros((self.nv, 3), np.float32),
+                   skin=np.zeros((self.nb, 16), np.float32), poses=np.zeros((self.nb, 7), np.float32),
+                   rates=np.zeros((self.nm,), np.float32))
+        self._run_time(self.h, float(seconds), _fp(out["pos"]), _fp(out["nrm"]), _fp(out["skin"]), _fp(out["poses"]),
+                       _fp(out["rates"]))
         return out
 
     def run_manual(self, bones, poses7, morphs, weights) -> dict:

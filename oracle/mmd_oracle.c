@@ -522,6 +522,54 @@ static float sample_morph(const model_t* m, uint32_t t, uint32_t frame) {
     return k[r - 1].w * (1 - lam) + k[r].w * lam;
 }
 
+/* Motion::GetBonePose / GetMorphPose(name, double time), L/motion/motion_impl.inl:321-380, 426-470: the frame is
+ * time*30 as a double, the bracket is upper_bound(size_t(dframe)), there is no "left key == frame" shortcut, and
+ * the barycentre is computed in double and cast to float. */
+static void sample_bone_time(const model_t* m, uint32_t t, double time, float* T, float* R) {
+    uint32_t n = m->bt_count[t];
+    const bkey* k = m->bkeys + m->bt_begin[t];
+    if (n == 0) { T[0] = T[1] = T[2] = 0; R[0] = R[1] = R[2] = 0; R[3] = 1; return; }
+    double dframe = time * 30.0;
+    const bkey* use = NULL;
+    if ((double)k[0].frame >= dframe) use = &k[0];
+    else if ((double)k[n - 1].frame <= dframe) use = &k[n - 1];
+    if (use) { memcpy(T, use->T, 12); memcpy(R, use->R, 16); return; }
+    size_t key = (size_t)dframe;
+    uint32_t r = 0;
+    while (k[r].frame <= key) ++r;
+    const bkey* rk = &k[r];
+    const bkey* lk = &k[r - 1];
+    float bary = (float)((dframe - (double)lk->frame) / (double)((size_t)rk->frame - (size_t)lk->frame));
+    for (int c = 0; c < 3; ++c) {
+        float lam = bezier_at(&lk->ip[c], bary);
+        T[c] = lk->T[c] * (1 - lam) + rk->T[c] * lam;
+    }
+    float l = bezier_at(&lk->ip[3], bary);
+    if (l < EPS_F) { memcpy(R, lk->R, 16); return; }
+    if (l > (1.0f - EPS_F)) { memcpy(R, rk->R, 16); return; }
+    const float* a = lk->R; const float* b = rk->R;
+    float dot = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3];
+    float v[4];
+    if (dot < 0.0f) for (int c = 0; c < 4; ++c) v[c] = (1.0f - l) * a[c] - l * b[c];
+    else for (int c = 0; c < 4; ++c) v[c] = (1.0f - l) * a[c] + l * b[c];
+    float nn = 1.0f / m_sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
+    for (int c = 0; c < 4; ++c) R[c] = v[c] * nn;
+}
+static float sample_morph_time(const model_t* m, uint32_t t, double time) {
+    uint32_t n = m->mt_count[t];
+    const mkey* k = m->mkeys + m->mt_begin[t];
+    if (n == 0) return 0.0f;
+    double dframe = time * 30.0;
+    if ((double)k[0].frame >= dframe) return k[0].w;
+    if ((double)k[n - 1].frame <= dframe) return k[n - 1].w;
+    size_t key = (size_t)dframe;
+    uint32_t r = 0;
+    while (k[r].frame <= key) ++r;
+    float bary = (float)((dframe - (double)k[r - 1].frame) / (double)((size_t)k[r].frame - (size_t)k[r - 1].frame));
+    float lam = bary;
+    return k[r - 1].w * (1 - lam) + k[r].w * lam;
+}
+
 /* ---- Poser -------------------------------------------------------------------------------------- */
 /* Poser::ResetPosing's pose part, L/motion/poser_impl.inl:131-137 */
 static void reset_poses(state_t* s) {
@@ -540,6 +588,17 @@ static void seek_frame(state_t* s, uint32_t frame) {
     for (uint32_t t = 0; t < m->n_btracks; ++t) {
         int32_t b = m->bt_bone[t];
         sample_bone(m, t, frame, s->T + 3 * b, s->R + 4 * b);
+    }
+}
+
+/* MotionPlayer::SeekTime, L/motion/poser_impl.inl:548-555 */
+static void seek_time(state_t* s, double time) {
+    const model_t* m = s->m;
+    if (!m->has_motion) return;
+    for (uint32_t t = 0; t < m->n_mtracks; ++t) s->rate[m->mt_morph[t]] = sample_morph_time(m, t, time);
+    for (uint32_t t = 0; t < m->n_btracks; ++t) {
+        int32_t b = m->bt_bone[t];
+        sample_bone_time(m, t, time, s->T + 3 * b, s->R + 4 * b);
     }
 }
 
@@ -821,6 +880,17 @@ EXPORT int port_run_frame(struct port_session* p, uint32_t frame, float* pos, fl
                           float* poses, float* rates) {
     one_frame(&p->s, frame);
     copy_out(&p->s, pos, nrm, skin, local, poses, rates);
+    return 0;
+}
+EXPORT int port_run_time(struct port_session* p, double seconds, float* pos, float* nrm, float* skin, float* poses,
+                         float* rates) {
+    state_t* s = &p->s;
+    reset_poses(s);
+    seek_time(s, seconds);
+    pre_physics(s);
+    post_physics(s);
+    deform(s);
+    copy_out(s, pos, nrm, skin, NULL, poses, rates);
     return 0;
 }
 EXPORT int port_run_manual(struct port_session* p, uint32_t nbp, const int32_t* bone, const float* pose7, uint32_t nmp,

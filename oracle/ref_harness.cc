@@ -372,6 +372,30 @@ __attribute__((visibility("default"))) int ref_run_frame(ref_session* s, uint32_
     return 0;
 }
 
+// Sub-frame path: ResetPosing, MotionPlayer::SeekTime(seconds) (L/motion/poser_impl.inl:548-555), Pre, Post, Deform.
+__attribute__((visibility("default"))) int ref_run_time(ref_session* s, double seconds, float* pos, float* nrm,
+                                                         float* skin, float* poses, float* rates) {
+    Poser& p = *s->poser;
+    p.ResetPosing();
+    s->player->SeekTime(seconds);
+    p.PrePhysicsPosing();
+    p.PostPhysicsPosing();
+    p.Deform();
+    size_t nv = s->model.GetVertexNum(), nb = s->model.GetBoneNum(), nm = s->model.GetMorphNum();
+    if (pos) memcpy(pos, p.pose_image.coordinates.data(), nv * 12);
+    if (nrm) memcpy(nrm, p.pose_image.normals.data(), nv * 12);
+    for (size_t b = 0; b < nb; ++b) {
+        if (skin) Spy::SkinningMatrix(p, b, skin + 16 * b);
+        if (poses) Spy::Pose(p, b, poses + 7 * b);
+    }
+    if (rates)
+        for (size_t m = 0; m < nm; ++m) {
+            std::wstring nmw = s->model.GetMorph(m).GetName();
+            rates[m] = s->motion.IsMorphRegistered(nmw) ? s->motion.GetMorphPose(nmw, seconds).GetWeight() : 0.0f;
+        }
+    return 0;
+}
+
 // Manual posing path: ResetPosing, SetBonePose/SetMorphPose for the listed items, Pre, Post, Deform.
 __attribute__((visibility("default"))) int ref_run_manual(ref_session* s, uint32_t n_bone_poses,
                                                            const int32_t* bone, const float* pose7,

@@ -95,6 +95,7 @@ struct DevFrames {
     float* out_nrm;     // SOA: [slot][nv_pad][3]
     float4* out_inter;  // INTERLEAVED: [slot][nv_pad][2]
     uint32_t* frame_id; // [slot]
+    double* time_s;     // [slot] seconds, for MotionPlayer::SeekTime
 };
 
 }  // namespace mmdgpu

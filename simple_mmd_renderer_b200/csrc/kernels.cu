@@ -31,14 +31,48 @@ __device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t* __restrict__
     return lo;
 }
 
+// Bracketing of one track at one slot: either one key verbatim (`use`) or keys (l, r) with barycentre `bary`.
+//   frame mode  Motion::GetBonePose(name, size_t), motion_impl.inl:266-291: `left.frame == frame` returns the left key
+//   time mode   Motion::GetBonePose(name, double), motion_impl.inl:333-354: frame = seconds*30 as a double, bracket by
+//               upper_bound(size_t(frame)), no equality shortcut, barycentre computed in double then cast to float
+struct Bracket { uint32_t use, l, r; float bary; };
+__device__ __forceinline__ Bracket bracket_keys(const uint32_t* __restrict__ kf, uint32_t n, bool time_mode, uint32_t frame,
+                                                double dframe) {
+    Bracket b{0xFFFFFFFFu, 0u, 0u, 0.0f};
+    if (!time_mode) {
+        if (kf[0] >= frame) b.use = 0;
+        else if (kf[n - 1] <= frame) b.use = n - 1;
+        else {
+            b.r = upper_bound_u32(kf, n, frame);
+            b.l = b.r - 1;
+            const uint32_t lf = kf[b.l], rf = kf[b.r];
+            if (lf == frame) b.use = b.l;
+            else b.bary = (float)(frame - lf) / (float)(rf - lf);
+        }
+    } else {
+        if ((double)kf[0] >= dframe) b.use = 0;
+        else if ((double)kf[n - 1] <= dframe) b.use = n - 1;
+        else {
+            b.r = upper_bound_u32(kf, n, (uint32_t)(unsigned long long)dframe);
+            b.l = b.r - 1;
+            const uint32_t lf = kf[b.l], rf = kf[b.r];
+            b.bary = (float)((dframe - (double)lf) / (double)(rf - lf));
+        }
+    }
+    return b;
+}
+
 __global__ void __launch_bounds__(128) pose_sample_kernel(DevModel M, const DevAnim* __restrict__ anims, DevFrames F,
                                                           uint32_t write_untracked, uint32_t range_mode,
-                                                          uint32_t frame_stride, uint32_t has_anims) {
+                                                          uint32_t frame_stride, uint32_t has_anims, uint32_t time_mode) {
     const uint32_t slot = blockIdx.y;
     const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
     if (item >= M.nb + M.nm) return;
     const uint32_t inst = slot / F.n_frames;
-    const uint32_t frame = range_mode ? (F.frame_id[inst] + (slot - inst * F.n_frames) * frame_stride) : F.frame_id[slot];
+    uint32_t frame = 0;
+    double dframe = 0.0;
+    if (time_mode) dframe = F.time_s[slot] * 30.0;
+    else frame = range_mode ? (F.frame_id[inst] + (slot - inst * F.n_frames) * frame_stride) : F.frame_id[slot];
     if (item < M.nb) {
         const uint32_t b = item;
         float4 T = make_float4(0.f, 0.f, 0.f, 0.f), R = make_float4(0.f, 0.f, 0.f, 1.f);
@@ -49,48 +83,38 @@ __global__ void __launch_bounds__(128) pose_sample_kernel(DevModel M, const DevA
             const uint32_t n = A.bone_key_count[b];
             if (tracked && n > 0) {
                 const uint32_t k0 = A.bone_key_begin[b];
-                const uint32_t* kf = A.key_frame + k0;
-                uint32_t use = 0xFFFFFFFFu;
-                if (kf[0] >= frame) use = 0;
-                else if (kf[n - 1] <= frame) use = n - 1;
-                else {
-                    const uint32_t r = upper_bound_u32(kf, n, frame);
-                    const uint32_t l = r - 1;
-                    const uint32_t lf = kf[l], rf = kf[r];
-                    if (lf == frame) use = l;
+                const Bracket br = bracket_keys(A.key_frame + k0, n, time_mode != 0, frame, dframe);
+                if (br.use != 0xFFFFFFFFu) {
+                    T = A.key_T[k0 + br.use];
+                    R = A.key_R[k0 + br.use];
+                } else {
+                    const float bary = br.bary;
+                    const float4 lT = A.key_T[k0 + br.l], rT = A.key_T[k0 + br.r];
+                    const float4 lR = A.key_R[k0 + br.l], rR = A.key_R[k0 + br.r];
+                    const uint4 cv = A.key_curve[k0 + br.l];  // curves of the LEFT key (motion_impl.inl:302-312)
+                    float lam = bezier_at(A.tables, cv.x, bary);
+                    T.x = lT.x * (1 - lam) + rT.x * lam;
+                    lam = bezier_at(A.tables, cv.y, bary);
+                    T.y = lT.y * (1 - lam) + rT.y * lam;
+                    lam = bezier_at(A.tables, cv.z, bary);
+                    T.z = lT.z * (1 - lam) + rT.z * lam;
+                    const float l_ = bezier_at(A.tables, cv.w, bary);
+                    // NLerpProxy<Vector4f>::operator[], L/util/math_impl.inl:1265-1277
+                    if (l_ < kEpsF) R = lR;
+                    else if (l_ > (1.0f - kEpsF)) R = rR;
                     else {
-                        const float bary = (float)(frame - lf) / (float)(rf - lf);
-                        const float4 lT = A.key_T[k0 + l], rT = A.key_T[k0 + r];
-                        const float4 lR = A.key_R[k0 + l], rR = A.key_R[k0 + r];
-                        const uint4 cv = A.key_curve[k0 + l];  // curves of the LEFT key (motion_impl.inl:302-312)
-                        float lam = bezier_at(A.tables, cv.x, bary);
-                        T.x = lT.x * (1 - lam) + rT.x * lam;
-                        lam = bezier_at(A.tables, cv.y, bary);
-                        T.y = lT.y * (1 - lam) + rT.y * lam;
-                        lam = bezier_at(A.tables, cv.z, bary);
-                        T.z = lT.z * (1 - lam) + rT.z * lam;
-                        const float l_ = bezier_at(A.tables, cv.w, bary);
-                        // NLerpProxy<Vector4f>::operator[], L/util/math_impl.inl:1265-1277
-                        if (l_ < kEpsF) R = lR;
-                        else if (l_ > (1.0f - kEpsF)) R = rR;
-                        else {
-                            const float dot = lR.x * rR.x + lR.y * rR.y + lR.z * rR.z + lR.w * rR.w;
-                            float4 v;
-                            if (dot < 0.0f) {
-                                v.x = (1.0f - l_) * lR.x - l_ * rR.x; v.y = (1.0f - l_) * lR.y - l_ * rR.y;
-                                v.z = (1.0f - l_) * lR.z - l_ * rR.z; v.w = (1.0f - l_) * lR.w - l_ * rR.w;
-                            } else {
-                                v.x = (1.0f - l_) * lR.x + l_ * rR.x; v.y = (1.0f - l_) * lR.y + l_ * rR.y;
-                                v.z = (1.0f - l_) * lR.z + l_ * rR.z; v.w = (1.0f - l_) * lR.w + l_ * rR.w;
-                            }
-                            const float nn = 1.0f / m_sqrt(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
-                            R = make_float4(v.x * nn, v.y * nn, v.z * nn, v.w * nn);
+                        const float dot = lR.x * rR.x + lR.y * rR.y + lR.z * rR.z + lR.w * rR.w;
+                        float4 v;
+                        if (dot < 0.0f) {
+                            v.x = (1.0f - l_) * lR.x - l_ * rR.x; v.y = (1.0f - l_) * lR.y - l_ * rR.y;
+                            v.z = (1.0f - l_) * lR.z - l_ * rR.z; v.w = (1.0f - l_) * lR.w - l_ * rR.w;
+                        } else {
+                            v.x = (1.0f - l_) * lR.x + l_ * rR.x; v.y = (1.0f - l_) * lR.y + l_ * rR.y;
+                            v.z = (1.0f - l_) * lR.z + l_ * rR.z; v.w = (1.0f - l_) * lR.w + l_ * rR.w;
                         }
+                        const float nn = 1.0f / m_sqrt(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
+                        R = make_float4(v.x * nn, v.y * nn, v.z * nn, v.w * nn);
                     }
-                }
-                if (use != 0xFFFFFFFFu) {
-                    T = A.key_T[k0 + use];
-                    R = A.key_R[k0 + use];
                 }
                 T.w = 0.f;
             }
@@ -109,19 +133,12 @@ __global__ void __launch_bounds__(128) pose_sample_kernel(DevModel M, const DevA
             const uint32_t n = A.morph_key_count[m];
             if (tracked && n > 0) {
                 const uint32_t k0 = A.morph_key_begin[m];
-                const uint32_t* kf = A.mkey_frame + k0;
                 const float* kw = A.mkey_weight + k0;
-                if (kf[0] >= frame) w = kw[0];
-                else if (kf[n - 1] <= frame) w = kw[n - 1];
+                const Bracket br = bracket_keys(A.mkey_frame + k0, n, time_mode != 0, frame, dframe);
+                if (br.use != 0xFFFFFFFFu) w = kw[br.use];
                 else {
-                    const uint32_t r = upper_bound_u32(kf, n, frame);
-                    const uint32_t l = r - 1;
-                    if (kf[l] == frame) w = kw[l];
-                    else {
-                        const float bary = (float)(frame - kf[l]) / (float)(kf[r] - kf[l]);
-                        const float lam = bary;  // default-constructed Bezier is linear (math_impl.inl:1350-1354)
-                        w = kw[l] * (1 - lam) + kw[r] * lam;
-                    }
+                    const float lam = br.bary;  // default-constructed Bezier is linear (math_impl.inl:1350-1354)
+                    w = kw[br.l] * (1 - lam) + kw[br.r] * lam;
                 }
             }
         }
@@ -982,12 +999,12 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
 // launchers
 // =================================================================================================
 cudaError_t launch_pose_sample(cudaStream_t st, const DevModel& M, const DevAnim* anims, const DevFrames& F,
-                               bool write_untracked, bool range_mode, uint32_t frame_stride) {
+                               bool write_untracked, bool range_mode, uint32_t frame_stride, bool time_mode) {
     const uint32_t items = M.nb + M.nm;
     if (items == 0 || F.n_slots == 0) return cudaSuccess;
     dim3 grid((items + 127) / 128, F.n_slots);
     pose_sample_kernel<<<grid, 128, 0, st>>>(M, anims, F, write_untracked ? 1u : 0u, range_mode ? 1u : 0u, frame_stride,
-                                             anims ? 1u : 0u);
+                                             anims ? 1u : 0u, time_mode ? 1u : 0u);
     return cudaGetLastError();
 }
 

@@ -10,7 +10,7 @@ namespace mmdgpu {
 // K1: keyframe sampling for every (slot, bone) and (slot, morph).  anims == nullptr: write identity / zero
 // (Poser::ResetPosing's pose part).  write_untracked: also write identity / zero for items without a track.
 cudaError_t launch_pose_sample(cudaStream_t st, const DevModel& M, const DevAnim* anims, const DevFrames& F,
-                               bool write_untracked, bool range_mode, uint32_t frame_stride);
+                               bool write_untracked, bool range_mode, uint32_t frame_stride, bool time_mode = false);
 // K2: waves [wave_lo, wave_hi) of the bone program; prologue = morph rates + reset + bone morphs.
 cudaError_t launch_hierarchy(cudaStream_t st, const DevModel& M, const DevFrames& F, uint32_t wave_lo, uint32_t wave_hi,
                              bool prologue);

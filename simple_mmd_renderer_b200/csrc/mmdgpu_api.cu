@@ -920,6 +920,7 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_create(mmdgpu_context_t ctx, mmdgpu_model
         CU(ctx, dalloc(f->mem, &F.out_inter, ns * M.nv_pad * 2, false, st));
     }
     CU(ctx, dalloc(f->mem, &F.frame_id, ns, true, st));
+    CU(ctx, dalloc(f->mem, &F.time_s, ns, true, st));
     CU(ctx, dalloc(f->mem, &f->d_anims, size_t(n_instances), true, st));
     f->slots_per_cta = choose_slots_per_cta(M.n_tiles, F.n_slots, ctx->sm_count);
     // Poser::Poser ends with ResetPosing() (poser_impl.inl:125-127): a fresh object holds identity poses.
@@ -966,6 +967,21 @@ MMDGPU_API mmdgpu_status mmdgpu_seek_frame_range(mmdgpu_frames_t f, const mmdgpu
     if (mmdgpu_status s = enter(f->ctx)) return s;
     f->main_dirty = true;
     return do_seek(f, per_instance, first_frame_per_instance, true, frame_stride, false, f->ctx->stream);
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_seek_time(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance, const double* time_per_slot) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    mmdgpu_context_t ctx = f->ctx;
+    if (mmdgpu_status s = enter(ctx)) return s;
+    if (!time_per_slot) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "time array is NULL");
+    f->main_dirty = true;
+    if (mmdgpu_status s = bind_anims(f, per_instance, ctx->stream)) return s;
+    CU(ctx, cudaMemcpyAsync(f->dev.time_s, time_per_slot, sizeof(double) * f->dev.n_slots, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        Timed t(ctx, MMDGPU_KERNEL_POSE_SAMPLE);
+        CU(ctx, launch_pose_sample(ctx->stream, f->model->dev, f->d_anims, f->dev, false, false, 1, true));
+    }
+    return MMDGPU_OK;
 }
 
 MMDGPU_API mmdgpu_status mmdgpu_set_bone_pose(mmdgpu_frames_t f, uint32_t slot, uint32_t bone, const float T[3],

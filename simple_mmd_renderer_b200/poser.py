@@ -194,6 +194,12 @@ class Frames:
             raise ValueError("one first frame per instance required")
         check(self.lib.mmdgpu_seek_frame_range(self.h, self._anim_array(motions), _ptr(f), int(stride)), self.ctx.h)
 
+    def seek_time(self, motions, time_per_slot):
+        t = np.ascontiguousarray(time_per_slot, np.float64)
+        if t.size != self.n_slots:
+            raise ValueError("one time per slot required")
+        check(self.lib.mmdgpu_seek_time(self.h, self._anim_array(motions), _ptr(t)), self.ctx.h)
+
     def set_bone_pose(self, slot: int, bone: int, translation, rotation):
         t = np.ascontiguousarray(translation, np.float32)
         r = np.ascontiguousarray(rotation, np.float32)
@@ -351,6 +357,10 @@ class MotionPlayer:
 
     def SeekFrame(self, frame: int):
         self.poser.frames.seek_frame(self.motion, [int(frame)])
+
+    def SeekTime(self, seconds: float):
+        """MotionPlayer::SeekTime(double), poser_impl.inl:548-555."""
+        self.poser.frames.seek_time(self.motion, [float(seconds)])
 
 
 # ------------------------------------------------------------------------------------ host-only plan access

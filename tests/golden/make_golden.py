@@ -24,6 +24,7 @@ CASES = {
     "small": [0, 59, 119],
 }
 STRIDE = 53
+TIMES = [0.0, 1.0 / 30.0, 0.0123, 0.5, 0.7777, 1.99, 2.5, 17.0]   # seconds, MotionPlayer::SeekTime
 
 
 def sha(a: np.ndarray) -> str:
@@ -66,6 +67,12 @@ def main():
             out[f"f{f}_pos_s"] = r["pos"][::STRIDE].copy()
             out[f"f{f}_nrm_s"] = r["nrm"][::STRIDE].copy()
             out[f"f{f}_sokol32_sha"] = np.asarray(sha(ref.repack_sokol32()))
+        out["times"] = np.asarray(TIMES, np.float64)
+        for i, t in enumerate(TIMES):
+            r = ref.run_time(t)
+            for k in ("pos", "nrm", "skin", "poses", "rates"):
+                out[f"t{i}_{k}_sha"] = np.asarray(sha(r[k]))
+            out[f"t{i}_poses"] = r["poses"]
         path = os.path.join(HERE, f"{name}.npz")
         np.savez_compressed(path, **out)
         print(name, os.path.getsize(path), "bytes")

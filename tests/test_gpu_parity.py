@@ -431,3 +431,48 @@ def test_large_skeleton_uses_the_global_state_hierarchy_kernel(ctx):
     fr.update(a, [4, 45, 88])
     for k, f in enumerate((4, 45, 88)):
         _check_frame(fr, k, orc.run_frame(f), f"1400 bones frame {f}")
+
+
+def test_seek_time_matches_oracle_and_golden(ctx):
+    """MotionPlayer::SeekTime(double) (poser_impl.inl:548-555): sub-frame sampling with the barycentre computed in
+    double; at an exact key frame it does NOT snap to the key (Bezier table entry 0 is ~2.7e-7, not 0)."""
+    from golden_util import load_golden, sha
+    cfg, model, motion = synth_case("tiny_full")
+    orc = _oracle(model, motion)
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    rng = np.random.default_rng(2)
+    times = list(rng.uniform(0, 3.1, 13)) + [0.0, 1 / 30, 0.5, 17.0]
+    fr = Frames(m, 1, len(times))
+    fr.reset_posing()
+    fr.seek_time(a, times)
+    fr.pre_physics_posing()
+    fr.post_physics_posing()
+    fr.deform()
+    for k, t in enumerate(times):
+        ref = orc.run_time(float(t))
+        assert_bitwise(fr.bone_poses(k), ref["poses"], f"t={t} poses")
+        assert_bitwise(fr.morph_rates(k), ref["rates"], f"t={t} rates")
+        assert_bitwise(fr.bone_matrices(k), ref["skin"], f"t={t} skin")
+        assert_bitwise(fr.download(k, capi.STREAM_POSITION), ref["pos"], f"t={t} pos")
+        assert_bitwise(fr.download(k, capi.STREAM_NORMAL), ref["nrm"], f"t={t} nrm")
+    g = load_golden("tiny_full")
+    gt = [float(t) for t in g["times"]]
+    fr2 = Frames(m, 1, len(gt))
+    fr2.reset_posing()
+    fr2.seek_time(a, gt)
+    fr2.pre_physics_posing()
+    fr2.post_physics_posing()
+    fr2.deform()
+    for i in range(len(gt)):
+        assert sha(fr2.download(i, capi.STREAM_POSITION)) == str(g[f"t{i}_pos_sha"])
+        assert sha(fr2.bone_poses(i)) == str(g[f"t{i}_poses_sha"])
+    # the libmmd-named mirror
+    poser = Poser(m)
+    player = MotionPlayer(a, poser)
+    poser.ResetPosing()
+    player.SeekTime(0.7777)
+    poser.PrePhysicsPosing()
+    poser.PostPhysicsPosing()
+    poser.Deform()
+    assert_bitwise(poser.pose_image.coordinates, orc.run_time(0.7777)["pos"], "MotionPlayer.SeekTime")

@@ -70,6 +70,31 @@ def test_restatement_manual_posing_matches_libmmd():
         assert_bitwise(p[k], r[k], f"manual {k}")
 
 
+@pytest.mark.parametrize("name", CASES)
+def test_restatement_seek_time_matches_golden(name):
+    """MotionPlayer::SeekTime(double): sub-frame sampling, barycentre in double, no key-frame snapping."""
+    cfg, model, motion = synth_case(name)
+    g = load_golden(name)
+    port = oracle.Restatement(model, motion)
+    for i, t in enumerate(g["times"]):
+        got = port.run_time(float(t))
+        np.testing.assert_array_equal(got["poses"].view(np.uint32), g[f"t{i}_poses"].view(np.uint32))
+        for k in ("pos", "nrm", "skin", "poses", "rates"):
+            assert sha(got[k]) == str(g[f"t{i}_{k}_sha"]), f"{name} t={t}: {k} differs from libmmd's"
+
+
+@pytest.mark.skipif(not oracle.have_reference(), reason="libmmd reference harness not built (needs /root/reference)")
+def test_restatement_seek_time_matches_libmmd_bitwise():
+    cfg, model, motion = synth_case("tiny_full")
+    ref = oracle.Reference(model, motion)
+    port = oracle.Restatement(model, motion)
+    rng = np.random.default_rng(9)
+    for t in list(rng.uniform(0, 3.2, 40)) + [0.0, 1 / 30, 2 / 30, 1.0, 3.0, 100.0]:
+        r, p = ref.run_time(float(t)), port.run_time(float(t))
+        for k in ("poses", "rates", "skin", "pos", "nrm"):
+            assert_bitwise(p[k], r[k], f"t={t} {k}")
+
+
 def test_multithreaded_timing_entry_is_consistent():
     """port_time_frames (the CPU-baseline leg of bench.py): same checksum for 1 and 4 threads."""
     cfg, model, motion = synth_case("tiny")

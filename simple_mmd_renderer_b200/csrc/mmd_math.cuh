@@ -17,7 +17,18 @@ namespace dm {
 constexpr float kEpsF = 1e-7f;   // T(mmd_math_const_eps)
 constexpr double kEpsD = 1e-7;   // mmd_math_const_eps as written (double macro, L/util/math.inl:24)
 
-MMD_DEV float m_sqrt(float x) { return (float)sqrt((double)x); }
+// libmmd: (float)sqrt((double)x).  Rounding a double square root to float equals the correctly rounded float square
+// root for every float (53 >= 2*24 + 2 bits; verified exhaustively, tools/micro/sqrt_identity.c), so the fp32
+// instruction (IEEE, -prec-sqrt=true) is used.
+MMD_DEV float m_sqrt(float x) { return sqrtf(x); }
+// sin and cos of one argument share the range reduction; sincos() is bit-identical to separate sin() / cos() on this
+// toolchain (verified over every float in [-64, 64] and a sweep of large arguments, tools/micro/sincos_check.cu).
+MMD_DEV void m_sincos(float x, float& s, float& c) {
+    double ds, dc;
+    sincos((double)x, &ds, &dc);
+    s = (float)ds;
+    c = (float)dc;
+}
 MMD_DEV float m_sin(float x) { return (float)sin((double)x); }
 MMD_DEV float m_cos(float x) { return (float)cos((double)x); }
 MMD_DEV float m_asin(float x) { return (float)asin((double)x); }
@@ -108,8 +119,10 @@ MMD_DEV Quat axis_to_quat(const Vec3& axis, float angle) {
     float norm = m_sqrt(axis.x * axis.x + axis.y * axis.y + axis.z * axis.z);
     if (norm < kEpsF) return q_identity();
     angle *= 0.5f;
-    float s = m_sin(angle) / norm;
-    return Quat{s * axis.x, s * axis.y, s * axis.z, m_cos(angle)};
+    float sn, cs;
+    m_sincos(angle, sn, cs);
+    float s = sn / norm;
+    return Quat{s * axis.x, s * axis.y, s * axis.z, cs};
 }
 // QuaternionTo{ZXY,XYZ,YZX}, L/util/math_impl.inl:1123-1137, 1059-1073, 1107-1121.  order: 0 YZX 1 ZXY 2 XYZ
 MMD_DEV Vec3 quat_to_euler(int order, const Quat& q) {
@@ -134,9 +147,10 @@ MMD_DEV Vec3 quat_to_euler(int order, const Quat& q) {
 }
 // {ZXY,XYZ,YZX}ToQuaternion, L/util/math_impl.inl:1212-1224, 1156-1168, 1198-1210
 MMD_DEV Quat euler_to_quat(int order, const Vec3& eu) {
-    float cx = m_cos(eu.x * 0.5f), sx = m_sin(eu.x * 0.5f);
-    float cy = m_cos(eu.y * 0.5f), sy = m_sin(eu.y * 0.5f);
-    float cz = m_cos(eu.z * 0.5f), sz = m_sin(eu.z * 0.5f);
+    float cx, sx, cy, sy, cz, sz;
+    m_sincos(eu.x * 0.5f, sx, cx);
+    m_sincos(eu.y * 0.5f, sy, cy);
+    m_sincos(eu.z * 0.5f, sz, cz);
     Quat q;
     if (order == 1) {
         q.e = cx * cy * cz - sx * sy * sz;

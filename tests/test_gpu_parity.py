@@ -476,3 +476,43 @@ def test_seek_time_matches_oracle_and_golden(ctx):
     poser.PostPhysicsPosing()
     poser.Deform()
     assert_bitwise(poser.pose_image.coordinates, orc.run_time(0.7777)["pos"], "MotionPlayer.SeekTime")
+
+
+def test_empty_and_ragged_inputs(ctx):
+    """Edge cases: a model without morphs and a clip without tracks (identity pose), a model without vertices,
+    a vertex count that is not a multiple of the tile size, a slot count that is not a multiple of the slot group."""
+    from dataclasses import replace
+    from simple_mmd_renderer_b200 import synth
+    cfg = replace(synth.TINY, name="ragged", config_id=34, n_vertices=513, n_vertex_morphs=0, n_bones=7)
+    model = synth.make_model(cfg)
+    assert model["n_morphs"] == 0
+    empty_motion = dict(n_bone_tracks=0, bone_track_bone=np.zeros(0, np.int32), bone_track_key_begin=np.zeros(0, np.uint32),
+                        bone_track_key_count=np.zeros(0, np.uint32), n_bone_keys=0, bone_keys=np.zeros(0, capi.BONE_KEY),
+                        n_morph_tracks=0, morph_track_morph=np.zeros(0, np.int32), morph_track_key_begin=np.zeros(0, np.uint32),
+                        morph_track_key_count=np.zeros(0, np.uint32), n_morph_keys=0, morph_keys=np.zeros(0, capi.MORPH_KEY))
+    m = Model(ctx, model)
+    a = Motion(m, empty_motion)
+    assert a.GetLength() == 0
+    fr = Frames(m, 1, 3)
+    fr.update(a, [0, 5, 1000])
+    ref = _oracle(model, empty_motion).run_frame(5)
+    for k in range(3):
+        assert_bitwise(fr.download(k, capi.STREAM_POSITION), ref["pos"], f"identity pose slot {k}")
+        # (x - bone) + bone is not exactly x in fp32: the rest pose is reproduced to rounding, like libmmd's
+        np.testing.assert_allclose(fr.download(k, capi.STREAM_POSITION), model["position"], rtol=0, atol=1e-5)
+    motion = synth.make_motion(cfg, model)
+    a2 = Motion(m, motion)
+    fr.update(a2, [3, 30, 59])
+    orc = _oracle(model, motion)
+    for k, f in enumerate((3, 30, 59)):
+        _check_frame(fr, k, orc.run_frame(f), f"ragged frame {f}")
+    # no vertices at all: hierarchy still runs, nothing to skin
+    nov = dict(model)
+    nov.update(n_vertices=0, position=np.zeros((0, 3), np.float32), normal=np.zeros((0, 3), np.float32),
+               uv=np.zeros((0, 2), np.float32), skin_type=np.zeros(0, np.uint8), bone_id=np.zeros((0, 4), np.int32),
+               weight=np.zeros((0, 4), np.float32))
+    m0 = Model(ctx, nov)
+    f0 = Frames(m0, 1, 2)
+    f0.update(Motion(m0, motion), [3, 30])
+    assert_bitwise(f0.bone_matrices(1), orc.run_frame(30)["skin"], "bones of a vertex-less model")
+    assert f0.download(0, capi.STREAM_POSITION).shape == (0, 3)

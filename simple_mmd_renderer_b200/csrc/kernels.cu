@@ -204,7 +204,7 @@ __device__ __forceinline__ void set_local(const SlotState& S, const BoneStatic& 
 }
 
 // Poser::UpdateBoneTransform(size_t) without the IK part, L/motion/poser_impl.inl:142-166
-__device__ __noinline__ void eval_bone(const DevModel& M, const SlotState& S, int32_t b) {
+__device__ __forceinline__ void eval_bone(const DevModel& M, const SlotState& S, int32_t b) {
     const BoneStatic s = load_bone(S.bones, b);
     const Quat R = q_from(S.poseR[b]);
     const float4 T = S.poseT[b];
@@ -243,7 +243,7 @@ __device__ __forceinline__ Vec3 local_pos(const SlotState& S, int32_t b) {
 }
 
 // CCD IK, L/motion/poser_impl.inl:168-310 (the part of UpdateBoneTransform after the bone's own transform)
-__device__ __noinline__ void solve_ik(const DevModel& M, const SlotState& S, const IkDesc k) {
+__device__ __forceinline__ void solve_ik(const DevModel& M, const SlotState& S, const IkDesc k) {
     const IkLink* __restrict__ links = M.links + k.link_begin;
     const int nl = k.link_count;
     for (int i = 0; i < nl; ++i) S.ikR[S.bones[links[i].bone].link_slot] = make_float4(0.f, 0.f, 0.f, 1.f);
@@ -498,6 +498,11 @@ __global__ void __launch_bounds__(kHierCtaThreads) hierarchy_cta_kernel(DevModel
     float4* g_morphR = F.morphR + (size_t)slot * M.n_morph_slots;
     float4* g_morphT = F.morphT + (size_t)slot * M.n_morph_slots;
 
+    // tell the compiler these pointers are shared-memory addresses: plain LDS / STS instead of generic accesses
+    __builtin_assume(__isShared(s_poseR)); __builtin_assume(__isShared(s_poseT)); __builtin_assume(__isShared(s_totR));
+    __builtin_assume(__isShared(s_totT)); __builtin_assume(__isShared(s_local)); __builtin_assume(__isShared(s_ikR));
+    __builtin_assume(__isShared(s_preIK)); __builtin_assume(__isShared(s_morphR)); __builtin_assume(__isShared(s_morphT));
+    __builtin_assume(__isShared(s_bones));
     SlotState S;
     S.bones = reinterpret_cast<const BoneStatic*>(s_bones);
     S.poseR = s_poseR; S.poseT = s_poseT; S.totR = s_totR; S.totT = s_totT; S.local = s_local;
@@ -762,7 +767,8 @@ constexpr int V = (int)kVertsPerThread;
 constexpr int G = (int)kSlotGroup;    // slots one CTA evaluates together
 
 // shared memory carve-up (bytes): [stage: G tiles][palette 0: G slots][palette 1][rates 0: n_nodes_pad float4][rates 1]
-template <int LAYOUT, bool EXT>
+// PALG: global-palette models (a tile touches too many bones to stage): bone ids are global, matrices come from L2.
+template <int LAYOUT, bool EXT, bool PALG>
 __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevModel M, DevFrames F, uint32_t chunk, uint32_t n_chunks) {
     constexpr uint32_t PS = EXT ? 5u : 3u;  // float4 per staged bone
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -837,7 +843,7 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
     // q % PS of tile bone q / PS: a matrix column (0..2) or, with extensions, the rotation quaternion / dual part
     const uint32_t tb0 = __ldg(M.tile_bone_begin + tile);
     // global-palette models stage nothing: their bone ids index the slot's palette in global memory directly
-    const uint32_t npal4 = M.global_palette ? 0u : (__ldg(M.tile_bone_begin + tile + 1) - tb0) * PS;
+    const uint32_t npal4 = PALG ? 0u : (__ldg(M.tile_bone_begin + tile + 1) - tb0) * PS;
     const uint32_t n_items = npal4 * G;
     const uint32_t npad = M.n_nodes_pad;               // float4 per rate block (one float4 = the G slots of a node)
     auto item_source = [&](uint32_t i) -> uint32_t {   // bits 31:30 = slot within the group, 29 = extension array
@@ -923,7 +929,7 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
                 // slots past the end of a partial last group are computed on the clamped palette and not stored
                 const bool live = (uint32_t)f < n_live;
                 const float4* __restrict__ palf =
-                    M.global_palette ? F.palette + (size_t)min(g0 + (uint32_t)f, F.n_slots - 1u) * M.nb * 3 : pal + (size_t)f * pal4;
+                    PALG ? F.palette + (size_t)min(g0 + (uint32_t)f, F.n_slots - 1u) * M.nb * 3 : pal + (size_t)f * pal4;
                 unsigned char* stage = stage_base + (size_t)f * stage_bytes;
                 float op[3], on[3];
                 // coordinate + vertex_image (poser_impl.inl:407)
@@ -1029,9 +1035,10 @@ size_t skin_smem_bytes(const DevModel& M, int layout) {
            2 * (size_t)M.n_nodes_pad * 16;
 }
 
-template <int LAYOUT, bool EXT>
+template <int LAYOUT, bool EXT, bool PALG>
 static cudaError_t skin_opt_in(const DevModel& M) {
-    return cudaFuncSetAttribute(skin_kernel<LAYOUT, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)skin_smem_bytes(M, LAYOUT));
+    return cudaFuncSetAttribute(skin_kernel<LAYOUT, EXT, PALG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)skin_smem_bytes(M, LAYOUT));
 }
 
 cudaError_t prepare_skin_kernels(const DevModel& M) {
@@ -1042,14 +1049,17 @@ cudaError_t prepare_skin_kernels(const DevModel& M) {
         e = cudaFuncSetAttribute(hierarchy_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHierCtaSmemLimit);
         if (e != cudaSuccess) return e;
     }
+    constexpr int SOA = MMDGPU_LAYOUT_SOA_POS_NRM, I32 = MMDGPU_LAYOUT_INTERLEAVED_SOKOL32;
     if (M.extensions) {
-        e = skin_opt_in<MMDGPU_LAYOUT_SOA_POS_NRM, true>(M);
-        if (e != cudaSuccess) return e;
-        return skin_opt_in<MMDGPU_LAYOUT_INTERLEAVED_SOKOL32, true>(M);
+        if ((e = skin_opt_in<SOA, true, false>(M)) != cudaSuccess) return e;
+        return skin_opt_in<I32, true, false>(M);
     }
-    e = skin_opt_in<MMDGPU_LAYOUT_SOA_POS_NRM, false>(M);
-    if (e != cudaSuccess) return e;
-    return skin_opt_in<MMDGPU_LAYOUT_INTERLEAVED_SOKOL32, false>(M);
+    if (M.global_palette) {
+        if ((e = skin_opt_in<SOA, false, true>(M)) != cudaSuccess) return e;
+        return skin_opt_in<I32, false, true>(M);
+    }
+    if ((e = skin_opt_in<SOA, false, false>(M)) != cudaSuccess) return e;
+    return skin_opt_in<I32, false, false>(M);
 }
 
 cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, int layout, uint32_t slots_per_cta) {
@@ -1059,13 +1069,16 @@ cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, 
     const uint32_t grid = M.n_tiles * n_chunks;
     const size_t smem = skin_smem_bytes(M, layout);
     const bool soa = layout == MMDGPU_LAYOUT_SOA_POS_NRM;
-    if (M.extensions) {
-        if (soa) skin_kernel<MMDGPU_LAYOUT_SOA_POS_NRM, true><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);
-        else skin_kernel<MMDGPU_LAYOUT_INTERLEAVED_SOKOL32, true><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);
-    } else {
-        if (soa) skin_kernel<MMDGPU_LAYOUT_SOA_POS_NRM, false><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);
-        else skin_kernel<MMDGPU_LAYOUT_INTERLEAVED_SOKOL32, false><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);
-    }
+    constexpr int SOA = MMDGPU_LAYOUT_SOA_POS_NRM, I32 = MMDGPU_LAYOUT_INTERLEAVED_SOKOL32;
+#define MMDGPU_LAUNCH_SKIN(EXT, PALG)                                                                                  \
+    do {                                                                                                               \
+        if (soa) skin_kernel<SOA, EXT, PALG><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);         \
+        else skin_kernel<I32, EXT, PALG><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);             \
+    } while (0)
+    if (M.extensions) MMDGPU_LAUNCH_SKIN(true, false);
+    else if (M.global_palette) MMDGPU_LAUNCH_SKIN(false, true);
+    else MMDGPU_LAUNCH_SKIN(false, false);
+#undef MMDGPU_LAUNCH_SKIN
     return cudaGetLastError();
 }
 

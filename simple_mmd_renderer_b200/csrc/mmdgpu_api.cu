@@ -30,6 +30,9 @@ struct mmdgpu_context {
     // fused updates run key-frame sampling and the bone hierarchy of update n+1 on this stream while the skinning
     // kernel of update n still runs on `stream`
     cudaStream_t pre_stream = nullptr;
+    // same, highest priority: for models with CCD IK, whose hierarchy kernel is a long latency-bound chain that
+    // should claim SM resources as soon as CTAs of the running skinning kernel retire
+    cudaStream_t pre_stream_hi = nullptr;
     std::string err;
     uint64_t launches = 0;
     int max_smem_optin = 0;
@@ -503,6 +506,12 @@ MMDGPU_API mmdgpu_status mmdgpu_context_create(int device, void* cuda_stream_or_
         return cuda_fail(nullptr, e, "cudaEventCreate");
     if ((e = cudaStreamCreateWithFlags(&c->pre_stream, cudaStreamNonBlocking)) != cudaSuccess)
         return cuda_fail(nullptr, e, "cudaStreamCreate");
+    {
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        if ((e = cudaStreamCreateWithPriority(&c->pre_stream_hi, cudaStreamNonBlocking, greatest)) != cudaSuccess)
+            return cuda_fail(nullptr, e, "cudaStreamCreate");
+    }
     *out = c.release();
     return MMDGPU_OK;
 }
@@ -511,9 +520,11 @@ MMDGPU_API void mmdgpu_context_destroy(mmdgpu_context_t ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->pre_stream) cudaStreamSynchronize(ctx->pre_stream);
+    if (ctx->pre_stream_hi) cudaStreamSynchronize(ctx->pre_stream_hi);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->dl_stream) { cudaStreamSynchronize(ctx->dl_stream); cudaStreamDestroy(ctx->dl_stream); }
     if (ctx->pre_stream) { cudaStreamSynchronize(ctx->pre_stream); cudaStreamDestroy(ctx->pre_stream); }
+    if (ctx->pre_stream_hi) { cudaStreamSynchronize(ctx->pre_stream_hi); cudaStreamDestroy(ctx->pre_stream_hi); }
     if (ctx->dl_event) cudaEventDestroy(ctx->dl_event);
     for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
@@ -526,6 +537,7 @@ MMDGPU_API const char* mmdgpu_last_error(mmdgpu_context_t ctx) { return ctx ? ct
 MMDGPU_API mmdgpu_status mmdgpu_context_synchronize(mmdgpu_context_t ctx) {
     if (mmdgpu_status s = enter(ctx)) return s;
     CU(ctx, cudaStreamSynchronize(ctx->pre_stream));
+    CU(ctx, cudaStreamSynchronize(ctx->pre_stream_hi));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->dl_stream));
     return MMDGPU_OK;
@@ -542,6 +554,7 @@ MMDGPU_API mmdgpu_status mmdgpu_context_profile_read(mmdgpu_context_t ctx, doubl
     if (mmdgpu_status s = enter(ctx)) return s;
     if (!ms_total || !launches) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "NULL argument");
     CU(ctx, cudaStreamSynchronize(ctx->pre_stream));
+    CU(ctx, cudaStreamSynchronize(ctx->pre_stream_hi));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < MMDGPU_KERNEL_COUNT; ++i) { ms_total[i] = 0.0; launches[i] = 0; }
     for (const auto& sp : ctx->spans) {
@@ -796,6 +809,7 @@ MMDGPU_API void mmdgpu_model_destroy(mmdgpu_model_t model) {
     if (!model) return;
     cudaSetDevice(model->ctx->device);
     cudaStreamSynchronize(model->ctx->pre_stream);
+    cudaStreamSynchronize(model->ctx->pre_stream_hi);
     cudaStreamSynchronize(model->ctx->stream);
     delete model;
 }
@@ -864,6 +878,7 @@ MMDGPU_API void mmdgpu_animation_destroy(mmdgpu_animation_t a) {
     if (!a) return;
     cudaSetDevice(a->ctx->device);
     cudaStreamSynchronize(a->ctx->pre_stream);
+    cudaStreamSynchronize(a->ctx->pre_stream_hi);
     cudaStreamSynchronize(a->ctx->stream);
     delete a;
 }
@@ -936,6 +951,7 @@ MMDGPU_API void mmdgpu_frames_destroy(mmdgpu_frames_t f) {
     if (!f) return;
     cudaSetDevice(f->ctx->device);
     cudaStreamSynchronize(f->ctx->pre_stream);
+    cudaStreamSynchronize(f->ctx->pre_stream_hi);
     cudaStreamSynchronize(f->ctx->stream);
     cudaStreamSynchronize(f->ctx->dl_stream);
     delete f;
@@ -1058,17 +1074,18 @@ static mmdgpu_status update_common(mmdgpu_frames_t f, const mmdgpu_animation_t* 
     // of (palette, rates) the previous update is NOT using, so they overlap that update's skinning kernel.
     mmdgpu_context_t ctx = f->ctx;
     const int next = f->cur ^ 1;
-    if (f->skin_recorded[next]) CU(ctx, cudaStreamWaitEvent(ctx->pre_stream, f->ev_skin[next], 0));
+    cudaStream_t pre = f->model->plan.plan.iks.empty() ? ctx->pre_stream : ctx->pre_stream_hi;
+    if (f->skin_recorded[next]) CU(ctx, cudaStreamWaitEvent(pre, f->ev_skin[next], 0));
     if (f->main_dirty) {  // step-wise calls / uploads issued on the main stream since the last fused update
         CU(ctx, cudaEventRecord(f->ev_main, ctx->stream));
-        CU(ctx, cudaStreamWaitEvent(ctx->pre_stream, f->ev_main, 0));
+        CU(ctx, cudaStreamWaitEvent(pre, f->ev_main, 0));
         f->main_dirty = false;
     }
     f->select(next);
-    if (mmdgpu_status s = do_seek(f, per_instance, frames, range, stride, true, ctx->pre_stream)) return s;
+    if (mmdgpu_status s = do_seek(f, per_instance, frames, range, stride, true, pre)) return s;
     const DevModel& M = f->model->dev;
-    if (mmdgpu_status s = do_hierarchy(f, 0, M.n_waves, true, ctx->pre_stream)) return s;
-    CU(ctx, cudaEventRecord(f->ev_pre[next], ctx->pre_stream));
+    if (mmdgpu_status s = do_hierarchy(f, 0, M.n_waves, true, pre)) return s;
+    CU(ctx, cudaEventRecord(f->ev_pre[next], pre));
     CU(ctx, cudaStreamWaitEvent(ctx->stream, f->ev_pre[next], 0));
     if (mmdgpu_status s = do_skin(f)) return s;
     CU(ctx, cudaEventRecord(f->ev_skin[next], ctx->stream));

@@ -257,9 +257,11 @@ def quick_measure(ctx, stream, workload: str, steps: int = 10, warmup: int = 3) 
         motions = [Motion(m, synth.make_motion(cfg, model, instance=i)) for i in range(n_inst)]
         what = "512 instances x 1 frame per step, independent clips"
     else:
-        n_inst, n_frames = 1, 512
+        # C2's hierarchy kernel is a long latency-bound chain per slot (sequential CCD IK): it needs a larger batch
+        # to amortise (54 G at 512 slots, 64 G at 2048, 68 G at 4096 vertex-frames/s on B200)
+        n_inst, n_frames = 1, (2048 if workload == "C2" else 512)
         motions = [Motion(m, synth.make_motion(cfg, model))]
-        what = "512 consecutive-frame slots per step"
+        what = f"{n_frames} consecutive-frame slots per step"
     fr = Frames(m, n_inst, n_frames)
     rng = np.random.default_rng(7)
 

@@ -109,3 +109,51 @@ def assemble(windows, n_frames_total: int, world: int):
             raise RuntimeError(f"rank {r} delivered {got} frames, expected {hi - lo}")
         out.extend(per_rank[r])
     return out
+
+
+class BakeDriver:
+    """Offline bake of one clip on one GPU (BASELINE configs[4], this rank's frame range): evaluates `window` frames
+    per fused update and streams every window's deformed buffers to pinned host memory.  Two frames objects
+    alternate, so the device->host copy of window k overlaps the evaluation of window k+1.
+
+    sink(first_frame, n_frames, positions[n, nv, 3], normals[n, nv, 3]) is called with numpy views of the pinned
+    buffers, valid until the next-but-one window is issued.
+    """
+
+    def __init__(self, model, motion, window: int = 64):
+        import torch
+        from . import capi
+        from .poser import Frames
+        self.model, self.motion, self.window = model, motion, int(window)
+        self.capi = capi
+        self.frames = [Frames(model, 1, self.window), Frames(model, 1, self.window)]
+        nbytes = self.window * model.n_vertices * 12
+        self.host = [[torch.empty(max(nbytes, 16), dtype=torch.uint8, pin_memory=True) for _ in range(2)] for _ in range(2)]
+        self.nbytes = nbytes
+
+    def run(self, frame_lo: int, frame_hi: int, sink):
+        ctx = self.model.ctx
+        nv = self.model.n_vertices
+        pending = None  # (buffer index, first frame, n)
+        k = 0
+        for first, n in bake_windows(frame_lo, frame_hi, self.window):
+            b = k & 1
+            fr = self.frames[b]
+            fr.update_range(self.motion, [first], 1)           # slots past n hold frames beyond the range: not copied
+            if n and self.nbytes:
+                for sid, buf in zip((self.capi.STREAM_POSITION, self.capi.STREAM_NORMAL), self.host[b]):
+                    fr.download_async(0, n, sid, buf.data_ptr(), n * nv * 12)
+            if pending is not None:
+                self._deliver(pending, sink)                   # window k-1: its copy was issued before window k's work
+            pending = (b, first, n)
+            k += 1
+        if pending is not None:
+            self._deliver(pending, sink)
+
+    def _deliver(self, pending, sink):
+        b, first, n = pending
+        self.model.ctx.synchronize()
+        nv = self.model.n_vertices
+        pos = self.host[b][0][: n * nv * 12].view(dtype=__import__("torch").float32).reshape(n, nv, 3).numpy()
+        nrm = self.host[b][1][: n * nv * 12].view(dtype=__import__("torch").float32).reshape(n, nv, 3).numpy()
+        sink(first, n, pos, nrm)

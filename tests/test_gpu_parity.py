@@ -516,3 +516,25 @@ def test_empty_and_ragged_inputs(ctx):
     f0.update(Motion(m0, motion), [3, 30])
     assert_bitwise(f0.bone_matrices(1), orc.run_frame(30)["skin"], "bones of a vertex-less model")
     assert f0.download(0, capi.STREAM_POSITION).shape == (0, 3)
+
+
+def test_bake_driver_streams_windows_to_host(ctx):
+    """Offline bake of a frame range (this rank's share of BASELINE configs[4]) in windows, double-buffered against
+    the device->host copies; every delivered frame equals the oracle's."""
+    from simple_mmd_renderer_b200 import shard
+    cfg, model, motion = synth_case("tiny_full")
+    orc = _oracle(model, motion)
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    lo, hi = shard.split_range(91, 2, 1)          # the second of two ranks
+    got = {}
+
+    def sink(first, n, pos, nrm):
+        for i in range(n):
+            got[first + i] = (pos[i].copy(), nrm[i].copy())
+    shard.BakeDriver(m, a, window=8).run(lo, hi, sink)
+    assert sorted(got) == list(range(lo, hi))
+    for f in range(lo, hi, 5):
+        ref = orc.run_frame(f)
+        assert_bitwise(got[f][0], ref["pos"], f"baked frame {f} pos")
+        assert_bitwise(got[f][1], ref["nrm"], f"baked frame {f} nrm")

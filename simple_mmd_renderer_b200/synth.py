@@ -369,3 +369,116 @@ def make_motion(cfg: SynthConfig, model: dict, instance: int = 0, n_frames: int 
 def mean_morph_entries_per_vertex(model: dict) -> float:
     """e of SURVEY 8d: vertex-morph entries reachable through application slots, per vertex."""
     return float(model["n_vertex_morph_entries"]) / max(1, model["n_vertices"])
+
+
+def make_ik_zoo(seed: int = 77, n_frames: int = 40):
+    """A small rig that exercises every CCD IK branch of L/motion/poser_impl.inl:168-310: chains of 2-4 links,
+    unlimited links, FIX_X / FIX_Y / FIX_Z / FIX_ALL links, the three Euler orders (ZXY, XYZ, YZX), swapped lo / hi
+    limits, odd iteration counts, an iteration count above the 256 cap, and an IK bone that sorts before its links.
+    Returns (model, motion) in the flat layout of `capi.model_desc` / `capi.anim_desc`."""
+    rng = np.random.Generator(np.random.PCG64([SEED_BASE + 99, seed]))
+    PI = float(np.pi)
+    chains = [
+        # (n_links, iterations, angle_limit, [per link (tip-most first): None | (lo, hi)])
+        (2, 40, 2.0, [((-PI, 0, 0), (-0.0087, 0, 0)), None]),                           # FIX_X, XYZ order (classic knee)
+        (3, 15, 0.6, [((0, -1.0, 0), (0, 1.2, 0)), None, ((-0.2, -0.3, -0.4), (0.3, 0.2, 0.5))]),   # FIX_Y ; ZXY
+        (3, 33, 1.0, [((0, 0, -2.5), (0, 0, 0.4)), ((0, 0, 0), (0, 0, 0)), None]),      # FIX_Z ; FIX_ALL (skipped)
+        (4, 300, 0.35, [((-2.0, -2.0, -0.5), (2.0, 2.0, 0.5)), None, ((0.4, -0.2, -0.1), (-0.9, 0.3, 0.2)), None]),  # YZX ; swapped lo/hi
+        (2, 7, 3.5, [((-2.0, -1.0, -3.0), (2.0, 1.0, 3.0)), ((-1.0, -2.5, -1.0), (1.0, 2.5, 1.0))]),  # XYZ ; ZXY
+    ]
+    pos, parent, level, flags = [(0.0, 0.0, 0.0)], [-1], [0], [0]
+    ik_target, ik_iter, ik_angle, ik_begin, ik_count = [-1], [0], [0.0], [0], [0]
+    l_bone, l_has, l_lo, l_hi = [], [], [], []
+    bind = []
+
+    def add_bone(p, par, lvl=0, fl=0):
+        pos.append(tuple(float(x) for x in p)); parent.append(par); level.append(lvl); flags.append(fl)
+        ik_target.append(-1); ik_iter.append(0); ik_angle.append(0.0); ik_begin.append(0); ik_count.append(0)
+        return len(pos) - 1
+
+    for c, (nl, iters, angle, lims) in enumerate(chains):
+        x = -6.0 + 3.0 * c
+        ik_first = (c == 3)                       # this IK bone is created (and therefore sorts) before its links
+        ikb = add_bone((x, 1.0, 0.3), 0, 0, capi.BONE_HAS_IK) if ik_first else None
+        links = []
+        par = 0
+        for j in range(nl):                       # root-most first
+            y = 12.0 - 11.0 * j / nl
+            b = add_bone((x + 0.1 * j, y, 0.15 * ((-1) ** j)), par)
+            links.append(b)
+            bind.append(b)
+            par = b
+        tgt = add_bone((x, 1.0, 0.0), par)
+        bind.append(tgt)
+        if ikb is None:
+            ikb = add_bone((x, 1.0, 0.3), 0, 0, capi.BONE_HAS_IK)
+        ik_target[ikb] = tgt
+        ik_iter[ikb] = iters
+        ik_angle[ikb] = angle
+        ik_begin[ikb] = len(l_bone)
+        ik_count[ikb] = nl
+        for j, lim in enumerate(lims):            # tip-most first
+            l_bone.append(links[nl - 1 - j])
+            l_has.append(0 if lim is None else 1)
+            l_lo.append((0, 0, 0) if lim is None else lim[0])
+            l_hi.append((0, 0, 0) if lim is None else lim[1])
+    nb = len(pos)
+    nv = 40 * len(bind)
+    vpos = np.empty((nv, 3), np.float32)
+    bid = np.zeros((nv, 4), np.int32)
+    w = np.zeros((nv, 4), np.float32)
+    stype = np.zeros(nv, np.uint8)
+    bpos = _f32(pos)
+    for i in range(nv):
+        b = bind[i // 40]
+        vpos[i] = bpos[b] + _f32(rng.uniform(-0.5, 0.5, 3))
+        if i % 2 == 0:
+            stype[i] = capi.SKIN_BDEF1
+            bid[i, 0] = b
+            w[i, 0] = 1.0
+        else:
+            stype[i] = capi.SKIN_BDEF2
+            bid[i, 0], bid[i, 1] = b, max(0, parent[b])
+            w[i, 0] = np.float32(rng.uniform(0.1, 0.9))
+    n = _f32(rng.normal(size=(nv, 3)))
+    n /= np.sqrt((n * n).sum(1, keepdims=True))
+    model = dict(
+        n_vertices=nv, position=vpos, normal=_f32(n), uv=_f32(rng.random((nv, 2))), skin_type=stype, bone_id=bid, weight=w,
+        n_bones=nb, bone_position=bpos, bone_parent=np.asarray(parent, np.int32),
+        bone_transform_level=np.asarray(level, np.int32), bone_flags=np.asarray(flags, np.uint16),
+        bone_append_parent=np.full(nb, -1, np.int32), bone_append_ratio=np.zeros(nb, np.float32),
+        ik_target=np.asarray(ik_target, np.int32), ik_iterations=np.asarray(ik_iter, np.int32),
+        ik_angle_limit=_f32(ik_angle), ik_link_begin=np.asarray(ik_begin, np.uint32), ik_link_count=np.asarray(ik_count, np.uint32),
+        n_ik_links=len(l_bone), ik_link_bone=np.asarray(l_bone, np.int32), ik_link_has_limit=np.asarray(l_has, np.uint8),
+        ik_link_lo=_f32(l_lo).reshape(-1, 3), ik_link_hi=_f32(l_hi).reshape(-1, 3),
+        n_morphs=0, morph_type=np.zeros(0, np.uint8), morph_entry_begin=np.zeros(0, np.uint32),
+        morph_entry_count=np.zeros(0, np.uint32),
+        n_vertex_morph_entries=0, vertex_morph_entries=np.zeros(0, capi.VERTEX_MORPH_ENTRY),
+        n_uv_morph_entries=0, uv_morph_entries=np.zeros(0, capi.UV_MORPH_ENTRY),
+        n_bone_morph_entries=0, bone_morph_entries=np.zeros(0, capi.BONE_MORPH_ENTRY),
+        n_group_morph_entries=0, group_morph_entries=np.zeros(0, capi.GROUP_MORPH_ENTRY),
+    )
+    # motion: every bone keyed every 4 frames; IK bones get translations that pull the targets around
+    t_bone, t_begin, t_count, chunks, total = [], [], [], [], 0
+    for b in range(nb):
+        frames = np.arange(0, n_frames + 1, 4, dtype=np.uint32)
+        k = frames.size
+        keys = np.zeros(k, capi.BONE_KEY)
+        keys["frame"] = frames
+        q = np.concatenate([_f32(rng.uniform(-0.3, 0.3, (k, 3))), np.ones((k, 1), np.float32)], 1)
+        keys["rotation"] = _f32(q / np.sqrt((q * q).sum(1, keepdims=True, dtype=np.float32)))
+        if flags[b] & capi.BONE_HAS_IK:
+            keys["translation"] = _f32(rng.uniform(-2.5, 2.5, (k, 3)))
+        interp = rng.integers(0, 128, (k, 4, 4)).astype(np.int8)
+        keys["interp"] = interp
+        t_bone.append(b); t_begin.append(total); t_count.append(k); total += k
+        chunks.append(keys)
+    bone_keys = np.concatenate(chunks)
+    motion = dict(
+        n_bone_tracks=len(t_bone), bone_track_bone=np.asarray(t_bone, np.int32),
+        bone_track_key_begin=np.asarray(t_begin, np.uint32), bone_track_key_count=np.asarray(t_count, np.uint32),
+        n_bone_keys=bone_keys.size, bone_keys=bone_keys,
+        n_morph_tracks=0, morph_track_morph=np.zeros(0, np.int32), morph_track_key_begin=np.zeros(0, np.uint32),
+        morph_track_key_count=np.zeros(0, np.uint32), n_morph_keys=0, morph_keys=np.zeros(0, capi.MORPH_KEY),
+    )
+    return model, motion

@@ -49,6 +49,10 @@ def synth_case(name: str):
     """(config, model arrays, motion arrays) for a named synthetic config, cached per session."""
     from simple_mmd_renderer_b200 import synth
     if name not in _cache:
+        if name == "ik_zoo":            # hand-built rig that exercises every CCD IK branch
+            model, motion = synth.make_ik_zoo()
+            _cache[name] = (None, model, motion)
+            return _cache[name]
         cfg = synth.CONFIGS[name]
         model = synth.make_model(cfg)
         motion = synth.make_motion(cfg, model)

@@ -22,6 +22,7 @@ CASES = {
     "tiny": [0, 1, 13, 30, 59, 60, 200],
     "tiny_full": [0, 1, 2, 7, 17, 30, 42, 45, 63, 88, 89, 90, 500],
     "small": [0, 59, 119],
+    "ik_zoo": list(range(0, 41, 3)),     # synth.make_ik_zoo(): every CCD IK branch
 }
 STRIDE = 53
 TIMES = [0.0, 1.0 / 30.0, 0.0123, 0.5, 0.7777, 1.99, 2.5, 17.0]   # seconds, MotionPlayer::SeekTime
@@ -47,9 +48,12 @@ def main():
     oracle.build()
     assert oracle.have_reference(), "the reference harness needs /root/reference"
     for name, frames in CASES.items():
-        cfg = synth.CONFIGS[name]
-        model = synth.make_model(cfg)
-        motion = synth.make_motion(cfg, model)
+        if name == "ik_zoo":
+            model, motion = synth.make_ik_zoo()
+        else:
+            cfg = synth.CONFIGS[name]
+            model = synth.make_model(cfg)
+            motion = synth.make_motion(cfg, model)
         ref = oracle.Reference(model, motion)
         out = {"frames": np.asarray(frames, np.uint32), "input_digest": np.asarray(input_digest(model, motion)),
                "stride": np.asarray(STRIDE)}

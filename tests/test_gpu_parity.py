@@ -268,7 +268,22 @@ def test_device_view_and_async_download(ctx):
         assert_bitwise(t[k].cpu().numpy(), want, f"view slot {k}")
 
 
-@pytest.mark.parametrize("name", ["tiny", "tiny_full", "small"])
+def test_every_ccd_ik_branch(ctx):
+    """synth.make_ik_zoo(): FIX_X / FIX_Y / FIX_Z / FIX_ALL links, ZXY / XYZ / YZX Euler orders, 2-4 link chains, swapped
+    limits, odd and capped iteration counts, an IK bone sorting before its links — bit-exact against the oracle
+    on every frame (CCD amplifies any rounding difference through its clamps and branches)."""
+    _, model, motion = synth_case("ik_zoo")
+    orc = _oracle(model, motion)
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    frames = list(range(0, 45))
+    fr = Frames(m, 1, len(frames))
+    fr.update(a, frames)
+    for k, f in enumerate(frames):
+        _check_frame(fr, k, orc.run_frame(f), f"ik_zoo frame {f}")
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_full", "small", "ik_zoo"])
 def test_gpu_matches_libmmd_golden_fixtures(ctx, name):
     """The committed libmmd-generated fixtures (tests/golden), independent of the C restatement."""
     from golden_util import check_against_golden, load_golden

@@ -8,7 +8,7 @@ import oracle
 from conftest import assert_bitwise, synth_case
 from golden_util import check_against_golden, input_digest, load_golden, sha
 
-CASES = ["tiny", "tiny_full", "small"]
+CASES = ["tiny", "tiny_full", "small", "ik_zoo"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -21,6 +21,8 @@ def test_generator_is_deterministic(name):
 
 @pytest.mark.parametrize("name", CASES)
 def test_restatement_matches_golden(name):
+    """ik_zoo covers what the random configs do not: FIX_Y / FIX_Z / FIX_ALL links, the YZX Euler order, 3- and
+    4-link chains, swapped limits, the 256-iteration cap, an IK bone that sorts before its links."""
     cfg, model, motion = synth_case(name)
     g = load_golden(name)
     port = oracle.Restatement(model, motion)
@@ -39,7 +41,8 @@ def test_restatement_matches_golden(name):
 
 
 @pytest.mark.skipif(not oracle.have_reference(), reason="libmmd reference harness not built (needs /root/reference)")
-@pytest.mark.parametrize("name,frames", [("tiny", range(0, 70, 3)), ("tiny_full", range(0, 100)), ("small", [0, 7, 60, 119])])
+@pytest.mark.parametrize("name,frames", [("tiny", range(0, 70, 3)), ("tiny_full", range(0, 100)), ("small", [0, 7, 60, 119]),
+                                         ("ik_zoo", range(0, 45))])
 def test_restatement_matches_libmmd_bitwise(name, frames):
     cfg, model, motion = synth_case(name)
     ref = oracle.Reference(model, motion)

@@ -37,7 +37,7 @@ def test_normalize_rewrite_matches_oracle(name):
     np.testing.assert_array_equal(pw[two & plain, 0].view(np.uint32), w[two & plain, 0].view(np.uint32))
 
 
-@pytest.mark.parametrize("name", ["tiny", "tiny_full", "small"])
+@pytest.mark.parametrize("name", ["tiny", "tiny_full", "small", "ik_zoo"])
 def test_normalize_and_ik_class_match_libmmd_golden(name):
     cfg, model, motion = synth_case(name)
     g = load_golden(name)
@@ -164,7 +164,7 @@ def _op_sets(model, kind, b):
     return R, W
 
 
-@pytest.mark.parametrize("name", ["tiny", "tiny_full", "small", "C2"])
+@pytest.mark.parametrize("name", ["tiny", "tiny_full", "small", "C2", "ik_zoo"])
 def test_wave_schedule_preserves_sequential_semantics(name):
     """Every op must observe, in the wave program, exactly the writers it observes in libmmd's sequential program,
     and ops that share a wave must not touch each other's state."""

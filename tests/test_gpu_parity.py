@@ -553,3 +553,33 @@ def test_bake_driver_streams_windows_to_host(ctx):
         ref = orc.run_frame(f)
         assert_bitwise(got[f][0], ref["pos"], f"baked frame {f} pos")
         assert_bitwise(got[f][1], ref["nrm"], f"baked frame {f} nrm")
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_randomized_configs(ctx, seed):
+    """Differential test over varied rigs: bone / vertex / morph counts, IK chains, post-physics share, binding
+    pattern and the stress features are drawn per seed; three frames each, bit-exact against the oracle."""
+    from dataclasses import replace
+    from simple_mmd_renderer_b200 import synth
+    rng = np.random.default_rng(1000 + seed)
+    ik = int(rng.integers(0, 3))
+    cfg = replace(synth.TINY_FULL, name=f"rand{seed}", config_id=200 + seed,
+                  n_bones=int(rng.integers(4 * ik + 12, 160)), n_vertices=int(rng.integers(1, 2600)),
+                  n_vertex_morphs=int(rng.integers(0, 24)), n_frames=int(rng.integers(8, 80)),
+                  binding=("coherent", "random")[int(rng.integers(0, 2))], ik_chains=ik,
+                  n_group_morphs=int(rng.integers(0, 3)), n_bone_morphs=int(rng.integers(0, 3)),
+                  n_uv_morphs=int(rng.integers(0, 3)), post_physics_frac=float(rng.choice([0.0, 0.1, 0.4])),
+                  stress=bool(rng.integers(0, 2)), morph_run_frac=float(rng.choice([0.018, 0.2])),
+                  morph_scatter_frac=float(rng.choice([0.002, 0.05])))
+    if cfg.n_group_morphs and cfg.n_vertex_morphs + cfg.n_uv_morphs + cfg.n_bone_morphs < 3:
+        cfg = replace(cfg, n_group_morphs=0)      # a group needs three distinct children
+    model = synth.make_model(cfg)
+    motion = synth.make_motion(cfg, model)
+    orc = _oracle(model, motion)
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    frames = [0, cfg.n_frames // 2 + 1, cfg.n_frames]
+    fr = Frames(m, 1, 3)
+    fr.update(a, frames)
+    for k, f in enumerate(frames):
+        _check_frame(fr, k, orc.run_frame(f), f"{cfg.name} frame {f}")

@@ -657,10 +657,12 @@ __device__ __forceinline__ float4 f4_scale(const float4& a, float s) { return ma
 __device__ __forceinline__ float4 f4_add(const float4& a, const float4& b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
 // One vertex.  ids: 4 x u16 tile-local bone indices (type in bits 15:13 of id0); w: BDEF2 uses w.x, BDEF4 all four.
+// Deliberately NOT inlined: the skinning kernel calls it V x G = 16 times per slot group, and the fully inlined
+// kernel stalled a quarter of its issue slots on instruction fetch.  Results come back in registers.
+struct Skinned { float px, py, pz, nx, ny, nz; };
 template <int PS>
-__device__ __forceinline__ void skin_vertex(const float4* __restrict__ pal, uint32_t ids_lo, uint32_t ids_hi,
-                                            const float4& w, float px, float py, float pz, float nx, float ny,
-                                            float nz, float* __restrict__ op, float* __restrict__ on) {
+__device__ __noinline__ Skinned skin_vertex(const float4* __restrict__ pal, uint32_t ids_lo, uint32_t ids_hi, float4 w,
+                                            float px, float py, float pz, float nx, float ny, float nz) {
     const uint32_t type = (ids_lo >> 13) & 7u;
     const uint32_t id0 = ids_lo & 0x1FFFu, id1 = ids_lo >> 16;
     Col3 Mx = pal_load<PS>(pal, id0);
@@ -680,12 +682,14 @@ __device__ __forceinline__ void skin_vertex(const float4* __restrict__ pal, uint
         Mx.c2 = f4_add(f4_add(f4_add(f4_scale(Mx.c2, w.x), f4_scale(B.c2, w.y)), f4_scale(C.c2, w.z)), f4_scale(D.c2, w.w));
     }
     // transform: v0*m00 + v1*m10 + v2*m20 + m30 ; rotate: without the translation row
-    op[0] = px * Mx.c0.x + py * Mx.c0.y + pz * Mx.c0.z + Mx.c0.w;
-    op[1] = px * Mx.c1.x + py * Mx.c1.y + pz * Mx.c1.z + Mx.c1.w;
-    op[2] = px * Mx.c2.x + py * Mx.c2.y + pz * Mx.c2.z + Mx.c2.w;
-    on[0] = nx * Mx.c0.x + ny * Mx.c0.y + nz * Mx.c0.z;
-    on[1] = nx * Mx.c1.x + ny * Mx.c1.y + nz * Mx.c1.z;
-    on[2] = nx * Mx.c2.x + ny * Mx.c2.y + nz * Mx.c2.z;
+    Skinned r;
+    r.px = px * Mx.c0.x + py * Mx.c0.y + pz * Mx.c0.z + Mx.c0.w;
+    r.py = px * Mx.c1.x + py * Mx.c1.y + pz * Mx.c1.z + Mx.c1.w;
+    r.pz = px * Mx.c2.x + py * Mx.c2.y + pz * Mx.c2.z + Mx.c2.w;
+    r.nx = nx * Mx.c0.x + ny * Mx.c0.y + nz * Mx.c0.z;
+    r.ny = nx * Mx.c1.x + ny * Mx.c1.y + nz * Mx.c1.z;
+    r.nz = nx * Mx.c2.x + ny * Mx.c2.y + nz * Mx.c2.z;
+    return r;
 }
 
 // ---- extensions (parity unpinned: libmmd implements none of these) -----------------------------
@@ -939,8 +943,11 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
                               nz[j], op, on);
                 else if (EXT && type == kDevQdef)
                     skin_qdef(palf, ilo[j], ihi[j], wv[j], qx, qy, qz, nx[j], ny[j], nz[j], op, on);
-                else
-                    skin_vertex<(int)PS>(palf, ilo[j], ihi[j], wv[j], qx, qy, qz, nx[j], ny[j], nz[j], op, on);
+                else {
+                    const Skinned r = skin_vertex<(int)PS>(palf, ilo[j], ihi[j], wv[j], qx, qy, qz, nx[j], ny[j], nz[j]);
+                    op[0] = r.px; op[1] = r.py; op[2] = r.pz;
+                    on[0] = r.nx; on[1] = r.ny; on[2] = r.nz;
+                }
                 float mu = su, mv = sv_;
                 if (EXT) {
                     // applied UV morphs: uv = uv + offset.xy * rate, application order

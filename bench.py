@@ -476,7 +476,9 @@ def run_mmdgpu(args):
                          "note": "static streams are read once per tile and slot run, so real DRAM traffic (`traffic`, "
                                  "ncu) is far below the algorithmic bytes and `frac` can exceed 1; the write-only floor "
                                  "is 24 B per vertex-frame",
-                         "output_write_gbs": 24.0 * nv * slots / (skin_ms * 1e-3) / 1e9 if skin_ms > 0 else None},
+                         "output_write_gbs": 24.0 * nv * slots / (skin_ms * 1e-3) / 1e9 if skin_ms > 0 else None,
+                         "dram_gbs_from_traffic": (ncu_traffic_bytes(args.workload) / (skin_ms * 1e-3) / 1e9)
+                         if (skin_ms > 0 and ncu_traffic_bytes(args.workload) and slots == 128 and world == 1) else None},
             "kernel_ms_per_step": {"pose_sample": kernel_ms[0] / args.steps, "hierarchy": kernel_ms[1] / args.steps,
                                    "skin": kernel_ms[2] / args.steps},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

@@ -660,9 +660,10 @@ __device__ __forceinline__ float4 f4_add(const float4& a, const float4& b) { ret
 // Deliberately NOT inlined: the skinning kernel calls it V x G = 16 times per slot group, and the fully inlined
 // kernel stalled a quarter of its issue slots on instruction fetch.  Results come back in registers.
 struct Skinned { float px, py, pz, nx, ny, nz; };
-template <int PS>
+template <int PS, bool PAL_SHARED>
 __device__ __noinline__ Skinned skin_vertex(const float4* __restrict__ pal, uint32_t ids_lo, uint32_t ids_hi, float4 w,
                                             float px, float py, float pz, float nx, float ny, float nz) {
+    if (PAL_SHARED) __builtin_assume(__isShared(pal));  // staged palette: shared-memory loads, not generic ones
     const uint32_t type = (ids_lo >> 13) & 7u;
     const uint32_t id0 = ids_lo & 0x1FFFu, id1 = ids_lo >> 16;
     Col3 Mx = pal_load<PS>(pal, id0);
@@ -944,7 +945,7 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
                 else if (EXT && type == kDevQdef)
                     skin_qdef(palf, ilo[j], ihi[j], wv[j], qx, qy, qz, nx[j], ny[j], nz[j], op, on);
                 else {
-                    const Skinned r = skin_vertex<(int)PS>(palf, ilo[j], ihi[j], wv[j], qx, qy, qz, nx[j], ny[j], nz[j]);
+                    const Skinned r = skin_vertex<(int)PS, !PALG>(palf, ilo[j], ihi[j], wv[j], qx, qy, qz, nx[j], ny[j], nz[j]);
                     op[0] = r.px; op[1] = r.py; op[2] = r.pz;
                     on[0] = r.nx; on[1] = r.ny; on[2] = r.nz;
                 }

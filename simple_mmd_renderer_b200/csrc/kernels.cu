@@ -762,8 +762,11 @@ __device__ __forceinline__ void skin_qdef(const float4* __restrict__ pal, uint32
 }
 
 // shared memory carve-up (bytes): [stage 0][stage 1][palette 0][palette 1][rates 0][rates 1]
+// Staging tile per slot.  The sokol32 layout needs none: its 32-byte records are whole DRAM sectors, so threads store
+// them straight to global memory (every sector is written exactly once, in full); the 12-byte SoA records would be
+// partial-sector writes and go through a shared-memory tile + bulk copy instead.
 __host__ __device__ inline uint32_t skin_stage_bytes(int layout, bool ext) {
-    return layout == MMDGPU_LAYOUT_SOA_POS_NRM ? kTileVerts * (ext ? 32u : 24u) : kTileVerts * 32u;  // ext SoA: + UV plane
+    return layout == MMDGPU_LAYOUT_SOA_POS_NRM ? kTileVerts * (ext ? 32u : 24u) : 0u;  // ext SoA: + UV plane
 }
 __host__ __device__ inline uint32_t skin_pal_bytes(uint32_t max_tile_bones, bool ext) { return max_tile_bones * (ext ? 80u : 48u); }
 
@@ -917,7 +920,7 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
                     iz[f] = iz[f] + ent.z * r[f];
                 }
             }
-            if (j == 0) {
+            if (j == 0 && LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) {
                 // the staging tiles are single-buffered: the previous group's bulk copies must have read them
                 if (tid == 0) bulk_wait_read_all();
                 __syncthreads();
@@ -970,9 +973,9 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
                 } else {
                     // main.cpp:838-859: Vertex{pos*0.1f, normal, uv}
                     const float mmd_to_meter = 0.1f;
-                    float4* sv = reinterpret_cast<float4*>(stage) + orig[j] * 2u;
-                    sv[0] = make_float4(op[0] * mmd_to_meter, op[1] * mmd_to_meter, op[2] * mmd_to_meter, on[0]);
-                    sv[1] = make_float4(on[1], on[2], mu, mv);
+                    float4* sv = F.out_inter + ((size_t)(g0 + f) * M.nv_pad + (size_t)tile * kTileVerts + orig[j]) * 2u;
+                    __stcs(sv, make_float4(op[0] * mmd_to_meter, op[1] * mmd_to_meter, op[2] * mmd_to_meter, on[0]));
+                    __stcs(sv + 1, make_float4(on[1], on[2], mu, mv));
                 }
             }
         }
@@ -988,10 +991,10 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
             if (tid < npad) nrt[tid] = rf;
             for (uint32_t i = tid + kSkinThreads; i < npad; i += kSkinThreads) nrt[i] = __ldg(gr + i);
         }
-        // ---- hand the staged tiles to the bulk-copy engine
-        fence_proxy_async_smem();  // my staging writes become visible to the async proxy
+        // ---- hand the staged tiles to the bulk-copy engine (the barrier also orders the palette double buffer)
+        if (LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) fence_proxy_async_smem();  // staging writes -> visible to the async proxy
         __syncthreads();
-        if (tid == 0) {
+        if (tid == 0 && LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) {
             for (uint32_t f = 0; f < n_live; ++f) {
                 unsigned char* stage = stage_base + (size_t)f * stage_bytes;
                 const size_t vbase = (size_t)(g0 + f) * M.nv_pad + (size_t)tile * kTileVerts;
@@ -999,8 +1002,6 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
                     bulk_s2g(F.out_pos + vbase * 3, stage, kTileVerts * 12u);
                     bulk_s2g(F.out_nrm + vbase * 3, stage + kTileVerts * 12u, kTileVerts * 12u);
                     if (EXT) bulk_s2g(F.out_uv + vbase, stage + kTileVerts * 24u, kTileVerts * 8u);
-                } else {
-                    bulk_s2g(F.out_inter + vbase * 2, stage, kTileVerts * 32u);
                 }
             }
             bulk_commit();

@@ -16,7 +16,7 @@ static_assert(kVertsPerThread == 2 || kVertsPerThread == 4, "vector loads are wr
 // of a warp step share a skinning type and a morph entry count.
 struct DevModel {
     uint32_t nv, nv_pad, nb, nm;
-    uint32_t n_nodes, n_nodes_pad;  // morph application slots; padded to a multiple of 4, >= n_nodes + 1
+    uint32_t n_nodes, n_nodes_pad;  // morph application slots; padded to a multiple of 4, >= n_nodes + 1 (the always-zero slot)
     uint32_t n_tiles, max_tile_bones;
     uint32_t global_palette;        // 1: tiles touch too many bones to stage; bone ids are global and the palette is read from HBM / L2
     // vertex streams (nv_pad entries each, storage order)
@@ -26,14 +26,14 @@ struct DevModel {
     const float2* uv;
     const uint16_t* orig;    // per storage position: PMX index within the tile
     const uint2* ell_hdr;    // per 32-lane group (tile, step, warp): (first entry, rounds)
-    const float4* ell_ent;   // (offset.xyz, bit-cast application slot); entry (round k, lane l) at base + 32 k + l
+    const float4* ell_ent;   // (offset.xyz, byte offset of the slot's float4 of rates); entry (round k, lane l) at base + 32 k + l
     const uint32_t* tile_bone_begin;  // n_tiles + 1
     const uint16_t* tile_bones;       // distinct bones of each tile
     // extension streams (NULL in libmmd-exact mode)
     uint32_t extensions;
     const float4* sdef;        // 3 per storage position: C, cr0, cr1 (spherical deform)
     const uint2* uv_ell_hdr;   // UV-morph sliced ELL, same group structure as ell_hdr
-    const float4* uv_ell_ent;  // (du, dv, byte offset of the application slot's rate, unused)
+    const float4* uv_ell_ent;  // (du, dv, byte offset of the slot's float4 of rates, unused)
     // bones
     const BoneStatic* bones;
     const IkDesc* iks;
@@ -52,7 +52,6 @@ struct DevModel {
     const int32_t* depth_begin;
     uint32_t n_depths;
     // bone morphs grouped by bone
-    const int32_t* morph_bones;
     const int32_t* bone_morph_row;
     const BoneMorphEntry* bone_morph_entries;
 };
@@ -80,7 +79,7 @@ struct DevFrames {
     float4* poseR;      // [slot][nb]   BoneImage::rotation_
     float4* poseT;      // [slot][nb]   BoneImage::translation_ (w unused)
     float* rate;        // [slot][nm]   Poser::morph_rates_
-    float* node_rate;   // [slot][n_nodes_pad]  rate of every application slot, 0 = skipped
+    float* node_rate;   // [slot / 4][n_nodes_pad][slot % 4]  rate of every application slot, 0 = skipped
     float4* totR;       // [slot][nb]
     float4* totT;       // [slot][nb]
     float* local;       // [slot][nb][12]  rows 0..3 x cols 0..2 of BoneImage::local_matrix_

@@ -299,7 +299,6 @@ mmdgpu_status upload_model(mmdgpu_model* m) {
     CU(ctx, upload(ctx, m->mem, p.nodes_by_depth, &D.nodes_by_depth));
     CU(ctx, upload(ctx, m->mem, p.depth_begin, &D.depth_begin));
     D.n_depths = p.depth_begin.empty() ? 0u : uint32_t(p.depth_begin.size() - 1);
-    CU(ctx, upload(ctx, m->mem, p.morph_bones, &D.morph_bones));
     CU(ctx, upload(ctx, m->mem, p.bone_morph_row, &D.bone_morph_row));
     CU(ctx, upload(ctx, m->mem, p.bone_morph_entries, &D.bone_morph_entries));
     CU(ctx, cudaStreamSynchronize(ctx->stream));  // the staging vectors above die with this frame

@@ -125,3 +125,64 @@ def test_pmx21_qdef_is_accepted_and_pmx20_qdef_rejected():
     with pytest.raises(MmdGpuError) as e:
         HostPlan(pmx_bytes=pmxio.write_pmx(_representable(model), version=2.0))
     assert e.value.status == capi.ERR_PARSE
+
+
+def test_parsers_survive_corrupted_streams():
+    """Robustness: truncated and bit-flipped PMX / VMD streams must come back as a status code (or parse, when the
+    damage hit a field that does not matter), never as a crash or a hang.  libmmd's readers throw or read out of
+    bounds on such input."""
+    cfg, model, motion = synth_case("tiny_full")
+    pmx = pmxio.write_pmx(_representable(model), version=2.1)
+    vmd = pmxio.write_vmd(_representable_motion(motion))
+    plan = HostPlan(pmx_bytes=pmx)
+    rng = np.random.default_rng(123)
+    outcomes = {"ok": 0, "err": 0}
+    for trial in range(150):
+        buf = bytearray(pmx)
+        mode = trial % 3
+        if mode == 0:
+            buf = buf[: int(rng.integers(0, len(buf)))]
+        elif mode == 1:
+            for _ in range(int(rng.integers(1, 6))):
+                buf[int(rng.integers(0, len(buf)))] = int(rng.integers(0, 256))
+        else:   # corrupt a count / index field region near the start of a section
+            at = int(rng.integers(0, min(len(buf), 4096)))
+            buf[at:at + 4] = bytes(int(x) for x in rng.integers(0, 256, 4))
+        try:
+            HostPlan(pmx_bytes=bytes(buf)).close()
+            outcomes["ok"] += 1
+        except MmdGpuError as e:
+            assert e.status in (capi.ERR_PARSE, capi.ERR_BAD_INDEX, capi.ERR_INVALID_ARG, capi.ERR_UNSUPPORTED, capi.ERR_OOM)
+            outcomes["err"] += 1
+    assert outcomes["err"] > 20
+    for trial in range(100):
+        buf = bytearray(vmd)
+        if trial % 2 == 0:
+            buf = buf[: int(rng.integers(0, len(buf)))]
+        else:
+            for _ in range(int(rng.integers(1, 6))):
+                buf[int(rng.integers(0, len(buf)))] = int(rng.integers(0, 256))
+        try:
+            plan.anim_from_vmd(bytes(buf))
+        except MmdGpuError as e:
+            assert e.status in (capi.ERR_PARSE, capi.ERR_BAD_INDEX, capi.ERR_INVALID_ARG)
+
+
+def test_host_code_under_address_and_ub_sanitizers(tmp_path):
+    """tools/fuzz_host.cc: PMX / VMD parsing, plan building and motion flattening compiled with
+    -fsanitize=address,undefined and driven with valid, truncated and bit-flipped streams."""
+    import subprocess
+    from conftest import ROOT
+    cfg, model, motion = synth_case("tiny_full")
+    (tmp_path / "m.pmx").write_bytes(pmxio.write_pmx(_representable(model), version=2.1))
+    (tmp_path / "m.vmd").write_bytes(pmxio.write_vmd(_representable_motion(motion)))
+    exe = tmp_path / "fuzz_host"
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                        f"-I{ROOT}/include", f"{ROOT}/tools/fuzz_host.cc", f"{ROOT}/simple_mmd_renderer_b200/csrc/host_plan.cpp",
+                        f"{ROOT}/simple_mmd_renderer_b200/csrc/pmx_vmd.cpp", "-o", str(exe)], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("sanitizer runtime not available: " + r.stderr[-200:])
+    r = subprocess.run([str(exe), str(tmp_path / "m.pmx"), str(tmp_path / "m.vmd"), "300"], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "no sanitizer report" in r.stdout

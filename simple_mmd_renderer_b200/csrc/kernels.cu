@@ -693,6 +693,53 @@ __device__ __noinline__ Skinned skin_vertex(const float4* __restrict__ pal, uint
     return r;
 }
 
+// NS slots of one vertex in one call: the id / weight decode is shared and the NS blends are independent
+// instruction streams the scheduler can interleave.  pal points at slot 0's palette, the others follow at pal4.
+template <int NS> struct SkinnedN { Skinned s[NS]; };
+template <int NS> struct MorphedN { float x[NS], y[NS], z[NS]; };
+template <int PS, bool PAL_SHARED, int NS>
+__device__ __noinline__ SkinnedN<NS> skin_vertex_n(const float4* __restrict__ pal, uint32_t pal4, uint32_t ids_lo, uint32_t ids_hi,
+                                                   float4 w, MorphedN<NS> q, float nx, float ny, float nz) {
+    if (PAL_SHARED) __builtin_assume(__isShared(pal));
+    const uint32_t type = (ids_lo >> 13) & 7u;
+    const uint32_t id0 = ids_lo & 0x1FFFu, id1 = ids_lo >> 16;
+    Col3 Mx[NS];
+#pragma unroll
+    for (int f = 0; f < NS; ++f) Mx[f] = pal_load<PS>(pal + (size_t)f * pal4, id0);
+    if (type == kDevBdef2) {
+        const float l = w.x, om = 1.0f - w.x;
+#pragma unroll
+        for (int f = 0; f < NS; ++f) {
+            const Col3 B = pal_load<PS>(pal + (size_t)f * pal4, id1);
+            Mx[f].c0 = f4_add(f4_scale(B.c0, om), f4_scale(Mx[f].c0, l));
+            Mx[f].c1 = f4_add(f4_scale(B.c1, om), f4_scale(Mx[f].c1, l));
+            Mx[f].c2 = f4_add(f4_scale(B.c2, om), f4_scale(Mx[f].c2, l));
+        }
+    } else if (type == kDevBdef4) {
+        const uint32_t id2 = ids_hi & 0xFFFFu, id3 = ids_hi >> 16;
+#pragma unroll
+        for (int f = 0; f < NS; ++f) {
+            const float4* pf = pal + (size_t)f * pal4;
+            const Col3 B = pal_load<PS>(pf, id1), C = pal_load<PS>(pf, id2), D = pal_load<PS>(pf, id3);
+            Mx[f].c0 = f4_add(f4_add(f4_add(f4_scale(Mx[f].c0, w.x), f4_scale(B.c0, w.y)), f4_scale(C.c0, w.z)), f4_scale(D.c0, w.w));
+            Mx[f].c1 = f4_add(f4_add(f4_add(f4_scale(Mx[f].c1, w.x), f4_scale(B.c1, w.y)), f4_scale(C.c1, w.z)), f4_scale(D.c1, w.w));
+            Mx[f].c2 = f4_add(f4_add(f4_add(f4_scale(Mx[f].c2, w.x), f4_scale(B.c2, w.y)), f4_scale(C.c2, w.z)), f4_scale(D.c2, w.w));
+        }
+    }
+    SkinnedN<NS> r;
+#pragma unroll
+    for (int f = 0; f < NS; ++f) {
+        const Col3& A = Mx[f];
+        r.s[f].px = q.x[f] * A.c0.x + q.y[f] * A.c0.y + q.z[f] * A.c0.z + A.c0.w;
+        r.s[f].py = q.x[f] * A.c1.x + q.y[f] * A.c1.y + q.z[f] * A.c1.z + A.c1.w;
+        r.s[f].pz = q.x[f] * A.c2.x + q.y[f] * A.c2.y + q.z[f] * A.c2.z + A.c2.w;
+        r.s[f].nx = nx * A.c0.x + ny * A.c0.y + nz * A.c0.z;
+        r.s[f].ny = nx * A.c1.x + ny * A.c1.y + nz * A.c1.z;
+        r.s[f].nz = nx * A.c2.x + ny * A.c2.y + nz * A.c2.z;
+    }
+    return r;
+}
+
 // ---- extensions (parity unpinned: libmmd implements none of these) -----------------------------
 __device__ __forceinline__ void quat_rotate(const float4& q, float vx, float vy, float vz, float* o) {
     // v' = v + 2 * cross(q.xyz, cross(q.xyz, v) + q.w * v)
@@ -776,6 +823,9 @@ constexpr int G = (int)kSlotGroup;    // slots one CTA evaluates together
 
 // shared memory carve-up (bytes): [stage: G tiles][palette 0: G slots][palette 1][rates 0: n_nodes_pad float4][rates 1]
 // PALG: global-palette models (a tile touches too many bones to stage): bone ids are global, matrices come from L2.
+// slots skinned per skin_vertex_n call: 2 measured best (1: -3.4 %, 4: spills, -11 %; profiles/r01_experiments.md)
+constexpr int kSkinCallSlots = 2;
+static_assert(kSlotGroup % kSkinCallSlots == 0, "a slot group is a whole number of skin calls");
 template <int LAYOUT, bool EXT, bool PALG>
 __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevModel M, DevFrames F, uint32_t chunk, uint32_t n_chunks) {
     constexpr uint32_t PS = EXT ? 5u : 3u;  // float4 per staged bone
@@ -932,6 +982,34 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
                 const float2 t = __ldg(M.uv + v0 + j);
                 su = t.x; sv_ = t.y;
             }
+            if (!EXT && !PALG) {
+                constexpr int NS = kSkinCallSlots;
+#pragma unroll
+                for (int f = 0; f < G; f += NS) {
+                    MorphedN<NS> q;
+#pragma unroll
+                    for (int h = 0; h < NS; ++h) { q.x[h] = px[j] + ix[f + h]; q.y[h] = py[j] + iy[f + h]; q.z[h] = pz[j] + iz[f + h]; }
+                    const SkinnedN<NS> rn = skin_vertex_n<(int)PS, true, NS>(pal + (size_t)f * pal4, pal4, ilo[j], ihi[j], wv[j], q,
+                                                                             nx[j], ny[j], nz[j]);
+#pragma unroll
+                    for (int h = 0; h < NS; ++h) {
+                        if ((uint32_t)(f + h) >= n_live) continue;
+                        const Skinned& r = rn.s[h];
+                        if (LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) {
+                            unsigned char* stage = stage_base + (size_t)(f + h) * stage_bytes;
+                            float* sp = reinterpret_cast<float*>(stage) + orig[j] * 3u;
+                            float* sn = reinterpret_cast<float*>(stage + kTileVerts * 12u) + orig[j] * 3u;
+                            sp[0] = r.px; sp[1] = r.py; sp[2] = r.pz;
+                            sn[0] = r.nx; sn[1] = r.ny; sn[2] = r.nz;
+                        } else {
+                            const float mmd_to_meter = 0.1f;
+                            float4* sv = F.out_inter + ((size_t)(g0 + f + h) * M.nv_pad + (size_t)tile * kTileVerts + orig[j]) * 2u;
+                            __stcs(sv, make_float4(r.px * mmd_to_meter, r.py * mmd_to_meter, r.pz * mmd_to_meter, r.nx));
+                            __stcs(sv + 1, make_float4(r.ny, r.nz, su, sv_));
+                        }
+                    }
+                }
+            } else {
 #pragma unroll
             for (int f = 0; f < G; ++f) {
                 // slots past the end of a partial last group are computed on the clamped palette and not stored
@@ -977,6 +1055,7 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
                     __stcs(sv, make_float4(op[0] * mmd_to_meter, op[1] * mmd_to_meter, op[2] * mmd_to_meter, on[0]));
                     __stcs(sv + 1, make_float4(on[1], on[2], mu, mv));
                 }
+            }
             }
         }
         // ---- publish the next group's palettes / rates into the other buffer

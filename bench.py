@@ -449,6 +449,22 @@ def run_mmdgpu(args):
         sec, _ = ses.time_frames(frames_for_step(0, nfr, cfg.n_frames), T)
         cpu = {"value": nfr * nv / sec, "unit": UNIT, "cores": T, "kind": kind,
                "sample": f"{nfr} frames of {cfg.name} on {T} host threads, {sec:.2f} s wall"}
+        # libmmd is single-threaded as shipped, and a release build would use -O3 / AVX2 / FMA
+        n1 = max(4, nfr // T)
+        sec1, _ = ses.time_frames(frames_for_step(0, n1, cfg.n_frames), 1)
+        cpu["single_thread"] = {"value": n1 * nv / sec1, "cores": 1, "sample": f"{n1} frames, {sec1:.2f} s wall"}
+        if kind == "reference":
+            t0 = time.perf_counter()
+            ses.repack_sokol32()
+            cpu["repack_sokol32_ms_per_frame"] = 1e3 * (time.perf_counter() - t0)
+            import oracle
+            if oracle.have_reference_fast():
+                fast = oracle.ReferenceFast(model, motion0)
+                secf, _ = fast.time_frames(frames_for_step(0, nfr, cfg.n_frames), T)
+                cpu["fast_build"] = {"value": nfr * nv / secf, "cores": T,
+                                     "flags": "-O3 -march=x86-64-v3 (contraction on; not parity-grade)",
+                                     "sample": f"{nfr} frames, {secf:.2f} s wall"}
+                fast.close()
 
     also = None
     if rank == 0 and world == 1 and not args.no_also:

@@ -23,6 +23,7 @@ from simple_mmd_renderer_b200 import capi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libmmd_ref.so")
+REF_FAST_SO = os.path.join(HERE, "_ref", "libmmd_ref_fast.so")
 PORT_SO = os.path.join(HERE, "libmmd_oracle.so")
 
 
@@ -161,6 +162,12 @@ class Reference(_Session):
     so_path = REF_SO
 
 
+class ReferenceFast(_Session):
+    """libmmd at -O3 -march=x86-64-v3 with contraction on: timing only (bench.py), never a checker."""
+    prefix = "ref_"
+    so_path = REF_FAST_SO
+
+
 class Restatement(_Session):
     """Plain-C restatement (oracle/libmmd_oracle.so)."""
     prefix = "port_"
@@ -169,6 +176,17 @@ class Restatement(_Session):
 
 def have_reference() -> bool:
     return os.path.exists(REF_SO)
+
+
+def have_reference_fast() -> bool:
+    """Built, and this host has the AVX2 + FMA the fast build assumes."""
+    if not os.path.exists(REF_FAST_SO):
+        return False
+    try:
+        flags = open("/proc/cpuinfo").read()
+    except OSError:
+        return False
+    return " avx2" in flags and " fma" in flags and " bmi2" in flags
 
 
 def have_restatement() -> bool:

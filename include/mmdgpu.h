@@ -100,6 +100,13 @@ typedef struct mmdgpu_vertex_morph_entry { uint32_t vertex; float offset[3]; } m
 typedef struct mmdgpu_uv_morph_entry     { uint32_t vertex; float offset[4]; } mmdgpu_uv_morph_entry;
 typedef struct mmdgpu_bone_morph_entry   { uint32_t bone; float translation[3]; float rotation[4]; } mmdgpu_bone_morph_entry;
 typedef struct mmdgpu_group_morph_entry  { uint32_t morph; float rate; } mmdgpu_group_morph_entry;
+/* Material morph entry, the PMX record of L/reader/interprete/pmx_types.inl:61-72 in its field order:
+ * value[0..3] diffuse rgba, [4..6] specular, [7] shininess, [8..10] ambient, [11..14] edge colour,
+ * [15] edge size, [16..19] texture, [20..23] sphere (sub) texture, [24..27] toon texture.
+ * material < 0 or >= n_materials: every material (pmx_reader_impl.inl:327-334). */
+#define MMDGPU_MATERIAL_FIELDS 28
+enum { MMDGPU_MATERIAL_MUL = 0, MMDGPU_MATERIAL_ADD = 1 };  /* model.inl:396-399 */
+typedef struct mmdgpu_material_morph_entry { int32_t material; uint32_t method; float value[MMDGPU_MATERIAL_FIELDS]; } mmdgpu_material_morph_entry;
 
 /*
  * Flat image of mmd::Model (L/model/model.inl:719-734) restricted to what
@@ -148,6 +155,10 @@ typedef struct mmdgpu_model_desc {
     uint32_t n_uv_morph_entries;     const mmdgpu_uv_morph_entry*     uv_morph_entries;
     uint32_t n_bone_morph_entries;   const mmdgpu_bone_morph_entry*   bone_morph_entries;
     uint32_t n_group_morph_entries;  const mmdgpu_group_morph_entry*  group_morph_entries;
+    /* materials: only their count and the material-morph pool (extensions; libmmd never fills
+     * Poser::material_mul_images_ / material_add_images_, L/motion/poser.inl:160-161) */
+    uint32_t n_materials;
+    uint32_t n_material_morph_entries; const mmdgpu_material_morph_entry* material_morph_entries;
 } mmdgpu_model_desc;
 
 /* ------------------------------------------------------ VMD-shaped motion */
@@ -265,6 +276,7 @@ MMDGPU_API void          mmdgpu_model_destroy(mmdgpu_model_t model);
 MMDGPU_API uint32_t      mmdgpu_model_vertex_count(mmdgpu_model_t model);
 MMDGPU_API uint32_t      mmdgpu_model_bone_count(mmdgpu_model_t model);
 MMDGPU_API uint32_t      mmdgpu_model_morph_count(mmdgpu_model_t model);
+MMDGPU_API uint32_t      mmdgpu_model_material_count(mmdgpu_model_t model);
 /* The host plan the model was built from (owned by the model). */
 MMDGPU_API mmdgpu_plan_t mmdgpu_model_plan(mmdgpu_model_t model);
 /* Bone / morph lookup by raw name bytes as stored in the PMX (only for models created from PMX). */
@@ -346,6 +358,13 @@ MMDGPU_API mmdgpu_status mmdgpu_bone_local_matrices_download(mmdgpu_frames_t fra
 /* Sampled BoneImage::rotation_/translation_ (nb x 7 floats: T xyz, R xyzw) and morph_rates_ (nm). */
 MMDGPU_API mmdgpu_status mmdgpu_bone_poses_download(mmdgpu_frames_t frames, uint32_t slot, float* host_dst);
 MMDGPU_API mmdgpu_status mmdgpu_morph_rates_download(mmdgpu_frames_t frames, uint32_t slot, float* host_dst);
+/* Poser::material_mul_images_ / material_add_images_ (L/motion/poser.inl:107-161): n_materials x 2 x
+ * MMDGPU_MATERIAL_FIELDS floats, per material the multiplicative image then the additive one, fields in the
+ * order of mmdgpu_material_morph_entry.value.  libmmd allocates these images as all 1 / all 0 and never fills
+ * them (poser_impl.inl:355-358), and that is what libmmd-exact mode returns.  With extensions = 1 (parity
+ * unpinned) material morphs are accumulated in application order during pre_physics_posing / update:
+ *   MUL entry: mul = mul * (1 + (value - 1) * rate)      ADD entry: add = add + value * rate. */
+MMDGPU_API mmdgpu_status mmdgpu_material_images_download(mmdgpu_frames_t frames, uint32_t slot, float* host_dst);
 
 /* Pinned host memory helpers for the download path. */
 MMDGPU_API mmdgpu_status mmdgpu_host_alloc(size_t bytes, void** out);
@@ -401,7 +420,11 @@ typedef enum mmdgpu_plan_array {
     MMDGPU_PLAN_BONE_STATIC = 32,   /* u8  [48 nb] per-bone record read by the hierarchy kernel (host_plan.hpp) */
     MMDGPU_PLAN_IK_DESC = 33,       /* u8  [32 n_ik] */
     MMDGPU_PLAN_IK_LINK = 34,       /* u8  [32 n_ik_links] */
-    MMDGPU_PLAN_BONE_MORPH = 35     /* u8  [32 n] bone-morph entries grouped by bone, application order        */
+    MMDGPU_PLAN_BONE_MORPH = 35,    /* u8  [32 n] bone-morph entries grouped by bone, application order        */
+    /* extensions only (empty otherwise): material morphs grouped by material, application order inside a material;
+     * an entry for "every material" is repeated under each */
+    MMDGPU_PLAN_MATERIAL_MORPH_ROW = 36, /* i32 [n_materials + 1]                                              */
+    MMDGPU_PLAN_MATERIAL_MORPH = 37      /* u8  [120 n] {i32 application slot; u32 method; f32 value[28]}      */
 } mmdgpu_plan_array;
 
 /* Host-only: parse a PMX 2.0 / 2.1 byte stream (layout of L/reader/pmx_reader_impl.inl:16-449) and build the

@@ -81,6 +81,7 @@ public:
     size_t GetVertexNum() const { return mmdgpu_model_vertex_count(h_); }
     size_t GetBoneNum() const { return mmdgpu_model_bone_count(h_); }
     size_t GetMorphNum() const { return mmdgpu_model_morph_count(h_); }
+    size_t GetMaterialNum() const { return mmdgpu_model_material_count(h_); }
     mmdgpu_model_t handle() const { return h_; }
     Context& context() const { return ctx_; }
 
@@ -191,6 +192,9 @@ public:
         check(mmdgpu_frames_download(frames_, 0, MMDGPU_STREAM_INTERLEAVED, dst_vertices, model_.GetVertexNum() * 32),
               "mmdgpu_frames_download");
     }
+    // Poser::material_mul_images_ / material_add_images_ (poser.inl:160-161): n_materials x 2 x 28 floats; all 1 / all 0
+    // unless the model was created with extensions (libmmd never fills them).
+    void DownloadMaterialImages(float* dst) { check(mmdgpu_material_images_download(frames_, 0, dst), "mmdgpu_material_images_download"); }
     void DownloadSkinningMatrices(float* dst_nb_x_16) { check(mmdgpu_bone_matrices_download(frames_, 0, dst_nb_x_16), "mmdgpu_bone_matrices_download"); }
     const Model& GetModel() const { return model_; }
     Model& GetModel() { return model_; }

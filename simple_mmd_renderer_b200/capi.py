@@ -25,7 +25,8 @@ STREAM_POSITION, STREAM_NORMAL, STREAM_INTERLEAVED, STREAM_SKIN_MATRIX, STREAM_U
  PLAN_APP_SLOT_PARENT, PLAN_APP_SLOT_MULT, PLAN_CSR_ROW_PTR, PLAN_CSR_SLOT, PLAN_CSR_OFFSET, PLAN_BEZIER_UNUSED,
  PLAN_WAVE_PHASE_SPLIT, PLAN_TILE_ORIG, PLAN_TILE_TYPE, PLAN_TILE_LOCAL_ID, PLAN_TILE_BONE_BEGIN, PLAN_TILE_BONES,
  PLAN_ELL_BASE, PLAN_ELL_ROUNDS, PLAN_ELL_SLOT, PLAN_ELL_OFFSET, PLAN_POSITION, PLAN_NORMAL, PLAN_UV,
- PLAN_BONE_STATIC, PLAN_IK_DESC, PLAN_IK_LINK, PLAN_BONE_MORPH) = range(36)
+ PLAN_BONE_STATIC, PLAN_IK_DESC, PLAN_IK_LINK, PLAN_BONE_MORPH, PLAN_MATERIAL_MORPH_ROW,
+ PLAN_MATERIAL_MORPH) = range(38)
 
 PLAN_DTYPES = {
     PLAN_SKIN_TYPE: np.uint8, PLAN_BONE_ID: np.uint16, PLAN_WEIGHT: np.float32, PLAN_ORDER_PRE: np.int32,
@@ -39,6 +40,7 @@ PLAN_DTYPES = {
     PLAN_ELL_ROUNDS: np.uint32, PLAN_ELL_SLOT: np.uint32, PLAN_ELL_OFFSET: np.float32,
     PLAN_POSITION: np.float32, PLAN_NORMAL: np.float32, PLAN_UV: np.float32, PLAN_BONE_STATIC: np.uint8,
     PLAN_IK_DESC: np.uint8, PLAN_IK_LINK: np.uint8, PLAN_BONE_MORPH: np.uint8,
+    PLAN_MATERIAL_MORPH_ROW: np.int32, PLAN_MATERIAL_MORPH: np.uint8,
 }
 
 (ANIM_BONE_KEY_BEGIN, ANIM_BONE_KEY_COUNT, ANIM_BONE_TRACKED, ANIM_KEY_FRAME, ANIM_KEY_T, ANIM_KEY_R, ANIM_KEY_CURVE,
@@ -56,6 +58,10 @@ VERTEX_MORPH_ENTRY = np.dtype([("vertex", "<u4"), ("offset", "<f4", (3,))])
 UV_MORPH_ENTRY = np.dtype([("vertex", "<u4"), ("offset", "<f4", (4,))])
 BONE_MORPH_ENTRY = np.dtype([("bone", "<u4"), ("translation", "<f4", (3,)), ("rotation", "<f4", (4,))])
 GROUP_MORPH_ENTRY = np.dtype([("morph", "<u4"), ("rate", "<f4")])
+MATERIAL_FIELDS = 28
+MATERIAL_MUL, MATERIAL_ADD = 0, 1
+MATERIAL_MORPH_ENTRY = np.dtype([("material", "<i4"), ("method", "<u4"), ("value", "<f4", (MATERIAL_FIELDS,))])
+assert MATERIAL_MORPH_ENTRY.itemsize == 120
 BONE_KEY = np.dtype([("frame", "<u4"), ("translation", "<f4", (3,)), ("rotation", "<f4", (4,)),
                      ("interp", "i1", (4, 4))])
 MORPH_KEY = np.dtype([("frame", "<u4"), ("weight", "<f4")])
@@ -83,6 +89,8 @@ class ModelDesc(C.Structure):
         ("n_uv_morph_entries", C.c_uint32), ("uv_morph_entries", _P),
         ("n_bone_morph_entries", C.c_uint32), ("bone_morph_entries", _P),
         ("n_group_morph_entries", C.c_uint32), ("group_morph_entries", _P),
+        ("n_materials", C.c_uint32),
+        ("n_material_morph_entries", C.c_uint32), ("material_morph_entries", _P),
     ]
 
 
@@ -122,9 +130,11 @@ _MODEL_ARRAYS = {
     "uv_morph_entries": (UV_MORPH_ENTRY, "n_uv_morph_entries", 1),
     "bone_morph_entries": (BONE_MORPH_ENTRY, "n_bone_morph_entries", 1),
     "group_morph_entries": (GROUP_MORPH_ENTRY, "n_group_morph_entries", 1),
+    "material_morph_entries": (MATERIAL_MORPH_ENTRY, "n_material_morph_entries", 1),
 }
 _MODEL_COUNTS = ["n_vertices", "n_bones", "n_ik_links", "n_morphs", "n_vertex_morph_entries",
-                 "n_uv_morph_entries", "n_bone_morph_entries", "n_group_morph_entries"]
+                 "n_uv_morph_entries", "n_bone_morph_entries", "n_group_morph_entries", "n_materials",
+                 "n_material_morph_entries"]
 
 _ANIM_ARRAYS = {
     "bone_track_bone": (np.int32, "n_bone_tracks", 1), "bone_track_key_begin": (np.uint32, "n_bone_tracks", 1),

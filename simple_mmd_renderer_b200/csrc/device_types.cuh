@@ -54,6 +54,10 @@ struct DevModel {
     // bone morphs grouped by bone
     const int32_t* bone_morph_row;
     const BoneMorphEntry* bone_morph_entries;
+    // extensions: material morphs grouped by material
+    uint32_t n_materials;
+    const int32_t* material_morph_row;
+    const MaterialMorphEntry* material_morph_entries;
 };
 
 // Flattened VMD clip bound to one model.
@@ -90,6 +94,7 @@ struct DevFrames {
     float4* palette;    // [slot][nb][3]   column c of skinning_matrix_: (M0c, M1c, M2c, M3c)
     float4* pal_ext;    // [slot][nb][2]   extensions: rotation quaternion and dual part of the skinning transform
     float2* out_uv;     // extensions, SOA layout: [slot][nv_pad] morphed UV
+    float* material_images;  // extensions: [slot][n_materials][2][28] multiplicative then additive image
     float* out_pos;     // SOA: [slot][nv_pad][3]
     float* out_nrm;     // SOA: [slot][nv_pad][3]
     float4* out_inter;  // INTERLEAVED: [slot][nv_pad][2]

@@ -276,6 +276,7 @@ mmdgpu_status build_plan(const mmdgpu_model_desc& d, const mmdgpu_options* opt, 
         else if (t == MMDGPU_MORPH_VERTEX) pool = d.n_vertex_morph_entries;
         else if (t == MMDGPU_MORPH_BONE) pool = d.n_bone_morph_entries;
         else if (t >= MMDGPU_MORPH_UV && t <= MMDGPU_MORPH_EXT_UV4) pool = d.n_uv_morph_entries;
+        else if (t == MMDGPU_MORPH_MATERIAL && d.material_morph_entries) pool = d.n_material_morph_entries;
         if (pool != 0xFFFFFFFFu && d.morph_entry_count[m] && end > pool)
             return fail(err, MMDGPU_ERR_BAD_INDEX, "morph entry range out of range at morph " + std::to_string(m));
     }
@@ -388,6 +389,43 @@ mmdgpu_status build_plan(const mmdgpu_model_desc& d, const mmdgpu_options* opt, 
             p.morph_bones.push_back(int32_t(b));
             p.bone_morph_entries.insert(p.bone_morph_entries.end(), per_bone[b].begin(), per_bone[b].end());
             p.bone_morph_row.push_back(int32_t(p.bone_morph_entries.size()));
+        }
+    }
+
+    // material morphs grouped by affected material (extensions; libmmd leaves its material images untouched,
+    // poser_impl.inl:355-358)
+    p.n_materials = d.n_materials;
+    if (p.extensions && d.n_materials && d.material_morph_entries) {
+        if (d.n_materials > 65535u) return fail(err, MMDGPU_ERR_UNSUPPORTED, "more than 65535 materials");
+        std::vector<std::vector<MaterialMorphEntry>> per_mat(d.n_materials);
+        for (size_t n = 0; n < n_nodes; ++n) {
+            const uint32_t m = uint32_t(p.node_morph[n]);
+            if (d.morph_type[m] != MMDGPU_MORPH_MATERIAL) continue;
+            for (uint32_t j = 0; j < d.morph_entry_count[m]; ++j) {
+                const mmdgpu_material_morph_entry& e = d.material_morph_entries[d.morph_entry_begin[m] + j];
+                if (e.method > MMDGPU_MATERIAL_ADD)
+                    return fail(err, MMDGPU_ERR_INVALID_ARG, "unknown material morph method at morph " + std::to_string(m));
+                MaterialMorphEntry x;
+                x.node = int32_t(n);
+                x.method = e.method;
+                for (int k = 0; k < MMDGPU_MATERIAL_FIELDS; ++k) {
+                    if (!std::isfinite(e.value[k]))
+                        return fail(err, MMDGPU_ERR_INVALID_ARG, "non-finite material morph value at morph " + std::to_string(m));
+                    x.value[k] = e.value[k];
+                }
+                if (e.material < 0 || uint32_t(e.material) >= d.n_materials) {
+                    for (auto& v : per_mat) v.push_back(x);
+                } else {
+                    per_mat[size_t(e.material)].push_back(x);
+                }
+            }
+        }
+        p.material_morph_row.push_back(0);
+        for (uint32_t i = 0; i < d.n_materials; ++i) {
+            p.material_morph_entries.insert(p.material_morph_entries.end(), per_mat[i].begin(), per_mat[i].end());
+            if (p.material_morph_entries.size() > (size_t(1) << 24))
+                return fail(err, MMDGPU_ERR_UNSUPPORTED, "material morph expansion too large");
+            p.material_morph_row.push_back(int32_t(p.material_morph_entries.size()));
         }
     }
 

@@ -53,6 +53,14 @@ struct BoneMorphEntry {
     float rotation[4];
 };
 
+// One entry of a material morph in application order (per affected material; an "every material" entry is
+// repeated under each material).
+struct MaterialMorphEntry {
+    int32_t node;     // application slot whose rate scales it
+    uint32_t method;  // MMDGPU_MATERIAL_MUL / _ADD
+    float value[MMDGPU_MATERIAL_FIELDS];
+};
+
 // Device-side skinning types (after Model::Normalize, the Lerp shortcuts and the compat mapping).
 enum : uint8_t { kDevBdef1 = 0, kDevBdef2 = 1, kDevBdef4 = 2, kDevSdef = 3, kDevQdef = 4 };
 
@@ -122,6 +130,11 @@ struct Plan {
     std::vector<int32_t> bone_morph_row;     // morph_bones.size() + 1
     std::vector<BoneMorphEntry> bone_morph_entries;
 
+    // extensions only: material morphs grouped by affected material, application order inside a material
+    uint32_t n_materials = 0;
+    std::vector<int32_t> material_morph_row;  // n_materials + 1
+    std::vector<MaterialMorphEntry> material_morph_entries;
+
     // names (only for models parsed from PMX bytes)
     std::vector<std::string> bone_names, morph_names;
     bool names_utf8 = false;  // PMX text encoding flag: UTF-8, else UTF-16LE
@@ -181,6 +194,8 @@ struct ParsedModel {  // owns the arrays a mmdgpu_model_desc points into
     std::vector<mmdgpu_uv_morph_entry> uvme;
     std::vector<mmdgpu_bone_morph_entry> bme;
     std::vector<mmdgpu_group_morph_entry> gme;
+    std::vector<mmdgpu_material_morph_entry> mme;
+    uint32_t n_materials = 0;
     std::vector<std::string> bone_names, morph_names;  // raw bytes as stored (UTF-16LE or UTF-8)
     bool utf8 = false;
     mmdgpu_model_desc desc{};

@@ -67,6 +67,12 @@ __global__ void __launch_bounds__(128) pose_sample_kernel(DevModel M, const DevA
                                                           uint32_t frame_stride, uint32_t has_anims, uint32_t time_mode) {
     const uint32_t slot = blockIdx.y;
     const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (!has_anims && F.material_images && blockIdx.x == 0) {
+        // ResetPosing: all rates are zero, so the material images (extension) are their initial 1 / 0
+        const uint32_t n = M.n_materials * 2 * MMDGPU_MATERIAL_FIELDS;
+        float* mi = F.material_images + (size_t)slot * n;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) mi[i] = ((i / MMDGPU_MATERIAL_FIELDS) & 1u) ? 0.0f : 1.0f;
+    }
     if (item >= M.nb + M.nm) return;
     const uint32_t inst = slot / F.n_frames;
     uint32_t frame = 0;
@@ -362,6 +368,33 @@ __device__ __forceinline__ void skin_bone(const DevModel& M, const SlotState& S,
     }
 }
 
+// Extension (parity unpinned): material morph accumulation.  libmmd allocates Poser::material_mul_images_ (all 1)
+// and material_add_images_ (all 0) (L/motion/poser.inl:160-161, poser_impl.inl:31-36) but UpdateMorphTransform
+// never fills them (poser_impl.inl:355-358).  Here, in application order per material and per field:
+//   MUL entry:  mul = mul * (1 + (value - 1) * rate)       ADD entry:  add = add + value * rate
+// (a renderer shows base * mul + add).  Skipped morphs have rate 0 and leave both images unchanged.
+__device__ __forceinline__ void accumulate_material_images(const DevModel& M, const DevFrames& F, uint32_t slot,
+                                                           const float* nrate, uint32_t tid, uint32_t nthreads) {
+    if (!F.material_images) return;
+    constexpr uint32_t NF = MMDGPU_MATERIAL_FIELDS;
+    float* out = F.material_images + (size_t)slot * M.n_materials * 2 * NF;
+    for (uint32_t i = tid; i < M.n_materials * NF; i += nthreads) {
+        const uint32_t mat = i / NF, k = i % NF;
+        float mul = 1.0f, add = 0.0f;
+        for (int32_t e = M.material_morph_row[mat]; e < M.material_morph_row[mat + 1]; ++e) {
+            const MaterialMorphEntry* E = M.material_morph_entries + e;
+            const float r = nrate[kSlotGroup * E->node];
+            if (r != 0.0f) {
+                const float v = __ldg(&E->value[k]);
+                if (E->method == MMDGPU_MATERIAL_MUL) mul = mul * (1.0f + (v - 1.0f) * r);
+                else add = add + v * r;
+            }
+        }
+        out[(size_t)mat * 2 * NF + k] = mul;
+        out[(size_t)mat * 2 * NF + NF + k] = add;
+    }
+}
+
 constexpr uint32_t kHierWarps = 4;
 
 __global__ void __launch_bounds__(32 * kHierWarps) hierarchy_kernel(DevModel M, DevFrames F, uint32_t wave_lo,
@@ -440,6 +473,7 @@ __global__ void __launch_bounds__(32 * kHierWarps) hierarchy_kernel(DevModel M, 
             morphR[i] = q_to4(mr);
             morphT[i] = make_float4(tx, ty, tz, 0.f);
         }
+        accumulate_material_images(M, F, slot, nrate, lane, 32);
         __syncwarp();
     }
 
@@ -575,6 +609,7 @@ __global__ void __launch_bounds__(kHierCtaThreads) hierarchy_cta_kernel(DevModel
             s_morphR[i] = q_to4(mr);
             s_morphT[i] = make_float4(tx, ty, tz, 0.f);
         }
+        accumulate_material_images(M, F, slot, nrate, tid, nthreads);
     } else {
         // continue from the state the previous launch (pre-physics segment, possibly edited by the host physics
         // hook) left in global memory

@@ -301,6 +301,11 @@ mmdgpu_status upload_model(mmdgpu_model* m) {
     D.n_depths = p.depth_begin.empty() ? 0u : uint32_t(p.depth_begin.size() - 1);
     CU(ctx, upload(ctx, m->mem, p.bone_morph_row, &D.bone_morph_row));
     CU(ctx, upload(ctx, m->mem, p.bone_morph_entries, &D.bone_morph_entries));
+    D.n_materials = p.n_materials;
+    if (!p.material_morph_entries.empty()) {
+        CU(ctx, upload(ctx, m->mem, p.material_morph_row, &D.material_morph_row));
+        CU(ctx, upload(ctx, m->mem, p.material_morph_entries, &D.material_morph_entries));
+    }
     CU(ctx, cudaStreamSynchronize(ctx->stream));  // the staging vectors above die with this frame
 
     const size_t smem = skin_smem_bytes(D, MMDGPU_LAYOUT_INTERLEAVED_SOKOL32);
@@ -749,6 +754,9 @@ MMDGPU_API mmdgpu_status mmdgpu_plan_get(mmdgpu_plan_t plan, mmdgpu_plan_array w
         *data = p.iks.data(); *count = p.iks.size() * sizeof(IkDesc); return MMDGPU_OK;
     case MMDGPU_PLAN_IK_LINK:
         *data = p.links.data(); *count = p.links.size() * sizeof(IkLink); return MMDGPU_OK;
+    case MMDGPU_PLAN_MATERIAL_MORPH_ROW: RET(p.material_morph_row);
+    case MMDGPU_PLAN_MATERIAL_MORPH:
+        *data = p.material_morph_entries.data(); *count = p.material_morph_entries.size() * sizeof(MaterialMorphEntry); return MMDGPU_OK;
     case MMDGPU_PLAN_BONE_MORPH:
         *data = p.bone_morph_entries.data(); *count = p.bone_morph_entries.size() * sizeof(BoneMorphEntry); return MMDGPU_OK;
     default: break;
@@ -815,6 +823,7 @@ MMDGPU_API void mmdgpu_model_destroy(mmdgpu_model_t model) {
 MMDGPU_API uint32_t mmdgpu_model_vertex_count(mmdgpu_model_t m) { return m ? m->plan.plan.nv : 0; }
 MMDGPU_API uint32_t mmdgpu_model_bone_count(mmdgpu_model_t m) { return m ? m->plan.plan.nb : 0; }
 MMDGPU_API uint32_t mmdgpu_model_morph_count(mmdgpu_model_t m) { return m ? m->plan.plan.nm : 0; }
+MMDGPU_API uint32_t mmdgpu_model_material_count(mmdgpu_model_t m) { return m ? m->plan.plan.n_materials : 0; }
 MMDGPU_API mmdgpu_plan_t mmdgpu_model_plan(mmdgpu_model_t m) { return m ? &m->plan : nullptr; }
 
 static int32_t find_name(const std::vector<std::string>& names, const void* bytes, size_t n) {
@@ -933,6 +942,7 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_create(mmdgpu_context_t ctx, mmdgpu_model
     } else {
         CU(ctx, dalloc(f->mem, &F.out_inter, ns * M.nv_pad * 2, false, st));
     }
+    if (M.material_morph_entries) CU(ctx, dalloc(f->mem, &F.material_images, ns * M.n_materials * 2 * MMDGPU_MATERIAL_FIELDS, true, st));
     CU(ctx, dalloc(f->mem, &F.frame_id, ns, true, st));
     CU(ctx, dalloc(f->mem, &F.time_s, ns, true, st));
     CU(ctx, dalloc(f->mem, &f->d_anims, size_t(n_instances), true, st));
@@ -1214,6 +1224,28 @@ MMDGPU_API mmdgpu_status mmdgpu_morph_rates_download(mmdgpu_frames_t f, uint32_t
     if (nm == 0) return MMDGPU_OK;
     if (!host_dst) return set_err(f->ctx, MMDGPU_ERR_INVALID_ARG, "host_dst is NULL");
     CU(f->ctx, cudaMemcpyAsync(host_dst, f->dev.rate + size_t(slot) * nm, size_t(nm) * 4, cudaMemcpyDeviceToHost, f->ctx->stream));
+    CU(f->ctx, cudaStreamSynchronize(f->ctx->stream));
+    return MMDGPU_OK;
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_material_images_download(mmdgpu_frames_t f, uint32_t slot, float* host_dst) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    if (mmdgpu_status s = enter(f->ctx)) return s;
+    if (slot >= f->dev.n_slots) return set_err(f->ctx, MMDGPU_ERR_BAD_INDEX, "slot out of range");
+    const uint32_t nmat = f->model->dev.n_materials;
+    if (nmat == 0) return MMDGPU_OK;
+    if (!host_dst) return set_err(f->ctx, MMDGPU_ERR_INVALID_ARG, "host_dst is NULL");
+    const size_t per = size_t(nmat) * 2 * MMDGPU_MATERIAL_FIELDS;
+    if (!f->dev.material_images) {
+        // libmmd-exact mode, or a model without material morphs: the images libmmd allocates and never touches
+        for (uint32_t m = 0; m < nmat; ++m)
+            for (uint32_t k = 0; k < MMDGPU_MATERIAL_FIELDS; ++k) {
+                host_dst[(size_t(m) * 2) * MMDGPU_MATERIAL_FIELDS + k] = 1.0f;
+                host_dst[(size_t(m) * 2 + 1) * MMDGPU_MATERIAL_FIELDS + k] = 0.0f;
+            }
+        return MMDGPU_OK;
+    }
+    CU(f->ctx, cudaMemcpyAsync(host_dst, f->dev.material_images + size_t(slot) * per, per * 4, cudaMemcpyDeviceToHost, f->ctx->stream));
     CU(f->ctx, cudaStreamSynchronize(f->ctx->stream));
     return MMDGPU_OK;
 }

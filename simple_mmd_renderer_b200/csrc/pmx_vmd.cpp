@@ -155,6 +155,8 @@ void ParsedModel::finish() {
     desc.n_uv_morph_entries = uint32_t(uvme.size()); desc.uv_morph_entries = uvme.data();
     desc.n_bone_morph_entries = uint32_t(bme.size()); desc.bone_morph_entries = bme.data();
     desc.n_group_morph_entries = uint32_t(gme.size()); desc.group_morph_entries = gme.data();
+    desc.n_materials = n_materials;
+    desc.n_material_morph_entries = uint32_t(mme.size()); desc.material_morph_entries = mme.data();
 }
 
 mmdgpu_status parse_pmx(const void* bytes, size_t n, ParsedModel& o, std::string& err) {
@@ -236,6 +238,7 @@ mmdgpu_status parse_pmx(const void* bytes, size_t n, ParsedModel& o, std::string
         r.skip(4);                     // face index count
     }
     if (!r.ok || n_tex < 0 || n_mat < 0) return fail(err, "truncated face / texture / material section");
+    o.n_materials = uint32_t(n_mat);
 
     // ---- bones, pmx_reader_impl.inl:191-265
     const int32_t nb = r.get<int32_t>();
@@ -335,9 +338,17 @@ mmdgpu_status parse_pmx(const void* bytes, size_t n, ParsedModel& o, std::string
                 o.uvme.push_back(e);
             }
             break;
-        case MMDGPU_MORPH_MATERIAL:
-            r.skip(size_t(cnt) * (size_t(msz) + 113));  // pmx_material_morph
-            kept = 0;
+        case MMDGPU_MORPH_MATERIAL:  // index + pmx_material_morph (113 B, interprete/pmx_types.inl:61-72)
+            begin = uint32_t(o.mme.size());
+            for (int32_t j = 0; j < cnt && r.ok; ++j) {
+                mmdgpu_material_morph_entry e;
+                const int64_t mi = r.index(msz);
+                e.material = (mi < 0 || mi >= n_mat) ? -1 : int32_t(mi);
+                e.method = r.get<uint8_t>();
+                r.floats(e.value, MMDGPU_MATERIAL_FIELDS);
+                if (e.method > MMDGPU_MATERIAL_ADD) return fail(err, "unknown material morph method at morph " + std::to_string(m));
+                o.mme.push_back(e);
+            }
             break;
         case 9:   // PMX 2.1 flip morph: morph index + rate
             r.skip(size_t(cnt) * (size_t(mosz) + 4));

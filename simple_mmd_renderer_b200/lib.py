@@ -58,6 +58,7 @@ SIGNATURES = {
     "mmdgpu_model_vertex_count": (_u32, [_vp]),
     "mmdgpu_model_bone_count": (_u32, [_vp]),
     "mmdgpu_model_morph_count": (_u32, [_vp]),
+    "mmdgpu_model_material_count": (_u32, [_vp]),
     "mmdgpu_model_plan": (_vp, [_vp]),
     "mmdgpu_model_find_bone": (_i32, [_vp, _vp, _sz]),
     "mmdgpu_model_find_morph": (_i32, [_vp, _vp, _sz]),
@@ -87,6 +88,7 @@ SIGNATURES = {
     "mmdgpu_bone_local_matrices_download": (C.c_int, [_vp, _u32, _vp]),
     "mmdgpu_bone_poses_download": (C.c_int, [_vp, _u32, _vp]),
     "mmdgpu_morph_rates_download": (C.c_int, [_vp, _u32, _vp]),
+    "mmdgpu_material_images_download": (C.c_int, [_vp, _u32, _vp]),
     "mmdgpu_host_alloc": (C.c_int, [_sz, _PP]),
     "mmdgpu_host_free": (None, [_vp]),
     "mmdgpu_plan_create": (C.c_int, [_vp, _vp, _PP, C.c_char_p, _sz]),

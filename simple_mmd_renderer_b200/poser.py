@@ -99,6 +99,7 @@ class Model:
         self.n_vertices = int(lib.mmdgpu_model_vertex_count(h))
         self.n_bones = int(lib.mmdgpu_model_bone_count(h))
         self.n_morphs = int(lib.mmdgpu_model_morph_count(h))
+        self.n_materials = int(lib.mmdgpu_model_material_count(h))
 
     def plan(self) -> dict:
         return _plan_to_dict(self.ctx.lib, self.ctx.lib.mmdgpu_model_plan(self.h))
@@ -270,6 +271,13 @@ class Frames:
     def morph_rates(self, slot: int = 0) -> np.ndarray:
         out = np.empty((self.model.n_morphs,), np.float32)
         check(self.lib.mmdgpu_morph_rates_download(self.h, int(slot), _ptr(out)), self.ctx.h)
+        return out
+
+    def material_images(self, slot: int = 0) -> np.ndarray:
+        """Poser::material_mul_images_ / material_add_images_ (poser.inl:107-161): (n_materials, 2, 28); [:, 0] is the
+        multiplicative image, [:, 1] the additive one.  All 1 / all 0 in libmmd-exact mode (libmmd never fills them)."""
+        out = np.empty((self.model.n_materials, 2, capi.MATERIAL_FIELDS), np.float32)
+        check(self.lib.mmdgpu_material_images_download(self.h, int(slot), _ptr(out)), self.ctx.h)
         return out
 
     def close(self):

@@ -366,6 +366,41 @@ def make_motion(cfg: SynthConfig, model: dict, instance: int = 0, n_frames: int 
     )
 
 
+def add_material_morphs(model: dict, n_materials: int = 5, n_morphs: int = 4, entries_per_morph: int = 3,
+                        seed: int = 0x4D4D4D41, in_group: bool = True) -> dict:
+    """Copy of `model` with `n_materials` materials and `n_morphs` material morphs appended after the existing morphs
+    (existing indices and random draws are untouched), plus optionally one group morph that drives the first two
+    of them.  Every third entry addresses all materials (material = -1, pmx_reader_impl.inl:327-334); methods
+    alternate between multiply and add (model.inl:396-399)."""
+    rng = np.random.default_rng(seed)
+    out = dict(model)
+    mtype, mbegin, mcount = (list(model[k]) for k in ("morph_type", "morph_entry_begin", "morph_entry_count"))
+    first = len(mtype)
+    ent = np.zeros(n_morphs * entries_per_morph, capi.MATERIAL_MORPH_ENTRY)
+    ent["material"] = rng.integers(0, n_materials, ent.size)
+    ent["material"][2::3] = -1
+    ent["method"] = np.arange(ent.size) % 2
+    ent["value"] = _f32(rng.uniform(0.0, 2.0, (ent.size, capi.MATERIAL_FIELDS)))
+    for m in range(n_morphs):
+        mtype.append(capi.MORPH_MATERIAL)
+        mbegin.append(m * entries_per_morph)
+        mcount.append(entries_per_morph)
+    if in_group and n_morphs >= 2:
+        g = np.zeros(2, capi.GROUP_MORPH_ENTRY)
+        g["morph"] = [first, first + 1]
+        g["rate"] = _f32([0.5, 0.75])
+        old = np.asarray(model["group_morph_entries"], capi.GROUP_MORPH_ENTRY)
+        mtype.append(capi.MORPH_GROUP)
+        mbegin.append(old.size)
+        mcount.append(2)
+        gall = np.concatenate([old, g])
+        out.update(n_group_morph_entries=gall.size, group_morph_entries=gall)
+    out.update(n_morphs=len(mtype), morph_type=np.asarray(mtype, np.uint8),
+               morph_entry_begin=np.asarray(mbegin, np.uint32), morph_entry_count=np.asarray(mcount, np.uint32),
+               n_materials=n_materials, n_material_morph_entries=ent.size, material_morph_entries=ent)
+    return out
+
+
 def mean_morph_entries_per_vertex(model: dict) -> float:
     """e of SURVEY 8d: vertex-morph entries reachable through application slots, per vertex."""
     return float(model["n_vertex_morph_entries"]) / max(1, model["n_vertices"])

@@ -61,6 +61,30 @@ def morph_images(model, rates):
     return dv, duv
 
 
+def material_images(model, rates):
+    """(n_materials, 2, 28) float64: multiplicative and additive material images, application order per material.
+    MUL entry: mul *= 1 + (value - 1) * rate;  ADD entry: add += value * rate (include/mmdgpu.h)."""
+    slots, sr = slot_rates(model, rates)
+    nmat = int(model["n_materials"])
+    img = np.zeros((nmat, 2, capi.MATERIAL_FIELDS))
+    img[:, 0] = 1.0
+    mt, mb, mc = model["morph_type"], model["morph_entry_begin"], model["morph_entry_count"]
+    for s, (m, _, _) in enumerate(slots):
+        r = float(sr[s])
+        if r == 0.0 or mt[m] != capi.MORPH_MATERIAL:
+            continue
+        for e in model["material_morph_entries"][int(mb[m]):int(mb[m]) + int(mc[m])]:
+            mi = int(e["material"])
+            targets = range(nmat) if (mi < 0 or mi >= nmat) else [mi]
+            v = e["value"].astype(np.float64)
+            for t in targets:
+                if int(e["method"]) == capi.MATERIAL_MUL:
+                    img[t, 0] *= 1.0 + (v - 1.0) * r
+                else:
+                    img[t, 1] += v * r
+    return img
+
+
 def mat_to_quat(R):
     """Unit quaternion (x, y, z, w) of a column-vector rotation matrix R (v' = R v)."""
     tr = R[0, 0] + R[1, 1] + R[2, 2]

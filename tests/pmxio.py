@@ -68,8 +68,12 @@ def write_pmx(model: dict, utf8: bool = False, version: float = 2.0, extra_uv: i
     # faces: one triangle; textures: one; materials: one
     out.append(struct.pack("<i", 3) + b"".join(_pack_idx(0, vsz) for _ in range(3)))
     out.append(struct.pack("<i", 1) + _text("tex.png", utf8))
-    out.append(struct.pack("<i", 1) + _text("mat", utf8) + _text("mat_en", utf8) + b"\0" * 65
-               + _pack_idx(0, tsz) + _pack_idx(0xFF, tsz) + bytes([0, 1, 3]) + _text("memo", utf8) + struct.pack("<i", 3))
+    n_mat = max(1, int(model.get("n_materials", 0)))
+    out.append(struct.pack("<i", n_mat))
+    for i in range(n_mat):
+        out.append(_text(f"mat{i}", utf8) + _text(f"mat_en{i}", utf8) + b"\0" * 65
+                   + _pack_idx(0, tsz) + _pack_idx(0xFF, tsz) + bytes([0, 1, 3]) + _text("memo", utf8)
+                   + struct.pack("<i", 3 if i == 0 else 0))
     # bones
     out.append(struct.pack("<i", nb))
     flags = model["bone_flags"]
@@ -124,8 +128,10 @@ def write_pmx(model: dict, utf8: bool = False, version: float = 2.0, extra_uv: i
             for e in model["uv_morph_entries"][b0:b0 + n]:
                 out.append(_pack_idx(int(e["vertex"]), vsz) + struct.pack("<4f", *e["offset"]))
         elif t == capi.MORPH_MATERIAL:
-            for _ in range(n):
-                out.append(_pack_idx(0, matsz) + b"\0" * 113)
+            for e in model.get("material_morph_entries", ())[b0:b0 + n]:
+                # "every material" is stored as -1, which ReadIndex returns as 255 for a 1-byte index
+                out.append(_pack_idx(int(e["material"]), matsz) + bytes([int(e["method"])])
+                           + struct.pack("<28f", *e["value"]))
     # display frames, rigid bodies, joints: empty
     out.append(struct.pack("<iii", 0, 0, 0))
     return b"".join(out)

@@ -169,3 +169,110 @@ def test_uv_stream_needs_extensions(ctx):
     with pytest.raises(MmdGpuError) as e:
         fr.download(0, capi.STREAM_UV)
     assert e.value.status == capi.ERR_INVALID_ARG
+
+
+# ---------------------------------------------------------------- material morph accumulation (extension)
+def _material_case():
+    from simple_mmd_renderer_b200 import synth
+    cfg, model, motion = synth_case("tiny_full")
+    return synth.add_material_morphs(model), motion
+
+
+def _material_rates(model, seed=5):
+    rng = np.random.default_rng(seed)
+    w = rng.uniform(0.0, 1.0, int(model["n_morphs"])).astype(np.float32)
+    w[rng.random(w.size) < 0.2] = 0.0
+    return w
+
+
+def test_material_images_against_fp64_restatement(ctx):
+    model, _ = _material_case()
+    m = Model(ctx, model, extensions=True)
+    assert m.n_materials == 5
+    fr = Frames(m, 3, 1)
+    np.testing.assert_array_equal(fr.material_images(1)[:, 0], 1.0)     # a fresh Poser: ResetPosing state
+    np.testing.assert_array_equal(fr.material_images(1)[:, 1], 0.0)
+    weights = [_material_rates(model, s) for s in (5, 6, 7)]
+    fr.reset_posing()
+    for slot, w in enumerate(weights):
+        for i, x in enumerate(w):
+            fr.set_morph_pose(slot, i, float(x))
+    fr.pre_physics_posing()
+    fr.post_physics_posing()
+    for slot, w in enumerate(weights):
+        want = ref.material_images(model, w)
+        got = fr.material_images(slot)
+        assert (np.abs(want[:, 0] - 1.0).max() > 1e-3) and (np.abs(want[:, 1]).max() > 1e-3)
+        np.testing.assert_allclose(got, want, **TOL)
+    fr.reset_posing()
+    np.testing.assert_array_equal(fr.material_images(0)[:, 0], 1.0)
+    np.testing.assert_array_equal(fr.material_images(0)[:, 1], 0.0)
+
+
+def test_material_images_through_the_fused_update_and_a_clip(ctx):
+    from simple_mmd_renderer_b200 import synth
+    model, _ = _material_case()
+    cfg = synth.TINY_FULL
+    motion = synth.make_motion(cfg, model)          # keys every morph, the material ones included
+    m = Model(ctx, model, extensions=True)
+    mo = Motion(m, motion)
+    fr = Frames(m, 1, 4)
+    frames = [3, 17, 18, 40]
+    fr.update([mo], frames)
+    for slot in range(4):
+        want = ref.material_images(model, fr.morph_rates(slot))
+        np.testing.assert_allclose(fr.material_images(slot), want, **TOL)
+    # the deformation itself does not depend on material morphs: same positions as the libmmd-exact model
+    plain = Frames(Model(ctx, model), 1, 4)
+    plain.update([Motion(plain.model, motion)], frames)
+    for slot in range(4):
+        t = _norm_types(model)[0]
+        keep = (t != capi.SKIN_SDEF) & (model["skin_type"] != capi.SKIN_QDEF)
+        assert_bitwise(fr.download(slot, capi.STREAM_POSITION)[keep], plain.download(slot, capi.STREAM_POSITION)[keep],
+                       "positions of non-extension vertices")
+
+
+def test_material_image_properties(ctx):
+    """Self-consistency: a multiply entry at rate 1 yields its value; additive images are linear in the rate; an entry
+    for "every material" reaches all of them; a skipped morph (rate < 1e-7) leaves the images untouched."""
+    from simple_mmd_renderer_b200 import synth
+    cfg, base, _ = synth_case("tiny")
+    model = synth.add_material_morphs(base, n_materials=3, n_morphs=2, entries_per_morph=1, in_group=False)
+    ent = model["material_morph_entries"].copy()
+    ent["material"] = [1, -1]
+    ent["method"] = [capi.MATERIAL_MUL, capi.MATERIAL_ADD]
+    model["material_morph_entries"] = ent
+    first = int(model["n_morphs"]) - 2
+    m = Model(ctx, model, extensions=True)
+
+    def images(w_mul, w_add):
+        fr = Frames(m, 1, 1)
+        fr.reset_posing()
+        fr.set_morph_pose(0, first, w_mul)
+        fr.set_morph_pose(0, first + 1, w_add)
+        fr.pre_physics_posing()
+        return fr.material_images(0)
+    a = images(1.0, 0.0)
+    np.testing.assert_allclose(a[1, 0], ent["value"][0], rtol=1e-6)
+    np.testing.assert_array_equal(a[[0, 2], 0], 1.0)
+    np.testing.assert_array_equal(a[:, 1], 0.0)
+    b1, b2 = images(0.0, 0.3), images(0.0, 0.6)
+    np.testing.assert_allclose(b2[:, 1], 2.0 * b1[:, 1], rtol=1e-6)
+    for t in range(3):
+        np.testing.assert_allclose(b1[t, 1], ent["value"][1] * np.float32(0.3), rtol=1e-6)
+    c = images(5e-8, -1.0)                                 # both skipped: below 1e-7 / negative (poser_impl.inl:329)
+    np.testing.assert_array_equal(c[:, 0], 1.0)
+    np.testing.assert_array_equal(c[:, 1], 0.0)
+
+
+def test_material_images_are_untouched_in_libmmd_exact_mode(ctx):
+    """libmmd allocates the images as 1 / 0 and never fills them (poser_impl.inl:31-36, 355-358)."""
+    model, _ = _material_case()
+    fr = Frames(Model(ctx, model), 1, 1)
+    for i, x in enumerate(_material_rates(model)):
+        fr.set_morph_pose(0, i, float(x))
+    fr.pre_physics_posing()
+    img = fr.material_images(0)
+    assert img.shape == (5, 2, capi.MATERIAL_FIELDS)
+    np.testing.assert_array_equal(img[:, 0], 1.0)
+    np.testing.assert_array_equal(img[:, 1], 0.0)

@@ -297,3 +297,34 @@ def test_tile_layout_is_a_faithful_permutation(name):
                 pos = ti * TILE + (w * 32 + np.arange(32)) * V + j
                 mixed += len(set(st_type[pos].tolist())) > 1
     assert mixed <= 3 * n_tiles
+
+
+def test_material_morph_plan_is_grouped_by_material_in_application_order():
+    """Extension plan: entries under each material appear in application-slot (DFS) order, an "every material" entry
+    is repeated under each material, and values / methods are carried over unchanged."""
+    from simple_mmd_renderer_b200 import synth
+    cfg, model, _ = synth_case("tiny_full")
+    model = synth.add_material_morphs(model)
+    plan = plan_arrays(model, extensions=True)
+    row = plan[capi.PLAN_MATERIAL_MORPH_ROW]
+    rec = plan[capi.PLAN_MATERIAL_MORPH].view(np.dtype([("node", "<i4"), ("method", "<u4"), ("value", "<f4", (28,))]))
+    node_morph = plan[capi.PLAN_APP_SLOT_MORPH]
+    nmat = int(model["n_materials"])
+    assert row.size == nmat + 1 and row[0] == 0 and row[-1] == rec.size
+    ent, mb, mc = model["material_morph_entries"], model["morph_entry_begin"], model["morph_entry_count"]
+    for mat in range(nmat):
+        want = []
+        for node, m in enumerate(node_morph):
+            if model["morph_type"][m] != capi.MORPH_MATERIAL:
+                continue
+            for e in ent[int(mb[m]):int(mb[m]) + int(mc[m])]:
+                if e["material"] < 0 or e["material"] >= nmat or e["material"] == mat:
+                    want.append((node, int(e["method"]), e["value"]))
+        got = rec[row[mat]:row[mat + 1]]
+        assert len(got) == len(want), mat
+        for g, (node, method, value) in zip(got, want):
+            assert g["node"] == node and g["method"] == method
+            np.testing.assert_array_equal(g["value"].view(np.uint32), value.view(np.uint32))
+    # a material morph inside a group shows up once per visit (direct + through the group)
+    n_material_morphs = int((model["morph_type"] == capi.MORPH_MATERIAL).sum())
+    assert sum(1 for m in node_morph if model["morph_type"][m] == capi.MORPH_MATERIAL) == n_material_morphs + 2

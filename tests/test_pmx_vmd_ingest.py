@@ -186,3 +186,20 @@ def test_host_code_under_address_and_ub_sanitizers(tmp_path):
                        timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "no sanitizer report" in r.stdout
+
+
+def test_material_morphs_survive_the_pmx_container():
+    """Material morph records (index + 113-byte pmx_material_morph, interprete/pmx_types.inl:61-72): same grouped plan
+    from bytes as from arrays; an index of 255 in a 1-byte field means every material (pmx_reader_impl.inl:327-334)."""
+    from simple_mmd_renderer_b200 import synth
+    cfg, model, _ = synth_case("tiny_full")
+    model = synth.add_material_morphs(_representable(model))
+    want = HostPlan(arrays=model, extensions=True).arrays()
+    got = HostPlan(pmx_bytes=pmxio.write_pmx(model, version=_version(model)), extensions=True).arrays()
+    row = want[capi.PLAN_MATERIAL_MORPH_ROW]
+    assert row.size == 6 and row[-1] * 120 == want[capi.PLAN_MATERIAL_MORPH].size and row[-1] > 12
+    for k in want:
+        np.testing.assert_array_equal(want[k].view(np.uint8) if want[k].dtype.kind == "f" else want[k],
+                                      got[k].view(np.uint8) if got[k].dtype.kind == "f" else got[k], err_msg=f"plan array {k}")
+    # libmmd-exact mode carries no material plan at all
+    assert HostPlan(arrays=model).arrays()[capi.PLAN_MATERIAL_MORPH].size == 0

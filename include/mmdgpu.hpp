@@ -114,30 +114,25 @@ private:
 
 class Poser {
 public:
-    // Poser::pose_image (L/motion/poser.inl:17-20).  The device owns the deformed buffer; each vector here is a
-    // host mirror that is downloaded on first access after Deform().
+    // Poser::pose_image (L/motion/poser.inl:17-20).  The device owns the deformed buffer; the two vectors here are
+    // host mirrors in page-locked memory, filled together (two asynchronous copies, one wait) on first access
+    // after Deform().
     class LazyVectors {
     public:
         size_t size() const { return owner_->model_.GetVertexNum(); }
         const Vector3f& operator[](size_t i) const { return data()[i]; }
         const Vector3f* data() const {
-            if (!valid_) {
-                host_.resize(size());
-                owner_->model_.context().check(
-                    mmdgpu_frames_download(owner_->frames_, 0, stream_, host_.data(), host_.size() * sizeof(Vector3f)),
-                    "mmdgpu_frames_download");
-                valid_ = true;
-            }
-            return host_.data();
+            owner_->Fetch();
+            return host_;
         }
+        const Vector3f* begin() const { return data(); }
+        const Vector3f* end() const { return data() + size(); }
 
     private:
         friend class Poser;
-        LazyVectors(Poser* owner, mmdgpu_stream_id id) : owner_(owner), stream_(id) {}
+        explicit LazyVectors(Poser* owner) : owner_(owner) {}
         Poser* owner_;
-        mmdgpu_stream_id stream_;
-        mutable std::vector<Vector3f> host_;
-        mutable bool valid_ = false;
+        Vector3f* host_ = nullptr;
     };
     struct PoseImage {
         LazyVectors coordinates, normals;
@@ -145,14 +140,27 @@ public:
 
     // Poser::Poser (poser_impl.inl:16-128) ends with ResetPosing(); Deform();
     explicit Poser(Model& model, mmdgpu_layout layout = MMDGPU_LAYOUT_SOA_POS_NRM)
-        : pose_image{LazyVectors(this, MMDGPU_STREAM_POSITION), LazyVectors(this, MMDGPU_STREAM_NORMAL)},
+        : pose_image{LazyVectors(this), LazyVectors(this)},
           model_(model),
           layout_(layout) {
         check(mmdgpu_frames_create(model.context().handle(), model.handle(), 1, 1, layout, &frames_), "mmdgpu_frames_create");
+        const size_t bytes = model.GetVertexNum() * sizeof(Vector3f);
+        void *a = nullptr, *b = nullptr;
+        if (mmdgpu_host_alloc(bytes, &a) != MMDGPU_OK || mmdgpu_host_alloc(bytes, &b) != MMDGPU_OK) {
+            mmdgpu_host_free(a);
+            mmdgpu_frames_destroy(frames_);
+            throw Error(MMDGPU_ERR_OOM, "page-locked pose_image allocation failed");
+        }
+        pose_image.coordinates.host_ = static_cast<Vector3f*>(a);
+        pose_image.normals.host_ = static_cast<Vector3f*>(b);
         ResetPosing();
         Deform();
     }
-    ~Poser() { mmdgpu_frames_destroy(frames_); }
+    ~Poser() {
+        mmdgpu_frames_destroy(frames_);
+        mmdgpu_host_free(pose_image.coordinates.host_);
+        mmdgpu_host_free(pose_image.normals.host_);
+    }
     Poser(const Poser&) = delete;
     Poser& operator=(const Poser&) = delete;
 
@@ -172,14 +180,14 @@ public:
     void PostPhysicsPosing() { check(mmdgpu_post_physics_posing(frames_), "mmdgpu_post_physics_posing"); }
     void Deform() {
         check(mmdgpu_deform(frames_), "mmdgpu_deform");
-        pose_image.coordinates.valid_ = pose_image.normals.valid_ = false;
+        image_valid_ = false;
     }
     // ResetPosing + SeekFrame + Pre + Post + Deform in one call (the fused path; physics off).
     void Update(const Motion& motion, size_t frame) {
         mmdgpu_animation_t a = motion.handle();
         const uint32_t f = uint32_t(frame);
         check(mmdgpu_update(frames_, &a, &f), "mmdgpu_update");
-        pose_image.coordinates.valid_ = pose_image.normals.valid_ = false;
+        image_valid_ = false;
     }
     // Physics hand-back between Pre and Post (PoserMotionState::Synchronize / Fix, mmd-bullet_impl.inl:34-56).
     void OverrideSkinningMatrix(size_t bone, const float skinning[16], const float* local_or_null = nullptr) {
@@ -202,9 +210,22 @@ public:
 
 private:
     void check(mmdgpu_status s, const char* what) const { model_.context().check(s, what); }
+    // both planes of pose_image in one round trip (SoA layout; the interleaved layout has DownloadInterleaved)
+    void Fetch() {
+        if (image_valid_) return;
+        const size_t bytes = model_.GetVertexNum() * sizeof(Vector3f);
+        check(mmdgpu_frames_download_async(frames_, 0, 1, MMDGPU_STREAM_POSITION, pose_image.coordinates.host_, bytes),
+              "mmdgpu_frames_download_async");
+        check(mmdgpu_frames_download_async(frames_, 0, 1, MMDGPU_STREAM_NORMAL, pose_image.normals.host_, bytes),
+              "mmdgpu_frames_download_async");
+        check(mmdgpu_context_join_downloads(model_.context().handle()), "mmdgpu_context_join_downloads");
+        model_.context().Synchronize();
+        image_valid_ = true;
+    }
     Model& model_;
     mmdgpu_layout layout_;
     mmdgpu_frames_t frames_ = nullptr;
+    bool image_valid_ = false;
 };
 
 class MotionPlayer {

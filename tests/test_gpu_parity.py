@@ -361,6 +361,33 @@ def test_full_size_bake_batch_equals_single_frame_runs(ctx):
     assert_bitwise(big.download(127, capi.STREAM_POSITION), ref["pos"], "slot 127 vs oracle")
 
 
+def test_output_planes_beyond_four_gib(ctx):
+    """400 slots of the 1 M-vertex model: each output plane is 4.8 GB, so any 32-bit byte offset in the kernels,
+    the bulk stores or the download path would wrap.  Slots on both sides of the 4 GiB boundary are checked against
+    the CPU oracle."""
+    import torch
+    if torch.cuda.mem_get_info(0)[0] < 24 * 2**30:
+        pytest.skip("needs 24 GB of free device memory")
+    cfg, model, motion = synth_case("C3")
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    n = 400
+    assert n * m.n_vertices * 12 > 2**32
+    fr = Frames(m, 1, n)
+    fr.update_range(a, [0], 1)
+    orc = _oracle(model, motion)
+    for k in (0, 357, 358, 399):     # 4 GiB / 12 MB = 357.9
+        ref = orc.run_frame(k)       # frames past the 300-frame clip hold its last keys
+        assert_bitwise(fr.download(k, capi.STREAM_POSITION), ref["pos"], f"slot {k} positions")
+        assert_bitwise(fr.download(k, capi.STREAM_NORMAL), ref["nrm"], f"slot {k} normals")
+    del fr
+    inter = Frames(m, 1, n, layout=capi.LAYOUT_INTERLEAVED_SOKOL32)
+    inter.update_range(a, [0], 1)
+    for k in (134, 135, 399):        # 4 GiB / 32 MB = 134.2
+        orc.run_frame(k)
+        assert_bitwise(inter.download(k, capi.STREAM_INTERLEAVED), orc.repack_sokol32(), f"slot {k} interleaved records")
+
+
 def test_full_size_crowd_equals_single_instance_runs(ctx):
     """BASELINE configs[3]: 512 instances of the 50 k-vertex model with independent clips; sampled instances are
     bit-identical to a one-instance run of the same clip and frame and to the CPU oracle."""

@@ -73,10 +73,11 @@ def measured_peaks():
     return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
 
 
-def ncu_traffic_bytes(workload: str):
-    """dram read+write bytes per skin launch from the committed ncu capture, if there is one for this workload."""
+def ncu_traffic_bytes(workload: str, layout: str = "soa"):
+    """dram read+write bytes per skin launch from the committed ncu capture, if there is one for this workload
+    (captured for the SoA layout at the default 128 frames per step)."""
     p = os.path.join(ROOT, "profiles", "skin_dram_traffic.json")
-    if os.path.exists(p):
+    if layout == "soa" and os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
         return d.get(workload)
@@ -485,7 +486,7 @@ def run_mmdgpu(args):
             "data": "synthetic",
             "config": workload_config(args, cfg, model, slots, "device-resident inputs and outputs"),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": ncu_traffic_bytes(args.workload),
+                         "frac": achieved / peak if peak else None, "traffic": ncu_traffic_bytes(args.workload, args.layout),
                          "kernel": "skin_kernel", "algorithmic_bytes_per_vertex": b_alg,
                          "vertices_per_launch": nv * slots, "avg_launch_ms": skin_ms, "peak_source": peak_src,
                          "frac_of_nominal_8TBs": achieved / 8000.0,
@@ -493,8 +494,8 @@ def run_mmdgpu(args):
                                  "ncu) is far below the algorithmic bytes and `frac` can exceed 1; the write-only floor "
                                  "is 24 B per vertex-frame",
                          "output_write_gbs": 24.0 * nv * slots / (skin_ms * 1e-3) / 1e9 if skin_ms > 0 else None,
-                         "dram_gbs_from_traffic": (ncu_traffic_bytes(args.workload) / (skin_ms * 1e-3) / 1e9)
-                         if (skin_ms > 0 and ncu_traffic_bytes(args.workload) and slots == 128 and world == 1) else None},
+                         "dram_gbs_from_traffic": (ncu_traffic_bytes(args.workload, args.layout) / (skin_ms * 1e-3) / 1e9)
+                         if (skin_ms > 0 and ncu_traffic_bytes(args.workload, args.layout) and slots == 128 and world == 1) else None},
             "kernel_ms_per_step": {"pose_sample": kernel_ms[0] / args.steps, "hierarchy": kernel_ms[1] / args.steps,
                                    "skin": kernel_ms[2] / args.steps},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

@@ -10,12 +10,15 @@ from simple_mmd_renderer_b200 import capi
 _KANA = ["センター", "上半身", "下半身", "左足", "右足", "左ひざ", "右ひざ", "頭", "首", "ｶﾀ", "左腕", "右腕"]
 
 
+ASCII_NAMES = False     # libmmd's own readers only join ASCII names reliably under glibc (dwarf_impl.inl:205-232)
+
+
 def bone_name(i: int) -> str:
-    return f"{_KANA[i % len(_KANA)]}{i}"
+    return f"bone_{i}" if ASCII_NAMES else f"{_KANA[i % len(_KANA)]}{i}"
 
 
 def morph_name(i: int) -> str:
-    return ["まばたき", "あ", "笑い", "ｳｨﾝｸ"][i % 4] + str(i)
+    return f"morph_{i}" if ASCII_NAMES else ["まばたき", "あ", "笑い", "ｳｨﾝｸ"][i % 4] + str(i)
 
 
 def _idx_size(n: int) -> int:

@@ -223,12 +223,15 @@ __device__ __forceinline__ void eval_bone(const DevModel& M, const SlotState& S,
     Quat totR = q_mul(mR, R);
     float4 totT = make_float4(mT.x + T.x, mT.y + T.y, mT.z + T.z, 0.f);
     if (s.flags & (kAppendRot | kAppendTrans)) {
+        // libmmd updates total_rotation_ / total_translation_ in place (poser_impl.inl:144-156): a bone that names
+        // ITSELF as its append parent reads the values just written, not last frame's / the reset ones
+        const bool self = s.append_parent == b;
         if (s.flags & kAppendRot) {
-            const Quat pr = q_from(S.totR[s.append_parent]);
+            const Quat pr = self ? totR : q_from(S.totR[s.append_parent]);
             totR = q_mul(totR, q_slerp(q_identity(), pr, s.append_ratio));
         }
         if (s.flags & kAppendTrans) {
-            const float4 pt = S.totT[s.append_parent];
+            const float4 pt = self ? totT : S.totT[s.append_parent];
             totT.x = totT.x + s.append_ratio * pt.x;
             totT.y = totT.y + s.append_ratio * pt.y;
             totT.z = totT.z + s.append_ratio * pt.z;

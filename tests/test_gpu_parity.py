@@ -610,3 +610,28 @@ def test_randomized_configs(ctx, seed):
     fr.update(a, frames)
     for k, f in enumerate(frames):
         _check_frame(fr, k, orc.run_frame(f), f"{cfg.name} frame {f}")
+
+
+def test_bone_that_appends_from_itself(ctx):
+    """Found by tools/gpu_fuzz.py: UpdateBoneTransform writes total_rotation_ / total_translation_ before the append
+    block reads the append parent's (poser_impl.inl:144-156), so a bone whose append parent is itself sees its own
+    fresh values."""
+    cfg, model, motion = synth_case("tiny_full")
+    model = dict(model)
+    flags, ap, ratio = model["bone_flags"].copy(), model["bone_append_parent"].copy(), model["bone_append_ratio"].copy()
+    plain = [b for b in range(3, int(model["n_bones"])) if not (flags[b] & (capi.BONE_APPEND_ROTATE | capi.BONE_APPEND_TRANSLATE
+                                                                       | capi.BONE_HAS_IK))]
+    for b, bits, r in ((plain[0], capi.BONE_APPEND_ROTATE, 0.75), (plain[5], capi.BONE_APPEND_TRANSLATE, -0.5),
+                       (plain[9], capi.BONE_APPEND_ROTATE | capi.BONE_APPEND_TRANSLATE, 1.0)):
+        flags[b] |= bits
+        ap[b] = b
+        ratio[b] = r
+    model.update(bone_flags=flags, bone_append_parent=ap, bone_append_ratio=ratio)
+    orc = _oracle(model, motion)
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    frames = [0, 9, 31, 60]
+    fr = Frames(m, 1, len(frames))
+    fr.update(a, frames)
+    for k, f in enumerate(frames):
+        _check_frame(fr, k, orc.run_frame(f), f"self-append frame {f}")

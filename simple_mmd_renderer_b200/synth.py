@@ -406,21 +406,23 @@ def mean_morph_entries_per_vertex(model: dict) -> float:
     return float(model["n_vertex_morph_entries"]) / max(1, model["n_vertices"])
 
 
-def make_ik_zoo(seed: int = 77, n_frames: int = 40):
+def make_ik_zoo(seed: int = 77, n_frames: int = 40, chains=None):
     """A small rig that exercises every CCD IK branch of L/motion/poser_impl.inl:168-310: chains of 2-4 links,
     unlimited links, FIX_X / FIX_Y / FIX_Z / FIX_ALL links, the three Euler orders (ZXY, XYZ, YZX), swapped lo / hi
     limits, odd iteration counts, an iteration count above the 256 cap, and an IK bone that sorts before its links.
     Returns (model, motion) in the flat layout of `capi.model_desc` / `capi.anim_desc`."""
     rng = np.random.Generator(np.random.PCG64([SEED_BASE + 99, seed]))
     PI = float(np.pi)
-    chains = [
-        # (n_links, iterations, angle_limit, [per link (tip-most first): None | (lo, hi)])
+    zoo = [
+        # (n_links, iterations, angle_limit, [per link (tip-most first): None | (lo, hi)][, IK bone sorts first])
         (2, 40, 2.0, [((-PI, 0, 0), (-0.0087, 0, 0)), None]),                           # FIX_X, XYZ order (classic knee)
         (3, 15, 0.6, [((0, -1.0, 0), (0, 1.2, 0)), None, ((-0.2, -0.3, -0.4), (0.3, 0.2, 0.5))]),   # FIX_Y ; ZXY
         (3, 33, 1.0, [((0, 0, -2.5), (0, 0, 0.4)), ((0, 0, 0), (0, 0, 0)), None]),      # FIX_Z ; FIX_ALL (skipped)
         (4, 300, 0.35, [((-2.0, -2.0, -0.5), (2.0, 2.0, 0.5)), None, ((0.4, -0.2, -0.1), (-0.9, 0.3, 0.2)), None]),  # YZX ; swapped lo/hi
         (2, 7, 3.5, [((-2.0, -1.0, -3.0), (2.0, 1.0, 3.0)), ((-1.0, -2.5, -1.0), (1.0, 2.5, 1.0))]),  # XYZ ; ZXY
     ]
+    if chains is None:
+        chains = zoo                              # custom chain lists: tools/gpu_fuzz.py
     pos, parent, level, flags = [(0.0, 0.0, 0.0)], [-1], [0], [0]
     ik_target, ik_iter, ik_angle, ik_begin, ik_count = [-1], [0], [0.0], [0], [0]
     l_bone, l_has, l_lo, l_hi = [], [], [], []
@@ -431,9 +433,10 @@ def make_ik_zoo(seed: int = 77, n_frames: int = 40):
         ik_target.append(-1); ik_iter.append(0); ik_angle.append(0.0); ik_begin.append(0); ik_count.append(0)
         return len(pos) - 1
 
-    for c, (nl, iters, angle, lims) in enumerate(chains):
+    for c, spec in enumerate(chains):
+        nl, iters, angle, lims = spec[:4]
         x = -6.0 + 3.0 * c
-        ik_first = (c == 3)                       # this IK bone is created (and therefore sorts) before its links
+        ik_first = spec[4] if len(spec) > 4 else (c == 3)   # this IK bone is created (and therefore sorts) before its links
         ikb = add_bone((x, 1.0, 0.3), 0, 0, capi.BONE_HAS_IK) if ik_first else None
         links = []
         par = 0

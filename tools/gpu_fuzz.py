@@ -1,6 +1,10 @@
 """GPU box: randomized model / motion configurations beyond the seeds the test-suite pins, each compared bit-for-bit
-with the CPU oracle (positions, normals, bone matrices, sampled poses, morph rates) in both output layouts.
-usage: python tools/gpu_fuzz.py [first_seed] [count]"""
+with the CPU oracle (positions, normals, bone matrices, sampled poses, morph rates).
+  phase "rig":  varied rigs through the fused update in both output layouts, plus MotionPlayer::SeekTime at random
+                times and the step-wise libmmd call sequence (must equal the fused path bit-for-bit)
+  phase "ik":   random CCD IK chains (1-5 links, 1-300 iterations, angle limits, per-axis limits with zero ranges /
+                swapped bounds / sub-quadrant ranges that select the three Euler orders)
+usage: python tools/gpu_fuzz.py [first_seed] [count] [rig|ik|all]"""
 import os, sys
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
@@ -12,9 +16,23 @@ from simple_mmd_renderer_b200.poser import Context, Frames, Model, Motion
 
 first = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 count = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+phase = sys.argv[3] if len(sys.argv) > 3 else "all"
 ctx = Context(0)
-bad = 0
-for seed in range(first, first + count):
+
+
+def same(a, b):
+    return np.array_equal(np.ascontiguousarray(a).view(np.uint32), np.ascontiguousarray(b).view(np.uint32))
+
+
+def check_slot(fr, k, ref):
+    ok = same(fr.download(k, capi.STREAM_POSITION), ref["pos"]) and same(fr.download(k, capi.STREAM_NORMAL), ref["nrm"])
+    ok &= same(fr.bone_matrices(k), ref["skin"]) and same(fr.bone_poses(k), ref["poses"])
+    if ref["rates"].size:
+        ok &= same(fr.morph_rates(k), ref["rates"])
+    return ok
+
+
+def rig_case(seed):
     rng = np.random.default_rng(1000 + seed)
     ik = int(rng.integers(0, 3))
     cfg = replace(synth.TINY_FULL, name=f"rand{seed}", config_id=200 + seed,
@@ -41,16 +59,75 @@ for seed in range(first, first + count):
     ok = True
     for k, f in enumerate(frames):
         ref = orc.run_frame(f)
-        ok &= np.array_equal(fr.download(k, capi.STREAM_POSITION).view(np.uint32), ref["pos"].view(np.uint32))
-        ok &= np.array_equal(fr.download(k, capi.STREAM_NORMAL).view(np.uint32), ref["nrm"].view(np.uint32))
-        ok &= np.array_equal(fr.bone_matrices(k).view(np.uint32), ref["skin"].view(np.uint32))
-        ok &= np.array_equal(fr.bone_poses(k).view(np.uint32), ref["poses"].view(np.uint32))
-        if ref["rates"].size:
-            ok &= np.array_equal(fr.morph_rates(k).view(np.uint32), ref["rates"].view(np.uint32))
-        ok &= np.array_equal(fi.download(k, capi.STREAM_INTERLEAVED).view(np.uint32), orc.repack_sokol32().view(np.uint32))
-    if not ok:
-        bad += 1
-        print(f"MISMATCH seed {seed}: {cfg}", flush=True)
+        ok &= check_slot(fr, k, ref)
+        ok &= same(fi.download(k, capi.STREAM_INTERLEAVED), orc.repack_sokol32())
+    # step-wise libmmd sequence == fused path
+    fused_pos = [fr.download(k, capi.STREAM_POSITION) for k in range(n_slots)]
+    fr.reset_posing(); fr.seek_frame(a, frames); fr.pre_physics_posing(); fr.post_physics_posing(); fr.deform()
+    for k in range(n_slots):
+        ok &= same(fr.download(k, capi.STREAM_POSITION), fused_pos[k])
+    # MotionPlayer::SeekTime at arbitrary times (sub-frame sampling)
+    times = rng.uniform(0.0, (cfg.n_frames + 3) / 30.0, n_slots)
+    fr.reset_posing(); fr.seek_time(a, times); fr.pre_physics_posing(); fr.post_physics_posing(); fr.deform()
+    for k, t in enumerate(times):
+        ref = orc.run_time(float(t))
+        ok &= same(fr.download(k, capi.STREAM_POSITION), ref["pos"]) and same(fr.bone_poses(k), ref["poses"])
+        ok &= same(fr.bone_matrices(k), ref["skin"])
     fr.close(); fi.close(); orc.close()
-print(f"fuzz: {count} configurations from seed {first}, {bad} mismatches", flush=True)
+    return ok, str(cfg)
+
+
+def ik_case(seed):
+    rng = np.random.default_rng(5000 + seed)
+    PI = float(np.pi)
+
+    def limit():
+        lo, hi = [0.0] * 3, [0.0] * 3
+        for ax in range(3):
+            kind = rng.random()
+            if kind < 0.35:
+                continue                                        # zero range: a fixed axis (poser_impl.inl:83-91)
+            if kind < 0.45:
+                lo[ax], hi[ax] = float(rng.uniform(0, 1.5)), float(rng.uniform(-1.5, 0))          # swapped
+            elif kind < 0.7:
+                lo[ax], hi[ax] = float(rng.uniform(-1.5, 0)), float(rng.uniform(0, 1.5))          # inside (-pi/2, pi/2)
+            else:
+                lo[ax], hi[ax] = float(rng.uniform(-PI, 0)), float(rng.uniform(0, PI))
+            if rng.random() < 0.1:
+                lo[ax] = 5e-8                                   # below the 1e-7 "is zero" threshold
+        return tuple(lo), tuple(hi)
+
+    chains = []
+    for _ in range(int(rng.integers(1, 6))):
+        nl = int(rng.integers(1, 6))
+        iters = int(rng.choice([1, 2, 3, 7, 15, 40, 41, 300]))
+        angle = float(rng.choice([0.05, 0.35, 1.0, 2.0, 3.5, 6.5]))
+        lims = [None if rng.random() < 0.4 else limit() for _ in range(nl)]
+        chains.append((nl, iters, angle, lims, bool(rng.random() < 0.25)))
+    model, motion = synth.make_ik_zoo(seed=1000 + seed, n_frames=24, chains=chains)
+    orc = oracle.Restatement(model, motion)
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    frames = [int(x) for x in rng.integers(0, 28, 6)]
+    fr = Frames(m, 1, len(frames))
+    fr.update(a, frames)
+    ok = True
+    for k, f in enumerate(frames):
+        ok &= check_slot(fr, k, orc.run_frame(f))
+    fr.close(); orc.close()
+    return ok, str(chains)
+
+
+bad = 0
+for name, fn in (("rig", rig_case), ("ik", ik_case)):
+    if phase not in (name, "all"):
+        continue
+    n_bad = 0
+    for seed in range(first, first + count):
+        ok, what = fn(seed)
+        if not ok:
+            n_bad += 1
+            print(f"MISMATCH {name} seed {seed}: {what}", flush=True)
+    print(f"fuzz {name}: {count} configurations from seed {first}, {n_bad} mismatches", flush=True)
+    bad += n_bad
 sys.exit(1 if bad else 0)

@@ -203,7 +203,9 @@ __device__ __forceinline__ void set_local(const SlotState& S, const BoneStatic& 
     L.m[3][1] = totT.y + s.local_offset[1];
     L.m[3][2] = totT.z + s.local_offset[2];
     if (s.flags & kHasParent) {
-        const Mat43 P = load_local(S.local + 3 * (size_t)s.parent);
+        // a bone that is its own parent multiplies the matrix it has just built by itself: libmmd's
+        // local_matrix_ = local_matrix_ * bone_images_[parent_].local_matrix_ names one object twice
+        const Mat43 P = (s.parent == b) ? L : load_local(S.local + 3 * (size_t)s.parent);
         L = m_mul(L, P);
     }
     store_local(S.local + 3 * (size_t)b, L);

@@ -612,7 +612,7 @@ def test_randomized_configs(ctx, seed):
         _check_frame(fr, k, orc.run_frame(f), f"{cfg.name} frame {f}")
 
 
-def test_bone_that_appends_from_itself(ctx):
+def test_bone_that_appends_from_or_is_parented_to_itself(ctx):
     """Found by tools/gpu_fuzz.py: UpdateBoneTransform writes total_rotation_ / total_translation_ before the append
     block reads the append parent's (poser_impl.inl:144-156), so a bone whose append parent is itself sees its own
     fresh values."""
@@ -626,7 +626,14 @@ def test_bone_that_appends_from_itself(ctx):
         flags[b] |= bits
         ap[b] = b
         ratio[b] = r
-    model.update(bone_flags=flags, bone_append_parent=ap, bone_append_ratio=ratio)
+    # the same in-place rule for the parent: local_matrix_ = local_matrix_ * bone_images_[parent_].local_matrix_
+    # (poser_impl.inl:164-166) squares the fresh matrix of a bone that is its own parent; and a parent may be a
+    # LATER bone, whose matrix is still the reset identity when the child is evaluated
+    parent = model["bone_parent"].copy()
+    parent[plain[2]] = plain[2]
+    parent[plain[12]] = plain[12]
+    parent[plain[4]] = plain[20]
+    model.update(bone_flags=flags, bone_append_parent=ap, bone_append_ratio=ratio, bone_parent=parent)
     orc = _oracle(model, motion)
     m = Model(ctx, model)
     a = Motion(m, motion)

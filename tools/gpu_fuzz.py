@@ -4,7 +4,10 @@ with the CPU oracle (positions, normals, bone matrices, sampled poses, morph rat
                 times and the step-wise libmmd call sequence (must equal the fused path bit-for-bit)
   phase "ik":   random CCD IK chains (1-5 links, 1-300 iterations, angle limits, per-axis limits with zero ranges /
                 swapped bounds / sub-quadrant ranges that select the three Euler orders)
-usage: python tools/gpu_fuzz.py [first_seed] [count] [rig|ik|all]"""
+  phase "topo": arbitrary skeleton topology - parents that are later bones or the bone itself, mixed transform levels,
+                append parents anywhere (self included), post-physics bones, IK chains over arbitrary bone sets that
+                share links and targets
+usage: python tools/gpu_fuzz.py [first_seed] [count] [rig|ik|topo|all]"""
 import os, sys
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
@@ -14,14 +17,15 @@ import oracle
 from simple_mmd_renderer_b200 import capi, synth
 from simple_mmd_renderer_b200.poser import Context, Frames, Model, Motion
 
-first = int(sys.argv[1]) if len(sys.argv) > 1 else 100
-count = int(sys.argv[2]) if len(sys.argv) > 2 else 100
-phase = sys.argv[3] if len(sys.argv) > 3 else "all"
-ctx = Context(0)
+ctx = None   # created by main()
 
 
 def same(a, b):
-    return np.array_equal(np.ascontiguousarray(a).view(np.uint32), np.ascontiguousarray(b).view(np.uint32))
+    """Bit-identical, except that NaN matches NaN regardless of payload: x86 and the GPU generate different default
+    NaN patterns (seen when a self-parented IK link squares its matrix every CCD step until it overflows)."""
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    na, nb_ = np.isnan(a), np.isnan(b)
+    return np.array_equal(na, nb_) and np.array_equal(a.view(np.uint32)[~na], b.view(np.uint32)[~nb_])
 
 
 def check_slot(fr, k, ref):
@@ -118,16 +122,94 @@ def ik_case(seed):
     return ok, str(chains)
 
 
-bad = 0
-for name, fn in (("rig", rig_case), ("ik", ik_case)):
-    if phase not in (name, "all"):
-        continue
-    n_bad = 0
-    for seed in range(first, first + count):
-        ok, what = fn(seed)
-        if not ok:
-            n_bad += 1
-            print(f"MISMATCH {name} seed {seed}: {what}", flush=True)
-    print(f"fuzz {name}: {count} configurations from seed {first}, {n_bad} mismatches", flush=True)
-    bad += n_bad
-sys.exit(1 if bad else 0)
+TOPO_MASK = int(os.environ.get("TOPO_MASK", "31"))   # 1 parents, 2 levels, 4 appends, 8 post-physics, 16 IK
+
+
+def topo_case_inputs(seed):
+    rng = np.random.default_rng(9000 + seed)
+    cfg = replace(synth.TINY_FULL, name=f"topo{seed}", config_id=400 + seed, n_bones=int(rng.integers(8, 60)),
+                  n_vertices=int(rng.integers(50, 1500)), ik_chains=0, n_frames=20, stress=bool(rng.integers(0, 2)),
+                  n_bone_morphs=int(rng.integers(0, 3)), n_group_morphs=0, n_uv_morphs=0, n_vertex_morphs=int(rng.integers(0, 6)))
+    model = dict(synth.make_model(cfg))
+    nb = int(model["n_bones"])
+    parent = model["bone_parent"].copy(); level = model["bone_transform_level"].copy()
+    flags = model["bone_flags"].copy(); ap = model["bone_append_parent"].copy(); ratio = model["bone_append_ratio"].copy()
+    for b in range(nb):
+        if rng.random() < 0.4 and (TOPO_MASK & 1):
+            parent[b] = int(rng.integers(-1, nb))            # any bone, itself and later ones included
+        if rng.random() < 0.3 and (TOPO_MASK & 2):
+            level[b] = int(rng.integers(0, 3))
+        if rng.random() < 0.2 and (TOPO_MASK & 4):
+            flags[b] |= int(rng.choice([capi.BONE_APPEND_ROTATE, capi.BONE_APPEND_TRANSLATE, capi.BONE_APPEND_ROTATE | capi.BONE_APPEND_TRANSLATE]))
+            ap[b] = int(rng.integers(0, nb))
+            ratio[b] = float(rng.choice([0.5, 1.0, -0.5, 0.25, 2.0]))
+        if rng.random() < 0.1 and (TOPO_MASK & 8):
+            flags[b] |= capi.BONE_POST_PHYSICS
+    n_ik = int(rng.integers(0, 4)) if (TOPO_MASK & 16) else 0
+    ik_target = np.full(nb, -1, np.int32); ik_iter = np.zeros(nb, np.int32); ik_angle = np.zeros(nb, np.float32)
+    ik_begin = np.zeros(nb, np.uint32); ik_count = np.zeros(nb, np.uint32)
+    l_bone, l_has, l_lo, l_hi = [], [], [], []
+    ik_bones = [int(x) for x in rng.choice(nb, n_ik, replace=False)] if n_ik else []
+    others = [b for b in range(nb) if b not in ik_bones]
+    for ikb in ik_bones:
+        if len(others) < 3: break
+        pick = [int(x) for x in rng.choice(others, min(len(others), int(rng.integers(2, 6))), replace=False)]
+        tgt, links = pick[0], pick[1:]
+        flags[ikb] |= capi.BONE_HAS_IK
+        ik_target[ikb] = tgt; ik_iter[ikb] = int(rng.choice([1, 3, 8, 20])); ik_angle[ikb] = float(rng.choice([0.3, 1.0, 2.0]))
+        ik_begin[ikb] = len(l_bone); ik_count[ikb] = len(links)
+        for l in links:
+            l_bone.append(l)
+            if rng.random() < 0.5:
+                l_has.append(0); l_lo.append((0, 0, 0)); l_hi.append((0, 0, 0))
+            else:
+                l_has.append(1)
+                lo = [float(rng.uniform(-2, 0)) if rng.random() < 0.6 else 0.0 for _ in range(3)]
+                hi = [float(rng.uniform(0, 2)) if lo[i] != 0.0 else 0.0 for i in range(3)]
+                l_lo.append(tuple(lo)); l_hi.append(tuple(hi))
+    model.update(bone_parent=parent, bone_transform_level=level, bone_flags=flags, bone_append_parent=ap, bone_append_ratio=ratio,
+                 ik_target=ik_target, ik_iterations=ik_iter, ik_angle_limit=ik_angle, ik_link_begin=ik_begin, ik_link_count=ik_count,
+                 n_ik_links=len(l_bone), ik_link_bone=np.asarray(l_bone, np.int32), ik_link_has_limit=np.asarray(l_has, np.uint8),
+                 ik_link_lo=np.asarray(l_lo, np.float32).reshape(-1, 3), ik_link_hi=np.asarray(l_hi, np.float32).reshape(-1, 3))
+    motion = synth.make_motion(cfg, model)
+    frames = [int(x) for x in rng.integers(0, 24, 4)]
+    return model, motion, frames
+
+
+def topo_case(seed):
+    model, motion, frames = topo_case_inputs(seed)
+    orc = oracle.Restatement(model, motion)
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    fr = Frames(m, 1, len(frames))
+    fr.update(a, frames)
+    ok = True
+    for k, f in enumerate(frames):
+        ok &= check_slot(fr, k, orc.run_frame(f))
+    fr.close(); orc.close()
+    return ok, f"topology seed {seed}"
+
+
+def main():
+    global ctx
+    first = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+    count = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+    phase = sys.argv[3] if len(sys.argv) > 3 else "all"
+    ctx = Context(0)
+    bad = 0
+    for name, fn in (("rig", rig_case), ("ik", ik_case), ("topo", topo_case)):
+        if phase not in (name, "all"):
+            continue
+        n_bad = 0
+        for seed in range(first, first + count):
+            ok, what = fn(seed)
+            if not ok:
+                n_bad += 1
+                print(f"MISMATCH {name} seed {seed}: {what}", flush=True)
+        print(f"fuzz {name}: {count} configurations from seed {first}, {n_bad} mismatches", flush=True)
+        bad += n_bad
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -7,7 +7,11 @@ with the CPU oracle (positions, normals, bone matrices, sampled poses, morph rat
   phase "topo": arbitrary skeleton topology - parents that are later bones or the bone itself, mixed transform levels,
                 append parents anywhere (self included), post-physics bones, IK chains over arbitrary bone sets that
                 share links and targets
-usage: python tools/gpu_fuzz.py [first_seed] [count] [rig|ik|topo|all]"""
+  phase "morph": random morph graphs (nested groups with negative / zero / sub-epsilon rates, bone morphs on any bone,
+                vertex morphs with repeated vertices) driven through SetBonePose / SetMorphPose with edge weights
+  phase "motion": random key-frame structure (empty / unsorted / repeated / far-away keys, extreme and linear Bezier
+                bytes, both quaternion hemispheres) sampled by SeekFrame and SeekTime, incl. far past the clip
+usage: python tools/gpu_fuzz.py [first_seed] [count] [rig|ik|topo|morph|motion|all]"""
 import os, sys
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
@@ -190,6 +194,168 @@ def topo_case(seed):
     return ok, f"topology seed {seed}"
 
 
+def morph_case_inputs(seed):
+    """Random morph graph on a small rig: vertex morphs with duplicate vertices, bone morphs on any bone (IK links
+    and IK bones included), group morphs nested up to four deep with negative / zero / below-epsilon / > 1 rates,
+    UV and material morphs in between; driven through SetBonePose / SetMorphPose with weights that include
+    negatives, 5e-8, 1e-7 and values above 1."""
+    rng = np.random.default_rng(7000 + seed)
+    cfg = replace(synth.TINY_FULL, name=f"morph{seed}", config_id=600 + seed, n_bones=int(rng.integers(14, 50)),
+                  n_vertices=int(rng.integers(30, 1200)), ik_chains=int(rng.integers(0, 3)), n_frames=10,
+                  stress=False, n_bone_morphs=0, n_group_morphs=0, n_uv_morphs=0, n_vertex_morphs=0)
+    model = dict(synth.make_model(cfg))
+    nv, nb = int(model["n_vertices"]), int(model["n_bones"])
+    nm = int(rng.integers(1, 24))
+    order = rng.permutation(nm)                 # group children must come later in this order: a DAG, no cycles
+    rank = np.empty(nm, np.int64); rank[order] = np.arange(nm)
+    mtype, mbegin, mcount = [], [], []
+    ve, be, ge, ue = [], [], [], []
+    for m in range(nm):
+        later = [int(x) for x in order[rank[m] + 1:]]
+        kind = rng.random()
+        if kind < 0.25 and later:
+            kids = [int(x) for x in rng.choice(later, min(len(later), int(rng.integers(1, 5))), replace=True)]
+            mtype.append(capi.MORPH_GROUP); mbegin.append(len(ge)); mcount.append(len(kids))
+            for k in kids:
+                ge.append((k, float(rng.choice([-0.5, 0.0, 1e-8, 0.25, 0.5, 1.0, 2.0]))))
+        elif kind < 0.45:
+            n = int(rng.integers(1, 5))
+            mtype.append(capi.MORPH_BONE); mbegin.append(len(be)); mcount.append(n)
+            for _ in range(n):
+                q = rng.normal(size=4); q /= np.linalg.norm(q)
+                be.append((int(rng.integers(0, nb)), tuple(rng.uniform(-1, 1, 3)), tuple(q)))
+        elif kind < 0.55:
+            n = int(rng.integers(1, 20))
+            mtype.append(capi.MORPH_UV); mbegin.append(len(ue)); mcount.append(n)
+            for _ in range(n):
+                ue.append((int(rng.integers(0, nv)), tuple(rng.uniform(-1, 1, 4))))
+        else:
+            n = int(rng.integers(1, max(2, nv // 2)))
+            mtype.append(capi.MORPH_VERTEX); mbegin.append(len(ve)); mcount.append(n)
+            for v in rng.integers(0, nv, n):     # with repeats
+                ve.append((int(v), tuple(rng.uniform(-0.5, 0.5, 3))))
+    def pool(items, dtype, fields):
+        a = np.zeros(len(items), dtype)
+        for i, it in enumerate(items):
+            for f, x in zip(fields, it):
+                a[f][i] = x
+        return a
+    model.update(
+        n_morphs=nm, morph_type=np.asarray(mtype, np.uint8), morph_entry_begin=np.asarray(mbegin, np.uint32),
+        morph_entry_count=np.asarray(mcount, np.uint32),
+        vertex_morph_entries=pool(ve, capi.VERTEX_MORPH_ENTRY, ("vertex", "offset")), n_vertex_morph_entries=len(ve),
+        bone_morph_entries=pool(be, capi.BONE_MORPH_ENTRY, ("bone", "translation", "rotation")), n_bone_morph_entries=len(be),
+        group_morph_entries=pool(ge, capi.GROUP_MORPH_ENTRY, ("morph", "rate")), n_group_morph_entries=len(ge),
+        uv_morph_entries=pool(ue, capi.UV_MORPH_ENTRY, ("vertex", "offset")), n_uv_morph_entries=len(ue))
+    poses = []
+    for _ in range(3):
+        nbp = int(rng.integers(0, nb))
+        bones = rng.choice(nb, nbp, replace=False).astype(np.int32)
+        q = rng.normal(size=(nbp, 4)); q[:, 3] += 2.0; q /= np.linalg.norm(q, axis=1, keepdims=True)
+        p7 = np.concatenate([rng.uniform(-1, 1, (nbp, 3)), q], 1).astype(np.float32)
+        morphs = np.arange(nm, dtype=np.int32)
+        w = rng.choice([-0.3, 0.0, 5e-8, 1e-7, 1.5e-7, 0.2, 0.5, 1.0, 1.7], nm).astype(np.float32)
+        poses.append((bones, p7, morphs, w))
+    return model, poses
+
+
+def morph_case(seed):
+    model, poses = morph_case_inputs(seed)
+    orc = oracle.Restatement(model, None)
+    m = Model(ctx, model)
+    fr = Frames(m, 1, len(poses))
+    fr.reset_posing()
+    for slot, (bones, p7, morphs, w) in enumerate(poses):
+        for b, p in zip(bones, p7):
+            fr.set_bone_pose(slot, int(b), p[:3], p[3:])
+        for i, x in zip(morphs, w):
+            fr.set_morph_pose(slot, int(i), float(x))
+    fr.pre_physics_posing(); fr.post_physics_posing(); fr.deform()
+    ok = True
+    for slot, (bones, p7, morphs, w) in enumerate(poses):
+        ref = orc.run_manual(bones, p7, morphs, w)
+        ok &= same(fr.download(slot, capi.STREAM_POSITION), ref["pos"]) and same(fr.download(slot, capi.STREAM_NORMAL), ref["nrm"])
+        ok &= same(fr.bone_matrices(slot), ref["skin"])
+    fr.close(); orc.close()
+    return ok, f"morph graph seed {seed}"
+
+
+def motion_case_inputs(seed):
+    """Random key-frame structure: 0-7 keys per track (0 = registered but empty), unsorted, repeated frames (last one
+    wins), frames far beyond the others, Bezier bytes over the whole 0..127 range plus exact-linear quadruples,
+    rotations in both hemispheres (NLerp's dot < 0 branch) and repeated poses; morph weights with negatives."""
+    rng = np.random.default_rng(11000 + seed)
+    cfg = replace(synth.TINY, name=f"motion{seed}", config_id=800 + seed, n_bones=int(rng.integers(6, 40)),
+                  n_vertices=int(rng.integers(20, 600)), n_vertex_morphs=int(rng.integers(0, 8)), n_frames=30)
+    model = synth.make_model(cfg)
+    nb, nm = int(model["n_bones"]), int(model["n_morphs"])
+    t_bone, t_begin, t_count, keys = [], [], [], []
+    for b in range(nb):
+        if rng.random() < 0.2:
+            continue
+        n = int(rng.integers(0, 8))
+        fr = rng.integers(0, 40, n)
+        if n and rng.random() < 0.3:
+            fr[rng.integers(0, n)] = int(rng.choice([0, 1000, 100000]))
+        if n > 1 and rng.random() < 0.4:
+            fr[1] = fr[0]
+        k = np.zeros(n, capi.BONE_KEY)
+        k["frame"] = fr
+        k["translation"] = rng.uniform(-2, 2, (n, 3)) * (rng.random((n, 1)) < 0.5)
+        q = rng.normal(size=(n, 4)); q /= np.maximum(np.linalg.norm(q, axis=1, keepdims=True), 1e-9)
+        if n > 1 and rng.random() < 0.3:
+            q[1] = q[0]
+        k["rotation"] = q
+        ip = rng.integers(0, 128, (n, 4, 4))
+        lin = rng.random((n, 4)) < 0.3
+        ip[lin] = [20, 20, 107, 107]
+        ext = rng.random((n, 4)) < 0.1
+        ip[ext] = rng.choice([0, 127], (int(ext.sum()), 4))
+        k["interp"] = ip
+        t_bone.append(b); t_begin.append(sum(x.size for x in keys)); t_count.append(n); keys.append(k)
+    bone_keys = np.concatenate(keys) if keys else np.zeros(0, capi.BONE_KEY)
+    m_morph, m_begin, m_count, mkeys = [], [], [], []
+    for m in range(nm):
+        if rng.random() < 0.2:
+            continue
+        n = int(rng.integers(0, 6))
+        k = np.zeros(n, capi.MORPH_KEY)
+        k["frame"] = rng.integers(0, 40, n)
+        k["weight"] = rng.choice([-0.5, 0.0, 5e-8, 0.3, 1.0, 1.5], n)
+        m_morph.append(m); m_begin.append(sum(x.size for x in mkeys)); m_count.append(n); mkeys.append(k)
+    morph_keys = np.concatenate(mkeys) if mkeys else np.zeros(0, capi.MORPH_KEY)
+    motion = dict(n_bone_tracks=len(t_bone), bone_track_bone=np.asarray(t_bone, np.int32),
+                  bone_track_key_begin=np.asarray(t_begin, np.uint32), bone_track_key_count=np.asarray(t_count, np.uint32),
+                  n_bone_keys=bone_keys.size, bone_keys=bone_keys,
+                  n_morph_tracks=len(m_morph), morph_track_morph=np.asarray(m_morph, np.int32),
+                  morph_track_key_begin=np.asarray(m_begin, np.uint32), morph_track_key_count=np.asarray(m_count, np.uint32),
+                  n_morph_keys=morph_keys.size, morph_keys=morph_keys)
+    frames = [int(x) for x in rng.integers(0, 45, 5)] + [int(rng.choice([999, 1000, 1001, 200000]))]
+    times = [float(x) for x in rng.uniform(0, 1.5, 5)] + [float(rng.choice([0.0, 1.0 / 30.0, 33.34, 7000.0]))]
+    return model, motion, frames, times
+
+
+def motion_case(seed):
+    model, motion, frames, times = motion_case_inputs(seed)
+    orc = oracle.Restatement(model, motion)
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    fr = Frames(m, 1, len(frames))
+    fr.update(a, frames)
+    ok = True
+    for k, f in enumerate(frames):
+        ok &= check_slot(fr, k, orc.run_frame(f))
+    fr.reset_posing(); fr.seek_time(a, times); fr.pre_physics_posing(); fr.post_physics_posing(); fr.deform()
+    for k, t in enumerate(times):
+        ref = orc.run_time(t)
+        ok &= same(fr.download(k, capi.STREAM_POSITION), ref["pos"]) and same(fr.bone_poses(k), ref["poses"])
+        ok &= same(fr.bone_matrices(k), ref["skin"])
+        if ref["rates"].size:
+            ok &= same(fr.morph_rates(k), ref["rates"])
+    fr.close(); orc.close()
+    return ok, f"motion structure seed {seed}"
+
+
 def main():
     global ctx
     first = int(sys.argv[1]) if len(sys.argv) > 1 else 100
@@ -197,7 +363,7 @@ def main():
     phase = sys.argv[3] if len(sys.argv) > 3 else "all"
     ctx = Context(0)
     bad = 0
-    for name, fn in (("rig", rig_case), ("ik", ik_case), ("topo", topo_case)):
+    for name, fn in (("rig", rig_case), ("ik", ik_case), ("topo", topo_case), ("morph", morph_case), ("motion", motion_case)):
         if phase not in (name, "all"):
             continue
         n_bad = 0

@@ -6,6 +6,7 @@
 //
 // Compiled with -fmad=false: the fp32 expression trees are libmmd's, un-contracted.
 #include <cstdint>
+#include <cstdlib>
 
 #include "device_types.cuh"
 #include "kernels.cuh"
@@ -1146,7 +1147,8 @@ cudaError_t launch_hierarchy(cudaStream_t st, const DevModel& M, const DevFrames
                              bool prologue) {
     if (F.n_slots == 0) return cudaSuccess;
     const size_t cta_smem = hier_cta_smem_bytes(M.nb, M.n_link_slots, M.n_morph_slots, M.n_ops, M.n_waves);
-    if (cta_smem <= kHierCtaSmemLimit) {
+    static const bool force_global = std::getenv("MMDGPU_FORCE_FALLBACKS") != nullptr;  // test knob
+    if (cta_smem <= kHierCtaSmemLimit && !force_global) {
         // small skeletons: narrower CTAs, so that more slots are resident per SM (a CCD IK solve is one thread)
         const uint32_t threads = M.nb <= 512 ? 128u : kHierCtaThreads;
         hierarchy_cta_kernel<<<F.n_slots, threads, cta_smem, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u);

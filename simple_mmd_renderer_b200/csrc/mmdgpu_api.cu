@@ -200,7 +200,9 @@ mmdgpu_status upload_model(mmdgpu_model* m) {
 
     // A tile that touches more bones than fit the staged palettes (4 slots x 2 buffers x 48 B per bone next to the
     // staging tiles) switches the whole model to global bone ids read straight from the slot's palette.
-    D.global_palette = (!p.extensions && p.max_tile_bones > kMaxStagedTileBones) ? 1u : 0u;
+    // MMDGPU_FORCE_FALLBACKS=1 (test knob, tools/gpu_fuzz.py): take the large-model code paths on small models
+    const bool force = std::getenv("MMDGPU_FORCE_FALLBACKS") != nullptr && !p.extensions;
+    D.global_palette = (!p.extensions && (p.max_tile_bones > kMaxStagedTileBones || force)) ? 1u : 0u;
     if (p.extensions && p.max_tile_bones > kMaxStagedTileBones)
         return set_err(ctx, MMDGPU_ERR_UNSUPPORTED, "extensions with more than " + std::to_string(kMaxStagedTileBones) +
                                                         " distinct bones in one 512-vertex tile");

@@ -11,7 +11,8 @@ with the CPU oracle (positions, normals, bone matrices, sampled poses, morph rat
                 vertex morphs with repeated vertices) driven through SetBonePose / SetMorphPose with edge weights
   phase "motion": random key-frame structure (empty / unsorted / repeated / far-away keys, extreme and linear Bezier
                 bytes, both quaternion hemispheres) sampled by SeekFrame and SeekTime, incl. far past the clip
-usage: python tools/gpu_fuzz.py [first_seed] [count] [rig|ik|topo|morph|motion|all]"""
+  phase "crowd": instances x frames with per-instance clips, range mode with a stride and per-slot frame ids
+usage: python tools/gpu_fuzz.py [first_seed] [count] [rig|ik|topo|morph|motion|crowd|all]"""
 import os, sys
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
@@ -356,6 +357,44 @@ def motion_case(seed):
     return ok, f"motion structure seed {seed}"
 
 
+def crowd_case(seed):
+    """Instances x frames: per-instance clips, range mode with a stride, then per-slot frame ids on the same object."""
+    rng = np.random.default_rng(13000 + seed)
+    cfg = replace(synth.TINY_FULL, name=f"crowd{seed}", config_id=900 + seed, n_bones=int(rng.integers(12, 60)),
+                  n_vertices=int(rng.integers(1, 1500)), n_frames=int(rng.integers(10, 40)), ik_chains=int(rng.integers(0, 2)),
+                  stress=bool(rng.integers(0, 2)))
+    model = synth.make_model(cfg)
+    ni, nf, stride = int(rng.integers(1, 6)), int(rng.integers(1, 8)), int(rng.integers(1, 4))
+    motions = [synth.make_motion(cfg, model, instance=i) for i in range(ni)]
+    m = Model(ctx, model)
+    clips = [Motion(m, mo) for mo in motions]
+    orcs = [oracle.Restatement(model, mo) for mo in motions]
+    first = [int(x) for x in rng.integers(0, cfg.n_frames, ni)]
+    layout = capi.LAYOUT_SOA_POS_NRM if seed % 2 == 0 else capi.LAYOUT_INTERLEAVED_SOKOL32
+    fr = Frames(m, ni, nf, layout)
+    fr.update_range(clips, first, stride)
+    ok = True
+
+    def check(slot, orc, f):
+        ref = orc.run_frame(f)
+        good = same(fr.bone_matrices(slot), ref["skin"])
+        if layout == capi.LAYOUT_SOA_POS_NRM:
+            return good and same(fr.download(slot, capi.STREAM_POSITION), ref["pos"]) and same(fr.download(slot, capi.STREAM_NORMAL), ref["nrm"])
+        return good and same(fr.download(slot, capi.STREAM_INTERLEAVED), orc.repack_sokol32())
+    for i in range(ni):
+        for k in range(nf):
+            ok &= check(i * nf + k, orcs[i], first[i] + k * stride)
+    per_slot = [int(x) for x in rng.integers(0, cfg.n_frames + 3, ni * nf)]
+    fr.update(clips, per_slot)
+    for i in range(ni):
+        for k in range(nf):
+            ok &= check(i * nf + k, orcs[i], per_slot[i * nf + k])
+    fr.close()
+    for o in orcs:
+        o.close()
+    return ok, f"crowd seed {seed}: {ni} instances x {nf} frames, stride {stride}"
+
+
 def main():
     global ctx
     first = int(sys.argv[1]) if len(sys.argv) > 1 else 100
@@ -363,7 +402,7 @@ def main():
     phase = sys.argv[3] if len(sys.argv) > 3 else "all"
     ctx = Context(0)
     bad = 0
-    for name, fn in (("rig", rig_case), ("ik", ik_case), ("topo", topo_case), ("morph", morph_case), ("motion", motion_case)):
+    for name, fn in (("rig", rig_case), ("ik", ik_case), ("topo", topo_case), ("morph", morph_case), ("motion", motion_case), ("crowd", crowd_case)):
         if phase not in (name, "all"):
             continue
         n_bad = 0

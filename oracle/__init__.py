@@ -63,6 +63,8 @@ class _Session:
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         self._run_time = getattr(self.lib, p + "run_time")
         self._run_time.argtypes = [C.c_void_p, C.c_double] + [C.c_void_p] * 5
+        self._override = getattr(self.lib, p + "run_frame_override")
+        self._override.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32] + [C.c_void_p] * 7
         self._skin = getattr(self.lib, p + "get_skinning")
         self._skin.argtypes = [C.c_void_p] * 4
         self._ik = getattr(self.lib, p + "get_ik_class")
@@ -116,6 +118,18 @@ class _Session:
                    rates=np.zeros((self.nm,), np.float32))
         self._run_time(self.h, float(seconds), _fp(out["pos"]), _fp(out["nrm"]), _fp(out["skin"]), _fp(out["poses"]),
                        _fp(out["rates"]))
+        return out
+
+    def run_frame_override(self, frame: int, bones, skin16, local16=None) -> dict:
+        """ResetPosing; SeekFrame; Pre; overwrite the listed bones' skinning (and local) matrices as a host physics
+        reactor would (mmd-bullet_impl.inl:34-56); Post; Deform."""
+        bones = np.ascontiguousarray(bones, np.int32)
+        skin16 = np.ascontiguousarray(skin16, np.float32).reshape(bones.size, 16)
+        loc = None if local16 is None else np.ascontiguousarray(local16, np.float32).reshape(bones.size, 16)
+        out = dict(pos=np.zeros((self.nv, 3), np.float32), nrm=np.zeros((self.nv, 3), np.float32),
+                   skin=np.zeros((self.nb, 16), np.float32), local=np.zeros((self.nb, 16), np.float32))
+        self._override(self.h, int(frame), bones.size, _fp(bones), _fp(skin16), _fp(loc), _fp(out["pos"]), _fp(out["nrm"]),
+                       _fp(out["skin"]), _fp(out["local"]))
         return out
 
     def run_manual(self, bones, poses7, morphs, weights) -> dict:

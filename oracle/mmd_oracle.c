@@ -882,6 +882,22 @@ EXPORT int port_run_frame(struct port_session* p, uint32_t frame, float* pos, fl
     copy_out(&p->s, pos, nrm, skin, local, poses, rates);
     return 0;
 }
+/* Host physics hand-back between Pre and Post (mmd-bullet_impl.inl:34-56): skinning / local matrices overwritten in place. */
+EXPORT int port_run_frame_override(struct port_session* p, uint32_t frame, uint32_t n, const int32_t* bones, const float* skin16,
+                                   const float* local16_or_null, float* pos, float* nrm, float* skin, float* local) {
+    state_t* s = &p->s;
+    reset_poses(s);
+    seek_frame(s, frame);
+    pre_physics(s);
+    for (uint32_t i = 0; i < n; ++i) {
+        memcpy(s->skin + 16 * (size_t)bones[i], skin16 + 16 * (size_t)i, 64);
+        if (local16_or_null) memcpy(s->local + 16 * (size_t)bones[i], local16_or_null + 16 * (size_t)i, 64);
+    }
+    post_physics(s);
+    deform(s);
+    copy_out(s, pos, nrm, skin, local, NULL, NULL);
+    return 0;
+}
 EXPORT int port_run_time(struct port_session* p, double seconds, float* pos, float* nrm, float* skin, float* poses,
                          float* rates) {
     state_t* s = &p->s;

@@ -70,6 +70,14 @@ public:
         BoneImageReference im = GetPoserBoneImage(p, b);
         for (int k = 0; k < 16; ++k) out16[k] = im.local_matrix_.v[k];
     }
+    // what a host physics reactor does between Pre and Post (PoserMotionState::Synchronize / Fix,
+    // L/../mmd-bullet/mmd-bullet_impl.inl:34-56): overwrite a bone's skinning and local matrices in place
+    static void Override(Poser& p, size_t b, const float* skin16, const float* local16) {
+        BoneImageReference im = GetPoserBoneImage(p, b);
+        for (int k = 0; k < 16; ++k) im.skinning_matrix_.v[k] = skin16[k];
+        if (local16)
+            for (int k = 0; k < 16; ++k) im.local_matrix_.v[k] = local16[k];
+    }
     static void Pose(Poser& p, size_t b, float* out7) {
         BoneImageReference im = GetPoserBoneImage(p, b);
         for (int k = 0; k < 3; ++k) out7[k] = im.translation_.v[k];
@@ -368,6 +376,29 @@ __attribute__((visibility("default"))) int ref_run_frame(ref_session* s, uint32_
             std::wstring nmw = s->model.GetMorph(m).GetName();
             rates[m] = s->motion.IsMorphRegistered(nmw) ? s->motion.GetMorphPose(nmw, (size_t)frame).GetWeight() : 0.0f;
         }
+    }
+    return 0;
+}
+
+// main.cpp:1788-1821 with a host reactor in the middle: ResetPosing, SeekFrame, PrePhysicsPosing, then the listed
+// bones' skinning (and optionally local) matrices are overwritten as PhysicsReactor::React would, PostPhysicsPosing, Deform.
+__attribute__((visibility("default"))) int ref_run_frame_override(ref_session* s, uint32_t frame, uint32_t n, const int32_t* bones,
+                                                                   const float* skin16, const float* local16_or_null,
+                                                                   float* pos, float* nrm, float* skin, float* local) {
+    Poser& p = *s->poser;
+    p.ResetPosing();
+    s->player->SeekFrame(frame);
+    p.PrePhysicsPosing();
+    for (uint32_t i = 0; i < n; ++i)
+        Spy::Override(p, (size_t)bones[i], skin16 + 16 * i, local16_or_null ? local16_or_null + 16 * i : nullptr);
+    p.PostPhysicsPosing();
+    p.Deform();
+    size_t nv = s->model.GetVertexNum(), nb = s->model.GetBoneNum();
+    if (pos) memcpy(pos, p.pose_image.coordinates.data(), nv * 12);
+    if (nrm) memcpy(nrm, p.pose_image.normals.data(), nv * 12);
+    for (size_t b = 0; b < nb; ++b) {
+        if (skin) Spy::SkinningMatrix(p, b, skin + 16 * b);
+        if (local) Spy::LocalMatrix(p, b, local + 16 * b);
     }
     return 0;
 }

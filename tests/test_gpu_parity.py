@@ -642,3 +642,55 @@ def test_bone_that_appends_from_or_is_parented_to_itself(ctx):
     fr.update(a, frames)
     for k, f in enumerate(frames):
         _check_frame(fr, k, orc.run_frame(f), f"self-append frame {f}")
+
+
+@pytest.mark.parametrize("name,seed", [("tiny_full", 0), ("tiny_full", 1), ("small", 2), ("C2", 3)])
+def test_physics_hand_back_matches_libmmd_bit_for_bit(ctx, name, seed):
+    """SURVEY 8f-3: what PhysicsReactor::React does between Pre and Post (PoserMotionState::Synchronize / Fix,
+    mmd-bullet_impl.inl:34-56) is to overwrite skinning_matrix_ and local_matrix_ of the simulated bones in place.  The
+    oracle does exactly that through libmmd's friend accessor; here the same matrices go through
+    mmdgpu_set_skinning_matrix_override.  Post-physics bones then chain off the overridden local matrices and Deform
+    uses the overridden skinning matrices: positions, normals and every bone matrix must be bit-identical."""
+    cfg, model, motion = synth_case(name)
+    rng = np.random.default_rng(500 + seed)
+    nb = int(model["n_bones"])
+    post = np.flatnonzero(model["bone_flags"] & capi.BONE_POST_PHYSICS)
+    pre = np.flatnonzero((model["bone_flags"] & capi.BONE_POST_PHYSICS) == 0)
+    assert post.size > 0
+    # parents of post-physics bones (their children re-evaluate on top of the override) plus a few others
+    parents = [int(model["bone_parent"][b]) for b in post if int(model["bone_parent"][b]) in set(pre.tolist())]
+    bones = sorted(set(parents[:4] + [int(x) for x in rng.choice(pre, 4, replace=False)]))
+
+    def rigid():
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        x, y, z, w = q
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y + z * w), 2 * (x * z - y * w)],
+                      [2 * (x * y - z * w), 1 - 2 * (x * x + z * z), 2 * (y * z + x * w)],
+                      [2 * (x * z + y * w), 2 * (y * z - x * w), 1 - 2 * (x * x + y * y)]])
+        M = np.eye(4, dtype=np.float32)
+        M[:3, :3] = R
+        M[3, :3] = rng.uniform(-3, 3, 3)
+        return M
+    skins = np.stack([rigid() for _ in bones]).astype(np.float32)
+    locals_ = np.stack([rigid() for _ in bones]).astype(np.float32)
+    orc = _oracle(model, motion)
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    frames = [4, 21]
+    fr = Frames(m, 1, len(frames))
+    for with_local in (True, False):
+        fr.reset_posing()
+        fr.seek_frame(a, frames)
+        fr.pre_physics_posing()
+        for slot in range(len(frames)):
+            for i, b in enumerate(bones):
+                fr.set_skinning_matrix_override(slot, b, skins[i], locals_[i] if with_local else None)
+        fr.post_physics_posing()
+        fr.deform()
+        for slot, f in enumerate(frames):
+            ref = orc.run_frame_override(f, bones, skins.reshape(-1, 16), locals_.reshape(-1, 16) if with_local else None)
+            what = f"{name} frame {f} override (local={with_local})"
+            assert_bitwise(fr.bone_local_matrices(slot), ref["local"], what + " local matrices")
+            assert_bitwise(fr.bone_matrices(slot), ref["skin"], what + " skinning matrices")
+            assert_bitwise(fr.download(slot, capi.STREAM_POSITION), ref["pos"], what + " positions")
+            assert_bitwise(fr.download(slot, capi.STREAM_NORMAL), ref["nrm"], what + " normals")

@@ -73,6 +73,24 @@ def test_restatement_manual_posing_matches_libmmd():
         assert_bitwise(p[k], r[k], f"manual {k}")
 
 
+@pytest.mark.skipif(not oracle.have_reference(), reason="libmmd reference harness not built (needs /root/reference)")
+@pytest.mark.parametrize("with_local", [True, False])
+def test_restatement_physics_hand_back_matches_libmmd(with_local):
+    """Skinning / local matrices overwritten between Pre and Post, as a host physics reactor does
+    (mmd-bullet_impl.inl:34-56): post-physics children and Deform must see them the same way in both checkers."""
+    cfg, model, motion = synth_case("tiny_full")
+    rng = np.random.default_rng(8)
+    pre = np.flatnonzero((model["bone_flags"] & 0x1000) == 0)
+    bones = rng.choice(pre, 8, replace=False).astype(np.int32)
+    skin = rng.normal(size=(8, 16)).astype(np.float32)
+    local = rng.normal(size=(8, 16)).astype(np.float32) if with_local else None
+    for f in (0, 14, 41):
+        r = oracle.Reference(model, motion).run_frame_override(f, bones, skin, local)
+        p = oracle.Restatement(model, motion).run_frame_override(f, bones, skin, local)
+        for k in r:
+            assert_bitwise(p[k], r[k], f"hand-back frame {f} {k}")
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_restatement_seek_time_matches_golden(name):
     """MotionPlayer::SeekTime(double): sub-frame sampling, barycentre in double, no key-frame snapping."""

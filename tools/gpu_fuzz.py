@@ -12,7 +12,8 @@ with the CPU oracle (positions, normals, bone matrices, sampled poses, morph rat
   phase "motion": random key-frame structure (empty / unsorted / repeated / far-away keys, extreme and linear Bezier
                 bytes, both quaternion hemispheres) sampled by SeekFrame and SeekTime, incl. far past the clip
   phase "crowd": instances x frames with per-instance clips, range mode with a stride and per-slot frame ids
-usage: python tools/gpu_fuzz.py [first_seed] [count] [rig|ik|topo|morph|motion|crowd|all]"""
+  phase "ext":   extensions = 1: non-extension vertices bit-exact, SDEF / QDEF / UV / material images vs the fp64 restatement
+usage: python tools/gpu_fuzz.py [first_seed] [count] [rig|ik|topo|morph|motion|crowd|ext|all]"""
 import os, sys
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
@@ -395,6 +396,54 @@ def crowd_case(seed):
     return ok, f"crowd seed {seed}: {ni} instances x {nf} frames, stride {stride}"
 
 
+def ext_case(seed):
+    """extensions = 1 (parity unpinned): vertices that are not SDEF / QDEF stay bit-identical to the oracle; SDEF, QDEF
+    and UV results are compared with the fp64 restatement of the documented formulas (tests/ext_reference.py, 1e-4)."""
+    import ext_reference as xr
+    rng = np.random.default_rng(17000 + seed)
+    cfg = replace(synth.TINY_FULL, name=f"ext{seed}", config_id=1100 + seed, n_bones=int(rng.integers(12, 80)),
+                  n_vertices=int(rng.integers(50, 1500)), n_vertex_morphs=int(rng.integers(0, 10)),
+                  n_uv_morphs=int(rng.integers(0, 4)), n_group_morphs=int(rng.integers(0, 2)),
+                  n_bone_morphs=int(rng.integers(0, 2)), ik_chains=int(rng.integers(0, 2)), n_frames=30,
+                  binding=("coherent", "random")[int(rng.integers(0, 2))], stress=bool(rng.integers(0, 2)))
+    if cfg.n_group_morphs and cfg.n_vertex_morphs + cfg.n_uv_morphs + cfg.n_bone_morphs < 3:
+        cfg = replace(cfg, n_group_morphs=0)
+    model = synth.add_material_morphs(synth.make_model(cfg), n_materials=int(rng.integers(1, 6)), seed=seed)
+    motion = synth.make_motion(cfg, model)
+    orc = oracle.Restatement(model, motion)
+    m = Model(ctx, model, extensions=True)
+    a = Motion(m, motion)
+    frames = [int(x) for x in rng.integers(0, 33, 3)]
+    fr = Frames(m, 1, len(frames))
+    fr.update(a, frames)
+    t_norm, ids, _ = orc.skinning()
+    is_sdef = t_norm == capi.SKIN_SDEF
+    is_qdef = model["skin_type"] == capi.SKIN_QDEF
+    plain = ~(is_sdef | is_qdef)
+    ok = True
+    tol = dict(rtol=1e-4, atol=1e-4)
+    for k, f in enumerate(frames):
+        want = orc.run_frame(f)
+        pos, nrm, skin = fr.download(k, capi.STREAM_POSITION), fr.download(k, capi.STREAM_NORMAL), fr.bone_matrices(k)
+        ok &= same(skin, want["skin"]) and same(pos[plain], want["pos"][plain]) and same(nrm[plain], want["nrm"][plain])
+        T = xr.bone_transforms(skin)
+        rates = fr.morph_rates(k)
+        dv, duv = xr.morph_images(model, rates)
+        P = model["position"].astype(np.float64) + dv
+        N = model["normal"].astype(np.float64)
+        for i in np.flatnonzero(is_sdef)[:40]:
+            p, n = xr.sdef(P[i], N[i], int(ids[i, 0]), int(ids[i, 1]), float(model["weight"][i, 0]), model["sdef_c"][i].astype(np.float64),
+                           model["sdef_r0"][i].astype(np.float64), model["sdef_r1"][i].astype(np.float64), T)
+            ok &= np.allclose(pos[i], p, **tol) and np.allclose(nrm[i], n, **tol)
+        for i in np.flatnonzero(is_qdef)[:40]:
+            p, n = xr.qdef(P[i], N[i], [int(x) for x in model["bone_id"][i]], model["weight"][i].astype(np.float64), T)
+            ok &= np.allclose(pos[i], p, **tol) and np.allclose(nrm[i], n, **tol)
+        ok &= np.allclose(fr.download(k, capi.STREAM_UV), model["uv"].astype(np.float64) + duv, rtol=1e-5, atol=1e-5)
+        ok &= np.allclose(fr.material_images(k), xr.material_images(model, rates), rtol=1e-4, atol=1e-5)
+    fr.close(); orc.close()
+    return ok, str(cfg)
+
+
 def main():
     global ctx
     first = int(sys.argv[1]) if len(sys.argv) > 1 else 100
@@ -402,7 +451,7 @@ def main():
     phase = sys.argv[3] if len(sys.argv) > 3 else "all"
     ctx = Context(0)
     bad = 0
-    for name, fn in (("rig", rig_case), ("ik", ik_case), ("topo", topo_case), ("morph", morph_case), ("motion", motion_case), ("crowd", crowd_case)):
+    for name, fn in (("rig", rig_case), ("ik", ik_case), ("topo", topo_case), ("morph", morph_case), ("motion", motion_case), ("crowd", crowd_case), ("ext", ext_case)):
         if phase not in (name, "all"):
             continue
         n_bad = 0

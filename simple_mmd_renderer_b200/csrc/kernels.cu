@@ -1165,31 +1165,29 @@ size_t skin_smem_bytes(const DevModel& M, int layout) {
            2 * (size_t)M.n_nodes_pad * 16;
 }
 
+// The dynamic shared-memory opt-in is an attribute of the kernel function (per device), not of a launch: every model
+// of the process shares it.  It is therefore raised to the device limit once, never to one model's requirement (a
+// smaller model loaded later would otherwise lower it under an earlier, larger one).
 template <int LAYOUT, bool EXT, bool PALG>
-static cudaError_t skin_opt_in(const DevModel& M) {
-    return cudaFuncSetAttribute(skin_kernel<LAYOUT, EXT, PALG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)skin_smem_bytes(M, LAYOUT));
+static cudaError_t skin_opt_in(int limit) {
+    return cudaFuncSetAttribute(skin_kernel<LAYOUT, EXT, PALG>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
 }
 
 cudaError_t prepare_skin_kernels(const DevModel& M) {
-    const size_t cta_smem = hier_cta_smem_bytes(M.nb, M.n_link_slots, M.n_morph_slots, M.n_ops, M.n_waves);
-    cudaError_t e = cudaSuccess;
-    if (cta_smem <= kHierCtaSmemLimit) {
-        // opt in to the largest size any model of this process may need; the attribute is per function and device
-        e = cudaFuncSetAttribute(hierarchy_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHierCtaSmemLimit);
-        if (e != cudaSuccess) return e;
-    }
+    (void)M;
+    int dev = 0, limit = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+    const int hier = limit < (int)kHierCtaSmemLimit ? limit : (int)kHierCtaSmemLimit;
+    if ((e = cudaFuncSetAttribute(hierarchy_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hier)) != cudaSuccess) return e;
     constexpr int SOA = MMDGPU_LAYOUT_SOA_POS_NRM, I32 = MMDGPU_LAYOUT_INTERLEAVED_SOKOL32;
-    if (M.extensions) {
-        if ((e = skin_opt_in<SOA, true, false>(M)) != cudaSuccess) return e;
-        return skin_opt_in<I32, true, false>(M);
-    }
-    if (M.global_palette) {
-        if ((e = skin_opt_in<SOA, false, true>(M)) != cudaSuccess) return e;
-        return skin_opt_in<I32, false, true>(M);
-    }
-    if ((e = skin_opt_in<SOA, false, false>(M)) != cudaSuccess) return e;
-    return skin_opt_in<I32, false, false>(M);
+    if ((e = skin_opt_in<SOA, true, false>(limit)) != cudaSuccess) return e;
+    if ((e = skin_opt_in<I32, true, false>(limit)) != cudaSuccess) return e;
+    if ((e = skin_opt_in<SOA, false, true>(limit)) != cudaSuccess) return e;
+    if ((e = skin_opt_in<I32, false, true>(limit)) != cudaSuccess) return e;
+    if ((e = skin_opt_in<SOA, false, false>(limit)) != cudaSuccess) return e;
+    return skin_opt_in<I32, false, false>(limit);
 }
 
 cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, int layout, uint32_t slots_per_cta) {

@@ -694,3 +694,61 @@ def test_physics_hand_back_matches_libmmd_bit_for_bit(ctx, name, seed):
             assert_bitwise(fr.bone_matrices(slot), ref["skin"], what + " skinning matrices")
             assert_bitwise(fr.download(slot, capi.STREAM_POSITION), ref["pos"], what + " positions")
             assert_bitwise(fr.download(slot, capi.STREAM_NORMAL), ref["nrm"], what + " normals")
+
+
+def test_independent_contexts_on_concurrent_host_threads():
+    """include/mmdgpu.h threading contract: one context per host thread, different contexts are independent.  Four
+    threads each own a context, a model and a frames object and run updates concurrently (ctypes releases the GIL)."""
+    import threading
+    from simple_mmd_renderer_b200.poser import Context
+    cases = [synth_case(n) for n in ("tiny", "tiny_full", "small", "ik_zoo")]
+    errors, results = [], {}
+
+    def worker(i):
+        try:
+            cfg, model, motion = cases[i]
+            c = Context(0)
+            m = Model(c, model)
+            a = Motion(m, motion)
+            fr = Frames(m, 1, 6)
+            out = None
+            for rep in range(20):
+                frames = [(rep * 7 + k * 3) % 40 for k in range(6)]
+                fr.update(a, frames)
+                out = (frames, [fr.download(k, capi.STREAM_POSITION) for k in range(6)], [fr.bone_matrices(k) for k in range(6)])
+            results[i] = out
+        except Exception as e:       # noqa: BLE001 - reported below
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for i, (cfg, model, motion) in enumerate(cases):
+        orc = _oracle(model, motion)
+        frames, pos, skin = results[i]
+        for k, f in enumerate(frames):
+            ref = orc.run_frame(f)
+            assert_bitwise(pos[k], ref["pos"], f"thread {i} frame {f} positions")
+            assert_bitwise(skin[k], ref["skin"], f"thread {i} frame {f} matrices")
+
+
+def test_models_of_different_sizes_coexist(ctx):
+    """The shared-memory opt-in belongs to the kernel, not to a model: loading a small model after a large one must
+    not shrink what the large one may launch with (found by the concurrent-contexts test)."""
+    big = synth_case("C2")            # 200 bones, IK, morphs: the larger shared-memory footprint
+    small = synth_case("tiny")
+    mb = Model(ctx, big[1])
+    ab = Motion(mb, big[2])
+    fb = Frames(mb, 1, 4)
+    ms = Model(ctx, small[1])         # created AFTER the large model, used before it
+    as_ = Motion(ms, small[2])
+    fs = Frames(ms, 1, 4)
+    fs.update(as_, [1, 2, 3, 4])
+    fb.update(ab, [5, 6, 7, 8])
+    fs.update(as_, [9, 10, 11, 12])
+    ob, os_ = _oracle(big[1], big[2]), _oracle(small[1], small[2])
+    assert_bitwise(fb.download(3, capi.STREAM_POSITION), ob.run_frame(8)["pos"], "large model after a small one was loaded")
+    assert_bitwise(fs.download(0, capi.STREAM_POSITION), os_.run_frame(9)["pos"], "small model")

@@ -9,7 +9,7 @@ from conftest import assert_bitwise, synth_case
 pytestmark = pytest.mark.gpu
 
 from simple_mmd_renderer_b200 import capi  # noqa: E402
-from simple_mmd_renderer_b200.poser import Frames, Model, Motion, MotionPlayer, Poser  # noqa: E402
+from simple_mmd_renderer_b200.poser import Frames, MmdGpuError, Model, Motion, MotionPlayer, Poser  # noqa: E402
 
 POS_RTOL, POS_ATOL, MAT_ATOL = 1e-5, 1e-6, 1e-6   # BASELINE.json north_star
 
@@ -752,3 +752,27 @@ def test_models_of_different_sizes_coexist(ctx):
     ob, os_ = _oracle(big[1], big[2]), _oracle(small[1], small[2])
     assert_bitwise(fb.download(3, capi.STREAM_POSITION), ob.run_frame(8)["pos"], "large model after a small one was loaded")
     assert_bitwise(fs.download(0, capi.STREAM_POSITION), os_.run_frame(9)["pos"], "small model")
+
+
+def test_maximum_slot_count(ctx):
+    """65535 slots per frames object (include/mmdgpu.h): one instance x 65535 frames in range mode, then 255 instances x
+    257 frames with per-slot frame ids in the interleaved layout; one more slot is refused."""
+    cfg, model, motion = synth_case("tiny_full")
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    orc = _oracle(model, motion)
+    fr = Frames(m, 1, 65535)
+    fr.update_range(a, [0], 1)
+    for k in (0, 63, 64, 4096, 32767, 32768, 65534):
+        ref = orc.run_frame(k)
+        assert_bitwise(fr.download(k, capi.STREAM_POSITION), ref["pos"], f"slot {k} positions")
+        assert_bitwise(fr.bone_matrices(k), ref["skin"], f"slot {k} matrices")
+    del fr
+    with pytest.raises(MmdGpuError):
+        Frames(m, 256, 257)
+    crowd = Frames(m, 255, 257, capi.LAYOUT_INTERLEAVED_SOKOL32)
+    ids = (np.arange(255 * 257) % 97).astype(np.uint32)
+    crowd.update([a] * 255, ids)
+    for k in (0, 256, 257, 65534):
+        orc.run_frame(int(ids[k]))
+        assert_bitwise(crowd.download(k, capi.STREAM_INTERLEAVED), orc.repack_sokol32(), f"crowd slot {k}")

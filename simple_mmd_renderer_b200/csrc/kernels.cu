@@ -700,6 +700,14 @@ __device__ __forceinline__ float4 f4_add(const float4& a, const float4& b) { ret
 // One vertex.  ids: 4 x u16 tile-local bone indices (type in bits 15:13 of id0); w: BDEF2 uses w.x, BDEF4 all four.
 // Deliberately NOT inlined: the skinning kernel calls it V x G = 16 times per slot group, and the fully inlined
 // kernel stalled a quarter of its issue slots on instruction fetch.  Results come back in registers.
+// One 32-byte sokol vertex (main.cpp:50-54) as a single 256-bit streaming store (sm_100: STG.E.256): the record is
+// exactly one DRAM sector, written by one request instead of two 16-byte halves.
+__device__ __forceinline__ void store_record32(float4* p, float a, float b, float c, float d, float e, float f, float g, float h) {
+    asm volatile("st.global.cs.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e),
+                 "f"(f), "f"(g), "f"(h)
+                 : "memory");
+}
+
 struct Skinned { float px, py, pz, nx, ny, nz; };
 template <int PS, bool PAL_SHARED>
 __device__ __noinline__ Skinned skin_vertex(const float4* __restrict__ pal, uint32_t ids_lo, uint32_t ids_hi, float4 w,
@@ -1045,8 +1053,7 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
                         } else {
                             const float mmd_to_meter = 0.1f;
                             float4* sv = F.out_inter + ((size_t)(g0 + f + h) * M.nv_pad + (size_t)tile * kTileVerts + orig[j]) * 2u;
-                            __stcs(sv, make_float4(r.px * mmd_to_meter, r.py * mmd_to_meter, r.pz * mmd_to_meter, r.nx));
-                            __stcs(sv + 1, make_float4(r.ny, r.nz, su, sv_));
+                            store_record32(sv, r.px * mmd_to_meter, r.py * mmd_to_meter, r.pz * mmd_to_meter, r.nx, r.ny, r.nz, su, sv_);
                         }
                     }
                 }
@@ -1093,8 +1100,7 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
                     // main.cpp:838-859: Vertex{pos*0.1f, normal, uv}
                     const float mmd_to_meter = 0.1f;
                     float4* sv = F.out_inter + ((size_t)(g0 + f) * M.nv_pad + (size_t)tile * kTileVerts + orig[j]) * 2u;
-                    __stcs(sv, make_float4(op[0] * mmd_to_meter, op[1] * mmd_to_meter, op[2] * mmd_to_meter, on[0]));
-                    __stcs(sv + 1, make_float4(on[1], on[2], mu, mv));
+                    store_record32(sv, op[0] * mmd_to_meter, op[1] * mmd_to_meter, op[2] * mmd_to_meter, on[0], on[1], on[2], mu, mv);
                 }
             }
             }

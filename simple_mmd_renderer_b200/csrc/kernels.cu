@@ -671,7 +671,10 @@ __global__ void __launch_bounds__(kHierCtaThreads) hierarchy_cta_kernel(DevModel
 //     no clear pass, no atomics.
 //   * Tiles are stored sorted by (skinning type, morph entry count), so a warp step runs one branch; results are
 //     written to shared-memory staging tiles at the vertex's PMX index and leave the SM as one bulk async copy
-//     (cp.async.bulk shared -> global) per output plane and slot.
+//     (cp.async.bulk shared -> global) per output plane and slot.  The interleaved layout's 32-byte records are
+//     whole DRAM sectors and go straight to global memory, one 256-bit store each.
+//   * The blend + transform is a real function (skin_vertex_n: two slots of one vertex per call); inlining every
+//     call site thrashed the instruction cache.
 // =================================================================================================
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -54,6 +54,16 @@ struct DevModel {
     // bone morphs grouped by bone
     const int32_t* bone_morph_row;
     const BoneMorphEntry* bone_morph_entries;
+    // chain-local IK images (one per IkDesc), used by the flat IK-wave kernel
+    const IkImage* ik_img;
+    const int32_t* ik_img_bones;       // global bone id of every image bone
+    const uint8_t* ik_img_written;     // 1: the solve writes this image bone (links, target)
+    const BoneStatic* ik_img_static;   // static records with parent / append parent / slots translated to image indices
+    const int32_t* ik_img_lslots;      // global link slot of every image link slot
+    const int32_t* ik_img_mslots;      // global bone-morph slot of every image morph slot
+    const IkDesc* ik_img_desc;         // IkDesc with bone / target / link_begin translated
+    const IkLink* ik_img_links;        // IkLink with bone translated
+    uint32_t ik_img_max_region;        // largest region_f4 over the model's solves (0: no images)
     // extensions: material morphs grouped by material
     uint32_t n_materials;
     const int32_t* material_morph_row;

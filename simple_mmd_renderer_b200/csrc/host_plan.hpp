@@ -40,6 +40,17 @@ struct IkLink {
     float lo[3], hi[3];                // min / max after the swap of poser_impl.inl:74-77
 };
 
+// Chain-local image of one CCD IK solve (device design, no libmmd counterpart): the few bones a solve touches -
+// its links, its target, the IK bone, their parents and append parents - renumbered 0..n_bones-1 together with
+// translated copies of their static records, so that a solve can run on a < 2 KB private copy of the state.
+struct IkImage {
+    int32_t bones_begin, n_bones;    // into ik_img_bones (global bone ids) / ik_img_static (translated records)
+    int32_t lslots_begin, n_lslots;  // into ik_img_lslots (global link slots)
+    int32_t mslots_begin, n_mslots;  // into ik_img_mslots (global bone-morph slots)
+    int32_t region_f4;               // float4 per solve: 7 n_bones + 2 n_lslots + 2 n_mslots, made odd (bank spread)
+    int32_t pad;
+};
+
 enum : uint8_t { kOpEval = 0, kOpIk = 1, kOpSkin = 2 };
 struct Op {
     uint8_t kind;

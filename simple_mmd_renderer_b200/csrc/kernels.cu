@@ -255,8 +255,9 @@ __device__ __forceinline__ Vec3 local_pos(const SlotState& S, int32_t b) {
 }
 
 // CCD IK, L/motion/poser_impl.inl:168-310 (the part of UpdateBoneTransform after the bone's own transform)
-__device__ __forceinline__ void solve_ik(const DevModel& M, const SlotState& S, const IkDesc k) {
-    const IkLink* __restrict__ links = M.links + k.link_begin;
+__device__ __forceinline__ void solve_ik(const DevModel& M, const SlotState& S, const IkDesc k,
+                                         const IkLink* __restrict__ link_table = nullptr) {
+    const IkLink* __restrict__ links = (link_table ? link_table : M.links) + k.link_begin;
     const int nl = k.link_count;
     for (int i = 0; i < nl; ++i) S.ikR[S.bones[links[i].bone].link_slot] = make_float4(0.f, 0.f, 0.f, 1.f);
     const Vec3 ik_pos = local_pos(S, k.bone);
@@ -403,11 +404,8 @@ __device__ __forceinline__ void accumulate_material_images(const DevModel& M, co
 
 constexpr uint32_t kHierWarps = 4;
 
-__global__ void __launch_bounds__(32 * kHierWarps) hierarchy_kernel(DevModel M, DevFrames F, uint32_t wave_lo,
-                                                                    uint32_t wave_hi, uint32_t prologue) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t slot = blockIdx.x * kHierWarps + (threadIdx.x >> 5);
-    if (slot >= F.n_slots) return;
+// one slot's bone state where the segment kernels leave it between launches: global memory
+__device__ __forceinline__ SlotState global_slot_state(const DevModel& M, const DevFrames& F, uint32_t slot) {
     SlotState S;
     S.bones = M.bones;
     S.poseR = F.poseR + (size_t)slot * M.nb;
@@ -417,12 +415,93 @@ __global__ void __launch_bounds__(32 * kHierWarps) hierarchy_kernel(DevModel M, 
     S.local = reinterpret_cast<float4*>(F.local) + (size_t)slot * M.nb * 3;
     S.ikR = F.ikR + (size_t)slot * M.n_link_slots;
     S.preIK = F.preIK + (size_t)slot * M.n_link_slots;
-    float4* morphR = F.morphR + (size_t)slot * M.n_morph_slots;
-    float4* morphT = F.morphT + (size_t)slot * M.n_morph_slots;
-    S.morphR = morphR;
-    S.morphT = morphT;
+    S.morphR = F.morphR + (size_t)slot * M.n_morph_slots;
+    S.morphT = F.morphT + (size_t)slot * M.n_morph_slots;
     S.palette = F.palette + (size_t)slot * M.nb * 3;
     S.pal_ext = F.pal_ext ? F.pal_ext + (size_t)slot * M.nb * 2 : nullptr;
+    return S;
+}
+
+// -------------------------------------------------------------------------------------------------
+// K2, flat form of ONE wave: a thread per (op of the wave, slot), slot-minor.  Used for the waves that hold CCD IK
+// solves when many slots are evaluated together.  In the CTA-per-slot kernel a solve keeps a CTA (34 KB of shared
+// memory on a 200-bone rig) resident for 40 x links dependent steps of one or two active lanes; here 32 slots'
+// solves of the same chain share a warp and each solve works on a CHAIN-LOCAL IMAGE of the state (IkImage: links,
+// target, their parents, < 2 KB) in shared memory, copied in from and back to the global state the segment kernels
+// exchange.  The image carries translated copies of the static records, so eval_bone / solve_ik run unchanged:
+// same arithmetic, bit-identical results.  Non-IK ops that share the wave run on the global state.
+// -------------------------------------------------------------------------------------------------
+constexpr uint32_t kFlatThreads = 64;
+
+__global__ void __launch_bounds__(kFlatThreads) hierarchy_flat_kernel(DevModel M, DevFrames F, uint32_t wave) {
+    extern __shared__ __align__(16) float4 fsm[];
+    const uint32_t o0 = M.wave_begin[wave], n = M.wave_begin[wave + 1] - o0;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * F.n_slots) return;
+    const uint32_t slot = t % F.n_slots;
+    const SlotState G = global_slot_state(M, F, slot);
+    const uint32_t word = __ldg(M.wave_ops + o0 + t / F.n_slots);
+    const uint32_t kind = word >> 28;
+    const int32_t arg = (int32_t)(word & 0x0FFFFFFFu);
+    if (kind == kOpEval) { eval_bone(M, G, arg); return; }
+    if (kind == kOpSkin) { skin_bone(M, G, arg); return; }
+    const IkImage I = M.ik_img[arg];
+    float4* reg = fsm + (size_t)threadIdx.x * M.ik_img_max_region;
+    __builtin_assume(__isShared(reg));
+    const uint32_t W = (uint32_t)I.n_bones, L = (uint32_t)I.n_lslots, Ms = (uint32_t)I.n_mslots;
+    SlotState S;
+    S.bones = M.ik_img_static + I.bones_begin;
+    float4* totR = reg;
+    float4* totT = totR + W;
+    float4* local = totT + W;            // 3 per bone
+    float4* poseR = local + 3 * W;
+    float4* poseT = poseR + W;
+    float4* ikR = poseT + W;
+    float4* preIK = ikR + L;
+    float4* morphR = preIK + L;
+    float4* morphT = morphR + Ms;
+    S.totR = totR; S.totT = totT; S.local = local; S.poseR = poseR; S.poseT = poseT; S.ikR = ikR; S.preIK = preIK;
+    S.morphR = morphR; S.morphT = morphT;
+    S.palette = nullptr; S.pal_ext = nullptr;
+    const int32_t* __restrict__ gb = M.ik_img_bones + I.bones_begin;
+    for (uint32_t i = 0; i < W; ++i) {
+        const int32_t b = __ldg(gb + i);
+        totR[i] = G.totR[b];
+        totT[i] = G.totT[b];
+        local[3 * i] = G.local[3 * (size_t)b];
+        local[3 * i + 1] = G.local[3 * (size_t)b + 1];
+        local[3 * i + 2] = G.local[3 * (size_t)b + 2];
+        poseR[i] = G.poseR[b];
+        poseT[i] = G.poseT[b];
+    }
+    const int32_t* __restrict__ gl = M.ik_img_lslots + I.lslots_begin;
+    for (uint32_t i = 0; i < L; ++i) { const int32_t x = __ldg(gl + i); ikR[i] = G.ikR[x]; preIK[i] = G.preIK[x]; }
+    const int32_t* __restrict__ gm = M.ik_img_mslots + I.mslots_begin;
+    for (uint32_t i = 0; i < Ms; ++i) { const int32_t x = __ldg(gm + i); morphR[i] = G.morphR[x]; morphT[i] = G.morphT[x]; }
+
+    solve_ik(M, S, M.ik_img_desc[arg], M.ik_img_links);
+
+    const uint8_t* __restrict__ wr = M.ik_img_written + I.bones_begin;
+    for (uint32_t i = 0; i < W; ++i) {
+        if (!__ldg(wr + i)) continue;
+        const int32_t b = __ldg(gb + i);
+        G.totR[b] = totR[i];
+        G.totT[b] = totT[i];
+        G.local[3 * (size_t)b] = local[3 * i];
+        G.local[3 * (size_t)b + 1] = local[3 * i + 1];
+        G.local[3 * (size_t)b + 2] = local[3 * i + 2];
+    }
+    for (uint32_t i = 0; i < L; ++i) { const int32_t x = __ldg(gl + i); G.ikR[x] = ikR[i]; G.preIK[x] = preIK[i]; }
+}
+
+__global__ void __launch_bounds__(32 * kHierWarps) hierarchy_kernel(DevModel M, DevFrames F, uint32_t wave_lo,
+                                                                    uint32_t wave_hi, uint32_t prologue) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t slot = blockIdx.x * kHierWarps + (threadIdx.x >> 5);
+    if (slot >= F.n_slots) return;
+    const SlotState S = global_slot_state(M, F, slot);
+    float4* morphR = F.morphR + (size_t)slot * M.n_morph_slots;
+    float4* morphT = F.morphT + (size_t)slot * M.n_morph_slots;
 
     if (prologue) {
         // ---- morph application-slot rates: Poser::UpdateMorphTransform's skip test and group recursion
@@ -1168,6 +1247,20 @@ cudaError_t launch_hierarchy(cudaStream_t st, const DevModel& M, const DevFrames
     return cudaGetLastError();
 }
 
+bool hierarchy_uses_cta_kernel(const DevModel& M) {
+    static const bool force_global = std::getenv("MMDGPU_FORCE_FALLBACKS") != nullptr;
+    return !force_global && hier_cta_smem_bytes(M.nb, M.n_link_slots, M.n_morph_slots, M.n_ops, M.n_waves) <= kHierCtaSmemLimit;
+}
+
+size_t hierarchy_flat_smem_bytes(const DevModel& M) { return (size_t)kFlatThreads * M.ik_img_max_region * sizeof(float4); }
+
+cudaError_t launch_hierarchy_wave_flat(cudaStream_t st, const DevModel& M, const DevFrames& F, uint32_t wave, uint32_t n_ops) {
+    const uint64_t threads = (uint64_t)n_ops * F.n_slots;
+    if (threads == 0) return cudaSuccess;
+    hierarchy_flat_kernel<<<(unsigned)((threads + kFlatThreads - 1) / kFlatThreads), kFlatThreads, hierarchy_flat_smem_bytes(M), st>>>(M, F, wave);
+    return cudaGetLastError();
+}
+
 size_t skin_smem_bytes(const DevModel& M, int layout) {
     const bool ext = M.extensions != 0;
     return (size_t)kSlotGroup * skin_stage_bytes(layout, ext) + 2 * (size_t)kSlotGroup * skin_pal_bytes(M.max_tile_bones, ext) +
@@ -1190,6 +1283,7 @@ cudaError_t prepare_skin_kernels(const DevModel& M) {
     if ((e = cudaDeviceGetAttribute(&limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
     const int hier = limit < (int)kHierCtaSmemLimit ? limit : (int)kHierCtaSmemLimit;
     if ((e = cudaFuncSetAttribute(hierarchy_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hier)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(hierarchy_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hier)) != cudaSuccess) return e;
     constexpr int SOA = MMDGPU_LAYOUT_SOA_POS_NRM, I32 = MMDGPU_LAYOUT_INTERLEAVED_SOKOL32;
     if ((e = skin_opt_in<SOA, true, false>(limit)) != cudaSuccess) return e;
     if ((e = skin_opt_in<I32, true, false>(limit)) != cudaSuccess) return e;

@@ -14,6 +14,10 @@ cudaError_t launch_pose_sample(cudaStream_t st, const DevModel& M, const DevAnim
 // K2: waves [wave_lo, wave_hi) of the bone program; prologue = morph rates + reset + bone morphs.
 cudaError_t launch_hierarchy(cudaStream_t st, const DevModel& M, const DevFrames& F, uint32_t wave_lo, uint32_t wave_hi,
                              bool prologue);
+// K2, one wave with a thread per (op, slot): CCD IK solves on chain-local images (kernels.cu), for large batches.
+bool hierarchy_uses_cta_kernel(const DevModel& M);
+size_t hierarchy_flat_smem_bytes(const DevModel& M);
+cudaError_t launch_hierarchy_wave_flat(cudaStream_t st, const DevModel& M, const DevFrames& F, uint32_t wave, uint32_t n_ops);
 // K3: skinning + fused vertex-morph gather.  One CTA = one 512-vertex tile x `slots_per_cta` consecutive slots, four at a time.
 size_t skin_smem_bytes(const DevModel& M, int layout);
 cudaError_t prepare_skin_kernels(const DevModel& M);

@@ -776,3 +776,38 @@ def test_maximum_slot_count(ctx):
     for k in (0, 256, 257, 65534):
         orc.run_frame(int(ids[k]))
         assert_bitwise(crowd.download(k, capi.STREAM_INTERLEAVED), orc.repack_sokol32(), f"crowd slot {k}")
+
+
+@pytest.mark.parametrize("name", ["ik_zoo", "C2", "tiny_full"])
+def test_ik_waves_on_chain_local_images(ctx, name, monkeypatch):
+    """Large batches run their CCD IK waves in the flat kernel, one thread per (solve, slot), on a chain-local image of
+    the state (links, target, their parents) with translated static records; the other waves stay in the CTA-per-slot
+    kernel and the state crosses the launches through global memory.  Forced here on a small batch, then taken
+    naturally by a 700-slot batch: both bit-identical to the oracle and to the single-launch path."""
+    cfg, model, motion = synth_case(name)
+    orc = _oracle(model, motion)
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    frames = [0, 3, 11, 26, 39]
+    monkeypatch.setenv("MMDGPU_IK_SPLIT", "0")
+    one = Frames(m, 1, len(frames))
+    one.update(a, frames)
+    base = [one.download(k, capi.STREAM_POSITION) for k in range(len(frames))]
+    monkeypatch.setenv("MMDGPU_IK_SPLIT", "1")
+    fr = Frames(m, 1, len(frames))
+    fr.update(a, frames)
+    for k, f in enumerate(frames):
+        _check_frame(fr, k, orc.run_frame(f), f"{name} split frame {f}")
+        assert_bitwise(fr.download(k, capi.STREAM_POSITION), base[k], f"{name} split vs single launch, frame {f}")
+    # the step-wise sequence crosses the pre / post physics boundary with the same mechanism
+    fr.reset_posing(); fr.seek_frame(a, frames); fr.pre_physics_posing(); fr.post_physics_posing(); fr.deform()
+    for k in range(len(frames)):
+        assert_bitwise(fr.download(k, capi.STREAM_POSITION), base[k], f"{name} split, step-wise, slot {k}")
+    monkeypatch.delenv("MMDGPU_IK_SPLIT")
+    if name != "C2":
+        big = Frames(m, 1, 700)
+        big.update_range(a, [0], 1)
+        for k in (0, 37, 699):
+            ref = orc.run_frame(k)
+            assert_bitwise(big.download(k, capi.STREAM_POSITION), ref["pos"], f"{name} 700-slot batch, slot {k}")
+            assert_bitwise(big.bone_matrices(k), ref["skin"], f"{name} 700-slot batch matrices, slot {k}")

@@ -29,10 +29,16 @@ struct mmdgpu_context {
     cudaEvent_t dl_event = nullptr;
     // fused updates run key-frame sampling and the bone hierarchy of update n+1 on this stream while the skinning
     // kernel of update n still runs on `stream`
-    cudaStream_t pre_stream = nullptr;
+    // (two of them: consecutive updates alternate, so that the latency-bound hierarchy chains of two updates overlap)
+    cudaStream_t pre_stream[2] = {nullptr, nullptr};
     // same, highest priority: for models with CCD IK, whose hierarchy kernel is a long latency-bound chain that
     // should claim SM resources as soon as CTAs of the running skinning kernel retire
-    cudaStream_t pre_stream_hi = nullptr;
+    cudaStream_t pre_stream_hi[2] = {nullptr, nullptr};
+    cudaError_t sync_pre() {
+        for (cudaStream_t st : {pre_stream[0], pre_stream[1], pre_stream_hi[0], pre_stream_hi[1]})
+            if (st) { cudaError_t e = cudaStreamSynchronize(st); if (e != cudaSuccess) return e; }
+        return cudaSuccess;
+    }
     std::string err;
     uint64_t launches = 0;
     int max_smem_optin = 0;
@@ -90,37 +96,50 @@ struct mmdgpu_animation {
     DevArena mem;
 };
 
+constexpr int kStateCopies = 3;
+
 struct mmdgpu_frames {
     mmdgpu_context_t ctx = nullptr;
     mmdgpu_model_t model = nullptr;
     mmdgpu_layout layout = MMDGPU_LAYOUT_SOA_POS_NRM;
     DevFrames dev{};
     DevArena mem;
-    DevAnim* d_anims = nullptr;                 // [n_instances]
-    std::vector<mmdgpu_animation_t> bound;      // what d_anims currently holds
+    DevAnim* d_anims = nullptr;                 // [n_instances], of the selected copy
     std::vector<DevAnim> h_anims;
     bool range_mode = false;
     uint32_t frame_stride = 1;
     uint32_t slots_per_cta = 1;
-    // What the hierarchy kernel hands to the skinning kernel (palette, extension palette, application-slot rates)
-    // exists twice: fused update n+1 writes one copy on the pre stream while update n's skinning reads the other.
-    float4* pal_buf[2] = {nullptr, nullptr};
-    float4* ext_buf[2] = {nullptr, nullptr};
-    float* rate_buf[2] = {nullptr, nullptr};
+    // Everything one fused update writes before its skinning kernel runs - sampled poses and rates, the hierarchy state
+    // that crosses launches, and what the hierarchy hands to the skinning kernel (palette, extension palette,
+    // application-slot rates) - exists kStateCopies = 3 times, used round-robin: updates n+1 and n+2 sample and run their
+    // hierarchies (on the two alternating pre streams) while update n's skinning kernel still reads its own copy.
+    struct StateSet {
+        float4 *poseR = nullptr, *poseT = nullptr, *totR = nullptr, *totT = nullptr, *ikR = nullptr, *preIK = nullptr,
+               *morphR = nullptr, *morphT = nullptr, *palette = nullptr, *pal_ext = nullptr;
+        float *rate = nullptr, *local = nullptr, *node_rate = nullptr, *material_images = nullptr;
+        uint32_t* frame_id = nullptr;
+        double* time_s = nullptr;
+        DevAnim* d_anims = nullptr;
+        std::vector<mmdgpu_animation_t> bound;  // what d_anims currently holds
+    } set[kStateCopies];
     int cur = 0;                                  // copy the step-wise entry points and the downloads use
-    cudaEvent_t ev_pre[2] = {nullptr, nullptr};   // hierarchy of the update that wrote copy i has finished
-    cudaEvent_t ev_skin[2] = {nullptr, nullptr};  // skinning that read copy i has finished
-    bool skin_recorded[2] = {false, false};
+    int update_parity = 0;                        // which of the two pre streams the last fused update used
+    cudaEvent_t ev_pre[kStateCopies] = {};    // hierarchy of the update that wrote copy i has finished
+    cudaEvent_t ev_skin[kStateCopies] = {};   // skinning that read copy i has finished
+    bool skin_recorded[kStateCopies] = {};
     cudaEvent_t ev_main = nullptr;                // main-stream work the next fused update must follow
     bool main_dirty = true;
     void select(int i) {
-        dev.palette = pal_buf[i];
-        dev.pal_ext = ext_buf[i];
-        dev.node_rate = rate_buf[i];
+        const StateSet& x = set[i];
+        dev.poseR = x.poseR; dev.poseT = x.poseT; dev.rate = x.rate; dev.totR = x.totR; dev.totT = x.totT; dev.local = x.local;
+        dev.ikR = x.ikR; dev.preIK = x.preIK; dev.morphR = x.morphR; dev.morphT = x.morphT;
+        dev.palette = x.palette; dev.pal_ext = x.pal_ext; dev.node_rate = x.node_rate; dev.material_images = x.material_images;
+        dev.frame_id = x.frame_id; dev.time_s = x.time_s;
+        d_anims = x.d_anims;
         cur = i;
     }
     ~mmdgpu_frames() {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kStateCopies; ++i) {
             if (ev_pre[i]) cudaEventDestroy(ev_pre[i]);
             if (ev_skin[i]) cudaEventDestroy(ev_skin[i]);
         }
@@ -440,12 +459,13 @@ mmdgpu_status bind_anims(mmdgpu_frames* f, const mmdgpu_animation_t* per_instanc
     mmdgpu_context_t ctx = f->ctx;
     const uint32_t ni = f->dev.n_instances;
     if (!per_instance) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "per_instance animation array is NULL");
-    bool same = f->bound.size() == ni;
+    std::vector<mmdgpu_animation_t>& bound = f->set[f->cur].bound;
+    bool same = bound.size() == ni;
     for (uint32_t i = 0; i < ni; ++i) {
         if (!per_instance[i]) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "animation handle is NULL");
         if (per_instance[i]->model != f->model)
             return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "animation was created for a different model");
-        if (same && f->bound[i] != per_instance[i]) same = false;
+        if (same && bound[i] != per_instance[i]) same = false;
     }
     if (same) return MMDGPU_OK;
     // the previous upload may still be in flight from pageable memory semantics' point of view: cudaMemcpyAsync
@@ -453,7 +473,7 @@ mmdgpu_status bind_anims(mmdgpu_frames* f, const mmdgpu_animation_t* per_instanc
     f->h_anims.resize(ni);
     for (uint32_t i = 0; i < ni; ++i) f->h_anims[i] = per_instance[i]->dev;
     CU(ctx, cudaMemcpyAsync(f->d_anims, f->h_anims.data(), sizeof(DevAnim) * ni, cudaMemcpyHostToDevice, st));
-    f->bound.assign(per_instance, per_instance + ni);
+    bound.assign(per_instance, per_instance + ni);
     return MMDGPU_OK;
 }
 
@@ -503,8 +523,9 @@ mmdgpu_status do_seek(mmdgpu_frames* f, const mmdgpu_animation_t* per_instance, 
 
 // Batches of this many slots or more run their CCD IK waves in the flat one-thread-per-(op, slot) kernel, on
 // chain-local images, between segments of the CTA-per-slot kernel (kernels.cu); below it one launch wins.
-// B200, C2 (two chains per slot): 512 slots 61.5 vs 64.1 G, 768 slots 76.4 vs 68.5 G, 2048 slots 110.9 vs 77.4 G.
-constexpr uint32_t kIkSplitMinSlots = 640;
+// B200, C2 (two chains per slot), G vertex-frames/s with / without: 256 slots 63.9 / 61.1, 512 slots 90.2 / 71.4,
+// 1024 slots 102 / 72, 2048 slots 110.9 / 77.4 (profiles/r01_experiments.md).
+constexpr uint32_t kIkSplitMinSlots = 256;
 constexpr size_t kIkSplitMaxWaves = 4;
 
 static bool split_ik_waves(const mmdgpu_frames* f) {
@@ -642,13 +663,15 @@ MMDGPU_API mmdgpu_status mmdgpu_context_create(int device, void* cuda_stream_or_
         return cuda_fail(nullptr, e, "cudaStreamCreate");
     if ((e = cudaEventCreateWithFlags(&c->dl_event, cudaEventDisableTiming)) != cudaSuccess)
         return cuda_fail(nullptr, e, "cudaEventCreate");
-    if ((e = cudaStreamCreateWithFlags(&c->pre_stream, cudaStreamNonBlocking)) != cudaSuccess)
-        return cuda_fail(nullptr, e, "cudaStreamCreate");
     {
         int least = 0, greatest = 0;
         cudaDeviceGetStreamPriorityRange(&least, &greatest);
-        if ((e = cudaStreamCreateWithPriority(&c->pre_stream_hi, cudaStreamNonBlocking, greatest)) != cudaSuccess)
-            return cuda_fail(nullptr, e, "cudaStreamCreate");
+        for (int i = 0; i < 2; ++i) {
+            if ((e = cudaStreamCreateWithFlags(&c->pre_stream[i], cudaStreamNonBlocking)) != cudaSuccess)
+                return cuda_fail(nullptr, e, "cudaStreamCreate");
+            if ((e = cudaStreamCreateWithPriority(&c->pre_stream_hi[i], cudaStreamNonBlocking, greatest)) != cudaSuccess)
+                return cuda_fail(nullptr, e, "cudaStreamCreate");
+        }
     }
     *out = c.release();
     return MMDGPU_OK;
@@ -657,12 +680,13 @@ MMDGPU_API mmdgpu_status mmdgpu_context_create(int device, void* cuda_stream_or_
 MMDGPU_API void mmdgpu_context_destroy(mmdgpu_context_t ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->pre_stream) cudaStreamSynchronize(ctx->pre_stream);
-    if (ctx->pre_stream_hi) cudaStreamSynchronize(ctx->pre_stream_hi);
+    ctx->sync_pre();
     cudaStreamSynchronize(ctx->stream);
     if (ctx->dl_stream) { cudaStreamSynchronize(ctx->dl_stream); cudaStreamDestroy(ctx->dl_stream); }
-    if (ctx->pre_stream) { cudaStreamSynchronize(ctx->pre_stream); cudaStreamDestroy(ctx->pre_stream); }
-    if (ctx->pre_stream_hi) { cudaStreamSynchronize(ctx->pre_stream_hi); cudaStreamDestroy(ctx->pre_stream_hi); }
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->pre_stream[i]) cudaStreamDestroy(ctx->pre_stream[i]);
+        if (ctx->pre_stream_hi[i]) cudaStreamDestroy(ctx->pre_stream_hi[i]);
+    }
     if (ctx->dl_event) cudaEventDestroy(ctx->dl_event);
     for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
@@ -674,8 +698,7 @@ MMDGPU_API const char* mmdgpu_last_error(mmdgpu_context_t ctx) { return ctx ? ct
 
 MMDGPU_API mmdgpu_status mmdgpu_context_synchronize(mmdgpu_context_t ctx) {
     if (mmdgpu_status s = enter(ctx)) return s;
-    CU(ctx, cudaStreamSynchronize(ctx->pre_stream));
-    CU(ctx, cudaStreamSynchronize(ctx->pre_stream_hi));
+    CU(ctx, ctx->sync_pre());
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->dl_stream));
     return MMDGPU_OK;
@@ -691,8 +714,7 @@ MMDGPU_API mmdgpu_status mmdgpu_context_profile_read(mmdgpu_context_t ctx, doubl
                                                      uint64_t launches[MMDGPU_KERNEL_COUNT]) {
     if (mmdgpu_status s = enter(ctx)) return s;
     if (!ms_total || !launches) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "NULL argument");
-    CU(ctx, cudaStreamSynchronize(ctx->pre_stream));
-    CU(ctx, cudaStreamSynchronize(ctx->pre_stream_hi));
+    CU(ctx, ctx->sync_pre());
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < MMDGPU_KERNEL_COUNT; ++i) { ms_total[i] = 0.0; launches[i] = 0; }
     for (const auto& sp : ctx->spans) {
@@ -949,8 +971,7 @@ MMDGPU_API mmdgpu_status mmdgpu_model_create_from_pmx(mmdgpu_context_t ctx, cons
 MMDGPU_API void mmdgpu_model_destroy(mmdgpu_model_t model) {
     if (!model) return;
     cudaSetDevice(model->ctx->device);
-    cudaStreamSynchronize(model->ctx->pre_stream);
-    cudaStreamSynchronize(model->ctx->pre_stream_hi);
+    model->ctx->sync_pre();
     cudaStreamSynchronize(model->ctx->stream);
     delete model;
 }
@@ -1019,8 +1040,7 @@ MMDGPU_API mmdgpu_status mmdgpu_animation_create_from_vmd(mmdgpu_context_t ctx, 
 MMDGPU_API void mmdgpu_animation_destroy(mmdgpu_animation_t a) {
     if (!a) return;
     cudaSetDevice(a->ctx->device);
-    cudaStreamSynchronize(a->ctx->pre_stream);
-    cudaStreamSynchronize(a->ctx->pre_stream_hi);
+    a->ctx->sync_pre();
     cudaStreamSynchronize(a->ctx->stream);
     delete a;
 }
@@ -1048,22 +1068,27 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_create(mmdgpu_context_t ctx, mmdgpu_model
     const size_t ns = size_t(n_instances) * n_frames;
     F.n_slots = uint32_t(ns); F.n_instances = n_instances; F.n_frames = n_frames;
     cudaStream_t st = ctx->stream;
-    CU(ctx, dalloc(f->mem, &F.poseR, ns * M.nb, false, st));
-    CU(ctx, dalloc(f->mem, &F.poseT, ns * M.nb, false, st));
-    CU(ctx, dalloc(f->mem, &F.rate, ns * M.nm, true, st));
-    // application-slot rates, [slot / 4][node][slot % 4] (kernels.cu)
-    for (int i = 0; i < 2; ++i)
-        CU(ctx, dalloc(f->mem, &f->rate_buf[i], (ns + kSlotGroup - 1) / kSlotGroup * kSlotGroup * M.n_nodes_pad, true, st));
-    CU(ctx, dalloc(f->mem, &F.totR, ns * M.nb, true, st));
-    CU(ctx, dalloc(f->mem, &F.totT, ns * M.nb, true, st));
-    CU(ctx, dalloc(f->mem, &F.local, ns * M.nb * 12, true, st));
-    CU(ctx, dalloc(f->mem, &F.ikR, ns * M.n_link_slots, true, st));
-    CU(ctx, dalloc(f->mem, &F.preIK, ns * M.n_link_slots, true, st));
-    CU(ctx, dalloc(f->mem, &F.morphR, ns * M.n_morph_slots, true, st));
-    CU(ctx, dalloc(f->mem, &F.morphT, ns * M.n_morph_slots, true, st));
-    for (int i = 0; i < 2; ++i) {
-        CU(ctx, dalloc(f->mem, &f->pal_buf[i], ns * M.nb * 3, true, st));
-        if (M.extensions) CU(ctx, dalloc(f->mem, &f->ext_buf[i], ns * M.nb * 2, true, st));
+    for (int i = 0; i < kStateCopies; ++i) {
+        mmdgpu_frames::StateSet& x = f->set[i];
+        CU(ctx, dalloc(f->mem, &x.poseR, ns * M.nb, false, st));
+        CU(ctx, dalloc(f->mem, &x.poseT, ns * M.nb, false, st));
+        CU(ctx, dalloc(f->mem, &x.rate, ns * M.nm, true, st));
+        // application-slot rates, [slot / 4][node][slot % 4] (kernels.cu)
+        CU(ctx, dalloc(f->mem, &x.node_rate, (ns + kSlotGroup - 1) / kSlotGroup * kSlotGroup * M.n_nodes_pad, true, st));
+        CU(ctx, dalloc(f->mem, &x.totR, ns * M.nb, true, st));
+        CU(ctx, dalloc(f->mem, &x.totT, ns * M.nb, true, st));
+        CU(ctx, dalloc(f->mem, &x.local, ns * M.nb * 12, true, st));
+        CU(ctx, dalloc(f->mem, &x.ikR, ns * M.n_link_slots, true, st));
+        CU(ctx, dalloc(f->mem, &x.preIK, ns * M.n_link_slots, true, st));
+        CU(ctx, dalloc(f->mem, &x.morphR, ns * M.n_morph_slots, true, st));
+        CU(ctx, dalloc(f->mem, &x.morphT, ns * M.n_morph_slots, true, st));
+        CU(ctx, dalloc(f->mem, &x.palette, ns * M.nb * 3, true, st));
+        if (M.extensions) CU(ctx, dalloc(f->mem, &x.pal_ext, ns * M.nb * 2, true, st));
+        if (M.material_morph_entries)
+            CU(ctx, dalloc(f->mem, &x.material_images, ns * M.n_materials * 2 * MMDGPU_MATERIAL_FIELDS, true, st));
+        CU(ctx, dalloc(f->mem, &x.frame_id, ns, true, st));
+        CU(ctx, dalloc(f->mem, &x.time_s, ns, true, st));
+        CU(ctx, dalloc(f->mem, &x.d_anims, size_t(n_instances), true, st));
         CU(ctx, cudaEventCreateWithFlags(&f->ev_pre[i], cudaEventDisableTiming));
         CU(ctx, cudaEventCreateWithFlags(&f->ev_skin[i], cudaEventDisableTiming));
     }
@@ -1076,13 +1101,10 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_create(mmdgpu_context_t ctx, mmdgpu_model
     } else {
         CU(ctx, dalloc(f->mem, &F.out_inter, ns * M.nv_pad * 2, false, st));
     }
-    if (M.material_morph_entries) CU(ctx, dalloc(f->mem, &F.material_images, ns * M.n_materials * 2 * MMDGPU_MATERIAL_FIELDS, true, st));
-    CU(ctx, dalloc(f->mem, &F.frame_id, ns, true, st));
-    CU(ctx, dalloc(f->mem, &F.time_s, ns, true, st));
-    CU(ctx, dalloc(f->mem, &f->d_anims, size_t(n_instances), true, st));
     f->slots_per_cta = choose_slots_per_cta(M.n_tiles, F.n_slots, ctx->sm_count);
-    // Poser::Poser ends with ResetPosing() (poser_impl.inl:125-127): a fresh object holds identity poses.
-    {
+    // Poser::Poser ends with ResetPosing() (poser_impl.inl:125-127): a fresh object holds identity poses (both copies).
+    for (int i = kStateCopies - 1; i >= 0; --i) {
+        f->select(i);
         Timed t(ctx, MMDGPU_KERNEL_POSE_SAMPLE);
         CU(ctx, launch_pose_sample(st, M, nullptr, F, true, false, 1));
     }
@@ -1093,8 +1115,7 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_create(mmdgpu_context_t ctx, mmdgpu_model
 MMDGPU_API void mmdgpu_frames_destroy(mmdgpu_frames_t f) {
     if (!f) return;
     cudaSetDevice(f->ctx->device);
-    cudaStreamSynchronize(f->ctx->pre_stream);
-    cudaStreamSynchronize(f->ctx->pre_stream_hi);
+    f->ctx->sync_pre();
     cudaStreamSynchronize(f->ctx->stream);
     cudaStreamSynchronize(f->ctx->dl_stream);
     delete f;
@@ -1216,12 +1237,15 @@ static mmdgpu_status update_common(mmdgpu_frames_t f, const mmdgpu_animation_t* 
     // clip does not animate (main.cpp:1788-1796).  Sampling and the hierarchy run on the pre stream into the copy
     // of (palette, rates) the previous update is NOT using, so they overlap that update's skinning kernel.
     mmdgpu_context_t ctx = f->ctx;
-    const int next = f->cur ^ 1;
-    cudaStream_t pre = f->model->plan.plan.iks.empty() ? ctx->pre_stream : ctx->pre_stream_hi;
+    const int next = (f->cur + 1) % kStateCopies;
+    const bool has_ik = !f->model->plan.plan.iks.empty();
+    f->update_parity ^= 1;
+    cudaStream_t pre = has_ik ? ctx->pre_stream_hi[f->update_parity] : ctx->pre_stream[f->update_parity];
     if (f->skin_recorded[next]) CU(ctx, cudaStreamWaitEvent(pre, f->ev_skin[next], 0));
     if (f->main_dirty) {  // step-wise calls / uploads issued on the main stream since the last fused update
         CU(ctx, cudaEventRecord(f->ev_main, ctx->stream));
-        CU(ctx, cudaStreamWaitEvent(pre, f->ev_main, 0));
+        // both copies may have been touched from the main stream: the update after this one waits as well
+        for (int i = 0; i < 2; ++i) CU(ctx, cudaStreamWaitEvent(has_ik ? ctx->pre_stream_hi[i] : ctx->pre_stream[i], f->ev_main, 0));
         f->main_dirty = false;
     }
     f->select(next);

@@ -424,7 +424,17 @@ typedef enum mmdgpu_plan_array {
     /* extensions only (empty otherwise): material morphs grouped by material, application order inside a material;
      * an entry for "every material" is repeated under each */
     MMDGPU_PLAN_MATERIAL_MORPH_ROW = 36, /* i32 [n_materials + 1]                                              */
-    MMDGPU_PLAN_MATERIAL_MORPH = 37      /* u8  [120 n] {i32 application slot; u32 method; f32 value[28]}      */
+    MMDGPU_PLAN_MATERIAL_MORPH = 37,     /* u8  [120 n] {i32 application slot; u32 method; f32 value[28]}      */
+    /* chain-local images of the CCD IK solves (device design, one image per IK bone in PLAN_IK_DESC order): the bones a
+     * solve touches renumbered 0..n-1, with translated copies of their static records, IK descriptor and links */
+    MMDGPU_PLAN_IK_IMAGE = 38,             /* u8  [32 n] {i32 bones_begin, n_bones, lslots_begin, n_lslots, mslots_begin, n_mslots, region_f4, pad} */
+    MMDGPU_PLAN_IK_IMAGE_BONES = 39,       /* i32 global bone id of every image bone                           */
+    MMDGPU_PLAN_IK_IMAGE_WRITTEN = 40,     /* u8  1: the solve evaluates this image bone (links, target)        */
+    MMDGPU_PLAN_IK_IMAGE_STATIC = 41,      /* u8  [48 n] PLAN_BONE_STATIC records with image-local references   */
+    MMDGPU_PLAN_IK_IMAGE_LINK_SLOTS = 42,  /* i32 global link slot of every image link slot                    */
+    MMDGPU_PLAN_IK_IMAGE_MORPH_SLOTS = 43, /* i32 global bone-morph slot of every image morph slot             */
+    MMDGPU_PLAN_IK_IMAGE_DESC = 44,        /* u8  [32 n] PLAN_IK_DESC records with image-local bone / target    */
+    MMDGPU_PLAN_IK_IMAGE_LINKS = 45        /* u8  [32 n] PLAN_IK_LINK records with image-local bone             */
 } mmdgpu_plan_array;
 
 /* Host-only: parse a PMX 2.0 / 2.1 byte stream (layout of L/reader/pmx_reader_impl.inl:16-449) and build the

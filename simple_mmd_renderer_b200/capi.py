@@ -26,7 +26,8 @@ STREAM_POSITION, STREAM_NORMAL, STREAM_INTERLEAVED, STREAM_SKIN_MATRIX, STREAM_U
  PLAN_WAVE_PHASE_SPLIT, PLAN_TILE_ORIG, PLAN_TILE_TYPE, PLAN_TILE_LOCAL_ID, PLAN_TILE_BONE_BEGIN, PLAN_TILE_BONES,
  PLAN_ELL_BASE, PLAN_ELL_ROUNDS, PLAN_ELL_SLOT, PLAN_ELL_OFFSET, PLAN_POSITION, PLAN_NORMAL, PLAN_UV,
  PLAN_BONE_STATIC, PLAN_IK_DESC, PLAN_IK_LINK, PLAN_BONE_MORPH, PLAN_MATERIAL_MORPH_ROW,
- PLAN_MATERIAL_MORPH) = range(38)
+ PLAN_MATERIAL_MORPH, PLAN_IK_IMAGE, PLAN_IK_IMAGE_BONES, PLAN_IK_IMAGE_WRITTEN, PLAN_IK_IMAGE_STATIC,
+ PLAN_IK_IMAGE_LINK_SLOTS, PLAN_IK_IMAGE_MORPH_SLOTS, PLAN_IK_IMAGE_DESC, PLAN_IK_IMAGE_LINKS) = range(46)
 
 PLAN_DTYPES = {
     PLAN_SKIN_TYPE: np.uint8, PLAN_BONE_ID: np.uint16, PLAN_WEIGHT: np.float32, PLAN_ORDER_PRE: np.int32,
@@ -41,6 +42,9 @@ PLAN_DTYPES = {
     PLAN_POSITION: np.float32, PLAN_NORMAL: np.float32, PLAN_UV: np.float32, PLAN_BONE_STATIC: np.uint8,
     PLAN_IK_DESC: np.uint8, PLAN_IK_LINK: np.uint8, PLAN_BONE_MORPH: np.uint8,
     PLAN_MATERIAL_MORPH_ROW: np.int32, PLAN_MATERIAL_MORPH: np.uint8,
+    PLAN_IK_IMAGE: np.uint8, PLAN_IK_IMAGE_BONES: np.int32, PLAN_IK_IMAGE_WRITTEN: np.uint8, PLAN_IK_IMAGE_STATIC: np.uint8,
+    PLAN_IK_IMAGE_LINK_SLOTS: np.int32, PLAN_IK_IMAGE_MORPH_SLOTS: np.int32, PLAN_IK_IMAGE_DESC: np.uint8,
+    PLAN_IK_IMAGE_LINKS: np.uint8,
 }
 
 (ANIM_BONE_KEY_BEGIN, ANIM_BONE_KEY_COUNT, ANIM_BONE_TRACKED, ANIM_KEY_FRAME, ANIM_KEY_T, ANIM_KEY_R, ANIM_KEY_CURVE,

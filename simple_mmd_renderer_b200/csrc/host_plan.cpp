@@ -392,6 +392,75 @@ mmdgpu_status build_plan(const mmdgpu_model_desc& d, const mmdgpu_options* opt, 
         }
     }
 
+    // ---------------------------------------------------------------- chain-local images of the IK solves
+    // (device design: hierarchy_flat_kernel runs a solve on a private copy of just the bones it touches)
+    {
+        p.ik_img_ok = !p.iks.empty();
+        for (const IkDesc& k : p.iks) {
+            std::vector<int32_t> bones;                 // image index -> global bone id
+            std::vector<uint8_t> written;
+            auto add = [&](int32_t b, bool wr) -> int32_t {
+                for (size_t i = 0; i < bones.size(); ++i)
+                    if (bones[i] == b) { written[i] |= uint8_t(wr); return int32_t(i); }
+                bones.push_back(b); written.push_back(uint8_t(wr));
+                return int32_t(bones.size() - 1);
+            };
+            std::vector<int32_t> evaluated;             // links and the target: eval_bone / set_local run on them
+            for (int32_t j = 0; j < k.link_count; ++j) evaluated.push_back(p.links[size_t(k.link_begin + j)].bone);
+            evaluated.push_back(k.target);
+            for (int32_t b : evaluated) add(b, true);
+            add(k.bone, false);
+            for (int32_t b : evaluated) {               // what evaluating them reads
+                const BoneStatic& s0 = p.bones[size_t(b)];
+                if (s0.flags & kHasParent) add(s0.parent, false);
+                if (s0.flags & (kAppendRot | kAppendTrans)) add(s0.append_parent, false);
+            }
+            std::vector<int32_t> lslots, mslots;
+            auto slot_of = [](std::vector<int32_t>& v, int32_t x) -> int32_t {
+                for (size_t i = 0; i < v.size(); ++i) if (v[i] == x) return int32_t(i);
+                v.push_back(x);
+                return int32_t(v.size() - 1);
+            };
+            IkImage I{};
+            I.bones_begin = int32_t(p.ik_img_bones.size());
+            I.n_bones = int32_t(bones.size());
+            for (size_t i = 0; i < size_t(I.n_bones); ++i) {
+                BoneStatic s1 = p.bones[size_t(bones[i])];
+                const bool ev = written[i] != 0;
+                // records of bones that are only read keep no references: they are never evaluated
+                if (ev && (s1.flags & kHasParent)) s1.parent = add(s1.parent, false);
+                else { s1.parent = -1; if (!ev) s1.flags &= ~kHasParent; }
+                if (ev && (s1.flags & (kAppendRot | kAppendTrans))) s1.append_parent = add(s1.append_parent, false);
+                else { s1.append_parent = -1; if (!ev) s1.flags &= ~(kAppendRot | kAppendTrans); }
+                s1.link_slot = (ev && s1.link_slot >= 0) ? slot_of(lslots, s1.link_slot) : -1;
+                if (!ev) s1.flags &= ~kIsLink;
+                s1.morph_slot = (ev && s1.morph_slot >= 0) ? slot_of(mslots, s1.morph_slot) : -1;
+                p.ik_img_static.push_back(s1);
+            }
+            if (int32_t(bones.size()) != I.n_bones) p.ik_img_ok = false;   // the translation must not grow the set
+            p.ik_img_bones.insert(p.ik_img_bones.end(), bones.begin(), bones.begin() + I.n_bones);
+            p.ik_img_written.insert(p.ik_img_written.end(), written.begin(), written.begin() + I.n_bones);
+            I.lslots_begin = int32_t(p.ik_img_lslots.size()); I.n_lslots = int32_t(lslots.size());
+            I.mslots_begin = int32_t(p.ik_img_mslots.size()); I.n_mslots = int32_t(mslots.size());
+            p.ik_img_lslots.insert(p.ik_img_lslots.end(), lslots.begin(), lslots.end());
+            p.ik_img_mslots.insert(p.ik_img_mslots.end(), mslots.begin(), mslots.end());
+            I.region_f4 = 7 * I.n_bones + 2 * I.n_lslots + 2 * I.n_mslots;
+            I.region_f4 |= 1;                           // odd: consecutive threads' regions start in different banks
+            p.ik_img_max_region = std::max<uint32_t>(p.ik_img_max_region, uint32_t(I.region_f4));
+            IkDesc kd = k;
+            kd.bone = add(k.bone, false);
+            kd.target = add(k.target, false);
+            kd.link_begin = int32_t(p.ik_img_links.size());
+            for (int32_t j = 0; j < k.link_count; ++j) {
+                IkLink l = p.links[size_t(k.link_begin + j)];
+                l.bone = add(l.bone, false);
+                p.ik_img_links.push_back(l);
+            }
+            p.ik_img_desc.push_back(kd);
+            p.ik_img.push_back(I);
+        }
+    }
+
     // material morphs grouped by affected material (extensions; libmmd leaves its material images untouched,
     // poser_impl.inl:355-358)
     p.n_materials = d.n_materials;

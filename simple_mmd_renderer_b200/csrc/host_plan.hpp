@@ -141,6 +141,17 @@ struct Plan {
     std::vector<int32_t> bone_morph_row;     // morph_bones.size() + 1
     std::vector<BoneMorphEntry> bone_morph_entries;
 
+    // chain-local images of the CCD IK solves, one per entry of `iks` (see IkImage)
+    std::vector<IkImage> ik_img;
+    std::vector<int32_t> ik_img_bones;       // global bone id of every image bone
+    std::vector<uint8_t> ik_img_written;     // 1: the solve evaluates (writes) this image bone: links, target
+    std::vector<BoneStatic> ik_img_static;   // static records, references translated to image indices
+    std::vector<int32_t> ik_img_lslots, ik_img_mslots;  // global link / bone-morph slot of every image slot
+    std::vector<IkDesc> ik_img_desc;         // bone / target / link_begin translated
+    std::vector<IkLink> ik_img_links;        // bone translated
+    uint32_t ik_img_max_region = 0;
+    bool ik_img_ok = false;
+
     // extensions only: material morphs grouped by affected material, application order inside a material
     uint32_t n_materials = 0;
     std::vector<int32_t> material_morph_row;  // n_materials + 1

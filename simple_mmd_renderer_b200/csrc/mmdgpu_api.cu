@@ -329,13 +329,7 @@ mmdgpu_status upload_model(mmdgpu_model* m) {
         CU(ctx, upload(ctx, m->mem, p.material_morph_row, &D.material_morph_row));
         CU(ctx, upload(ctx, m->mem, p.material_morph_entries, &D.material_morph_entries));
     }
-    // ---- chain-local images of the CCD IK solves (kernels.cu, hierarchy_flat_kernel)
-    std::vector<IkImage> img;
-    std::vector<int32_t> img_bones, img_lslots, img_mslots;
-    std::vector<uint8_t> img_written;
-    std::vector<BoneStatic> img_static;
-    std::vector<IkDesc> img_desc;
-    std::vector<IkLink> img_links;
+    // ---- chain-local images of the CCD IK solves (built by build_plan; kernels.cu, hierarchy_flat_kernel)
     {
         m->ik_waves.clear();
         for (uint32_t w = 0; w + 1 < p.wave_begin.size(); ++w) {
@@ -343,84 +337,18 @@ mmdgpu_status upload_model(mmdgpu_model* m) {
             for (int32_t i = p.wave_begin[w]; i < p.wave_begin[w + 1]; ++i) has_ik |= p.ops[size_t(p.wave_ops[size_t(i)])].kind == kOpIk;
             if (has_ik) m->ik_waves.push_back({w, uint32_t(p.wave_begin[w + 1] - p.wave_begin[w])});
         }
-        uint32_t max_region = 0;
-        bool ok = !p.iks.empty();
-        for (const IkDesc& k : p.iks) {
-            std::vector<int32_t> bones;                 // image index -> global bone id
-            std::vector<uint8_t> written;
-            auto add = [&](int32_t b, bool wr) -> int32_t {
-                for (size_t i = 0; i < bones.size(); ++i)
-                    if (bones[i] == b) { written[i] |= uint8_t(wr); return int32_t(i); }
-                bones.push_back(b); written.push_back(uint8_t(wr));
-                return int32_t(bones.size() - 1);
-            };
-            std::vector<int32_t> evaluated;             // links and the target: eval_bone / set_local run on them
-            for (int32_t j = 0; j < k.link_count; ++j) evaluated.push_back(p.links[size_t(k.link_begin + j)].bone);
-            evaluated.push_back(k.target);
-            for (int32_t b : evaluated) add(b, true);
-            add(k.bone, false);
-            for (int32_t b : evaluated) {               // what evaluating them reads
-                const BoneStatic& s0 = p.bones[size_t(b)];
-                if (s0.flags & kHasParent) add(s0.parent, false);
-                if (s0.flags & (kAppendRot | kAppendTrans)) add(s0.append_parent, false);
-            }
-            std::vector<int32_t> lslots, mslots;
-            auto slot_of = [](std::vector<int32_t>& v, int32_t x) -> int32_t {
-                for (size_t i = 0; i < v.size(); ++i) if (v[i] == x) return int32_t(i);
-                v.push_back(x);
-                return int32_t(v.size() - 1);
-            };
-            IkImage I{};
-            I.bones_begin = int32_t(img_bones.size());
-            I.n_bones = int32_t(bones.size());
-            for (size_t i = 0; i < bones.size(); ++i) {
-                BoneStatic s1 = p.bones[size_t(bones[i])];
-                const bool ev = written[i] != 0;
-                // records of bones that are only read keep no references: they are never evaluated
-                if (ev && (s1.flags & kHasParent)) s1.parent = add(s1.parent, false); else { s1.parent = -1; if (!ev) s1.flags &= ~kHasParent; }
-                if (ev && (s1.flags & (kAppendRot | kAppendTrans))) s1.append_parent = add(s1.append_parent, false);
-                else { s1.append_parent = -1; if (!ev) s1.flags &= ~(kAppendRot | kAppendTrans); }
-                s1.link_slot = (ev && s1.link_slot >= 0) ? slot_of(lslots, s1.link_slot) : -1;
-                if (!ev) s1.flags &= ~kIsLink;
-                s1.morph_slot = (ev && s1.morph_slot >= 0) ? slot_of(mslots, s1.morph_slot) : -1;
-                img_static.push_back(s1);
-            }
-            img_bones.insert(img_bones.end(), bones.begin(), bones.end());
-            img_written.insert(img_written.end(), written.begin(), written.end());
-            I.lslots_begin = int32_t(img_lslots.size()); I.n_lslots = int32_t(lslots.size());
-            I.mslots_begin = int32_t(img_mslots.size()); I.n_mslots = int32_t(mslots.size());
-            img_lslots.insert(img_lslots.end(), lslots.begin(), lslots.end());
-            img_mslots.insert(img_mslots.end(), mslots.begin(), mslots.end());
-            I.region_f4 = 7 * I.n_bones + 2 * I.n_lslots + 2 * I.n_mslots;
-            I.region_f4 |= 1;                           // odd: consecutive threads' regions start in different banks
-            max_region = std::max<uint32_t>(max_region, uint32_t(I.region_f4));
-            IkDesc kd = k;
-            auto local_of = [&](int32_t b) { return add(b, false); };
-            kd.bone = local_of(k.bone);
-            kd.target = local_of(k.target);
-            kd.link_begin = int32_t(img_links.size());
-            for (int32_t j = 0; j < k.link_count; ++j) {
-                IkLink l = p.links[size_t(k.link_begin + j)];
-                l.bone = local_of(l.bone);
-                img_links.push_back(l);
-            }
-            img_desc.push_back(kd);
-            img.push_back(I);
-            if (int32_t(bones.size()) != I.n_bones) ok = false;   // the translation above must not have grown the set
-        }
         // 64 solves per CTA must fit the shared memory a CTA may have next to the skinning kernel's
-        ok = ok && size_t(max_region) * 64 * sizeof(float4) <= 96 * 1024;
-        m->ik_images_ok = ok;
-        if (ok) {
-            CU(ctx, upload(ctx, m->mem, img, &D.ik_img));
-            CU(ctx, upload(ctx, m->mem, img_bones, &D.ik_img_bones));
-            CU(ctx, upload(ctx, m->mem, img_written, &D.ik_img_written));
-            CU(ctx, upload(ctx, m->mem, img_static, &D.ik_img_static));
-            CU(ctx, upload(ctx, m->mem, img_lslots, &D.ik_img_lslots));
-            CU(ctx, upload(ctx, m->mem, img_mslots, &D.ik_img_mslots));
-            CU(ctx, upload(ctx, m->mem, img_desc, &D.ik_img_desc));
-            CU(ctx, upload(ctx, m->mem, img_links, &D.ik_img_links));
-            D.ik_img_max_region = max_region;
+        m->ik_images_ok = p.ik_img_ok && size_t(p.ik_img_max_region) * 64 * sizeof(float4) <= 96 * 1024;
+        if (m->ik_images_ok) {
+            CU(ctx, upload(ctx, m->mem, p.ik_img, &D.ik_img));
+            CU(ctx, upload(ctx, m->mem, p.ik_img_bones, &D.ik_img_bones));
+            CU(ctx, upload(ctx, m->mem, p.ik_img_written, &D.ik_img_written));
+            CU(ctx, upload(ctx, m->mem, p.ik_img_static, &D.ik_img_static));
+            CU(ctx, upload(ctx, m->mem, p.ik_img_lslots, &D.ik_img_lslots));
+            CU(ctx, upload(ctx, m->mem, p.ik_img_mslots, &D.ik_img_mslots));
+            CU(ctx, upload(ctx, m->mem, p.ik_img_desc, &D.ik_img_desc));
+            CU(ctx, upload(ctx, m->mem, p.ik_img_links, &D.ik_img_links));
+            D.ik_img_max_region = p.ik_img_max_region;
         }
     }
     CU(ctx, cudaStreamSynchronize(ctx->stream));  // the staging vectors above die with this frame
@@ -910,6 +838,18 @@ MMDGPU_API mmdgpu_status mmdgpu_plan_get(mmdgpu_plan_t plan, mmdgpu_plan_array w
         *data = p.iks.data(); *count = p.iks.size() * sizeof(IkDesc); return MMDGPU_OK;
     case MMDGPU_PLAN_IK_LINK:
         *data = p.links.data(); *count = p.links.size() * sizeof(IkLink); return MMDGPU_OK;
+    case MMDGPU_PLAN_IK_IMAGE:
+        *data = p.ik_img.data(); *count = p.ik_img.size() * sizeof(IkImage); return MMDGPU_OK;
+    case MMDGPU_PLAN_IK_IMAGE_BONES: RET(p.ik_img_bones);
+    case MMDGPU_PLAN_IK_IMAGE_WRITTEN: RET(p.ik_img_written);
+    case MMDGPU_PLAN_IK_IMAGE_STATIC:
+        *data = p.ik_img_static.data(); *count = p.ik_img_static.size() * sizeof(BoneStatic); return MMDGPU_OK;
+    case MMDGPU_PLAN_IK_IMAGE_LINK_SLOTS: RET(p.ik_img_lslots);
+    case MMDGPU_PLAN_IK_IMAGE_MORPH_SLOTS: RET(p.ik_img_mslots);
+    case MMDGPU_PLAN_IK_IMAGE_DESC:
+        *data = p.ik_img_desc.data(); *count = p.ik_img_desc.size() * sizeof(IkDesc); return MMDGPU_OK;
+    case MMDGPU_PLAN_IK_IMAGE_LINKS:
+        *data = p.ik_img_links.data(); *count = p.ik_img_links.size() * sizeof(IkLink); return MMDGPU_OK;
     case MMDGPU_PLAN_MATERIAL_MORPH_ROW: RET(p.material_morph_row);
     case MMDGPU_PLAN_MATERIAL_MORPH:
         *data = p.material_morph_entries.data(); *count = p.material_morph_entries.size() * sizeof(MaterialMorphEntry); return MMDGPU_OK;

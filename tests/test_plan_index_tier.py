@@ -328,3 +328,70 @@ def test_material_morph_plan_is_grouped_by_material_in_application_order():
     # a material morph inside a group shows up once per visit (direct + through the group)
     n_material_morphs = int((model["morph_type"] == capi.MORPH_MATERIAL).sum())
     assert sum(1 for m in node_morph if model["morph_type"][m] == capi.MORPH_MATERIAL) == n_material_morphs + 2
+
+
+BONE_STATIC = np.dtype([("local_offset", "<f4", (3,)), ("parent", "<i4"), ("position", "<f4", (3,)), ("append_parent", "<i4"),
+                        ("append_ratio", "<f4"), ("flags", "<u4"), ("link_slot", "<i4"), ("morph_slot", "<i4")])
+IK_DESC = np.dtype([("bone", "<i4"), ("target", "<i4"), ("iterations", "<i4"), ("angle_limit", "<f4"), ("link_begin", "<i4"),
+                    ("link_count", "<i4"), ("pad", "<i4", (2,))])
+IK_LINK = np.dtype([("bone", "<i4"), ("limited", "u1"), ("fix", "u1"), ("order", "u1"), ("pad", "u1"), ("lo", "<f4", (3,)),
+                    ("hi", "<f4", (3,))])
+IK_IMAGE = np.dtype([("bones_begin", "<i4"), ("n_bones", "<i4"), ("lslots_begin", "<i4"), ("n_lslots", "<i4"),
+                     ("mslots_begin", "<i4"), ("n_mslots", "<i4"), ("region_f4", "<i4"), ("pad", "<i4")])
+HAS_PARENT, APPEND_ROT, APPEND_TRANS, IS_LINK = 1, 2, 4, 8
+
+
+@pytest.mark.parametrize("name", ["tiny_full", "small", "C2", "ik_zoo"])
+def test_ik_images_are_faithful_renumberings(name):
+    """Chain-local images of the CCD IK solves (device design): every image holds the solve's links, target and IK bone
+    plus the parents / append parents evaluating them reads; the translated static records, IK descriptor and links
+    name the same bones as the originals once mapped back through the image's bone list; read-only bones carry no
+    references; the evaluated set is exactly links + target."""
+    cfg, model, _ = synth_case(name)
+    plan = plan_arrays(model)
+    static = plan[capi.PLAN_BONE_STATIC].view(BONE_STATIC)
+    desc = plan[capi.PLAN_IK_DESC].view(IK_DESC)
+    links = plan[capi.PLAN_IK_LINK].view(IK_LINK)
+    img = plan[capi.PLAN_IK_IMAGE].view(IK_IMAGE)
+    ibones, iwritten = plan[capi.PLAN_IK_IMAGE_BONES], plan[capi.PLAN_IK_IMAGE_WRITTEN]
+    istatic = plan[capi.PLAN_IK_IMAGE_STATIC].view(BONE_STATIC)
+    ils, ims = plan[capi.PLAN_IK_IMAGE_LINK_SLOTS], plan[capi.PLAN_IK_IMAGE_MORPH_SLOTS]
+    idesc = plan[capi.PLAN_IK_IMAGE_DESC].view(IK_DESC)
+    ilinks = plan[capi.PLAN_IK_IMAGE_LINKS].view(IK_LINK)
+    assert img.size == desc.size == idesc.size > 0
+    for k in range(desc.size):
+        I, d, di = img[k], desc[k], idesc[k]
+        gb = ibones[I["bones_begin"]:I["bones_begin"] + I["n_bones"]]
+        wr = iwritten[I["bones_begin"]:I["bones_begin"] + I["n_bones"]]
+        st = istatic[I["bones_begin"]:I["bones_begin"] + I["n_bones"]]
+        ls = ils[I["lslots_begin"]:I["lslots_begin"] + I["n_lslots"]]
+        ms = ims[I["mslots_begin"]:I["mslots_begin"] + I["n_mslots"]]
+        assert len(set(gb.tolist())) == gb.size, "image bones are distinct"
+        assert I["region_f4"] % 2 == 1 and I["region_f4"] >= 7 * I["n_bones"] + 2 * I["n_lslots"] + 2 * I["n_mslots"]
+        chain = [int(links[d["link_begin"] + j]["bone"]) for j in range(d["link_count"])]
+        assert gb[di["bone"]] == d["bone"] and gb[di["target"]] == d["target"]
+        assert di["iterations"] == d["iterations"] and di["angle_limit"] == d["angle_limit"] and di["link_count"] == d["link_count"]
+        for j in range(d["link_count"]):
+            a, b = links[d["link_begin"] + j], ilinks[di["link_begin"] + j]
+            assert gb[b["bone"]] == a["bone"]
+            for f in ("limited", "fix", "order"):
+                assert a[f] == b[f]
+            np.testing.assert_array_equal(a["lo"], b["lo"]); np.testing.assert_array_equal(a["hi"], b["hi"])
+        assert sorted(gb[wr != 0].tolist()) == sorted(set(chain + [int(d["target"])])), "evaluated = links + target"
+        for i in range(gb.size):
+            o, t = static[gb[i]], st[i]
+            np.testing.assert_array_equal(o["local_offset"], t["local_offset"]); np.testing.assert_array_equal(o["position"], t["position"])
+            if wr[i]:
+                assert t["flags"] == o["flags"] and t["append_ratio"] == o["append_ratio"]
+                if o["flags"] & HAS_PARENT:
+                    assert gb[t["parent"]] == o["parent"]
+                if o["flags"] & (APPEND_ROT | APPEND_TRANS):
+                    assert gb[t["append_parent"]] == o["append_parent"]
+                assert (t["link_slot"] < 0) == (o["link_slot"] < 0) and (t["morph_slot"] < 0) == (o["morph_slot"] < 0)
+                if o["link_slot"] >= 0:
+                    assert ls[t["link_slot"]] == o["link_slot"]
+                if o["morph_slot"] >= 0:
+                    assert ms[t["morph_slot"]] == o["morph_slot"]
+            else:
+                assert t["parent"] == -1 and t["append_parent"] == -1 and t["link_slot"] == -1 and t["morph_slot"] == -1
+                assert not (t["flags"] & (HAS_PARENT | APPEND_ROT | APPEND_TRANS | IS_LINK))

@@ -1174,8 +1174,12 @@ MMDGPU_API mmdgpu_status mmdgpu_set_skinning_matrix_override(mmdgpu_frames_t f, 
 static mmdgpu_status update_common(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance, const uint32_t* frames,
                                    bool range, uint32_t stride) {
     // ResetPosing + SeekFrame collapse into one sampling launch that writes identity / zero for items the
-    // clip does not animate (main.cpp:1788-1796).  Sampling and the hierarchy run on the pre stream into the copy
-    // of (palette, rates) the previous update is NOT using, so they overlap that update's skinning kernel.
+    // clip does not animate (main.cpp:1788-1796).  Sampling and the hierarchy run on one of two alternating pre streams
+    // into the next of the kStateCopies copies of the per-update state (mmdgpu_frames::StateSet), so they overlap the
+    // previous update's hierarchy (other pre stream, other copy) and the skinning kernels still reading older copies.
+    // Ordering: a copy is rewritten only after the skinning kernel that read it has finished (ev_skin), which in turn
+    // ran after the hierarchy that wrote it (ev_pre); work issued on the main stream in between (step-wise calls,
+    // pose uploads) is followed through ev_main by BOTH pre streams.
     mmdgpu_context_t ctx = f->ctx;
     const int next = (f->cur + 1) % kStateCopies;
     const bool has_ik = !f->model->plan.plan.iks.empty();
@@ -1184,7 +1188,7 @@ static mmdgpu_status update_common(mmdgpu_frames_t f, const mmdgpu_animation_t* 
     if (f->skin_recorded[next]) CU(ctx, cudaStreamWaitEvent(pre, f->ev_skin[next], 0));
     if (f->main_dirty) {  // step-wise calls / uploads issued on the main stream since the last fused update
         CU(ctx, cudaEventRecord(f->ev_main, ctx->stream));
-        // both copies may have been touched from the main stream: the update after this one waits as well
+        // any copy may have been touched from the main stream: the update after this one waits as well
         for (int i = 0; i < 2; ++i) CU(ctx, cudaStreamWaitEvent(has_ik ? ctx->pre_stream_hi[i] : ctx->pre_stream[i], f->ev_main, 0));
         f->main_dirty = false;
     }

@@ -341,7 +341,9 @@ MMDGPU_API mmdgpu_status mmdgpu_update(mmdgpu_frames_t frames, const mmdgpu_anim
 MMDGPU_API mmdgpu_status mmdgpu_update_range(mmdgpu_frames_t frames, const mmdgpu_animation_t* per_instance,
                                              const uint32_t* first_frame_per_instance, uint32_t frame_stride);
 
-/* Device pointer of slot 0 of one output stream and the byte stride between slots. */
+/* Device pointer of slot 0 of one output stream and the byte stride between slots.  The vertex streams
+ * (POSITION / NORMAL / INTERLEAVED / UV) keep their address for the life of the frames object; SKIN_MATRIX belongs
+ * to the per-update state, of which fused updates rotate several copies: ask again after every mmdgpu_update. */
 MMDGPU_API mmdgpu_status mmdgpu_frames_device_ptr(mmdgpu_frames_t frames, mmdgpu_stream_id id, void** dptr,
                                                   size_t* slot_stride_bytes);
 /* Copy one slot's output stream to host memory (synchronous); feeds sg_update_buffer (main.cpp:862)

@@ -342,7 +342,8 @@ MMDGPU_API mmdgpu_status mmdgpu_update_range(mmdgpu_frames_t frames, const mmdgp
                                              const uint32_t* first_frame_per_instance, uint32_t frame_stride);
 
 /* Device pointer of slot 0 of one output stream and the byte stride between slots.  The vertex streams
- * (POSITION / NORMAL / INTERLEAVED / UV) keep their address for the life of the frames object; SKIN_MATRIX belongs
+ * (POSITION / NORMAL / INTERLEAVED / UV) keep their address for the life of the frames object (unless rebound with
+ * mmdgpu_frames_bind_output); SKIN_MATRIX belongs
  * to the per-update state, of which fused updates rotate several copies: ask again after every mmdgpu_update. */
 MMDGPU_API mmdgpu_status mmdgpu_frames_device_ptr(mmdgpu_frames_t frames, mmdgpu_stream_id id, void** dptr,
                                                   size_t* slot_stride_bytes);
@@ -350,10 +351,28 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_device_ptr(mmdgpu_frames_t frames, mmdgpu
  * or Poser::pose_image unchanged.  bytes must equal the stream's size for one slot. */
 MMDGPU_API mmdgpu_status mmdgpu_frames_download(mmdgpu_frames_t frames, uint32_t slot, mmdgpu_stream_id id,
                                                 void* host_dst, size_t bytes);
-/* Asynchronous variant on the context's download stream for a slot range into pinned host memory;
- * pair with mmdgpu_context_synchronize.  Overlaps with the next update on the compute stream. */
+/* Asynchronous variant on the context's download stream for a slot range into pinned host memory.  The copy
+ * starts when the work queued on the compute stream so far has finished and overlaps whatever is queued afterwards;
+ * the next skinning launch on THIS frames object waits (on the device) until the copy has read the vertex buffers,
+ * so updating the same object right away is safe - sampling and hierarchy of that update still overlap the copy.
+ * Completion on the host: mmdgpu_frames_wait_downloads (this object's copies only) or mmdgpu_context_synchronize. */
 MMDGPU_API mmdgpu_status mmdgpu_frames_download_async(mmdgpu_frames_t frames, uint32_t first_slot, uint32_t n_slots,
                                                       mmdgpu_stream_id id, void* pinned_host_dst, size_t bytes);
+/* Block the calling thread until every mmdgpu_frames_download_async issued for this frames object has landed in host
+ * memory.  Does not wait for compute or for copies of other frames objects: a bake alternating two frames objects
+ * hands window k to its sink while window k+1 is being evaluated (simple_mmd_renderer_b200/shard.py BakeDriver). */
+MMDGPU_API mmdgpu_status mmdgpu_frames_wait_downloads(mmdgpu_frames_t frames);
+/* Zero-copy hand-off (replaces the CPU repack + sg_update_buffer of main.cpp:820-863): let the skinning kernel write
+ * one vertex output stream straight into caller-owned DEVICE memory - e.g. the pointer cudaGraphicsResourceGetMappedPointer
+ * returns for sokol's GL vertex buffer (sg_gl_query_buffer_info, 3rd_party/sokol/sokol_gfx.h:5213).
+ * id: POSITION / NORMAL (SoA frames), INTERLEAVED (sokol32 frames: main.cpp:50-54 records, positions x0.1, static UV),
+ * UV (extensions).  Slot s is written at device_ptr + s * slot_stride_bytes; exactly n_vertices records per slot are
+ * stored (no padding).  device_ptr and slot_stride_bytes must be 16-byte aligned (32 for INTERLEAVED).
+ * device_ptr = NULL restores the library-owned buffer.  The binding applies to launches issued after the call; the
+ * caller orders its own use of the buffer against the context's stream (mmdgpu_context_stream / _synchronize).
+ * mmdgpu_frames_device_ptr / _download[_async] follow the binding. */
+MMDGPU_API mmdgpu_status mmdgpu_frames_bind_output(mmdgpu_frames_t frames, mmdgpu_stream_id id, void* device_ptr,
+                                                   size_t slot_stride_bytes);
 /* BoneImage::skinning_matrix_ / local_matrix_ of one slot as nb x 16 floats (parity on bone globals). */
 MMDGPU_API mmdgpu_status mmdgpu_bone_matrices_download(mmdgpu_frames_t frames, uint32_t slot, float* host_dst);
 MMDGPU_API mmdgpu_status mmdgpu_bone_local_matrices_download(mmdgpu_frames_t frames, uint32_t slot, float* host_dst);

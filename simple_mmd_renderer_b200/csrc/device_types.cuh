@@ -103,11 +103,14 @@ struct DevFrames {
     float4* morphT;     // [slot][n_morph_slots]
     float4* palette;    // [slot][nb][3]   column c of skinning_matrix_: (M0c, M1c, M2c, M3c)
     float4* pal_ext;    // [slot][nb][2]   extensions: rotation quaternion and dual part of the skinning transform
-    float2* out_uv;     // extensions, SOA layout: [slot][nv_pad] morphed UV
+    float2* out_uv;     // extensions, SOA layout: [slot][uv_stride] morphed UV
     float* material_images;  // extensions: [slot][n_materials][2][28] multiplicative then additive image
-    float* out_pos;     // SOA: [slot][nv_pad][3]
-    float* out_nrm;     // SOA: [slot][nv_pad][3]
-    float4* out_inter;  // INTERLEAVED: [slot][nv_pad][2]
+    // Vertex outputs: the library's own buffers ([slot][nv_pad] records) or caller-owned device memory bound with
+    // mmdgpu_frames_bind_output (e.g. a mapped GL vertex buffer, [slot][>= nv] records).  Only vertices < nv are stored.
+    float* out_pos;     // SOA: [slot][pos_stride floats], 3 per vertex
+    float* out_nrm;     // SOA: [slot][nrm_stride floats]
+    float4* out_inter;  // INTERLEAVED: [slot][inter_stride float4], 2 per vertex
+    size_t pos_stride, nrm_stride, inter_stride, uv_stride;  // slot strides in elements of the respective pointer
     uint32_t* frame_id; // [slot]
     double* time_s;     // [slot] seconds, for MotionPlayer::SeekTime
 };

@@ -281,31 +281,42 @@ mmdgpu_status build_plan(const mmdgpu_model_desc& d, const mmdgpu_options* opt, 
             return fail(err, MMDGPU_ERR_BAD_INDEX, "morph entry range out of range at morph " + std::to_string(m));
     }
     {
+        // Depth-first with an explicit stack (a crafted chain of hundreds of thousands of nested groups must not
+        // overflow the host stack) and a nesting cap far above any real model: libmmd itself recurses once per level.
+        constexpr int32_t kMaxGroupDepth = 64;
         std::vector<uint8_t> on_stack(nm, 0);
-        mmdgpu_status st = MMDGPU_OK;
-        std::function<void(uint32_t, int32_t, float, int32_t)> visit = [&](uint32_t m, int32_t parent, float mult,
-                                                                          int32_t depth) {
-            if (st != MMDGPU_OK) return;
-            if (p.node_morph.size() >= kMaxNodes) { st = fail(err, MMDGPU_ERR_UNSUPPORTED, "group morph expansion too large"); return; }
+        struct Visit { uint32_t morph; int32_t node; uint32_t next_child; };
+        std::vector<Visit> stack;
+        auto enter_node = [&](uint32_t m, int32_t parent, float mult, int32_t depth) -> mmdgpu_status {
+            if (p.node_morph.size() >= kMaxNodes) return fail(err, MMDGPU_ERR_UNSUPPORTED, "group morph expansion too large");
+            if (depth > kMaxGroupDepth)
+                return fail(err, MMDGPU_ERR_UNSUPPORTED, "group morphs nested deeper than " + std::to_string(kMaxGroupDepth));
             const int32_t me = int32_t(p.node_morph.size());
             p.node_morph.push_back(int32_t(m));
             p.node_parent.push_back(parent);
             p.node_mult.push_back(mult);
             p.node_depth.push_back(depth);
-            if (d.morph_type[m] != MMDGPU_MORPH_GROUP) return;
-            on_stack[m] = 1;
-            for (uint32_t j = 0; j < d.morph_entry_count[m]; ++j) {
-                const mmdgpu_group_morph_entry& g = d.group_morph_entries[d.morph_entry_begin[m] + j];
-                if (g.morph >= nm) { st = fail(err, MMDGPU_ERR_BAD_INDEX, "group morph child out of range"); return; }
-                if (on_stack[g.morph]) { st = fail(err, MMDGPU_ERR_BAD_INDEX, "group morph cycle (libmmd would recurse forever)"); return; }
-                visit(g.morph, me, g.rate, depth + 1);
-                if (st != MMDGPU_OK) return;
+            if (d.morph_type[m] == MMDGPU_MORPH_GROUP) {
+                on_stack[m] = 1;
+                stack.push_back({m, me, 0u});
             }
-            on_stack[m] = 0;
+            return MMDGPU_OK;
         };
         for (uint32_t m = 0; m < nm; ++m) {
-            visit(m, -1, 1.0f, 0);
-            if (st != MMDGPU_OK) return st;
+            if (mmdgpu_status st = enter_node(m, -1, 1.0f, 0)) return st;
+            while (!stack.empty()) {
+                Visit& v = stack.back();
+                if (v.next_child >= d.morph_entry_count[v.morph]) {
+                    on_stack[v.morph] = 0;
+                    stack.pop_back();
+                    continue;
+                }
+                const mmdgpu_group_morph_entry& g = d.group_morph_entries[d.morph_entry_begin[v.morph] + v.next_child++];
+                if (g.morph >= nm) return fail(err, MMDGPU_ERR_BAD_INDEX, "group morph child out of range");
+                if (on_stack[g.morph]) return fail(err, MMDGPU_ERR_BAD_INDEX, "group morph cycle (libmmd would recurse forever)");
+                const int32_t parent = v.node, depth = p.node_depth[size_t(v.node)] + 1;
+                if (mmdgpu_status st = enter_node(g.morph, parent, g.rate, depth)) return st;  // may grow `stack`: v is dead
+            }
         }
     }
     const size_t n_nodes = p.node_morph.size();

@@ -972,6 +972,9 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
     const uint32_t s1 = min(F.n_slots, s0 + chunk);
     if (s0 >= s1) return;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    // vertices of this tile that exist (the last tile is padded): only those are stored, so a caller-owned output buffer
+    // (mmdgpu_frames_bind_output) needs nv records per slot, not nv_pad
+    const uint32_t tile_nv = min(kTileVerts, M.nv - tile * kTileVerts);
 
     // ---- the tile's static streams: read once, kept in registers for every slot of this work item
     const uint32_t v0 = tile * kTileVerts + tid * kVertsPerThread;
@@ -1132,9 +1135,9 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
                             float* sn = reinterpret_cast<float*>(stage + kTileVerts * 12u) + orig[j] * 3u;
                             sp[0] = r.px; sp[1] = r.py; sp[2] = r.pz;
                             sn[0] = r.nx; sn[1] = r.ny; sn[2] = r.nz;
-                        } else {
+                        } else if (orig[j] < tile_nv) {
                             const float mmd_to_meter = 0.1f;
-                            float4* sv = F.out_inter + ((size_t)(g0 + f + h) * M.nv_pad + (size_t)tile * kTileVerts + orig[j]) * 2u;
+                            float4* sv = F.out_inter + (size_t)(g0 + f + h) * F.inter_stride + ((size_t)tile * kTileVerts + orig[j]) * 2u;
                             store_record32(sv, r.px * mmd_to_meter, r.py * mmd_to_meter, r.pz * mmd_to_meter, r.nx, r.ny, r.nz, su, sv_);
                         }
                     }
@@ -1178,10 +1181,10 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
                     sp[0] = op[0]; sp[1] = op[1]; sp[2] = op[2];
                     sn[0] = on[0]; sn[1] = on[1]; sn[2] = on[2];
                     if (EXT) reinterpret_cast<float2*>(stage + kTileVerts * 24u)[orig[j]] = make_float2(mu, mv);
-                } else {
+                } else if (orig[j] < tile_nv) {
                     // main.cpp:838-859: Vertex{pos*0.1f, normal, uv}
                     const float mmd_to_meter = 0.1f;
-                    float4* sv = F.out_inter + ((size_t)(g0 + f) * M.nv_pad + (size_t)tile * kTileVerts + orig[j]) * 2u;
+                    float4* sv = F.out_inter + (size_t)(g0 + f) * F.inter_stride + ((size_t)tile * kTileVerts + orig[j]) * 2u;
                     store_record32(sv, op[0] * mmd_to_meter, op[1] * mmd_to_meter, op[2] * mmd_to_meter, on[0], on[1], on[2], mu, mv);
                 }
             }
@@ -1203,13 +1206,26 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
         if (LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) fence_proxy_async_smem();  // staging writes -> visible to the async proxy
         __syncthreads();
         if (tid == 0 && LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) {
+            // bulk copies move whole 16-byte units; a last tile whose vertex count is not a multiple of 4 leaves up to
+            // three floats per plane, stored by this thread
+            const uint32_t b3 = (tile_nv * 12u) & ~15u, b2 = (tile_nv * 8u) & ~15u;
             for (uint32_t f = 0; f < n_live; ++f) {
                 unsigned char* stage = stage_base + (size_t)f * stage_bytes;
-                const size_t vbase = (size_t)(g0 + f) * M.nv_pad + (size_t)tile * kTileVerts;
-                if (LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) {
-                    bulk_s2g(F.out_pos + vbase * 3, stage, kTileVerts * 12u);
-                    bulk_s2g(F.out_nrm + vbase * 3, stage + kTileVerts * 12u, kTileVerts * 12u);
-                    if (EXT) bulk_s2g(F.out_uv + vbase, stage + kTileVerts * 24u, kTileVerts * 8u);
+                const size_t vt = (size_t)tile * kTileVerts;
+                float* dp = F.out_pos + (size_t)(g0 + f) * F.pos_stride + vt * 3;
+                float* dn = F.out_nrm + (size_t)(g0 + f) * F.nrm_stride + vt * 3;
+                if (b3) {
+                    bulk_s2g(dp, stage, b3);
+                    bulk_s2g(dn, stage + kTileVerts * 12u, b3);
+                }
+                for (uint32_t w = b3 / 4u; w < tile_nv * 3u; ++w) {
+                    dp[w] = reinterpret_cast<const float*>(stage)[w];
+                    dn[w] = reinterpret_cast<const float*>(stage + kTileVerts * 12u)[w];
+                }
+                if (EXT) {
+                    float2* du = F.out_uv + (size_t)(g0 + f) * F.uv_stride + vt;
+                    if (b2) bulk_s2g(du, stage + kTileVerts * 24u, b2);
+                    for (uint32_t w = b2 / 8u; w < tile_nv; ++w) du[w] = reinterpret_cast<const float2*>(stage + kTileVerts * 24u)[w];
                 }
             }
             bulk_commit();

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -91,6 +92,9 @@ struct mmdgpu_model {
 struct mmdgpu_animation {
     mmdgpu_context_t ctx = nullptr;
     mmdgpu_model_t model = nullptr;
+    // Identity of this clip for the frames objects' "what is uploaded" caches.  Never the handle address: a clip created
+    // after another was destroyed usually gets the same heap block back, and its DevAnim points at different arrays.
+    uint64_t uid = 0;
     HostAnim host;
     DevAnim dev{};
     DevArena mem;
@@ -120,7 +124,7 @@ struct mmdgpu_frames {
         uint32_t* frame_id = nullptr;
         double* time_s = nullptr;
         DevAnim* d_anims = nullptr;
-        std::vector<mmdgpu_animation_t> bound;  // what d_anims currently holds
+        std::vector<uint64_t> bound;            // uid of the clip whose DevAnim each entry of d_anims currently holds
     } set[kStateCopies];
     int cur = 0;                                  // copy the step-wise entry points and the downloads use
     int update_parity = 0;                        // which of the two pre streams the last fused update used
@@ -129,6 +133,15 @@ struct mmdgpu_frames {
     bool skin_recorded[kStateCopies] = {};
     cudaEvent_t ev_main = nullptr;                // main-stream work the next fused update must follow
     bool main_dirty = true;
+    // The vertex output streams are single-buffered: a skinning kernel must not overwrite them while an asynchronous
+    // download of the previous update is still reading.  ev_dl follows the last copy issued on the download stream.
+    cudaEvent_t ev_dl = nullptr;
+    bool dl_pending = false;                      // a skinning launch has yet to wait for ev_dl
+    bool dl_recorded = false;                     // ev_dl has been recorded at least once
+    // library-owned output buffers (what mmdgpu_frames_bind_output(.., NULL, ..) restores)
+    float *own_pos = nullptr, *own_nrm = nullptr;
+    float4* own_inter = nullptr;
+    float2* own_uv = nullptr;
     void select(int i) {
         const StateSet& x = set[i];
         dev.poseR = x.poseR; dev.poseT = x.poseT; dev.rate = x.rate; dev.totR = x.totR; dev.totT = x.totT; dev.local = x.local;
@@ -139,11 +152,14 @@ struct mmdgpu_frames {
         cur = i;
     }
     ~mmdgpu_frames() {
+        // also the error path of mmdgpu_frames_create: queued launches may still reference the arena freed after this body
+        if (ctx && ctx->stream) cudaStreamSynchronize(ctx->stream);
         for (int i = 0; i < kStateCopies; ++i) {
             if (ev_pre[i]) cudaEventDestroy(ev_pre[i]);
             if (ev_skin[i]) cudaEventDestroy(ev_skin[i]);
         }
         if (ev_main) cudaEventDestroy(ev_main);
+        if (ev_dl) cudaEventDestroy(ev_dl);
     }
 };
 
@@ -383,25 +399,35 @@ mmdgpu_status upload_anim(mmdgpu_animation* a) {
     return MMDGPU_OK;
 }
 
-mmdgpu_status bind_anims(mmdgpu_frames* f, const mmdgpu_animation_t* per_instance, cudaStream_t st) {
+std::atomic<uint64_t> g_next_anim_uid{1};
+
+// Argument check shared by every entry point that takes clips; nothing is modified on failure.
+mmdgpu_status check_anims(const mmdgpu_frames* f, const mmdgpu_animation_t* per_instance) {
     mmdgpu_context_t ctx = f->ctx;
-    const uint32_t ni = f->dev.n_instances;
     if (!per_instance) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "per_instance animation array is NULL");
-    std::vector<mmdgpu_animation_t>& bound = f->set[f->cur].bound;
-    bool same = bound.size() == ni;
-    for (uint32_t i = 0; i < ni; ++i) {
+    for (uint32_t i = 0; i < f->dev.n_instances; ++i) {
         if (!per_instance[i]) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "animation handle is NULL");
         if (per_instance[i]->model != f->model)
             return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "animation was created for a different model");
-        if (same && bound[i] != per_instance[i]) same = false;
     }
+    return MMDGPU_OK;
+}
+
+mmdgpu_status bind_anims(mmdgpu_frames* f, const mmdgpu_animation_t* per_instance, cudaStream_t st) {
+    mmdgpu_context_t ctx = f->ctx;
+    const uint32_t ni = f->dev.n_instances;
+    if (mmdgpu_status s = check_anims(f, per_instance)) return s;
+    std::vector<uint64_t>& bound = f->set[f->cur].bound;
+    bool same = bound.size() == ni;
+    for (uint32_t i = 0; same && i < ni; ++i) same = bound[i] == per_instance[i]->uid;
     if (same) return MMDGPU_OK;
     // the previous upload may still be in flight from pageable memory semantics' point of view: cudaMemcpyAsync
     // from pageable memory returns after staging, so h_anims may be rewritten immediately.
     f->h_anims.resize(ni);
     for (uint32_t i = 0; i < ni; ++i) f->h_anims[i] = per_instance[i]->dev;
     CU(ctx, cudaMemcpyAsync(f->d_anims, f->h_anims.data(), sizeof(DevAnim) * ni, cudaMemcpyHostToDevice, st));
-    bound.assign(per_instance, per_instance + ni);
+    bound.resize(ni);
+    for (uint32_t i = 0; i < ni; ++i) bound[i] = per_instance[i]->uid;
     return MMDGPU_OK;
 }
 
@@ -498,6 +524,10 @@ mmdgpu_status do_hierarchy(mmdgpu_frames* f, uint32_t lo, uint32_t hi, bool prol
 mmdgpu_status do_skin(mmdgpu_frames* f) {
     mmdgpu_context_t ctx = f->ctx;
     if (f->model->dev.nv_pad == 0) return MMDGPU_OK;
+    if (f->dl_pending) {  // the copy of the previous update's vertices must have read the buffers this launch overwrites
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, f->ev_dl, 0));
+        f->dl_pending = false;
+    }
     {
         Timed t(ctx, MMDGPU_KERNEL_SKIN);
         CU(ctx, launch_skin(ctx->stream, f->model->dev, f->dev, int(f->layout), f->slots_per_cta));
@@ -517,14 +547,14 @@ mmdgpu_status stream_view(mmdgpu_frames* f, mmdgpu_stream_id id, StreamView& v) 
         if (f->layout != MMDGPU_LAYOUT_SOA_POS_NRM)
             return set_err(f->ctx, MMDGPU_ERR_INVALID_ARG, "frames were created with the interleaved layout");
         v.base = reinterpret_cast<const char*>(id == MMDGPU_STREAM_POSITION ? f->dev.out_pos : f->dev.out_nrm);
-        v.slot_stride = size_t(M.nv_pad) * 12;
+        v.slot_stride = (id == MMDGPU_STREAM_POSITION ? f->dev.pos_stride : f->dev.nrm_stride) * 4;
         v.slot_bytes = size_t(M.nv) * 12;
         return MMDGPU_OK;
     case MMDGPU_STREAM_INTERLEAVED:
         if (f->layout != MMDGPU_LAYOUT_INTERLEAVED_SOKOL32)
             return set_err(f->ctx, MMDGPU_ERR_INVALID_ARG, "frames were created with the SoA layout");
         v.base = reinterpret_cast<const char*>(f->dev.out_inter);
-        v.slot_stride = size_t(M.nv_pad) * 32;
+        v.slot_stride = f->dev.inter_stride * 16;
         v.slot_bytes = size_t(M.nv) * 32;
         return MMDGPU_OK;
     case MMDGPU_STREAM_SKIN_MATRIX:
@@ -535,7 +565,7 @@ mmdgpu_status stream_view(mmdgpu_frames* f, mmdgpu_stream_id id, StreamView& v) 
         if (!f->dev.out_uv)
             return set_err(f->ctx, MMDGPU_ERR_INVALID_ARG, "the UV stream exists only for SoA frames of a model created with extensions");
         v.base = reinterpret_cast<const char*>(f->dev.out_uv);
-        v.slot_stride = size_t(M.nv_pad) * 8;
+        v.slot_stride = f->dev.uv_stride * 8;
         v.slot_bytes = size_t(M.nv) * 8;
         return MMDGPU_OK;
     }
@@ -570,7 +600,9 @@ MMDGPU_API mmdgpu_status mmdgpu_context_create(int device, void* cuda_stream_or_
     if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceCount");
     if (count == 0) return set_err(nullptr, MMDGPU_ERR_CUDA, "no CUDA device");
     if (device < 0 || device >= count) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "device ordinal out of range");
-    std::unique_ptr<mmdgpu_context> c(new (std::nothrow) mmdgpu_context());
+    // every failure below leaves through mmdgpu_context_destroy, which releases whatever had been created by then
+    std::unique_ptr<mmdgpu_context, void (*)(mmdgpu_context*)> c(new (std::nothrow) mmdgpu_context(),
+                                                                 [](mmdgpu_context* p) { mmdgpu_context_destroy(p); });
     if (!c) return set_err(nullptr, MMDGPU_ERR_OOM, "host allocation failed");
     c->device = device;
     if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
@@ -946,6 +978,7 @@ MMDGPU_API mmdgpu_status mmdgpu_animation_create_from_arrays(mmdgpu_context_t ct
     if (!a) return set_err(ctx, MMDGPU_ERR_OOM, "host allocation failed");
     a->ctx = ctx;
     a->model = model;
+    a->uid = g_next_anim_uid.fetch_add(1, std::memory_order_relaxed);
     std::string err;
     mmdgpu_status s;
     try {
@@ -1034,6 +1067,7 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_create(mmdgpu_context_t ctx, mmdgpu_model
     }
     CU(ctx, cudaEventCreateWithFlags(&f->ev_main, cudaEventDisableTiming));
     f->select(0);
+    CU(ctx, cudaEventCreateWithFlags(&f->ev_dl, cudaEventDisableTiming));
     if (layout == MMDGPU_LAYOUT_SOA_POS_NRM) {
         CU(ctx, dalloc(f->mem, &F.out_pos, ns * M.nv_pad * 3, false, st));
         CU(ctx, dalloc(f->mem, &F.out_nrm, ns * M.nv_pad * 3, false, st));
@@ -1041,6 +1075,10 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_create(mmdgpu_context_t ctx, mmdgpu_model
     } else {
         CU(ctx, dalloc(f->mem, &F.out_inter, ns * M.nv_pad * 2, false, st));
     }
+    F.pos_stride = F.nrm_stride = size_t(M.nv_pad) * 3;  // floats
+    F.inter_stride = size_t(M.nv_pad) * 2;               // float4
+    F.uv_stride = size_t(M.nv_pad);                      // float2
+    f->own_pos = F.out_pos; f->own_nrm = F.out_nrm; f->own_inter = F.out_inter; f->own_uv = F.out_uv;
     f->slots_per_cta = choose_slots_per_cta(M.n_tiles, F.n_slots, ctx->sm_count);
     // Poser::Poser ends with ResetPosing() (poser_impl.inl:125-127): a fresh object holds identity poses (both copies).
     for (int i = kStateCopies - 1; i >= 0; --i) {
@@ -1147,6 +1185,9 @@ MMDGPU_API mmdgpu_status mmdgpu_post_physics_posing(mmdgpu_frames_t f) {
 MMDGPU_API mmdgpu_status mmdgpu_deform(mmdgpu_frames_t f) {
     if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
     if (mmdgpu_status s = enter(f->ctx)) return s;
+    // this launch reads state copy `cur` from the main stream: the fused updates' pre streams, which rewrite the copies
+    // round-robin, must follow it (ev_main)
+    f->main_dirty = true;
     return do_skin(f);
 }
 
@@ -1181,6 +1222,9 @@ static mmdgpu_status update_common(mmdgpu_frames_t f, const mmdgpu_animation_t* 
     // ran after the hierarchy that wrote it (ev_pre); work issued on the main stream in between (step-wise calls,
     // pose uploads) is followed through ev_main by BOTH pre streams.
     mmdgpu_context_t ctx = f->ctx;
+    // arguments are checked before anything rotates: a rejected call leaves `cur` on the copy of the last good update
+    if (!frames) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "frame id array is NULL");
+    if (mmdgpu_status s = check_anims(f, per_instance)) return s;
     const int next = (f->cur + 1) % kStateCopies;
     const bool has_ik = !f->model->plan.plan.iks.empty();
     f->update_parity ^= 1;
@@ -1253,8 +1297,66 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_download_async(mmdgpu_frames_t f, uint32_
     if (bytes == 0) return MMDGPU_OK;
     CU(ctx, cudaEventRecord(ctx->dl_event, ctx->stream));
     CU(ctx, cudaStreamWaitEvent(ctx->dl_stream, ctx->dl_event, 0));
-    CU(ctx, cudaMemcpy2DAsync(pinned_host_dst, v.slot_bytes, v.base + size_t(first_slot) * v.slot_stride, v.slot_stride,
-                              v.slot_bytes, n_slots, cudaMemcpyDeviceToHost, ctx->dl_stream));
+    const char* src = v.base + size_t(first_slot) * v.slot_stride;
+    if (v.slot_bytes == v.slot_stride || n_slots == 1)   // contiguous: one plain copy
+        CU(ctx, cudaMemcpyAsync(pinned_host_dst, src, bytes, cudaMemcpyDeviceToHost, ctx->dl_stream));
+    else
+        CU(ctx, cudaMemcpy2DAsync(pinned_host_dst, v.slot_bytes, src, v.slot_stride, v.slot_bytes, n_slots,
+                                  cudaMemcpyDeviceToHost, ctx->dl_stream));
+    CU(ctx, cudaEventRecord(f->ev_dl, ctx->dl_stream));
+    f->dl_pending = f->dl_recorded = true;
+    return MMDGPU_OK;
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_frames_wait_downloads(mmdgpu_frames_t f) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    if (mmdgpu_status s = enter(f->ctx)) return s;
+    if (f->dl_recorded) CU(f->ctx, cudaEventSynchronize(f->ev_dl));
+    return MMDGPU_OK;
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_frames_bind_output(mmdgpu_frames_t f, mmdgpu_stream_id id, void* device_ptr, size_t slot_stride_bytes) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    mmdgpu_context_t ctx = f->ctx;
+    if (mmdgpu_status s = enter(ctx)) return s;
+    const DevModel& M = f->model->dev;
+    const bool soa = f->layout == MMDGPU_LAYOUT_SOA_POS_NRM;
+    size_t rec = 0, align = 16;
+    switch (id) {
+    case MMDGPU_STREAM_POSITION: case MMDGPU_STREAM_NORMAL:
+        if (!soa) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "frames were created with the interleaved layout");
+        rec = 12; break;
+    case MMDGPU_STREAM_INTERLEAVED:
+        if (soa) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "frames were created with the SoA layout");
+        rec = 32; align = 32; break;  // records leave the SM as one 256-bit store each
+    case MMDGPU_STREAM_UV:
+        if (!f->own_uv) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "the UV stream exists only for SoA frames of a model created with extensions");
+        rec = 8; break;
+    default: return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "only the vertex output streams can be bound");
+    }
+    // queued kernels keep the pointers they were launched with; later launches see the new binding
+    f->main_dirty = true;
+    DevFrames& F = f->dev;
+    if (!device_ptr) {  // back to the library-owned buffer
+        if (id == MMDGPU_STREAM_POSITION) { F.out_pos = f->own_pos; F.pos_stride = size_t(M.nv_pad) * 3; }
+        else if (id == MMDGPU_STREAM_NORMAL) { F.out_nrm = f->own_nrm; F.nrm_stride = size_t(M.nv_pad) * 3; }
+        else if (id == MMDGPU_STREAM_INTERLEAVED) { F.out_inter = f->own_inter; F.inter_stride = size_t(M.nv_pad) * 2; }
+        else { F.out_uv = f->own_uv; F.uv_stride = size_t(M.nv_pad); }
+        return MMDGPU_OK;
+    }
+    if (reinterpret_cast<uintptr_t>(device_ptr) % align || slot_stride_bytes % align)
+        return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "bound output pointer and slot stride must be " + std::to_string(align) + "-byte aligned");
+    if (slot_stride_bytes < size_t(M.nv) * rec && F.n_slots > 1)
+        return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "slot stride is smaller than one slot of the stream");
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, device_ptr) != cudaSuccess || (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)) {
+        cudaGetLastError();
+        return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "bound output pointer is not device memory");
+    }
+    if (id == MMDGPU_STREAM_POSITION) { F.out_pos = static_cast<float*>(device_ptr); F.pos_stride = slot_stride_bytes / 4; }
+    else if (id == MMDGPU_STREAM_NORMAL) { F.out_nrm = static_cast<float*>(device_ptr); F.nrm_stride = slot_stride_bytes / 4; }
+    else if (id == MMDGPU_STREAM_INTERLEAVED) { F.out_inter = static_cast<float4*>(device_ptr); F.inter_stride = slot_stride_bytes / 16; }
+    else { F.out_uv = static_cast<float2*>(device_ptr); F.uv_stride = slot_stride_bytes / 8; }
     return MMDGPU_OK;
 }
 

@@ -253,6 +253,15 @@ class Frames:
         check(self.lib.mmdgpu_frames_download_async(self.h, int(first_slot), int(n_slots), int(stream_id),
                                                     C.c_void_p(pinned_ptr), int(nbytes)), self.ctx.h)
 
+    def wait_downloads(self):
+        """Host-blocks until this object's download_async copies have landed (not compute, not other objects)."""
+        check(self.lib.mmdgpu_frames_wait_downloads(self.h), self.ctx.h)
+
+    def bind_output(self, stream_id: int, device_ptr: int | None, slot_stride_bytes: int = 0):
+        """Let the skinning kernel write `stream_id` into caller-owned device memory (None: library buffer again)."""
+        check(self.lib.mmdgpu_frames_bind_output(self.h, int(stream_id), C.c_void_p(device_ptr) if device_ptr else None,
+                                                 int(slot_stride_bytes)), self.ctx.h)
+
     def bone_matrices(self, slot: int = 0) -> np.ndarray:
         out = np.empty((self.model.n_bones, 16), np.float32)
         check(self.lib.mmdgpu_bone_matrices_download(self.h, int(slot), _ptr(out)), self.ctx.h)

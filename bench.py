@@ -4,12 +4,18 @@
 One step = one pass of the whole hot path (VMD sampling K1 -> bone hierarchy / CCD IK / palette K2 -> morph
 gather + skinning K3) over one batch of (instance, frame) slots of a synthetic PMX/VMD:
 
-  workload C3 (default): 1 M vertices, 1 k bones, 200 vertex morphs; `--frames-per-step` consecutive VMD frames
-                         per step per GPU (the bake pattern of BASELINE configs[2]/[4]); N > 1 shards by frame
+  workload C3 (default, headline): 1 M vertices, 1 k bones, 200 vertex morphs; `--frames-per-step` consecutive VMD
+                         frames per step per GPU (the bake pattern of BASELINE configs[2]/[4]); N > 1 shards by frame
                          range, every rank fully independent ("scaling": "weak").
   workload C4:           512 instances of the 50 k-vertex model with independent clips, one frame each per
                          step, instances sharded across ranks ("scaling": "strong").
+  workload C5:           offline bake: a 10 k-frame VMD on the 1 M-vertex model, frame range sharded across ranks, 64-frame
+                         windows, every window's positions + normals gathered to rank 0 over NCCL ("scaling": "strong").
   workload C1 / C2:      one 50 k-vertex model (C2 adds SDEF/QDEF tags, UV/group/bone morphs, two CCD IK chains).
+
+Whatever the headline workload, the same run also measures the other BASELINE configs briefly and reports them under
+"also" (C4 strong scaling, the C5 bake with its gather, C3 with random bone binding, C1, C2 at several batch sizes) —
+at every N, so that the driver's 1/2/4/8 scaling run carries them.
 
 `--impl reference` times the reference's own CPU implementation (libmmd, compiled into oracle/_ref; else the
 C restatement) on the host cores for the same workload.
@@ -25,6 +31,7 @@ import subprocess
 import sys
 import tempfile
 import time
+from dataclasses import replace
 
 import numpy as np
 
@@ -34,6 +41,8 @@ if ROOT not in sys.path:
 
 METRIC = "skinned_vertex_frames_per_sec"
 UNIT = "vertex-frames/s"
+BAKE_FRAMES = 10_000      # BASELINE configs[4]
+BAKE_WINDOW = 64          # frames per fused update and per gather round
 
 
 def parse_args():
@@ -42,20 +51,21 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="mmdgpu", choices=["mmdgpu", "reference"])
-    ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4"])
+    ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--frames-per-step", type=int, default=128, help="C1/C2/C3: VMD frames per step per GPU")
     ap.add_argument("--instances", type=int, default=512, help="C4: crowd size (whole job)")
     ap.add_argument("--layout", default="soa", choices=["soa", "sokol32"])
+    ap.add_argument("--binding", default="coherent", choices=["coherent", "random"], help="vertex -> bone binding of the synthetic model")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-also", action="store_true", help="skip the short secondary measurements of C1 / C2 / C4")
-    ap.add_argument("--gather", action="store_true",
-                    help="N > 1: also time the NCCL gather of one window of baked frames to rank 0 (reported separately)")
+    ap.add_argument("--no-also", action="store_true", help="skip the short measurements of the other BASELINE configs")
+    ap.add_argument("--also", default="C1,C2,C4,C5,C3_random", help="which secondary measurements to run")
+    ap.add_argument("--bake-frames", type=int, default=BAKE_FRAMES)
     return ap.parse_args()
 
 
 def algorithmic_bytes_per_vertex(model: dict, layout: str) -> float:
-    """48 B static read + 24 B write + 4 B CSR row pointer + 16 B per morph entry
+    """SURVEY 8(d), streaming model: 48 B static read + 24 B write + 4 B CSR row pointer + 16 B per morph entry
     (+8 B uv read +8 B wider record for the interleaved layout)."""
     e = float(model["n_vertex_morph_entries"]) / max(1, int(model["n_vertices"]))
     b = 48.0 + 24.0 + 4.0 + 16.0 * e
@@ -73,15 +83,53 @@ def measured_peaks():
     return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
 
 
-def ncu_traffic_bytes(workload: str, layout: str = "soa"):
-    """dram read+write bytes per skin launch from the committed ncu capture, if there is one for this workload
-    (captured for the SoA layout at the default 128 frames per step)."""
+def ncu_traffic_bytes(workload: str, layout: str, slots: int, binding: str = "coherent"):
+    """dram read + write bytes per skin launch from the committed ncu capture of exactly this configuration, else None."""
     p = os.path.join(ROOT, "profiles", "skin_dram_traffic.json")
-    if layout == "soa" and os.path.exists(p):
-        with open(p) as f:
-            d = json.load(f)
-        return d.get(workload)
-    return None
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    key = f"{workload}/{layout}/{slots}" + ("" if binding == "coherent" else f"/{binding}")
+    v = d.get(key)
+    if v is None and layout == "soa" and slots == 128 and binding == "coherent":
+        v = d.get(workload)   # round-1 key
+    return v
+
+
+def skin_roofline(model: dict, layout: str, slots: int, slots_per_cta: int, skin_ms: float, workload: str, binding: str) -> dict:
+    """Roofline of the skinning kernel.
+
+    `achieved` / `frac` are PHYSICAL: bytes that must cross the HBM interface per launch — every output record once
+    (24 or 32 B per vertex-frame) plus the tile's static streams and morph table once per (tile, slot run) — divided by
+    the measured launch time.  `traffic` is what ncu counted for the same launch (committed capture), and when it exists
+    `frac` is computed from it instead of the model.  The SURVEY 8(d) streaming figure (static streams counted once per
+    vertex-FRAME, which the kernel avoids by keeping a tile in registers across a slot run) is kept as *_streaming_model.
+    """
+    nv = int(model["n_vertices"])
+    peak, peak_src = measured_peaks()
+    e = float(model["n_vertex_morph_entries"]) / max(1, nv)
+    out_b = 32.0 if layout == "sokol32" else 24.0
+    static_b = 48.0 + 2.0 + 16.0 * e + (8.0 if layout == "sokol32" else 0.0)   # streams + PMX index + sliced-ELL entries (+uv)
+    runs = max(1, (slots + max(1, slots_per_cta) - 1) // max(1, slots_per_cta))
+    model_bytes = nv * (out_b * slots + static_b * runs)
+    traffic = ncu_traffic_bytes(workload, layout, slots, binding)
+    phys = float(traffic) if traffic else model_bytes
+    b_alg = algorithmic_bytes_per_vertex(model, layout)
+    t = skin_ms * 1e-3
+    ach = phys / t / 1e9 if t > 0 else 0.0
+    ach_stream = b_alg * nv * slots / t / 1e9 if t > 0 else 0.0
+    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None,
+            "traffic": traffic, "kernel": "skin_kernel", "avg_launch_ms": skin_ms, "peak_source": peak_src,
+            "bytes_per_launch": phys, "bytes_source": "ncu dram__bytes_read+write (profiles/skin_dram_traffic.json)" if traffic
+            else "model: output once + static streams once per (tile, slot run)",
+            "bytes_per_launch_model": model_bytes, "output_bytes_per_vertex_frame": out_b,
+            "vertices_per_launch": nv * slots, "slots_per_cta_run": slots_per_cta,
+            "frac_of_nominal_8TBs": ach / 8000.0,
+            "algorithmic_bytes_per_vertex_streaming_model": b_alg,
+            "achieved_streaming_model": ach_stream, "frac_streaming_model": ach_stream / peak if peak else None,
+            "note": "frac is physical HBM traffic / time / measured copy peak; the streaming model counts static streams "
+                    "once per vertex-frame (SURVEY 8d) although the kernel reads them once per 64-slot run, so it can exceed 1"}
 
 
 class ClockSampler:
@@ -144,38 +192,19 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def bind_to_gpu_numa(device_index: int):
-    """Pin this rank to the CPUs of its GPU's NUMA node before any pinned host memory is allocated, so that the
-    device->host copies of the e2e leg land in local memory (8 ranks on a 2-socket host otherwise share one UPI)."""
-    try:
-        import torch
-        props = torch.cuda.get_device_properties(device_index)
-        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
-        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
-            node = int(f.read().strip())
-        if node < 0:
-            return None
-        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
-            spec = f.read().strip()
-        cpus = set()
-        for part in spec.split(","):
-            a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-            return node
-    except Exception:
-        return None
-    return None
-
-
-def build_inputs(args):
+def synth_config(workload: str, binding: str = "coherent"):
     from simple_mmd_renderer_b200 import synth
-    wl = args.workload
-    cfg = synth.CONFIGS[wl]
-    model = synth.make_model(cfg)
-    return cfg, model
+    cfg = synth.CONFIGS["C3" if workload == "C5" else workload]
+    if workload == "C5":
+        cfg = replace(cfg, name="C5")          # the C3 model; the 10 k-frame clip is built by bake_motion()
+    if binding != "coherent":
+        cfg = replace(cfg, binding=binding, name=f"{cfg.name}_{binding}")
+    return cfg
+
+
+def bake_motion(cfg, model, n_frames: int):
+    from simple_mmd_renderer_b200 import synth
+    return synth.make_motion(replace(cfg, n_frames=n_frames), model)
 
 
 def host_threads() -> int:
@@ -199,33 +228,55 @@ def frames_for_step(step: int, n: int, clip_len: int) -> np.ndarray:
     return ((first + np.arange(n)) % (clip_len + 1)).astype(np.uint32)
 
 
+def slots_per_step(args, cfg) -> int:
+    if args.workload == "C4":
+        return args.instances // max(1, args.gpus)
+    if args.workload == "C5":
+        return BAKE_WINDOW
+    return args.frames_per_step
+
+
+def workload_config(args, cfg, model, n_slots):
+    """Identical in both arms (the driver compares it): what is evaluated per step, not where."""
+    e = float(model["n_vertex_morph_entries"]) / max(1, int(model["n_vertices"]))
+    return {
+        "workload": f"{cfg.name}: {cfg.n_vertices} vertices, {cfg.n_bones} bones, {int(model['n_morphs'])} morphs "
+                    f"(e={e:.2f} morph entries/vertex), {cfg.n_frames}-frame VMD, physics off",
+        "slots_per_step_per_gpu": int(n_slots), "layout": args.layout, "binding": cfg.binding,
+        "l2": f"every step writes its slots' output ({n_slots * cfg.n_vertices * 24 / 1e6:.0f} MB per GPU; L2 is "
+              "126 MB) between re-reads of the static streams; no separate flush",
+    }
+
+
 # ------------------------------------------------------------------------------------------ reference arm
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from simple_mmd_renderer_b200 import synth
-    cfg, model = build_inputs(args)
+    cfg = synth_config(args.workload, args.binding)
+    model = synth.make_model(cfg)
     motion = synth.make_motion(cfg, model)
     ses, kind = cpu_session(model, motion)
     T = host_threads()
     nv = int(model["n_vertices"])
-    per_step = 2 * T if nv >= 500_000 else 16 * T
+    n_slots = slots_per_step(args, cfg)          # the same batch the GPU arm evaluates per step and per GPU
     times = []
     for s in range(args.warmup + args.steps):
-        fr = frames_for_step(s, per_step, cfg.n_frames)
+        fr = frames_for_step(s, n_slots, cfg.n_frames)
         sec, _ = ses.time_frames(fr, T)
         if s >= args.warmup:
             times.append(sec)
     total = float(sum(times))
-    value = per_step * nv * args.steps / total
-    sample = f"{per_step} frames of {cfg.name} per step on {T} host threads (private Poser per thread, shared Model)"
+    value = n_slots * nv * args.steps / total
+    sample = f"{n_slots} frames of {cfg.name} per step on {T} host threads (private Poser per thread, shared Model)"
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
-        "scaling": "strong" if args.workload == "C4" else "weak", "vs_baseline": None, "dtype": "f32",
+        "scaling": "strong" if args.workload in ("C4", "C5") else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": workload_config(args, cfg, model, per_step, "host"),
+        "config": workload_config(args, cfg, model, n_slots),
+        "where": "host: libmmd on the box's CPU threads",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": T, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -233,101 +284,344 @@ def run_reference(args):
     print(json.dumps(out), flush=True)
 
 
-def workload_config(args, cfg, model, slots_per_step, where):
-    e = float(model["n_vertex_morph_entries"]) / max(1, int(model["n_vertices"]))
-    return {
-        "workload": f"{cfg.name}: {cfg.n_vertices} vertices, {cfg.n_bones} bones, {int(model['n_morphs'])} morphs "
-                    f"(e={e:.2f} morph entries/vertex), {cfg.n_frames}-frame VMD, physics off",
-        "slots_per_step_per_gpu": int(slots_per_step), "layout": args.layout, "where": where,
-        "l2": f"every step writes its slots' output ({slots_per_step * cfg.n_vertices * 24 / 1e6:.0f} MB per GPU; L2 is "
-              "126 MB) between re-reads of the static streams; no separate flush",
-    }
-
-
 # ------------------------------------------------------------------------------------------ own arm
-def quick_measure(ctx, stream, workload: str, steps: int = 10, warmup: int = 3) -> dict:
-    """Short device-resident measurement of another BASELINE config (reported under "also"; not the headline)."""
-    import torch
-    from simple_mmd_renderer_b200 import synth
-    from simple_mmd_renderer_b200.poser import Frames, Model, Motion
-    cfg = synth.CONFIGS[workload]
-    model = synth.make_model(cfg)
-    m = Model(ctx, model)
-    if workload == "C4":
-        n_inst, n_frames = 512, 1
-        motions = [Motion(m, synth.make_motion(cfg, model, instance=i)) for i in range(n_inst)]
-        what = "512 instances x 1 frame per step, independent clips"
-    else:
-        # C2's hierarchy kernel is a long latency-bound chain per slot (sequential CCD IK): it needs a larger batch
-        # to amortise (54 G at 512 slots, 64 G at 2048, 68 G at 4096 vertex-frames/s on B200)
-        n_inst, n_frames = 1, (2048 if workload == "C2" else 512)
-        motions = [Motion(m, synth.make_motion(cfg, model))]
-        what = f"{n_frames} consecutive-frame slots per step"
-    fr = Frames(m, n_inst, n_frames)
-    rng = np.random.default_rng(7)
+class Env:
+    """Process-wide state of one rank."""
 
-    def step(s):
-        if workload == "C4":
-            first = rng.integers(0, cfg.n_frames, n_inst).astype(np.uint32)
-        else:
-            first = np.asarray([(s * 37) % cfg.n_frames], np.uint32)
-        fr.update_range(motions, first, 1)
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dev = f"cuda:{self.local}"
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x: float) -> float:
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+
+def timed_updates(env: Env, ctx, stream, step_fn, steps: int, warmup: int):
+    """W untimed + K timed calls of step_fn(s) between barriers; returns (max-over-ranks ms, kernel ms[3], launches[3])."""
+    torch = env.torch
     for s in range(warmup):
-        step(s)
+        step_fn(s)
     ctx.synchronize()
     ctx.set_profiling(True)
     ctx.profile_read()
+    env.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for s in range(steps):
-        step(warmup + s)
+        step_fn(warmup + s)
     e1.record(stream)
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    env.barrier()
+    ms = env.max_over_ranks(e0.elapsed_time(e1))
     kms, kn = ctx.profile_read()
     ctx.set_profiling(False)
+    return ms, kms, kn
+
+
+def isolated_kernel_ms(ctx, step_fn, base: int, reps: int = 3) -> dict:
+    """Per-kernel time with nothing else running: every update is followed by a full synchronize, so the event pairs on
+    the sampling / hierarchy streams are not stretched by the skinning kernel of the previous update."""
+    ctx.synchronize()
+    ctx.set_profiling(True)
+    ctx.profile_read()
+    for s in range(reps):
+        step_fn(base + s)
+        ctx.synchronize()
+    kms, kn = ctx.profile_read()
+    ctx.set_profiling(False)
+    return {"pose_sample": kms[0] / reps, "hierarchy": kms[1] / reps, "skin": kms[2] / reps,
+            "hierarchy_launches_per_update": kn[1] / reps,
+            "note": "ms per update, each update run alone (synchronize between updates)"}
+
+
+def measure_batch(env: Env, ctx, stream, workload: str, n_frames: int, steps: int = 10, warmup: int = 3, binding: str = "coherent",
+                  model_cache: dict | None = None) -> dict:
+    """Device-resident measurement of one model at one batch size on THIS rank (every rank does the same work)."""
+    from simple_mmd_renderer_b200 import synth
+    from simple_mmd_renderer_b200.poser import Frames, Model, Motion
+    cfg = synth_config(workload, binding)
+    key = (workload, binding)
+    if model_cache is not None and key in model_cache:
+        model, m, motion = model_cache[key]
+    else:
+        model = synth.make_model(cfg)
+        m = Model(ctx, model)
+        motion = Motion(m, synth.make_motion(cfg, model))
+        if model_cache is not None:
+            model_cache[key] = (model, m, motion)
+    fr = Frames(m, 1, n_frames)
+
+    def step(s):
+        fr.update_range(motion, np.asarray([(s * 37) % max(1, cfg.n_frames - n_frames + 1)], np.uint32), 1)
+    ms, kms, kn = timed_updates(env, ctx, stream, step, steps, warmup)
     nv = int(model["n_vertices"])
-    slots = n_inst * n_frames
-    b_alg = algorithmic_bytes_per_vertex(model, "soa")
     skin_ms = kms[2] / max(1, kn[2])
-    peak, _ = measured_peaks()
-    out = {"value": slots * nv * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
-           "slots_per_step": slots, "batch": what, "algorithmic_bytes_per_vertex": b_alg,
-           "skin_ms_per_launch": skin_ms,
-           "skin_frac_of_measured_hbm": (b_alg * nv * slots / (skin_ms * 1e-3) / 1e9 / peak) if skin_ms > 0 else None}
-    del fr, motions, m
+    roof = skin_roofline(model, "soa", n_frames, fr.slots_per_cta, skin_ms, workload, binding)
+    iso = isolated_kernel_ms(ctx, step, warmup + steps, 2)
+    out = {"value": env.world * n_frames * nv * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+           "slots_per_step_per_gpu": n_frames, "scaling": "weak", "skin_ms_per_launch": skin_ms,
+           "skin_frac_of_measured_hbm": roof["frac"], "skin_frac_streaming_model": roof["frac_streaming_model"],
+           "kernel_ms_isolated": iso}
+    fr.close()
     return out
+
+
+def measure_crowd(env: Env, ctx, stream, total_inst: int, steps: int, warmup: int) -> dict:
+    """BASELINE configs[3]: `total_inst` instances of the 50 k-vertex model with independent clips, contiguous instance
+    blocks per rank, one frame per instance per step.  Strong scaling: the whole job is fixed."""
+    from simple_mmd_renderer_b200 import shard, synth
+    from simple_mmd_renderer_b200.poser import Frames, Model, Motion
+    cfg = synth.CONFIGS["C4"]
+    model = synth.make_model(cfg)
+    m = Model(ctx, model)
+    lo, hi = shard.split_range(total_inst, env.world, env.rank)
+    motions = [Motion(m, synth.make_motion(cfg, model, instance=i)) for i in range(lo, hi)]
+    fr = Frames(m, hi - lo, 1)
+    rng = np.random.default_rng(99 + env.rank)
+
+    def step(s):
+        fr.update_range(motions, ((s * 3 + rng.integers(0, cfg.n_frames, hi - lo)) % (cfg.n_frames + 1)).astype(np.uint32), 1)
+    ms, kms, kn = timed_updates(env, ctx, stream, step, steps, warmup)
+    nv = int(model["n_vertices"])
+    out = {"value": total_inst * nv * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+           "instances": total_inst, "instances_per_gpu": hi - lo, "scaling": "strong", "n_gpus": env.world,
+           "skin_ms_per_launch": kms[2] / max(1, kn[2]),
+           "kernel_ms_isolated": isolated_kernel_ms(ctx, step, warmup + steps, 2),
+           "batch": f"{total_inst} instances x 1 frame per step, independent clips, sharded by instance"}
+    fr.close()
+    for a in motions:
+        a.close()
+    m.close()
+    return out
+
+
+def measure_bake(env: Env, ctx, stream, m, model, cfg, n_frames_total: int, window: int) -> dict:
+    """BASELINE configs[4]: a `n_frames_total`-frame clip baked on the 1 M-vertex model, contiguous frame ranges per rank,
+    `window` frames per fused update.  Three passes over the whole clip:
+      compute   every rank bakes its range, outputs stay on the device                       -> value_compute
+      gather    + after every window, positions AND normals of all ranks go to rank 0 over NCCL (torch.distributed.gather
+                on the library's output buffers, zero-copy; window k's gather overlaps window k+1's evaluation)
+      p2p       + instead of NCCL, every rank's skinning kernel writes its window straight into rank 0's receive buffer
+                (bulk stores over NVLink into peer memory bound with mmdgpu_frames_bind_output): compute and gather are
+                one kernel; a 4-byte all-reduce per window orders it against the root
+    `value` is the bake WITH the NCCL gather (whole clip, max over ranks)."""
+    torch, dist = env.torch, env.dist
+    from simple_mmd_renderer_b200 import capi, shard
+    from simple_mmd_renderer_b200.poser import Frames, Motion
+    nv = int(model["n_vertices"])
+    motion = Motion(m, bake_motion(cfg, model, n_frames_total))
+    lo, hi = shard.split_range(n_frames_total, env.world, env.rank)
+    wins = list(shard.bake_windows(lo, hi, window))
+    n_rounds = shard.n_windows(n_frames_total, env.world, window)
+    frames = [Frames(m, 1, window), Frames(m, 1, window)]
+    # outputs bound to plain torch tensors: contiguous [window, nv, 3], what NCCL sends without a staging copy
+    outs = []
+    for fr in frames:
+        pos = torch.empty((window, nv, 3), dtype=torch.float32, device=env.dev)
+        nrm = torch.empty((window, nv, 3), dtype=torch.float32, device=env.dev)
+        fr.bind_output(capi.STREAM_POSITION, pos.data_ptr(), nv * 12)
+        fr.bind_output(capi.STREAM_NORMAL, nrm.data_ptr(), nv * 12)
+        outs.append((pos, nrm))
+    recv = None
+    if env.world > 1 and env.rank == 0:
+        recv = [[(torch.empty((window, nv, 3), dtype=torch.float32, device=env.dev),
+                  torch.empty((window, nv, 3), dtype=torch.float32, device=env.dev)) for _ in range(env.world)] for _ in range(2)]
+
+    def evaluate(k):
+        if k < len(wins):
+            frames[k & 1].update_range(motion, np.asarray([wins[k][0]], np.uint32), 1)
+
+    def run(mode):
+        works = [None, None]
+        with torch.cuda.stream(stream):
+            env.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for k in range(n_rounds):
+                b = k & 1
+                if works[b] is not None:            # window k-2's gather must have read this buffer pair
+                    for w in works[b]:
+                        w.wait()                    # stream-level wait, the host does not block
+                evaluate(k)
+                if mode == "gather" and env.world > 1:
+                    pos, nrm = outs[b]
+                    works[b] = [dist.gather(pos, [r[0] for r in recv[b]] if env.rank == 0 else None, dst=0, async_op=True),
+                                dist.gather(nrm, [r[1] for r in recv[b]] if env.rank == 0 else None, dst=0, async_op=True)]
+            for ws in works:
+                if ws is not None:
+                    for w in ws:
+                        w.wait()
+            e1.record(stream)
+            env.barrier()
+        return env.max_over_ranks(e0.elapsed_time(e1))
+
+    for k in range(min(2, len(wins))):               # warm-up: both frames objects, NCCL channels
+        evaluate(k)
+    ctx.synchronize()
+    if env.world > 1:
+        run("gather")
+    ms_compute = run("compute")
+    ms_gather = run("gather") if env.world > 1 else None
+    total_vf = float(n_frames_total) * nv
+    bytes_into_root = 0
+    for r in range(1, env.world):
+        rlo, rhi = shard.split_range(n_frames_total, env.world, r)
+        bytes_into_root += (rhi - rlo) * nv * 24
+    sent_padded = (env.world - 1) * n_rounds * window * nv * 24    # what NCCL actually moves (whole windows)
+    seen = int(env.sum_over_ranks(1.0))
+    out = {"value": total_vf / ((ms_gather if ms_gather else ms_compute) * 1e-3), "unit": UNIT, "scaling": "strong", "n_gpus": env.world,
+           "frames": n_frames_total, "frames_per_gpu": hi - lo, "window": window, "windows_per_gpu": n_rounds,
+           "bake_seconds_compute_only": ms_compute * 1e-3, "value_compute": total_vf / (ms_compute * 1e-3),
+           "gather": None if ms_gather is None else {
+               "bake_seconds_with_gather": ms_gather * 1e-3, "streams": "position + normal, every window",
+               "bytes_into_root": int(bytes_into_root), "bytes_moved_incl_window_padding": int(sent_padded),
+               "gbs_into_root": sent_padded / (ms_gather * 1e-3) / 1e9,
+               "gbs_into_root_excess_over_compute": sent_padded / (max(ms_gather - ms_compute, 1e-6) * 1e-3) / 1e9,
+               "comm_nranks_seen": seen, "collective": "torch.distributed.gather (NCCL), async, window k overlaps evaluation of k+1"},
+           "comm_nranks_seen": seen,
+           "note": "value = whole bake including the NCCL gather of every window to rank 0 (compute-only at N = 1: nothing to gather)"}
+    # ---- fused variant: peers' skinning kernels store into rank 0's memory
+    if env.world > 1:
+        try:
+            out["p2p_fused"] = bake_p2p(env, ctx, stream, frames, outs, motion, wins, n_rounds, window, nv, total_vf, sent_padded)
+        except Exception as ex:   # IPC mapping is a platform capability; the NCCL numbers above stand without it
+            out["p2p_fused"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+        env.barrier()
+    for fr in frames:
+        fr.close()
+    motion.close()
+    return out
+
+
+def bake_p2p(env: Env, ctx, stream, frames, outs, motion, wins, n_rounds, window, nv, total_vf, sent_padded) -> dict:
+    torch, dist = env.torch, env.dist
+    from simple_mmd_renderer_b200 import capi, shard
+    peer = shard.PeerWindows(ctx, env.world, env.rank, 2, window * nv * 3)   # [buffer][rank] x (pos, nrm) on rank 0
+    flag = torch.zeros(1, dtype=torch.int32, device=env.dev)
+    for b, fr in enumerate(frames):
+        ppos, pnrm = peer.slot(b, env.rank)
+        fr.bind_output(capi.STREAM_POSITION, ppos, nv * 12)
+        fr.bind_output(capi.STREAM_NORMAL, pnrm, nv * 12)
+
+    def run():
+        with torch.cuda.stream(stream):
+            env.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for k in range(n_rounds):
+                if k < len(wins):
+                    frames[k & 1].update_range(motion, np.asarray([wins[k][0]], np.uint32), 1)
+                dist.all_reduce(flag)     # window k of every rank has landed on rank 0 / rank 0 may reuse buffer k & 1
+            e1.record(stream)
+            env.barrier()
+        return env.max_over_ranks(e0.elapsed_time(e1))
+    run()
+    ms = run()
+    # ---- check: every rank re-bakes its last window into local memory; rank 0 compares checksums of the bits
+    for b, fr in enumerate(frames):
+        fr.bind_output(capi.STREAM_POSITION, outs[b][0].data_ptr(), nv * 12)
+        fr.bind_output(capi.STREAM_NORMAL, outs[b][1].data_ptr(), nv * 12)
+    last = len(wins) - 1
+    with torch.cuda.stream(stream):
+        sums = torch.zeros(2, dtype=torch.int64, device=env.dev)
+        if last >= 0:
+            frames[last & 1].update_range(motion, np.asarray([wins[last][0]], np.uint32), 1)
+            ctx.synchronize()
+            sums[0] = outs[last & 1][0].view(torch.int32).sum(dtype=torch.int64)
+            sums[1] = outs[last & 1][1].view(torch.int32).sum(dtype=torch.int64)
+        info = torch.tensor([last], dtype=torch.int64, device=env.dev)
+        all_sums = [torch.zeros_like(sums) for _ in range(env.world)]
+        all_last = [torch.zeros_like(info) for _ in range(env.world)]
+        dist.all_gather(all_sums, sums)
+        dist.all_gather(all_last, info)
+        ok = None
+        if env.rank == 0:
+            ok = True
+            for r in range(env.world):
+                lr = int(all_last[r].item())
+                if lr < 0:
+                    continue
+                got0 = peer.tensor(lr & 1, r, 0, (window * nv * 3,)).view(torch.int32).sum(dtype=torch.int64)
+                got1 = peer.tensor(lr & 1, r, 1, (window * nv * 3,)).view(torch.int32).sum(dtype=torch.int64)
+                ok = ok and bool(got0 == all_sums[r][0]) and bool(got1 == all_sums[r][1])
+        torch.cuda.synchronize()
+    env.barrier()
+    peer.close()
+    return {"bake_seconds": ms * 1e-3, "value": total_vf / (ms * 1e-3), "gbs_into_root": sent_padded / (ms * 1e-3) / 1e9,
+            "bit_identical_to_local_bake": ok,
+            "how": "skin_kernel's cp.async.bulk shared->global stores target rank 0's buffer (CUDA IPC mapping, NVLink); "
+                   "one 4-byte NCCL all-reduce per window orders producers and consumer"}
 
 
 def run_mmdgpu(args):
     import torch
     import torch.distributed as dist
-    from simple_mmd_renderer_b200 import capi, lib, synth
+    from simple_mmd_renderer_b200 import capi, hostmem, lib, shard, synth
     from simple_mmd_renderer_b200.poser import Context, Frames, Model, Motion
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    env = Env()
+    world, rank, local = env.world, env.rank, env.local
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the deformation path has no CPU fallback")
     if not os.path.exists(lib.SO_PATH):
         if local == 0:
             lib.build_library()
     torch.cuda.set_device(local)
-    numa_node = bind_to_gpu_numa(local) if world > 1 else None
+    numa = hostmem.bind_to_gpu_numa(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
 
-    cfg, model = build_inputs(args)
+    cfg = synth_config(args.workload, args.binding)
+    model = synth.make_model(cfg)
     nv = int(model["n_vertices"])
     layout = capi.LAYOUT_SOA_POS_NRM if args.layout == "soa" else capi.LAYOUT_INTERLEAVED_SOKOL32
     stream = torch.cuda.Stream(device=local)
     ctx = Context(local, stream.cuda_stream)
     m = Model(ctx, model)
+    out = None
+    if args.workload == "C5":
+        # the bake IS the step loop: one pass over the whole clip; `steps` / `warmup` are reported, not used
+        bake = measure_bake(env, ctx, stream, m, model, cfg, args.bake_frames, BAKE_WINDOW)
+        if rank == 0:
+            out = {"metric": METRIC, "value": bake["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                   "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                   "data": "synthetic", "config": workload_config(args, cfg, model, BAKE_WINDOW), "bake": bake}
+    else:
+        out = headline(args, env, ctx, stream, m, model, cfg, layout, numa)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def headline(args, env: Env, ctx, stream, m, model, cfg, layout, numa):
+    torch, dist = env.torch, env.dist
+    from simple_mmd_renderer_b200 import capi, shard, synth
+    from simple_mmd_renderer_b200.poser import Frames, Motion
+    world, rank, local = env.world, env.rank, env.local
+    nv = int(model["n_vertices"])
     if args.workload == "C4":
-        total_inst = args.instances
-        lo, hi = total_inst * rank // world, total_inst * (rank + 1) // world
+        lo, hi = shard.split_range(args.instances, world, rank)
         n_inst, n_frames = hi - lo, 1
         motions = [Motion(m, synth.make_motion(cfg, model, instance=i)) for i in range(lo, hi)]
     else:
@@ -347,19 +641,14 @@ def run_mmdgpu(args):
     def step(s):
         fr.update_range(motions, first_frames(s), 1)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident throughput
+    # ---- device-resident throughput (the headline `value`)
+    sampler = ClockSampler(local) if rank == 0 else None
     for s in range(args.warmup):
         step(s)
     ctx.synchronize()
     ctx.set_profiling(True)
     ctx.profile_read()
-    sampler = ClockSampler(local) if rank == 0 else None
-    barrier()
+    env.barrier()
     if sampler:
         sampler.start()
     launches0 = ctx.launch_count
@@ -368,18 +657,14 @@ def run_mmdgpu(args):
     for s in range(args.steps):
         step(args.warmup + s)
     e1.record(stream)
-    barrier()
+    env.barrier()
     launches = ctx.launch_count - launches0
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")
+    total_ms = env.max_over_ranks(e0.elapsed_time(e1))
     kernel_ms, kernel_n = ctx.profile_read()
     ctx.set_profiling(False)
-    slots_t = torch.tensor([float(slots)], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(slots_t, op=dist.ReduceOp.SUM)
-    total_ms = float(ms.item())
-    total_slots = float(slots_t.item())
+    total_slots = env.sum_over_ranks(float(slots))
     value = total_slots * nv * args.steps / (total_ms * 1e-3)
+    iso = isolated_kernel_ms(ctx, step, args.warmup + args.steps)
 
     # ---- end to end through the C-ABI with host buffers: frame ids in, deformed vertex buffers out (pinned)
     e2e = None
@@ -387,6 +672,8 @@ def run_mmdgpu(args):
         stream_ids = [capi.STREAM_POSITION, capi.STREAM_NORMAL] if args.layout == "soa" else [capi.STREAM_INTERLEAVED]
         per_stream = nv * (12 if args.layout == "soa" else 32) * slots
         host = [torch.empty(per_stream, dtype=torch.uint8, pin_memory=True) for _ in stream_ids]
+        for h in host:
+            h.zero_()
         h2d = 4 * n_inst
         d2h = per_stream * len(stream_ids)
 
@@ -399,46 +686,43 @@ def run_mmdgpu(args):
         e2e_steps = max(3, min(args.steps, 10))
         for s in range(2):
             e2e_step(s)
-        barrier()
+        env.barrier()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record(stream)
         for s in range(e2e_steps):
             e2e_step(2 + s)
         a1.record(stream)
-        barrier()
-        ems = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=f"cuda:{local}")
-        if world > 1:
-            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        e2e = {"value": total_slots * nv * e2e_steps / (float(ems.item()) * 1e-3), "unit": UNIT,
+        env.barrier()
+        ems = env.max_over_ranks(a0.elapsed_time(a1))
+        # the platform's ceiling for the same bytes: plain cudaMemcpyAsync of contiguous device memory into the same
+        # pinned buffers, all ranks at once, no kernels (tools/d2h_ceiling.py is the standalone form)
+        src = [torch.empty(per_stream, dtype=torch.uint8, device=env.dev) for _ in stream_ids]
+        with torch.cuda.stream(stream):
+            for h, d in zip(host, src):
+                h.copy_(d, non_blocking=True)
+            env.barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(stream)
+            for _ in range(3):
+                for h, d in zip(host, src):
+                    h.copy_(d, non_blocking=True)
+            c1.record(stream)
+            env.barrier()
+        cms = env.max_over_ranks(c0.elapsed_time(c1)) / 3
+        del src
+        e2e_gbs = d2h * e2e_steps / (ems * 1e-3) / 1e9
+        ceil_gbs = d2h / (cms * 1e-3) / 1e9
+        e2e = {"value": total_slots * nv * e2e_steps / (ems * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-               "ms_per_step": float(ems.item()) / e2e_steps,
-               "note": "update_range + download of every slot's deformed buffer to pinned host memory, per GPU",
-               "numa_node_of_rank0": numa_node}
+               "ms_per_step": ems / e2e_steps,
+               "d2h_gbs_per_gpu": e2e_gbs, "d2h_ceiling_gbs_per_gpu": ceil_gbs, "frac_of_d2h_ceiling": e2e_gbs / ceil_gbs if ceil_gbs else None,
+               "d2h_gbs_aggregate": e2e_gbs * world, "d2h_ceiling_gbs_aggregate": ceil_gbs * world,
+               "note": "update_range + download of every slot's deformed buffer to pinned host memory, per GPU; the ceiling is "
+                       "a bare cudaMemcpyAsync of the same bytes into the same buffers by all ranks at once",
+               "numa": numa}
+        del host
 
     clocks = sampler.stop() if sampler else None
-
-    # ---- optional: NCCL gather of one window of baked frames to rank 0 (bake pattern; not part of `value`)
-    gather = None
-    if args.gather and world > 1 and args.layout == "soa":
-        from simple_mmd_renderer_b200 import shard
-        local_t = shard.frames_as_tensor(fr, capi.STREAM_POSITION).contiguous()
-        torch.cuda.synchronize()
-        for _ in range(2):
-            shard.gather_window(local_t, slots, root=0)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
-        g0.record()
-        for _ in range(reps):
-            shard.gather_window(local_t, slots, root=0)
-        g1.record()
-        barrier()
-        gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
-        nbytes = local_t.numel() * 4 * (world - 1)
-        gather = {"bytes_into_root_per_window": int(nbytes), "ms_per_window": float(gms.item()) / reps,
-                  "gbs_into_root": nbytes * reps / (float(gms.item()) * 1e-3) / 1e9,
-                  "note": "torch.distributed.gather (NCCL) of every rank's position plane for one window of frames"}
 
     # ---- CPU baseline (rank 0, N = 1 only): libmmd itself on a bounded sample
     cpu = None
@@ -466,48 +750,62 @@ def run_mmdgpu(args):
                                      "flags": "-O3 -march=x86-64-v3 (contraction on; not parity-grade)",
                                      "sample": f"{nfr} frames, {secf:.2f} s wall"}
                 fast.close()
+        ses.close()
 
+    spc = fr.slots_per_cta
+    fr.close()
+
+    # ---- the other BASELINE configs, briefly, at every N (all ranks take part)
     also = None
-    if rank == 0 and world == 1 and not args.no_also:
+    if not args.no_also:
+        want = [w for w in args.also.split(",") if w]
         also = {}
-        for wl in ("C1", "C2", "C4"):
-            if wl != args.workload:
-                also[wl] = quick_measure(ctx, stream, wl)
+        cache = {}
 
-    if rank == 0:
-        b_alg = algorithmic_bytes_per_vertex(model, args.layout)
-        peak, peak_src = measured_peaks()
-        skin_ms = kernel_ms[2] / max(1, kernel_n[2])
-        achieved = b_alg * nv * slots / (skin_ms * 1e-3) / 1e9 if skin_ms > 0 else 0.0
-        out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if args.workload == "C4" else "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": workload_config(args, cfg, model, slots, "device-resident inputs and outputs"),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": ncu_traffic_bytes(args.workload, args.layout),
-                         "kernel": "skin_kernel", "algorithmic_bytes_per_vertex": b_alg,
-                         "vertices_per_launch": nv * slots, "avg_launch_ms": skin_ms, "peak_source": peak_src,
-                         "frac_of_nominal_8TBs": achieved / 8000.0,
-                         "note": "static streams are read once per tile and slot run, so real DRAM traffic (`traffic`, "
-                                 "ncu) is far below the algorithmic bytes and `frac` can exceed 1; the write-only floor "
-                                 "is 24 B per vertex-frame",
-                         "output_write_gbs": 24.0 * nv * slots / (skin_ms * 1e-3) / 1e9 if skin_ms > 0 else None,
-                         "dram_gbs_from_traffic": (ncu_traffic_bytes(args.workload, args.layout) / (skin_ms * 1e-3) / 1e9)
-                         if (skin_ms > 0 and ncu_traffic_bytes(args.workload, args.layout) and slots == 128 and world == 1) else None},
-            "kernel_ms_per_step": {"pose_sample": kernel_ms[0] / args.steps, "hierarchy": kernel_ms[1] / args.steps,
-                                   "skin": kernel_ms[2] / args.steps},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        }
-        if gather is not None:
-            out["gather"] = gather
-        if also is not None:
-            out["also"] = also
-        print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        def guarded(name, fn):
+            try:
+                also[name] = fn()
+            except Exception as ex:          # a secondary measurement must not take the headline line down with it
+                also[name] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+                if world > 1:
+                    raise                    # ...but ranks must not diverge inside collectives
+        if "C5" in want and args.workload == "C3" and args.binding == "coherent":
+            guarded("C5", lambda: measure_bake(env, ctx, stream, m, model, replace(cfg, name="C5"), args.bake_frames, BAKE_WINDOW))
+        if "C4" in want and args.workload != "C4":
+            guarded("C4", lambda: measure_crowd(env, ctx, stream, 512, 10, 3))
+        if "C1" in want and args.workload != "C1":
+            guarded("C1", lambda: measure_batch(env, ctx, stream, "C1", 512, model_cache=cache))
+        if "C2" in want and args.workload != "C2":
+            # two CCD IK chains per slot: small batches are bound by the latency of one solve chain, large ones by skinning
+            for n in (128, 256, 512, 2048):
+                guarded(f"C2_{n}", lambda n=n: measure_batch(env, ctx, stream, "C2", n, model_cache=cache))
+        for _, mm, mo in cache.values():
+            mo.close(); mm.close()
+        cache.clear()
+        if "C3_random" in want and args.workload == "C3" and args.binding == "coherent":
+            # stress binding: every vertex picks its bones uniformly from all 1 k bones, so no tile-local palette fits and
+            # the skinning kernel reads matrices from the slot's global palette (L2)
+            guarded("C3_random", lambda: measure_batch(env, ctx, stream, "C3", 64, steps=5, warmup=2, binding="random"))
+
+    if rank != 0:
+        return None
+    skin_ms = kernel_ms[2] / max(1, kernel_n[2])
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.workload == "C4" else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": workload_config(args, cfg, model, slots),
+        "where": "device-resident inputs and outputs (value); host buffers through the C-ABI (e2e)",
+        "roofline": skin_roofline(model, args.layout, slots, spc, skin_ms, args.workload, args.binding),
+        "kernel_ms": {"skin_per_launch_in_step": skin_ms, "isolated": iso,
+                      "note": "sampling and hierarchy of update n+1 overlap the skinning kernel of update n on other streams; "
+                              "their own durations are the isolated ones"},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if also is not None:
+        out["also"] = also
+    return out
 
 
 def main():

@@ -362,6 +362,9 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_download_async(mmdgpu_frames_t frames, ui
  * memory.  Does not wait for compute or for copies of other frames objects: a bake alternating two frames objects
  * hands window k to its sink while window k+1 is being evaluated (simple_mmd_renderer_b200/shard.py BakeDriver). */
 MMDGPU_API mmdgpu_status mmdgpu_frames_wait_downloads(mmdgpu_frames_t frames);
+/* Non-blocking form: 1 if this object's asynchronous downloads have all landed (or none was issued), 0 if one is
+ * still in flight, -1 on a CUDA error. */
+MMDGPU_API int           mmdgpu_frames_downloads_done(mmdgpu_frames_t frames);
 /* Zero-copy hand-off (replaces the CPU repack + sg_update_buffer of main.cpp:820-863): let the skinning kernel write
  * one vertex output stream straight into caller-owned DEVICE memory - e.g. the pointer cudaGraphicsResourceGetMappedPointer
  * returns for sokol's GL vertex buffer (sg_gl_query_buffer_info, 3rd_party/sokol/sokol_gfx.h:5213).
@@ -386,6 +389,19 @@ MMDGPU_API mmdgpu_status mmdgpu_morph_rates_download(mmdgpu_frames_t frames, uin
  * unpinned) material morphs are accumulated in application order during pre_physics_posing / update:
  *   MUL entry: mul = mul * (1 + (value - 1) * rate)      ADD entry: add = add + value * rate. */
 MMDGPU_API mmdgpu_status mmdgpu_material_images_download(mmdgpu_frames_t frames, uint32_t slot, float* host_dst);
+
+/* Slots one skinning work item walks for its tile (the run over which a tile's static streams stay in registers). */
+MMDGPU_API uint32_t      mmdgpu_frames_slot_run(mmdgpu_frames_t frames);
+
+/* Peer buffers: the receive side of the optional bake gather (BASELINE configs[4]).  The root rank creates a
+ * device buffer and gets a 64-byte handle (cudaIpcMemHandle_t) to hand to the other processes of the node by any
+ * means; each of them opens it and binds a window of it with mmdgpu_frames_bind_output, so that its skinning kernel
+ * stores the baked vertices straight into the root's memory over NVLink - compute and gather in one kernel.  Ordering
+ * between producers and the consumer is the caller's (one small collective per window; simple_mmd_renderer_b200/shard.py).
+ * release: opened = 1 for a pointer from _open, 0 for one from _create. */
+MMDGPU_API mmdgpu_status mmdgpu_peer_buffer_create(mmdgpu_context_t ctx, size_t bytes, void** dptr, unsigned char handle[64]);
+MMDGPU_API mmdgpu_status mmdgpu_peer_buffer_open(mmdgpu_context_t ctx, const unsigned char handle[64], void** dptr);
+MMDGPU_API mmdgpu_status mmdgpu_peer_buffer_release(mmdgpu_context_t ctx, void* dptr, int opened);
 
 /* Pinned host memory helpers for the download path. */
 MMDGPU_API mmdgpu_status mmdgpu_host_alloc(size_t bytes, void** out);

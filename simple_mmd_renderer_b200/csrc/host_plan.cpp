@@ -48,6 +48,111 @@ bool bezier_table(const int8_t c[4], float table[32]) {
 }
 
 // --------------------------------------------------------------------------------------------------
+// Second step of the tile order (the first is the stable sort by (skinning type, morph entry count, PMX index)).
+//
+// The skinning kernel scatters a group's 32 results into a shared-memory staging tile at 12 bytes x PMX index, so two
+// lanes of one group whose indices are congruent mod 32 hit the same banks (3 is coprime to 32): a group costs as many
+// wavefronts per store as its most frequent residue.  After the sort a group is an irregular subset of the tile and its
+// residues collide like random numbers (3.2 wavefronts per store on the 1 M-vertex benchmark model, measured with ncu).
+// Hill climbing over swaps of two vertices of the SAME skinning type between groups lowers
+//     cost(group) = 6 x sum over its types (worst residue multiplicity) + 2 x morph rounds (largest entry count)
+// (six stores per vertex and slot against one extra morph round for the group; lanes of different types run in
+// different branches, so they never store together).  Types never mix more than the sort left them.
+template <class TypeOf, class CountOf>
+void refine_tile_order(std::vector<uint32_t>& order, const TypeOf& type_of, const CountOf& count_of) {
+    constexpr uint32_t G = kTileGroups, kTypes = 5;
+    // in units of 1/8 wavefront; the sum of squared multiplicities breaks the plateaus of the worst-multiplicity term
+    constexpr int kWConflict = 48, kWRound = 16, kWSpread = 1;
+    struct Bucket {               // one (group, type): residue histogram and how many residues sit at each multiplicity
+        uint8_t hist[32];
+        uint8_t at[33];
+        uint8_t mx;
+    };
+    struct Group {
+        Bucket b[kTypes];
+        uint32_t top1, n_top1, top2;   // largest entry count, how many members have it, the next smaller count
+    };
+    std::vector<Group> gr(G);
+    std::vector<uint8_t> ty(kTileVerts);
+    std::vector<uint32_t> cnt(kTileVerts);
+    for (uint32_t i = 0; i < kTileVerts; ++i) { ty[i] = uint8_t(std::min<uint32_t>(type_of(i), kTypes - 1)); cnt[i] = count_of(i); }
+    auto rebuild = [&](uint32_t g) {
+        Group& Gp = gr[g];
+        std::memset(&Gp, 0, sizeof Gp);
+        for (uint32_t t = 0; t < kTypes; ++t) Gp.b[t].at[0] = 32;
+        for (uint32_t l = 0; l < 32; ++l) {
+            const uint32_t v = order[g * 32 + l];
+            Bucket& B = Gp.b[ty[v]];
+            const uint8_t h = B.hist[v & 31u]++;
+            B.at[h]--; B.at[h + 1]++;
+            if (h + 1 > B.mx) B.mx = uint8_t(h + 1);
+            const uint32_t c = cnt[v];
+            if (c > Gp.top1) { Gp.top2 = Gp.top1; Gp.top1 = c; Gp.n_top1 = 1; }
+            else if (c == Gp.top1) Gp.n_top1++;
+            else if (c > Gp.top2) Gp.top2 = c;
+        }
+    };
+    for (uint32_t g = 0; g < G; ++g) rebuild(g);
+    // worst multiplicity of a bucket after one vertex with residue `out` leaves and one with residue `in` joins
+    auto mx_after = [](const Bucket& B, uint32_t out, uint32_t in) -> int {
+        if (out == in) return B.mx;
+        const int ho = B.hist[out];
+        int m = (ho == B.mx && B.at[B.mx] == 1) ? B.mx - 1 : B.mx;
+        return std::max(m, int(B.hist[in]) + 1);
+    };
+    auto rounds_after = [](const Group& Gp, uint32_t out, uint32_t in) -> uint32_t {
+        const uint32_t rest = (out == Gp.top1 && Gp.n_top1 == 1) ? Gp.top2 : Gp.top1;
+        return std::max(rest, in);
+    };
+    // rank range of every type (the sort made them contiguous)
+    uint32_t t_begin[kTypes + 1];
+    {
+        uint32_t r = 0;
+        for (uint32_t t = 0; t < kTypes; ++t) {
+            t_begin[t] = r;
+            while (r < kTileVerts && ty[order[r]] == t) ++r;
+        }
+        t_begin[kTypes] = kTileVerts;
+        if (r != kTileVerts) return;   // not type-sorted (cannot happen): leave the order alone
+    }
+    for (int pass = 0; pass < 12; ++pass) {
+        bool improved = false;
+        for (uint32_t ra = 0; ra < kTileVerts; ++ra) {
+            const uint32_t a = order[ra], ga = ra / 32, t = ty[a];
+            const Bucket& A = gr[ga].b[t];
+            if (A.hist[a & 31u] <= 1) continue;                   // collides with nobody
+            int best = 0;
+            uint32_t best_rb = 0;
+            for (uint32_t rb = t_begin[t]; rb < t_begin[t + 1]; ++rb) {
+                const uint32_t gb = rb / 32;
+                if (gb == ga) continue;
+                const uint32_t b = order[rb];
+                const Bucket& B = gr[gb].b[t];
+                const uint32_t ra5 = a & 31u, rb5 = b & 31u;
+                if (ra5 == rb5) continue;
+                // change of the sum of squares: a bucket loses one at `out` and gains one at `in`
+                const int spread = 2 * (int(A.hist[rb5]) - int(A.hist[ra5])) + 2 + 2 * (int(B.hist[ra5]) - int(B.hist[rb5])) + 2;
+                const int d = kWConflict * ((mx_after(A, ra5, rb5) - A.mx) + (mx_after(B, rb5, ra5) - B.mx)) + kWSpread * spread +
+                              kWRound * (int(rounds_after(gr[ga], cnt[a], cnt[b])) - int(gr[ga].top1) +
+                                         int(rounds_after(gr[gb], cnt[b], cnt[a])) - int(gr[gb].top1));
+                if (d < best) { best = d; best_rb = rb; }
+            }
+            if (best < 0) {
+                std::swap(order[ra], order[best_rb]);
+                rebuild(ga);
+                rebuild(best_rb / 32);
+                improved = true;
+            }
+        }
+        if (!improved) break;
+    }
+    // inside a group: by (type, PMX index) again, so that the layout does not depend on the order of the swaps
+    for (uint32_t g = 0; g < G; ++g)
+        std::sort(order.begin() + g * 32, order.begin() + g * 32 + 32, [&](uint32_t x, uint32_t y) {
+            return ty[x] != ty[y] ? ty[x] < ty[y] : x < y;
+        });
+}
+
 mmdgpu_status build_plan(const mmdgpu_model_desc& d, const mmdgpu_options* opt, Plan& p, std::string& err) {
     const uint32_t nv = d.n_vertices, nb = d.n_bones, nm = d.n_morphs;
     p = Plan();
@@ -599,6 +704,7 @@ mmdgpu_status build_plan(const mmdgpu_model_desc& d, const mmdgpu_options* opt, 
                 if (ta != tb) return ta < tb;
                 return count_of(a) < count_of(b);
             });
+            refine_tile_order(order, type_of, count_of);
             // distinct bones of the tile, ascending
             std::vector<uint16_t> used;
             for (uint32_t i = 0; i < kTileVerts && v0 + i < nv; ++i) {

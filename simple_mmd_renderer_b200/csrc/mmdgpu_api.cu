@@ -1315,6 +1315,15 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_wait_downloads(mmdgpu_frames_t f) {
     return MMDGPU_OK;
 }
 
+MMDGPU_API int mmdgpu_frames_downloads_done(mmdgpu_frames_t f) {
+    if (!f || !f->dl_recorded) return 1;
+    if (enter(f->ctx) != MMDGPU_OK) return -1;
+    const cudaError_t e = cudaEventQuery(f->ev_dl);
+    if (e == cudaSuccess) return 1;
+    if (e == cudaErrorNotReady) { cudaGetLastError(); return 0; }
+    return -1;
+}
+
 MMDGPU_API mmdgpu_status mmdgpu_frames_bind_output(mmdgpu_frames_t f, mmdgpu_stream_id id, void* device_ptr, size_t slot_stride_bytes) {
     if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
     mmdgpu_context_t ctx = f->ctx;
@@ -1451,6 +1460,43 @@ MMDGPU_API mmdgpu_status mmdgpu_material_images_download(mmdgpu_frames_t f, uint
     }
     CU(f->ctx, cudaMemcpyAsync(host_dst, f->dev.material_images + size_t(slot) * per, per * 4, cudaMemcpyDeviceToHost, f->ctx->stream));
     CU(f->ctx, cudaStreamSynchronize(f->ctx->stream));
+    return MMDGPU_OK;
+}
+
+MMDGPU_API uint32_t mmdgpu_frames_slot_run(mmdgpu_frames_t f) { return f ? f->slots_per_cta : 0; }
+
+// ---- peer buffers: the receive side of a bake gather that the skinning kernels of other ranks write into directly
+MMDGPU_API mmdgpu_status mmdgpu_peer_buffer_create(mmdgpu_context_t ctx, size_t bytes, void** dptr, unsigned char handle[64]) {
+    if (mmdgpu_status s = enter(ctx)) return s;
+    if (!dptr || !handle) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "NULL argument");
+    *dptr = nullptr;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the C-ABI");
+    void* p = nullptr;
+    CU(ctx, cudaMalloc(&p, bytes ? bytes : 16));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail(ctx, e, "cudaIpcGetMemHandle"); }
+    std::memcpy(handle, &h, 64);
+    *dptr = p;
+    return MMDGPU_OK;
+}
+MMDGPU_API mmdgpu_status mmdgpu_peer_buffer_open(mmdgpu_context_t ctx, const unsigned char handle[64], void** dptr) {
+    if (mmdgpu_status s = enter(ctx)) return s;
+    if (!dptr || !handle) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "NULL argument");
+    *dptr = nullptr;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    // mapped into this context's device; peer access to the exporting device is enabled as part of the call
+    CU(ctx, cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return MMDGPU_OK;
+}
+MMDGPU_API mmdgpu_status mmdgpu_peer_buffer_release(mmdgpu_context_t ctx, void* dptr, int opened) {
+    if (mmdgpu_status s = enter(ctx)) return s;
+    if (!dptr) return MMDGPU_OK;
+    CU(ctx, ctx->sync_pre());
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (opened) CU(ctx, cudaIpcCloseMemHandle(dptr));
+    else CU(ctx, cudaFree(dptr));
     return MMDGPU_OK;
 }
 

@@ -85,12 +85,17 @@ SIGNATURES = {
     "mmdgpu_frames_download": (C.c_int, [_vp, _u32, C.c_int, _vp, _sz]),
     "mmdgpu_frames_download_async": (C.c_int, [_vp, _u32, _u32, C.c_int, _vp, _sz]),
     "mmdgpu_frames_wait_downloads": (C.c_int, [_vp]),
+    "mmdgpu_frames_downloads_done": (C.c_int, [_vp]),
     "mmdgpu_frames_bind_output": (C.c_int, [_vp, C.c_int, _vp, _sz]),
     "mmdgpu_bone_matrices_download": (C.c_int, [_vp, _u32, _vp]),
     "mmdgpu_bone_local_matrices_download": (C.c_int, [_vp, _u32, _vp]),
     "mmdgpu_bone_poses_download": (C.c_int, [_vp, _u32, _vp]),
     "mmdgpu_morph_rates_download": (C.c_int, [_vp, _u32, _vp]),
     "mmdgpu_material_images_download": (C.c_int, [_vp, _u32, _vp]),
+    "mmdgpu_frames_slot_run": (_u32, [_vp]),
+    "mmdgpu_peer_buffer_create": (C.c_int, [_vp, _sz, _PP, _vp]),
+    "mmdgpu_peer_buffer_open": (C.c_int, [_vp, _vp, _PP]),
+    "mmdgpu_peer_buffer_release": (C.c_int, [_vp, _vp, C.c_int]),
     "mmdgpu_host_alloc": (C.c_int, [_sz, _PP]),
     "mmdgpu_host_free": (None, [_vp]),
     "mmdgpu_plan_create": (C.c_int, [_vp, _vp, _PP, C.c_char_p, _sz]),

@@ -253,9 +253,19 @@ class Frames:
         check(self.lib.mmdgpu_frames_download_async(self.h, int(first_slot), int(n_slots), int(stream_id),
                                                     C.c_void_p(pinned_ptr), int(nbytes)), self.ctx.h)
 
+    @property
+    def slots_per_cta(self) -> int:
+        return int(self.lib.mmdgpu_frames_slot_run(self.h))
+
     def wait_downloads(self):
         """Host-blocks until this object's download_async copies have landed (not compute, not other objects)."""
         check(self.lib.mmdgpu_frames_wait_downloads(self.h), self.ctx.h)
+
+    def downloads_done(self) -> bool:
+        r = int(self.lib.mmdgpu_frames_downloads_done(self.h))
+        if r < 0:
+            raise MmdGpuError(capi.ERR_CUDA, "cudaEventQuery failed")
+        return r == 1
 
     def bind_output(self, stream_id: int, device_ptr: int | None, slot_stride_bytes: int = 0):
         """Let the skinning kernel write `stream_id` into caller-owned device memory (None: library buffer again)."""

@@ -114,10 +114,11 @@ def assemble(windows, n_frames_total: int, world: int):
 class BakeDriver:
     """Offline bake of one clip on one GPU (BASELINE configs[4], this rank's frame range): evaluates `window` frames
     per fused update and streams every window's deformed buffers to pinned host memory.  Two frames objects
-    alternate, so the device->host copy of window k overlaps the evaluation of window k+1.
+    alternate: while the host sink consumes window k-1, the device evaluates window k and copies it out.  The driver
+    waits per window (mmdgpu_frames_wait_downloads: that frames object's copies only), never for the whole context.
 
     sink(first_frame, n_frames, positions[n, nv, 3], normals[n, nv, 3]) is called with numpy views of the pinned
-    buffers, valid until the next-but-one window is issued.
+    buffers, valid until it returns.
     """
 
     def __init__(self, model, motion, window: int = 64):
@@ -130,30 +131,82 @@ class BakeDriver:
         nbytes = self.window * model.n_vertices * 12
         self.host = [[torch.empty(max(nbytes, 16), dtype=torch.uint8, pin_memory=True) for _ in range(2)] for _ in range(2)]
         self.nbytes = nbytes
+        self.issued = 0   # windows whose evaluation + copy have been queued (tests look at this from inside the sink)
 
     def run(self, frame_lo: int, frame_hi: int, sink):
-        ctx = self.model.ctx
         nv = self.model.n_vertices
         pending = None  # (buffer index, first frame, n)
-        k = 0
+        self.issued = 0
         for first, n in bake_windows(frame_lo, frame_hi, self.window):
-            b = k & 1
+            b = self.issued & 1
             fr = self.frames[b]
-            fr.update_range(self.motion, [first], 1)           # slots past n hold frames beyond the range: not copied
+            # slots past n hold frames beyond the range: evaluated, not copied.  The skinning kernel of this update waits
+            # on the device for this object's previous copy (window k-2), which the sink has long consumed.
+            fr.update_range(self.motion, [first], 1)
             if n and self.nbytes:
                 for sid, buf in zip((self.capi.STREAM_POSITION, self.capi.STREAM_NORMAL), self.host[b]):
                     fr.download_async(0, n, sid, buf.data_ptr(), n * nv * 12)
+            self.issued += 1
             if pending is not None:
-                self._deliver(pending, sink)                   # window k-1: its copy was issued before window k's work
+                self._deliver(pending, sink)       # window k-1 on the host while window k runs on the device
             pending = (b, first, n)
-            k += 1
         if pending is not None:
             self._deliver(pending, sink)
 
     def _deliver(self, pending, sink):
+        import torch
         b, first, n = pending
-        self.model.ctx.synchronize()
+        self.frames[b].wait_downloads()            # this window's two copies, nothing else
         nv = self.model.n_vertices
-        pos = self.host[b][0][: n * nv * 12].view(dtype=__import__("torch").float32).reshape(n, nv, 3).numpy()
-        nrm = self.host[b][1][: n * nv * 12].view(dtype=__import__("torch").float32).reshape(n, nv, 3).numpy()
+        pos = self.host[b][0][: n * nv * 12].view(dtype=torch.float32).reshape(n, nv, 3).numpy()
+        nrm = self.host[b][1][: n * nv * 12].view(dtype=torch.float32).reshape(n, nv, 3).numpy()
         sink(first, n, pos, nrm)
+
+    def close(self):
+        for fr in self.frames:
+            fr.close()
+
+
+class PeerWindows:
+    """Receive buffer of the fused bake gather: `n_buffers` x `world` windows of (position, normal) planes in rank 0's
+    memory, mapped into every rank (CUDA IPC over NVLink) so that each rank's skinning kernel writes its window straight
+    into its place (mmdgpu_frames_bind_output).  Layout: [buffer][rank][plane][floats_per_plane] float32.
+    The 64-byte handle travels over torch.distributed; ordering of producers and the consumer is the caller's job."""
+
+    def __init__(self, ctx, world: int, rank: int, n_buffers: int, floats_per_plane: int, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from .lib import check
+        self.ctx, self.world, self.rank = ctx, world, rank
+        self.n_buffers, self.fpp = int(n_buffers), int(floats_per_plane)
+        self.total_bytes = self.n_buffers * world * 2 * self.fpp * 4
+        p = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        self.opened = rank != 0
+        if rank == 0:
+            check(ctx.lib.mmdgpu_peer_buffer_create(ctx.h, self.total_bytes, C.byref(p), handle), ctx.h)
+        t = torch.tensor(list(handle), dtype=torch.uint8, device=f"cuda:{ctx.device}")
+        dist.broadcast(t, src=0, group=group)
+        if rank != 0:
+            handle = (C.c_ubyte * 64)(*t.cpu().tolist())
+            check(ctx.lib.mmdgpu_peer_buffer_open(ctx.h, handle, C.byref(p)), ctx.h)
+        self.base = int(p.value)
+
+    def slot(self, buffer: int, rank: int) -> tuple[int, int]:
+        """Device addresses (position plane, normal plane) of `rank`'s window in `buffer`."""
+        off = ((buffer * self.world + rank) * 2) * self.fpp * 4
+        return self.base + off, self.base + off + self.fpp * 4
+
+    def tensor(self, buffer: int, rank: int, plane: int, shape):
+        """torch view of one plane (any rank can look, but only rank 0 reads local memory)."""
+        import torch
+        addr = self.slot(buffer, rank)[plane]
+        return torch.as_tensor(DeviceView(addr, shape), device=f"cuda:{self.ctx.device}")
+
+    def close(self):
+        from .lib import check
+        import ctypes as C
+        if getattr(self, "base", 0):
+            check(self.ctx.lib.mmdgpu_peer_buffer_release(self.ctx.h, C.c_void_p(self.base), 1 if self.opened else 0), self.ctx.h)
+            self.base = 0

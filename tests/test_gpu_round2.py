@@ -1,0 +1,217 @@
+"""GPU tests of the round-2 entry points: clip identity across destroy / create, ordering of skinning against
+asynchronous downloads, caller-owned output buffers (the GL-free half of the zero-copy hand-off),
+per-window waits of the bake driver.  All comparisons are bit-exact against the oracle (libmmd where its harness is built)."""
+import time
+from dataclasses import replace
+
+import numpy as np
+import pytest
+
+from conftest import assert_bitwise, synth_case
+
+pytestmark = pytest.mark.gpu
+
+from simple_mmd_renderer_b200 import capi, synth  # noqa: E402
+from simple_mmd_renderer_b200.poser import Frames, MmdGpuError, Model, Motion  # noqa: E402
+
+
+def _oracle(model, motion):
+    import oracle
+    if oracle.have_reference():
+        return oracle.Reference(model, motion)
+    return oracle.Restatement(model, motion)
+
+
+def test_clip_destroyed_and_another_created_is_not_mistaken_for_the_first(ctx):
+    """destroy(A); create(B) usually hands B the heap block A had: the frames object must still upload B's arrays."""
+    cfg, model, motion_a = synth_case("tiny_full")
+    m = Model(ctx, model)
+    fr = Frames(m, 1, 3)
+    frames = [5, 31, 77]
+    for round_ in range(4):
+        motion = synth.make_motion(cfg, model, instance=round_)     # a different clip every round
+        a = Motion(m, motion)
+        for _ in range(3):                                          # all three rotating state copies see this clip
+            fr.update(a, frames)
+        orc = _oracle(model, motion)
+        for k, f in enumerate(frames):
+            ref = orc.run_frame(f)
+            assert_bitwise(fr.bone_poses(k), ref["poses"], f"round {round_} frame {f} poses")
+            assert_bitwise(fr.download(k, capi.STREAM_POSITION), ref["pos"], f"round {round_} frame {f} positions")
+        a.close()                                                   # mmdgpu_animation_destroy: the next clip reuses the block
+
+
+def test_rejected_update_leaves_the_last_good_result_selected(ctx):
+    cfg, model, motion = synth_case("tiny")
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    fr = Frames(m, 1, 1)
+    fr.update(a, [12])
+    want = fr.download(0, capi.STREAM_POSITION)
+    skin = fr.bone_matrices(0)
+    other = Model(ctx, model)
+    foreign = Motion(other, motion)                                 # bound to a different model handle
+    with pytest.raises(MmdGpuError):
+        fr.update(foreign, [40])
+    assert_bitwise(fr.bone_matrices(0), skin, "skinning matrices after a rejected update")
+    assert_bitwise(fr.download(0, capi.STREAM_POSITION), want, "positions after a rejected update")
+    fr.update(a, [12])
+    assert_bitwise(fr.download(0, capi.STREAM_POSITION), want, "positions after the next good update")
+
+
+def test_update_right_after_download_async_does_not_tear_the_copy(ctx):
+    """One frames object: download of update n is still in flight when update n+1 is issued.  The skinning kernel of
+    n+1 must wait for the copy; what arrives on the host is update n, bit for bit."""
+    import torch
+    cfg, model, motion = synth_case("C1")
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    n = 96
+    fr = Frames(m, 1, n)
+    nv = m.n_vertices
+    host = [torch.empty(n * nv * 12, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    orc = _oracle(model, motion)
+    for first in (0, 100, 200):
+        fr.update_range(a, [first], 1)
+        for sid, buf in zip((capi.STREAM_POSITION, capi.STREAM_NORMAL), host):
+            fr.download_async(0, n, sid, buf.data_ptr(), n * nv * 12)
+        fr.update_range(a, [(first + 150) % 300], 1)       # overwrites the same output planes
+        fr.update_range(a, [(first + 37) % 300], 1)
+        fr.wait_downloads()
+        assert fr.downloads_done()
+        pos = host[0].view(torch.float32).reshape(n, nv, 3).numpy()
+        nrm = host[1].view(torch.float32).reshape(n, nv, 3).numpy()
+        for k in (0, 1, n // 2, n - 1):
+            ref = orc.run_frame(first + k)
+            assert_bitwise(pos[k], ref["pos"], f"window at {first}, slot {k} positions")
+            assert_bitwise(nrm[k], ref["nrm"], f"window at {first}, slot {k} normals")
+    ctx.synchronize()
+
+
+@pytest.mark.parametrize("nv", [3000, 3001, 3002, 3003, 517])
+def test_bound_interleaved_output_is_main_cpp_repack(ctx, nv):
+    """mmdgpu_frames_bind_output(INTERLEAVED): the skinning kernel writes main.cpp:50-54 records straight into a
+    caller-owned device buffer of exactly nv records per slot (what a mapped GL vertex buffer is), nothing beyond it.
+    Compared bit-for-bit with libmmd's Deform + the repack of main.cpp:838-859."""
+    import torch
+    cfg = replace(synth.TINY_FULL, n_vertices=nv, name=f"tiny_full_{nv}")
+    model = synth.make_model(cfg)
+    motion = synth.make_motion(cfg, model)
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    n_slots = 3
+    fr = Frames(m, 1, n_slots, capi.LAYOUT_INTERLEAVED_SOKOL32)
+    stride = nv * 32
+    guard = 4096
+    buf = torch.full((n_slots * stride + guard,), 0xAB, dtype=torch.uint8, device="cuda:0")
+    fr.bind_output(capi.STREAM_INTERLEAVED, buf.data_ptr(), stride)
+    frames = [4, 40, 88]
+    fr.update(a, frames)
+    ctx.synchronize()
+    got = buf.cpu().numpy()
+    assert (got[n_slots * stride:] == 0xAB).all(), "the kernel wrote past the bound buffer"
+    orc = _oracle(model, motion)
+    for k, f in enumerate(frames):
+        orc.run_frame(f)
+        want = orc.repack_sokol32()
+        rec = got[k * stride:(k + 1) * stride].view(np.float32).reshape(nv, 8)
+        assert_bitwise(rec, want, f"nv {nv} frame {f} sokol32 records in the bound buffer")
+    # the download entry points follow the binding
+    assert_bitwise(fr.download(1, capi.STREAM_INTERLEAVED), got[stride:2 * stride].view(np.float32).reshape(nv, 8), "download follows binding")
+    # unbind: the library's own buffer again
+    fr.bind_output(capi.STREAM_INTERLEAVED, None)
+    buf.fill_(0xCD)
+    fr.update(a, frames)
+    ctx.synchronize()
+    assert (buf.cpu().numpy() == 0xCD).all(), "an unbound buffer must not be written"
+    orc.run_frame(frames[2])
+    assert_bitwise(fr.download(2, capi.STREAM_INTERLEAVED), orc.repack_sokol32(), "library buffer after unbinding")
+
+
+@pytest.mark.parametrize("nv", [3000, 3001, 3002, 3003])
+def test_bound_soa_outputs_with_ragged_last_tile(ctx, nv):
+    """POSITION / NORMAL planes bound to caller memory, nv records per slot: the last tile's bulk copy stops at the
+    16-byte boundary below nv * 12 and the remaining floats are stored individually."""
+    import torch
+    cfg = replace(synth.TINY_FULL, n_vertices=nv, name=f"tiny_full_{nv}")
+    model = synth.make_model(cfg)
+    motion = synth.make_motion(cfg, model)
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    n_slots = 5
+    fr = Frames(m, 1, n_slots)
+    stride = (nv * 12 + 15) // 16 * 16
+    guard = 1024
+    pos = torch.full((n_slots * stride + guard,), 0xAB, dtype=torch.uint8, device="cuda:0")
+    nrm = torch.full((n_slots * stride + guard,), 0xAB, dtype=torch.uint8, device="cuda:0")
+    fr.bind_output(capi.STREAM_POSITION, pos.data_ptr(), stride)
+    fr.bind_output(capi.STREAM_NORMAL, nrm.data_ptr(), stride)
+    frames = [0, 9, 33, 61, 89]
+    fr.update(a, frames)
+    ctx.synchronize()
+    gp, gn = pos.cpu().numpy(), nrm.cpu().numpy()
+    orc = _oracle(model, motion)
+    for k, f in enumerate(frames):
+        ref = orc.run_frame(f)
+        assert_bitwise(gp[k * stride:k * stride + nv * 12].view(np.float32).reshape(nv, 3), ref["pos"], f"nv {nv} frame {f} positions")
+        assert_bitwise(gn[k * stride:k * stride + nv * 12].view(np.float32).reshape(nv, 3), ref["nrm"], f"nv {nv} frame {f} normals")
+        assert (gp[k * stride + nv * 12:(k + 1) * stride] == 0xAB).all(), "bytes between slots were written"
+    assert (gp[n_slots * stride:] == 0xAB).all() and (gn[n_slots * stride:] == 0xAB).all()
+    with pytest.raises(MmdGpuError):
+        fr.bind_output(capi.STREAM_POSITION, pos.data_ptr() + 4, stride)      # misaligned
+    with pytest.raises(MmdGpuError):
+        fr.bind_output(capi.STREAM_INTERLEAVED, pos.data_ptr(), stride)       # wrong layout
+
+
+def test_bake_driver_hands_a_window_to_the_sink_while_the_next_one_runs(ctx):
+    """BakeDriver waits per window (mmdgpu_frames_wait_downloads), not for the whole context: when the sink for window
+    k-1 starts, window k has been issued and is normally still running / copying.  Results are checked against the
+    oracle; the overlap through the non-blocking mmdgpu_frames_downloads_done of the OTHER frames object."""
+    from simple_mmd_renderer_b200 import shard
+    cfg, model, motion = synth_case("C1")
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    window = 128
+    drv = shard.BakeDriver(m, a, window)
+    orc = _oracle(model, motion)
+    seen, next_in_flight, order = [], [], []
+
+    def sink(first, n, pos, nrm):
+        k = len(seen)
+        # window k+1 was issued before this call (except after the last one)
+        order.append(drv.issued)
+        other = drv.frames[(k + 1) & 1]
+        next_in_flight.append(not other.downloads_done())
+        ref = orc.run_frame(first + n - 1)
+        assert_bitwise(pos[n - 1], ref["pos"], f"window at {first}: last frame positions")
+        assert_bitwise(nrm[n - 1], ref["nrm"], f"window at {first}: last frame normals")
+        seen.append((first, n))
+    drv.run(10, 10 + 5 * window + 17, sink)
+    assert seen == [(10 + i * window, window) for i in range(5)] + [(10 + 5 * window, 17)]
+    assert order[:-1] == [k + 2 for k in range(len(order) - 1)], "window k+1 must be issued before window k is delivered"
+    # 128 frames x 50 k vertices: 150 MB of copies per window (~3 ms) against microseconds of host work before the check
+    assert any(next_in_flight[:-1]), "every next window had already finished when its predecessor was delivered: no overlap"
+    drv.close()
+
+
+def test_bake_driver_overlaps_a_slow_sink_with_the_device(ctx):
+    """Wall-clock form of the same property: a sink that takes as long as a window takes on the device must cost
+    about max(sink, device) per window, not their sum."""
+    from simple_mmd_renderer_b200 import shard
+    cfg, model, motion = synth_case("C1")
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    drv = shard.BakeDriver(m, a, 128)
+    n_win = 8
+
+    def run(delay):
+        t0 = time.perf_counter()
+        drv.run(0, n_win * 128, lambda *_: time.sleep(delay))
+        ctx.synchronize()
+        return time.perf_counter() - t0
+    run(0.0)
+    base = min(run(0.0) for _ in range(3))          # device-bound: ~ n_win x (evaluate + copy)
+    per = base / n_win
+    slow = min(run(per) for _ in range(3))
+    assert slow < 1.6 * base, f"sink and device ran one after the other: {slow:.4f} s against {base:.4f} s without a sink delay"
+    drv.close()

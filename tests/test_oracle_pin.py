@@ -57,6 +57,20 @@ def test_restatement_matches_libmmd_bitwise(name, frames):
 
 
 @pytest.mark.skipif(not oracle.have_reference(), reason="libmmd reference harness not built (needs /root/reference)")
+@pytest.mark.parametrize("name,frames", [("C1", [0, 7, 150, 299]), ("C2", [0, 7, 33, 150, 299]), ("C3", [3, 144, 167, 357, 399])])
+def test_restatement_matches_libmmd_on_baseline_configs(name, frames):
+    """The BASELINE configs at full size, at every frame tests/test_gpu_parity.py evaluates on them: wherever a GPU test
+    falls back to the restatement, it has been compared with libmmd on exactly that input."""
+    cfg, model, motion = synth_case(name)
+    ref = oracle.Reference(model, motion)
+    port = oracle.Restatement(model, motion)
+    for f in frames:
+        r, p = ref.run_frame(f), port.run_frame(f)
+        for k in ("poses", "rates", "local", "skin", "pos", "nrm"):
+            assert_bitwise(p[k], r[k], f"{name} frame {f} {k}")
+
+
+@pytest.mark.skipif(not oracle.have_reference(), reason="libmmd reference harness not built (needs /root/reference)")
 def test_restatement_manual_posing_matches_libmmd():
     cfg, model, motion = synth_case("tiny_full")
     rng = np.random.default_rng(3)

@@ -199,6 +199,9 @@ def synth_config(workload: str, binding: str = "coherent"):
         cfg = replace(cfg, name="C5")          # the C3 model; the 10 k-frame clip is built by bake_motion()
     if binding != "coherent":
         cfg = replace(cfg, binding=binding, name=f"{cfg.name}_{binding}")
+    if os.environ.get("MMDGPU_BENCH_MORPHS"):      # experiments only: another number of vertex morphs (0 = no morph gather at all)
+        n = int(os.environ["MMDGPU_BENCH_MORPHS"])
+        cfg = replace(cfg, n_vertex_morphs=n, name=f"{cfg.name}_{n}morphs")
     return cfg
 
 

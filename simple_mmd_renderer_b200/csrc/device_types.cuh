@@ -38,6 +38,7 @@ struct DevModel {
     const BoneStatic* bones;
     const IkDesc* iks;
     const IkLink* links;
+    uint32_t ik_nested;      // some solve's link / target has IK itself: solves recurse (kernels.cu)
     const int32_t* reset_bones;
     uint32_t n_reset, n_link_slots, n_morph_slots;
     // program: ops grouped by wave; op word = kind << 28 | arg

@@ -255,13 +255,47 @@ mmdgpu_status build_plan(const mmdgpu_model_desc& d, const mmdgpu_options* opt, 
         ik_of_bone[b] = int32_t(p.iks.size());
         p.iks.push_back(k);
     }
-    for (const IkDesc& k : p.iks) {
-        // libmmd would recurse into a nested solve here (UpdateBoneTransform on a bone that itself has IK).
-        if (p.bones[k.target].flags & kHasIk)
-            return fail(err, MMDGPU_ERR_UNSUPPORTED, "IK target is itself an IK bone (nested solve)");
-        for (int32_t j = 0; j < k.link_count; ++j)
-            if (p.bones[p.links[k.link_begin + j].bone].flags & kHasIk)
-                return fail(err, MMDGPU_ERR_UNSUPPORTED, "IK link is itself an IK bone (nested solve)");
+    // Nested solves: libmmd re-evaluates a solve's links and target with UpdateBoneTransform (poser_impl.inl:203-206, :303),
+    // which re-enters the IK block when that bone has IK itself.  The device runs the same recursion to a fixed depth.
+    // A cycle (an IK bone reached again from its own solve) makes libmmd recurse until the stack overflows: rejected.
+    {
+        const size_t nik = p.iks.size();
+        if (nik > 0xFFFFu) return fail(err, MMDGPU_ERR_UNSUPPORTED, "more than 65535 IK bones");
+        std::vector<std::vector<int32_t>> inner(nik);
+        for (size_t i = 0; i < nik; ++i) {
+            const IkDesc& k = p.iks[i];
+            p.bones[size_t(k.bone)].flags |= uint32_t(i) << 16;      // bits 31:16 of an IK bone's flags: its IkDesc index
+            for (int32_t j = 0; j < k.link_count; ++j) {
+                const int32_t lb = p.links[size_t(k.link_begin + j)].bone;
+                if (p.bones[size_t(lb)].flags & kHasIk) inner[i].push_back(ik_of_bone[size_t(lb)]);
+            }
+            if (p.bones[size_t(k.target)].flags & kHasIk) inner[i].push_back(ik_of_bone[size_t(k.target)]);
+            if (!inner[i].empty()) p.ik_nested = true;
+        }
+        std::vector<int32_t> depth(nik, 0);      // 0 unvisited, -1 on the stack, > 0 levels of solves below and including this one
+        struct Frame { int32_t ik; size_t next; };
+        std::vector<Frame> stack;
+        for (size_t root = 0; root < nik && p.ik_nested; ++root) {
+            if (depth[root] != 0) continue;
+            stack.push_back({int32_t(root), 0});
+            depth[root] = -1;
+            while (!stack.empty()) {
+                Frame& f = stack.back();
+                if (f.next < inner[size_t(f.ik)].size()) {
+                    const int32_t c = inner[size_t(f.ik)][f.next++];
+                    if (depth[size_t(c)] == -1)
+                        return fail(err, MMDGPU_ERR_BAD_INDEX, "IK bones reach each other through their links / targets (libmmd would recurse forever)");
+                    if (depth[size_t(c)] == 0) { depth[size_t(c)] = -1; stack.push_back({c, 0}); }
+                    continue;
+                }
+                int32_t dmax = 0;
+                for (int32_t c : inner[size_t(f.ik)]) dmax = std::max(dmax, depth[size_t(c)]);
+                depth[size_t(f.ik)] = dmax + 1;
+                if (dmax + 1 > kMaxIkDepth)
+                    return fail(err, MMDGPU_ERR_UNSUPPORTED, "IK solves nested deeper than " + std::to_string(kMaxIkDepth) + " levels");
+                stack.pop_back();
+            }
+        }
     }
     for (uint32_t b = 0; b < nb; ++b)
         if (p.bones[b].flags & kIsLink) {
@@ -317,33 +351,34 @@ mmdgpu_status build_plan(const mmdgpu_model_desc& d, const mmdgpu_options* opt, 
             eval_sets(b, R, W);
             emit(kOpEval, b, R, W);
             if (p.bones[b].flags & kHasIk) {
-                const IkDesc& k = p.iks[ik_of_bone[b]];
                 R.clear(); W.clear();
-                R.push_back(var(V_LOCAL, b));
-                // Internal order of the solve (poser_impl.inl:199-206): reset ikR, re-evaluate links root-most
-                // first, then the target.  State an inner step reads after an earlier inner step wrote it is
-                // not an external read; the sets below are the external view.
+                // Internal order of a solve (poser_impl.inl:199-206): reset ikR, re-evaluate links root-most first, then
+                // the target - each followed by its own solve if that bone has IK.  State an inner step reads after an
+                // earlier inner step wrote it is not an external read; the sets below are the external view.
                 std::vector<size_t> wrote;
-                auto add_eval = [&](int32_t x) {
-                    std::vector<size_t> r2, w2;
-                    eval_sets(x, r2, w2);
-                    for (size_t v : r2)
-                        if (std::find(wrote.begin(), wrote.end(), v) == wrote.end()) R.push_back(v);
-                    for (size_t v : w2) { W.push_back(v); wrote.push_back(v); }
-                };
-                for (int32_t j = 0; j < k.link_count; ++j) {
-                    const size_t v = var(V_IK, p.links[k.link_begin + j].bone);
-                    W.push_back(v); wrote.push_back(v);
-                }
-                for (int32_t j = k.link_count - 1; j >= 0; --j) add_eval(p.links[k.link_begin + j].bone);
-                add_eval(k.target);
-                for (int32_t j = 0; j < k.link_count; ++j) {
-                    const BoneStatic& ls = p.bones[p.links[k.link_begin + j].bone];
-                    if (ls.flags & kHasParent) {
-                        const size_t v = var(V_LOCAL, ls.parent);
-                        if (std::find(wrote.begin(), wrote.end(), v) == wrote.end()) R.push_back(v);
+                auto ext_read = [&](size_t v) { if (std::find(wrote.begin(), wrote.end(), v) == wrote.end()) R.push_back(v); };
+                std::function<void(int32_t)> solve_sets = [&](int32_t ki) {
+                    const IkDesc& k = p.iks[size_t(ki)];
+                    ext_read(var(V_LOCAL, k.bone));
+                    auto add_eval = [&](int32_t x) {
+                        std::vector<size_t> r2, w2;
+                        eval_sets(x, r2, w2);
+                        for (size_t v : r2) ext_read(v);
+                        for (size_t v : w2) { W.push_back(v); wrote.push_back(v); }
+                        if (p.bones[size_t(x)].flags & kHasIk) solve_sets(ik_of_bone[size_t(x)]);   // depth bounded above
+                    };
+                    for (int32_t j = 0; j < k.link_count; ++j) {
+                        const size_t v = var(V_IK, p.links[k.link_begin + j].bone);
+                        W.push_back(v); wrote.push_back(v);
                     }
-                }
+                    for (int32_t j = k.link_count - 1; j >= 0; --j) add_eval(p.links[k.link_begin + j].bone);
+                    add_eval(k.target);
+                    for (int32_t j = 0; j < k.link_count; ++j) {
+                        const BoneStatic& ls = p.bones[p.links[k.link_begin + j].bone];
+                        if (ls.flags & kHasParent) ext_read(var(V_LOCAL, ls.parent));
+                    }
+                };
+                solve_sets(ik_of_bone[b]);
                 emit(kOpIk, ik_of_bone[b], R, W);
             }
         }
@@ -511,7 +546,7 @@ mmdgpu_status build_plan(const mmdgpu_model_desc& d, const mmdgpu_options* opt, 
     // ---------------------------------------------------------------- chain-local images of the IK solves
     // (device design: hierarchy_flat_kernel runs a solve on a private copy of just the bones it touches)
     {
-        p.ik_img_ok = !p.iks.empty();
+        p.ik_img_ok = !p.iks.empty() && !p.ik_nested;   // a nested solve touches bones outside its parent's image
         for (const IkDesc& k : p.iks) {
             std::vector<int32_t> bones;                 // image index -> global bone id
             std::vector<uint8_t> written;

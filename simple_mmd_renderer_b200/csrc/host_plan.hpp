@@ -26,7 +26,9 @@ struct BoneStatic {
 };
 enum : uint32_t {
     kHasParent = 1u, kAppendRot = 2u, kAppendTrans = 4u, kIsLink = 8u, kHasIk = 16u, kPostPhysics = 32u
+    // bits 31:16 of an IK bone's flags: index of its IkDesc (nested solves look it up from the bone)
 };
+constexpr int32_t kMaxIkDepth = 3;   // solve inside solve inside solve; deeper nesting is refused at load
 
 struct IkDesc {
     int32_t bone, target, iterations;  // iterations already min(limit, 256) (poser_impl.inl:96)
@@ -91,6 +93,7 @@ struct Plan {
     std::vector<BoneStatic> bones;
     std::vector<int32_t> order_pre, order_post;
     std::vector<IkDesc> iks;
+    bool ik_nested = false;          // some solve's link or target is itself an IK bone (poser_impl.inl:203-206)
     std::vector<IkLink> links;       // in descriptor order (PLAN_IK_* arrays index this)
     std::vector<int32_t> link_bones; // compact list: link_slot -> bone
     std::vector<int32_t> reset_bones;// bones whose tot / local state is read before it is written

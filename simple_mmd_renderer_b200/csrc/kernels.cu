@@ -213,7 +213,7 @@ __device__ __forceinline__ void set_local(const SlotState& S, const BoneStatic& 
 }
 
 // Poser::UpdateBoneTransform(size_t) without the IK part, L/motion/poser_impl.inl:142-166
-__device__ __forceinline__ void eval_bone(const DevModel& M, const SlotState& S, int32_t b) {
+__device__ __forceinline__ void eval_bone(const SlotState& S, int32_t b) {
     const BoneStatic s = load_bone(S.bones, b);
     const Quat R = q_from(S.poseR[b]);
     const float4 T = S.poseT[b];
@@ -248,21 +248,45 @@ __device__ __forceinline__ void eval_bone(const DevModel& M, const SlotState& S,
     S.totT[b] = totT;
     set_local(S, s, b, totR, totT);
 }
+__device__ __forceinline__ void eval_bone(const DevModel&, const SlotState& S, int32_t b) { eval_bone(S, b); }
 
 __device__ __forceinline__ Vec3 local_pos(const SlotState& S, int32_t b) {
     const float4 c = S.local[3 * (size_t)b + 2];
     return Vec3{c.y, c.z, c.w};
 }
 
-// CCD IK, L/motion/poser_impl.inl:168-310 (the part of UpdateBoneTransform after the bone's own transform)
-__device__ __forceinline__ void solve_ik(const DevModel& M, const SlotState& S, const IkDesc k,
-                                         const IkLink* __restrict__ link_table = nullptr) {
-    const IkLink* __restrict__ links = (link_table ? link_table : M.links) + k.link_begin;
+// CCD IK, L/motion/poser_impl.inl:168-310 (the part of UpdateBoneTransform after the bone's own transform).
+//
+// Nested solves: libmmd re-evaluates the links and the target with UpdateBoneTransform itself (:203-206, :303), so a
+// link or target that has IK runs ITS solve at that point - for the target, after every CCD step.  DEPTH counts the
+// levels above this one; the host refuses models nested deeper than kMaxIkDepth.  A nested solve is a real call (one
+// copy of the code per level, cold), the top level stays inlined in the kernels.
+struct IkTables {
+    const IkDesc* iks;
+    const IkLink* links;
+};
+template <int DEPTH>
+__device__ __noinline__ void solve_ik_nested(IkTables T, SlotState S, uint32_t ik_index);
+
+// UpdateBoneTransform(b) as the solver calls it: the bone's own transform, then its solve if it has one
+// NEST = false is the kernel every model without nested solves runs: no call, no extra registers.
+template <int DEPTH, bool NEST>
+__device__ __forceinline__ void eval_bone_and_solve(const IkTables& T, const SlotState& S, int32_t b) {
+    eval_bone(S, b);
+    if (NEST && DEPTH + 1 < kMaxIkDepth) {
+        const uint32_t flags = S.bones[b].flags;
+        if (flags & kHasIk) solve_ik_nested<DEPTH + 1>(T, S, flags >> 16);
+    }
+}
+
+template <int DEPTH, bool NEST>
+__device__ __forceinline__ void solve_ik(const IkTables& T, const SlotState& S, const IkDesc k) {
+    const IkLink* __restrict__ links = T.links + k.link_begin;
     const int nl = k.link_count;
     for (int i = 0; i < nl; ++i) S.ikR[S.bones[links[i].bone].link_slot] = make_float4(0.f, 0.f, 0.f, 1.f);
     const Vec3 ik_pos = local_pos(S, k.bone);
-    for (int i = 0; i < nl; ++i) eval_bone(M, S, links[nl - i - 1].bone);
-    eval_bone(M, S, k.target);
+    for (int i = 0; i < nl; ++i) eval_bone_and_solve<DEPTH, NEST>(T, S, links[nl - i - 1].bone);
+    eval_bone_and_solve<DEPTH, NEST>(T, S, k.target);
     Vec3 tp = local_pos(S, k.target);
     Vec3 err{ik_pos.x - tp.x, ik_pos.y - tp.y, ik_pos.z - tp.z};
     if ((double)v_dot(err, err) < kEpsD) return;
@@ -316,12 +340,17 @@ __device__ __forceinline__ void solve_ik(const DevModel& M, const SlotState& S, 
                 S.totR[cb] = q_to4(tot);
                 set_local(S, cs, cb, tot, S.totT[cb]);
             }
-            eval_bone(M, S, k.target);
+            eval_bone_and_solve<DEPTH, NEST>(T, S, k.target);
             tp = local_pos(S, k.target);
         }
         err = Vec3{ik_pos.x - tp.x, ik_pos.y - tp.y, ik_pos.z - tp.z};
         if (v_dot(err, err) < kEpsF) return;
     }
+}
+
+template <int DEPTH>
+__device__ __noinline__ void solve_ik_nested(IkTables T, SlotState S, uint32_t ik_index) {
+    if (DEPTH < kMaxIkDepth) solve_ik<(DEPTH < kMaxIkDepth ? DEPTH : kMaxIkDepth - 1), true>(T, S, T.iks[ik_index]);
 }
 
 // Poser::UpdateBoneSkinningMatrix, L/motion/poser_impl.inl:320-326: skin = global_offset * local, stored as
@@ -479,7 +508,7 @@ __global__ void __launch_bounds__(kFlatThreads) hierarchy_flat_kernel(DevModel M
     const int32_t* __restrict__ gm = M.ik_img_mslots + I.mslots_begin;
     for (uint32_t i = 0; i < Ms; ++i) { const int32_t x = __ldg(gm + i); morphR[i] = G.morphR[x]; morphT[i] = G.morphT[x]; }
 
-    solve_ik(M, S, M.ik_img_desc[arg], M.ik_img_links);
+    solve_ik<0, false>(IkTables{M.ik_img_desc, M.ik_img_links}, S, M.ik_img_desc[arg]);
 
     const uint8_t* __restrict__ wr = M.ik_img_written + I.bones_begin;
     for (uint32_t i = 0; i < W; ++i) {
@@ -494,6 +523,7 @@ __global__ void __launch_bounds__(kFlatThreads) hierarchy_flat_kernel(DevModel M
     for (uint32_t i = 0; i < L; ++i) { const int32_t x = __ldg(gl + i); G.ikR[x] = ikR[i]; G.preIK[x] = preIK[i]; }
 }
 
+template <bool NEST>
 __global__ void __launch_bounds__(32 * kHierWarps) hierarchy_kernel(DevModel M, DevFrames F, uint32_t wave_lo,
                                                                     uint32_t wave_hi, uint32_t prologue) {
     const uint32_t lane = threadIdx.x & 31u;
@@ -569,7 +599,7 @@ __global__ void __launch_bounds__(32 * kHierWarps) hierarchy_kernel(DevModel M, 
             const uint32_t kind = word >> 28;
             const int32_t arg = (int32_t)(word & 0x0FFFFFFFu);
             if (kind == kOpEval) eval_bone(M, S, arg);
-            else if (kind == kOpIk) solve_ik(M, S, M.iks[arg]);
+            else if (kind == kOpIk) solve_ik<0, NEST>(IkTables{M.iks, M.links}, S, M.iks[arg]);
             else skin_bone(M, S, arg);
         }
         __syncwarp();
@@ -592,6 +622,7 @@ __host__ __device__ inline size_t hier_cta_smem_bytes(uint32_t nb, uint32_t n_li
            (((size_t)n_ops + n_waves + 1 + 3) & ~(size_t)3) * sizeof(uint32_t);
 }
 
+template <bool NEST>
 __global__ void __launch_bounds__(kHierCtaThreads) hierarchy_cta_kernel(DevModel M, DevFrames F, uint32_t wave_lo,
                                                                         uint32_t wave_hi, uint32_t prologue) {
     extern __shared__ __align__(16) float4 hsm[];
@@ -717,7 +748,7 @@ __global__ void __launch_bounds__(kHierCtaThreads) hierarchy_cta_kernel(DevModel
             const uint32_t kind = word >> 28;
             const int32_t arg = (int32_t)(word & 0x0FFFFFFFu);
             if (kind == kOpEval) eval_bone(M, S, arg);
-            else if (kind == kOpIk) solve_ik(M, S, M.iks[arg]);
+            else if (kind == kOpIk) solve_ik<0, NEST>(IkTables{M.iks, M.links}, S, M.iks[arg]);
             else skin_bone(M, S, arg);
         }
         __syncthreads();
@@ -1255,11 +1286,13 @@ cudaError_t launch_hierarchy(cudaStream_t st, const DevModel& M, const DevFrames
     if (cta_smem <= kHierCtaSmemLimit && !force_global) {
         // small skeletons: narrower CTAs, so that more slots are resident per SM (a CCD IK solve is one thread)
         const uint32_t threads = M.nb <= 512 ? 128u : kHierCtaThreads;
-        hierarchy_cta_kernel<<<F.n_slots, threads, cta_smem, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u);
+        if (M.ik_nested) hierarchy_cta_kernel<true><<<F.n_slots, threads, cta_smem, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u);
+        else hierarchy_cta_kernel<false><<<F.n_slots, threads, cta_smem, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u);
         return cudaGetLastError();
     }
     const uint32_t blocks = (F.n_slots + kHierWarps - 1) / kHierWarps;
-    hierarchy_kernel<<<blocks, 32 * kHierWarps, 0, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u);
+    if (M.ik_nested) hierarchy_kernel<true><<<blocks, 32 * kHierWarps, 0, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u);
+    else hierarchy_kernel<false><<<blocks, 32 * kHierWarps, 0, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u);
     return cudaGetLastError();
 }
 
@@ -1298,7 +1331,8 @@ cudaError_t prepare_skin_kernels(const DevModel& M) {
     if (e != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
     const int hier = limit < (int)kHierCtaSmemLimit ? limit : (int)kHierCtaSmemLimit;
-    if ((e = cudaFuncSetAttribute(hierarchy_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hier)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(hierarchy_cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, hier)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(hierarchy_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, hier)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(hierarchy_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hier)) != cudaSuccess) return e;
     constexpr int SOA = MMDGPU_LAYOUT_SOA_POS_NRM, I32 = MMDGPU_LAYOUT_INTERLEAVED_SOKOL32;
     if ((e = skin_opt_in<SOA, true, false>(limit)) != cudaSuccess) return e;

@@ -317,6 +317,7 @@ mmdgpu_status upload_model(mmdgpu_model* m) {
     CU(ctx, upload(ctx, m->mem, p.bones, &D.bones));
     CU(ctx, upload(ctx, m->mem, p.iks, &D.iks));
     CU(ctx, upload(ctx, m->mem, p.links, &D.links));
+    D.ik_nested = p.ik_nested ? 1u : 0u;
     CU(ctx, upload(ctx, m->mem, p.reset_bones, &D.reset_bones));
     D.n_reset = uint32_t(p.reset_bones.size());
     D.n_link_slots = uint32_t(p.link_bones.size());

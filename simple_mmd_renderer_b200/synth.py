@@ -520,3 +520,47 @@ def make_ik_zoo(seed: int = 77, n_frames: int = 40, chains=None):
         morph_track_key_count=np.zeros(0, np.uint32), n_morph_keys=0, morph_keys=np.zeros(0, capi.MORPH_KEY),
     )
     return model, motion
+
+
+def make_ik_nested(seed: int = 78, n_frames: int = 40):
+    """A rig whose CCD IK solves nest: libmmd re-evaluates a solve's links and target with UpdateBoneTransform
+    (L/motion/poser_impl.inl:203-206, :303), which re-enters the IK block when that bone has IK itself.
+      * chain 0's TARGET is an IK bone (its own solve runs after every CCD step of the outer one),
+      * chain 2's middle LINK is an IK bone (its solve runs once, when the outer solve first re-evaluates its links),
+      * chain 4 -> its target -> that solve's target: three levels.
+    Built from make_ik_zoo's chains by moving the IK record of a helper chain onto a link / target of another one."""
+    PI = float(np.pi)
+    chains = [
+        (2, 12, 1.5, [((-PI, 0, 0), (-0.0087, 0, 0)), None], False),                     # 0: outer, target gets chain 1's solve
+        (1, 6, 2.0, [None], False),                                                     # 1: helper
+        (3, 9, 0.8, [None, ((-0.5, -0.5, -0.5), (0.5, 0.5, 0.5)), None], False),         # 2: outer, middle link gets chain 3's solve
+        (2, 5, 1.0, [((0, -1.0, 0), (0, 1.2, 0)), None], False),                         # 3: helper
+        (2, 8, 1.2, [None, None], False),                                               # 4: outer (level 1)
+        (1, 4, 2.5, [((-2.0, -1.0, -3.0), (2.0, 1.0, 3.0))], False),                     # 5: helper (level 2), moved onto 4's target
+        (2, 3, 0.7, [None, None], False),                                               # 6: helper (level 3), moved onto 5's target
+    ]
+    model, motion = make_ik_zoo(seed=seed, n_frames=n_frames, chains=chains)
+    # bone indices by construction order: per chain its links (root-most first), its target, its IK bone
+    first, layout = 1, []
+    for spec in chains:
+        nl = spec[0]
+        layout.append(dict(links=list(range(first, first + nl)), target=first + nl, ik=first + nl + 1))
+        first += nl + 2
+    flags = model["bone_flags"].copy()
+
+    def move_ik(src_chain: int, dst_bone: int):
+        src = layout[src_chain]["ik"]
+        for k in ("ik_target", "ik_iterations", "ik_angle_limit", "ik_link_begin", "ik_link_count"):
+            a = model[k].copy()
+            a[dst_bone] = a[src]
+            a[src] = -1 if k == "ik_target" else 0
+            model[k] = a
+        flags[dst_bone] |= capi.BONE_HAS_IK
+        flags[src] &= ~np.uint16(capi.BONE_HAS_IK)
+
+    move_ik(1, layout[0]["target"])
+    move_ik(3, layout[2]["links"][1])
+    move_ik(5, layout[4]["target"])
+    move_ik(6, layout[5]["target"])
+    model["bone_flags"] = flags
+    return model, motion

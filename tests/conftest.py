@@ -53,6 +53,10 @@ def synth_case(name: str):
             model, motion = synth.make_ik_zoo()
             _cache[name] = (None, model, motion)
             return _cache[name]
+        if name == "ik_nested":         # solves whose links / targets have IK themselves
+            model, motion = synth.make_ik_nested()
+            _cache[name] = (None, model, motion)
+            return _cache[name]
         cfg = synth.CONFIGS[name]
         model = synth.make_model(cfg)
         motion = synth.make_motion(cfg, model)

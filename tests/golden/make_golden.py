@@ -23,6 +23,7 @@ CASES = {
     "tiny_full": [0, 1, 2, 7, 17, 30, 42, 45, 63, 88, 89, 90, 500],
     "small": [0, 59, 119],
     "ik_zoo": list(range(0, 41, 3)),     # synth.make_ik_zoo(): every CCD IK branch
+    "ik_nested": list(range(0, 41, 4)),  # synth.make_ik_nested(): solves inside solves (poser_impl.inl:203-206, :303)
 }
 STRIDE = 53
 TIMES = [0.0, 1.0 / 30.0, 0.0123, 0.5, 0.7777, 1.99, 2.5, 17.0]   # seconds, MotionPlayer::SeekTime
@@ -50,6 +51,8 @@ def main():
     for name, frames in CASES.items():
         if name == "ik_zoo":
             model, motion = synth.make_ik_zoo()
+        elif name == "ik_nested":
+            model, motion = synth.make_ik_nested()
         else:
             cfg = synth.CONFIGS[name]
             model = synth.make_model(cfg)

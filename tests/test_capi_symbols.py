@@ -109,6 +109,66 @@ def test_group_morph_cycle_is_rejected():
     assert e.value.status == capi.ERR_BAD_INDEX
 
 
+def test_deep_group_morph_chain_is_refused_not_overflowed():
+    """A crafted chain of nested group morphs (each holding the next) must come back as a status, not as a host stack
+    overflow: the expansion is iterative and capped at 64 levels (libmmd itself recurses once per level)."""
+    cfg, model, _ = synth_case("tiny")
+
+    def chain(n):
+        m = dict(model)
+        base = int(model["n_morphs"])
+        m["n_morphs"] = base + n
+        m["morph_type"] = np.concatenate([model["morph_type"], np.full(n, capi.MORPH_GROUP, np.uint8)])
+        ge = np.zeros(n, capi.GROUP_MORPH_ENTRY)
+        ge["morph"] = np.concatenate([base + 1 + np.arange(n - 1), [0]]).astype(np.uint32)   # i -> i + 1 ... -> morph 0
+        ge["rate"] = 1.0
+        m["group_morph_entries"], m["n_group_morph_entries"] = ge, n
+        m["morph_entry_begin"] = np.concatenate([model["morph_entry_begin"], np.arange(n, dtype=np.uint32)])
+        m["morph_entry_count"] = np.concatenate([model["morph_entry_count"], np.ones(n, np.uint32)])
+        return m
+    plan = plan_arrays(chain(40))                         # legal depth
+    assert plan[capi.PLAN_APP_SLOT_MORPH].size > 40
+    with pytest.raises(MmdGpuError) as e:
+        plan_arrays(chain(300_000))
+    assert e.value.status == capi.ERR_UNSUPPORTED
+
+
+def test_ik_solves_that_reach_each_other_are_refused():
+    """An IK bone that is (transitively) a link or target of its own solve makes libmmd recurse forever
+    (poser_impl.inl:203-206); nesting deeper than three levels is refused as unsupported."""
+    from simple_mmd_renderer_b200 import synth
+    model, _ = synth.make_ik_nested()
+    plan_arrays(model)                                    # three levels: accepted
+    ikb = np.flatnonzero(model["bone_flags"] & capi.BONE_HAS_IK)
+    bad = dict(model)
+    tgt = model["ik_target"].copy()
+    tgt[ikb[0]] = ikb[0]                                  # its own target
+    bad["ik_target"] = tgt
+    with pytest.raises(MmdGpuError) as e:
+        plan_arrays(bad)
+    assert e.value.status == capi.ERR_BAD_INDEX
+    # a fourth level: the innermost solve's target becomes an IK bone as well
+    depth = {}
+
+    def levels(b):
+        lb, lc = int(model["ik_link_begin"][b]), int(model["ik_link_count"][b])
+        kids = [int(x) for x in model["ik_link_bone"][lb:lb + lc]] + [int(model["ik_target"][b])]
+        return 1 + max([levels(k) for k in kids if model["bone_flags"][k] & capi.BONE_HAS_IK] or [0])
+    outer = [int(b) for b in ikb if levels(int(b)) == 3][0]
+    inner = int(model["ik_target"][int(model["ik_target"][outer])])       # level 3 solve sits on this bone
+    assert model["bone_flags"][inner] & capi.BONE_HAS_IK
+    deep = dict(model)
+    fl = model["bone_flags"].copy()
+    leaf_target = int(model["ik_target"][inner])
+    fl[leaf_target] |= capi.BONE_HAS_IK
+    deep["bone_flags"] = fl
+    for k, v in (("ik_target", 0), ("ik_iterations", 2), ("ik_angle_limit", 1.0), ("ik_link_begin", 0), ("ik_link_count", 0)):
+        a = model[k].copy(); a[leaf_target] = v; deep[k] = a
+    with pytest.raises(MmdGpuError) as e:
+        plan_arrays(deep)
+    assert e.value.status == capi.ERR_UNSUPPORTED
+
+
 def test_bezier_table_linear_and_endpoints():
     assert bezier_table([20, 20, 107, 107]) is None          # c0.x == c0.y and c1.x == c1.y -> linear
     t = bezier_table([10, 90, 100, 30])

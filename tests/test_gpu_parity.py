@@ -255,7 +255,7 @@ def test_every_ccd_ik_branch(ctx):
         _check_frame(fr, k, orc.run_frame(f), f"ik_zoo frame {f}")
 
 
-@pytest.mark.parametrize("name", ["tiny", "tiny_full", "small", "ik_zoo"])
+@pytest.mark.parametrize("name", ["tiny", "tiny_full", "small", "ik_zoo", "ik_nested"])
 def test_gpu_matches_libmmd_golden_fixtures(ctx, name):
     """The committed libmmd-generated fixtures (tests/golden), independent of the C restatement."""
     from golden_util import check_against_golden, load_golden

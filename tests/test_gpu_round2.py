@@ -215,3 +215,31 @@ def test_bake_driver_overlaps_a_slow_sink_with_the_device(ctx):
     slow = min(run(per) for _ in range(3))
     assert slow < 1.6 * base, f"sink and device ran one after the other: {slow:.4f} s against {base:.4f} s without a sink delay"
     drv.close()
+
+
+@pytest.mark.parametrize("n_slots", [1, 45, 300])
+def test_nested_ik_solves(ctx, n_slots):
+    """synth.make_ik_nested(): an IK bone as the target of another solve (its solve runs after every CCD step of the
+    outer one), an IK bone as a link (its solve runs when the outer solve first re-evaluates its links) and three levels
+    deep — libmmd's recursion through UpdateBoneTransform (poser_impl.inl:203-206, :303).  Fused and step-wise, small
+    and large batches (the large one would take the chain-local-image kernel, which nested models must not)."""
+    _, model, motion = synth_case("ik_nested")
+    orc = _oracle(model, motion)
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    frames = [(7 * k) % 45 for k in range(n_slots)]
+    fr = Frames(m, 1, n_slots)
+    fr.update(a, frames)
+    for k in sorted(set([0, n_slots // 2, n_slots - 1] + list(range(min(n_slots, 45))))):
+        ref = orc.run_frame(frames[k])
+        assert_bitwise(fr.bone_local_matrices(k), ref["local"], f"slot {k} frame {frames[k]} local matrices")
+        assert_bitwise(fr.bone_matrices(k), ref["skin"], f"slot {k} frame {frames[k]} skinning matrices")
+        assert_bitwise(fr.download(k, capi.STREAM_POSITION), ref["pos"], f"slot {k} frame {frames[k]} positions")
+        assert_bitwise(fr.download(k, capi.STREAM_NORMAL), ref["nrm"], f"slot {k} frame {frames[k]} normals")
+    # libmmd's call sequence, one frame at a time
+    one = Frames(m, 1, 1)
+    for f in (3, 22, 40):
+        one.reset_posing(); one.seek_frame(a, [f]); one.pre_physics_posing(); one.post_physics_posing(); one.deform()
+        ref = orc.run_frame(f)
+        assert_bitwise(one.bone_matrices(0), ref["skin"], f"step-wise frame {f} skinning matrices")
+        assert_bitwise(one.download(0, capi.STREAM_POSITION), ref["pos"], f"step-wise frame {f} positions")

@@ -8,7 +8,7 @@ import oracle
 from conftest import assert_bitwise, synth_case
 from golden_util import check_against_golden, input_digest, load_golden, sha
 
-CASES = ["tiny", "tiny_full", "small", "ik_zoo"]
+CASES = ["tiny", "tiny_full", "small", "ik_zoo", "ik_nested"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -42,7 +42,7 @@ def test_restatement_matches_golden(name):
 
 @pytest.mark.skipif(not oracle.have_reference(), reason="libmmd reference harness not built (needs /root/reference)")
 @pytest.mark.parametrize("name,frames", [("tiny", range(0, 70, 3)), ("tiny_full", range(0, 100)), ("small", [0, 7, 60, 119]),
-                                         ("ik_zoo", range(0, 45))])
+                                         ("ik_zoo", range(0, 45)), ("ik_nested", range(0, 45))])
 def test_restatement_matches_libmmd_bitwise(name, frames):
     cfg, model, motion = synth_case(name)
     ref = oracle.Reference(model, motion)

@@ -147,24 +147,33 @@ def _op_sets(model, kind, b):
         return eval_sets(b)
     if kind == 2:
         return [("local", b)], [("skin", b)]
-    lb, lc = int(model["ik_link_begin"][b]), int(model["ik_link_count"][b])
-    links = [int(x) for x in model["ik_link_bone"][lb:lb + lc]]
-    R, W = [("local", b)], []
+    R, W = [], []
     wrote = set()
-    for l in links:
-        W.append(("ik", l)); wrote.add(("ik", l))
-    for x in list(reversed(links)) + [int(model["ik_target"][b])]:
-        r2, w2 = eval_sets(x)
-        R += [v for v in r2 if v not in wrote]
-        W += w2
-        wrote.update(w2)
-    for l in links:
-        if 0 <= parent[l] < nb and ("local", int(parent[l])) not in wrote:
-            R.append(("local", int(parent[l])))
+
+    def solve(ikb):
+        """The IK block of UpdateBoneTransform(ikb); links and target are re-evaluated with UpdateBoneTransform itself
+        (poser_impl.inl:203-206), so one that has IK runs its own solve right there."""
+        lb, lc = int(model["ik_link_begin"][ikb]), int(model["ik_link_count"][ikb])
+        links = [int(x) for x in model["ik_link_bone"][lb:lb + lc]]
+        if ("local", ikb) not in wrote:
+            R.append(("local", ikb))
+        for l in links:
+            W.append(("ik", l)); wrote.add(("ik", l))
+        for x in list(reversed(links)) + [int(model["ik_target"][ikb])]:
+            r2, w2 = eval_sets(x)
+            R.extend(v for v in r2 if v not in wrote)
+            W.extend(w2)
+            wrote.update(w2)
+            if flags[x] & capi.BONE_HAS_IK:
+                solve(x)
+        for l in links:
+            if 0 <= parent[l] < nb and ("local", int(parent[l])) not in wrote:
+                R.append(("local", int(parent[l])))
+    solve(b)
     return R, W
 
 
-@pytest.mark.parametrize("name", ["tiny", "tiny_full", "small", "C2", "ik_zoo"])
+@pytest.mark.parametrize("name", ["tiny", "tiny_full", "small", "C2", "ik_zoo", "ik_nested"])
 def test_wave_schedule_preserves_sequential_semantics(name):
     """Every op must observe, in the wave program, exactly the writers it observes in libmmd's sequential program,
     and ops that share a wave must not touch each other's state."""

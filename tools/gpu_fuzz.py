@@ -13,7 +13,7 @@ with the CPU oracle (positions, normals, bone matrices, sampled poses, morph rat
                 bytes, both quaternion hemispheres) sampled by SeekFrame and SeekTime, incl. far past the clip
   phase "crowd": instances x frames with per-instance clips, range mode with a stride and per-slot frame ids
   phase "ext":   extensions = 1: non-extension vertices bit-exact, SDEF / QDEF / UV / material images vs the fp64 restatement
-usage: python tools/gpu_fuzz.py [first_seed] [count] [rig|ik|topo|morph|motion|crowd|ext|all]"""
+usage: python tools/gpu_fuzz.py [first_seed] [count] [rig|ik|topo|nest|morph|motion|crowd|ext|all]"""
 import os, sys
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
@@ -21,7 +21,7 @@ from dataclasses import replace
 import numpy as np
 import oracle
 from simple_mmd_renderer_b200 import capi, synth
-from simple_mmd_renderer_b200.poser import Context, Frames, Model, Motion
+from simple_mmd_renderer_b200.poser import Context, Frames, MmdGpuError, Model, Motion
 
 ctx = None   # created by main()
 
@@ -134,8 +134,8 @@ def ik_case(seed):
 TOPO_MASK = int(os.environ.get("TOPO_MASK", "31"))   # 1 parents, 2 levels, 4 appends, 8 post-physics, 16 IK
 
 
-def topo_case_inputs(seed):
-    rng = np.random.default_rng(9000 + seed)
+def topo_case_inputs(seed, nest=False):
+    rng = np.random.default_rng((19000 if nest else 9000) + seed)
     cfg = replace(synth.TINY_FULL, name=f"topo{seed}", config_id=400 + seed, n_bones=int(rng.integers(8, 60)),
                   n_vertices=int(rng.integers(50, 1500)), ik_chains=0, n_frames=20, stress=bool(rng.integers(0, 2)),
                   n_bone_morphs=int(rng.integers(0, 3)), n_group_morphs=0, n_uv_morphs=0, n_vertex_morphs=int(rng.integers(0, 6)))
@@ -154,7 +154,7 @@ def topo_case_inputs(seed):
             ratio[b] = float(rng.choice([0.5, 1.0, -0.5, 0.25, 2.0]))
         if rng.random() < 0.1 and (TOPO_MASK & 8):
             flags[b] |= capi.BONE_POST_PHYSICS
-    n_ik = int(rng.integers(0, 4)) if (TOPO_MASK & 16) else 0
+    n_ik = (int(rng.integers(2, 6)) if nest else int(rng.integers(0, 4))) if (TOPO_MASK & 16) else 0
     ik_target = np.full(nb, -1, np.int32); ik_iter = np.zeros(nb, np.int32); ik_angle = np.zeros(nb, np.float32)
     ik_begin = np.zeros(nb, np.uint32); ik_count = np.zeros(nb, np.uint32)
     l_bone, l_has, l_lo, l_hi = [], [], [], []
@@ -162,7 +162,8 @@ def topo_case_inputs(seed):
     others = [b for b in range(nb) if b not in ik_bones]
     for ikb in ik_bones:
         if len(others) < 3: break
-        pick = [int(x) for x in rng.choice(others, min(len(others), int(rng.integers(2, 6))), replace=False)]
+        pool = [b for b in range(nb) if b != ikb] if nest else others      # nest: links / targets may be IK bones themselves
+        pick = [int(x) for x in rng.choice(pool, min(len(pool), int(rng.integers(2, 6))), replace=False)]
         tgt, links = pick[0], pick[1:]
         flags[ikb] |= capi.BONE_HAS_IK
         ik_target[ikb] = tgt; ik_iter[ikb] = int(rng.choice([1, 3, 8, 20])); ik_angle[ikb] = float(rng.choice([0.3, 1.0, 2.0]))
@@ -185,10 +186,16 @@ def topo_case_inputs(seed):
     return model, motion, frames
 
 
-def topo_case(seed):
-    model, motion, frames = topo_case_inputs(seed)
+def topo_case(seed, nest=False):
+    model, motion, frames = topo_case_inputs(seed, nest)
+    try:
+        m = Model(ctx, model)
+    except MmdGpuError as e:
+        # solves that reach each other (libmmd recurses forever: the oracle must not be run) or nest deeper than 3 levels
+        if nest and e.status in (capi.ERR_BAD_INDEX, capi.ERR_UNSUPPORTED):
+            return True, f"nested topology seed {seed}: refused ({e.message})"
+        raise
     orc = oracle.Restatement(model, motion)
-    m = Model(ctx, model)
     a = Motion(m, motion)
     fr = Frames(m, 1, len(frames))
     fr.update(a, frames)
@@ -196,7 +203,12 @@ def topo_case(seed):
     for k, f in enumerate(frames):
         ok &= check_slot(fr, k, orc.run_frame(f))
     fr.close(); orc.close()
-    return ok, f"topology seed {seed}"
+    return ok, f"{'nested ' if nest else ''}topology seed {seed}"
+
+
+def nest_case(seed):
+    """Topology phase with IK bones allowed as links / targets of other solves (poser_impl.inl:203-206, :303)."""
+    return topo_case(seed, nest=True)
 
 
 def morph_case_inputs(seed):
@@ -454,7 +466,7 @@ def main():
     phase = sys.argv[3] if len(sys.argv) > 3 else "all"
     ctx = Context(0)
     bad = 0
-    for name, fn in (("rig", rig_case), ("ik", ik_case), ("topo", topo_case), ("morph", morph_case), ("motion", motion_case), ("crowd", crowd_case), ("ext", ext_case)):
+    for name, fn in (("rig", rig_case), ("ik", ik_case), ("topo", topo_case), ("nest", nest_case), ("morph", morph_case), ("motion", motion_case), ("crowd", crowd_case), ("ext", ext_case)):
         if phase not in (name, "all"):
             continue
         n_bad = 0

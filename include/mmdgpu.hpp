@@ -31,10 +31,16 @@ public:
     mmdgpu_status status;
 };
 
-// Same member spelling as mmd::Vector3f where main.cpp reads it (pos.p.x, main.cpp:843-855).
+// Element type of Poser::pose_image.  In a translation unit that has libmmd's headers (main.cpp keeps them for mmd::Model)
+// it IS mmd::Vector3f, so that `const mmd::Vector3f& pos = poser->pose_image.coordinates[i];` (main.cpp:843-844)
+// compiles unchanged; elsewhere a 12-byte struct with the member spelling main.cpp reads (pos.p.x, main.cpp:848-854).
+#ifdef __MMD_H_7F46DEA0A2C1F5902D557E3545B096B5_INCLUDED__
+using Vector3f = mmd::Vector3f;
+#else
 struct Vector3f {
     struct { float x, y, z; } p;
 };
+#endif
 static_assert(sizeof(Vector3f) == 12, "Vector3f must be three packed floats");
 
 class Context {

@@ -797,6 +797,13 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// 16-byte asynchronous copy global -> shared (LDGSTS): no register holds the data while it is in flight
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 struct Col3 { float4 c0, c1, c2; };  // skinning matrix as three columns (M0c, M1c, M2c, M3c)
 
 template <int PS>  // PS = float4 per staged bone: 3 (matrix columns) or 5 (+ rotation quaternion, dual part)
@@ -979,6 +986,13 @@ __host__ __device__ inline uint32_t skin_stage_bytes(int layout, bool ext) {
 }
 __host__ __device__ inline uint32_t skin_pal_bytes(uint32_t max_tile_bones, bool ext) { return max_tile_bones * (ext ? 80u : 48u); }
 
+// Morph entries of a thread's NEXT storage position travel global -> shared memory (cp.async) while it skins the
+// current one: the sliced-ELL rows come from L2 (a tile's 37 KB of entries are re-read for every slot group and three
+// CTAs' worth does not fit L1), and with 12 warps per SM nothing else hides that latency.  Ring = one step deep,
+// kRingRounds entries per thread; rows longer than that read the rest straight from global memory.
+constexpr uint32_t kRingRounds = 6;
+__host__ __device__ inline uint32_t skin_ring_bytes() { return kRingRounds * kSkinThreads * 16u; }
+
 constexpr uint32_t kPalPrefetch = 2;  // palette float4 per thread held in registers across the compute phase
 constexpr int V = (int)kVertsPerThread;
 constexpr int G = (int)kSlotGroup;    // slots one CTA evaluates together
@@ -988,7 +1002,7 @@ constexpr int G = (int)kSlotGroup;    // slots one CTA evaluates together
 // slots skinned per skin_vertex_n call: 2 measured best (1: -3.4 %, 4: spills, -11 %; profiles/r01_experiments.md)
 constexpr int kSkinCallSlots = 2;
 static_assert(kSlotGroup % kSkinCallSlots == 0, "a slot group is a whole number of skin calls");
-template <int LAYOUT, bool EXT, bool PALG>
+template <int LAYOUT, bool EXT, bool PALG, bool RING>
 __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevModel M, DevFrames F, uint32_t chunk, uint32_t n_chunks) {
     constexpr uint32_t PS = EXT ? 5u : 3u;  // float4 per staged bone
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -997,6 +1011,8 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
     unsigned char* stage_base = smem_raw;
     float4* pal_base = reinterpret_cast<float4*>(smem_raw + G * stage_bytes);
     float4* rate_base = pal_base + 2u * G * pal4;
+    float4* ring = rate_base + 2u * M.n_nodes_pad + threadIdx.x;   // this thread's column: entry k at ring[k * kSkinThreads]
+    __builtin_assume(__isShared(ring));
 
     const uint32_t tile = blockIdx.x / n_chunks, ck = blockIdx.x - tile * n_chunks;
     const uint32_t s0 = ck * chunk;                      // chunk is a multiple of G: groups never straddle work items
@@ -1053,6 +1069,13 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
         ebase[j] = h.x + lane;
         erounds[j] = h.y;
     }
+    auto ring_issue = [&](const uint32_t base, const uint32_t rounds) {
+        const float4* __restrict__ src = M.ell_ent + base;
+        const uint32_t n = min(rounds, kRingRounds);
+        for (uint32_t k = 0; k < n; ++k) cp_async16(ring + k * kSkinThreads, src + (size_t)k * 32);
+        cp_async_commit();
+    };
+    if (RING) ring_issue(ebase[0], erounds[0]);   // step 0 of the first slot group; later ones are issued one step ahead
     uint32_t uvbase[V], uvrounds[V];
     if (EXT) {
 #pragma unroll
@@ -1124,8 +1147,7 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
 #pragma unroll
             for (int f = 0; f < G; ++f) ix[f] = iy[f] = iz[f] = 0.f;
             const float4* __restrict__ e = M.ell_ent + ebase[j];
-            for (uint32_t k = 0; k < erounds[j]; ++k) {
-                const float4 ent = __ldg(e + (size_t)k * 32);
+            auto accumulate = [&](const float4& ent) {
                 const float4 r4 = *reinterpret_cast<const float4*>(nrate + __float_as_uint(ent.w));
                 const float r[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
@@ -1134,6 +1156,19 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
                     iy[f] = iy[f] + ent.y * r[f];
                     iz[f] = iz[f] + ent.z * r[f];
                 }
+            };
+            if (RING) {
+                cp_async_wait_all();   // this step's entries, issued while the previous step was skinned (own copies only)
+                const uint32_t nr = min(erounds[j], kRingRounds);
+#pragma unroll
+                for (uint32_t k = 0; k < kRingRounds; ++k)
+                    if (k < nr) accumulate(ring[k * kSkinThreads]);
+                for (uint32_t k = kRingRounds; k < erounds[j]; ++k) accumulate(__ldg(e + (size_t)k * 32));
+                // the ring is free again (its entries are in the accumulators): fetch the next step's rows behind the skinning
+                if (j + 1 < V) ring_issue(ebase[(j + 1) % V], erounds[(j + 1) % V]);
+                else if (has_next) ring_issue(ebase[0], erounds[0]);
+            } else {
+                for (uint32_t k = 0; k < erounds[j]; ++k) accumulate(__ldg(e + (size_t)k * 32));
             }
             if (j == 0 && LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) {
                 // the staging tiles are single-buffered: the previous group's bulk copies must have read them
@@ -1310,10 +1345,16 @@ cudaError_t launch_hierarchy_wave_flat(cudaStream_t st, const DevModel& M, const
     return cudaGetLastError();
 }
 
+// Experiment knob: MMDGPU_RING=1 stages morph entries through the cp.async ring (measured slower on B200, see
+// profiles/r02_experiments.md); default off.
+static bool skin_uses_ring() {
+    static const bool on = [] { const char* e = std::getenv("MMDGPU_RING"); return e && e[0] == '1'; }();
+    return on;
+}
 size_t skin_smem_bytes(const DevModel& M, int layout) {
     const bool ext = M.extensions != 0;
     return (size_t)kSlotGroup * skin_stage_bytes(layout, ext) + 2 * (size_t)kSlotGroup * skin_pal_bytes(M.max_tile_bones, ext) +
-           2 * (size_t)M.n_nodes_pad * 16;
+           2 * (size_t)M.n_nodes_pad * 16 + (skin_uses_ring() ? skin_ring_bytes() : 0u);
 }
 
 // The dynamic shared-memory opt-in is an attribute of the kernel function (per device), not of a launch: every model
@@ -1321,7 +1362,9 @@ size_t skin_smem_bytes(const DevModel& M, int layout) {
 // smaller model loaded later would otherwise lower it under an earlier, larger one).
 template <int LAYOUT, bool EXT, bool PALG>
 static cudaError_t skin_opt_in(int limit) {
-    return cudaFuncSetAttribute(skin_kernel<LAYOUT, EXT, PALG>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+    cudaError_t e = cudaFuncSetAttribute(skin_kernel<LAYOUT, EXT, PALG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(skin_kernel<LAYOUT, EXT, PALG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
 }
 
 cudaError_t prepare_skin_kernels(const DevModel& M) {
@@ -1351,10 +1394,13 @@ cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, 
     const size_t smem = skin_smem_bytes(M, layout);
     const bool soa = layout == MMDGPU_LAYOUT_SOA_POS_NRM;
     constexpr int SOA = MMDGPU_LAYOUT_SOA_POS_NRM, I32 = MMDGPU_LAYOUT_INTERLEAVED_SOKOL32;
+    const bool ring = skin_uses_ring();
 #define MMDGPU_LAUNCH_SKIN(EXT, PALG)                                                                                  \
     do {                                                                                                               \
-        if (soa) skin_kernel<SOA, EXT, PALG><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);         \
-        else skin_kernel<I32, EXT, PALG><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);             \
+        if (soa && ring) skin_kernel<SOA, EXT, PALG, true><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);  \
+        else if (soa) skin_kernel<SOA, EXT, PALG, false><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);    \
+        else if (ring) skin_kernel<I32, EXT, PALG, true><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);    \
+        else skin_kernel<I32, EXT, PALG, false><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);             \
     } while (0)
     if (M.extensions) MMDGPU_LAUNCH_SKIN(true, false);
     else if (M.global_palette) MMDGPU_LAUNCH_SKIN(false, true);

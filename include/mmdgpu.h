@@ -403,6 +403,15 @@ MMDGPU_API mmdgpu_status mmdgpu_peer_buffer_create(mmdgpu_context_t ctx, size_t 
 MMDGPU_API mmdgpu_status mmdgpu_peer_buffer_open(mmdgpu_context_t ctx, const unsigned char handle[64], void** dptr);
 MMDGPU_API mmdgpu_status mmdgpu_peer_buffer_release(mmdgpu_context_t ctx, void* dptr, int opened);
 
+/* Test export (function-level known answers): run ONE device math function of the path on n rows
+ * of inputs.  op / row layouts: 0 Bezier {4 control bytes as floats, x} -> lambda (host-built table + device lookup,
+ * L/util/math_impl.inl:1372-1428); 1 NLerp {a4, b4, l} -> 4 (:1265-1277); 2 SLerp {a4, b4, l} -> 4 (:1312-1340);
+ * 3 quaternion -> Euler {q4, order 0 YZX / 1 ZXY / 2 XYZ} -> 3 (:1059-1137); 4 Euler -> quaternion {e3, order} -> 4
+ * (:1156-1224); 5 AxisToQuaternion {axis3, angle} -> 4 (:1047-1058); 6 quaternion product {a4, b4} -> 4 (:510-517);
+ * 7 ToRotateMatrix {q4} -> rows 0..2 (9) (:540-563); 8 Inverse {q4} -> 4 (:474-477); 9 affine 4x4 product {a16, b16}
+ * -> 16 (:984-1003); 10 Vector3D::Normalize {v3} -> 3 (:393-400). */
+MMDGPU_API mmdgpu_status mmdgpu_test_math(mmdgpu_context_t ctx, int op, const float* in, uint32_t n, float* out);
+
 /* Pinned host memory helpers for the download path. */
 MMDGPU_API mmdgpu_status mmdgpu_host_alloc(size_t bytes, void** out);
 MMDGPU_API void          mmdgpu_host_free(void* p);

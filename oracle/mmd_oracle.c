@@ -970,3 +970,57 @@ EXPORT double port_time_frames(struct port_session* p, const uint32_t* frames, u
     free(jobs); free(th);
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+
+/* ---- function-level known-answer interface (tests/test_math_kat.py): one row of `in` per case --------------------
+ * op 0 BEZIER  in: 4 control bytes (as floats), x            out: lambda              (Bezier::SetC + operator[])
+ * op 1 NLERP   in: a[4], b[4], l                             out: v[4]                (NLerpProxy<Vector4f>::operator[])
+ * op 2 SLERP   in: a[4], b[4], l                             out: q[4]                (SLerpProxy<Quaternionf>::operator[])
+ * op 3 Q2E     in: q[4], order (0 YZX, 1 ZXY, 2 XYZ)         out: euler[3]            (QuaternionTo{YZX,ZXY,XYZ})
+ * op 4 E2Q     in: euler[3], order                           out: q[4]                ({YZX,ZXY,XYZ}ToQuaternion)
+ * op 5 AXIS    in: axis[3], angle                            out: q[4]                (AxisToQuaternion)
+ * op 6 QMUL    in: a[4], b[4]                                out: q[4]                (Quaternion::operator*)
+ * op 7 QROT    in: q[4]                                      out: rows 0..2 (9)       (Quaternion::ToRotateMatrix)
+ * op 8 QINV    in: q[4]                                      out: q[4]                (Quaternion::Inverse)
+ * op 9 MATMUL  in: a[16], b[16]                              out: m[16]               (Matrix4x4::operator*)
+ * op 10 VNORM  in: v[3]                                      out: v[3]                (Vector3D::Normalize)           */
+static const int kat_in[11] = {5, 9, 9, 5, 4, 4, 8, 4, 4, 32, 3};
+static const int kat_out[11] = {1, 4, 4, 3, 4, 4, 4, 9, 4, 16, 3};
+EXPORT int port_math_kat(int op, const float* in, uint32_t n, float* out) {
+    if (op < 0 || op > 10) return -1;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = in + (size_t)i * kat_in[op];
+        float* o = out + (size_t)i * kat_out[op];
+        switch (op) {
+        case 0: {
+            bezier b;
+            int8_t c[4] = {(int8_t)a[0], (int8_t)a[1], (int8_t)a[2], (int8_t)a[3]};
+            bezier_set(&b, c);
+            o[0] = bezier_at(&b, a[4]);
+            break;
+        }
+        case 1: {
+            const float* x = a; const float* y = a + 4; float l = a[8];
+            if (l < EPS_F) { memcpy(o, x, 16); break; }
+            if (l > (1.0f - EPS_F)) { memcpy(o, y, 16); break; }
+            float dot = x[0] * y[0] + x[1] * y[1] + x[2] * y[2] + x[3] * y[3];
+            float v[4];
+            if (dot < 0.0f) for (int c = 0; c < 4; ++c) v[c] = (1.0f - l) * x[c] - l * y[c];
+            else for (int c = 0; c < 4; ++c) v[c] = (1.0f - l) * x[c] + l * y[c];
+            float nn = 1.0f / m_sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
+            for (int c = 0; c < 4; ++c) o[c] = v[c] * nn;
+            break;
+        }
+        case 2: q_slerp(a, a + 4, a[8], o); break;
+        case 3: quat_to_euler((int)a[4], a, o); break;
+        case 4: euler_to_quat((int)a[3], a, o); break;
+        case 5: axis_to_quat(a, a[3], o); break;
+        case 6: q_mul(a, a + 4, o); break;
+        case 7: { float m[16]; q_to_matrix(a, m); for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) o[3 * r + c] = m[4 * r + c]; break; }
+        case 8: q_inverse(a, o); break;
+        case 9: m_mul(a, a + 16, o); break;
+        case 10: v3_normalize(a, o); break;
+        }
+    }
+    return 0;
+}

@@ -512,4 +512,68 @@ __attribute__((visibility("default"))) double ref_time_frames(ref_session* s, co
     return sec;
 }
 
+// Function-level known-answer interface: libmmd's own math on one row of `in` per case (layout: oracle/mmd_oracle.c,
+// port_math_kat).  These are the functions SURVEY section 4 item 3 lists (L/util/math_impl.inl:1047-1224, 1265-1340,
+// 1372-1428); tests/golden/make_math_kat.py stores their outputs as fixtures.
+__attribute__((visibility("default"))) int ref_math_kat(int op, const float* in, uint32_t n, float* out) {
+    static const int kin[11] = {5, 9, 9, 5, 4, 4, 8, 4, 4, 32, 3};
+    static const int kout[11] = {1, 4, 4, 3, 4, 4, 4, 9, 4, 16, 3};
+    if (op < 0 || op > 10) return -1;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* a = in + (size_t)i * kin[op];
+        float* o = out + (size_t)i * kout[op];
+        auto quat = [](const float* p) { Quaternionf q; q.i = p[0]; q.j = p[1]; q.k = p[2]; q.e = p[3]; return q; };
+        auto putq = [](const Quaternionf& q, float* p) { p[0] = q.i; p[1] = q.j; p[2] = q.k; p[3] = q.e; };
+        auto vec3 = [](const float* p) { Vector3f v; v.v[0] = p[0]; v.v[1] = p[1]; v.v[2] = p[2]; return v; };
+        switch (op) {
+        case 0: {   // control bytes exactly as VmdReader feeds them (vmd_reader_impl.inl:32-41)
+            const float r = 1.0f / 127.0f;
+            Vector2f c0, c1;
+            c0.p.x = (signed char)a[0] * r; c0.p.y = (signed char)a[1] * r;
+            c1.p.x = (signed char)a[2] * r; c1.p.y = (signed char)a[3] * r;
+            Bezier<float> bz;
+            bz.SetC(c0, c1);
+            o[0] = bz[a[4]];
+            break;
+        }
+        case 1: {
+            Vector4f x, y;
+            for (int c = 0; c < 4; ++c) { x.v[c] = a[c]; y.v[c] = a[4 + c]; }
+            Vector4f v = NLerp(x, y)[a[8]];
+            for (int c = 0; c < 4; ++c) o[c] = v.v[c];
+            break;
+        }
+        case 2: putq(SLerp(quat(a), quat(a + 4))[a[8]], o); break;
+        case 3: {
+            const int order = (int)a[4];
+            Vector3f e = order == 1 ? QuaternionToZXY(quat(a)) : order == 2 ? QuaternionToXYZ(quat(a)) : QuaternionToYZX(quat(a));
+            o[0] = e.v[0]; o[1] = e.v[1]; o[2] = e.v[2];
+            break;
+        }
+        case 4: {
+            const int order = (int)a[3];
+            putq(order == 1 ? ZXYToQuaternion(vec3(a)) : order == 2 ? XYZToQuaternion(vec3(a)) : YZXToQuaternion(vec3(a)), o);
+            break;
+        }
+        case 5: putq(AxisToQuaternion(vec3(a), a[3]), o); break;
+        case 6: putq(quat(a) * quat(a + 4), o); break;
+        case 7: {
+            Matrix4f m = quat(a).ToRotateMatrix();
+            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) o[3 * r + c] = m.r.v[r].v[c];
+            break;
+        }
+        case 8: putq(quat(a).Inverse(), o); break;
+        case 9: {
+            Matrix4f x, y;
+            for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) { x.r.v[r].v[c] = a[4 * r + c]; y.r.v[r].v[c] = a[16 + 4 * r + c]; }
+            Matrix4f m = x * y;
+            for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) o[4 * r + c] = m.r.v[r].v[c];
+            break;
+        }
+        case 10: { Vector3f v = vec3(a).Normalize(); o[0] = v.v[0]; o[1] = v.v[1]; o[2] = v.v[2]; break; }
+        }
+    }
+    return 0;
+}
+
 }  // extern "C"

@@ -106,22 +106,7 @@ __global__ void __launch_bounds__(128) pose_sample_kernel(DevModel M, const DevA
                     lam = bezier_at(A.tables, cv.z, bary);
                     T.z = lT.z * (1 - lam) + rT.z * lam;
                     const float l_ = bezier_at(A.tables, cv.w, bary);
-                    // NLerpProxy<Vector4f>::operator[], L/util/math_impl.inl:1265-1277
-                    if (l_ < kEpsF) R = lR;
-                    else if (l_ > (1.0f - kEpsF)) R = rR;
-                    else {
-                        const float dot = lR.x * rR.x + lR.y * rR.y + lR.z * rR.z + lR.w * rR.w;
-                        float4 v;
-                        if (dot < 0.0f) {
-                            v.x = (1.0f - l_) * lR.x - l_ * rR.x; v.y = (1.0f - l_) * lR.y - l_ * rR.y;
-                            v.z = (1.0f - l_) * lR.z - l_ * rR.z; v.w = (1.0f - l_) * lR.w - l_ * rR.w;
-                        } else {
-                            v.x = (1.0f - l_) * lR.x + l_ * rR.x; v.y = (1.0f - l_) * lR.y + l_ * rR.y;
-                            v.z = (1.0f - l_) * lR.z + l_ * rR.z; v.w = (1.0f - l_) * lR.w + l_ * rR.w;
-                        }
-                        const float nn = 1.0f / m_sqrt(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
-                        R = make_float4(v.x * nn, v.y * nn, v.z * nn, v.w * nn);
-                    }
+                    R = v4_nlerp(lR, rR, l_);
                 }
                 T.w = 0.f;
             }
@@ -1298,6 +1283,55 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
         }
     }
     if (tid == 0) bulk_wait_all();  // shared memory must outlive the copies that read it
+}
+
+// =================================================================================================
+// Function-level known-answer kernel (mmdgpu_test_math): one thread per case runs ONE device function of
+// mmd_math.cuh on a row of inputs.  Row layouts: oracle/mmd_oracle.c, port_math_kat.
+// =================================================================================================
+__global__ void math_kat_kernel(int op, const float* __restrict__ in, uint32_t n, float* __restrict__ out,
+                                const float* __restrict__ tables, const uint32_t* __restrict__ curve) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int kin[11] = {5, 9, 9, 5, 4, 4, 8, 4, 4, 32, 3}, kout[11] = {1, 4, 4, 3, 4, 4, 4, 9, 4, 16, 3};
+    const float* a = in + (size_t)i * kin[op];
+    float* o = out + (size_t)i * kout[op];
+    auto putq = [&](const Quat& q) { o[0] = q.i; o[1] = q.j; o[2] = q.k; o[3] = q.e; };
+    switch (op) {
+    case 0: o[0] = bezier_at(tables, curve[i], a[4]); break;   // table built on the host by bezier_table(), looked up here
+    case 1: {
+        const float4 v = v4_nlerp(make_float4(a[0], a[1], a[2], a[3]), make_float4(a[4], a[5], a[6], a[7]), a[8]);
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+        break;
+    }
+    case 2: putq(q_slerp(Quat{a[0], a[1], a[2], a[3]}, Quat{a[4], a[5], a[6], a[7]}, a[8])); break;
+    case 3: { const Vec3 e = quat_to_euler((int)a[4], Quat{a[0], a[1], a[2], a[3]}); o[0] = e.x; o[1] = e.y; o[2] = e.z; break; }
+    case 4: putq(euler_to_quat((int)a[3], Vec3{a[0], a[1], a[2]})); break;
+    case 5: putq(axis_to_quat(Vec3{a[0], a[1], a[2]}, a[3])); break;
+    case 6: putq(q_mul(Quat{a[0], a[1], a[2], a[3]}, Quat{a[4], a[5], a[6], a[7]})); break;
+    case 7: {
+        Mat43 M;
+        q_to_rows(Quat{a[0], a[1], a[2], a[3]}, M);
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) o[3 * r + c] = M.m[r][c];
+        break;
+    }
+    case 8: putq(q_inverse(Quat{a[0], a[1], a[2], a[3]})); break;
+    case 9: {   // affine 4 x 4 operands only (fourth column 0,0,0,1): the device keeps 12 elements (mmd_math.cuh, m_mul)
+        Mat43 A, B;
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 3; ++c) { A.m[r][c] = a[4 * r + c]; B.m[r][c] = a[16 + 4 * r + c]; }
+        const Mat43 R = m_mul(A, B);
+        for (int r = 0; r < 4; ++r) { for (int c = 0; c < 3; ++c) o[4 * r + c] = R.m[r][c]; o[4 * r + 3] = r == 3 ? 1.0f : 0.0f; }
+        break;
+    }
+    case 10: { const Vec3 v = v_normalize(Vec3{a[0], a[1], a[2]}); o[0] = v.x; o[1] = v.y; o[2] = v.z; break; }
+    default: break;
+    }
+}
+
+cudaError_t launch_math_kat(cudaStream_t st, int op, const float* in, uint32_t n, float* out, const float* tables, const uint32_t* curve) {
+    if (n == 0) return cudaSuccess;
+    math_kat_kernel<<<(n + 127) / 128, 128, 0, st>>>(op, in, n, out, tables, curve);
+    return cudaGetLastError();
 }
 
 // =================================================================================================

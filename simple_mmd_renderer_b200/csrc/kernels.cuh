@@ -23,4 +23,7 @@ size_t skin_smem_bytes(const DevModel& M, int layout);
 cudaError_t prepare_skin_kernels(const DevModel& M);
 cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, int layout, uint32_t slots_per_cta);
 
+// Test export: one device math function per case (kernels.cu, math_kat_kernel).
+cudaError_t launch_math_kat(cudaStream_t st, int op, const float* in, uint32_t n, float* out, const float* tables, const uint32_t* curve);
+
 }  // namespace mmdgpu

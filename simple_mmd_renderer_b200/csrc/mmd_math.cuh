@@ -77,6 +77,22 @@ MMD_DEV Quat q_slerp(const Quat& a, const Quat& b, float l) {
     }
     return a;
 }
+// NLerpProxy<Vector4f>::operator[], L/util/math_impl.inl:1265-1277 (key-frame rotations, motion_impl.inl:312)
+MMD_DEV float4 v4_nlerp(const float4& a, const float4& b, float l) {
+    if (l < kEpsF) return a;
+    if (l > (1.0f - kEpsF)) return b;
+    const float dot = a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+    float4 v;
+    if (dot < 0.0f) {
+        v.x = (1.0f - l) * a.x - l * b.x; v.y = (1.0f - l) * a.y - l * b.y;
+        v.z = (1.0f - l) * a.z - l * b.z; v.w = (1.0f - l) * a.w - l * b.w;
+    } else {
+        v.x = (1.0f - l) * a.x + l * b.x; v.y = (1.0f - l) * a.y + l * b.y;
+        v.z = (1.0f - l) * a.z + l * b.z; v.w = (1.0f - l) * a.w + l * b.w;
+    }
+    const float nn = 1.0f / m_sqrt(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
+    return make_float4(v.x * nn, v.y * nn, v.z * nn, v.w * nn);
+}
 // Quaternion::ToRotateMatrix, L/util/math_impl.inl:540-563 (rows 0..2; row 3 is set by the caller)
 MMD_DEV void q_to_rows(const Quat& q, Mat43& M) {
     float ii = q.i * q.i, jj = q.j * q.j, kk = q.k * q.k;

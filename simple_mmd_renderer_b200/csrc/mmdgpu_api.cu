@@ -1466,6 +1466,36 @@ MMDGPU_API mmdgpu_status mmdgpu_material_images_download(mmdgpu_frames_t f, uint
 
 MMDGPU_API uint32_t mmdgpu_frames_slot_run(mmdgpu_frames_t f) { return f ? f->slots_per_cta : 0; }
 
+// Test export: runs ONE device math function (csrc/mmd_math.cuh) on n rows of inputs.
+MMDGPU_API mmdgpu_status mmdgpu_test_math(mmdgpu_context_t ctx, int op, const float* in, uint32_t n, float* out) {
+    if (mmdgpu_status s = enter(ctx)) return s;
+    static const int kin[11] = {5, 9, 9, 5, 4, 4, 8, 4, 4, 32, 3}, kout[11] = {1, 4, 4, 3, 4, 4, 4, 9, 4, 16, 3};
+    if (op < 0 || op > 10 || !in || !out) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "unknown op or NULL argument");
+    DevArena mem;
+    std::vector<float> tables;
+    std::vector<uint32_t> curve;
+    if (op == 0) {   // Bezier: the host builds the presampled tables exactly as for a clip, the device looks them up
+        curve.resize(n);
+        for (uint32_t i = 0; i < n; ++i) {
+            const int8_t c[4] = {int8_t(in[5 * i]), int8_t(in[5 * i + 1]), int8_t(in[5 * i + 2]), int8_t(in[5 * i + 3])};
+            float t[32];
+            if (bezier_table(c, t)) curve[i] = 0xFFFFFFFFu;
+            else { curve[i] = uint32_t(tables.size() / 32); tables.insert(tables.end(), t, t + 32); }
+        }
+    }
+    const float *d_in = nullptr, *d_tab = nullptr;
+    const uint32_t* d_curve = nullptr;
+    float* d_out = nullptr;
+    CU(ctx, upload(ctx, mem, in, size_t(n) * kin[op], &d_in));
+    CU(ctx, upload(ctx, mem, tables, &d_tab));
+    CU(ctx, upload(ctx, mem, curve, &d_curve));
+    CU(ctx, dalloc(mem, &d_out, size_t(n) * kout[op], true, ctx->stream));
+    CU(ctx, launch_math_kat(ctx->stream, op, d_in, n, d_out, d_tab, d_curve));
+    CU(ctx, cudaMemcpyAsync(out, d_out, size_t(n) * kout[op] * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return MMDGPU_OK;
+}
+
 // ---- peer buffers: the receive side of a bake gather that the skinning kernels of other ranks write into directly
 MMDGPU_API mmdgpu_status mmdgpu_peer_buffer_create(mmdgpu_context_t ctx, size_t bytes, void** dptr, unsigned char handle[64]) {
     if (mmdgpu_status s = enter(ctx)) return s;

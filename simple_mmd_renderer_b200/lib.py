@@ -96,6 +96,7 @@ SIGNATURES = {
     "mmdgpu_peer_buffer_create": (C.c_int, [_vp, _sz, _PP, _vp]),
     "mmdgpu_peer_buffer_open": (C.c_int, [_vp, _vp, _PP]),
     "mmdgpu_peer_buffer_release": (C.c_int, [_vp, _vp, C.c_int]),
+    "mmdgpu_test_math": (C.c_int, [_vp, C.c_int, _vp, _u32, _vp]),
     "mmdgpu_host_alloc": (C.c_int, [_sz, _PP]),
     "mmdgpu_host_free": (None, [_vp]),
     "mmdgpu_plan_create": (C.c_int, [_vp, _vp, _PP, C.c_char_p, _sz]),

@@ -782,13 +782,6 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// 16-byte asynchronous copy global -> shared (LDGSTS): no register holds the data while it is in flight
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
 struct Col3 { float4 c0, c1, c2; };  // skinning matrix as three columns (M0c, M1c, M2c, M3c)
 
 template <int PS>  // PS = float4 per staged bone: 3 (matrix columns) or 5 (+ rotation quaternion, dual part)
@@ -971,13 +964,6 @@ __host__ __device__ inline uint32_t skin_stage_bytes(int layout, bool ext) {
 }
 __host__ __device__ inline uint32_t skin_pal_bytes(uint32_t max_tile_bones, bool ext) { return max_tile_bones * (ext ? 80u : 48u); }
 
-// Morph entries of a thread's NEXT storage position travel global -> shared memory (cp.async) while it skins the
-// current one: the sliced-ELL rows come from L2 (a tile's 37 KB of entries are re-read for every slot group and three
-// CTAs' worth does not fit L1), and with 12 warps per SM nothing else hides that latency.  Ring = one step deep,
-// kRingRounds entries per thread; rows longer than that read the rest straight from global memory.
-constexpr uint32_t kRingRounds = 6;
-__host__ __device__ inline uint32_t skin_ring_bytes() { return kRingRounds * kSkinThreads * 16u; }
-
 constexpr uint32_t kPalPrefetch = 2;  // palette float4 per thread held in registers across the compute phase
 constexpr int V = (int)kVertsPerThread;
 constexpr int G = (int)kSlotGroup;    // slots one CTA evaluates together
@@ -987,7 +973,7 @@ constexpr int G = (int)kSlotGroup;    // slots one CTA evaluates together
 // slots skinned per skin_vertex_n call: 2 measured best (1: -3.4 %, 4: spills, -11 %; profiles/r01_experiments.md)
 constexpr int kSkinCallSlots = 2;
 static_assert(kSlotGroup % kSkinCallSlots == 0, "a slot group is a whole number of skin calls");
-template <int LAYOUT, bool EXT, bool PALG, bool RING>
+template <int LAYOUT, bool EXT, bool PALG>
 __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevModel M, DevFrames F, uint32_t chunk, uint32_t n_chunks) {
     constexpr uint32_t PS = EXT ? 5u : 3u;  // float4 per staged bone
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -996,8 +982,6 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
     unsigned char* stage_base = smem_raw;
     float4* pal_base = reinterpret_cast<float4*>(smem_raw + G * stage_bytes);
     float4* rate_base = pal_base + 2u * G * pal4;
-    float4* ring = rate_base + 2u * M.n_nodes_pad + threadIdx.x;   // this thread's column: entry k at ring[k * kSkinThreads]
-    __builtin_assume(__isShared(ring));
 
     const uint32_t tile = blockIdx.x / n_chunks, ck = blockIdx.x - tile * n_chunks;
     const uint32_t s0 = ck * chunk;                      // chunk is a multiple of G: groups never straddle work items
@@ -1054,13 +1038,6 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
         ebase[j] = h.x + lane;
         erounds[j] = h.y;
     }
-    auto ring_issue = [&](const uint32_t base, const uint32_t rounds) {
-        const float4* __restrict__ src = M.ell_ent + base;
-        const uint32_t n = min(rounds, kRingRounds);
-        for (uint32_t k = 0; k < n; ++k) cp_async16(ring + k * kSkinThreads, src + (size_t)k * 32);
-        cp_async_commit();
-    };
-    if (RING) ring_issue(ebase[0], erounds[0]);   // step 0 of the first slot group; later ones are issued one step ahead
     uint32_t uvbase[V], uvrounds[V];
     if (EXT) {
 #pragma unroll
@@ -1142,19 +1119,7 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
                     iz[f] = iz[f] + ent.z * r[f];
                 }
             };
-            if (RING) {
-                cp_async_wait_all();   // this step's entries, issued while the previous step was skinned (own copies only)
-                const uint32_t nr = min(erounds[j], kRingRounds);
-#pragma unroll
-                for (uint32_t k = 0; k < kRingRounds; ++k)
-                    if (k < nr) accumulate(ring[k * kSkinThreads]);
-                for (uint32_t k = kRingRounds; k < erounds[j]; ++k) accumulate(__ldg(e + (size_t)k * 32));
-                // the ring is free again (its entries are in the accumulators): fetch the next step's rows behind the skinning
-                if (j + 1 < V) ring_issue(ebase[(j + 1) % V], erounds[(j + 1) % V]);
-                else if (has_next) ring_issue(ebase[0], erounds[0]);
-            } else {
-                for (uint32_t k = 0; k < erounds[j]; ++k) accumulate(__ldg(e + (size_t)k * 32));
-            }
+            for (uint32_t k = 0; k < erounds[j]; ++k) accumulate(__ldg(e + (size_t)k * 32));
             if (j == 0 && LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) {
                 // the staging tiles are single-buffered: the previous group's bulk copies must have read them
                 if (tid == 0) bulk_wait_read_all();
@@ -1286,6 +1251,281 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
 }
 
 // =================================================================================================
+// K3, packed form (the kernel every libmmd-exact model with staged tile palettes runs).
+//
+// Same work decomposition as skin_kernel above, but all per-slot arithmetic is done for TWO slots at once in packed
+// fp32x2 registers (Blackwell FFMA2): the blend and the transform of slots (2p, 2p+1) of one vertex are the same
+// operations on different data, so one issue slot carries both.  Bit parity with libmmd needs un-fused multiplies and
+// adds; sm_100 has no packed FMUL / FADD, and ptxas contracts `mul.f32x2` + `add.f32x2` into one FFMA2 even when both
+// carry .rn, so a product is written  fma(a, b, -0)  and a sum  fma(a, 1, b)  with -0 and 1 coming from kernel
+// ARGUMENTS (opaque to the compiler).  Both are exact restatements: a*b + (-0) rounds the exact product once and keeps
+// its zero sign, a*1 + b is a + b (tools/micro/ffma2.cu checks 4 M operand triples incl. zeros, denormals, infinities).
+// For this the staged palettes are stored pair-interleaved: per slot pair two planes of 16-byte cells,
+// lo[bone][col] = (x0, x1, y0, y1) and hi[bone][col] = (z0, z1, w0, w1), so that one LDS.128 yields two ready pairs.
+// The four slots' morph rates of a node are already one float4 = two pairs.
+// =================================================================================================
+typedef unsigned long long f2;   // two floats in one 64-bit register: (lo, hi) = (even slot, odd slot)
+__device__ __forceinline__ f2 pk2(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float lo2(f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float hi2(f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+struct PairK { f2 nz, one; };    // (-0, -0) and (1, 1), from kernel arguments
+__device__ __forceinline__ f2 mul2(f2 a, f2 b, const PairK& K) { return fma2(a, b, K.nz); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b, const PairK& K) { return fma2(a, K.one, b); }
+
+struct SkinnedP { f2 px, py, pz, nx, ny, nz; };
+struct ColP { f2 x, y, z, w; };  // one matrix column (M0c, M1c, M2c, M3c) of a slot pair
+__device__ __forceinline__ ColP colp_load(const ulonglong2* __restrict__ pal, uint32_t hi_off, uint32_t cell) {
+    const ulonglong2 lo = pal[cell], hi = pal[hi_off + cell];
+    return ColP{lo.x, lo.y, hi.x, hi.y};
+}
+// One vertex, two slots.  pal: the slot pair's lo plane; hi_off: distance to its hi plane (16-byte cells).
+// Poser::Deform's blend (poser_impl.inl:404-436) and transform / rotate (math_impl.inl:1032-1045), association order kept.
+__device__ __noinline__ SkinnedP skin_vertex_pair(const ulonglong2* __restrict__ pal, uint32_t hi_off, uint32_t ids_lo, uint32_t ids_hi,
+                                                  float4 w, f2 qx, f2 qy, f2 qz, float nx, float ny, float nz, f2 k_nz, f2 k_one) {
+    __builtin_assume(__isShared(pal));
+    const PairK K{k_nz, k_one};
+    const uint32_t type = (ids_lo >> 13) & 7u;
+    const uint32_t id0 = ids_lo & 0x1FFFu, id1 = ids_lo >> 16;
+    ColP m[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) m[c] = colp_load(pal, hi_off, id0 * 3u + c);
+    if (type == kDevBdef2) {
+        // Lerp(mat_1, mat_0)[w] = (1-w)*mat_1 + w*mat_0
+        const float om1 = 1.0f - w.x;
+        const f2 L = pk2(w.x, w.x), OM = pk2(om1, om1);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const ColP b = colp_load(pal, hi_off, id1 * 3u + c);
+            m[c].x = add2(mul2(b.x, OM, K), mul2(m[c].x, L, K), K);
+            m[c].y = add2(mul2(b.y, OM, K), mul2(m[c].y, L, K), K);
+            m[c].z = add2(mul2(b.z, OM, K), mul2(m[c].z, L, K), K);
+            m[c].w = add2(mul2(b.w, OM, K), mul2(m[c].w, L, K), K);
+        }
+    } else if (type == kDevBdef4) {
+        // mat_0*w0 + mat_1*w1 + mat_2*w2 + mat_3*w3, left to right
+        const uint32_t id2 = ids_hi & 0xFFFFu, id3 = ids_hi >> 16;
+        const f2 W0 = pk2(w.x, w.x), W1 = pk2(w.y, w.y), W2 = pk2(w.z, w.z), W3 = pk2(w.w, w.w);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const ColP b = colp_load(pal, hi_off, id1 * 3u + c), cc = colp_load(pal, hi_off, id2 * 3u + c), d = colp_load(pal, hi_off, id3 * 3u + c);
+            m[c].x = add2(add2(add2(mul2(m[c].x, W0, K), mul2(b.x, W1, K), K), mul2(cc.x, W2, K), K), mul2(d.x, W3, K), K);
+            m[c].y = add2(add2(add2(mul2(m[c].y, W0, K), mul2(b.y, W1, K), K), mul2(cc.y, W2, K), K), mul2(d.y, W3, K), K);
+            m[c].z = add2(add2(add2(mul2(m[c].z, W0, K), mul2(b.z, W1, K), K), mul2(cc.z, W2, K), K), mul2(d.z, W3, K), K);
+            m[c].w = add2(add2(add2(mul2(m[c].w, W0, K), mul2(b.w, W1, K), K), mul2(cc.w, W2, K), K), mul2(d.w, W3, K), K);
+        }
+    }
+    const f2 NX = pk2(nx, nx), NY = pk2(ny, ny), NZ = pk2(nz, nz);
+    SkinnedP r;
+    r.px = add2(add2(add2(mul2(qx, m[0].x, K), mul2(qy, m[0].y, K), K), mul2(qz, m[0].z, K), K), m[0].w, K);
+    r.py = add2(add2(add2(mul2(qx, m[1].x, K), mul2(qy, m[1].y, K), K), mul2(qz, m[1].z, K), K), m[1].w, K);
+    r.pz = add2(add2(add2(mul2(qx, m[2].x, K), mul2(qy, m[2].y, K), K), mul2(qz, m[2].z, K), K), m[2].w, K);
+    r.nx = add2(add2(mul2(NX, m[0].x, K), mul2(NY, m[0].y, K), K), mul2(NZ, m[0].z, K), K);
+    r.ny = add2(add2(mul2(NX, m[1].x, K), mul2(NY, m[1].y, K), K), mul2(NZ, m[1].z, K), K);
+    r.nz = add2(add2(mul2(NX, m[2].x, K), mul2(NY, m[2].y, K), K), mul2(NZ, m[2].z, K), K);
+    return r;
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(kSkinThreads, 3) skin_pair_kernel(DevModel M, DevFrames F, uint32_t chunk, uint32_t n_chunks,
+                                                                    float arg_neg_zero, float arg_one) {
+    static_assert(G == 4, "two slot pairs per group");
+    constexpr int NP = G / 2;                           // slot pairs per group
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t stage_bytes = skin_stage_bytes(LAYOUT, false), pal_bytes = skin_pal_bytes(M.max_tile_bones, false);
+    const uint32_t pal4 = pal_bytes >> 4;               // 16-byte cells per slot; a pair owns 2 * pal4: lo plane, hi plane
+    unsigned char* stage_base = smem_raw;
+    ulonglong2* pal_base = reinterpret_cast<ulonglong2*>(smem_raw + G * stage_bytes);
+    float4* rate_base = reinterpret_cast<float4*>(pal_base + 2u * G * pal4);
+    const PairK K{pk2(arg_neg_zero, arg_neg_zero), pk2(arg_one, arg_one)};
+
+    const uint32_t tile = blockIdx.x / n_chunks, ck = blockIdx.x - tile * n_chunks;
+    const uint32_t s0 = ck * chunk;
+    const uint32_t s1 = min(F.n_slots, s0 + chunk);
+    if (s0 >= s1) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t tile_nv = min(kTileVerts, M.nv - tile * kTileVerts);
+
+    // ---- the tile's static streams: read once, kept in registers for every slot of this work item
+    static_assert(V == 4, "four storage positions per thread");
+    const uint32_t v0 = tile * kTileVerts + tid * kVertsPerThread;
+    float px[V], py[V], pz[V], nx[V], ny[V], nz[V];
+    uint32_t ilo[V], ihi[V], orig[V];
+    float4 wv[V];
+    {
+        const float4 PX = __ldg(reinterpret_cast<const float4*>(M.px + v0)), PY = __ldg(reinterpret_cast<const float4*>(M.py + v0)),
+                     PZ = __ldg(reinterpret_cast<const float4*>(M.pz + v0)), NX = __ldg(reinterpret_cast<const float4*>(M.nx + v0)),
+                     NY = __ldg(reinterpret_cast<const float4*>(M.ny + v0)), NZ = __ldg(reinterpret_cast<const float4*>(M.nz + v0));
+        const float a[6][4] = {{PX.x, PX.y, PX.z, PX.w}, {PY.x, PY.y, PY.z, PY.w}, {PZ.x, PZ.y, PZ.z, PZ.w},
+                               {NX.x, NX.y, NX.z, NX.w}, {NY.x, NY.y, NY.z, NY.w}, {NZ.x, NZ.y, NZ.z, NZ.w}};
+#pragma unroll
+        for (int j = 0; j < V; ++j) { px[j] = a[0][j]; py[j] = a[1][j]; pz[j] = a[2][j]; nx[j] = a[3][j]; ny[j] = a[4][j]; nz[j] = a[5][j]; }
+        const uint2 OR = __ldg(reinterpret_cast<const uint2*>(M.orig + v0));
+        const uint32_t o[4] = {OR.x & 0xFFFFu, OR.x >> 16, OR.y & 0xFFFFu, OR.y >> 16};
+#pragma unroll
+        for (int j = 0; j < V; ++j) orig[j] = o[j];
+    }
+#pragma unroll
+    for (int j = 0; j < V; j += 2) {
+        const uint4 I = __ldg(reinterpret_cast<const uint4*>(M.ids + v0 + j));
+        ilo[j] = I.x; ihi[j] = I.y; ilo[j + 1] = I.z; ihi[j + 1] = I.w;
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) wv[j] = __ldg(M.weights + v0 + j);
+    uint32_t ebase[V], erounds[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const uint2 h = __ldg(M.ell_hdr + tile * kTileGroups + j * kSkinWarps + warp);
+        ebase[j] = h.x + lane;
+        erounds[j] = h.y;
+    }
+    // ---- tile-local palettes of one slot group, pair-interleaved.  Item i = (pair p = i / npal4, cell q = i % npal4); cell q
+    //      is column q % 3 of tile bone q / 3.  Its two source float4 (slots 2p and 2p+1 of the group) become the cells
+    //      lo = (x0, x1, y0, y1) and hi = (z0, z1, w0, w1).
+    const uint32_t tb0 = __ldg(M.tile_bone_begin + tile);
+    const uint32_t npal4 = (__ldg(M.tile_bone_begin + tile + 1) - tb0) * 3u;
+    const uint32_t n_items = npal4 * NP;
+    const uint32_t npad = M.n_nodes_pad;
+    auto item_cell = [&](uint32_t i, uint32_t& pair, uint32_t& q) -> uint32_t {   // returns the source float4 index inside a slot's palette
+        pair = i / npal4; q = i - pair * npal4;
+        return (uint32_t)__ldg(M.tile_bones + tb0 + q / 3u) * 3u + q % 3u;
+    };
+    auto fetch = [&](uint32_t group_slot0, uint32_t pair, uint32_t src, float4& A, float4& B) {
+        const uint32_t sa = min(group_slot0 + 2u * pair, F.n_slots - 1u), sb = min(group_slot0 + 2u * pair + 1u, F.n_slots - 1u);
+        A = __ldg(F.palette + (size_t)sa * M.nb * 3 + src);
+        B = __ldg(F.palette + (size_t)sb * M.nb * 3 + src);
+    };
+    auto publish = [&](ulonglong2* buf, uint32_t pair, uint32_t q, const float4& A, const float4& B) {
+        ulonglong2* cell = buf + (size_t)pair * 2u * pal4 + q;
+        cell[0] = make_ulonglong2(pk2(A.x, B.x), pk2(A.y, B.y));
+        cell[pal4] = make_ulonglong2(pk2(A.z, B.z), pk2(A.w, B.w));
+    };
+    // one item per thread is prefetched in registers across the compute phase (C3: 2 pairs x ~8 bones x 3 = 48 items)
+    uint32_t my_pair = 0, my_q = 0, my_src = 0xFFFFFFFFu;
+    if (tid < n_items) my_src = item_cell(tid, my_pair, my_q);
+
+    // ---- prologue: first group straight into buffer 0
+    {
+        for (uint32_t i = tid; i < n_items; i += kSkinThreads) {
+            uint32_t p, q; float4 A, B;
+            const uint32_t src = item_cell(i, p, q);
+            fetch(s0, p, src, A, B);
+            publish(pal_base, p, q, A, B);
+        }
+        const float4* gr = reinterpret_cast<const float4*>(F.node_rate) + (size_t)(s0 / G) * npad;
+        for (uint32_t i = tid; i < npad; i += kSkinThreads) rate_base[i] = __ldg(gr + i);
+    }
+    __syncthreads();
+
+    uint32_t b = 0;
+    for (uint32_t g0 = s0; g0 < s1; g0 += G, b ^= 1u) {
+        const ulonglong2* __restrict__ pal = pal_base + (size_t)b * G * pal4;
+        const char* __restrict__ nrate = reinterpret_cast<const char*>(rate_base + (size_t)b * npad);
+        const uint32_t n_live = min((uint32_t)G, s1 - g0);
+        const bool has_next = g0 + G < s1;
+        // ---- next group's palettes and rates: loads issued now, consumed after the compute phase
+        float4 pfA = make_float4(0.f, 0.f, 0.f, 0.f), pfB = pfA, rf = pfA;
+        const float4* gr = reinterpret_cast<const float4*>(F.node_rate) + (size_t)(g0 / G + 1) * npad;
+        if (has_next) {
+            if (my_src != 0xFFFFFFFFu) fetch(g0 + G, my_pair, my_src, pfA, pfB);
+            if (tid < npad) rf = __ldg(gr + tid);
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            // vertex_images_[i] of the four slots as two pairs; img = img + off * rate in application order (poser_impl.inl:340-346).
+            // A skipped slot has rate +0 and is applied unconditionally (the accumulator starts at +0 and can never become -0).
+            f2 IX[NP], IY[NP], IZ[NP];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) IX[p] = IY[p] = IZ[p] = 0ull;
+            const float4* __restrict__ e = M.ell_ent + ebase[j];
+            for (uint32_t k = 0; k < erounds[j]; ++k) {
+                const float4 ent = __ldg(e + (size_t)k * 32);
+                const ulonglong2 r = *reinterpret_cast<const ulonglong2*>(nrate + __float_as_uint(ent.w));
+                const f2 EX = pk2(ent.x, ent.x), EY = pk2(ent.y, ent.y), EZ = pk2(ent.z, ent.z);
+                IX[0] = add2(IX[0], mul2(EX, r.x, K), K); IX[1] = add2(IX[1], mul2(EX, r.y, K), K);
+                IY[0] = add2(IY[0], mul2(EY, r.x, K), K); IY[1] = add2(IY[1], mul2(EY, r.y, K), K);
+                IZ[0] = add2(IZ[0], mul2(EZ, r.x, K), K); IZ[1] = add2(IZ[1], mul2(EZ, r.y, K), K);
+            }
+            if (j == 0 && LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) {
+                // the staging tiles are single-buffered: the previous group's bulk copies must have read them
+                if (tid == 0) bulk_wait_read_all();
+                __syncthreads();
+            }
+            float su = 0.f, sv_ = 0.f;
+            if (LAYOUT == MMDGPU_LAYOUT_INTERLEAVED_SOKOL32) {
+                const float2 t = __ldg(M.uv + v0 + j);   // static UV passthrough (main.cpp:840,855-856)
+                su = t.x; sv_ = t.y;
+            }
+            const f2 PX2 = pk2(px[j], px[j]), PY2 = pk2(py[j], py[j]), PZ2 = pk2(pz[j], pz[j]);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                // coordinate + vertex_image (poser_impl.inl:407)
+                const SkinnedP r = skin_vertex_pair(pal + (size_t)p * 2u * pal4, pal4, ilo[j], ihi[j], wv[j], add2(PX2, IX[p], K),
+                                                    add2(PY2, IY[p], K), add2(PZ2, IZ[p], K), nx[j], ny[j], nz[j], K.nz, K.one);
+                if (LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if ((uint32_t)(2 * p + h) >= n_live) continue;
+                        unsigned char* stage = stage_base + (size_t)(2 * p + h) * stage_bytes;
+                        float* sp = reinterpret_cast<float*>(stage) + orig[j] * 3u;
+                        float* sn = reinterpret_cast<float*>(stage + kTileVerts * 12u) + orig[j] * 3u;
+                        sp[0] = h ? hi2(r.px) : lo2(r.px); sp[1] = h ? hi2(r.py) : lo2(r.py); sp[2] = h ? hi2(r.pz) : lo2(r.pz);
+                        sn[0] = h ? hi2(r.nx) : lo2(r.nx); sn[1] = h ? hi2(r.ny) : lo2(r.ny); sn[2] = h ? hi2(r.nz) : lo2(r.nz);
+                    }
+                } else if (orig[j] < tile_nv) {
+                    // main.cpp:838-859: Vertex{pos * 0.1f, normal, uv}
+                    const f2 T = pk2(0.1f, 0.1f);
+                    const f2 sx = mul2(r.px, T, K), sy = mul2(r.py, T, K), sz = mul2(r.pz, T, K);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if ((uint32_t)(2 * p + h) >= n_live) continue;
+                        float4* sv = F.out_inter + (size_t)(g0 + 2 * p + h) * F.inter_stride + ((size_t)tile * kTileVerts + orig[j]) * 2u;
+                        store_record32(sv, h ? hi2(sx) : lo2(sx), h ? hi2(sy) : lo2(sy), h ? hi2(sz) : lo2(sz), h ? hi2(r.nx) : lo2(r.nx),
+                                       h ? hi2(r.ny) : lo2(r.ny), h ? hi2(r.nz) : lo2(r.nz), su, sv_);
+                    }
+                }
+            }
+        }
+        // ---- publish the next group's palettes / rates into the other buffer
+        if (has_next) {
+            ulonglong2* npal = pal_base + (size_t)(b ^ 1u) * G * pal4;
+            float4* nrt = rate_base + (size_t)(b ^ 1u) * npad;
+            if (my_src != 0xFFFFFFFFu) publish(npal, my_pair, my_q, pfA, pfB);
+            for (uint32_t i = tid + kSkinThreads; i < n_items; i += kSkinThreads) {
+                uint32_t p, q; float4 A, B;
+                const uint32_t src = item_cell(i, p, q);
+                fetch(g0 + G, p, src, A, B);
+                publish(npal, p, q, A, B);
+            }
+            if (tid < npad) nrt[tid] = rf;
+            for (uint32_t i = tid + kSkinThreads; i < npad; i += kSkinThreads) nrt[i] = __ldg(gr + i);
+        }
+        // ---- hand the staged tiles to the bulk-copy engine (the barrier also orders the palette double buffer)
+        if (LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0 && LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) {
+            const uint32_t b3 = (tile_nv * 12u) & ~15u;
+            for (uint32_t f = 0; f < n_live; ++f) {
+                unsigned char* stage = stage_base + (size_t)f * stage_bytes;
+                const size_t vt = (size_t)tile * kTileVerts;
+                float* dp = F.out_pos + (size_t)(g0 + f) * F.pos_stride + vt * 3;
+                float* dn = F.out_nrm + (size_t)(g0 + f) * F.nrm_stride + vt * 3;
+                if (b3) {
+                    bulk_s2g(dp, stage, b3);
+                    bulk_s2g(dn, stage + kTileVerts * 12u, b3);
+                }
+                for (uint32_t w = b3 / 4u; w < tile_nv * 3u; ++w) {
+                    dp[w] = reinterpret_cast<const float*>(stage)[w];
+                    dn[w] = reinterpret_cast<const float*>(stage + kTileVerts * 12u)[w];
+                }
+            }
+            bulk_commit();
+        }
+    }
+    if (tid == 0) bulk_wait_all();  // shared memory must outlive the copies that read it
+}
+
+// =================================================================================================
 // Function-level known-answer kernel (mmdgpu_test_math): one thread per case runs ONE device function of
 // mmd_math.cuh on a row of inputs.  Row layouts: oracle/mmd_oracle.c, port_math_kat.
 // =================================================================================================
@@ -1379,16 +1619,10 @@ cudaError_t launch_hierarchy_wave_flat(cudaStream_t st, const DevModel& M, const
     return cudaGetLastError();
 }
 
-// Experiment knob: MMDGPU_RING=1 stages morph entries through the cp.async ring (measured slower on B200, see
-// profiles/r02_experiments.md); default off.
-static bool skin_uses_ring() {
-    static const bool on = [] { const char* e = std::getenv("MMDGPU_RING"); return e && e[0] == '1'; }();
-    return on;
-}
 size_t skin_smem_bytes(const DevModel& M, int layout) {
     const bool ext = M.extensions != 0;
     return (size_t)kSlotGroup * skin_stage_bytes(layout, ext) + 2 * (size_t)kSlotGroup * skin_pal_bytes(M.max_tile_bones, ext) +
-           2 * (size_t)M.n_nodes_pad * 16 + (skin_uses_ring() ? skin_ring_bytes() : 0u);
+           2 * (size_t)M.n_nodes_pad * 16;
 }
 
 // The dynamic shared-memory opt-in is an attribute of the kernel function (per device), not of a launch: every model
@@ -1396,9 +1630,7 @@ size_t skin_smem_bytes(const DevModel& M, int layout) {
 // smaller model loaded later would otherwise lower it under an earlier, larger one).
 template <int LAYOUT, bool EXT, bool PALG>
 static cudaError_t skin_opt_in(int limit) {
-    cudaError_t e = cudaFuncSetAttribute(skin_kernel<LAYOUT, EXT, PALG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(skin_kernel<LAYOUT, EXT, PALG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+    return cudaFuncSetAttribute(skin_kernel<LAYOUT, EXT, PALG>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
 }
 
 cudaError_t prepare_skin_kernels(const DevModel& M) {
@@ -1417,7 +1649,9 @@ cudaError_t prepare_skin_kernels(const DevModel& M) {
     if ((e = skin_opt_in<SOA, false, true>(limit)) != cudaSuccess) return e;
     if ((e = skin_opt_in<I32, false, true>(limit)) != cudaSuccess) return e;
     if ((e = skin_opt_in<SOA, false, false>(limit)) != cudaSuccess) return e;
-    return skin_opt_in<I32, false, false>(limit);
+    if ((e = skin_opt_in<I32, false, false>(limit)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(skin_pair_kernel<SOA>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(skin_pair_kernel<I32>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
 }
 
 cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, int layout, uint32_t slots_per_cta) {
@@ -1428,17 +1662,18 @@ cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, 
     const size_t smem = skin_smem_bytes(M, layout);
     const bool soa = layout == MMDGPU_LAYOUT_SOA_POS_NRM;
     constexpr int SOA = MMDGPU_LAYOUT_SOA_POS_NRM, I32 = MMDGPU_LAYOUT_INTERLEAVED_SOKOL32;
-    const bool ring = skin_uses_ring();
 #define MMDGPU_LAUNCH_SKIN(EXT, PALG)                                                                                  \
     do {                                                                                                               \
-        if (soa && ring) skin_kernel<SOA, EXT, PALG, true><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);  \
-        else if (soa) skin_kernel<SOA, EXT, PALG, false><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);    \
-        else if (ring) skin_kernel<I32, EXT, PALG, true><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);    \
-        else skin_kernel<I32, EXT, PALG, false><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);             \
+        if (soa) skin_kernel<SOA, EXT, PALG><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);         \
+        else skin_kernel<I32, EXT, PALG><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks);             \
     } while (0)
+    // MMDGPU_SKIN_SCALAR=1 (test / experiment knob): the scalar kernel instead of the packed-pair one
+    static const bool scalar = [] { const char* e = std::getenv("MMDGPU_SKIN_SCALAR"); return e && e[0] == '1'; }();
     if (M.extensions) MMDGPU_LAUNCH_SKIN(true, false);
     else if (M.global_palette) MMDGPU_LAUNCH_SKIN(false, true);
-    else MMDGPU_LAUNCH_SKIN(false, false);
+    else if (scalar) MMDGPU_LAUNCH_SKIN(false, false);
+    else if (soa) skin_pair_kernel<SOA><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks, -0.0f, 1.0f);
+    else skin_pair_kernel<I32><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks, -0.0f, 1.0f);
 #undef MMDGPU_LAUNCH_SKIN
     return cudaGetLastError();
 }

@@ -322,6 +322,12 @@ MMDGPU_API mmdgpu_status mmdgpu_seek_frame_range(mmdgpu_frames_t frames, const m
  * 426-470): frame = seconds * 30 as a double, no snapping to key frames.  time_per_slot: n_slots seconds (host). */
 MMDGPU_API mmdgpu_status mmdgpu_seek_time(mmdgpu_frames_t frames, const mmdgpu_animation_t* per_instance,
                                           const double* time_per_slot);
+/* mmdgpu_reset_posing followed by mmdgpu_seek_frame / _seek_time as ONE sampling launch: bones and morphs the clip does not
+ * animate get identity / zero, the others their sampled key frames (what main.cpp:1788-1796 leaves in the Poser). */
+MMDGPU_API mmdgpu_status mmdgpu_reset_and_seek_frame(mmdgpu_frames_t frames, const mmdgpu_animation_t* per_instance,
+                                                     const uint32_t* frame_per_slot);
+MMDGPU_API mmdgpu_status mmdgpu_reset_and_seek_time(mmdgpu_frames_t frames, const mmdgpu_animation_t* per_instance,
+                                                    const double* time_per_slot);
 /* Poser::SetBonePose / SetMorphPose by index (L/motion/poser_impl.inl:466-480). */
 MMDGPU_API mmdgpu_status mmdgpu_set_bone_pose(mmdgpu_frames_t frames, uint32_t slot, uint32_t bone,
                                               const float translation[3], const float rotation[4]);

@@ -170,26 +170,53 @@ public:
     Poser(const Poser&) = delete;
     Poser& operator=(const Poser&) = delete;
 
-    // poser_impl.inl:130-140 — zero rates, identity poses, then a full Pre + PostPhysicsPosing
+    // poser_impl.inl:130-140 — zero rates, identity poses, then a full Pre + PostPhysicsPosing.
+    //
+    // main.cpp:1788-1810 calls ResetPosing(); SeekFrame(f); PrePhysicsPosing(); PostPhysicsPosing() every frame.  The
+    // evaluation ResetPosing ends with is dead there: PrePhysicsPosing clears every bone's scratch state and Pre + Post
+    // recompute all bones from the poses alone (poser_impl.inl:362-394).  The calls are therefore recorded, and when the
+    // sequence Reset [, Seek], Pre, Post completes it is issued as ONE sampling launch (identity / zero for what the clip
+    // does not animate, the sampled key frames for the rest) plus the two hierarchy passes.  Any other continuation
+    // (Deform right after ResetPosing, SetBonePose, a download, Pre without Post ...) replays the recorded calls exactly
+    // as libmmd would have run them, so every observable state is libmmd's.
     void ResetPosing() {
-        check(mmdgpu_reset_posing(frames_), "mmdgpu_reset_posing");
-        PrePhysicsPosing();
-        PostPhysicsPosing();
+        Flush();
+        pending_ = kReset;
     }
     void SetBonePose(size_t index, const float translation[3], const float rotation_xyzw[4]) {
+        Flush();
         check(mmdgpu_set_bone_pose(frames_, 0, uint32_t(index), translation, rotation_xyzw), "mmdgpu_set_bone_pose");
     }
     void SetMorphPose(size_t index, float weight) {
+        Flush();
         check(mmdgpu_set_morph_pose(frames_, 0, uint32_t(index), weight), "mmdgpu_set_morph_pose");
     }
-    void PrePhysicsPosing() { check(mmdgpu_pre_physics_posing(frames_), "mmdgpu_pre_physics_posing"); }
-    void PostPhysicsPosing() { check(mmdgpu_post_physics_posing(frames_), "mmdgpu_post_physics_posing"); }
+    void PrePhysicsPosing() {
+        if (pending_ == kReset || pending_ == (kReset | kSeek)) { pending_ |= kPre; return; }
+        Flush();
+        check(mmdgpu_pre_physics_posing(frames_), "mmdgpu_pre_physics_posing");
+    }
+    void PostPhysicsPosing() {
+        if (pending_ & kPre) {   // Reset [, Seek], Pre, Post: nothing of ResetPosing's own evaluation survives
+            const unsigned had = pending_;
+            pending_ = kNone;
+            if (had & kSeek) IssueSeek(true);
+            else check(mmdgpu_reset_posing(frames_), "mmdgpu_reset_posing");
+            check(mmdgpu_pre_physics_posing(frames_), "mmdgpu_pre_physics_posing");
+            check(mmdgpu_post_physics_posing(frames_), "mmdgpu_post_physics_posing");
+            return;
+        }
+        Flush();
+        check(mmdgpu_post_physics_posing(frames_), "mmdgpu_post_physics_posing");
+    }
     void Deform() {
+        Flush();
         check(mmdgpu_deform(frames_), "mmdgpu_deform");
         image_valid_ = false;
     }
     // ResetPosing + SeekFrame + Pre + Post + Deform in one call (the fused path; physics off).
     void Update(const Motion& motion, size_t frame) {
+        pending_ = kNone;        // everything recorded so far is overwritten by the fused update
         mmdgpu_animation_t a = motion.handle();
         const uint32_t f = uint32_t(frame);
         check(mmdgpu_update(frames_, &a, &f), "mmdgpu_update");
@@ -197,27 +224,60 @@ public:
     }
     // Physics hand-back between Pre and Post (PoserMotionState::Synchronize / Fix, mmd-bullet_impl.inl:34-56).
     void OverrideSkinningMatrix(size_t bone, const float skinning[16], const float* local_or_null = nullptr) {
+        Flush();   // with physics on, the recorded calls run exactly as libmmd's (the host Bullet step dominates the frame anyway)
         check(mmdgpu_set_skinning_matrix_override(frames_, 0, uint32_t(bone), skinning, local_or_null),
               "mmdgpu_set_skinning_matrix_override");
     }
     // The 32-byte Vertex{pos*0.1f, normal, uv} records main.cpp:838-859 builds, ready for sg_update_buffer
     // (requires layout = MMDGPU_LAYOUT_INTERLEAVED_SOKOL32).
     void DownloadInterleaved(void* dst_vertices) {
+        Flush();
         check(mmdgpu_frames_download(frames_, 0, MMDGPU_STREAM_INTERLEAVED, dst_vertices, model_.GetVertexNum() * 32),
               "mmdgpu_frames_download");
     }
     // Poser::material_mul_images_ / material_add_images_ (poser.inl:160-161): n_materials x 2 x 28 floats; all 1 / all 0
     // unless the model was created with extensions (libmmd never fills them).
-    void DownloadMaterialImages(float* dst) { check(mmdgpu_material_images_download(frames_, 0, dst), "mmdgpu_material_images_download"); }
-    void DownloadSkinningMatrices(float* dst_nb_x_16) { check(mmdgpu_bone_matrices_download(frames_, 0, dst_nb_x_16), "mmdgpu_bone_matrices_download"); }
+    void DownloadMaterialImages(float* dst) { Flush(); check(mmdgpu_material_images_download(frames_, 0, dst), "mmdgpu_material_images_download"); }
+    void DownloadSkinningMatrices(float* dst_nb_x_16) { Flush(); check(mmdgpu_bone_matrices_download(frames_, 0, dst_nb_x_16), "mmdgpu_bone_matrices_download"); }
     const Model& GetModel() const { return model_; }
     Model& GetModel() { return model_; }
-    mmdgpu_frames_t frames() const { return frames_; }
+    // The frames object behind this Poser, with every recorded call issued (for mmdgpu_frames_bind_output and friends).
+    mmdgpu_frames_t frames() { Flush(); return frames_; }
 
 private:
+    friend class MotionPlayer;
+    enum : unsigned { kNone = 0, kReset = 1, kSeek = 2, kPre = 4 };
     void check(mmdgpu_status s, const char* what) const { model_.context().check(s, what); }
+    // MotionPlayer::SeekFrame / SeekTime land here
+    void Seek(mmdgpu_animation_t anim, bool by_time, uint32_t frame, double seconds) {
+        if (pending_ != kReset) Flush();
+        seek_anim_ = anim; seek_by_time_ = by_time; seek_frame_ = frame; seek_seconds_ = seconds;
+        if (pending_ == kReset) { pending_ |= kSeek; return; }
+        IssueSeek(false);
+    }
+    void IssueSeek(bool with_reset) {
+        if (seek_by_time_)
+            check(with_reset ? mmdgpu_reset_and_seek_time(frames_, &seek_anim_, &seek_seconds_) : mmdgpu_seek_time(frames_, &seek_anim_, &seek_seconds_),
+                  "mmdgpu_seek_time");
+        else
+            check(with_reset ? mmdgpu_reset_and_seek_frame(frames_, &seek_anim_, &seek_frame_) : mmdgpu_seek_frame(frames_, &seek_anim_, &seek_frame_),
+                  "mmdgpu_seek_frame");
+    }
+    // Issue the recorded calls one by one, as libmmd would have executed them.
+    void Flush() {
+        const unsigned had = pending_;
+        pending_ = kNone;
+        if (had & kReset) {
+            check(mmdgpu_reset_posing(frames_), "mmdgpu_reset_posing");
+            check(mmdgpu_pre_physics_posing(frames_), "mmdgpu_pre_physics_posing");
+            check(mmdgpu_post_physics_posing(frames_), "mmdgpu_post_physics_posing");
+        }
+        if (had & kSeek) IssueSeek(false);
+        if (had & kPre) check(mmdgpu_pre_physics_posing(frames_), "mmdgpu_pre_physics_posing");
+    }
     // both planes of pose_image in one round trip (SoA layout; the interleaved layout has DownloadInterleaved)
     void Fetch() {
+        Flush();
         if (image_valid_) return;
         const size_t bytes = model_.GetVertexNum() * sizeof(Vector3f);
         check(mmdgpu_frames_download_async(frames_, 0, 1, MMDGPU_STREAM_POSITION, pose_image.coordinates.host_, bytes),
@@ -232,6 +292,11 @@ private:
     mmdgpu_layout layout_;
     mmdgpu_frames_t frames_ = nullptr;
     bool image_valid_ = false;
+    unsigned pending_ = kNone;
+    mmdgpu_animation_t seek_anim_ = nullptr;
+    bool seek_by_time_ = false;
+    uint32_t seek_frame_ = 0;
+    double seek_seconds_ = 0.0;
 };
 
 class MotionPlayer {
@@ -240,16 +305,9 @@ public:
         if (&motion.model() != &poser.GetModel()) throw Error(MMDGPU_ERR_INVALID_ARG, "motion and poser use different models");
     }
     // MotionPlayer::SeekFrame(size_t), poser_impl.inl:539-546
-    void SeekFrame(size_t frame) {
-        mmdgpu_animation_t a = motion_.handle();
-        const uint32_t f = uint32_t(frame);
-        poser_.GetModel().context().check(mmdgpu_seek_frame(poser_.frames(), &a, &f), "mmdgpu_seek_frame");
-    }
+    void SeekFrame(size_t frame) { poser_.Seek(motion_.handle(), false, uint32_t(frame), 0.0); }
     // MotionPlayer::SeekTime(double), poser_impl.inl:548-555 (main.cpp itself only uses SeekFrame)
-    void SeekTime(double time_seconds) {
-        mmdgpu_animation_t a = motion_.handle();
-        poser_.GetModel().context().check(mmdgpu_seek_time(poser_.frames(), &a, &time_seconds), "mmdgpu_seek_time");
-    }
+    void SeekTime(double time_seconds) { poser_.Seek(motion_.handle(), true, 0u, time_seconds); }
 
 private:
     const Motion& motion_;

@@ -63,9 +63,12 @@ __device__ __forceinline__ Bracket bracket_keys(const uint32_t* __restrict__ kf,
     return b;
 }
 
+// by_value: the (single) frame id / time arrives as a kernel argument instead of through F.frame_id / F.time_s - the
+// interactive path (one Poser, one frame per call) then needs no host-to-device copy at all.
 __global__ void __launch_bounds__(128) pose_sample_kernel(DevModel M, const DevAnim* __restrict__ anims, DevFrames F,
                                                           uint32_t write_untracked, uint32_t range_mode,
-                                                          uint32_t frame_stride, uint32_t has_anims, uint32_t time_mode) {
+                                                          uint32_t frame_stride, uint32_t has_anims, uint32_t time_mode,
+                                                          uint32_t by_value, uint32_t frame0, double time0) {
     const uint32_t slot = blockIdx.y;
     const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
     if (!has_anims && F.material_images && blockIdx.x == 0) {
@@ -78,7 +81,8 @@ __global__ void __launch_bounds__(128) pose_sample_kernel(DevModel M, const DevA
     const uint32_t inst = slot / F.n_frames;
     uint32_t frame = 0;
     double dframe = 0.0;
-    if (time_mode) dframe = F.time_s[slot] * 30.0;
+    if (time_mode) dframe = (by_value ? time0 : F.time_s[slot]) * 30.0;
+    else if (by_value) frame = frame0 + (range_mode ? (slot - inst * F.n_frames) * frame_stride : 0u);
     else frame = range_mode ? (F.frame_id[inst] + (slot - inst * F.n_frames) * frame_stride) : F.frame_id[slot];
     if (item < M.nb) {
         const uint32_t b = item;
@@ -1327,7 +1331,7 @@ __device__ __noinline__ SkinnedP skin_vertex_pair(const ulonglong2* __restrict__
 }
 
 template <int LAYOUT>
-__global__ void __launch_bounds__(kSkinThreads, 3) skin_pair_kernel(DevModel M, DevFrames F, uint32_t chunk, uint32_t n_chunks,
+__global__ void __launch_bounds__(kSkinThreads, kVertsPerThread == 4 ? 3 : 2) skin_pair_kernel(DevModel M, DevFrames F, uint32_t chunk, uint32_t n_chunks,
                                                                     float arg_neg_zero, float arg_one) {
     static_assert(G == 4, "two slot pairs per group");
     constexpr int NP = G / 2;                           // slot pairs per group
@@ -1347,12 +1351,11 @@ __global__ void __launch_bounds__(kSkinThreads, 3) skin_pair_kernel(DevModel M, 
     const uint32_t tile_nv = min(kTileVerts, M.nv - tile * kTileVerts);
 
     // ---- the tile's static streams: read once, kept in registers for every slot of this work item
-    static_assert(V == 4, "four storage positions per thread");
     const uint32_t v0 = tile * kTileVerts + tid * kVertsPerThread;
     float px[V], py[V], pz[V], nx[V], ny[V], nz[V];
     uint32_t ilo[V], ihi[V], orig[V];
     float4 wv[V];
-    {
+    if (V == 4) {
         const float4 PX = __ldg(reinterpret_cast<const float4*>(M.px + v0)), PY = __ldg(reinterpret_cast<const float4*>(M.py + v0)),
                      PZ = __ldg(reinterpret_cast<const float4*>(M.pz + v0)), NX = __ldg(reinterpret_cast<const float4*>(M.nx + v0)),
                      NY = __ldg(reinterpret_cast<const float4*>(M.ny + v0)), NZ = __ldg(reinterpret_cast<const float4*>(M.nz + v0));
@@ -1364,6 +1367,14 @@ __global__ void __launch_bounds__(kSkinThreads, 3) skin_pair_kernel(DevModel M, 
         const uint32_t o[4] = {OR.x & 0xFFFFu, OR.x >> 16, OR.y & 0xFFFFu, OR.y >> 16};
 #pragma unroll
         for (int j = 0; j < V; ++j) orig[j] = o[j];
+    } else {
+        const float2 PX = __ldg(reinterpret_cast<const float2*>(M.px + v0)), PY = __ldg(reinterpret_cast<const float2*>(M.py + v0)),
+                     PZ = __ldg(reinterpret_cast<const float2*>(M.pz + v0)), NX = __ldg(reinterpret_cast<const float2*>(M.nx + v0)),
+                     NY = __ldg(reinterpret_cast<const float2*>(M.ny + v0)), NZ = __ldg(reinterpret_cast<const float2*>(M.nz + v0));
+        px[0] = PX.x; px[1] = PX.y; py[0] = PY.x; py[1] = PY.y; pz[0] = PZ.x; pz[1] = PZ.y;
+        nx[0] = NX.x; nx[1] = NX.y; ny[0] = NY.x; ny[1] = NY.y; nz[0] = NZ.x; nz[1] = NZ.y;
+        const uint32_t OR = __ldg(reinterpret_cast<const uint32_t*>(M.orig + v0));
+        orig[0] = OR & 0xFFFFu; orig[1] = OR >> 16;
     }
 #pragma unroll
     for (int j = 0; j < V; j += 2) {
@@ -1578,12 +1589,15 @@ cudaError_t launch_math_kat(cudaStream_t st, int op, const float* in, uint32_t n
 // launchers
 // =================================================================================================
 cudaError_t launch_pose_sample(cudaStream_t st, const DevModel& M, const DevAnim* anims, const DevFrames& F,
-                               bool write_untracked, bool range_mode, uint32_t frame_stride, bool time_mode) {
+                               bool write_untracked, bool range_mode, uint32_t frame_stride, bool time_mode,
+                               const uint32_t* frame_by_value, const double* time_by_value) {
     const uint32_t items = M.nb + M.nm;
     if (items == 0 || F.n_slots == 0) return cudaSuccess;
     dim3 grid((items + 127) / 128, F.n_slots);
+    const bool by_value = frame_by_value || time_by_value;
     pose_sample_kernel<<<grid, 128, 0, st>>>(M, anims, F, write_untracked ? 1u : 0u, range_mode ? 1u : 0u, frame_stride,
-                                             anims ? 1u : 0u, time_mode ? 1u : 0u);
+                                             anims ? 1u : 0u, time_mode ? 1u : 0u, by_value ? 1u : 0u,
+                                             frame_by_value ? *frame_by_value : 0u, time_by_value ? *time_by_value : 0.0);
     return cudaGetLastError();
 }
 

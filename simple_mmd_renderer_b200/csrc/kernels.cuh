@@ -9,8 +9,11 @@ namespace mmdgpu {
 
 // K1: keyframe sampling for every (slot, bone) and (slot, morph).  anims == nullptr: write identity / zero
 // (Poser::ResetPosing's pose part).  write_untracked: also write identity / zero for items without a track.
+// frame_by_value / time_by_value: one frame id (first frame of a one-instance range) or one time handed over as a kernel
+// argument instead of through F.frame_id / F.time_s.
 cudaError_t launch_pose_sample(cudaStream_t st, const DevModel& M, const DevAnim* anims, const DevFrames& F,
-                               bool write_untracked, bool range_mode, uint32_t frame_stride, bool time_mode = false);
+                               bool write_untracked, bool range_mode, uint32_t frame_stride, bool time_mode = false,
+                               const uint32_t* frame_by_value = nullptr, const double* time_by_value = nullptr);
 // K2: waves [wave_lo, wave_hi) of the bone program; prologue = morph rates + reset + bone morphs.
 cudaError_t launch_hierarchy(cudaStream_t st, const DevModel& M, const DevFrames& F, uint32_t wave_lo, uint32_t wave_hi,
                              bool prologue);

@@ -466,12 +466,15 @@ mmdgpu_status do_seek(mmdgpu_frames* f, const mmdgpu_animation_t* per_instance, 
     if (!frames) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "frame id array is NULL");
     if (mmdgpu_status s = bind_anims(f, per_instance, st)) return s;
     const uint32_t n = range ? f->dev.n_instances : f->dev.n_slots;
-    CU(ctx, cudaMemcpyAsync(f->dev.frame_id, frames, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+    // one frame id travels as a kernel argument: no host-to-device copy on the interactive / single-clip bake path
+    const bool by_value = n == 1;
+    if (!by_value) CU(ctx, cudaMemcpyAsync(f->dev.frame_id, frames, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
     f->range_mode = range;
     f->frame_stride = stride;
     {
         Timed t(ctx, MMDGPU_KERNEL_POSE_SAMPLE, st);
-        CU(ctx, launch_pose_sample(st, f->model->dev, f->d_anims, f->dev, write_untracked, range, stride));
+        CU(ctx, launch_pose_sample(st, f->model->dev, f->d_anims, f->dev, write_untracked, range, stride, false,
+                                   by_value ? frames : nullptr, nullptr));
     }
     return MMDGPU_OK;
 }
@@ -1128,19 +1131,39 @@ MMDGPU_API mmdgpu_status mmdgpu_seek_frame_range(mmdgpu_frames_t f, const mmdgpu
     return do_seek(f, per_instance, first_frame_per_instance, true, frame_stride, false, f->ctx->stream);
 }
 
-MMDGPU_API mmdgpu_status mmdgpu_seek_time(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance, const double* time_per_slot) {
+static mmdgpu_status seek_time_common(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance, const double* time_per_slot,
+                                      bool write_untracked) {
     if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
     mmdgpu_context_t ctx = f->ctx;
     if (mmdgpu_status s = enter(ctx)) return s;
     if (!time_per_slot) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "time array is NULL");
     f->main_dirty = true;
     if (mmdgpu_status s = bind_anims(f, per_instance, ctx->stream)) return s;
-    CU(ctx, cudaMemcpyAsync(f->dev.time_s, time_per_slot, sizeof(double) * f->dev.n_slots, cudaMemcpyHostToDevice, ctx->stream));
+    const bool by_value = f->dev.n_slots == 1;
+    if (!by_value)
+        CU(ctx, cudaMemcpyAsync(f->dev.time_s, time_per_slot, sizeof(double) * f->dev.n_slots, cudaMemcpyHostToDevice, ctx->stream));
     {
         Timed t(ctx, MMDGPU_KERNEL_POSE_SAMPLE);
-        CU(ctx, launch_pose_sample(ctx->stream, f->model->dev, f->d_anims, f->dev, false, false, 1, true));
+        CU(ctx, launch_pose_sample(ctx->stream, f->model->dev, f->d_anims, f->dev, write_untracked, false, 1, true, nullptr,
+                                   by_value ? time_per_slot : nullptr));
     }
     return MMDGPU_OK;
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_seek_time(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance, const double* time_per_slot) {
+    return seek_time_common(f, per_instance, time_per_slot, false);
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_reset_and_seek_time(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance, const double* time_per_slot) {
+    return seek_time_common(f, per_instance, time_per_slot, true);
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_reset_and_seek_frame(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance,
+                                                     const uint32_t* frame_per_slot) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    if (mmdgpu_status s = enter(f->ctx)) return s;
+    f->main_dirty = true;
+    return do_seek(f, per_instance, frame_per_slot, false, 1, true, f->ctx->stream);
 }
 
 MMDGPU_API mmdgpu_status mmdgpu_set_bone_pose(mmdgpu_frames_t f, uint32_t slot, uint32_t bone, const float T[3],

@@ -201,6 +201,19 @@ class Frames:
             raise ValueError("one time per slot required")
         check(self.lib.mmdgpu_seek_time(self.h, self._anim_array(motions), _ptr(t)), self.ctx.h)
 
+    def reset_and_seek_frame(self, motions, frame_per_slot):
+        """reset_posing + seek_frame as one sampling launch (unanimated bones / morphs get identity / zero)."""
+        f = np.ascontiguousarray(frame_per_slot, np.uint32)
+        if f.size != self.n_slots:
+            raise ValueError("one frame id per slot required")
+        check(self.lib.mmdgpu_reset_and_seek_frame(self.h, self._anim_array(motions), _ptr(f)), self.ctx.h)
+
+    def reset_and_seek_time(self, motions, time_per_slot):
+        t = np.ascontiguousarray(time_per_slot, np.float64)
+        if t.size != self.n_slots:
+            raise ValueError("one time per slot required")
+        check(self.lib.mmdgpu_reset_and_seek_time(self.h, self._anim_array(motions), _ptr(t)), self.ctx.h)
+
     def set_bone_pose(self, slot: int, bone: int, translation, rotation):
         t = np.ascontiguousarray(translation, np.float32)
         r = np.ascontiguousarray(rotation, np.float32)

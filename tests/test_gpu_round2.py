@@ -243,3 +243,60 @@ def test_nested_ik_solves(ctx, n_slots):
         ref = orc.run_frame(f)
         assert_bitwise(one.bone_matrices(0), ref["skin"], f"step-wise frame {f} skinning matrices")
         assert_bitwise(one.download(0, capi.STREAM_POSITION), ref["pos"], f"step-wise frame {f} positions")
+
+
+def test_reset_and_seek_is_reset_then_seek(ctx):
+    """mmdgpu_reset_and_seek_frame / _time = reset_posing + seek in one sampling launch: untracked bones / morphs get
+    identity / zero, tracked ones their key frames - also after manual poses and a different clip had been set."""
+    cfg, model, motion = synth_case("tiny_full")
+    other = synth.make_motion(cfg, model, instance=3)
+    m = Model(ctx, model)
+    a, b = Motion(m, motion), Motion(m, other)
+    two, one = Frames(m, 1, 3), Frames(m, 1, 3)
+    frames = [4, 55, 89]
+    q = np.asarray([0.5, 0.5, 0.5, 0.5], np.float32)
+    for fr in (two, one):
+        fr.reset_posing(); fr.seek_frame(b, [9, 9, 9])
+        for s in range(3):
+            fr.set_bone_pose(s, 1, [1, 2, 3], q)
+            fr.set_morph_pose(s, 0, 0.7)
+    two.reset_posing(); two.seek_frame(a, frames)
+    one.reset_and_seek_frame(a, frames)
+    for fr in (two, one):
+        fr.pre_physics_posing(); fr.post_physics_posing(); fr.deform()
+    for k in range(3):
+        assert_bitwise(one.bone_poses(k), two.bone_poses(k), f"slot {k} poses")
+        assert_bitwise(one.morph_rates(k), two.morph_rates(k), f"slot {k} rates")
+        assert_bitwise(one.download(k, capi.STREAM_POSITION), two.download(k, capi.STREAM_POSITION), f"slot {k} positions")
+    times = [0.25, 1.0123, 2.9]
+    two.reset_posing(); two.seek_time(a, times)
+    one.reset_and_seek_time(a, times)
+    for k in range(3):
+        assert_bitwise(one.bone_poses(k), two.bone_poses(k), f"slot {k} poses (time)")
+    # single-slot objects pass the frame id / time as a kernel argument: same results as the array path
+    s1 = Frames(m, 1, 1)
+    orc = _oracle(model, motion)
+    for f in (0, 17, 90):
+        s1.update(a, [f])
+        assert_bitwise(s1.download(0, capi.STREAM_POSITION), orc.run_frame(f)["pos"], f"by-value frame {f}")
+    s1.reset_and_seek_time(a, [1.5]); s1.pre_physics_posing(); s1.post_physics_posing(); s1.deform()
+    assert_bitwise(s1.download(0, capi.STREAM_POSITION), orc.run_time(1.5)["pos"], "by-value time 1.5 s")
+
+
+def test_cxx_shim_replays_recorded_calls_exactly(ctx, tmp_path):
+    """include/mmdgpu.hpp records ResetPosing / SeekFrame / PrePhysicsPosing and fuses main.cpp's sequence; every other
+    continuation must behave as if each call had been issued when it was made (tests/cxx/shim_sequences.cc)."""
+    import subprocess
+    import pmxio
+    from conftest import ROOT
+    from simple_mmd_renderer_b200 import lib
+    cfg, model, motion = synth_case("tiny_full")          # has post-physics bones, IK, bone / group morphs
+    (tmp_path / "m.pmx").write_bytes(pmxio.write_pmx(model))
+    (tmp_path / "m.vmd").write_bytes(pmxio.write_vmd(motion))
+    exe = tmp_path / "shim_sequences"
+    r = subprocess.run(["g++", "-std=c++14", "-O1", "-Wall", "-Wextra", f"-I{ROOT}/include", f"{ROOT}/tests/cxx/shim_sequences.cc",
+                        lib.SO_PATH, "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), str(tmp_path / "m.pmx"), str(tmp_path / "m.vmd")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("same") == 12 and "DIFFERENT" not in r.stdout, r.stdout

@@ -364,6 +364,11 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_download(mmdgpu_frames_t frames, uint32_t
  * Completion on the host: mmdgpu_frames_wait_downloads (this object's copies only) or mmdgpu_context_synchronize. */
 MMDGPU_API mmdgpu_status mmdgpu_frames_download_async(mmdgpu_frames_t frames, uint32_t first_slot, uint32_t n_slots,
                                                       mmdgpu_stream_id id, void* pinned_host_dst, size_t bytes);
+/* Positions then normals of ONE slot into one pinned block of 2 x n_vertices x 12 bytes (Poser::pose_image.coordinates and
+ * .normals, L/motion/poser.inl:17-20, behind each other).  A one-slot frames object - an interactive Poser - keeps the
+ * two planes adjacent on the device, so this is a single transfer.  Same ordering rules as mmdgpu_frames_download_async. */
+MMDGPU_API mmdgpu_status mmdgpu_frames_download_pair_async(mmdgpu_frames_t frames, uint32_t slot, void* pinned_host_dst,
+                                                           size_t bytes);
 /* Block the calling thread until every mmdgpu_frames_download_async issued for this frames object has landed in host
  * memory.  Does not wait for compute or for copies of other frames objects: a bake alternating two frames objects
  * hands window k to its sink while window k+1 is being evaluated (simple_mmd_renderer_b200/shard.py BakeDriver). */

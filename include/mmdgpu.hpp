@@ -150,22 +150,21 @@ public:
           model_(model),
           layout_(layout) {
         check(mmdgpu_frames_create(model.context().handle(), model.handle(), 1, 1, layout, &frames_), "mmdgpu_frames_create");
+        // one page-locked block: coordinates, then normals (filled by a single transfer, mmdgpu_frames_download_pair_async)
         const size_t bytes = model.GetVertexNum() * sizeof(Vector3f);
-        void *a = nullptr, *b = nullptr;
-        if (mmdgpu_host_alloc(bytes, &a) != MMDGPU_OK || mmdgpu_host_alloc(bytes, &b) != MMDGPU_OK) {
-            mmdgpu_host_free(a);
+        void* a = nullptr;
+        if (mmdgpu_host_alloc(2 * bytes, &a) != MMDGPU_OK) {
             mmdgpu_frames_destroy(frames_);
             throw Error(MMDGPU_ERR_OOM, "page-locked pose_image allocation failed");
         }
         pose_image.coordinates.host_ = static_cast<Vector3f*>(a);
-        pose_image.normals.host_ = static_cast<Vector3f*>(b);
+        pose_image.normals.host_ = static_cast<Vector3f*>(a) + model.GetVertexNum();
         ResetPosing();
         Deform();
     }
     ~Poser() {
         mmdgpu_frames_destroy(frames_);
-        mmdgpu_host_free(pose_image.coordinates.host_);
-        mmdgpu_host_free(pose_image.normals.host_);
+        mmdgpu_host_free(pose_image.coordinates.host_);   // the block holds both mirrors
     }
     Poser(const Poser&) = delete;
     Poser& operator=(const Poser&) = delete;
@@ -279,13 +278,13 @@ private:
     void Fetch() {
         Flush();
         if (image_valid_) return;
-        const size_t bytes = model_.GetVertexNum() * sizeof(Vector3f);
-        check(mmdgpu_frames_download_async(frames_, 0, 1, MMDGPU_STREAM_POSITION, pose_image.coordinates.host_, bytes),
-              "mmdgpu_frames_download_async");
-        check(mmdgpu_frames_download_async(frames_, 0, 1, MMDGPU_STREAM_NORMAL, pose_image.normals.host_, bytes),
-              "mmdgpu_frames_download_async");
-        check(mmdgpu_context_join_downloads(model_.context().handle()), "mmdgpu_context_join_downloads");
-        model_.context().Synchronize();
+        if (layout_ == MMDGPU_LAYOUT_SOA_POS_NRM) {
+            const size_t bytes = model_.GetVertexNum() * sizeof(Vector3f);
+            check(mmdgpu_frames_download_pair_async(frames_, 0, pose_image.coordinates.host_, 2 * bytes), "mmdgpu_frames_download_pair_async");
+            check(mmdgpu_frames_wait_downloads(frames_), "mmdgpu_frames_wait_downloads");   // this copy only, not the whole context
+        } else {
+            throw Error(MMDGPU_ERR_INVALID_ARG, "pose_image needs the SoA layout; interleaved Posers use DownloadInterleaved or a bound output");
+        }
         image_valid_ = true;
     }
     Model& model_;

@@ -1073,8 +1073,12 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_create(mmdgpu_context_t ctx, mmdgpu_model
     f->select(0);
     CU(ctx, cudaEventCreateWithFlags(&f->ev_dl, cudaEventDisableTiming));
     if (layout == MMDGPU_LAYOUT_SOA_POS_NRM) {
-        CU(ctx, dalloc(f->mem, &F.out_pos, ns * M.nv_pad * 3, false, st));
-        CU(ctx, dalloc(f->mem, &F.out_nrm, ns * M.nv_pad * 3, false, st));
+        // one allocation, position planes then normal planes: a one-slot object (an interactive Poser) can hand both to the
+        // host with a single copy (mmdgpu_frames_download_pair_async)
+        CU(ctx, dalloc(f->mem, &F.out_pos, 2 * ns * M.nv_pad * 3, false, st));
+        // (the skinning kernel stores exactly nv vertices per slot, so a single slot's normals may start right behind its
+        // nv positions when that keeps them 16-byte aligned for the bulk copies)
+        F.out_nrm = F.out_pos + ((ns == 1 && M.nv % 4 == 0) ? size_t(M.nv) * 3 : ns * M.nv_pad * 3);
         if (M.extensions) CU(ctx, dalloc(f->mem, &F.out_uv, ns * M.nv_pad, false, st));
     } else {
         CU(ctx, dalloc(f->mem, &F.out_inter, ns * M.nv_pad * 2, false, st));
@@ -1327,6 +1331,33 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_download_async(mmdgpu_frames_t f, uint32_
     else
         CU(ctx, cudaMemcpy2DAsync(pinned_host_dst, v.slot_bytes, src, v.slot_stride, v.slot_bytes, n_slots,
                                   cudaMemcpyDeviceToHost, ctx->dl_stream));
+    CU(ctx, cudaEventRecord(f->ev_dl, ctx->dl_stream));
+    f->dl_pending = f->dl_recorded = true;
+    return MMDGPU_OK;
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_frames_download_pair_async(mmdgpu_frames_t f, uint32_t slot, void* pinned_host_dst, size_t bytes) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    mmdgpu_context_t ctx = f->ctx;
+    if (mmdgpu_status s = enter(ctx)) return s;
+    if (!pinned_host_dst) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "host_dst is NULL");
+    if (f->layout != MMDGPU_LAYOUT_SOA_POS_NRM) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "frames were created with the interleaved layout");
+    if (slot >= f->dev.n_slots) return set_err(ctx, MMDGPU_ERR_BAD_INDEX, "slot out of range");
+    const DevModel& M = f->model->dev;
+    const size_t plane = size_t(M.nv) * 12;
+    if (bytes != 2 * plane) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "bytes must equal positions + normals of one slot");
+    if (bytes == 0) return MMDGPU_OK;
+    const char* pos = reinterpret_cast<const char*>(f->dev.out_pos) + size_t(slot) * f->dev.pos_stride * 4;
+    const char* nrm = reinterpret_cast<const char*>(f->dev.out_nrm) + size_t(slot) * f->dev.nrm_stride * 4;
+    CU(ctx, cudaEventRecord(ctx->dl_event, ctx->stream));
+    CU(ctx, cudaStreamWaitEvent(ctx->dl_stream, ctx->dl_event, 0));
+    char* dst = static_cast<char*>(pinned_host_dst);
+    if (nrm == pos + plane)   // one-slot object with unpadded planes next to each other: one transfer
+        CU(ctx, cudaMemcpyAsync(dst, pos, bytes, cudaMemcpyDeviceToHost, ctx->dl_stream));
+    else {
+        CU(ctx, cudaMemcpyAsync(dst, pos, plane, cudaMemcpyDeviceToHost, ctx->dl_stream));
+        CU(ctx, cudaMemcpyAsync(dst + plane, nrm, plane, cudaMemcpyDeviceToHost, ctx->dl_stream));
+    }
     CU(ctx, cudaEventRecord(f->ev_dl, ctx->dl_stream));
     f->dl_pending = f->dl_recorded = true;
     return MMDGPU_OK;

@@ -291,7 +291,7 @@ def test_cxx_shim_replays_recorded_calls_exactly(ctx, tmp_path):
     from conftest import ROOT
     from simple_mmd_renderer_b200 import lib
     cfg, model, motion = synth_case("tiny_full")          # has post-physics bones, IK, bone / group morphs
-    (tmp_path / "m.pmx").write_bytes(pmxio.write_pmx(model))
+    (tmp_path / "m.pmx").write_bytes(pmxio.write_pmx(model, version=2.1))      # QDEF-tagged vertices need a 2.1 container
     (tmp_path / "m.vmd").write_bytes(pmxio.write_vmd(motion))
     exe = tmp_path / "shim_sequences"
     r = subprocess.run(["g++", "-std=c++14", "-O1", "-Wall", "-Wextra", f"-I{ROOT}/include", f"{ROOT}/tests/cxx/shim_sequences.cc",

@@ -119,6 +119,18 @@ int main() {
     add("lds64 12 bones random, stride 6", 3, [&](int l) { return 6 * rnd12[l]; });
     add("lds64 12 bones sorted, stride 6", 3, [&](int l) { return 6 * rnd12s[l]; });
     add("lds64 uniform", 3, [](int) { return 0; });
+    // planar palette for slot PAIRS: one element of bone b for two slots = one 8-byte cell at float2 index b
+    add("lds64 planar: 7 bones random", 3, [&](int l) { return rnd7[l]; });
+    add("lds64 planar: 12 bones random", 3, [&](int l) { return rnd12[l]; });
+    add("lds64 planar: 12 bones sorted", 3, [&](int l) { return rnd12s[l]; });
+    add("lds64 planar: 16 bones (lane % 16)", 3, [](int l) { return l % 16; });
+    add("lds64 planar: 24 bones random", 3, [&](int l) { return rnd24[l]; });
+    add("lds64 planar: lane / 2", 3, [](int l) { return l / 2; });
+    // the same for LDS.128 planar (two elements of a bone for two slots in one 16-byte cell at float4 index b)
+    add("lds128 planar: 7 bones random", 0, [&](int l) { return rnd7[l]; });
+    add("lds128 planar: 12 bones random", 0, [&](int l) { return rnd12[l]; });
+    add("lds128 planar: lane % 4", 0, [](int l) { return l % 4; });
+    add("lds128 planar: 4 bones random", 0, [&](int l) { return rnd12[l] % 4; });
     // ---- LDS.32, index in words (planar palette: one element of bone b at word b)
     add("lds32 consecutive", 1, [](int l) { return l; });
     add("lds32 planar: 12 bones random", 1, [&](int l) { return rnd12[l]; });

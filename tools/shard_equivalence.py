@@ -62,6 +62,44 @@ def main():
         print(f"bake: {world}-GPU frame-range shards gathered over NCCL == 1-GPU bake bit-for-bit: {same}; == CPU oracle on sampled frames: {exact}")
         ok = ok and same and exact
 
+    # ---- bake with the FUSED gather: every rank's skinning kernel stores its windows straight into rank 0's memory
+    #      (mmdgpu_frames_bind_output on a CUDA-IPC mapping of the root's buffer, NVLink), one small all-reduce per window
+    try:
+        nv = m.n_vertices
+        n_rounds = shard.n_windows(n_frames, world, window)
+        peer = shard.PeerWindows(ctx, world, rank, n_rounds, window * nv * 3)       # one buffer per round: nothing is reused
+        flag = torch.zeros(1, dtype=torch.int32, device=f"cuda:{local}")
+        stream = torch.cuda.current_stream()
+        for k in range(n_rounds):
+            if k < len(chunks):
+                ppos, pnrm = peer.slot(k, rank)
+                fr.bind_output(capi.STREAM_POSITION, ppos, nv * 12)
+                fr.bind_output(capi.STREAM_NORMAL, pnrm, nv * 12)
+                fr.update_range(a, [chunks[k][0]], 1)
+            ctx.synchronize()
+            dist.all_reduce(flag)
+        fr.bind_output(capi.STREAM_POSITION, None)
+        fr.bind_output(capi.STREAM_NORMAL, None)
+        torch.cuda.synchronize()
+        if rank == 0:
+            same = True
+            single_n = np.stack([single.download(k, capi.STREAM_NORMAL) for k in range(n_frames)])
+            for r in range(world):
+                rlo, rhi = shard.split_range(n_frames, world, r)
+                for k, (first, n_valid) in enumerate(shard.bake_windows(rlo, rhi, window)):
+                    gp = peer.tensor(k, r, 0, (window, nv, 3))[:n_valid].cpu().numpy()
+                    gn = peer.tensor(k, r, 1, (window, nv, 3))[:n_valid].cpu().numpy()
+                    same = same and bool((gp.view(np.uint32) == alone[first:first + n_valid].view(np.uint32)).all())
+                    same = same and bool((gn.view(np.uint32) == single_n[first:first + n_valid].view(np.uint32)).all())
+            print(f"bake, fused gather: {world} ranks' skinning kernels storing into rank 0's memory == 1-GPU bake bit-for-bit "
+                  f"(positions and normals): {same}")
+            ok = ok and same
+        dist.barrier()
+        peer.close()
+    except Exception as ex:   # CUDA IPC is a platform capability
+        if rank == 0:
+            print(f"bake, fused gather: unavailable here ({type(ex).__name__}: {ex})")
+
     # ---- crowd by instance
     n_inst = 24
     clips = [synth.make_motion(cfg, model, instance=i) for i in range(n_inst)]

@@ -10,7 +10,7 @@ moves (3.07 GB per step per GPU on C3).
 
 Variants timed: one 1-D copy of the whole buffer; the same bytes as `--pieces` 1-D copies (one per slot, what a
 pitched 2-D copy degenerates to); a pitched cudaMemcpy2DAsync (what mmdgpu_frames_download_async used in round 1).
-With --numa the rank first binds itself (CPU affinity + preferred memory node) to the NUMA node `nvidia-smi topo`
+With --bind-numa the rank first binds itself (CPU affinity + preferred memory node) to the NUMA node `nvidia-smi topo`
 reports for its GPU, so that the pinned buffer is node-local.
 """
 from __future__ import annotations
@@ -30,7 +30,7 @@ def main():
     ap.add_argument("--bytes", type=int, default=3_072_000_000)
     ap.add_argument("--pieces", type=int, default=128)
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--numa", action="store_true")
+    ap.add_argument("--bind-numa", dest="numa", action="store_true")
     args = ap.parse_args()
 
     import torch

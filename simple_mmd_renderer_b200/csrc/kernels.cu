@@ -1330,8 +1330,8 @@ __device__ __noinline__ SkinnedP skin_vertex_pair(const ulonglong2* __restrict__
     return r;
 }
 
-template <int LAYOUT>
-__global__ void __launch_bounds__(kSkinThreads, kVertsPerThread == 4 ? 3 : 2) skin_pair_kernel(DevModel M, DevFrames F, uint32_t chunk, uint32_t n_chunks,
+template <int LAYOUT, int MIN_CTAS>
+__global__ void __launch_bounds__(kSkinThreads, MIN_CTAS) skin_pair_kernel(DevModel M, DevFrames F, uint32_t chunk, uint32_t n_chunks,
                                                                     float arg_neg_zero, float arg_one) {
     static_assert(G == 4, "two slot pairs per group");
     constexpr int NP = G / 2;                           // slot pairs per group
@@ -1664,8 +1664,9 @@ cudaError_t prepare_skin_kernels(const DevModel& M) {
     if ((e = skin_opt_in<I32, false, true>(limit)) != cudaSuccess) return e;
     if ((e = skin_opt_in<SOA, false, false>(limit)) != cudaSuccess) return e;
     if ((e = skin_opt_in<I32, false, false>(limit)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(skin_pair_kernel<SOA>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit)) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(skin_pair_kernel<I32>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+    if ((e = cudaFuncSetAttribute(skin_pair_kernel<SOA, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(skin_pair_kernel<I32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(skin_pair_kernel<I32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
 }
 
 cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, int layout, uint32_t slots_per_cta) {
@@ -1686,8 +1687,14 @@ cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, 
     if (M.extensions) MMDGPU_LAUNCH_SKIN(true, false);
     else if (M.global_palette) MMDGPU_LAUNCH_SKIN(false, true);
     else if (scalar) MMDGPU_LAUNCH_SKIN(false, false);
-    else if (soa) skin_pair_kernel<SOA><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks, -0.0f, 1.0f);
-    else skin_pair_kernel<I32><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks, -0.0f, 1.0f);
+    else if (soa) skin_pair_kernel<SOA, 3><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks, -0.0f, 1.0f);
+    else {
+        // the interleaved layout has no staging tiles (11 KB of shared memory per CTA): registers alone decide residency.
+        // MMDGPU_I32_CTAS=4 (experiment knob): 128 registers with a few spills, 16 warps per SM instead of 12
+        static const bool four = [] { const char* e = std::getenv("MMDGPU_I32_CTAS"); return e && e[0] == '4'; }();
+        if (four) skin_pair_kernel<I32, 4><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks, -0.0f, 1.0f);
+        else skin_pair_kernel<I32, 3><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks, -0.0f, 1.0f);
+    }
 #undef MMDGPU_LAUNCH_SKIN
     return cudaGetLastError();
 }

@@ -172,7 +172,16 @@ class Frames:
         self.h = h
 
     # ---- libmmd-named entry points, batched
+    def anim_array(self, motions):
+        """Marshal one clip per instance once; the result can be passed wherever `motions` is accepted (a crowd step that
+        re-marshals 512 handles per call spends more time in ctypes than on the device)."""
+        return self._anim_array(motions)
+
     def _anim_array(self, motions):
+        if isinstance(motions, C.Array):
+            if len(motions) != self.n_instances:
+                raise ValueError("one motion per instance required")
+            return motions
         if isinstance(motions, Motion):
             motions = [motions] * self.n_instances
         if len(motions) != self.n_instances:

@@ -63,82 +63,108 @@ __device__ __forceinline__ Bracket bracket_keys(const uint32_t* __restrict__ kf,
     return b;
 }
 
-// by_value: the (single) frame id / time arrives as a kernel argument instead of through F.frame_id / F.time_s - the
-// interactive path (one Poser, one frame per call) then needs no host-to-device copy at all.
-__global__ void __launch_bounds__(128) pose_sample_kernel(DevModel M, const DevAnim* __restrict__ anims, DevFrames F,
-                                                          uint32_t write_untracked, uint32_t range_mode,
-                                                          uint32_t frame_stride, uint32_t has_anims, uint32_t time_mode,
-                                                          uint32_t by_value, uint32_t frame0, double time0) {
+// How the slots of a launch get their frame.  by_value: the (single) frame id / time arrives as a kernel argument instead
+// of through F.frame_id / F.time_s - the interactive path (one Poser, one frame per call) then needs no host-to-device copy.
+struct SampleArgs {
+    const DevAnim* anims;      // [n_instances], nullptr: ResetPosing (identity / zero everywhere)
+    uint32_t write_untracked;  // also write identity / zero for bones and morphs the clip does not animate (ResetPosing + SeekFrame)
+    uint32_t range_mode, frame_stride, time_mode, by_value, frame0;
+    double time0;
+};
+struct SlotFrame { uint32_t inst, frame; double dframe; };
+__device__ __forceinline__ SlotFrame frame_of_slot(const DevFrames& F, const SampleArgs& A, uint32_t slot) {
+    SlotFrame s{slot / F.n_frames, 0u, 0.0};
+    if (A.time_mode) s.dframe = (A.by_value ? A.time0 : F.time_s[slot]) * 30.0;
+    else if (A.by_value) s.frame = A.frame0 + (A.range_mode ? (slot - s.inst * F.n_frames) * A.frame_stride : 0u);
+    else s.frame = A.range_mode ? (F.frame_id[s.inst] + (slot - s.inst * F.n_frames) * A.frame_stride) : F.frame_id[slot];
+    return s;
+}
+// Motion::GetBonePose for model bone b; returns false if the pose in the Poser must be left as it is (bone not in the clip
+// and no reset requested)
+__device__ __forceinline__ bool sample_bone(const SampleArgs& SA, const SlotFrame& sf, uint32_t b, float4& T, float4& R) {
+    T = make_float4(0.f, 0.f, 0.f, 0.f); R = make_float4(0.f, 0.f, 0.f, 1.f);
+    bool tracked = false;
+    if (SA.anims) {
+        const DevAnim A = SA.anims[sf.inst];
+        tracked = A.bone_tracked[b] != 0;
+        const uint32_t n = A.bone_key_count[b];
+        if (tracked && n > 0) {
+            const uint32_t k0 = A.bone_key_begin[b];
+            const Bracket br = bracket_keys(A.key_frame + k0, n, SA.time_mode != 0, sf.frame, sf.dframe);
+            if (br.use != 0xFFFFFFFFu) {
+                T = A.key_T[k0 + br.use];
+                R = A.key_R[k0 + br.use];
+            } else {
+                const float bary = br.bary;
+                const float4 lT = A.key_T[k0 + br.l], rT = A.key_T[k0 + br.r];
+                const float4 lR = A.key_R[k0 + br.l], rR = A.key_R[k0 + br.r];
+                const uint4 cv = A.key_curve[k0 + br.l];  // curves of the LEFT key (motion_impl.inl:302-312)
+                float lam = bezier_at(A.tables, cv.x, bary);
+                T.x = lT.x * (1 - lam) + rT.x * lam;
+                lam = bezier_at(A.tables, cv.y, bary);
+                T.y = lT.y * (1 - lam) + rT.y * lam;
+                lam = bezier_at(A.tables, cv.z, bary);
+                T.z = lT.z * (1 - lam) + rT.z * lam;
+                const float l_ = bezier_at(A.tables, cv.w, bary);
+                R = v4_nlerp(lR, rR, l_);
+            }
+            T.w = 0.f;
+        }
+    }
+    return tracked || SA.write_untracked;
+}
+// Motion::GetMorphPose for model morph m
+__device__ __forceinline__ bool sample_morph(const SampleArgs& SA, const SlotFrame& sf, uint32_t m, float& w) {
+    w = 0.0f;
+    bool tracked = false;
+    if (SA.anims) {
+        const DevAnim A = SA.anims[sf.inst];
+        tracked = A.morph_tracked[m] != 0;
+        const uint32_t n = A.morph_key_count[m];
+        if (tracked && n > 0) {
+            const uint32_t k0 = A.morph_key_begin[m];
+            const float* kw = A.mkey_weight + k0;
+            const Bracket br = bracket_keys(A.mkey_frame + k0, n, SA.time_mode != 0, sf.frame, sf.dframe);
+            if (br.use != 0xFFFFFFFFu) w = kw[br.use];
+            else {
+                const float lam = br.bary;  // default-constructed Bezier is linear (math_impl.inl:1350-1354)
+                w = kw[br.l] * (1 - lam) + kw[br.r] * lam;
+            }
+        }
+    }
+    return tracked || SA.write_untracked;
+}
+
+// out-of-line copies for the hierarchy kernel's prologue: sampling runs once per bone there, and inlined it would take
+// registers from the wave program and the IK solver
+__device__ __noinline__ bool sample_bone_call(const SampleArgs* SA, SlotFrame sf, uint32_t b, float4* T, float4* R) {
+    return sample_bone(*SA, sf, b, *T, *R);
+}
+__device__ __noinline__ bool sample_morph_call(const SampleArgs* SA, SlotFrame sf, uint32_t m, float* w) {
+    return sample_morph(*SA, sf, m, *w);
+}
+
+__global__ void __launch_bounds__(128) pose_sample_kernel(DevModel M, DevFrames F, SampleArgs SA) {
     const uint32_t slot = blockIdx.y;
     const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
-    if (!has_anims && F.material_images && blockIdx.x == 0) {
+    if (!SA.anims && F.material_images && blockIdx.x == 0) {
         // ResetPosing: all rates are zero, so the material images (extension) are their initial 1 / 0
         const uint32_t n = M.n_materials * 2 * MMDGPU_MATERIAL_FIELDS;
         float* mi = F.material_images + (size_t)slot * n;
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) mi[i] = ((i / MMDGPU_MATERIAL_FIELDS) & 1u) ? 0.0f : 1.0f;
     }
     if (item >= M.nb + M.nm) return;
-    const uint32_t inst = slot / F.n_frames;
-    uint32_t frame = 0;
-    double dframe = 0.0;
-    if (time_mode) dframe = (by_value ? time0 : F.time_s[slot]) * 30.0;
-    else if (by_value) frame = frame0 + (range_mode ? (slot - inst * F.n_frames) * frame_stride : 0u);
-    else frame = range_mode ? (F.frame_id[inst] + (slot - inst * F.n_frames) * frame_stride) : F.frame_id[slot];
+    const SlotFrame sf = frame_of_slot(F, SA, slot);
     if (item < M.nb) {
-        const uint32_t b = item;
-        float4 T = make_float4(0.f, 0.f, 0.f, 0.f), R = make_float4(0.f, 0.f, 0.f, 1.f);
-        bool tracked = false;
-        if (has_anims) {
-            const DevAnim A = anims[inst];
-            tracked = A.bone_tracked[b] != 0;
-            const uint32_t n = A.bone_key_count[b];
-            if (tracked && n > 0) {
-                const uint32_t k0 = A.bone_key_begin[b];
-                const Bracket br = bracket_keys(A.key_frame + k0, n, time_mode != 0, frame, dframe);
-                if (br.use != 0xFFFFFFFFu) {
-                    T = A.key_T[k0 + br.use];
-                    R = A.key_R[k0 + br.use];
-                } else {
-                    const float bary = br.bary;
-                    const float4 lT = A.key_T[k0 + br.l], rT = A.key_T[k0 + br.r];
-                    const float4 lR = A.key_R[k0 + br.l], rR = A.key_R[k0 + br.r];
-                    const uint4 cv = A.key_curve[k0 + br.l];  // curves of the LEFT key (motion_impl.inl:302-312)
-                    float lam = bezier_at(A.tables, cv.x, bary);
-                    T.x = lT.x * (1 - lam) + rT.x * lam;
-                    lam = bezier_at(A.tables, cv.y, bary);
-                    T.y = lT.y * (1 - lam) + rT.y * lam;
-                    lam = bezier_at(A.tables, cv.z, bary);
-                    T.z = lT.z * (1 - lam) + rT.z * lam;
-                    const float l_ = bezier_at(A.tables, cv.w, bary);
-                    R = v4_nlerp(lR, rR, l_);
-                }
-                T.w = 0.f;
-            }
-        }
-        if (tracked || write_untracked) {
-            F.poseT[(size_t)slot * M.nb + b] = T;
-            F.poseR[(size_t)slot * M.nb + b] = R;
+        float4 T, R;
+        if (sample_bone(SA, sf, item, T, R)) {
+            F.poseT[(size_t)slot * M.nb + item] = T;
+            F.poseR[(size_t)slot * M.nb + item] = R;
         }
     } else {
         const uint32_t m = item - M.nb;
-        float w = 0.0f;
-        bool tracked = false;
-        if (has_anims) {
-            const DevAnim A = anims[inst];
-            tracked = A.morph_tracked[m] != 0;
-            const uint32_t n = A.morph_key_count[m];
-            if (tracked && n > 0) {
-                const uint32_t k0 = A.morph_key_begin[m];
-                const float* kw = A.mkey_weight + k0;
-                const Bracket br = bracket_keys(A.mkey_frame + k0, n, time_mode != 0, frame, dframe);
-                if (br.use != 0xFFFFFFFFu) w = kw[br.use];
-                else {
-                    const float lam = br.bary;  // default-constructed Bezier is linear (math_impl.inl:1350-1354)
-                    w = kw[br.l] * (1 - lam) + kw[br.r] * lam;
-                }
-            }
-        }
-        if (tracked || write_untracked) F.rate[(size_t)slot * M.nm + m] = w;
+        float w;
+        if (sample_morph(SA, sf, m, w)) F.rate[(size_t)slot * M.nm + m] = w;
     }
 }
 
@@ -611,9 +637,12 @@ __host__ __device__ inline size_t hier_cta_smem_bytes(uint32_t nb, uint32_t n_li
            (((size_t)n_ops + n_waves + 1 + 3) & ~(size_t)3) * sizeof(uint32_t);
 }
 
+// sample != 0 (fused updates): the CTA samples its slot's key frames itself (K1's work) instead of reading what a
+// separate sampling launch left in global memory - one launch and one global round trip fewer per update.
 template <bool NEST>
 __global__ void __launch_bounds__(kHierCtaThreads) hierarchy_cta_kernel(DevModel M, DevFrames F, uint32_t wave_lo,
-                                                                        uint32_t wave_hi, uint32_t prologue) {
+                                                                        uint32_t wave_hi, uint32_t prologue, uint32_t sample,
+                                                                        SampleArgs SA) {
     extern __shared__ __align__(16) float4 hsm[];
     const uint32_t slot = blockIdx.x, tid = threadIdx.x, nb = M.nb, nthreads = blockDim.x;
     float4* s_poseR = hsm;
@@ -649,10 +678,32 @@ __global__ void __launch_bounds__(kHierCtaThreads) hierarchy_cta_kernel(DevModel
     S.palette = F.palette + (size_t)slot * nb * 3;
     S.pal_ext = F.pal_ext ? F.pal_ext + (size_t)slot * nb * 2 : nullptr;
 
-    // ---- sampled poses of every bone (written by K1 / SetBonePose), the static bone records and the program
-    for (uint32_t b = tid; b < nb; b += nthreads) {
-        s_poseR[b] = F.poseR[(size_t)slot * nb + b];
-        s_poseT[b] = F.poseT[(size_t)slot * nb + b];
+    // ---- poses of every bone: sampled here (fused updates) or as K1 / SetBonePose left them; the static bone records
+    //      and the program
+    if (sample) {
+        const SlotFrame sf = frame_of_slot(F, SA, slot);
+        for (uint32_t b = tid; b < nb; b += nthreads) {
+            float4 T, R;
+            if (sample_bone_call(&SA, sf, b, &T, &R)) {
+                F.poseT[(size_t)slot * nb + b] = T;      // kept in global memory for the download entry points
+                F.poseR[(size_t)slot * nb + b] = R;
+            } else {
+                T = F.poseT[(size_t)slot * nb + b];
+                R = F.poseR[(size_t)slot * nb + b];
+            }
+            s_poseR[b] = R;
+            s_poseT[b] = T;
+        }
+        for (uint32_t m = tid; m < M.nm; m += nthreads) {
+            float w;
+            if (sample_morph_call(&SA, sf, m, &w)) F.rate[(size_t)slot * M.nm + m] = w;
+        }
+        __syncthreads();   // the morph rates just written are read below by other threads of this CTA
+    } else {
+        for (uint32_t b = tid; b < nb; b += nthreads) {
+            s_poseR[b] = F.poseR[(size_t)slot * nb + b];
+            s_poseT[b] = F.poseT[(size_t)slot * nb + b];
+        }
     }
     {
         const float4* gb = reinterpret_cast<const float4*>(M.bones);
@@ -1470,6 +1521,7 @@ __global__ void __launch_bounds__(kSkinThreads, MIN_CTAS) skin_pair_kernel(DevMo
             const f2 PX2 = pk2(px[j], px[j]), PY2 = pk2(py[j], py[j]), PZ2 = pk2(pz[j], pz[j]);
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
+                if ((uint32_t)(2 * p) >= n_live) continue;   // a partial last group (a one-slot Poser): nothing to store for this pair
                 // coordinate + vertex_image (poser_impl.inl:407)
                 const SkinnedP r = skin_vertex_pair(pal + (size_t)p * 2u * pal4, pal4, ilo[j], ihi[j], wv[j], add2(PX2, IX[p], K),
                                                     add2(PY2, IY[p], K), add2(PZ2, IZ[p], K), nx[j], ny[j], nz[j], K.nz, K.one);
@@ -1588,30 +1640,44 @@ cudaError_t launch_math_kat(cudaStream_t st, int op, const float* in, uint32_t n
 // =================================================================================================
 // launchers
 // =================================================================================================
-cudaError_t launch_pose_sample(cudaStream_t st, const DevModel& M, const DevAnim* anims, const DevFrames& F,
-                               bool write_untracked, bool range_mode, uint32_t frame_stride, bool time_mode,
-                               const uint32_t* frame_by_value, const double* time_by_value) {
+static SampleArgs make_sample_args(const SampleSpec& sp) {
+    SampleArgs a{};
+    a.anims = sp.anims;
+    a.write_untracked = sp.write_untracked ? 1u : 0u;
+    a.range_mode = sp.range_mode ? 1u : 0u;
+    a.frame_stride = sp.frame_stride;
+    a.time_mode = sp.time_mode ? 1u : 0u;
+    a.by_value = (sp.frame_by_value || sp.time_by_value) ? 1u : 0u;
+    a.frame0 = sp.frame_by_value ? *sp.frame_by_value : 0u;
+    a.time0 = sp.time_by_value ? *sp.time_by_value : 0.0;
+    return a;
+}
+
+cudaError_t launch_pose_sample(cudaStream_t st, const DevModel& M, const DevFrames& F, const SampleSpec& sp) {
     const uint32_t items = M.nb + M.nm;
     if (items == 0 || F.n_slots == 0) return cudaSuccess;
     dim3 grid((items + 127) / 128, F.n_slots);
-    const bool by_value = frame_by_value || time_by_value;
-    pose_sample_kernel<<<grid, 128, 0, st>>>(M, anims, F, write_untracked ? 1u : 0u, range_mode ? 1u : 0u, frame_stride,
-                                             anims ? 1u : 0u, time_mode ? 1u : 0u, by_value ? 1u : 0u,
-                                             frame_by_value ? *frame_by_value : 0u, time_by_value ? *time_by_value : 0.0);
+    pose_sample_kernel<<<grid, 128, 0, st>>>(M, F, make_sample_args(sp));
     return cudaGetLastError();
 }
 
 cudaError_t launch_hierarchy(cudaStream_t st, const DevModel& M, const DevFrames& F, uint32_t wave_lo, uint32_t wave_hi,
-                             bool prologue) {
+                             bool prologue, const SampleSpec* sample) {
     if (F.n_slots == 0) return cudaSuccess;
     const size_t cta_smem = hier_cta_smem_bytes(M.nb, M.n_link_slots, M.n_morph_slots, M.n_ops, M.n_waves);
     static const bool force_global = std::getenv("MMDGPU_FORCE_FALLBACKS") != nullptr;  // test knob
     if (cta_smem <= kHierCtaSmemLimit && !force_global) {
         // small skeletons: narrower CTAs, so that more slots are resident per SM (a CCD IK solve is one thread)
         const uint32_t threads = M.nb <= 512 ? 128u : kHierCtaThreads;
-        if (M.ik_nested) hierarchy_cta_kernel<true><<<F.n_slots, threads, cta_smem, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u);
-        else hierarchy_cta_kernel<false><<<F.n_slots, threads, cta_smem, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u);
+        const SampleArgs sa = sample ? make_sample_args(*sample) : SampleArgs{};
+        const uint32_t smp = sample ? 1u : 0u;
+        if (M.ik_nested) hierarchy_cta_kernel<true><<<F.n_slots, threads, cta_smem, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u, smp, sa);
+        else hierarchy_cta_kernel<false><<<F.n_slots, threads, cta_smem, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u, smp, sa);
         return cudaGetLastError();
+    }
+    if (sample) {   // the warp-per-slot fallback does not sample: run K1 first
+        const cudaError_t e = launch_pose_sample(st, M, F, *sample);
+        if (e != cudaSuccess) return e;
     }
     const uint32_t blocks = (F.n_slots + kHierWarps - 1) / kHierWarps;
     if (M.ik_nested) hierarchy_kernel<true><<<blocks, 32 * kHierWarps, 0, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u);
@@ -1665,7 +1731,6 @@ cudaError_t prepare_skin_kernels(const DevModel& M) {
     if ((e = skin_opt_in<SOA, false, false>(limit)) != cudaSuccess) return e;
     if ((e = skin_opt_in<I32, false, false>(limit)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(skin_pair_kernel<SOA, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(skin_pair_kernel<I32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(skin_pair_kernel<I32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
 }
 
@@ -1688,13 +1753,7 @@ cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, 
     else if (M.global_palette) MMDGPU_LAUNCH_SKIN(false, true);
     else if (scalar) MMDGPU_LAUNCH_SKIN(false, false);
     else if (soa) skin_pair_kernel<SOA, 3><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks, -0.0f, 1.0f);
-    else {
-        // the interleaved layout has no staging tiles (11 KB of shared memory per CTA): registers alone decide residency.
-        // MMDGPU_I32_CTAS=4 (experiment knob): 128 registers with a few spills, 16 warps per SM instead of 12
-        static const bool four = [] { const char* e = std::getenv("MMDGPU_I32_CTAS"); return e && e[0] == '4'; }();
-        if (four) skin_pair_kernel<I32, 4><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks, -0.0f, 1.0f);
-        else skin_pair_kernel<I32, 3><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks, -0.0f, 1.0f);
-    }
+    else skin_pair_kernel<I32, 3><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks, -0.0f, 1.0f);
 #undef MMDGPU_LAUNCH_SKIN
     return cudaGetLastError();
 }

@@ -7,16 +7,23 @@
 
 namespace mmdgpu {
 
-// K1: keyframe sampling for every (slot, bone) and (slot, morph).  anims == nullptr: write identity / zero
-// (Poser::ResetPosing's pose part).  write_untracked: also write identity / zero for items without a track.
-// frame_by_value / time_by_value: one frame id (first frame of a one-instance range) or one time handed over as a kernel
-// argument instead of through F.frame_id / F.time_s.
-cudaError_t launch_pose_sample(cudaStream_t st, const DevModel& M, const DevAnim* anims, const DevFrames& F,
-                               bool write_untracked, bool range_mode, uint32_t frame_stride, bool time_mode = false,
-                               const uint32_t* frame_by_value = nullptr, const double* time_by_value = nullptr);
-// K2: waves [wave_lo, wave_hi) of the bone program; prologue = morph rates + reset + bone morphs.
+// What to sample: anims == nullptr writes identity / zero (Poser::ResetPosing's pose part); write_untracked: also write
+// identity / zero for items the clip does not animate; frame_by_value / time_by_value: one frame id (first frame of a
+// one-instance range) or one time handed over as a kernel argument instead of through F.frame_id / F.time_s.
+struct SampleSpec {
+    const DevAnim* anims = nullptr;
+    bool write_untracked = false, range_mode = false;
+    uint32_t frame_stride = 1;
+    bool time_mode = false;
+    const uint32_t* frame_by_value = nullptr;
+    const double* time_by_value = nullptr;
+};
+// K1: keyframe sampling for every (slot, bone) and (slot, morph).
+cudaError_t launch_pose_sample(cudaStream_t st, const DevModel& M, const DevFrames& F, const SampleSpec& spec);
+// K2: waves [wave_lo, wave_hi) of the bone program; prologue = morph rates + reset + bone morphs.  sample != nullptr
+// (fused updates, needs prologue): the kernel samples the key frames itself - K1 and K2 in one launch.
 cudaError_t launch_hierarchy(cudaStream_t st, const DevModel& M, const DevFrames& F, uint32_t wave_lo, uint32_t wave_hi,
-                             bool prologue);
+                             bool prologue, const SampleSpec* sample = nullptr);
 // K2, one wave with a thread per (op, slot): CCD IK solves on chain-local images (kernels.cu), for large batches.
 bool hierarchy_uses_cta_kernel(const DevModel& M);
 size_t hierarchy_flat_smem_bytes(const DevModel& M);

@@ -460,8 +460,11 @@ mmdgpu_status enter(mmdgpu_context_t ctx) {
     return MMDGPU_OK;
 }
 
+// Binds the clips, uploads the frame ids and either launches the sampling kernel (fused_out == nullptr) or only describes
+// the sampling in *fused_out so that the hierarchy kernel of a fused update does it in its prologue.  *fused_out points
+// into `frames` / the frames object: it must be consumed before this call's caller returns.
 mmdgpu_status do_seek(mmdgpu_frames* f, const mmdgpu_animation_t* per_instance, const uint32_t* frames, bool range,
-                      uint32_t stride, bool write_untracked, cudaStream_t st) {
+                      uint32_t stride, bool write_untracked, cudaStream_t st, SampleSpec* fused_out = nullptr) {
     mmdgpu_context_t ctx = f->ctx;
     if (!frames) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "frame id array is NULL");
     if (mmdgpu_status s = bind_anims(f, per_instance, st)) return s;
@@ -471,10 +474,16 @@ mmdgpu_status do_seek(mmdgpu_frames* f, const mmdgpu_animation_t* per_instance, 
     if (!by_value) CU(ctx, cudaMemcpyAsync(f->dev.frame_id, frames, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
     f->range_mode = range;
     f->frame_stride = stride;
+    SampleSpec sp;
+    sp.anims = f->d_anims;
+    sp.write_untracked = write_untracked;
+    sp.range_mode = range;
+    sp.frame_stride = stride;
+    sp.frame_by_value = by_value ? frames : nullptr;
+    if (fused_out) { *fused_out = sp; return MMDGPU_OK; }
     {
         Timed t(ctx, MMDGPU_KERNEL_POSE_SAMPLE, st);
-        CU(ctx, launch_pose_sample(st, f->model->dev, f->d_anims, f->dev, write_untracked, range, stride, false,
-                                   by_value ? frames : nullptr, nullptr));
+        CU(ctx, launch_pose_sample(st, f->model->dev, f->dev, sp));
     }
     return MMDGPU_OK;
 }
@@ -494,12 +503,13 @@ static bool split_ik_waves(const mmdgpu_frames* f) {
     return f->dev.n_slots >= kIkSplitMinSlots;
 }
 
-mmdgpu_status do_hierarchy(mmdgpu_frames* f, uint32_t lo, uint32_t hi, bool prologue, cudaStream_t st) {
+// sample: key-frame sampling to be done by the first launch (the one that runs the prologue)
+mmdgpu_status do_hierarchy(mmdgpu_frames* f, uint32_t lo, uint32_t hi, bool prologue, cudaStream_t st, const SampleSpec* sample = nullptr) {
     mmdgpu_context_t ctx = f->ctx;
     const DevModel& M = f->model->dev;
     if (!split_ik_waves(f)) {
         Timed t(ctx, MMDGPU_KERNEL_HIERARCHY, st);
-        CU(ctx, launch_hierarchy(st, M, f->dev, lo, hi, prologue));
+        CU(ctx, launch_hierarchy(st, M, f->dev, lo, hi, prologue, sample));
         return MMDGPU_OK;
     }
     uint32_t cur = lo;
@@ -509,7 +519,7 @@ mmdgpu_status do_hierarchy(mmdgpu_frames* f, uint32_t lo, uint32_t hi, bool prol
         if (w < lo || w >= hi) continue;
         if (w > cur || pro) {  // the segment before the IK wave (possibly empty: prologue only)
             Timed t(ctx, MMDGPU_KERNEL_HIERARCHY, st);
-            CU(ctx, launch_hierarchy(st, M, f->dev, cur, w, pro));
+            CU(ctx, launch_hierarchy(st, M, f->dev, cur, w, pro, pro ? sample : nullptr));
             pro = false;
         }
         {
@@ -520,7 +530,7 @@ mmdgpu_status do_hierarchy(mmdgpu_frames* f, uint32_t lo, uint32_t hi, bool prol
     }
     if (cur < hi || pro) {
         Timed t(ctx, MMDGPU_KERNEL_HIERARCHY, st);
-        CU(ctx, launch_hierarchy(st, M, f->dev, cur, hi, pro));
+        CU(ctx, launch_hierarchy(st, M, f->dev, cur, hi, pro, pro ? sample : nullptr));
     }
     return MMDGPU_OK;
 }
@@ -1092,7 +1102,9 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_create(mmdgpu_context_t ctx, mmdgpu_model
     for (int i = kStateCopies - 1; i >= 0; --i) {
         f->select(i);
         Timed t(ctx, MMDGPU_KERNEL_POSE_SAMPLE);
-        CU(ctx, launch_pose_sample(st, M, nullptr, F, true, false, 1));
+        SampleSpec reset;
+        reset.write_untracked = true;
+        CU(ctx, launch_pose_sample(st, M, F, reset));
     }
     *out = f.release();
     return MMDGPU_OK;
@@ -1114,7 +1126,9 @@ MMDGPU_API mmdgpu_status mmdgpu_reset_posing(mmdgpu_frames_t f) {
     f->main_dirty = true;
     {
         Timed t(f->ctx, MMDGPU_KERNEL_POSE_SAMPLE);
-        CU(f->ctx, launch_pose_sample(f->ctx->stream, f->model->dev, nullptr, f->dev, true, false, 1));
+        SampleSpec reset;
+        reset.write_untracked = true;
+        CU(f->ctx, launch_pose_sample(f->ctx->stream, f->model->dev, f->dev, reset));
     }
     return MMDGPU_OK;
 }
@@ -1148,8 +1162,12 @@ static mmdgpu_status seek_time_common(mmdgpu_frames_t f, const mmdgpu_animation_
         CU(ctx, cudaMemcpyAsync(f->dev.time_s, time_per_slot, sizeof(double) * f->dev.n_slots, cudaMemcpyHostToDevice, ctx->stream));
     {
         Timed t(ctx, MMDGPU_KERNEL_POSE_SAMPLE);
-        CU(ctx, launch_pose_sample(ctx->stream, f->model->dev, f->d_anims, f->dev, write_untracked, false, 1, true, nullptr,
-                                   by_value ? time_per_slot : nullptr));
+        SampleSpec sp;
+        sp.anims = f->d_anims;
+        sp.write_untracked = write_untracked;
+        sp.time_mode = true;
+        sp.time_by_value = by_value ? time_per_slot : nullptr;
+        CU(ctx, launch_pose_sample(ctx->stream, f->model->dev, f->dev, sp));
     }
     return MMDGPU_OK;
 }
@@ -1265,9 +1283,11 @@ static mmdgpu_status update_common(mmdgpu_frames_t f, const mmdgpu_animation_t* 
         f->main_dirty = false;
     }
     f->select(next);
-    if (mmdgpu_status s = do_seek(f, per_instance, frames, range, stride, true, pre)) return s;
+    // sampling happens in the prologue of the hierarchy kernel (one launch fewer; the fallback kernel runs K1 itself)
+    SampleSpec sample;
+    if (mmdgpu_status s = do_seek(f, per_instance, frames, range, stride, true, pre, &sample)) return s;
     const DevModel& M = f->model->dev;
-    if (mmdgpu_status s = do_hierarchy(f, 0, M.n_waves, true, pre)) return s;
+    if (mmdgpu_status s = do_hierarchy(f, 0, M.n_waves, true, pre, &sample)) return s;
     CU(ctx, cudaEventRecord(f->ev_pre[next], pre));
     CU(ctx, cudaStreamWaitEvent(ctx->stream, f->ev_pre[next], 0));
     if (mmdgpu_status s = do_skin(f)) return s;

@@ -199,8 +199,12 @@ public:
         if (pending_ & kPre) {   // Reset [, Seek], Pre, Post: nothing of ResetPosing's own evaluation survives
             const unsigned had = pending_;
             pending_ = kNone;
-            if (had & kSeek) IssueSeek(true);
-            else check(mmdgpu_reset_posing(frames_), "mmdgpu_reset_posing");
+            if (had & kSeek) {   // one call: the key frames are sampled in the prologue of the hierarchy kernel
+                if (seek_by_time_) check(mmdgpu_pose_time(frames_, &seek_anim_, &seek_seconds_), "mmdgpu_pose_time");
+                else check(mmdgpu_pose_frame(frames_, &seek_anim_, &seek_frame_), "mmdgpu_pose_frame");
+                return;
+            }
+            check(mmdgpu_reset_posing(frames_), "mmdgpu_reset_posing");
             check(mmdgpu_pre_physics_posing(frames_), "mmdgpu_pre_physics_posing");
             check(mmdgpu_post_physics_posing(frames_), "mmdgpu_post_physics_posing");
             return;

@@ -1150,7 +1150,7 @@ MMDGPU_API mmdgpu_status mmdgpu_seek_frame_range(mmdgpu_frames_t f, const mmdgpu
 }
 
 static mmdgpu_status seek_time_common(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance, const double* time_per_slot,
-                                      bool write_untracked) {
+                                      bool write_untracked, SampleSpec* fused_out = nullptr) {
     if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
     mmdgpu_context_t ctx = f->ctx;
     if (mmdgpu_status s = enter(ctx)) return s;
@@ -1167,6 +1167,7 @@ static mmdgpu_status seek_time_common(mmdgpu_frames_t f, const mmdgpu_animation_
         sp.write_untracked = write_untracked;
         sp.time_mode = true;
         sp.time_by_value = by_value ? time_per_slot : nullptr;
+        if (fused_out) { *fused_out = sp; return MMDGPU_OK; }
         CU(ctx, launch_pose_sample(ctx->stream, f->model->dev, f->dev, sp));
     }
     return MMDGPU_OK;
@@ -1178,6 +1179,23 @@ MMDGPU_API mmdgpu_status mmdgpu_seek_time(mmdgpu_frames_t f, const mmdgpu_animat
 
 MMDGPU_API mmdgpu_status mmdgpu_reset_and_seek_time(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance, const double* time_per_slot) {
     return seek_time_common(f, per_instance, time_per_slot, true);
+}
+
+// ResetPosing + SeekFrame / SeekTime + PrePhysicsPosing + PostPhysicsPosing on the context's stream: the sampling runs in
+// the prologue of the hierarchy kernel (one launch for models without CCD IK waves to split).
+MMDGPU_API mmdgpu_status mmdgpu_pose_frame(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance, const uint32_t* frame_per_slot) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    if (mmdgpu_status s = enter(f->ctx)) return s;
+    f->main_dirty = true;
+    SampleSpec sample;
+    if (mmdgpu_status s = do_seek(f, per_instance, frame_per_slot, false, 1, true, f->ctx->stream, &sample)) return s;
+    return do_hierarchy(f, 0, f->model->dev.n_waves, true, f->ctx->stream, &sample);
+}
+MMDGPU_API mmdgpu_status mmdgpu_pose_time(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance, const double* time_per_slot) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    SampleSpec sample;
+    if (mmdgpu_status s = seek_time_common(f, per_instance, time_per_slot, true, &sample)) return s;
+    return do_hierarchy(f, 0, f->model->dev.n_waves, true, f->ctx->stream, &sample);
 }
 
 MMDGPU_API mmdgpu_status mmdgpu_reset_and_seek_frame(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance,

@@ -73,6 +73,8 @@ SIGNATURES = {
     "mmdgpu_seek_frame": (C.c_int, [_vp, _vp, _vp]),
     "mmdgpu_seek_frame_range": (C.c_int, [_vp, _vp, _vp, _u32]),
     "mmdgpu_seek_time": (C.c_int, [_vp, _vp, _vp]),
+    "mmdgpu_pose_frame": (C.c_int, [_vp, _vp, _vp]),
+    "mmdgpu_pose_time": (C.c_int, [_vp, _vp, _vp]),
     "mmdgpu_reset_and_seek_frame": (C.c_int, [_vp, _vp, _vp]),
     "mmdgpu_reset_and_seek_time": (C.c_int, [_vp, _vp, _vp]),
     "mmdgpu_set_bone_pose": (C.c_int, [_vp, _u32, _u32, _vp, _vp]),

@@ -210,6 +210,19 @@ class Frames:
             raise ValueError("one time per slot required")
         check(self.lib.mmdgpu_seek_time(self.h, self._anim_array(motions), _ptr(t)), self.ctx.h)
 
+    def pose_frame(self, motions, frame_per_slot):
+        """reset_posing + seek_frame + pre_physics_posing + post_physics_posing in one call (sampling inside the hierarchy kernel)."""
+        f = np.ascontiguousarray(frame_per_slot, np.uint32)
+        if f.size != self.n_slots:
+            raise ValueError("one frame id per slot required")
+        check(self.lib.mmdgpu_pose_frame(self.h, self._anim_array(motions), _ptr(f)), self.ctx.h)
+
+    def pose_time(self, motions, time_per_slot):
+        t = np.ascontiguousarray(time_per_slot, np.float64)
+        if t.size != self.n_slots:
+            raise ValueError("one time per slot required")
+        check(self.lib.mmdgpu_pose_time(self.h, self._anim_array(motions), _ptr(t)), self.ctx.h)
+
     def reset_and_seek_frame(self, motions, frame_per_slot):
         """reset_posing + seek_frame as one sampling launch (unanimated bones / morphs get identity / zero)."""
         f = np.ascontiguousarray(frame_per_slot, np.uint32)

@@ -300,3 +300,41 @@ def test_cxx_shim_replays_recorded_calls_exactly(ctx, tmp_path):
     r = subprocess.run([str(exe), str(tmp_path / "m.pmx"), str(tmp_path / "m.vmd")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("same") == 12 and "DIFFERENT" not in r.stdout, r.stdout
+
+
+@pytest.mark.parametrize("name", ["tiny_full", "ik_zoo", "C2"])
+def test_pose_frame_is_the_four_libmmd_calls(ctx, name):
+    """mmdgpu_pose_frame / _time = ResetPosing; SeekFrame / SeekTime; PrePhysicsPosing; PostPhysicsPosing with the key
+    frames sampled inside the hierarchy kernel: same poses, rates, matrices and vertices as the four separate calls, and
+    as libmmd."""
+    _, model, motion = synth_case(name)
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    n = 5
+    frames = [0, 3, 17, 29, 40]
+    four, one = Frames(m, 1, n), Frames(m, 1, n)
+    for fr in (four, one):                                  # leftovers a reset must wipe
+        fr.update(a, [9] * n)
+        fr.set_morph_pose(2, 0, 0.5) if m.n_morphs else None
+        fr.set_bone_pose(1, 1, [1, 2, 3], [0.5, 0.5, 0.5, 0.5])
+    four.reset_posing(); four.seek_frame(a, frames); four.pre_physics_posing(); four.post_physics_posing(); four.deform()
+    one.pose_frame(a, frames); one.deform()
+    orc = _oracle(model, motion)
+    for k, f in enumerate(frames):
+        ref = orc.run_frame(f)
+        assert_bitwise(one.bone_poses(k), four.bone_poses(k), f"{name} slot {k} poses")
+        assert_bitwise(one.bone_matrices(k), four.bone_matrices(k), f"{name} slot {k} skinning matrices")
+        assert_bitwise(one.bone_matrices(k), ref["skin"], f"{name} frame {f} skinning matrices vs oracle")
+        assert_bitwise(one.download(k, capi.STREAM_POSITION), ref["pos"], f"{name} frame {f} positions vs oracle")
+    times = [0.0, 0.31, 0.777, 1.0, 1.29]
+    four.reset_posing(); four.seek_time(a, times); four.pre_physics_posing(); four.post_physics_posing(); four.deform()
+    one.pose_time(a, times); one.deform()
+    for k, t in enumerate(times):
+        assert_bitwise(one.download(k, capi.STREAM_POSITION), orc.run_time(t)["pos"], f"{name} time {t} positions vs oracle")
+        assert_bitwise(one.bone_matrices(k), four.bone_matrices(k), f"{name} time {t} skinning matrices")
+    # one-slot object: frame id / time by kernel argument
+    s1 = Frames(m, 1, 1)
+    s1.pose_frame(a, [17]); s1.deform()
+    assert_bitwise(s1.download(0, capi.STREAM_POSITION), orc.run_frame(17)["pos"], f"{name} one-slot pose_frame")
+    s1.pose_time(a, [0.777]); s1.deform()
+    assert_bitwise(s1.download(0, capi.STREAM_POSITION), orc.run_time(0.777)["pos"], f"{name} one-slot pose_time")

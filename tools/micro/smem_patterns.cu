@@ -114,6 +114,12 @@ int main() {
     add("lds128 palette stride 3: 24 bones random", 0, [&](int l) { return 3 * rnd24[l]; });
     add("lds128 palette stride 3: 24 bones sorted", 0, [&](int l) { return 3 * rnd24s[l]; });
     add("lds128 palette stride 3: 32 distinct bones", 0, [](int l) { return 3 * l; });
+    // is the pair fast path all-or-nothing, or per quarter-warp?
+    add("lds128 q0 aligned pairs, rest distinct", 0, [](int l) { return l < 8 ? l / 2 : l; });
+    add("lds128 q0-q1 aligned pairs, rest distinct", 0, [](int l) { return l < 16 ? l / 2 : l; });
+    add("lds128 aligned pairs except one mixed pair", 0, [](int l) { return l == 31 ? 40 : l / 2; });
+    add("lds128 pairs shifted by one lane ((l+1)/2)", 0, [](int l) { return (l + 1) / 2; });
+    add("lds128 stride 3: sorted runs, boundaries on even lanes", 0, [](int l) { const int b[16] = {0,0,1,1,1,2,3,3,3,3,4,5,5,6,6,7}; return 3 * b[l / 2]; });
     // ---- LDS.64, index in float2 units
     add("lds64 consecutive", 3, [](int l) { return l; });
     add("lds64 12 bones random, stride 6", 3, [&](int l) { return 6 * rnd12[l]; });

@@ -329,7 +329,8 @@ MMDGPU_API mmdgpu_status mmdgpu_reset_and_seek_frame(mmdgpu_frames_t frames, con
 MMDGPU_API mmdgpu_status mmdgpu_reset_and_seek_time(mmdgpu_frames_t frames, const mmdgpu_animation_t* per_instance,
                                                     const double* time_per_slot);
 /* ResetPosing + SeekFrame (or SeekTime) + PrePhysicsPosing + PostPhysicsPosing in one call - main.cpp:1788-1810 without the
- * physics step; the key frames are sampled in the prologue of the hierarchy kernel.  Deform is the caller's next call. */
+ * physics step: one sampling launch and ONE hierarchy pass over the whole bone program (pre- and post-physics bones).
+ * Deform is the caller's next call. */
 MMDGPU_API mmdgpu_status mmdgpu_pose_frame(mmdgpu_frames_t frames, const mmdgpu_animation_t* per_instance,
                                            const uint32_t* frame_per_slot);
 MMDGPU_API mmdgpu_status mmdgpu_pose_time(mmdgpu_frames_t frames, const mmdgpu_animation_t* per_instance,

@@ -199,7 +199,7 @@ public:
         if (pending_ & kPre) {   // Reset [, Seek], Pre, Post: nothing of ResetPosing's own evaluation survives
             const unsigned had = pending_;
             pending_ = kNone;
-            if (had & kSeek) {   // one call: the key frames are sampled in the prologue of the hierarchy kernel
+            if (had & kSeek) {   // one call: one sampling launch + one hierarchy pass
                 if (seek_by_time_) check(mmdgpu_pose_time(frames_, &seek_anim_, &seek_seconds_), "mmdgpu_pose_time");
                 else check(mmdgpu_pose_frame(frames_, &seek_anim_, &seek_frame_), "mmdgpu_pose_frame");
                 return;

@@ -135,15 +135,6 @@ __device__ __forceinline__ bool sample_morph(const SampleArgs& SA, const SlotFra
     return tracked || SA.write_untracked;
 }
 
-// out-of-line copies for the hierarchy kernel's prologue: sampling runs once per bone there, and inlined it would take
-// registers from the wave program and the IK solver
-__device__ __noinline__ bool sample_bone_call(const SampleArgs* SA, SlotFrame sf, uint32_t b, float4* T, float4* R) {
-    return sample_bone(*SA, sf, b, *T, *R);
-}
-__device__ __noinline__ bool sample_morph_call(const SampleArgs* SA, SlotFrame sf, uint32_t m, float* w) {
-    return sample_morph(*SA, sf, m, *w);
-}
-
 __global__ void __launch_bounds__(128) pose_sample_kernel(DevModel M, DevFrames F, SampleArgs SA) {
     const uint32_t slot = blockIdx.y;
     const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
@@ -637,12 +628,9 @@ __host__ __device__ inline size_t hier_cta_smem_bytes(uint32_t nb, uint32_t n_li
            (((size_t)n_ops + n_waves + 1 + 3) & ~(size_t)3) * sizeof(uint32_t);
 }
 
-// sample != 0 (fused updates): the CTA samples its slot's key frames itself (K1's work) instead of reading what a
-// separate sampling launch left in global memory - one launch and one global round trip fewer per update.
 template <bool NEST>
 __global__ void __launch_bounds__(kHierCtaThreads) hierarchy_cta_kernel(DevModel M, DevFrames F, uint32_t wave_lo,
-                                                                        uint32_t wave_hi, uint32_t prologue, uint32_t sample,
-                                                                        SampleArgs SA) {
+                                                                        uint32_t wave_hi, uint32_t prologue) {
     extern __shared__ __align__(16) float4 hsm[];
     const uint32_t slot = blockIdx.x, tid = threadIdx.x, nb = M.nb, nthreads = blockDim.x;
     float4* s_poseR = hsm;
@@ -678,32 +666,10 @@ __global__ void __launch_bounds__(kHierCtaThreads) hierarchy_cta_kernel(DevModel
     S.palette = F.palette + (size_t)slot * nb * 3;
     S.pal_ext = F.pal_ext ? F.pal_ext + (size_t)slot * nb * 2 : nullptr;
 
-    // ---- poses of every bone: sampled here (fused updates) or as K1 / SetBonePose left them; the static bone records
-    //      and the program
-    if (sample) {
-        const SlotFrame sf = frame_of_slot(F, SA, slot);
-        for (uint32_t b = tid; b < nb; b += nthreads) {
-            float4 T, R;
-            if (sample_bone_call(&SA, sf, b, &T, &R)) {
-                F.poseT[(size_t)slot * nb + b] = T;      // kept in global memory for the download entry points
-                F.poseR[(size_t)slot * nb + b] = R;
-            } else {
-                T = F.poseT[(size_t)slot * nb + b];
-                R = F.poseR[(size_t)slot * nb + b];
-            }
-            s_poseR[b] = R;
-            s_poseT[b] = T;
-        }
-        for (uint32_t m = tid; m < M.nm; m += nthreads) {
-            float w;
-            if (sample_morph_call(&SA, sf, m, &w)) F.rate[(size_t)slot * M.nm + m] = w;
-        }
-        __syncthreads();   // the morph rates just written are read below by other threads of this CTA
-    } else {
-        for (uint32_t b = tid; b < nb; b += nthreads) {
-            s_poseR[b] = F.poseR[(size_t)slot * nb + b];
-            s_poseT[b] = F.poseT[(size_t)slot * nb + b];
-        }
+    // ---- sampled poses of every bone (written by K1 / SetBonePose), the static bone records and the program
+    for (uint32_t b = tid; b < nb; b += nthreads) {
+        s_poseR[b] = F.poseR[(size_t)slot * nb + b];
+        s_poseT[b] = F.poseT[(size_t)slot * nb + b];
     }
     {
         const float4* gb = reinterpret_cast<const float4*>(M.bones);
@@ -1662,22 +1628,16 @@ cudaError_t launch_pose_sample(cudaStream_t st, const DevModel& M, const DevFram
 }
 
 cudaError_t launch_hierarchy(cudaStream_t st, const DevModel& M, const DevFrames& F, uint32_t wave_lo, uint32_t wave_hi,
-                             bool prologue, const SampleSpec* sample) {
+                             bool prologue) {
     if (F.n_slots == 0) return cudaSuccess;
     const size_t cta_smem = hier_cta_smem_bytes(M.nb, M.n_link_slots, M.n_morph_slots, M.n_ops, M.n_waves);
     static const bool force_global = std::getenv("MMDGPU_FORCE_FALLBACKS") != nullptr;  // test knob
     if (cta_smem <= kHierCtaSmemLimit && !force_global) {
         // small skeletons: narrower CTAs, so that more slots are resident per SM (a CCD IK solve is one thread)
         const uint32_t threads = M.nb <= 512 ? 128u : kHierCtaThreads;
-        const SampleArgs sa = sample ? make_sample_args(*sample) : SampleArgs{};
-        const uint32_t smp = sample ? 1u : 0u;
-        if (M.ik_nested) hierarchy_cta_kernel<true><<<F.n_slots, threads, cta_smem, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u, smp, sa);
-        else hierarchy_cta_kernel<false><<<F.n_slots, threads, cta_smem, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u, smp, sa);
+        if (M.ik_nested) hierarchy_cta_kernel<true><<<F.n_slots, threads, cta_smem, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u);
+        else hierarchy_cta_kernel<false><<<F.n_slots, threads, cta_smem, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u);
         return cudaGetLastError();
-    }
-    if (sample) {   // the warp-per-slot fallback does not sample: run K1 first
-        const cudaError_t e = launch_pose_sample(st, M, F, *sample);
-        if (e != cudaSuccess) return e;
     }
     const uint32_t blocks = (F.n_slots + kHierWarps - 1) / kHierWarps;
     if (M.ik_nested) hierarchy_kernel<true><<<blocks, 32 * kHierWarps, 0, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u);

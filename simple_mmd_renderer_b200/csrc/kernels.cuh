@@ -20,10 +20,9 @@ struct SampleSpec {
 };
 // K1: keyframe sampling for every (slot, bone) and (slot, morph).
 cudaError_t launch_pose_sample(cudaStream_t st, const DevModel& M, const DevFrames& F, const SampleSpec& spec);
-// K2: waves [wave_lo, wave_hi) of the bone program; prologue = morph rates + reset + bone morphs.  sample != nullptr
-// (fused updates, needs prologue): the kernel samples the key frames itself - K1 and K2 in one launch.
+// K2: waves [wave_lo, wave_hi) of the bone program; prologue = morph rates + reset + bone morphs.
 cudaError_t launch_hierarchy(cudaStream_t st, const DevModel& M, const DevFrames& F, uint32_t wave_lo, uint32_t wave_hi,
-                             bool prologue, const SampleSpec* sample = nullptr);
+                             bool prologue);
 // K2, one wave with a thread per (op, slot): CCD IK solves on chain-local images (kernels.cu), for large batches.
 bool hierarchy_uses_cta_kernel(const DevModel& M);
 size_t hierarchy_flat_smem_bytes(const DevModel& M);

@@ -460,11 +460,8 @@ mmdgpu_status enter(mmdgpu_context_t ctx) {
     return MMDGPU_OK;
 }
 
-// Binds the clips, uploads the frame ids and either launches the sampling kernel (fused_out == nullptr) or only describes
-// the sampling in *fused_out so that the hierarchy kernel of a fused update does it in its prologue.  *fused_out points
-// into `frames` / the frames object: it must be consumed before this call's caller returns.
 mmdgpu_status do_seek(mmdgpu_frames* f, const mmdgpu_animation_t* per_instance, const uint32_t* frames, bool range,
-                      uint32_t stride, bool write_untracked, cudaStream_t st, SampleSpec* fused_out = nullptr) {
+                      uint32_t stride, bool write_untracked, cudaStream_t st) {
     mmdgpu_context_t ctx = f->ctx;
     if (!frames) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "frame id array is NULL");
     if (mmdgpu_status s = bind_anims(f, per_instance, st)) return s;
@@ -480,7 +477,6 @@ mmdgpu_status do_seek(mmdgpu_frames* f, const mmdgpu_animation_t* per_instance, 
     sp.range_mode = range;
     sp.frame_stride = stride;
     sp.frame_by_value = by_value ? frames : nullptr;
-    if (fused_out) { *fused_out = sp; return MMDGPU_OK; }
     {
         Timed t(ctx, MMDGPU_KERNEL_POSE_SAMPLE, st);
         CU(ctx, launch_pose_sample(st, f->model->dev, f->dev, sp));
@@ -503,13 +499,12 @@ static bool split_ik_waves(const mmdgpu_frames* f) {
     return f->dev.n_slots >= kIkSplitMinSlots;
 }
 
-// sample: key-frame sampling to be done by the first launch (the one that runs the prologue)
-mmdgpu_status do_hierarchy(mmdgpu_frames* f, uint32_t lo, uint32_t hi, bool prologue, cudaStream_t st, const SampleSpec* sample = nullptr) {
+mmdgpu_status do_hierarchy(mmdgpu_frames* f, uint32_t lo, uint32_t hi, bool prologue, cudaStream_t st) {
     mmdgpu_context_t ctx = f->ctx;
     const DevModel& M = f->model->dev;
     if (!split_ik_waves(f)) {
         Timed t(ctx, MMDGPU_KERNEL_HIERARCHY, st);
-        CU(ctx, launch_hierarchy(st, M, f->dev, lo, hi, prologue, sample));
+        CU(ctx, launch_hierarchy(st, M, f->dev, lo, hi, prologue));
         return MMDGPU_OK;
     }
     uint32_t cur = lo;
@@ -519,7 +514,7 @@ mmdgpu_status do_hierarchy(mmdgpu_frames* f, uint32_t lo, uint32_t hi, bool prol
         if (w < lo || w >= hi) continue;
         if (w > cur || pro) {  // the segment before the IK wave (possibly empty: prologue only)
             Timed t(ctx, MMDGPU_KERNEL_HIERARCHY, st);
-            CU(ctx, launch_hierarchy(st, M, f->dev, cur, w, pro, pro ? sample : nullptr));
+            CU(ctx, launch_hierarchy(st, M, f->dev, cur, w, pro));
             pro = false;
         }
         {
@@ -530,7 +525,7 @@ mmdgpu_status do_hierarchy(mmdgpu_frames* f, uint32_t lo, uint32_t hi, bool prol
     }
     if (cur < hi || pro) {
         Timed t(ctx, MMDGPU_KERNEL_HIERARCHY, st);
-        CU(ctx, launch_hierarchy(st, M, f->dev, cur, hi, pro, pro ? sample : nullptr));
+        CU(ctx, launch_hierarchy(st, M, f->dev, cur, hi, pro));
     }
     return MMDGPU_OK;
 }
@@ -1150,7 +1145,7 @@ MMDGPU_API mmdgpu_status mmdgpu_seek_frame_range(mmdgpu_frames_t f, const mmdgpu
 }
 
 static mmdgpu_status seek_time_common(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance, const double* time_per_slot,
-                                      bool write_untracked, SampleSpec* fused_out = nullptr) {
+                                      bool write_untracked) {
     if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
     mmdgpu_context_t ctx = f->ctx;
     if (mmdgpu_status s = enter(ctx)) return s;
@@ -1167,7 +1162,6 @@ static mmdgpu_status seek_time_common(mmdgpu_frames_t f, const mmdgpu_animation_
         sp.write_untracked = write_untracked;
         sp.time_mode = true;
         sp.time_by_value = by_value ? time_per_slot : nullptr;
-        if (fused_out) { *fused_out = sp; return MMDGPU_OK; }
         CU(ctx, launch_pose_sample(ctx->stream, f->model->dev, f->dev, sp));
     }
     return MMDGPU_OK;
@@ -1181,21 +1175,19 @@ MMDGPU_API mmdgpu_status mmdgpu_reset_and_seek_time(mmdgpu_frames_t f, const mmd
     return seek_time_common(f, per_instance, time_per_slot, true);
 }
 
-// ResetPosing + SeekFrame / SeekTime + PrePhysicsPosing + PostPhysicsPosing on the context's stream: the sampling runs in
-// the prologue of the hierarchy kernel (one launch for models without CCD IK waves to split).
+// ResetPosing + SeekFrame / SeekTime + PrePhysicsPosing + PostPhysicsPosing on the context's stream: one sampling launch
+// (identity / zero for what the clip does not animate) and the whole bone program in one hierarchy pass.
 MMDGPU_API mmdgpu_status mmdgpu_pose_frame(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance, const uint32_t* frame_per_slot) {
     if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
     if (mmdgpu_status s = enter(f->ctx)) return s;
     f->main_dirty = true;
-    SampleSpec sample;
-    if (mmdgpu_status s = do_seek(f, per_instance, frame_per_slot, false, 1, true, f->ctx->stream, &sample)) return s;
-    return do_hierarchy(f, 0, f->model->dev.n_waves, true, f->ctx->stream, &sample);
+    if (mmdgpu_status s = do_seek(f, per_instance, frame_per_slot, false, 1, true, f->ctx->stream)) return s;
+    return do_hierarchy(f, 0, f->model->dev.n_waves, true, f->ctx->stream);
 }
 MMDGPU_API mmdgpu_status mmdgpu_pose_time(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance, const double* time_per_slot) {
     if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
-    SampleSpec sample;
-    if (mmdgpu_status s = seek_time_common(f, per_instance, time_per_slot, true, &sample)) return s;
-    return do_hierarchy(f, 0, f->model->dev.n_waves, true, f->ctx->stream, &sample);
+    if (mmdgpu_status s = seek_time_common(f, per_instance, time_per_slot, true)) return s;
+    return do_hierarchy(f, 0, f->model->dev.n_waves, true, f->ctx->stream);
 }
 
 MMDGPU_API mmdgpu_status mmdgpu_reset_and_seek_frame(mmdgpu_frames_t f, const mmdgpu_animation_t* per_instance,
@@ -1301,11 +1293,9 @@ static mmdgpu_status update_common(mmdgpu_frames_t f, const mmdgpu_animation_t* 
         f->main_dirty = false;
     }
     f->select(next);
-    // sampling happens in the prologue of the hierarchy kernel (one launch fewer; the fallback kernel runs K1 itself)
-    SampleSpec sample;
-    if (mmdgpu_status s = do_seek(f, per_instance, frames, range, stride, true, pre, &sample)) return s;
+    if (mmdgpu_status s = do_seek(f, per_instance, frames, range, stride, true, pre)) return s;
     const DevModel& M = f->model->dev;
-    if (mmdgpu_status s = do_hierarchy(f, 0, M.n_waves, true, pre, &sample)) return s;
+    if (mmdgpu_status s = do_hierarchy(f, 0, M.n_waves, true, pre)) return s;
     CU(ctx, cudaEventRecord(f->ev_pre[next], pre));
     CU(ctx, cudaStreamWaitEvent(ctx->stream, f->ev_pre[next], 0));
     if (mmdgpu_status s = do_skin(f)) return s;

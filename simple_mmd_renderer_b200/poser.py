@@ -211,7 +211,7 @@ class Frames:
         check(self.lib.mmdgpu_seek_time(self.h, self._anim_array(motions), _ptr(t)), self.ctx.h)
 
     def pose_frame(self, motions, frame_per_slot):
-        """reset_posing + seek_frame + pre_physics_posing + post_physics_posing in one call (sampling inside the hierarchy kernel)."""
+        """reset_posing + seek_frame + pre_physics_posing + post_physics_posing in one call (one sampling launch, one hierarchy pass)."""
         f = np.ascontiguousarray(frame_per_slot, np.uint32)
         if f.size != self.n_slots:
             raise ValueError("one frame id per slot required")

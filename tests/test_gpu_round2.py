@@ -304,9 +304,9 @@ def test_cxx_shim_replays_recorded_calls_exactly(ctx, tmp_path):
 
 @pytest.mark.parametrize("name", ["tiny_full", "ik_zoo", "C2"])
 def test_pose_frame_is_the_four_libmmd_calls(ctx, name):
-    """mmdgpu_pose_frame / _time = ResetPosing; SeekFrame / SeekTime; PrePhysicsPosing; PostPhysicsPosing with the key
-    frames sampled inside the hierarchy kernel: same poses, rates, matrices and vertices as the four separate calls, and
-    as libmmd."""
+    """mmdgpu_pose_frame / _time = ResetPosing; SeekFrame / SeekTime; PrePhysicsPosing; PostPhysicsPosing in one call (one
+    sampling launch, one hierarchy pass): same poses, rates, matrices and vertices as the four separate calls, and as
+    libmmd."""
     _, model, motion = synth_case(name)
     m = Model(ctx, model)
     a = Motion(m, motion)

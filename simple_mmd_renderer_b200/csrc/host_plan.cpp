@@ -59,8 +59,8 @@ bool bezier_table(const int8_t c[4], float table[32]) {
 //     cost(group) = 6 x sum over its types (worst residue multiplicity) + 2 x morph rounds (largest entry count)
 // (six stores per vertex and slot against one extra morph round for the group; lanes of different types run in
 // different branches, so they never store together).  Types never mix more than the sort left them.
-template <class TypeOf, class CountOf, class BonesOf>
-void refine_tile_order(std::vector<uint32_t>& order, const TypeOf& type_of, const CountOf& count_of, const BonesOf& bones_of) {
+template <class TypeOf, class CountOf>
+void refine_tile_order(std::vector<uint32_t>& order, const TypeOf& type_of, const CountOf& count_of) {
     constexpr uint32_t G = kTileGroups, kTypes = 5;
     // in units of 1/8 wavefront; the sum of squared multiplicities breaks the plateaus of the worst-multiplicity term
     constexpr int kWConflict = 48, kWRound = 16, kWSpread = 1;
@@ -147,15 +147,12 @@ void refine_tile_order(std::vector<uint32_t>& order, const TypeOf& type_of, cons
         }
         if (!improved) break;
     }
-    // inside a group: by (type, PMX index) again, so that the layout does not depend on the order of the swaps.
-    // MMDGPU_TILE_SORT_BONES=1 (experiment): by (type, bone ids) instead, so that lanes with the same bones sit next to each
-    // other (an LDS.128 whose aligned lane pairs read the same cell costs 2 wavefronts instead of 4)
-    static const bool by_bones = [] { const char* e = std::getenv("MMDGPU_TILE_SORT_BONES"); return e && e[0] == '1'; }();
+    // inside a group: by (type, PMX index) again, so that the layout does not depend on the order of the swaps.  (Sorting by
+    // bone ids instead changes nothing: an LDS.128 takes its 2-wavefront path only when EVERY aligned lane pair of the warp
+    // reads one cell, measured in profiles/r02_smem_patterns.txt and on the kernel in profiles/r02_experiments.md.)
     for (uint32_t g = 0; g < G; ++g)
         std::sort(order.begin() + g * 32, order.begin() + g * 32 + 32, [&](uint32_t x, uint32_t y) {
-            if (ty[x] != ty[y]) return ty[x] < ty[y];
-            if (by_bones) { const uint64_t bx = bones_of(x), by = bones_of(y); if (bx != by) return bx < by; }
-            return x < y;
+            return ty[x] != ty[y] ? ty[x] < ty[y] : x < y;
         });
 }
 
@@ -745,12 +742,7 @@ mmdgpu_status build_plan(const mmdgpu_model_desc& d, const mmdgpu_options* opt, 
                 if (ta != tb) return ta < tb;
                 return count_of(a) < count_of(b);
             });
-            auto bones_of = [&](uint32_t i) -> uint64_t {
-                if (v0 + i >= nv) return 0;
-                const uint16_t* b = &p.bone_id[size_t(v0 + i) * 4];
-                return (uint64_t(b[0]) << 48) | (uint64_t(b[1]) << 32) | (uint64_t(b[2]) << 16) | uint64_t(b[3]);
-            };
-            refine_tile_order(order, type_of, count_of, bones_of);
+            refine_tile_order(order, type_of, count_of);
             // distinct bones of the tile, ascending
             std::vector<uint16_t> used;
             for (uint32_t i = 0; i < kTileVerts && v0 + i < nv; ++i) {

@@ -55,11 +55,11 @@ def parse_args():
     ap.add_argument("--frames-per-step", type=int, default=128, help="C1/C2/C3: VMD frames per step per GPU")
     ap.add_argument("--instances", type=int, default=512, help="C4: crowd size (whole job)")
     ap.add_argument("--layout", default="soa", choices=["soa", "sokol32"])
-    ap.add_argument("--binding", default="coherent", choices=["coherent", "random"], help="vertex -> bone binding of the synthetic model")
+    ap.add_argument("--binding", default="coherent", choices=["coherent", "wide", "random"], help="vertex -> bone binding of the synthetic model")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the short measurements of the other BASELINE configs")
-    ap.add_argument("--also", default="C1,C2,C4,C5,C3_random", help="which secondary measurements to run")
+    ap.add_argument("--also", default="C1,C2,C4,C5,C3_wide,C3_random", help="which secondary measurements to run")
     ap.add_argument("--bake-frames", type=int, default=BAKE_FRAMES)
     return ap.parse_args()
 
@@ -791,6 +791,10 @@ def headline(args, env: Env, ctx, stream, m, model, cfg, layout, numa):
         for _, mm, mo in cache.values():
             mo.close(); mm.close()
         cache.clear()
+        if "C3_wide" in want and args.workload == "C3" and args.binding == "coherent":
+            # bones drawn from +- 24 around the vertex's place in the skeleton: ~50 distinct bones per 512-vertex tile instead of
+            # ~8, still staged in shared memory (real PMX vertex order is less bone-coherent than the headline model)
+            guarded("C3_wide", lambda: measure_batch(env, ctx, stream, "C3", 128, steps=5, warmup=2, binding="wide"))
         if "C3_random" in want and args.workload == "C3" and args.binding == "coherent":
             # stress binding: every vertex picks its bones uniformly from all 1 k bones, so no tile-local palette fits and
             # the skinning kernel reads matrices from the slot's global palette (L2)

@@ -26,7 +26,7 @@ class SynthConfig:
     n_bones: int
     n_vertex_morphs: int
     n_frames: int
-    binding: str = "coherent"        # "coherent": bones from floor(i*NB/NV) +- 3 ; "random": uniform
+    binding: str = "coherent"        # "coherent": bones from floor(i*NB/NV) +- 3 ; "wide": +- 24 (~50 bones per 512-vertex tile) ; "random": uniform
     sdef_qdef: bool = False          # tag 15 % of BDEF2 as SDEF, 10 % of BDEF4 as QDEF
     n_uv_morphs: int = 0
     n_group_morphs: int = 0
@@ -161,9 +161,10 @@ def make_model(cfg: SynthConfig) -> dict:
     n /= np.maximum(np.sqrt((n * n).sum(1, keepdims=True)), np.float32(1e-6))
     vnrm = _f32(n)
     uv = _f32(rng.random((nv, 2)))
-    if cfg.binding == "coherent":
+    if cfg.binding in ("coherent", "wide"):
+        half = 3 if cfg.binding == "coherent" else 24
         centre = (np.arange(nv, dtype=np.int64) * nb) // nv
-        bid = centre[:, None] + rng.integers(-3, 4, (nv, 4))
+        bid = centre[:, None] + rng.integers(-half, half + 1, (nv, 4))
         bid = np.clip(bid, 0, nb - 1).astype(np.int32)
     else:
         bid = rng.integers(0, nb, (nv, 4)).astype(np.int32)

@@ -2,6 +2,9 @@
 #include "host_plan.hpp"
 
 #include <algorithm>
+#include <array>
+#include <atomic>
+#include <thread>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -154,6 +157,240 @@ void refine_tile_order(std::vector<uint32_t>& order, const TypeOf& type_of, cons
         std::sort(order.begin() + g * 32, order.begin() + g * 32 + 32, [&](uint32_t x, uint32_t y) {
             return ty[x] != ty[y] ? ty[x] < ty[y] : x < y;
         });
+}
+
+// --------------------------------------------------------------------------------------------------
+// Tile order, pairing form (default).  profiles/r02_smem_patterns.txt: an LDS.128 whose 32 lanes read unrelated 16-byte
+// cells costs 4 wavefronts, but 2 when EVERY aligned lane pair (2k, 2k+1) of the instruction reads one cell.  The skinning
+// kernel reads bone k of a vertex with six such loads per slot pair, so a 32-lane group whose lane pairs agree on bone k
+// gets those six loads at half price.  Vertices of a tile use few bones (the point of the tile-local palette), so most of
+// them can be paired with a vertex of the same skinning type and the same leading bone ids:
+//   1. per type, vertices are matched hierarchically: first those that agree on all bone ids, the leftovers of each such
+//      class on one id fewer, ... down to "same first bone", then arbitrarily (level 0); partners are chosen close in morph
+//      entry count.  At most one vertex per type stays single; singles fill the last lane pairs of the tile.
+//   2. a type's pairs are ordered by (level class, morph entry count) and cut into groups of 16 pairs in sequence; the
+//      class of a (group, type) bucket is the lowest level in it, i.e. the number of leading bone ids whose loads take the
+//      2-wavefront path.
+//   3. hill climbing as in refine_tile_order (staging-scatter conflicts, morph rounds), with two kinds of moves that keep
+//      every bucket's class: two vertices of one type trade places if each still agrees with its new partner on the
+//      bucket's class many ids; two pairs trade places if each meets the other bucket's class.
+struct TileVert {
+    uint8_t ty, keep;
+    uint16_t id[4];
+    uint32_t cnt;
+};
+inline uint32_t prefix_match(const TileVert& a, const TileVert& b) {
+    if (a.ty != b.ty) return 0;
+    uint32_t k = 0;
+    while (k < a.keep && a.id[k] == b.id[k]) ++k;
+    return k;
+}
+
+void pair_tile_order(std::vector<uint32_t>& order, const std::vector<TileVert>& tv) {
+    constexpr uint32_t G = kTileGroups, kTypes = 5, N = kTileVerts, kUnitsPerGroup = 16;
+    constexpr int kWConflict = 48, kWRound = 16, kWSpread = 1;   // 1/8 wavefront per slot, as in refine_tile_order
+    struct Unit { uint32_t a, b; uint8_t ty, level, cls; uint32_t cnt; };
+    auto by_cnt = [&](uint32_t x, uint32_t y) { return tv[x].cnt != tv[y].cnt ? tv[x].cnt < tv[y].cnt : x < y; };
+    std::vector<Unit> units;
+    units.reserve(N / 2);
+    std::vector<uint32_t> singles, rem, nxt;
+    for (uint32_t t = 0; t < kTypes; ++t) {
+        rem.clear();
+        for (uint32_t i = 0; i < N; ++i) if (tv[i].ty == t) rem.push_back(i);
+        if (rem.empty()) continue;
+        const uint32_t keep = tv[rem[0]].keep;
+        std::sort(rem.begin(), rem.end(), [&](uint32_t x, uint32_t y) {
+            for (uint32_t k = 0; k < keep; ++k) if (tv[x].id[k] != tv[y].id[k]) return tv[x].id[k] < tv[y].id[k];
+            return x < y;
+        });
+        const size_t u0 = units.size();
+        for (uint32_t L = keep; L >= 1; --L) {
+            nxt.clear();
+            for (size_t i = 0; i < rem.size();) {
+                size_t j = i + 1;
+                while (j < rem.size() && prefix_match(tv[rem[i]], tv[rem[j]]) >= L) ++j;
+                std::sort(rem.begin() + i, rem.begin() + j, by_cnt);
+                size_t k = i;
+                for (; k + 1 < j; k += 2)
+                    units.push_back(Unit{std::min(rem[k], rem[k + 1]), std::max(rem[k], rem[k + 1]), uint8_t(t), uint8_t(L), 0,
+                                         std::max(tv[rem[k]].cnt, tv[rem[k + 1]].cnt)});
+                if (k < j) nxt.push_back(rem[k]);   // one leftover per class, classes stay in lexicographic order
+                i = j;
+            }
+            rem.swap(nxt);
+        }
+        std::sort(rem.begin(), rem.end(), by_cnt);
+        size_t k = 0;
+        for (; k + 1 < rem.size(); k += 2)
+            units.push_back(Unit{std::min(rem[k], rem[k + 1]), std::max(rem[k], rem[k + 1]), uint8_t(t), 0, 0,
+                                 std::max(tv[rem[k]].cnt, tv[rem[k + 1]].cnt)});
+        if (k < rem.size()) singles.push_back(rem[k]);
+        // level-major order, then the class of each (group, type) bucket, then (class, count) order inside the type's range
+        auto unit_less = [](const Unit& x, const Unit& y) { return x.cnt != y.cnt ? x.cnt < y.cnt : x.a < y.a; };
+        std::sort(units.begin() + u0, units.end(), [&](const Unit& x, const Unit& y) {
+            return x.level != y.level ? x.level > y.level : unit_less(x, y);
+        });
+        for (size_t i = u0; i < units.size();) {
+            const size_t g_end = std::min(units.size(), (i / kUnitsPerGroup + 1) * kUnitsPerGroup);
+            uint8_t lo = 255;
+            for (size_t j = i; j < g_end; ++j) lo = std::min(lo, units[j].level);
+            for (size_t j = i; j < g_end; ++j) units[j].cls = lo;
+            i = g_end;
+        }
+        std::sort(units.begin() + u0, units.end(), [&](const Unit& x, const Unit& y) {
+            return x.cls != y.cls ? x.cls > y.cls : unit_less(x, y);
+        });
+    }
+    for (size_t k = 0; k + 1 < singles.size(); k += 2)   // N is even, so the singles pair up; mixed types, level 0
+        units.push_back(Unit{singles[k], singles[k + 1], tv[singles[k]].ty, 0, 0, std::max(tv[singles[k]].cnt, tv[singles[k + 1]].cnt)});
+    for (size_t u = 0; u < units.size(); ++u) { order[2 * u] = units[u].a; order[2 * u + 1] = units[u].b; }
+
+    // ---- state of the hill climbing: per (group, type) residue histogram, required class; per group the lanes' counts
+    struct Bucket { uint8_t hist[32]; uint8_t at[33]; uint8_t mx; uint8_t req; };
+    struct Group { Bucket b[kTypes]; uint32_t top; uint32_t sorted_cnt[32]; };   // the lanes' counts, descending
+    std::vector<Group> gr(G);
+    auto rebuild = [&](uint32_t g) {
+        Group& Gp = gr[g];
+        uint8_t req[kTypes];
+        for (uint32_t t = 0; t < kTypes; ++t) req[t] = Gp.b[t].req;
+        std::memset(&Gp, 0, sizeof Gp);
+        for (uint32_t t = 0; t < kTypes; ++t) { Gp.b[t].at[0] = 32; Gp.b[t].req = req[t]; }
+        for (uint32_t l = 0; l < 32; ++l) {
+            const uint32_t v = order[g * 32 + l];
+            Bucket& B = Gp.b[tv[v].ty];
+            const uint8_t h = B.hist[v & 31u]++;
+            B.at[h]--; B.at[h + 1]++;
+            if (h + 1 > B.mx) B.mx = uint8_t(h + 1);
+            Gp.sorted_cnt[l] = tv[v].cnt;
+        }
+        std::sort(Gp.sorted_cnt, Gp.sorted_cnt + 32, std::greater<uint32_t>());
+        Gp.top = Gp.sorted_cnt[0];
+    };
+    for (uint32_t g = 0; g < G; ++g) {
+        for (uint32_t t = 0; t < kTypes; ++t) gr[g].b[t].req = 255;
+        for (uint32_t u = g * kUnitsPerGroup; u < (g + 1) * kUnitsPerGroup; ++u) {
+            const uint32_t a = order[2 * u], b = order[2 * u + 1];
+            const uint8_t lv = uint8_t(prefix_match(tv[a], tv[b]));
+            gr[g].b[tv[a].ty].req = std::min(gr[g].b[tv[a].ty].req, lv);
+            gr[g].b[tv[b].ty].req = std::min(gr[g].b[tv[b].ty].req, lv);
+        }
+        for (uint32_t t = 0; t < kTypes; ++t) if (gr[g].b[t].req == 255) gr[g].b[t].req = 0;
+        rebuild(g);
+    }
+    // worst multiplicity / change of the sum of squares of a bucket after n <= 2 residues lose and n gain one member
+    auto bucket_delta = [](const Bucket& B, const uint32_t* out, const uint32_t* in, int n, int& d_mx, int& d_sq) {
+        uint32_t r[4]; int d[4]; int m = 0;
+        auto add = [&](uint32_t res, int dv) {
+            for (int i = 0; i < m; ++i) if (r[i] == res) { d[i] += dv; return; }
+            r[m] = res; d[m] = dv; ++m;
+        };
+        for (int i = 0; i < n; ++i) { add(out[i], -1); add(in[i], +1); }
+        int best = 0; d_sq = 0;
+        for (int i = 0; i < m; ++i) {
+            const int o = B.hist[r[i]], nw = o + d[i];
+            best = std::max(best, nw);
+            d_sq += nw * nw - o * o;
+        }
+        int res_mx = best;
+        for (int h = B.mx; h > best; --h) {
+            int c = B.at[h];
+            for (int i = 0; i < m; ++i) if (d[i] != 0 && B.hist[r[i]] == h) --c;
+            if (c > 0) { res_mx = h; break; }
+        }
+        d_mx = res_mx - int(B.mx);
+    };
+    // largest count of group g when members with counts o0, o1 (o1 = ~0u: only one leaves) are replaced by counts c0, c1
+    auto top_after = [&](uint32_t g, uint32_t o0, uint32_t o1, uint32_t c0, uint32_t c1) -> uint32_t {
+        const uint32_t* sc = gr[g].sorted_cnt;
+        bool gone0 = false, gone1 = (o1 == ~0u);
+        uint32_t i = 0;
+        for (; i < 32; ++i) {
+            if (!gone0 && sc[i] == o0) { gone0 = true; continue; }
+            if (!gone1 && sc[i] == o1) { gone1 = true; continue; }
+            break;
+        }
+        return std::max(std::max(c0, c1), i < 32 ? sc[i] : 0u);
+    };
+    std::vector<uint32_t> ranks_of_type[kTypes];
+    for (uint32_t r = 0; r < N; ++r) ranks_of_type[tv[order[r]].ty].push_back(r);   // moves keep the type of every rank
+
+    for (int pass = 0; pass < 10; ++pass) {
+        bool improved = false;
+        // (a) two vertices of one type trade places
+        for (uint32_t ra = 0; ra < N; ++ra) {
+            const uint32_t a = order[ra], ga = ra / 32, t = tv[a].ty;
+            const Bucket& A = gr[ga].b[t];
+            if (A.hist[a & 31u] <= 1) continue;                   // collides with nobody
+            const uint32_t pa = order[ra ^ 1u];
+            int best = 0; uint32_t best_rb = 0;
+            for (uint32_t rb : ranks_of_type[t]) {
+                const uint32_t gb = rb / 32;
+                if (gb == ga) continue;
+                const uint32_t b = order[rb], pb = order[rb ^ 1u];
+                const Bucket& B = gr[gb].b[t];
+                if (prefix_match(tv[b], tv[pa]) < A.req || prefix_match(tv[a], tv[pb]) < B.req) continue;
+                const uint32_t ra5 = a & 31u, rb5 = b & 31u;
+                int dmA = 0, dsA = 0, dmB = 0, dsB = 0;
+                if (ra5 != rb5) { bucket_delta(A, &ra5, &rb5, 1, dmA, dsA); bucket_delta(B, &rb5, &ra5, 1, dmB, dsB); }
+                int d = kWConflict * (dmA + dmB) + kWSpread * (dsA + dsB);
+                if (tv[a].cnt != tv[b].cnt)
+                    d += kWRound * (int(top_after(ga, tv[a].cnt, ~0u, tv[b].cnt, 0)) - int(gr[ga].top) + int(top_after(gb, tv[b].cnt, ~0u, tv[a].cnt, 0)) - int(gr[gb].top));
+                if (d < best) { best = d; best_rb = rb; }
+            }
+            if (best < 0) {
+                std::swap(order[ra], order[best_rb]);
+                rebuild(ga); rebuild(best_rb / 32);
+                improved = true;
+            }
+        }
+        // (b) two pairs of one type trade places
+        for (uint32_t ua = 0; ua < N / 2; ++ua) {
+            const uint32_t a0 = order[2 * ua], a1 = order[2 * ua + 1], ga = ua / kUnitsPerGroup, t = tv[a0].ty;
+            if (tv[a1].ty != t) continue;
+            const Bucket& A = gr[ga].b[t];
+            if (A.hist[a0 & 31u] <= 1 && A.hist[a1 & 31u] <= 1) continue;
+            const uint32_t la = prefix_match(tv[a0], tv[a1]);
+            int best = 0; uint32_t best_ub = 0;
+            for (uint32_t ub = 0; ub < N / 2; ++ub) {
+                const uint32_t gb = ub / kUnitsPerGroup;
+                if (gb == ga) continue;
+                const uint32_t b0 = order[2 * ub], b1 = order[2 * ub + 1];
+                if (tv[b0].ty != t || tv[b1].ty != t) continue;
+                const Bucket& B = gr[gb].b[t];
+                if (la < B.req || prefix_match(tv[b0], tv[b1]) < A.req) continue;
+                const uint32_t outA[2] = {a0 & 31u, a1 & 31u}, outB[2] = {b0 & 31u, b1 & 31u};
+                int dmA, dsA, dmB, dsB;
+                bucket_delta(A, outA, outB, 2, dmA, dsA);
+                bucket_delta(B, outB, outA, 2, dmB, dsB);
+                int d = kWConflict * (dmA + dmB) + kWSpread * (dsA + dsB);
+                d += kWRound * (int(top_after(ga, tv[a0].cnt, tv[a1].cnt, tv[b0].cnt, tv[b1].cnt)) - int(gr[ga].top) +
+                                int(top_after(gb, tv[b0].cnt, tv[b1].cnt, tv[a0].cnt, tv[a1].cnt)) - int(gr[gb].top));
+                if (d < best) { best = d; best_ub = ub; }
+            }
+            if (best < 0) {
+                std::swap(order[2 * ua], order[2 * best_ub]);
+                std::swap(order[2 * ua + 1], order[2 * best_ub + 1]);
+                rebuild(ga); rebuild(best_ub / kUnitsPerGroup);
+                improved = true;
+            }
+        }
+        if (!improved) break;
+    }
+    // canonical order inside a group: pairs by (type, smaller PMX index), the smaller index in the even lane
+    for (uint32_t g = 0; g < G; ++g) {
+        std::array<std::pair<uint32_t, uint32_t>, kUnitsPerGroup> us;
+        for (uint32_t u = 0; u < kUnitsPerGroup; ++u) {
+            const uint32_t x = order[g * 32 + 2 * u], y = order[g * 32 + 2 * u + 1];
+            const bool swap = tv[x].ty != tv[y].ty ? tv[x].ty > tv[y].ty : x > y;
+            us[u] = swap ? std::make_pair(y, x) : std::make_pair(x, y);
+        }
+        std::sort(us.begin(), us.end(), [&](const std::pair<uint32_t, uint32_t>& x, const std::pair<uint32_t, uint32_t>& y) {
+            if (tv[x.first].ty != tv[y.first].ty) return tv[x.first].ty < tv[y.first].ty;
+            if (tv[x.second].ty != tv[y.second].ty) return tv[x.second].ty < tv[y.second].ty;
+            return x.first < y.first;
+        });
+        for (uint32_t u = 0; u < kUnitsPerGroup; ++u) { order[g * 32 + 2 * u] = us[u].first; order[g * 32 + 2 * u + 1] = us[u].second; }
+    }
 }
 
 mmdgpu_status build_plan(const mmdgpu_model_desc& d, const mmdgpu_options* opt, Plan& p, std::string& err) {
@@ -729,20 +966,50 @@ mmdgpu_status build_plan(const mmdgpu_model_desc& d, const mmdgpu_options* opt, 
     p.ell_rounds.assign(size_t(p.n_tiles) * kTileGroups, 0);
     p.pad_node = uint32_t(n_nodes);
     {
-        std::vector<uint32_t> order(kTileVerts);
         std::vector<int32_t> local_of(nb, -1);
         std::vector<uint16_t> rank_vertex(p.nv_pad);  // tile rank -> PMX index within the tile
-        for (uint32_t t = 0; t < p.n_tiles; ++t) {
+        // tile orders, tiles in parallel (the hill climbing is the expensive part of the plan: ~1 ms per tile)
+        static const bool pairing = [] { const char* e = std::getenv("MMDGPU_TILE_PAIRING"); return !(e && e[0] == '0'); }();
+        auto order_tile = [&](uint32_t t, std::vector<uint32_t>& order, std::vector<TileVert>& tv) {
             const uint32_t v0 = t * kTileVerts;
             auto type_of = [&](uint32_t i) -> uint32_t { return (v0 + i < nv) ? p.dev_type[v0 + i] : uint32_t(kDevBdef1); };
             auto count_of = [&](uint32_t i) -> uint32_t { return (v0 + i < nv) ? p.csr_row[v0 + i + 1] - p.csr_row[v0 + i] : 0u; };
-            for (uint32_t i = 0; i < kTileVerts; ++i) order[i] = i;
-            std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-                const uint32_t ta = type_of(a), tb = type_of(b);
-                if (ta != tb) return ta < tb;
-                return count_of(a) < count_of(b);
-            });
-            refine_tile_order(order, type_of, count_of);
+            if (pairing) {
+                for (uint32_t i = 0; i < kTileVerts; ++i) {
+                    TileVert& x = tv[i];
+                    x.ty = uint8_t(std::min<uint32_t>(type_of(i), 4u));
+                    x.keep = (x.ty == kDevBdef1) ? 1 : (x.ty == kDevBdef2 || x.ty == kDevSdef) ? 2 : 4;
+                    x.cnt = count_of(i);
+                    for (int k = 0; k < 4; ++k) x.id[k] = (v0 + i < nv && k < x.keep) ? p.bone_id[size_t(v0 + i) * 4 + k] : uint16_t(0xFFFF);
+                }
+                pair_tile_order(order, tv);
+            } else {
+                for (uint32_t i = 0; i < kTileVerts; ++i) order[i] = i;
+                std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+                    const uint32_t ta = type_of(a), tb = type_of(b);
+                    if (ta != tb) return ta < tb;
+                    return count_of(a) < count_of(b);
+                });
+                refine_tile_order(order, type_of, count_of);
+            }
+            for (uint32_t r = 0; r < kTileVerts; ++r) rank_vertex[size_t(v0) + r] = uint16_t(order[r]);
+        };
+        {
+            const uint32_t n_thr = std::max(1u, std::min<uint32_t>({std::thread::hardware_concurrency(), 16u, p.n_tiles / 8u}));
+            std::atomic<uint32_t> next{0};
+            auto work = [&] {
+                std::vector<uint32_t> order(kTileVerts);
+                std::vector<TileVert> tv(kTileVerts);
+                for (uint32_t t; (t = next.fetch_add(1)) < p.n_tiles;) order_tile(t, order, tv);
+            };
+            std::vector<std::thread> pool;
+            for (uint32_t i = 1; i < n_thr; ++i) pool.emplace_back(work);
+            work();
+            for (auto& th : pool) th.join();
+        }
+        for (uint32_t t = 0; t < p.n_tiles; ++t) {
+            const uint32_t v0 = t * kTileVerts;
+            const uint16_t* order = &rank_vertex[size_t(v0)];
             // distinct bones of the tile, ascending
             std::vector<uint16_t> used;
             for (uint32_t i = 0; i < kTileVerts && v0 + i < nv; ++i) {
@@ -774,7 +1041,6 @@ mmdgpu_status build_plan(const mmdgpu_model_desc& d, const mmdgpu_options* opt, 
                     p.st_local_id[pos * 4] = uint16_t(local_of[0] < 0 ? 0 : local_of[0]);
                 }
             }
-            for (uint32_t r = 0; r < kTileVerts; ++r) rank_vertex[size_t(v0) + r] = uint16_t(order[r]);
             for (uint16_t b : used) local_of[b] = -1;
         }
         p.tile_bone_begin[p.n_tiles] = uint32_t(p.tile_bones.size());

@@ -42,6 +42,23 @@ for t in range(5):                                              # conflict domai
     # wavefronts of one STS of this branch = its worst bank; a group costs the sum over its branches
     deg += d
     mixed |= (present > 0) & (present < 32)
+# palette loads: an LDS.128 takes 2 wavefronts instead of 4 when every aligned lane pair of the (type-uniform) instruction
+# reads the same cell, i.e. agrees on the tile-local bone id at that position (profiles/r02_smem_patterns.txt)
+lid = plan[capi.PLAN_TILE_LOCAL_ID].reshape(-1, 4).astype(np.int64).reshape(n_tiles, TILE, 4)[:, pos]   # [tile][group][lane][k]
+keep_of = {0: 1, 1: 2, 2: 4, 3: 2, 4: 4}
+wf_now = wf_all4 = 0.0
+for t, keep in keep_of.items():
+    m = ty == t
+    if not m.any():
+        continue
+    present = m.any(axis=2)                                     # [tile][group]
+    pair_same_type = m[:, :, 0::2] == m[:, :, 1::2]
+    for k in range(keep):
+        agree = (lid[:, :, 0::2, k] == lid[:, :, 1::2, k]) | ~m[:, :, 0::2]
+        fast = (agree & pair_same_type).all(axis=2) & present
+        wf_now += 6 * (2 * fast.sum() + 4 * (present & ~fast).sum())
+        wf_all4 += 6 * 4 * present.sum()
+print(f"  palette loads: {wf_now / n_tiles:.0f} wavefronts per tile and slot pair ({wf_all4 / n_tiles:.0f} with no pair on the 2-wavefront path)")
 rounds = plan[capi.PLAN_ELL_ROUNDS].astype(np.int64)
 row = plan[capi.PLAN_CSR_ROW_PTR].astype(np.int64)
 real_entries = int(row[-1])

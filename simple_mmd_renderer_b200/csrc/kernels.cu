@@ -983,6 +983,10 @@ __device__ __forceinline__ void skin_qdef(const float4* __restrict__ pal, uint32
 __host__ __device__ inline uint32_t skin_stage_bytes(int layout, bool ext) {
     return layout == MMDGPU_LAYOUT_SOA_POS_NRM ? kTileVerts * (ext ? 32u : 24u) : 0u;  // ext SoA: + UV plane
 }
+// the packed-pair kernel also stages the 32-byte records (16 KB per slot) unless told not to (experiment knob)
+__host__ __device__ constexpr uint32_t skin_pair_stage_bytes(int layout, bool sokol_staged) {
+    return layout == MMDGPU_LAYOUT_SOA_POS_NRM ? kTileVerts * 24u : (sokol_staged ? kTileVerts * 32u : 0u);
+}
 __host__ __device__ inline uint32_t skin_pal_bytes(uint32_t max_tile_bones, bool ext) { return max_tile_bones * (ext ? 80u : 48u); }
 
 constexpr uint32_t kPalPrefetch = 2;  // palette float4 per thread held in registers across the compute phase
@@ -1347,13 +1351,16 @@ __device__ __noinline__ SkinnedP skin_vertex_pair(const ulonglong2* __restrict__
     return r;
 }
 
-template <int LAYOUT, int MIN_CTAS>
+template <int LAYOUT, int MIN_CTAS, bool STAGED>
 __global__ void __launch_bounds__(kSkinThreads, MIN_CTAS) skin_pair_kernel(DevModel M, DevFrames F, uint32_t chunk, uint32_t n_chunks,
                                                                     float arg_neg_zero, float arg_one) {
+    static_assert(STAGED || LAYOUT != MMDGPU_LAYOUT_SOA_POS_NRM, "the planar layout always leaves through staging tiles");
     static_assert(G == 4, "two slot pairs per group");
     constexpr int NP = G / 2;                           // slot pairs per group
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const uint32_t stage_bytes = skin_stage_bytes(LAYOUT, false), pal_bytes = skin_pal_bytes(M.max_tile_bones, false);
+    constexpr bool staged = STAGED;
+    constexpr uint32_t stage_bytes = skin_pair_stage_bytes(LAYOUT, staged);
+    const uint32_t pal_bytes = skin_pal_bytes(M.max_tile_bones, false);
     const uint32_t pal4 = pal_bytes >> 4;               // 16-byte cells per slot; a pair owns 2 * pal4: lo plane, hi plane
     unsigned char* stage_base = smem_raw;
     ulonglong2* pal_base = reinterpret_cast<ulonglong2*>(smem_raw + G * stage_bytes);
@@ -1474,7 +1481,7 @@ __global__ void __launch_bounds__(kSkinThreads, MIN_CTAS) skin_pair_kernel(DevMo
                 IY[0] = add2(IY[0], mul2(EY, r.x, K), K); IY[1] = add2(IY[1], mul2(EY, r.y, K), K);
                 IZ[0] = add2(IZ[0], mul2(EZ, r.x, K), K); IZ[1] = add2(IZ[1], mul2(EZ, r.y, K), K);
             }
-            if (j == 0 && LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) {
+            if (j == 0 && staged) {
                 // the staging tiles are single-buffered: the previous group's bulk copies must have read them
                 if (tid == 0) bulk_wait_read_all();
                 __syncthreads();
@@ -1501,8 +1508,24 @@ __global__ void __launch_bounds__(kSkinThreads, MIN_CTAS) skin_pair_kernel(DevMo
                         sp[0] = h ? hi2(r.px) : lo2(r.px); sp[1] = h ? hi2(r.py) : lo2(r.py); sp[2] = h ? hi2(r.pz) : lo2(r.pz);
                         sn[0] = h ? hi2(r.nx) : lo2(r.nx); sn[1] = h ? hi2(r.ny) : lo2(r.ny); sn[2] = h ? hi2(r.nz) : lo2(r.nz);
                     }
+                } else if (staged) {
+                    // main.cpp:838-859: Vertex{pos * 0.1f, normal, uv}, staged at 32 bytes x PMX index as two 16-byte halves.
+                    // A lane whose index has bit 2 set stores its halves in the opposite order: the 16-byte bank group of a
+                    // store is (2 * index + half) mod 8, so 32 lanes with distinct indices mod 32 cover all eight groups
+                    // evenly in each of the two STS.128 (4 wavefronts each = the floor for 512 bytes).
+                    const f2 T = pk2(0.1f, 0.1f);
+                    const f2 sx = mul2(r.px, T, K), sy = mul2(r.py, T, K), sz = mul2(r.pz, T, K);
+                    const bool flip = (orig[j] & 4u) != 0u;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if ((uint32_t)(2 * p + h) >= n_live) continue;
+                        float4* rec = reinterpret_cast<float4*>(stage_base + (size_t)(2 * p + h) * stage_bytes) + orig[j] * 2u;
+                        const float4 lo = make_float4(h ? hi2(sx) : lo2(sx), h ? hi2(sy) : lo2(sy), h ? hi2(sz) : lo2(sz), h ? hi2(r.nx) : lo2(r.nx));
+                        const float4 hi = make_float4(h ? hi2(r.ny) : lo2(r.ny), h ? hi2(r.nz) : lo2(r.nz), su, sv_);
+                        rec[flip ? 1 : 0] = flip ? hi : lo;
+                        rec[flip ? 0 : 1] = flip ? lo : hi;
+                    }
                 } else if (orig[j] < tile_nv) {
-                    // main.cpp:838-859: Vertex{pos * 0.1f, normal, uv}
                     const f2 T = pk2(0.1f, 0.1f);
                     const f2 sx = mul2(r.px, T, K), sy = mul2(r.py, T, K), sz = mul2(r.pz, T, K);
 #pragma unroll
@@ -1530,7 +1553,7 @@ __global__ void __launch_bounds__(kSkinThreads, MIN_CTAS) skin_pair_kernel(DevMo
             for (uint32_t i = tid + kSkinThreads; i < npad; i += kSkinThreads) nrt[i] = __ldg(gr + i);
         }
         // ---- hand the staged tiles to the bulk-copy engine (the barrier also orders the palette double buffer)
-        if (LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) fence_proxy_async_smem();
+        if (staged) fence_proxy_async_smem();
         __syncthreads();
         if (tid == 0 && LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) {
             const uint32_t b3 = (tile_nv * 12u) & ~15u;
@@ -1548,6 +1571,12 @@ __global__ void __launch_bounds__(kSkinThreads, MIN_CTAS) skin_pair_kernel(DevMo
                     dn[w] = reinterpret_cast<const float*>(stage + kTileVerts * 12u)[w];
                 }
             }
+            bulk_commit();
+        } else if (tid == 0 && staged) {
+            // one copy per slot: the tile's records are contiguous and whole multiples of 16 bytes
+            for (uint32_t f = 0; f < n_live; ++f)
+                bulk_s2g(F.out_inter + (size_t)(g0 + f) * F.inter_stride + (size_t)tile * kTileVerts * 2u,
+                         stage_base + (size_t)f * stage_bytes, tile_nv * 32u);
             bulk_commit();
         }
     }
@@ -1659,10 +1688,35 @@ cudaError_t launch_hierarchy_wave_flat(cudaStream_t st, const DevModel& M, const
     return cudaGetLastError();
 }
 
+static bool skin_runs_pair_kernel(const DevModel& M) {
+    static const bool scalar = [] { const char* e = std::getenv("MMDGPU_SKIN_SCALAR"); return e && e[0] == '1'; }();
+    return !M.extensions && !M.global_palette && !scalar;
+}
+static size_t skin_smem_rest(const DevModel& M) {   // palettes and rates, both double-buffered
+    return 2 * (size_t)kSlotGroup * skin_pal_bytes(M.max_tile_bones, M.extensions != 0) + 2 * (size_t)M.n_nodes_pad * 16;
+}
+// The packed-pair kernel stages the 32-byte records too (16 KB per slot, one bulk copy per tile and slot) as long as three
+// CTAs still fit an SM (228 KB, 1 KB reserved per CTA); larger tile palettes / more morph nodes keep the direct 256-bit
+// stores.  MMDGPU_SOKOL_STAGED=0|1 forces either form (tests, A/B).
+bool skin_sokol_staged(const DevModel& M, const DevFrames& F) {
+    static const int forced = [] { const char* e = std::getenv("MMDGPU_SOKOL_STAGED"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+    if (!skin_runs_pair_kernel(M)) return false;
+    // measured (profiles/r02_experiments.md): +6 % on a bake of the 1 M-vertex model, -14 % on the crowd of 50 k-vertex
+    // instances, whose lighter per-vertex work leaves the extra selects, moves and barriers of the staged form exposed
+    if (forced < 0 && F.n_frames <= 1) return false;
+    const size_t bytes = (size_t)kSlotGroup * skin_pair_stage_bytes(MMDGPU_LAYOUT_INTERLEAVED_SOKOL32, true) + skin_smem_rest(M);
+    if (forced >= 0) return forced == 1 && bytes + 1024 <= 227 * 1024;
+    return 3 * (bytes + 1024) <= 228 * 1024;
+}
+
+// upper bound over the forms a frames object of this model may run (load-time check)
 size_t skin_smem_bytes(const DevModel& M, int layout) {
-    const bool ext = M.extensions != 0;
-    return (size_t)kSlotGroup * skin_stage_bytes(layout, ext) + 2 * (size_t)kSlotGroup * skin_pal_bytes(M.max_tile_bones, ext) +
-           2 * (size_t)M.n_nodes_pad * 16;
+    const uint32_t stage = skin_runs_pair_kernel(M) ? skin_pair_stage_bytes(layout, false) : skin_stage_bytes(layout, M.extensions != 0);
+    return (size_t)kSlotGroup * stage + skin_smem_rest(M);
+}
+static size_t skin_launch_smem_bytes(const DevModel& M, const DevFrames& F, int layout) {
+    if (!skin_runs_pair_kernel(M)) return skin_smem_bytes(M, layout);
+    return (size_t)kSlotGroup * skin_pair_stage_bytes(layout, skin_sokol_staged(M, F)) + skin_smem_rest(M);
 }
 
 // The dynamic shared-memory opt-in is an attribute of the kernel function (per device), not of a launch: every model
@@ -1690,8 +1744,9 @@ cudaError_t prepare_skin_kernels(const DevModel& M) {
     if ((e = skin_opt_in<I32, false, true>(limit)) != cudaSuccess) return e;
     if ((e = skin_opt_in<SOA, false, false>(limit)) != cudaSuccess) return e;
     if ((e = skin_opt_in<I32, false, false>(limit)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(skin_pair_kernel<SOA, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit)) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(skin_pair_kernel<I32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+    if ((e = cudaFuncSetAttribute(skin_pair_kernel<SOA, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(skin_pair_kernel<I32, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(skin_pair_kernel<I32, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
 }
 
 cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, int layout, uint32_t slots_per_cta) {
@@ -1699,7 +1754,7 @@ cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, 
     slots_per_cta = (std::max<uint32_t>(slots_per_cta, 1u) + kSlotGroup - 1) / kSlotGroup * kSlotGroup;  // whole slot groups
     const uint32_t n_chunks = (F.n_slots + slots_per_cta - 1) / slots_per_cta;
     const uint32_t grid = M.n_tiles * n_chunks;
-    const size_t smem = skin_smem_bytes(M, layout);
+    const size_t smem = skin_launch_smem_bytes(M, F, layout);
     const bool soa = layout == MMDGPU_LAYOUT_SOA_POS_NRM;
     constexpr int SOA = MMDGPU_LAYOUT_SOA_POS_NRM, I32 = MMDGPU_LAYOUT_INTERLEAVED_SOKOL32;
 #define MMDGPU_LAUNCH_SKIN(EXT, PALG)                                                                                  \
@@ -1712,8 +1767,9 @@ cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, 
     if (M.extensions) MMDGPU_LAUNCH_SKIN(true, false);
     else if (M.global_palette) MMDGPU_LAUNCH_SKIN(false, true);
     else if (scalar) MMDGPU_LAUNCH_SKIN(false, false);
-    else if (soa) skin_pair_kernel<SOA, 3><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks, -0.0f, 1.0f);
-    else skin_pair_kernel<I32, 3><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks, -0.0f, 1.0f);
+    else if (soa) skin_pair_kernel<SOA, 3, true><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks, -0.0f, 1.0f);
+    else if (skin_sokol_staged(M, F)) skin_pair_kernel<I32, 3, true><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks, -0.0f, 1.0f);
+    else skin_pair_kernel<I32, 3, false><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks, -0.0f, 1.0f);
 #undef MMDGPU_LAUNCH_SKIN
     return cudaGetLastError();
 }

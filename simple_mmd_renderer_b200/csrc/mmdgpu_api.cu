@@ -22,6 +22,9 @@
 using namespace mmdgpu;
 
 // ------------------------------------------------------------------------------------------- handles
+constexpr int kPreStreams = 8;                   // hierarchy chains of fused updates in flight
+constexpr int kStateCopies = kPreStreams + 1;    // copies of the per-update state
+
 struct mmdgpu_context {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -30,14 +33,18 @@ struct mmdgpu_context {
     cudaEvent_t dl_event = nullptr;
     // fused updates run key-frame sampling and the bone hierarchy of update n+1 on this stream while the skinning
     // kernel of update n still runs on `stream`
-    // (two of them: consecutive updates alternate, so that the latency-bound hierarchy chains of two updates overlap)
-    cudaStream_t pre_stream[2] = {nullptr, nullptr};
+    // (kPreStreams of them, taken in turn, so that the latency-bound hierarchy chains of consecutive updates overlap each
+    // other: a batch of CCD IK solves is one dependent chain of ~0.2 ms that occupies a few hundred threads)
+    cudaStream_t pre_stream[kPreStreams] = {};
     // same, highest priority: for models with CCD IK, whose hierarchy kernel is a long latency-bound chain that
     // should claim SM resources as soon as CTAs of the running skinning kernel retire
-    cudaStream_t pre_stream_hi[2] = {nullptr, nullptr};
+    cudaStream_t pre_stream_hi[kPreStreams] = {};
+    int n_pre_ik = kPreStreams;                   // streams a model with CCD IK uses (MMDGPU_PRE_STREAMS=1..8, experiment knob)
+    int n_pre_plain = 2;                          // ... and a model without: its hierarchy is short, deeper buys nothing
     cudaError_t sync_pre() {
-        for (cudaStream_t st : {pre_stream[0], pre_stream[1], pre_stream_hi[0], pre_stream_hi[1]})
-            if (st) { cudaError_t e = cudaStreamSynchronize(st); if (e != cudaSuccess) return e; }
+        for (int i = 0; i < kPreStreams; ++i)
+            for (cudaStream_t st : {pre_stream[i], pre_stream_hi[i]})
+                if (st) { cudaError_t e = cudaStreamSynchronize(st); if (e != cudaSuccess) return e; }
         return cudaSuccess;
     }
     std::string err;
@@ -100,7 +107,6 @@ struct mmdgpu_animation {
     DevArena mem;
 };
 
-constexpr int kStateCopies = 3;
 
 struct mmdgpu_frames {
     mmdgpu_context_t ctx = nullptr;
@@ -115,8 +121,8 @@ struct mmdgpu_frames {
     uint32_t slots_per_cta = 1;
     // Everything one fused update writes before its skinning kernel runs - sampled poses and rates, the hierarchy state
     // that crosses launches, and what the hierarchy hands to the skinning kernel (palette, extension palette,
-    // application-slot rates) - exists kStateCopies = 3 times, used round-robin: updates n+1 and n+2 sample and run their
-    // hierarchies (on the two alternating pre streams) while update n's skinning kernel still reads its own copy.
+    // application-slot rates) - exists kStateCopies = kPreStreams + 1 times, used round-robin: updates n+1 .. n+kPreStreams
+    // sample and run their hierarchies (on the pre streams, in turn) while update n's skinning kernel still reads its copy.
     struct StateSet {
         float4 *poseR = nullptr, *poseT = nullptr, *totR = nullptr, *totT = nullptr, *ikR = nullptr, *preIK = nullptr,
                *morphR = nullptr, *morphT = nullptr, *palette = nullptr, *pal_ext = nullptr;
@@ -127,7 +133,7 @@ struct mmdgpu_frames {
         std::vector<uint64_t> bound;            // uid of the clip whose DevAnim each entry of d_anims currently holds
     } set[kStateCopies];
     int cur = 0;                                  // copy the step-wise entry points and the downloads use
-    int update_parity = 0;                        // which of the two pre streams the last fused update used
+    int update_turn = 0;                          // which of the pre streams the last fused update used
     cudaEvent_t ev_pre[kStateCopies] = {};    // hierarchy of the update that wrote copy i has finished
     cudaEvent_t ev_skin[kStateCopies] = {};   // skinning that read copy i has finished
     bool skin_recorded[kStateCopies] = {};
@@ -370,7 +376,7 @@ mmdgpu_status upload_model(mmdgpu_model* m) {
     }
     CU(ctx, cudaStreamSynchronize(ctx->stream));  // the staging vectors above die with this frame
 
-    const size_t smem = skin_smem_bytes(D, MMDGPU_LAYOUT_INTERLEAVED_SOKOL32);
+    const size_t smem = std::max(skin_smem_bytes(D, MMDGPU_LAYOUT_INTERLEAVED_SOKOL32), skin_smem_bytes(D, MMDGPU_LAYOUT_SOA_POS_NRM));
     if (smem + 1024 > size_t(ctx->max_smem_optin))
         return set_err(ctx, MMDGPU_ERR_UNSUPPORTED,
                        "tile palettes + morph slot rates (" + std::to_string(smem) + " B) exceed shared memory per CTA");
@@ -635,7 +641,8 @@ MMDGPU_API mmdgpu_status mmdgpu_context_create(int device, void* cuda_stream_or_
     {
         int least = 0, greatest = 0;
         cudaDeviceGetStreamPriorityRange(&least, &greatest);
-        for (int i = 0; i < 2; ++i) {
+        if (const char* env = std::getenv("MMDGPU_PRE_STREAMS")) c->n_pre_ik = std::min(kPreStreams, std::max(1, std::atoi(env)));
+        for (int i = 0; i < kPreStreams; ++i) {
             if ((e = cudaStreamCreateWithFlags(&c->pre_stream[i], cudaStreamNonBlocking)) != cudaSuccess)
                 return cuda_fail(nullptr, e, "cudaStreamCreate");
             if ((e = cudaStreamCreateWithPriority(&c->pre_stream_hi[i], cudaStreamNonBlocking, greatest)) != cudaSuccess)
@@ -652,7 +659,7 @@ MMDGPU_API void mmdgpu_context_destroy(mmdgpu_context_t ctx) {
     ctx->sync_pre();
     cudaStreamSynchronize(ctx->stream);
     if (ctx->dl_stream) { cudaStreamSynchronize(ctx->dl_stream); cudaStreamDestroy(ctx->dl_stream); }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kPreStreams; ++i) {
         if (ctx->pre_stream[i]) cudaStreamDestroy(ctx->pre_stream[i]);
         if (ctx->pre_stream_hi[i]) cudaStreamDestroy(ctx->pre_stream_hi[i]);
     }
@@ -1281,15 +1288,16 @@ static mmdgpu_status update_common(mmdgpu_frames_t f, const mmdgpu_animation_t* 
     // arguments are checked before anything rotates: a rejected call leaves `cur` on the copy of the last good update
     if (!frames) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "frame id array is NULL");
     if (mmdgpu_status s = check_anims(f, per_instance)) return s;
-    const int next = (f->cur + 1) % kStateCopies;
     const bool has_ik = !f->model->plan.plan.iks.empty();
-    f->update_parity ^= 1;
-    cudaStream_t pre = has_ik ? ctx->pre_stream_hi[f->update_parity] : ctx->pre_stream[f->update_parity];
+    const int n_pre = has_ik ? ctx->n_pre_ik : ctx->n_pre_plain;
+    const int next = (f->cur + 1) % (n_pre + 1);
+    f->update_turn = (f->update_turn + 1) % n_pre;
+    cudaStream_t pre = has_ik ? ctx->pre_stream_hi[f->update_turn] : ctx->pre_stream[f->update_turn];
     if (f->skin_recorded[next]) CU(ctx, cudaStreamWaitEvent(pre, f->ev_skin[next], 0));
     if (f->main_dirty) {  // step-wise calls / uploads issued on the main stream since the last fused update
         CU(ctx, cudaEventRecord(f->ev_main, ctx->stream));
         // any copy may have been touched from the main stream: the update after this one waits as well
-        for (int i = 0; i < 2; ++i) CU(ctx, cudaStreamWaitEvent(has_ik ? ctx->pre_stream_hi[i] : ctx->pre_stream[i], f->ev_main, 0));
+        for (int i = 0; i < kPreStreams; ++i) CU(ctx, cudaStreamWaitEvent(has_ik ? ctx->pre_stream_hi[i] : ctx->pre_stream[i], f->ev_main, 0));
         f->main_dirty = false;
     }
     f->select(next);

@@ -385,7 +385,10 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_wait_downloads(mmdgpu_frames_t frames);
 MMDGPU_API int           mmdgpu_frames_downloads_done(mmdgpu_frames_t frames);
 /* Zero-copy hand-off (replaces the CPU repack + sg_update_buffer of main.cpp:820-863): let the skinning kernel write
  * one vertex output stream straight into caller-owned DEVICE memory - e.g. the pointer cudaGraphicsResourceGetMappedPointer
- * returns for sokol's GL vertex buffer (sg_gl_query_buffer_info, 3rd_party/sokol/sokol_gfx.h:5213).
+ * returns for sokol's GL vertex buffer (sg_gl_query_buffer_info, 3rd_party/sokol/sokol_gfx.h:5213) - or
+ * into PAGE-LOCKED HOST memory (mmdgpu_host_alloc / cudaHostAlloc / cudaHostRegister): the kernel's stores then cross
+ * PCIe while it computes and Poser::pose_image (L/motion/poser.inl:17-20) needs no copy of its own, only
+ * mmdgpu_frames_wait_skinning before the host reads it (what mmdgpu::Poser of mmdgpu.hpp does).
  * id: POSITION / NORMAL (SoA frames), INTERLEAVED (sokol32 frames: main.cpp:50-54 records, positions x0.1, static UV),
  * UV (extensions).  Slot s is written at device_ptr + s * slot_stride_bytes; exactly n_vertices records per slot are
  * stored (no padding).  device_ptr and slot_stride_bytes must be 16-byte aligned (32 for INTERLEAVED).
@@ -394,6 +397,10 @@ MMDGPU_API int           mmdgpu_frames_downloads_done(mmdgpu_frames_t frames);
  * mmdgpu_frames_device_ptr / _download[_async] follow the binding. */
 MMDGPU_API mmdgpu_status mmdgpu_frames_bind_output(mmdgpu_frames_t frames, mmdgpu_stream_id id, void* device_ptr,
                                                    size_t slot_stride_bytes);
+/* Block the calling thread until the most recent skinning launch of this frames object (mmdgpu_deform or a fused update)
+ * has finished: its bound or library-owned outputs are then complete and, when bound to page-locked host memory, visible
+ * to the host.  Does not wait for other frames objects or for downloads. */
+MMDGPU_API mmdgpu_status mmdgpu_frames_wait_skinning(mmdgpu_frames_t frames);
 /* BoneImage::skinning_matrix_ / local_matrix_ of one slot as nb x 16 floats (parity on bone globals). */
 MMDGPU_API mmdgpu_status mmdgpu_bone_matrices_download(mmdgpu_frames_t frames, uint32_t slot, float* host_dst);
 MMDGPU_API mmdgpu_status mmdgpu_bone_local_matrices_download(mmdgpu_frames_t frames, uint32_t slot, float* host_dst);

@@ -15,6 +15,7 @@
 #define MMDGPU_HPP_INCLUDED
 
 #include <cstddef>
+#include <cstdlib>
 #include <cstdint>
 #include <cstdio>
 #include <stdexcept>
@@ -120,9 +121,9 @@ private:
 
 class Poser {
 public:
-    // Poser::pose_image (L/motion/poser.inl:17-20).  The device owns the deformed buffer; the two vectors here are
-    // host mirrors in page-locked memory, filled together (two asynchronous copies, one wait) on first access
-    // after Deform().
+    // Poser::pose_image (L/motion/poser.inl:17-20).  The two vectors live in one page-locked host block that the
+    // skinning kernel writes DIRECTLY (mmdgpu_frames_bind_output on host memory): Deform() is the transfer, the first
+    // access afterwards only waits for that kernel (mmdgpu_frames_wait_skinning).
     class LazyVectors {
     public:
         size_t size() const { return owner_->model_.GetVertexNum(); }
@@ -150,15 +151,24 @@ public:
           model_(model),
           layout_(layout) {
         check(mmdgpu_frames_create(model.context().handle(), model.handle(), 1, 1, layout, &frames_), "mmdgpu_frames_create");
-        // one page-locked block: coordinates, then normals (filled by a single transfer, mmdgpu_frames_download_pair_async)
-        const size_t bytes = model.GetVertexNum() * sizeof(Vector3f);
+        // one page-locked block: coordinates, then normals at the next 16-byte boundary (bound outputs are 16-byte aligned)
+        const size_t bytes = model.GetVertexNum() * sizeof(Vector3f), nrm_at = (bytes + 15) / 16 * 16;
         void* a = nullptr;
-        if (mmdgpu_host_alloc(2 * bytes, &a) != MMDGPU_OK) {
+        if (mmdgpu_host_alloc(nrm_at + bytes, &a) != MMDGPU_OK) {
             mmdgpu_frames_destroy(frames_);
             throw Error(MMDGPU_ERR_OOM, "page-locked pose_image allocation failed");
         }
         pose_image.coordinates.host_ = static_cast<Vector3f*>(a);
-        pose_image.normals.host_ = static_cast<Vector3f*>(a) + model.GetVertexNum();
+        pose_image.normals.host_ = reinterpret_cast<Vector3f*>(static_cast<char*>(a) + nrm_at);
+        if (layout == MMDGPU_LAYOUT_SOA_POS_NRM && bytes) {
+            // MMDGPU_POSE_IMAGE_COPY=1 keeps the deformed buffer on the device and copies it on first access instead
+            const char* e = std::getenv("MMDGPU_POSE_IMAGE_COPY");
+            if (!(e && e[0] == '1') &&
+                mmdgpu_frames_bind_output(frames_, MMDGPU_STREAM_POSITION, pose_image.coordinates.host_, nrm_at) == MMDGPU_OK) {
+                if (mmdgpu_frames_bind_output(frames_, MMDGPU_STREAM_NORMAL, pose_image.normals.host_, nrm_at) == MMDGPU_OK) host_bound_ = true;
+                else mmdgpu_frames_bind_output(frames_, MMDGPU_STREAM_POSITION, nullptr, 0);
+            }
+        }
         ResetPosing();
         Deform();
     }
@@ -282,10 +292,17 @@ private:
     void Fetch() {
         Flush();
         if (image_valid_) return;
-        if (layout_ == MMDGPU_LAYOUT_SOA_POS_NRM) {
+        if (host_bound_) {
+            check(mmdgpu_frames_wait_skinning(frames_), "mmdgpu_frames_wait_skinning");   // the kernel wrote pose_image itself
+        } else if (layout_ == MMDGPU_LAYOUT_SOA_POS_NRM) {
             const size_t bytes = model_.GetVertexNum() * sizeof(Vector3f);
-            check(mmdgpu_frames_download_pair_async(frames_, 0, pose_image.coordinates.host_, 2 * bytes), "mmdgpu_frames_download_pair_async");
-            check(mmdgpu_frames_wait_downloads(frames_), "mmdgpu_frames_wait_downloads");   // this copy only, not the whole context
+            if (bytes % 16 == 0) {   // the planes are adjacent on the device and on the host: one transfer
+                check(mmdgpu_frames_download_pair_async(frames_, 0, pose_image.coordinates.host_, 2 * bytes), "mmdgpu_frames_download_pair_async");
+            } else {
+                check(mmdgpu_frames_download_async(frames_, 0, 1, MMDGPU_STREAM_POSITION, pose_image.coordinates.host_, bytes), "mmdgpu_frames_download_async");
+                check(mmdgpu_frames_download_async(frames_, 0, 1, MMDGPU_STREAM_NORMAL, pose_image.normals.host_, bytes), "mmdgpu_frames_download_async");
+            }
+            check(mmdgpu_frames_wait_downloads(frames_), "mmdgpu_frames_wait_downloads");   // these copies only, not the whole context
         } else {
             throw Error(MMDGPU_ERR_INVALID_ARG, "pose_image needs the SoA layout; interleaved Posers use DownloadInterleaved or a bound output");
         }
@@ -295,6 +312,7 @@ private:
     mmdgpu_layout layout_;
     mmdgpu_frames_t frames_ = nullptr;
     bool image_valid_ = false;
+    bool host_bound_ = false;                     // the skinning kernel writes pose_image's host block directly
     unsigned pending_ = kNone;
     mmdgpu_animation_t seek_anim_ = nullptr;
     bool seek_by_time_ = false;

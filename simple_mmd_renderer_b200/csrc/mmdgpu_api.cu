@@ -141,6 +141,8 @@ struct mmdgpu_frames {
     bool main_dirty = true;
     // The vertex output streams are single-buffered: a skinning kernel must not overwrite them while an asynchronous
     // download of the previous update is still reading.  ev_dl follows the last copy issued on the download stream.
+    cudaEvent_t ev_deform = nullptr;              // follows the last step-wise mmdgpu_deform
+    cudaEvent_t last_skin = nullptr;              // event behind the most recent skinning launch (fused or step-wise)
     cudaEvent_t ev_dl = nullptr;
     bool dl_pending = false;                      // a skinning launch has yet to wait for ev_dl
     bool dl_recorded = false;                     // ev_dl has been recorded at least once
@@ -166,6 +168,7 @@ struct mmdgpu_frames {
         }
         if (ev_main) cudaEventDestroy(ev_main);
         if (ev_dl) cudaEventDestroy(ev_dl);
+        if (ev_deform) cudaEventDestroy(ev_deform);
     }
 };
 
@@ -494,7 +497,9 @@ mmdgpu_status do_seek(mmdgpu_frames* f, const mmdgpu_animation_t* per_instance, 
 // chain-local images, between segments of the CTA-per-slot kernel (kernels.cu); below it one launch wins.
 // B200, C2 (two chains per slot), G vertex-frames/s with / without: 256 slots 63.9 / 61.1, 512 slots 90.2 / 71.4,
 // 1024 slots 102 / 72, 2048 slots 110.9 / 77.4 (profiles/r01_experiments.md).
-constexpr uint32_t kIkSplitMinSlots = 256;
+// Round 2, with up to eight updates' hierarchies in flight (the CTA kernel holds 34 KB of shared memory per slot for the
+// whole solve, the flat kernel almost nothing): 128 slots 59.7 / 51.9, 256 slots 79.3 / 64.2 (profiles/r02_experiments.md).
+constexpr uint32_t kIkSplitMinSlots = 128;
 constexpr size_t kIkSplitMaxWaves = 4;
 
 static bool split_ik_waves(const mmdgpu_frames* f) {
@@ -1084,6 +1089,7 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_create(mmdgpu_context_t ctx, mmdgpu_model
     CU(ctx, cudaEventCreateWithFlags(&f->ev_main, cudaEventDisableTiming));
     f->select(0);
     CU(ctx, cudaEventCreateWithFlags(&f->ev_dl, cudaEventDisableTiming));
+    CU(ctx, cudaEventCreateWithFlags(&f->ev_deform, cudaEventDisableTiming));
     if (layout == MMDGPU_LAYOUT_SOA_POS_NRM) {
         // one allocation, position planes then normal planes: a one-slot object (an interactive Poser) can hand both to the
         // host with a single copy (mmdgpu_frames_download_pair_async)
@@ -1251,7 +1257,10 @@ MMDGPU_API mmdgpu_status mmdgpu_deform(mmdgpu_frames_t f) {
     // this launch reads state copy `cur` from the main stream: the fused updates' pre streams, which rewrite the copies
     // round-robin, must follow it (ev_main)
     f->main_dirty = true;
-    return do_skin(f);
+    if (mmdgpu_status s = do_skin(f)) return s;
+    CU(f->ctx, cudaEventRecord(f->ev_deform, f->ctx->stream));
+    f->last_skin = f->ev_deform;
+    return MMDGPU_OK;
 }
 
 MMDGPU_API mmdgpu_status mmdgpu_set_skinning_matrix_override(mmdgpu_frames_t f, uint32_t slot, uint32_t bone,
@@ -1309,6 +1318,7 @@ static mmdgpu_status update_common(mmdgpu_frames_t f, const mmdgpu_animation_t* 
     if (mmdgpu_status s = do_skin(f)) return s;
     CU(ctx, cudaEventRecord(f->ev_skin[next], ctx->stream));
     f->skin_recorded[next] = true;
+    f->last_skin = f->ev_skin[next];
     return MMDGPU_OK;
 }
 
@@ -1343,7 +1353,7 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_download(mmdgpu_frames_t f, uint32_t slot
     StreamView v{};
     if (mmdgpu_status s = stream_view(f, id, v)) return s;
     if (bytes != v.slot_bytes) return set_err(f->ctx, MMDGPU_ERR_INVALID_ARG, "bytes must equal the size of one slot of the stream");
-    if (bytes) CU(f->ctx, cudaMemcpyAsync(host_dst, v.base + size_t(slot) * v.slot_stride, bytes, cudaMemcpyDeviceToHost, f->ctx->stream));
+    if (bytes) CU(f->ctx, cudaMemcpyAsync(host_dst, v.base + size_t(slot) * v.slot_stride, bytes, cudaMemcpyDefault, f->ctx->stream));
     CU(f->ctx, cudaStreamSynchronize(f->ctx->stream));
     return MMDGPU_OK;
 }
@@ -1363,10 +1373,10 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_download_async(mmdgpu_frames_t f, uint32_
     CU(ctx, cudaStreamWaitEvent(ctx->dl_stream, ctx->dl_event, 0));
     const char* src = v.base + size_t(first_slot) * v.slot_stride;
     if (v.slot_bytes == v.slot_stride || n_slots == 1)   // contiguous: one plain copy
-        CU(ctx, cudaMemcpyAsync(pinned_host_dst, src, bytes, cudaMemcpyDeviceToHost, ctx->dl_stream));
+        CU(ctx, cudaMemcpyAsync(pinned_host_dst, src, bytes, cudaMemcpyDefault, ctx->dl_stream));
     else
         CU(ctx, cudaMemcpy2DAsync(pinned_host_dst, v.slot_bytes, src, v.slot_stride, v.slot_bytes, n_slots,
-                                  cudaMemcpyDeviceToHost, ctx->dl_stream));
+                                  cudaMemcpyDefault, ctx->dl_stream));
     CU(ctx, cudaEventRecord(f->ev_dl, ctx->dl_stream));
     f->dl_pending = f->dl_recorded = true;
     return MMDGPU_OK;
@@ -1389,10 +1399,10 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_download_pair_async(mmdgpu_frames_t f, ui
     CU(ctx, cudaStreamWaitEvent(ctx->dl_stream, ctx->dl_event, 0));
     char* dst = static_cast<char*>(pinned_host_dst);
     if (nrm == pos + plane)   // one-slot object with unpadded planes next to each other: one transfer
-        CU(ctx, cudaMemcpyAsync(dst, pos, bytes, cudaMemcpyDeviceToHost, ctx->dl_stream));
+        CU(ctx, cudaMemcpyAsync(dst, pos, bytes, cudaMemcpyDefault, ctx->dl_stream));
     else {
-        CU(ctx, cudaMemcpyAsync(dst, pos, plane, cudaMemcpyDeviceToHost, ctx->dl_stream));
-        CU(ctx, cudaMemcpyAsync(dst + plane, nrm, plane, cudaMemcpyDeviceToHost, ctx->dl_stream));
+        CU(ctx, cudaMemcpyAsync(dst, pos, plane, cudaMemcpyDefault, ctx->dl_stream));
+        CU(ctx, cudaMemcpyAsync(dst + plane, nrm, plane, cudaMemcpyDefault, ctx->dl_stream));
     }
     CU(ctx, cudaEventRecord(f->ev_dl, ctx->dl_stream));
     f->dl_pending = f->dl_recorded = true;
@@ -1403,6 +1413,13 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_wait_downloads(mmdgpu_frames_t f) {
     if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
     if (mmdgpu_status s = enter(f->ctx)) return s;
     if (f->dl_recorded) CU(f->ctx, cudaEventSynchronize(f->ev_dl));
+    return MMDGPU_OK;
+}
+
+MMDGPU_API mmdgpu_status mmdgpu_frames_wait_skinning(mmdgpu_frames_t f) {
+    if (!f) return set_err(nullptr, MMDGPU_ERR_INVALID_ARG, "frames is NULL");
+    if (mmdgpu_status s = enter(f->ctx)) return s;
+    if (f->last_skin) CU(f->ctx, cudaEventSynchronize(f->last_skin));
     return MMDGPU_OK;
 }
 
@@ -1449,9 +1466,14 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_bind_output(mmdgpu_frames_t f, mmdgpu_str
     if (slot_stride_bytes < size_t(M.nv) * rec && F.n_slots > 1)
         return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "slot stride is smaller than one slot of the stream");
     cudaPointerAttributes attr{};
-    if (cudaPointerGetAttributes(&attr, device_ptr) != cudaSuccess || (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)) {
+    if (cudaPointerGetAttributes(&attr, device_ptr) != cudaSuccess) attr.type = cudaMemoryTypeUnregistered;
+    if (attr.type == cudaMemoryTypeHost && attr.devicePointer) {
+        // page-locked host memory (mmdgpu_host_alloc, cudaHostAlloc, cudaHostRegister): the skinning kernel's stores travel
+        // over PCIe while it computes; no separate device-to-host copy
+        device_ptr = attr.devicePointer;
+    } else if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged) {
         cudaGetLastError();
-        return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "bound output pointer is not device memory");
+        return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "bound output pointer is neither device memory nor page-locked host memory");
     }
     if (id == MMDGPU_STREAM_POSITION) { F.out_pos = static_cast<float*>(device_ptr); F.pos_stride = slot_stride_bytes / 4; }
     else if (id == MMDGPU_STREAM_NORMAL) { F.out_nrm = static_cast<float*>(device_ptr); F.nrm_stride = slot_stride_bytes / 4; }

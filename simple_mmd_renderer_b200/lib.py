@@ -90,6 +90,7 @@ SIGNATURES = {
     "mmdgpu_frames_download_async": (C.c_int, [_vp, _u32, _u32, C.c_int, _vp, _sz]),
     "mmdgpu_frames_download_pair_async": (C.c_int, [_vp, _u32, _vp, _sz]),
     "mmdgpu_frames_wait_downloads": (C.c_int, [_vp]),
+    "mmdgpu_frames_wait_skinning": (C.c_int, [_vp]),
     "mmdgpu_frames_downloads_done": (C.c_int, [_vp]),
     "mmdgpu_frames_bind_output": (C.c_int, [_vp, C.c_int, _vp, _sz]),
     "mmdgpu_bone_matrices_download": (C.c_int, [_vp, _u32, _vp]),

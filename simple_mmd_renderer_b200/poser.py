@@ -295,6 +295,10 @@ class Frames:
     def download_pair_async(self, slot: int, pinned_ptr: int, nbytes: int):
         check(self.lib.mmdgpu_frames_download_pair_async(self.h, int(slot), C.c_void_p(pinned_ptr), int(nbytes)), self.ctx.h)
 
+    def wait_skinning(self):
+        """Blocks until the latest skinning launch of this object has finished (bound host outputs are then complete)."""
+        check(self.lib.mmdgpu_frames_wait_skinning(self.h), self.ctx.h)
+
     def wait_downloads(self):
         """Host-blocks until this object's download_async copies have landed (not compute, not other objects)."""
         check(self.lib.mmdgpu_frames_wait_downloads(self.h), self.ctx.h)

@@ -31,7 +31,7 @@ def test_clip_destroyed_and_another_created_is_not_mistaken_for_the_first(ctx):
     for round_ in range(4):
         motion = synth.make_motion(cfg, model, instance=round_)     # a different clip every round
         a = Motion(m, motion)
-        for _ in range(3):                                          # all three rotating state copies see this clip
+        for _ in range(10):                                         # every rotating state copy sees this clip
             fr.update(a, frames)
         orc = _oracle(model, motion)
         for k, f in enumerate(frames):
@@ -161,6 +161,46 @@ def test_bound_soa_outputs_with_ragged_last_tile(ctx, nv):
         fr.bind_output(capi.STREAM_POSITION, pos.data_ptr() + 4, stride)      # misaligned
     with pytest.raises(MmdGpuError):
         fr.bind_output(capi.STREAM_INTERLEAVED, pos.data_ptr(), stride)       # wrong layout
+
+
+@pytest.mark.parametrize("nv", [3000, 3002])
+def test_outputs_bound_to_page_locked_host_memory(ctx, nv):
+    """POSITION / NORMAL bound to pinned HOST memory: the skinning kernel's stores cross PCIe themselves, the host reads
+    the planes after mmdgpu_frames_wait_skinning - no device-to-host copy (what mmdgpu::Poser::pose_image does).  Both
+    the fused update and the step-wise Deform are covered; bytes outside the records stay untouched."""
+    import torch
+    cfg = replace(synth.TINY_FULL, n_vertices=nv, name=f"tiny_full_{nv}")
+    model = synth.make_model(cfg)
+    motion = synth.make_motion(cfg, model)
+    m = Model(ctx, model)
+    a = Motion(m, motion)
+    orc = _oracle(model, motion)
+    stride = (nv * 12 + 15) // 16 * 16
+    for n_slots in (1, 3):
+        fr = Frames(m, 1, n_slots)
+        guard = 256
+        host = torch.full((2 * n_slots * stride + guard,), 0xAB, dtype=torch.uint8).pin_memory()
+        fr.bind_output(capi.STREAM_POSITION, host.data_ptr(), stride)
+        fr.bind_output(capi.STREAM_NORMAL, host.data_ptr() + n_slots * stride, stride)
+        frames = [7, 40, 88][:n_slots]
+        for rep in range(2):
+            if rep == 0:
+                fr.update(a, frames)
+            else:   # libmmd's call sequence, one call at a time
+                frames = [f + 3 for f in frames]
+                fr.reset_posing(); fr.seek_frame(a, frames); fr.pre_physics_posing(); fr.post_physics_posing(); fr.deform()
+            fr.wait_skinning()
+            g = host.numpy()
+            for k, f in enumerate(frames):
+                ref = orc.run_frame(f)
+                assert_bitwise(g[k * stride:k * stride + nv * 12].view(np.float32).reshape(nv, 3), ref["pos"], f"host-bound positions, frame {f}")
+                o = (n_slots + k) * stride
+                assert_bitwise(g[o:o + nv * 12].view(np.float32).reshape(nv, 3), ref["nrm"], f"host-bound normals, frame {f}")
+                assert (g[k * stride + nv * 12:(k + 1) * stride] == 0xAB).all()
+            assert (g[2 * n_slots * stride:] == 0xAB).all()
+        fr.close()
+    with pytest.raises(MmdGpuError):
+        Frames(m, 1, 1).bind_output(capi.STREAM_POSITION, np.zeros(nv * 3 + 8, np.float32).ctypes.data // 16 * 16 + 16, stride)   # pageable memory
 
 
 def test_bake_driver_hands_a_window_to_the_sink_while_the_next_one_runs(ctx):

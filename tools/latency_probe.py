@@ -17,9 +17,12 @@ open(os.path.join(d, "m.vmd"), "wb").write(pmxio.write_vmd(motion))
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 exe = os.path.join(d, "headless_update")
 subprocess.run(["g++", "-std=c++14", "-O2", f"-I{root}/include", f"{root}/examples/headless_update.cc", lib.SO_PATH, "-o", exe], check=True)
-for _ in range(2):
-    r = subprocess.run([exe, os.path.join(d, "m.pmx"), os.path.join(d, "m.vmd"), "0", "300"], capture_output=True, text=True)
-print(r.stdout.strip())
+for mode, label in (("0", "pose_image written by the skinning kernel (page-locked host block bound as its output)"),
+                    ("1", "pose_image copied from the device on first access (MMDGPU_POSE_IMAGE_COPY=1)")):
+    for _ in range(3):
+        r = subprocess.run([exe, os.path.join(d, "m.pmx"), os.path.join(d, "m.vmd"), "0", "300"], capture_output=True, text=True,
+                           env=dict(os.environ, MMDGPU_POSE_IMAGE_COPY=mode))
+    print(label + ":\n  " + r.stdout.strip().replace("\n", "\n  "))
 ses = oracle.Reference(model, motion) if oracle.have_reference() else oracle.Restatement(model, motion)
 sec, _ = ses.time_frames(np.arange(300, dtype=np.uint32), 1)
 print(f"libmmd CPU, 1 thread: 300 frames in {sec*1e3:.1f} ms ({sec/300*1e6:.0f} us / frame)")

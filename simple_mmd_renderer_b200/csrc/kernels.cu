@@ -16,6 +16,13 @@ namespace mmdgpu {
 
 using namespace dm;
 
+// Programmatic dependent launch (one-slot objects: the interactive frame loop is three small dependent kernels).  A kernel
+// launched with the attribute may start while its predecessor in the stream still runs; everything the predecessor wrote is
+// only visible after pdl_wait(), so the model's static data is fetched before it and the slot state after it.  Both are
+// no-ops in a launch without the attribute / without a dependent.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // =================================================================================================
 // K1 — keyframe sampling.  One thread per (slot, bone) and (slot, morph).
 // Motion::GetBonePose(name, size_t)  L/motion/motion_impl.inl:255-319
@@ -23,10 +30,21 @@ using namespace dm;
 // MotionPlayer::SeekFrame            L/motion/poser_impl.inl:539-546
 // Poser::ResetPosing (pose part)     L/motion/poser_impl.inl:131-137   (write_untracked = 1)
 // =================================================================================================
-__device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t* __restrict__ a, uint32_t n, uint32_t key) {
-    uint32_t lo = 0, hi = n;  // first index with a[i] > key
+// upper_bound for a key strictly inside (a[0], a[n-1]): four probes around the position a uniform key spacing predicts are
+// loaded together and narrow [lo, hi) before the bisection, which then usually has nothing left to do - the search is a
+// chain of dependent loads (log2 n of them) on the latency-bound interactive path.  Returns the first index whose key is greater (std::upper_bound).
+__device__ __forceinline__ uint32_t upper_bound_guess_u32(const uint32_t* __restrict__ a, uint32_t n, uint32_t key, uint32_t first,
+                                                          uint32_t last) {
+    uint32_t lo = 1, hi = n - 1;   // a[0] <= key < a[n-1] is known
+    const uint32_t g = (uint32_t)(((unsigned long long)(key - first) * (n - 1)) / (last - first));   // 0 .. n-2
+    const uint32_t p0 = g > 0 ? g - 1 : 0, p1 = g, p2 = min(g + 1, n - 1), p3 = min(g + 2, n - 1);
+    const uint32_t v0 = __ldg(a + p0), v1 = __ldg(a + p1), v2 = __ldg(a + p2), v3 = __ldg(a + p3);
+    if (v0 <= key) lo = max(lo, p0 + 1); else hi = min(hi, p0);
+    if (v1 <= key) lo = max(lo, p1 + 1); else hi = min(hi, p1);
+    if (v2 <= key) lo = max(lo, p2 + 1); else hi = min(hi, p2);
+    if (v3 <= key) lo = max(lo, p3 + 1); else hi = min(hi, p3);
     while (lo < hi) {
-        uint32_t mid = (lo + hi) >> 1;
+        const uint32_t mid = (lo + hi) >> 1;
         if (__ldg(a + mid) <= key) lo = mid + 1; else hi = mid;
     }
     return lo;
@@ -40,21 +58,22 @@ struct Bracket { uint32_t use, l, r; float bary; };
 __device__ __forceinline__ Bracket bracket_keys(const uint32_t* __restrict__ kf, uint32_t n, bool time_mode, uint32_t frame,
                                                 double dframe) {
     Bracket b{0xFFFFFFFFu, 0u, 0u, 0.0f};
+    const uint32_t first = __ldg(kf), last = __ldg(kf + n - 1);
     if (!time_mode) {
-        if (kf[0] >= frame) b.use = 0;
-        else if (kf[n - 1] <= frame) b.use = n - 1;
+        if (first >= frame) b.use = 0;
+        else if (last <= frame) b.use = n - 1;
         else {
-            b.r = upper_bound_u32(kf, n, frame);
+            b.r = upper_bound_guess_u32(kf, n, frame, first, last);
             b.l = b.r - 1;
             const uint32_t lf = kf[b.l], rf = kf[b.r];
             if (lf == frame) b.use = b.l;
             else b.bary = (float)(frame - lf) / (float)(rf - lf);
         }
     } else {
-        if ((double)kf[0] >= dframe) b.use = 0;
-        else if ((double)kf[n - 1] <= dframe) b.use = n - 1;
+        if ((double)first >= dframe) b.use = 0;
+        else if ((double)last <= dframe) b.use = n - 1;
         else {
-            b.r = upper_bound_u32(kf, n, (uint32_t)(unsigned long long)dframe);
+            b.r = upper_bound_guess_u32(kf, n, (uint32_t)(unsigned long long)dframe, first, last);
             b.l = b.r - 1;
             const uint32_t lf = kf[b.l], rf = kf[b.r];
             b.bary = (float)((dframe - (double)lf) / (double)(rf - lf));
@@ -136,6 +155,7 @@ __device__ __forceinline__ bool sample_morph(const SampleArgs& SA, const SlotFra
 }
 
 __global__ void __launch_bounds__(128) pose_sample_kernel(DevModel M, DevFrames F, SampleArgs SA) {
+    pdl_trigger();
     const uint32_t slot = blockIdx.y;
     const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
     if (!SA.anims && F.material_images && blockIdx.x == 0) {
@@ -666,17 +686,20 @@ __global__ void __launch_bounds__(kHierCtaThreads) hierarchy_cta_kernel(DevModel
     S.palette = F.palette + (size_t)slot * nb * 3;
     S.pal_ext = F.pal_ext ? F.pal_ext + (size_t)slot * nb * 2 : nullptr;
 
-    // ---- sampled poses of every bone (written by K1 / SetBonePose), the static bone records and the program
-    for (uint32_t b = tid; b < nb; b += nthreads) {
-        s_poseR[b] = F.poseR[(size_t)slot * nb + b];
-        s_poseT[b] = F.poseT[(size_t)slot * nb + b];
-    }
+    // ---- the static bone records and the program (model data: fetched while a predecessor launched with programmatic
+    //      dependent launch may still be running), then the sampled poses of every bone (written by K1 / SetBonePose)
+    pdl_trigger();
     {
         const float4* gb = reinterpret_cast<const float4*>(M.bones);
         for (uint32_t i = tid; i < 3 * nb; i += nthreads) s_bones[i] = __ldg(gb + i);
         for (uint32_t i = tid; i <= M.n_waves; i += nthreads) s_wave_begin[i] = __ldg(M.wave_begin + i);
         const uint32_t n_ops = __ldg(M.wave_begin + M.n_waves);
         for (uint32_t i = tid; i < n_ops; i += nthreads) s_wave_ops[i] = __ldg(M.wave_ops + i);
+    }
+    pdl_wait();
+    for (uint32_t b = tid; b < nb; b += nthreads) {
+        s_poseR[b] = F.poseR[(size_t)slot * nb + b];
+        s_poseT[b] = F.poseT[(size_t)slot * nb + b];
     }
     if (prologue) {
         // ---- morph application-slot rates (poser_impl.inl:329-339), breadth-first over the static DFS tree
@@ -1088,8 +1111,10 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
     auto item_fetch = [&](uint32_t group_slot0, uint32_t src) -> float4 {
         const uint32_t slot = min(group_slot0 + (src >> 30), F.n_slots - 1u);  // a partial last group re-reads its last slot
         const uint32_t idx = src & 0x1FFFFFFFu;
-        if (EXT && (src & 0x20000000u)) return __ldg(F.pal_ext + (size_t)slot * M.nb * 2 + idx);
-        return __ldg(F.palette + (size_t)slot * M.nb * 3 + idx);
+        // (plain loads, not the read-only path: under programmatic dependent launch the hierarchy may still have been
+        // writing these while this kernel was already resident)
+        if (EXT && (src & 0x20000000u)) return F.pal_ext[(size_t)slot * M.nb * 2 + idx];
+        return F.palette[(size_t)slot * M.nb * 3 + idx];
     };
     uint32_t psrc[kPalPrefetch], pdst[kPalPrefetch];
 #pragma unroll
@@ -1099,11 +1124,12 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
         pdst[q] = (i < n_items) ? item_dest(i) : 0u;
     }
 
-    // ---- prologue: first group straight into buffer 0
+    // ---- prologue: first group straight into buffer 0 (slot state: only now does a dependent launch wait for the hierarchy)
+    pdl_wait();
     {
         for (uint32_t i = tid; i < n_items; i += kSkinThreads) pal_base[item_dest(i)] = item_fetch(s0, item_source(i));
         const float4* gr = reinterpret_cast<const float4*>(F.node_rate) + (size_t)(s0 / G) * npad;
-        for (uint32_t i = tid; i < npad; i += kSkinThreads) rate_base[i] = __ldg(gr + i);
+        for (uint32_t i = tid; i < npad; i += kSkinThreads) rate_base[i] = gr[i];
     }
     __syncthreads();
 
@@ -1120,7 +1146,7 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
 #pragma unroll
             for (uint32_t q = 0; q < kPalPrefetch; ++q)
                 if (psrc[q] != 0xFFFFFFFFu) pf[q] = item_fetch(g0 + G, psrc[q]);
-            if (tid < npad) rf = __ldg(gr + tid);
+            if (tid < npad) rf = gr[tid];
         }
         // ---- per storage position: morph gather for the G slots at once, then G skinnings.  vertex_images_[i]
         //      accumulates in application order: img = img + off*rate (poser_impl.inl:340-346).  ent.w = byte
@@ -1241,7 +1267,7 @@ __global__ void __launch_bounds__(kSkinThreads, EXT ? 2 : 3) skin_kernel(DevMode
             for (uint32_t i = tid + kPalPrefetch * kSkinThreads; i < n_items; i += kSkinThreads)
                 npal[item_dest(i)] = item_fetch(g0 + G, item_source(i));
             if (tid < npad) nrt[tid] = rf;
-            for (uint32_t i = tid + kSkinThreads; i < npad; i += kSkinThreads) nrt[i] = __ldg(gr + i);
+            for (uint32_t i = tid + kSkinThreads; i < npad; i += kSkinThreads) nrt[i] = gr[i];
         }
         // ---- hand the staged tiles to the bulk-copy engine (the barrier also orders the palette double buffer)
         if (LAYOUT == MMDGPU_LAYOUT_SOA_POS_NRM) fence_proxy_async_smem();  // staging writes -> visible to the async proxy
@@ -1427,8 +1453,10 @@ __global__ void __launch_bounds__(kSkinThreads, MIN_CTAS) skin_pair_kernel(DevMo
     };
     auto fetch = [&](uint32_t group_slot0, uint32_t pair, uint32_t src, float4& A, float4& B) {
         const uint32_t sa = min(group_slot0 + 2u * pair, F.n_slots - 1u), sb = min(group_slot0 + 2u * pair + 1u, F.n_slots - 1u);
-        A = __ldg(F.palette + (size_t)sa * M.nb * 3 + src);
-        B = __ldg(F.palette + (size_t)sb * M.nb * 3 + src);
+        // (plain loads, not the read-only path: under programmatic dependent launch the hierarchy may still have been
+        // writing these while this kernel was already resident)
+        A = F.palette[(size_t)sa * M.nb * 3 + src];
+        B = F.palette[(size_t)sb * M.nb * 3 + src];
     };
     auto publish = [&](ulonglong2* buf, uint32_t pair, uint32_t q, const float4& A, const float4& B) {
         ulonglong2* cell = buf + (size_t)pair * 2u * pal4 + q;
@@ -1439,7 +1467,8 @@ __global__ void __launch_bounds__(kSkinThreads, MIN_CTAS) skin_pair_kernel(DevMo
     uint32_t my_pair = 0, my_q = 0, my_src = 0xFFFFFFFFu;
     if (tid < n_items) my_src = item_cell(tid, my_pair, my_q);
 
-    // ---- prologue: first group straight into buffer 0
+    // ---- prologue: first group straight into buffer 0 (slot state: only now does a dependent launch wait for the hierarchy)
+    pdl_wait();
     {
         for (uint32_t i = tid; i < n_items; i += kSkinThreads) {
             uint32_t p, q; float4 A, B;
@@ -1448,7 +1477,7 @@ __global__ void __launch_bounds__(kSkinThreads, MIN_CTAS) skin_pair_kernel(DevMo
             publish(pal_base, p, q, A, B);
         }
         const float4* gr = reinterpret_cast<const float4*>(F.node_rate) + (size_t)(s0 / G) * npad;
-        for (uint32_t i = tid; i < npad; i += kSkinThreads) rate_base[i] = __ldg(gr + i);
+        for (uint32_t i = tid; i < npad; i += kSkinThreads) rate_base[i] = gr[i];
     }
     __syncthreads();
 
@@ -1463,7 +1492,7 @@ __global__ void __launch_bounds__(kSkinThreads, MIN_CTAS) skin_pair_kernel(DevMo
         const float4* gr = reinterpret_cast<const float4*>(F.node_rate) + (size_t)(g0 / G + 1) * npad;
         if (has_next) {
             if (my_src != 0xFFFFFFFFu) fetch(g0 + G, my_pair, my_src, pfA, pfB);
-            if (tid < npad) rf = __ldg(gr + tid);
+            if (tid < npad) rf = gr[tid];
         }
 #pragma unroll
         for (int j = 0; j < V; ++j) {
@@ -1550,7 +1579,7 @@ __global__ void __launch_bounds__(kSkinThreads, MIN_CTAS) skin_pair_kernel(DevMo
                 publish(npal, p, q, A, B);
             }
             if (tid < npad) nrt[tid] = rf;
-            for (uint32_t i = tid + kSkinThreads; i < npad; i += kSkinThreads) nrt[i] = __ldg(gr + i);
+            for (uint32_t i = tid + kSkinThreads; i < npad; i += kSkinThreads) nrt[i] = gr[i];
         }
         // ---- hand the staged tiles to the bulk-copy engine (the barrier also orders the palette double buffer)
         if (staged) fence_proxy_async_smem();
@@ -1656,6 +1685,25 @@ cudaError_t launch_pose_sample(cudaStream_t st, const DevModel& M, const DevFram
     return cudaGetLastError();
 }
 
+// One-slot objects (an interactive Poser: sampling -> hierarchy -> skinning, each a few microseconds) launch the hierarchy
+// and the skinning kernel with programmatic stream serialization: the kernel becomes resident and fetches the model's
+// static data while its predecessor still runs, and passes its pdl_wait() the moment that one has finished.
+// MMDGPU_PDL=0 switches it off.
+static bool use_pdl(const DevFrames& F) {
+    static const bool on = [] { const char* e = std::getenv("MMDGPU_PDL"); return !(e && e[0] == '0'); }();
+    return on && F.n_slots == 1;
+}
+template <class... KArgs>
+static cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, KArgs... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 cudaError_t launch_hierarchy(cudaStream_t st, const DevModel& M, const DevFrames& F, uint32_t wave_lo, uint32_t wave_hi,
                              bool prologue) {
     if (F.n_slots == 0) return cudaSuccess;
@@ -1664,9 +1712,9 @@ cudaError_t launch_hierarchy(cudaStream_t st, const DevModel& M, const DevFrames
     if (cta_smem <= kHierCtaSmemLimit && !force_global) {
         // small skeletons: narrower CTAs, so that more slots are resident per SM (a CCD IK solve is one thread)
         const uint32_t threads = M.nb <= 512 ? 128u : kHierCtaThreads;
-        if (M.ik_nested) hierarchy_cta_kernel<true><<<F.n_slots, threads, cta_smem, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u);
-        else hierarchy_cta_kernel<false><<<F.n_slots, threads, cta_smem, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u);
-        return cudaGetLastError();
+        const bool pdl = use_pdl(F);
+        if (M.ik_nested) return launch_kernel(hierarchy_cta_kernel<true>, dim3(F.n_slots), dim3(threads), cta_smem, st, pdl, M, F, wave_lo, wave_hi, prologue ? 1u : 0u);
+        return launch_kernel(hierarchy_cta_kernel<false>, dim3(F.n_slots), dim3(threads), cta_smem, st, pdl, M, F, wave_lo, wave_hi, prologue ? 1u : 0u);
     }
     const uint32_t blocks = (F.n_slots + kHierWarps - 1) / kHierWarps;
     if (M.ik_nested) hierarchy_kernel<true><<<blocks, 32 * kHierWarps, 0, st>>>(M, F, wave_lo, wave_hi, prologue ? 1u : 0u);
@@ -1767,9 +1815,13 @@ cudaError_t launch_skin(cudaStream_t st, const DevModel& M, const DevFrames& F, 
     if (M.extensions) MMDGPU_LAUNCH_SKIN(true, false);
     else if (M.global_palette) MMDGPU_LAUNCH_SKIN(false, true);
     else if (scalar) MMDGPU_LAUNCH_SKIN(false, false);
-    else if (soa) skin_pair_kernel<SOA, 3, true><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks, -0.0f, 1.0f);
-    else if (skin_sokol_staged(M, F)) skin_pair_kernel<I32, 3, true><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks, -0.0f, 1.0f);
-    else skin_pair_kernel<I32, 3, false><<<grid, kSkinThreads, smem, st>>>(M, F, slots_per_cta, n_chunks, -0.0f, 1.0f);
+    else {
+        // (the scalar kernels above read the palette through the read-only path and are never launched programmatically)
+        const bool pdl = use_pdl(F);
+        if (soa) return launch_kernel(skin_pair_kernel<SOA, 3, true>, dim3(grid), dim3(kSkinThreads), smem, st, pdl, M, F, slots_per_cta, n_chunks, -0.0f, 1.0f);
+        if (skin_sokol_staged(M, F)) return launch_kernel(skin_pair_kernel<I32, 3, true>, dim3(grid), dim3(kSkinThreads), smem, st, pdl, M, F, slots_per_cta, n_chunks, -0.0f, 1.0f);
+        return launch_kernel(skin_pair_kernel<I32, 3, false>, dim3(grid), dim3(kSkinThreads), smem, st, pdl, M, F, slots_per_cta, n_chunks, -0.0f, 1.0f);
+    }
 #undef MMDGPU_LAUNCH_SKIN
     return cudaGetLastError();
 }

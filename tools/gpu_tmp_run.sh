@@ -1,4 +1,4 @@
-tag=r2s
+tag=r2t
 line() {
   python -c "
 import sys,json
@@ -8,9 +8,8 @@ for l in sys.stdin:
 " | tee -a gpurun_out/${tag}_ab.txt
 }
 B="timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-also"
-timeout 600 python -m pytest tests/test_gpu_round2.py tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/${tag}_pytest.txt
+timeout 700 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/${tag}_pytest.txt
 timeout 300 python tools/latency_probe.py 2>&1 | tee gpurun_out/${tag}_latency.txt
-for sp in 0 1; do
-  MMDGPU_IK_SPLIT=$sp $B --workload C2 --frames-per-step 128 2>>gpurun_out/${tag}_err.txt | line "IK_SPLIT=$sp C2 x 128"
-  MMDGPU_IK_SPLIT=$sp $B --workload C2 --frames-per-step 256 2>>gpurun_out/${tag}_err.txt | line "IK_SPLIT=$sp C2 x 256"
-done
+timeout 200 python tools/latency_breakdown.py 2>&1 | tee gpurun_out/${tag}_latency_breakdown.txt
+$B 2>>gpurun_out/${tag}_err.txt | line "C3"
+$B --workload C4 2>>gpurun_out/${tag}_err.txt | line "C4"

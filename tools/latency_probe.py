@@ -17,11 +17,13 @@ open(os.path.join(d, "m.vmd"), "wb").write(pmxio.write_vmd(motion))
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 exe = os.path.join(d, "headless_update")
 subprocess.run(["g++", "-std=c++14", "-O2", f"-I{root}/include", f"{root}/examples/headless_update.cc", lib.SO_PATH, "-o", exe], check=True)
-for mode, label in (("0", "pose_image written by the skinning kernel (page-locked host block bound as its output)"),
-                    ("1", "pose_image copied from the device on first access (MMDGPU_POSE_IMAGE_COPY=1)")):
+for mode, pdl, label in (("0", "1", "default: pose_image written by the skinning kernel (page-locked host block bound as its output), programmatic dependent launch"),
+                         ("0", "0", "MMDGPU_PDL=0: ordinary launches"),
+                         ("1", "1", "MMDGPU_POSE_IMAGE_COPY=1: pose_image copied from the device on first access"),
+                         ("1", "0", "MMDGPU_POSE_IMAGE_COPY=1 MMDGPU_PDL=0 (the path of the previous measurement)")):
     for _ in range(3):
         r = subprocess.run([exe, os.path.join(d, "m.pmx"), os.path.join(d, "m.vmd"), "0", "300"], capture_output=True, text=True,
-                           env=dict(os.environ, MMDGPU_POSE_IMAGE_COPY=mode))
+                           env=dict(os.environ, MMDGPU_POSE_IMAGE_COPY=mode, MMDGPU_PDL=pdl))
     print(label + ":\n  " + r.stdout.strip().replace("\n", "\n  "))
 ses = oracle.Reference(model, motion) if oracle.have_reference() else oracle.Restatement(model, motion)
 sec, _ = ses.time_frames(np.arange(300, dtype=np.uint32), 1)

@@ -141,6 +141,7 @@ struct mmdgpu_frames {
     bool main_dirty = true;
     // The vertex output streams are single-buffered: a skinning kernel must not overwrite them while an asynchronous
     // download of the previous update is still reading.  ev_dl follows the last copy issued on the download stream.
+    bool host_bound = false;                      // some vertex output stream is bound to page-locked host memory
     cudaEvent_t ev_deform = nullptr;              // follows the last step-wise mmdgpu_deform
     cudaEvent_t last_skin = nullptr;              // event behind the most recent skinning launch (fused or step-wise)
     cudaEvent_t ev_dl = nullptr;
@@ -1353,7 +1354,7 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_download(mmdgpu_frames_t f, uint32_t slot
     StreamView v{};
     if (mmdgpu_status s = stream_view(f, id, v)) return s;
     if (bytes != v.slot_bytes) return set_err(f->ctx, MMDGPU_ERR_INVALID_ARG, "bytes must equal the size of one slot of the stream");
-    if (bytes) CU(f->ctx, cudaMemcpyAsync(host_dst, v.base + size_t(slot) * v.slot_stride, bytes, cudaMemcpyDefault, f->ctx->stream));
+    if (bytes) CU(f->ctx, cudaMemcpyAsync(host_dst, v.base + size_t(slot) * v.slot_stride, bytes, (f->host_bound ? cudaMemcpyDefault : cudaMemcpyDeviceToHost), f->ctx->stream));
     CU(f->ctx, cudaStreamSynchronize(f->ctx->stream));
     return MMDGPU_OK;
 }
@@ -1373,10 +1374,10 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_download_async(mmdgpu_frames_t f, uint32_
     CU(ctx, cudaStreamWaitEvent(ctx->dl_stream, ctx->dl_event, 0));
     const char* src = v.base + size_t(first_slot) * v.slot_stride;
     if (v.slot_bytes == v.slot_stride || n_slots == 1)   // contiguous: one plain copy
-        CU(ctx, cudaMemcpyAsync(pinned_host_dst, src, bytes, cudaMemcpyDefault, ctx->dl_stream));
+        CU(ctx, cudaMemcpyAsync(pinned_host_dst, src, bytes, (f->host_bound ? cudaMemcpyDefault : cudaMemcpyDeviceToHost), ctx->dl_stream));
     else
         CU(ctx, cudaMemcpy2DAsync(pinned_host_dst, v.slot_bytes, src, v.slot_stride, v.slot_bytes, n_slots,
-                                  cudaMemcpyDefault, ctx->dl_stream));
+                                  (f->host_bound ? cudaMemcpyDefault : cudaMemcpyDeviceToHost), ctx->dl_stream));
     CU(ctx, cudaEventRecord(f->ev_dl, ctx->dl_stream));
     f->dl_pending = f->dl_recorded = true;
     return MMDGPU_OK;
@@ -1399,10 +1400,10 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_download_pair_async(mmdgpu_frames_t f, ui
     CU(ctx, cudaStreamWaitEvent(ctx->dl_stream, ctx->dl_event, 0));
     char* dst = static_cast<char*>(pinned_host_dst);
     if (nrm == pos + plane)   // one-slot object with unpadded planes next to each other: one transfer
-        CU(ctx, cudaMemcpyAsync(dst, pos, bytes, cudaMemcpyDefault, ctx->dl_stream));
+        CU(ctx, cudaMemcpyAsync(dst, pos, bytes, (f->host_bound ? cudaMemcpyDefault : cudaMemcpyDeviceToHost), ctx->dl_stream));
     else {
-        CU(ctx, cudaMemcpyAsync(dst, pos, plane, cudaMemcpyDefault, ctx->dl_stream));
-        CU(ctx, cudaMemcpyAsync(dst + plane, nrm, plane, cudaMemcpyDefault, ctx->dl_stream));
+        CU(ctx, cudaMemcpyAsync(dst, pos, plane, (f->host_bound ? cudaMemcpyDefault : cudaMemcpyDeviceToHost), ctx->dl_stream));
+        CU(ctx, cudaMemcpyAsync(dst + plane, nrm, plane, (f->host_bound ? cudaMemcpyDefault : cudaMemcpyDeviceToHost), ctx->dl_stream));
     }
     CU(ctx, cudaEventRecord(f->ev_dl, ctx->dl_stream));
     f->dl_pending = f->dl_recorded = true;
@@ -1471,6 +1472,7 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_bind_output(mmdgpu_frames_t f, mmdgpu_str
         // page-locked host memory (mmdgpu_host_alloc, cudaHostAlloc, cudaHostRegister): the skinning kernel's stores travel
         // over PCIe while it computes; no separate device-to-host copy
         device_ptr = attr.devicePointer;
+        f->host_bound = true;   // (stays set: it only selects cudaMemcpyDefault for the downloads of this object)
     } else if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged) {
         cudaGetLastError();
         return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "bound output pointer is neither device memory nor page-locked host memory");

@@ -308,6 +308,51 @@ def test_tile_layout_is_a_faithful_permutation(name):
     assert mixed <= 3 * n_tiles
 
 
+@pytest.mark.parametrize("name", ["small", "C2"])
+def test_tile_order_pairs_lanes_on_their_leading_bones(name):
+    """The tile order puts two vertices of one skinning type that agree on their leading bone ids into an aligned lane
+    pair (2k, 2k + 1), and fills 32-lane groups with pairs of one agreement level, so that the skinning kernel's LDS.128
+    of bone k reads ONE palette cell per lane pair (2 shared-memory wavefronts instead of 4).  Checked here: the share of
+    (group, type, bone position) load sets in which every lane pair agrees, and that it is what the order was built for
+    (the same model ordered without pairing has almost none)."""
+    import os, subprocess, sys, json
+    cfg, model, _ = synth_case(name)
+
+    def fast_share(plan):
+        TILE, V = 512, 4
+        WARPS = TILE // V // 32
+        st = plan[capi.PLAN_TILE_TYPE].astype(np.int64)
+        n_tiles = st.size // TILE
+        j, w, l = np.meshgrid(np.arange(V), np.arange(WARPS), np.arange(32), indexing="ij")
+        pos = ((w * 32 + l) * V + j).reshape(V * WARPS, 32)
+        ty = st.reshape(n_tiles, TILE)[:, pos]
+        lid = plan[capi.PLAN_TILE_LOCAL_ID].reshape(-1, 4).astype(np.int64).reshape(n_tiles, TILE, 4)[:, pos]
+        fast = total = 0
+        for t, keep in {0: 1, 1: 2, 2: 4}.items():
+            m = ty == t
+            present = m.any(axis=2)
+            same_type = m[:, :, 0::2] == m[:, :, 1::2]
+            for k in range(keep):
+                agree = (lid[:, :, 0::2, k] == lid[:, :, 1::2, k]) | ~m[:, :, 0::2]
+                fast += int(((agree & same_type).all(axis=2) & present).sum())
+                total += int(present.sum())
+        return fast / max(1, total)
+
+    share = fast_share(plan_arrays(model))
+    assert share > 0.45, share
+    # the same plan without pairing, in a fresh process (the knob is read once per process)
+    code = ("import sys, json; sys.path.insert(0, %r); sys.path.insert(0, %r);"
+            "from conftest import synth_case; from simple_mmd_renderer_b200.poser import plan_arrays;"
+            "from simple_mmd_renderer_b200 import capi; import numpy as np;"
+            "cfg, model, _ = synth_case(%r); p = plan_arrays(model);"
+            "print(json.dumps({'orig': p[capi.PLAN_TILE_ORIG].tolist()}))") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                                 os.path.dirname(os.path.abspath(__file__)), name)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True,
+                         env=dict(os.environ, MMDGPU_TILE_PAIRING="0")).stdout
+    orig_unpaired = np.asarray(json.loads(out.strip().splitlines()[-1])["orig"])
+    assert not np.array_equal(orig_unpaired, plan_arrays(model)[capi.PLAN_TILE_ORIG]), "the pairing knob must change the order"
+
+
 def test_material_morph_plan_is_grouped_by_material_in_application_order():
     """Extension plan: entries under each material appear in application-slot (DFS) order, an "every material" entry
     is repeated under each material, and values / methods are carried over unchanged."""

@@ -1,15 +1,18 @@
-tag=r2t
-line() {
-  python -c "
-import sys,json
-for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); print('$1'.ljust(60), 'value %.2f G  ms/step %.4f  skin %.4f ms' % (d['value']/1e9, d['ms_per_step'], d['kernel_ms']['skin_per_launch_in_step']))
-" | tee -a gpurun_out/${tag}_ab.txt
-}
-B="timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-also"
-timeout 700 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/${tag}_pytest.txt
-timeout 300 python tools/latency_probe.py 2>&1 | tee gpurun_out/${tag}_latency.txt
-timeout 200 python tools/latency_breakdown.py 2>&1 | tee gpurun_out/${tag}_latency_breakdown.txt
-$B 2>>gpurun_out/${tag}_err.txt | line "C3"
-$B --workload C4 2>>gpurun_out/${tag}_err.txt | line "C4"
+tag=r2u
+mkdir -p gpurun_out
+timeout 900 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
+timeout 600 python bench.py --impl reference > gpurun_out/${tag}_ref.json 2> gpurun_out/${tag}_ref.err
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-also --layout sokol32 > gpurun_out/${tag}_bench_sokol32.json 2>> gpurun_out/${tag}_bench.err
+bash tools/ncu_capture.sh ${tag} skin_pair
+python - <<PY
+import json
+for f in ("bench", "bench_sokol32", "ref"):
+    try:
+        d = json.loads(open("gpurun_out/${tag}_%s.json" % f).read().strip().splitlines()[-1])
+        print(f, "value %.3f G" % (d["value"] / 1e9), "e2e", d.get("e2e", {}).get("value"), "frac", (d.get("roofline") or {}).get("frac"))
+        for k, v in (d.get("also") or {}).items():
+            print("   ", k, "%.2f G" % (v["value"] / 1e9), v.get("ms_per_step"))
+    except Exception as e:
+        print(f, "failed:", e)
+PY
+tail -3 gpurun_out/${tag}_bench.err

@@ -89,12 +89,15 @@ struct SampleArgs {
     uint32_t write_untracked;  // also write identity / zero for bones and morphs the clip does not animate (ResetPosing + SeekFrame)
     uint32_t range_mode, frame_stride, time_mode, by_value, frame0;
     double time0;
+    uint32_t n_inline;         // > 0: frame ids come from `inline_ids` instead of F.frame_id
+    uint32_t inline_ids[kInlineFrameIds];
 };
 struct SlotFrame { uint32_t inst, frame; double dframe; };
 __device__ __forceinline__ SlotFrame frame_of_slot(const DevFrames& F, const SampleArgs& A, uint32_t slot) {
     SlotFrame s{slot / F.n_frames, 0u, 0.0};
     if (A.time_mode) s.dframe = (A.by_value ? A.time0 : F.time_s[slot]) * 30.0;
     else if (A.by_value) s.frame = A.frame0 + (A.range_mode ? (slot - s.inst * F.n_frames) * A.frame_stride : 0u);
+    else if (A.n_inline) s.frame = A.range_mode ? (A.inline_ids[s.inst] + (slot - s.inst * F.n_frames) * A.frame_stride) : A.inline_ids[slot];
     else s.frame = A.range_mode ? (F.frame_id[s.inst] + (slot - s.inst * F.n_frames) * A.frame_stride) : F.frame_id[slot];
     return s;
 }
@@ -1674,6 +1677,8 @@ static SampleArgs make_sample_args(const SampleSpec& sp) {
     a.by_value = (sp.frame_by_value || sp.time_by_value) ? 1u : 0u;
     a.frame0 = sp.frame_by_value ? *sp.frame_by_value : 0u;
     a.time0 = sp.time_by_value ? *sp.time_by_value : 0.0;
+    a.n_inline = (sp.frame_ids_inline && sp.n_inline <= kInlineFrameIds) ? sp.n_inline : 0u;
+    for (uint32_t i = 0; i < a.n_inline; ++i) a.inline_ids[i] = sp.frame_ids_inline[i];
     return a;
 }
 

@@ -9,7 +9,11 @@ namespace mmdgpu {
 
 // What to sample: anims == nullptr writes identity / zero (Poser::ResetPosing's pose part); write_untracked: also write
 // identity / zero for items the clip does not animate; frame_by_value / time_by_value: one frame id (first frame of a
-// one-instance range) or one time handed over as a kernel argument instead of through F.frame_id / F.time_s.
+// one-instance range) or one time handed over as a kernel argument instead of through F.frame_id / F.time_s;
+// frame_ids_inline / n_inline: up to kInlineFrameIds frame ids (per slot, or first frames per instance in range mode) handed
+// over the same way - a small crowd's step is tens of microseconds of device work, and the host-to-device copy of its
+// ids from pageable memory is the most expensive driver call of the update.
+constexpr uint32_t kInlineFrameIds = 64;
 struct SampleSpec {
     const DevAnim* anims = nullptr;
     bool write_untracked = false, range_mode = false;
@@ -17,6 +21,8 @@ struct SampleSpec {
     bool time_mode = false;
     const uint32_t* frame_by_value = nullptr;
     const double* time_by_value = nullptr;
+    const uint32_t* frame_ids_inline = nullptr;
+    uint32_t n_inline = 0;
 };
 // K1: keyframe sampling for every (slot, bone) and (slot, morph).
 cudaError_t launch_pose_sample(cudaStream_t st, const DevModel& M, const DevFrames& F, const SampleSpec& spec);

@@ -132,6 +132,7 @@ struct mmdgpu_frames {
         DevAnim* d_anims = nullptr;
         std::vector<uint64_t> bound;            // uid of the clip whose DevAnim each entry of d_anims currently holds
     } set[kStateCopies];
+    int n_copies = kStateCopies;                  // copies this object allocates and rotates: pre streams of its model + 1
     int cur = 0;                                  // copy the step-wise entry points and the downloads use
     int update_turn = 0;                          // which of the pre streams the last fused update used
     cudaEvent_t ev_pre[kStateCopies] = {};    // hierarchy of the update that wrote copy i has finished
@@ -477,8 +478,10 @@ mmdgpu_status do_seek(mmdgpu_frames* f, const mmdgpu_animation_t* per_instance, 
     if (mmdgpu_status s = bind_anims(f, per_instance, st)) return s;
     const uint32_t n = range ? f->dev.n_instances : f->dev.n_slots;
     // one frame id travels as a kernel argument: no host-to-device copy on the interactive / single-clip bake path
-    const bool by_value = n == 1;
-    if (!by_value) CU(ctx, cudaMemcpyAsync(f->dev.frame_id, frames, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+    // ... and up to kInlineFrameIds of them too (a small crowd): the copy from pageable memory costs more than the launch
+    static const bool allow_inline = [] { const char* e = std::getenv("MMDGPU_INLINE_IDS"); return !(e && e[0] == '0'); }();   // A/B knob
+    const bool by_value = n == 1, inline_ids = allow_inline && !by_value && n <= kInlineFrameIds;
+    if (!by_value && !inline_ids) CU(ctx, cudaMemcpyAsync(f->dev.frame_id, frames, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
     f->range_mode = range;
     f->frame_stride = stride;
     SampleSpec sp;
@@ -487,6 +490,7 @@ mmdgpu_status do_seek(mmdgpu_frames* f, const mmdgpu_animation_t* per_instance, 
     sp.range_mode = range;
     sp.frame_stride = stride;
     sp.frame_by_value = by_value ? frames : nullptr;
+    if (inline_ids) { sp.frame_ids_inline = frames; sp.n_inline = n; }
     {
         Timed t(ctx, MMDGPU_KERNEL_POSE_SAMPLE, st);
         CU(ctx, launch_pose_sample(st, f->model->dev, f->dev, sp));
@@ -1063,7 +1067,8 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_create(mmdgpu_context_t ctx, mmdgpu_model
     const size_t ns = size_t(n_instances) * n_frames;
     F.n_slots = uint32_t(ns); F.n_instances = n_instances; F.n_frames = n_frames;
     cudaStream_t st = ctx->stream;
-    for (int i = 0; i < kStateCopies; ++i) {
+    f->n_copies = (model->plan.plan.iks.empty() ? ctx->n_pre_plain : ctx->n_pre_ik) + 1;
+    for (int i = 0; i < f->n_copies; ++i) {
         mmdgpu_frames::StateSet& x = f->set[i];
         CU(ctx, dalloc(f->mem, &x.poseR, ns * M.nb, false, st));
         CU(ctx, dalloc(f->mem, &x.poseT, ns * M.nb, false, st));
@@ -1108,7 +1113,7 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_create(mmdgpu_context_t ctx, mmdgpu_model
     f->own_pos = F.out_pos; f->own_nrm = F.out_nrm; f->own_inter = F.out_inter; f->own_uv = F.out_uv;
     f->slots_per_cta = choose_slots_per_cta(M.n_tiles, F.n_slots, ctx->sm_count);
     // Poser::Poser ends with ResetPosing() (poser_impl.inl:125-127): a fresh object holds identity poses (both copies).
-    for (int i = kStateCopies - 1; i >= 0; --i) {
+    for (int i = f->n_copies - 1; i >= 0; --i) {
         f->select(i);
         Timed t(ctx, MMDGPU_KERNEL_POSE_SAMPLE);
         SampleSpec reset;
@@ -1299,8 +1304,8 @@ static mmdgpu_status update_common(mmdgpu_frames_t f, const mmdgpu_animation_t* 
     if (!frames) return set_err(ctx, MMDGPU_ERR_INVALID_ARG, "frame id array is NULL");
     if (mmdgpu_status s = check_anims(f, per_instance)) return s;
     const bool has_ik = !f->model->plan.plan.iks.empty();
-    const int n_pre = has_ik ? ctx->n_pre_ik : ctx->n_pre_plain;
-    const int next = (f->cur + 1) % (n_pre + 1);
+    const int n_pre = f->n_copies - 1;
+    const int next = (f->cur + 1) % f->n_copies;
     f->update_turn = (f->update_turn + 1) % n_pre;
     cudaStream_t pre = has_ik ? ctx->pre_stream_hi[f->update_turn] : ctx->pre_stream[f->update_turn];
     if (f->skin_recorded[next]) CU(ctx, cudaStreamWaitEvent(pre, f->ev_skin[next], 0));

@@ -1,18 +1,12 @@
-tag=r2u
-mkdir -p gpurun_out
-timeout 900 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
-timeout 600 python bench.py --impl reference > gpurun_out/${tag}_ref.json 2> gpurun_out/${tag}_ref.err
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-also --layout sokol32 > gpurun_out/${tag}_bench_sokol32.json 2>> gpurun_out/${tag}_bench.err
-bash tools/ncu_capture.sh ${tag} skin_pair
-python - <<PY
+tag=r2x
+timeout 700 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/${tag}_pytest.txt
+for v in 0 1 0 1; do
+MMDGPU_INLINE_IDS=$v timeout 300 python bench.py --workload C4 --instances 64 --steps 200 --warmup 20 --no-cpu-baseline --no-e2e --no-also > gpurun_out/${tag}_c4_64.json 2>gpurun_out/${tag}_err.txt
+python - <<PY | tee -a gpurun_out/${tag}_ab.txt
 import json
-for f in ("bench", "bench_sokol32", "ref"):
-    try:
-        d = json.loads(open("gpurun_out/${tag}_%s.json" % f).read().strip().splitlines()[-1])
-        print(f, "value %.3f G" % (d["value"] / 1e9), "e2e", d.get("e2e", {}).get("value"), "frac", (d.get("roofline") or {}).get("frac"))
-        for k, v in (d.get("also") or {}).items():
-            print("   ", k, "%.2f G" % (v["value"] / 1e9), v.get("ms_per_step"))
-    except Exception as e:
-        print(f, "failed:", e)
+d=json.loads(open("gpurun_out/${tag}_c4_64.json").read().strip().splitlines()[-1])
+print("INLINE_IDS=$v  C4 x 64 instances: %.1f G  %.1f us/step" % (d["value"]/1e9, d["ms_per_step"]*1e3))
 PY
-tail -3 gpurun_out/${tag}_bench.err
+done
+timeout 600 python tools/gpu_fuzz.py 3000 300 crowd 2>&1 | tail -2 | tee gpurun_out/${tag}_fuzz_crowd.txt
+timeout 600 python tools/gpu_fuzz.py 3000 200 motion 2>&1 | tail -2 | tee gpurun_out/${tag}_fuzz_motion.txt

@@ -220,6 +220,17 @@ constexpr uint32_t kMaxStagedTileBones = 256;
 // How many consecutive slots one CTA walks for its tile (a multiple of the slot group).  Long runs amortise the
 // per-item prologue (static streams, first palette); enough items must remain to fill the machine.  Measured on
 // B200 (profiles/r01_experiments.md): 64-slot runs are best whenever they still leave >= ~1.5 waves of work items.
+// Slot strides of the library-owned output planes: exactly nv records, rounded up to 16 bytes (bulk copies).
+// MMDGPU_PADDED_SLOTS=1 (A/B knob): slots a whole number of 512-vertex tiles apart, as in round 1.
+inline bool padded_slots() {
+    static const bool on = [] { const char* e = std::getenv("MMDGPU_PADDED_SLOTS"); return e && e[0] == '1'; }();
+    return on;
+}
+inline size_t tile_pad(uint32_t nv) { return (size_t(nv) + kTileVerts - 1) / kTileVerts * kTileVerts; }
+inline size_t own_plane_stride(uint32_t nv) { return padded_slots() ? tile_pad(nv) * 3 : (size_t(nv) * 3 + 3) / 4 * 4; }   // floats
+inline size_t own_inter_stride(uint32_t nv) { return padded_slots() ? tile_pad(nv) * 2 : size_t(nv) * 2; }                // float4
+inline size_t own_uv_stride(uint32_t nv) { return padded_slots() ? tile_pad(nv) : (size_t(nv) + 1) / 2 * 2; }             // float2
+
 uint32_t choose_slots_per_cta(uint32_t tiles, uint32_t n_slots, int sm_count) {
     if (tiles == 0 || n_slots == 0) return kSlotGroup;
     if (const char* env = std::getenv("MMDGPU_SLOTS_PER_CTA")) {  // tuning knob for experiments
@@ -1100,16 +1111,17 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_create(mmdgpu_context_t ctx, mmdgpu_model
         // one allocation, position planes then normal planes: a one-slot object (an interactive Poser) can hand both to the
         // host with a single copy (mmdgpu_frames_download_pair_async)
         CU(ctx, dalloc(f->mem, &F.out_pos, 2 * ns * M.nv_pad * 3, false, st));
-        // (the skinning kernel stores exactly nv vertices per slot, so a single slot's normals may start right behind its
-        // nv positions when that keeps them 16-byte aligned for the bulk copies)
-        F.out_nrm = F.out_pos + ((ns == 1 && M.nv % 4 == 0) ? size_t(M.nv) * 3 : ns * M.nv_pad * 3);
+        // (the skinning kernel stores exactly nv vertices per slot, so slots - and the normal planes behind the position
+        // planes - follow each other at the next 16-byte boundary: for nv % 4 == 0 a stream of all slots is one contiguous
+        // block and leaves in a plain 1-D copy instead of a pitched one)
+        F.out_nrm = F.out_pos + ns * own_plane_stride(M.nv);
         if (M.extensions) CU(ctx, dalloc(f->mem, &F.out_uv, ns * M.nv_pad, false, st));
     } else {
         CU(ctx, dalloc(f->mem, &F.out_inter, ns * M.nv_pad * 2, false, st));
     }
-    F.pos_stride = F.nrm_stride = size_t(M.nv_pad) * 3;  // floats
-    F.inter_stride = size_t(M.nv_pad) * 2;               // float4
-    F.uv_stride = size_t(M.nv_pad);                      // float2
+    F.pos_stride = F.nrm_stride = own_plane_stride(M.nv);  // floats
+    F.inter_stride = own_inter_stride(M.nv);               // float4
+    F.uv_stride = own_uv_stride(M.nv);                     // float2
     f->own_pos = F.out_pos; f->own_nrm = F.out_nrm; f->own_inter = F.out_inter; f->own_uv = F.out_uv;
     f->slots_per_cta = choose_slots_per_cta(M.n_tiles, F.n_slots, ctx->sm_count);
     // Poser::Poser ends with ResetPosing() (poser_impl.inl:125-127): a fresh object holds identity poses (both copies).
@@ -1461,10 +1473,10 @@ MMDGPU_API mmdgpu_status mmdgpu_frames_bind_output(mmdgpu_frames_t f, mmdgpu_str
     f->main_dirty = true;
     DevFrames& F = f->dev;
     if (!device_ptr) {  // back to the library-owned buffer
-        if (id == MMDGPU_STREAM_POSITION) { F.out_pos = f->own_pos; F.pos_stride = size_t(M.nv_pad) * 3; }
-        else if (id == MMDGPU_STREAM_NORMAL) { F.out_nrm = f->own_nrm; F.nrm_stride = size_t(M.nv_pad) * 3; }
-        else if (id == MMDGPU_STREAM_INTERLEAVED) { F.out_inter = f->own_inter; F.inter_stride = size_t(M.nv_pad) * 2; }
-        else { F.out_uv = f->own_uv; F.uv_stride = size_t(M.nv_pad); }
+        if (id == MMDGPU_STREAM_POSITION) { F.out_pos = f->own_pos; F.pos_stride = own_plane_stride(M.nv); }
+        else if (id == MMDGPU_STREAM_NORMAL) { F.out_nrm = f->own_nrm; F.nrm_stride = own_plane_stride(M.nv); }
+        else if (id == MMDGPU_STREAM_INTERLEAVED) { F.out_inter = f->own_inter; F.inter_stride = own_inter_stride(M.nv); }
+        else { F.out_uv = f->own_uv; F.uv_stride = own_uv_stride(M.nv); }
         return MMDGPU_OK;
     }
     if (reinterpret_cast<uintptr_t>(device_ptr) % align || slot_stride_bytes % align)

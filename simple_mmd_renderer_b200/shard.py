@@ -59,7 +59,7 @@ class DeviceView:
 
 def frames_as_tensor(frames, stream_id: int, n_slots: int | None = None):
     """torch tensor [n_slots, nv, 3] (SoA streams) or [n_slots, nv, 8] (interleaved) over the frames object's
-    device output; slots are nv_pad apart, so the view is strided."""
+    device output (slot stride as reported by mmdgpu_frames_device_ptr)."""
     import torch
     from . import capi
     ptr, stride = frames.device_ptr(stream_id)

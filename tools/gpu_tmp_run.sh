@@ -1,10 +1,13 @@
-tag=r3a
-timeout 700 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/${tag}_pytest.txt
-for v in 1 0 1 0; do
-MMDGPU_PADDED_SLOTS=$v timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-also > gpurun_out/${tag}_b.json 2>gpurun_out/${tag}_err.txt
-python - <<PY | tee -a gpurun_out/${tag}_ab.txt
+tag=r3b_n8
+N=8
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port"
+timeout 900 $TR 29514 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/${tag}_bench.json 2>gpurun_out/${tag}_bench.err
+python - <<PY
 import json
-d=json.loads(open("gpurun_out/${tag}_b.json").read().strip().splitlines()[-1]); e=d["e2e"]
-print("PADDED_SLOTS=$v  value %.1f G  e2e %.3f G  %.2f ms/step  d2h %.1f GB/s  ceiling %.1f  frac %.3f" % (d["value"]/1e9, e["value"]/1e9, e["ms_per_step"], e["d2h_gbs_per_gpu"], e["d2h_ceiling_gbs_per_gpu"], e["frac_of_d2h_ceiling"]))
+d = json.loads([l for l in open("gpurun_out/${tag}_bench.json").read().strip().splitlines() if l.startswith("{")][-1])
+print("value %.1f G" % (d["value"] / 1e9), "e2e %.3f G" % (d["e2e"]["value"]/1e9), "frac_ceiling %.3f" % d["e2e"]["frac_of_d2h_ceiling"], "frac", d["roofline"]["frac"])
+for k, v in (d.get("also") or {}).items():
+    print("   ", k, "%.2f G" % (v["value"] / 1e9), v.get("ms_per_step"))
+c5 = d["also"]["C5"]; print(json.dumps(c5.get("gather"))[:400]); print(json.dumps(c5.get("p2p_fused"))[:300])
 PY
-done
+tail -3 gpurun_out/${tag}_bench.err

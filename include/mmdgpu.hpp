@@ -293,6 +293,13 @@ private:
         Flush();
         if (image_valid_) return;
         if (host_bound_) {
+            // still our binding?  (a caller may have re-bound the planes through frames(); then pose_image is a copy again)
+            void *p = nullptr, *n = nullptr;
+            if (mmdgpu_frames_device_ptr(frames_, MMDGPU_STREAM_POSITION, &p, nullptr) != MMDGPU_OK || p != pose_image.coordinates.host_ ||
+                mmdgpu_frames_device_ptr(frames_, MMDGPU_STREAM_NORMAL, &n, nullptr) != MMDGPU_OK || n != pose_image.normals.host_)
+                host_bound_ = false;
+        }
+        if (host_bound_) {
             check(mmdgpu_frames_wait_skinning(frames_), "mmdgpu_frames_wait_skinning");   // the kernel wrote pose_image itself
         } else if (layout_ == MMDGPU_LAYOUT_SOA_POS_NRM) {
             const size_t bytes = model_.GetVertexNum() * sizeof(Vector3f);

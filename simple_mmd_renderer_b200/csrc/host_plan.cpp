@@ -52,7 +52,8 @@ bool bezier_table(const int8_t c[4], float table[32]) {
 }
 
 // --------------------------------------------------------------------------------------------------
-// Second step of the tile order (the first is the stable sort by (skinning type, morph entry count, PMX index)).
+// Round 1's tile order, kept behind MMDGPU_TILE_PAIRING=0 for A/B runs (pair_tile_order below is the default): second step
+// after the stable sort by (skinning type, morph entry count, PMX index).
 //
 // The skinning kernel scatters a group's 32 results into a shared-memory staging tile at 12 bytes x PMX index, so two
 // lanes of one group whose indices are congruent mod 32 hit the same banks (3 is coprime to 32): a group costs as many
@@ -150,9 +151,9 @@ void refine_tile_order(std::vector<uint32_t>& order, const TypeOf& type_of, cons
         }
         if (!improved) break;
     }
-    // inside a group: by (type, PMX index) again, so that the layout does not depend on the order of the swaps.  (Sorting by
-    // bone ids instead changes nothing: an LDS.128 takes its 2-wavefront path only when EVERY aligned lane pair of the warp
-    // reads one cell, measured in profiles/r02_smem_patterns.txt and on the kernel in profiles/r02_experiments.md.)
+    // inside a group: by (type, PMX index) again, so that the layout does not depend on the order of the swaps.  (Merely
+    // sorting the lanes by bone ids changes nothing: an LDS.128 takes its 2-wavefront path only when EVERY aligned lane pair
+    // of the warp reads one cell - profiles/r02_smem_patterns.txt - which is what pair_tile_order arranges.)
     for (uint32_t g = 0; g < G; ++g)
         std::sort(order.begin() + g * 32, order.begin() + g * 32 + 32, [&](uint32_t x, uint32_t y) {
             return ty[x] != ty[y] ? ty[x] < ty[y] : x < y;
